@@ -1,0 +1,650 @@
+/*
+ * oracle/tm_oracle.c -- CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT (see tm_oracle.h).
+ *
+ * Plain C restatement of the reference's Dornic lattice step.  Compile with
+ * -ffp-contract=off (oracle/Makefile does): every fused multiply-add below is an explicit
+ * fma(), everything else rounds once per operation, so the result is a pure function of the
+ * inputs on any IEEE-754 machine.
+ *
+ * Citation shorthands are defined in tm_oracle.h (P/, R/, F/, LS).
+ */
+#include "tm_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ================================================================================== */
+/* 1. Elementary functions of the sampler spec (DESIGN.md "Sampler spec").           */
+/*    Only +,-,*,/,sqrt,fma and integer bit operations: bit-reproducible on CPU/GPU.  */
+/* ================================================================================== */
+
+static inline uint64_t d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
+static inline double   u2d(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
+
+/* Natural log for finite x > 0 (subnormals excluded by construction of the callers).
+ * Argument reduction x = 2^k m, m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = f/(2+f), f = m-1,
+ * with the classical degree-14 odd minimax polynomial (Sun fdlibm e_log.c coefficients).
+ * Replaces std::log at LS:1832 (polar normal), LS:1344/1382 (-log(1-u)), LS:2372 (gamma test). */
+double tmo_log(double x)
+{
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    static const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                        Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                        Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                        Lg7 = 1.479819860511658591e-01;
+    if (!(x > 0.0)) return (x == 0.0) ? -INFINITY : NAN;
+    if (x == INFINITY) return x;
+    uint64_t b = d2u(x);
+    int k = (int)(b >> 52) - 1023;
+    uint64_t mant = b & 0x000FFFFFFFFFFFFFull;
+    if (mant > 0x6A09E667F3BCCull) { /* m > sqrt(2): halve it */
+        b = mant | 0x3FE0000000000000ull; k += 1;
+    } else {
+        b = mant | 0x3FF0000000000000ull;
+    }
+    double m = u2d(b);
+    double f = m - 1.0;
+    double dk = (double)k;
+    double s = f / (2.0 + f);
+    double z = s * s;
+    double w = z * z;
+    double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
+    double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
+    double R = t2 + t1;
+    double hfsq = 0.5 * f * f;
+    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f);
+}
+
+/* exp(x): k = rint(x log2 e), r = x - k ln2 (two-part), degree-13 Taylor in r, scaled by 2^k in
+ * two exact-then-rounded steps.  Replaces std::exp at LS:1295 (Poisson threshold e^-mean),
+ * LS:1288-1290 (Devroye constants) and the pow() of LS:2384 (via exp(p log u)). */
+double tmo_exp(double x)
+{
+    static const double LOG2E = 1.44269504088896338700e+00;
+    static const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    if (x != x) return x;
+    if (x > 709.782712893384) return INFINITY;
+    if (x < -745.2) return 0.0;
+    double kf = rint(x * LOG2E);
+    double r = fma(kf, -ln2_hi, x);
+    r = fma(kf, -ln2_lo, r);
+    double q = 1.0 / 6227020800.0;          /* 1/13! */
+    q = fma(q, r, 1.0 / 479001600.0);       /* 1/12! */
+    q = fma(q, r, 1.0 / 39916800.0);
+    q = fma(q, r, 1.0 / 3628800.0);
+    q = fma(q, r, 1.0 / 362880.0);
+    q = fma(q, r, 1.0 / 40320.0);
+    q = fma(q, r, 1.0 / 5040.0);
+    q = fma(q, r, 1.0 / 720.0);
+    q = fma(q, r, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    double y = 1.0 + fma(r * r, q, r);
+    int k = (int)kf;
+    int k1 = k / 2, k2 = k - k1;
+    y *= u2d((uint64_t)(k1 + 1023) << 52);
+    y *= u2d((uint64_t)(k2 + 1023) << 52);
+    return y;
+}
+
+/* log Gamma(k) for integer-valued k >= 1 (the only arguments LS:1280 and LS:1388 ever pass:
+ * floor(mean)+1 and x+m+1 with x integer-valued).  Exact table of log((k-1)!) rounded to double
+ * for k <= 40, Stirling series beyond. */
+static const double TMO_LOGFACT[40] = {
+#include "tm_logfact_table.inc"
+};
+
+double tmo_lgamma_int(double k)
+{
+    if (!(k >= 1.0)) return NAN;
+    if (k <= 40.0) return TMO_LOGFACT[(int)k - 1];
+    static const double HALF_LOG_2PI = 0.91893853320467274178;
+    double ik = 1.0 / k, ik2 = ik * ik;
+    double ser = ik * fma(ik2, fma(ik2, fma(ik2, -1.0 / 1680.0, 1.0 / 1260.0), -1.0 / 360.0), 1.0 / 12.0);
+    return (fma(k - 0.5, tmo_log(k), -k) + HALF_LOG_2PI) + ser;
+}
+
+/* Philox4x32-10 (Salmon et al., SC'11), the counter-based generator that replaces
+ * std::mt19937_64 (P/:975, R/:3513) in the product. */
+void tmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* 52-bit uniform in [0,1): top 52 bits of w as the mantissa of a double in [1,2), minus 1. */
+double tmo_u52_from_bits(uint64_t w)
+{
+    return u2d(0x3FF0000000000000ull | (w >> 12)) - 1.0;
+}
+
+/* ================================================================================== */
+/* 2. Uniform streams                                                                 */
+/* ================================================================================== */
+
+typedef struct {
+    tmo_rng *g;
+    uint64_t cell;     /* REPLAY / PHILOX */
+    uint64_t k;        /* draw index within the cell */
+    double second;     /* PHILOX: second uniform of the current block */
+} cstream;
+
+static void cs_begin_cell(cstream *s, tmo_rng *g, uint64_t cell)
+{
+    s->g = g; s->cell = cell; s->k = 0; s->second = 0.0;
+}
+
+static double next_u(cstream *s)
+{
+    tmo_rng *g = s->g;
+    g->draws++;
+    switch (g->kind) {
+    case TMO_SRC_SEQ:
+        if (g->pos < g->n_u) return g->u[g->pos++];
+        g->overflow++; return 0.75;
+    case TMO_SRC_REPLAY: {
+        uint64_t k = s->k++;
+        if (k < g->stride && s->cell * g->stride + k < g->n_u) return g->u[s->cell * g->stride + k];
+        g->overflow++; return 0.75;
+    }
+    default: { /* TMO_SRC_PHILOX: block b = k/2 yields uniforms 2b (words 0,1) and 2b+1 (words 2,3) */
+        uint64_t k = s->k++;
+        if (k & 1) return s->second;
+        uint32_t ctr[4] = { (uint32_t)s->cell, g->trial, g->step, (uint32_t)(k >> 1) };
+        uint32_t key[2] = { (uint32_t)g->seed, (uint32_t)(g->seed >> 32) };
+        uint32_t o[4];
+        tmo_philox4x32_10(ctr, key, o);
+        s->second = tmo_u52_from_bits(((uint64_t)o[3] << 32) | o[2]);
+        return tmo_u52_from_bits(((uint64_t)o[1] << 32) | o[0]);
+    }
+    }
+}
+
+/* ================================================================================== */
+/* 3. Samplers: restatement of libstdc++ 13 (LS)                                      */
+/* ================================================================================== */
+
+typedef struct { int saved_available; double saved; } normal_state;
+
+/* Spec addition (not in LS): every rejection loop is bounded, so that a replay buffer that
+ * runs dry -- or a GPU thread fed garbage -- cannot spin forever.  The bounds are never reached
+ * with genuine uniforms (polar: 0.215^64; Devroye/Marsaglia-Tsang accept with p > 0.5). */
+#define TM_MAX_REJECT 64
+#define TM_MAX_PRODUCT 4096
+
+/* std::normal_distribution<double>(0,1)::operator(), Marsaglia polar with one cached
+ * variate: LS:1811-1848. */
+static double normal01(cstream *s, normal_state *st)
+{
+    if (st->saved_available) {
+        st->saved_available = 0;
+        return st->saved;
+    }
+    double x, y, r2;
+    int it = 0;
+    do {
+        x = 2.0 * next_u(s) - 1.0;
+        y = 2.0 * next_u(s) - 1.0;
+        r2 = fma(x, x, y * y);
+    } while ((r2 > 1.0 || r2 == 0.0) && ++it < TM_MAX_REJECT);
+    if (r2 > 1.0 || r2 == 0.0) { s->g->overflow++; r2 = 0.5; x = 0.5; y = 0.5; }
+    double mult = sqrt(-2.0 * tmo_log(r2) / r2);
+    st->saved = x * mult;
+    st->saved_available = 1;
+    return y * mult;
+}
+
+
+/* std::poisson_distribution<int>(mean)::operator() for a freshly constructed object
+ * (the reference constructs one per cell: P/:1055, R/:3781).  Parameter set-up LS:1267-1296,
+ * draw LS:1310-1400: Devroye's rejection for mean >= 12, product of uniforms below. */
+static long poisson_draw(cstream *s, double mean)
+{
+    if (mean >= 12.0) {
+        normal_state nd = {0, 0.0}; /* the distribution's own _M_nd, fresh (LS: poisson ctor) */
+        /* _M_initialize, LS:1276-1291 */
+        const double m = floor(mean);
+        const double lm_thr = tmo_log(mean);
+        const double lfm = tmo_lgamma_int(m + 1.0);
+        const double sm = sqrt(m);
+        const double pi_4 = 0.7853981633974483096156608458198757;
+        const double dxx = sqrt(2.0 * m * tmo_log(32.0 * m / pi_4));
+        double dm = (m < dxx) ? m : dxx;          /* std::min(m, dx) */
+        dm = (6.0 < dm) ? dm : 6.0;               /* std::max(6.0, .) */
+        const double d = floor(dm + 0.5);         /* std::round, argument >= 6 */
+        const double cx = 2.0 * m + d;
+        const double scx = sqrt(cx / 2.0);
+        const double i1cx = 1.0 / cx;
+        const double c2b = sqrt(pi_4 * cx) * tmo_exp(i1cx);
+        const double cb = 2.0 * cx * tmo_exp(-d * i1cx * (1.0 + d / 2.0)) / d;
+        /* operator(), LS:1322-1398 */
+        const double naf = (1.0 - 2.220446049250313e-16) / 2.0;
+        const double thr = 2147483647.0 + naf;
+        const double spi_2 = 1.2533141373155002512078826424055226;
+        const double c1 = sm * spi_2;
+        const double c2 = c2b + c1;
+        const double c3 = c2 + 1.0;
+        const double c4 = c3 + 1.0;
+        const double v178 = 0.0128205128205128205128205128205128;
+        const double e178 = 1.0129030479320018583185514777512983;
+        const double c5 = c4 + e178;
+        const double c = cb + c5;
+        const double v2cx = 2.0 * (2.0 * m + d);
+        double x = 0.0;
+        int reject = 1, it = 0;
+        do {
+            const double u = c * next_u(s);
+            const double e = -tmo_log(1.0 - next_u(s));
+            double w = 0.0;
+            if (u <= c1) {
+                const double n = normal01(s, &nd);
+                const double y = -fabs(n) * sm - 1.0;
+                x = floor(y);
+                w = -n * n / 2.0;
+                if (x < -m) continue;
+            } else if (u <= c2) {
+                const double n = normal01(s, &nd);
+                const double y = 1.0 + fabs(n) * scx;
+                x = ceil(y);
+                w = y * (2.0 - y) * i1cx;
+                if (x > d) continue;
+            } else if (u <= c3) {
+                x = -1.0;
+            } else if (u <= c4) {
+                x = 0.0;
+            } else if (u <= c5) {
+                x = 1.0;
+                w = v178;
+            } else {
+                const double v = -tmo_log(1.0 - next_u(s));
+                const double y = d + v * v2cx / d;
+                x = ceil(y);
+                w = -d * i1cx * (1.0 + y / 2.0);
+            }
+            reject = (w - e - x * lm_thr > lfm - tmo_lgamma_int(x + m + 1.0));
+            reject |= (x + m >= thr);
+        } while (reject && ++it < TM_MAX_REJECT);
+        if (reject) { s->g->overflow++; x = 0.0; }
+        return (long)(x + m + naf);
+    } else {
+        long x = 0;
+        double prod = 1.0;
+        const double lm_thr = tmo_exp(-mean); /* LS:1295 */
+        do {
+            prod *= next_u(s);
+            x += 1;
+        } while (prod > lm_thr && x < TM_MAX_PRODUCT);
+        return x - 1;
+    }
+}
+
+/* std::gamma_distribution<double>(alpha, 1.0)::operator() for a freshly constructed object
+ * (P/:1057, R/:3792): Marsaglia-Tsang with the alpha < 1 boost; set-up LS:2338-2345, draw
+ * LS:2352-2387.  std::pow(u, 1/alpha) is restated as exp(log(u)/alpha). */
+static double gamma_draw(cstream *s, double alpha)
+{
+    normal_state nd = {0, 0.0};
+    const double malpha = (alpha < 1.0) ? alpha + 1.0 : alpha;
+    const double a1 = malpha - 1.0 / 3.0;
+    const double a2 = 1.0 / sqrt(9.0 * a1);
+    double u, v, n;
+    int it = 0, again;
+    do {
+        int it2 = 0;
+        do {
+            n = normal01(s, &nd);
+            v = 1.0 + a2 * n;
+        } while (v <= 0.0 && ++it2 < TM_MAX_REJECT);
+        if (v <= 0.0) { s->g->overflow++; v = 1.0; n = 0.0; }
+        v = v * v * v;
+        u = next_u(s);
+        again = (u > 1.0 - 0.0331 * n * n * n * n)
+             && (tmo_log(u) > (0.5 * n * n + a1 * (1.0 - v + tmo_log(v))));
+    } while (again && ++it < TM_MAX_REJECT);
+    if (again) s->g->overflow++;
+    if (alpha == malpha)
+        return a1 * v * 1.0;
+    int it3 = 0;
+    do {
+        u = next_u(s);
+    } while (u == 0.0 && ++it3 < TM_MAX_REJECT);
+    if (u == 0.0) return 0.0;
+    /* pow(u, 1/alpha): u in (0,1); alpha == 0 gives u^inf = 0 exactly as LS does */
+    const double ex = (1.0 / alpha) * tmo_log(u);
+    return tmo_exp(ex) * a1 * v * 1.0;
+}
+
+/* test hooks: drive the samplers from a flat array of uniforms (SEQ semantics) */
+static void seq_rng(tmo_rng *g, const double *u, uint64_t n, uint64_t pos)
+{
+    memset(g, 0, sizeof *g);
+    g->kind = TMO_SRC_SEQ; g->u = u; g->n_u = n; g->pos = pos;
+}
+double tmo_test_normal_pair(const double *u, uint64_t n, uint64_t *pos, double *second)
+{
+    tmo_rng g; seq_rng(&g, u, n, *pos);
+    cstream s; cs_begin_cell(&s, &g, 0);
+    normal_state st = {0, 0.0};
+    double a = normal01(&s, &st);
+    *second = normal01(&s, &st);
+    *pos = g.pos;
+    return a;
+}
+long tmo_test_poisson(const double *u, uint64_t n, uint64_t *pos, double mean)
+{
+    tmo_rng g; seq_rng(&g, u, n, *pos);
+    cstream s; cs_begin_cell(&s, &g, 0);
+    long r = poisson_draw(&s, mean);
+    *pos = g.pos;
+    return r;
+}
+double tmo_test_gamma(const double *u, uint64_t n, uint64_t *pos, double shape)
+{
+    tmo_rng g; seq_rng(&g, u, n, *pos);
+    cstream s; cs_begin_cell(&s, &g, 0);
+    double r = gamma_draw(&s, shape);
+    *pos = g.pos;
+    return r;
+}
+
+/* ================================================================================== */
+/* 4. The Dornic cell update                                             */
+/* ================================================================================== */
+
+typedef struct {
+    double diffc;       /* D/dx^2            P/:952   R/:3463 */
+    double beta;        /* P/:953  R/:3461 */
+    double lambda_exp;  /* exp(beta dt)      P/:954   R/:3462 */
+    double lambda;      /* 2 beta/(sigma^2 (lambda_exp-1)) */
+    double sigma2;      /* sigma*sigma */
+    double sigma2_1;    /* 1/(sigma*sigma)   R/:3463 */
+} dornic_consts;
+
+static void derive_consts(const tmo_params *p, dornic_consts *k)
+{
+    const double dx2 = p->dx * p->dx;
+    if (p->model == TMO_MODEL_DP || p->model == TMO_MODEL_DP_CUBIC) {
+        k->diffc = p->D / (p->dx * p->dx);
+        k->beta = p->a - 4 * p->D / (p->dx * p->dx);
+        k->lambda_exp = exp(k->beta * p->dt);
+        k->lambda = 2 * k->beta / (p->sigma * p->sigma * (k->lambda_exp - 1.0));
+        k->sigma2 = p->sigma * p->sigma;
+        k->sigma2_1 = 1 / k->sigma2;
+    } else {
+        k->beta = -p->d - 4 * p->D0 / dx2;
+        k->lambda_exp = exp(k->beta * p->dt);
+        k->lambda = 2 * k->beta / (p->sigma0 * p->sigma0 * (k->lambda_exp - 1.0));
+        k->diffc = p->D0 / dx2;
+        k->sigma2 = p->sigma0 * p->sigma0;
+        k->sigma2_1 = 1 / (p->sigma0 * p->sigma0);
+    }
+}
+
+/* rho* for one live cell.  alpha_i already computed; rho_i = Rho_dt[i] (== DRho[i]). */
+static double dornic_cell(const tmo_params *p, const dornic_consts *k, cstream *s,
+                          normal_state *norm, double alpha_i, double rho_i)
+{
+    double mu, ziggy, gru;
+    switch (p->model) {
+    case TMO_MODEL_DP: /* P/:1054-1059 */
+        mu = -1.0 + 2.0 * alpha_i / k->sigma2;
+        ziggy = k->lambda * k->lambda_exp * rho_i;
+        /* poisson_distribution<int>(0.0) still burns one uniform (LS:1390-1397) */
+        gru = mu + 1.0 + (double)poisson_draw(s, ziggy);
+        return gamma_draw(s, gru) / k->lambda;
+    case TMO_MODEL_DP_CUBIC: /* P/:1957-1977 */
+        mu = -1.0 + 2.0 * alpha_i / k->sigma2;
+        ziggy = k->lambda * k->lambda_exp * rho_i;
+        if (ziggy == 0.0) gru = mu + 1.0;
+        else              gru = mu + 1.0 + (double)poisson_draw(s, ziggy);
+        return gamma_draw(s, gru) / k->lambda;
+    default: /* Rietkerk vegetation, R/:3766-3794 (= F/:4168-4196) */
+        mu = -1.0 + 2.0 * alpha_i * k->sigma2_1;
+        ziggy = k->lambda * k->lambda_exp * rho_i;
+        if (ziggy == 0.0) {
+            gru = mu + 1.0;
+        } else if (ziggy > 100) {
+            long gauss = (long)fma(normal01(s, norm), sqrt(ziggy), ziggy);
+            gru = mu + 1.0 + (double)gauss;
+        } else {
+            gru = mu + 1.0 + (double)poisson_draw(s, ziggy);
+        }
+        if (gru > 100) {
+            double gauss = fma(normal01(s, norm), sqrt(gru), gru);
+            return gauss / k->lambda;
+        }
+        return gamma_draw(s, gru) / k->lambda;
+    }
+}
+
+/* The cell loop: P/:1032-1061 (S8 table, P/:416-436), R/:3752-3809 (Sq4 table, R/:1609-1628). */
+static void dornic_sweep(const tmo_params *p, const dornic_consts *k, tmo_rng *rng,
+                         const double *prev, double *out)
+{
+    const int L = p->L;
+    cstream s;
+    normal_state norm_cell;
+    normal_state norm_seq = { rng->norm_saved_available, rng->norm_saved };
+    cs_begin_cell(&s, rng, 0);
+    for (int r = 0; r < L; r++) {
+        const int up = ((r - 1) % L + L) % L, dn = ((r + 1) % L + L) % L;
+        for (int q = 0; q < L; q++) {
+            const int lf = ((q - 1) % L + L) % L, rt = ((q + 1) % L + L) % L;
+            const int i = r * L + q;
+            const double alpha_i = k->diffc * (prev[up * L + q] + prev[dn * L + q]
+                                             + prev[r * L + lf] + prev[r * L + rt]);
+            if (alpha_i == 0 && prev[i] == 0) { out[i] = prev[i]; continue; }
+            normal_state *norm = &norm_seq;
+            if (rng->kind != TMO_SRC_SEQ) {
+                cs_begin_cell(&s, rng, (uint64_t)i);
+                norm_cell.saved_available = 0; norm_cell.saved = 0.0;
+                norm = &norm_cell;
+            }
+            out[i] = dornic_cell(p, k, &s, norm, alpha_i, prev[i]);
+        }
+    }
+    rng->norm_saved_available = norm_seq.saved_available;
+    rng->norm_saved = norm_seq.saved;
+}
+
+/* ================================================================================== */
+/* 5. Deterministic remainders                                                        */
+/* ================================================================================== */
+
+/* f_2Dor, R/:2359-2386.  s = {P,W,O} state, f = RHS; neighbour order up,down,left,right. */
+static void f_2Dor(const tmo_params *p, const double *S, double *f)
+{
+    const int L = p->L; const int64_t n = (int64_t)L * L;
+    const double *P = S, *W = S + n, *O = S + 2 * n;
+    const double dx2 = p->dx * p->dx;
+    const double Dxd2_1 = p->D1 / dx2, Dxd2_2 = p->D2 / dx2; /* R/:3479-3480 */
+    const double cgmax = p->rc * p->gmax;
+    for (int r = 0; r < L; r++) {
+        const int up = ((r - 1) % L + L) % L, dn = ((r + 1) % L + L) % L;
+        for (int q = 0; q < L; q++) {
+            const int lf = ((q - 1) % L + L) % L, rt = ((q + 1) % L + L) % L;
+            const int64_t i = (int64_t)r * L + q, iu = (int64_t)up * L + q, id = (int64_t)dn * L + q,
+                          il = (int64_t)r * L + lf, ir = (int64_t)r * L + rt;
+            f[i] = cgmax * W[i] * P[i] / (W[i] + p->K1);
+            f[n + i] = p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i]
+                     - p->gmax * W[i] * P[i] / (W[i] + p->K1) - p->rW * W[i]
+                     + Dxd2_1 * (W[iu] + W[id] + W[il] + W[ir] - 4 * W[i]);
+            f[2 * n + i] = p->a - p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i]
+                     + Dxd2_2 * (O[iu] + O[id] + O[il] + O[ir] - 4 * O[i]);
+        }
+    }
+}
+
+/* f_2D, R/:1718-1743: the full right-hand side (noise-off path). */
+static void f_2D(const tmo_params *p, const double *S, double *f)
+{
+    const int L = p->L; const int64_t n = (int64_t)L * L;
+    const double *P = S, *W = S + n, *O = S + 2 * n;
+    const double dx2 = p->dx * p->dx;
+    const double Dxd2_0 = p->D0 / dx2, Dxd2_1 = p->D1 / dx2, Dxd2_2 = p->D2 / dx2;
+    for (int r = 0; r < L; r++) {
+        const int up = ((r - 1) % L + L) % L, dn = ((r + 1) % L + L) % L;
+        for (int q = 0; q < L; q++) {
+            const int lf = ((q - 1) % L + L) % L, rt = ((q + 1) % L + L) % L;
+            const int64_t i = (int64_t)r * L + q, iu = (int64_t)up * L + q, id = (int64_t)dn * L + q,
+                          il = (int64_t)r * L + lf, ir = (int64_t)r * L + rt;
+            f[i] = p->rc * p->gmax * W[i] * P[i] / (W[i] + p->K1) - p->d * P[i]
+                 + Dxd2_0 * (P[iu] + P[id] + P[il] + P[ir] - 4 * P[i]);
+            f[n + i] = p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i]
+                     - p->gmax * W[i] * P[i] / (W[i] + p->K1) - p->rW * W[i]
+                     + Dxd2_1 * (W[iu] + W[id] + W[il] + W[ir] - 4 * W[i]);
+            f[2 * n + i] = p->a - p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i]
+                     + Dxd2_2 * (O[iu] + O[id] + O[il] + O[ir] - 4 * O[i]);
+        }
+    }
+}
+
+/* Classical RK4 over the three fields: RK4_Integrate_Stochastic_1Sp R/:2389-2440 (f_2Dor)
+ * and RK4_Integrate R/:1753-1814 (f_2D); dt2 = dt/2, dt6 = dt/6 (R/:170). */
+static int rk4_3field(const tmo_params *p, double *S, int full_rhs)
+{
+    const int64_t n3 = 3 * (int64_t)p->L * p->L;
+    double *buf = (double *)malloc(sizeof(double) * 5 * n3);
+    if (!buf) return -1;
+    double *tsar = buf, *K1 = buf + n3, *K2 = buf + 2 * n3, *K3 = buf + 3 * n3, *K4 = buf + 4 * n3;
+    const double dt = p->dt, dt2 = dt / 2.0, dt6 = dt / 6.0;
+    void (*f)(const tmo_params *, const double *, double *) = full_rhs ? f_2D : f_2Dor;
+    f(p, S, K1);
+    for (int64_t i = 0; i < n3; i++) tsar[i] = S[i] + dt2 * K1[i];
+    f(p, tsar, K2);
+    for (int64_t i = 0; i < n3; i++) tsar[i] = S[i] + dt2 * K2[i];
+    f(p, tsar, K3);
+    for (int64_t i = 0; i < n3; i++) tsar[i] = S[i] + dt * K3[i];
+    f(p, tsar, K4);
+    for (int64_t i = 0; i < n3; i++) S[i] += dt6 * (K1[i] + 2.0 * K2[i] + 2.0 * K3[i] + K4[i]);
+    free(buf);
+    return 0;
+}
+
+/* ================================================================================== */
+/* 6. One full time step                                                              */
+/* ================================================================================== */
+
+int tmo_dornic_only(const tmo_params *p, tmo_rng *rng, const double *prev, double *out)
+{
+    if (!p || !rng || !prev || !out || p->L < 1 || p->model == TMO_MODEL_RIETKERK_DET) return -1;
+    dornic_consts k; derive_consts(p, &k);
+    dornic_sweep(p, &k, rng, prev, out);
+    return 0;
+}
+
+int tmo_step(const tmo_params *p, tmo_rng *rng, double *f)
+{
+    if (!p || !f || p->L < 1) return -1;
+    const int64_t n = (int64_t)p->L * p->L;
+    dornic_consts k;
+    if (p->model == TMO_MODEL_RIETKERK_DET)
+        return rk4_3field(p, f, 1);
+    if (!rng) return -1;
+    derive_consts(p, &k);
+    double *star = (double *)malloc(sizeof(double) * n);
+    if (!star) return -1;
+    dornic_sweep(p, &k, rng, f, star); /* DRho == f[0..n), Rho_dt[0] <- star */
+    switch (p->model) {
+    case TMO_MODEL_DP: /* P/:1064-1068 */
+        for (int64_t i = 0; i < n; i++) f[i] = star[i] / (1 + p->b * star[i] * p->dt);
+        break;
+    case TMO_MODEL_DP_CUBIC: { /* RK4_Integrate P/:1775-1790 */
+        const double dt = p->dt, dt6 = dt / 6.0, dt2 = dt / 2.0, b = p->b, c = p->c;
+        for (int64_t i = 0; i < n; i++) {
+            const double r0 = star[i];
+            double K1, K2, K3, K4, M;
+            K1 = -b * r0 * r0 - c * r0 * r0 * r0;
+            M = r0 + dt2 * K1;
+            K2 = -b * M * M - c * M * M * M; M = r0 + dt2 * K2;
+            K3 = -b * M * M - c * M * M * M; M = r0 + dt * K3;
+            K4 = -b * M * M - c * M * M * M;
+            f[i] = r0 + dt6 * (K1 + 2.0 * K2 + 2.0 * K3 + K4);
+        }
+        break;
+    }
+    default: { /* Rietkerk: R/:4139 then clamp+commit R/:4150-4181 (F/:4460 for the FPE bounds) */
+        memcpy(f, star, sizeof(double) * n);
+        if (rk4_3field(p, f, 0)) { free(star); return -1; }
+        for (int64_t i = 0; i < 3 * n; i++)
+            if (f[i] < p->clamp_eps && f[i] >= p->clamp_lo) f[i] = 0.0;
+        break;
+    }
+    }
+    free(star);
+    return 0;
+}
+
+/* ================================================================================== */
+/* 7. Reductions and host-side bookkeeping                                            */
+/* ================================================================================== */
+
+double tmo_mean(const double *x, int64_t n) /* R/:1211-1219 = P/:123-131 */
+{
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; ++i) sum += x[i];
+    return sum / (double)n;
+}
+
+double tmo_occupied(const double *x, int64_t n) /* R/:1245-1254 = P/:145-154 */
+{
+    double sum = 0.0;
+    for (int64_t i = 0; i < n; ++i) if (x[i] > 0) sum += 1;
+    return sum;
+}
+
+int tmo_logarithm10_time_bins(double t_max, double dt, double *out, int cap) /* P/:336-378 */
+{
+    int n = 0;
+    if (t_max <= 1) return 0;
+    double tend_one = (double)(floor(log10(t_max) * 10.)) / 10.0;
+    double power = 0.0;
+    while (power <= tend_one) {
+        double t_raw = pow(10, power);
+        double t_fin = (int)(t_raw / dt) * dt;
+        if (t_fin <= 1.0) t_fin = t_fin + dt;
+        if (n > 0 && t_fin != out[n - 1]) { if (n < cap) out[n++] = t_fin; }
+        else if (n == 0) { if (n < cap) out[n++] = t_fin; }
+        power += 0.04;
+    }
+    for (int i = n - 1; i > 0; i--) {
+        if (out[i] < out[i - 1] + dt / 2.0) {
+            memmove(out + i, out + i + 1, sizeof(double) * (size_t)(n - i - 1));
+            n--;
+        }
+    }
+    return n;
+}
+
+void tmo_var_mean_incremental_surv_runs(double *acc, const double *rep, int n, int j) /* P/:173-208 */
+{
+    (void)j;
+    for (int i = 0; i < n; i++) {
+        double *A = acc + 5 * i; const double *X = rep + 2 * i;
+        int r = (int)(A[3] + 1);
+        if (X[0] == 0.0) break;
+        double mean_prev = A[1];
+        if (A[3] == 0.0) {
+            A[1] = X[1]; A[2] = 0.0; A[4] = X[0];
+        } else {
+            A[1] = (X[1] + (r - 1) * A[1]) / r;
+            A[4] = (X[0] + (r - 1) * A[4]) / r;
+            A[2] = (A[1] - mean_prev) * (A[1] - mean_prev)
+                 + (1 / (r - 1)) * ((r - 2) * A[2] + (X[1] - A[1]) * (X[1] - A[1])); /* int 1/(r-1) */
+        }
+        A[3] = r;
+    }
+}

@@ -1,0 +1,119 @@
+/*
+ * oracle/tm_oracle.h -- CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT.
+ *
+ * A plain-C restatement of the reference's Dornic lattice time step
+ * (HAL9K000/Trophic_Maelstorm, simulations/{Percolation_FD,Rietkerk_FD,Rietkerk_FPE}).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker.  The product path
+ * (trophic_maelstorm_b200/, include/tm_lattice.h) never links or calls it.
+ *
+ * Parity status: PINNED against the reference itself.  oracle/Makefile compiles the
+ * reference's own sources from /root/reference into oracle/_ref/ (git-ignored) with a
+ * replay URBG substituted for std::mt19937_64 (oracle/ref_shim/replay_urbg.h); the
+ * SEQ stream mode below consumes the very same uniforms in the very same order, and
+ * tests/golden/ holds reference outputs generated that way (tests/golden/make_golden.py).
+ *
+ * Every function cites the reference file:line it follows.  Shorthands:
+ *   P/ = simulations/Percolation_FD/stochasticSPDP.cpp
+ *   R/ = simulations/Rietkerk_FD/rietkerk_bjork_basic.cpp
+ *   F/ = simulations/Rietkerk_FPE/rietkerk_bjork_FKE.cpp
+ *   LS = libstdc++ 13 <bits/random.tcc> (the reference's sampler dependency,
+ *        /usr/include/c++/13/bits/random.tcc; not vendored by the reference)
+ */
+#ifndef TM_ORACLE_H
+#define TM_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- models ------------------------------------------------------------------- */
+enum {
+    TMO_MODEL_DP        = 0, /* P/:940-1072   Dornic + closed form rho/(1+b rho dt)      */
+    TMO_MODEL_DP_CUBIC  = 1, /* P/:1809-2062  Dornic + pointwise RK4 of -b rho^2-c rho^3 */
+    TMO_MODEL_RIETKERK  = 2, /* R/:3648-4183  veg Dornic + 3-field RK4 (f_2Dor) + clamp  */
+    TMO_MODEL_RIETKERK_DET = 3 /* R/:1718-1814 noise-off: full RHS f_2D, classical RK4    */
+};
+
+/* Field order everywhere: [0]=P (vegetation / rho), [1]=W (soil water), [2]=O (surface water);
+ * row-major i = row*L + col, periodic (R/:1609-1628, P/:416-436). */
+typedef struct tmo_params {
+    int32_t model;
+    int32_t L;
+    double dt, dx;
+    /* DP: d rho = a rho - b rho^2 (- c rho^3) + D lap rho + sigma sqrt(rho) eta */
+    double a, b, c, D, sigma;
+    /* Rietkerk (names as R/:3397): rainfall a is `a` above; c is `rc` */
+    double rc, gmax, alpha, rW, W0, d /* = M[0] */, K1, K2;
+    double D0, D1, D2;   /* D[0..2] (P, W, O) */
+    double sigma0;       /* sigma[0] */
+    /* clamp (R/:4176: eps=1e-12, lo=-1e-80 ; F/:4460: eps=1e-10, lo=0) */
+    double clamp_eps, clamp_lo;
+} tmo_params;
+
+/* ---- uniform streams -------------------------------------------------------------- */
+enum {
+    TMO_SRC_SEQ     = 0, /* one sequential array of uniforms shared by all cells, visited in
+                            increasing i -- the reference's mt19937_64 order.  The explicit
+                            std::normal_distribution `norm` (R/:3631) keeps its cached second
+                            variate across cells, as in the reference.                     */
+    TMO_SRC_REPLAY  = 1, /* per-cell slice u[cell*stride + k], k < stride (host-supplied
+                            uniforms; the replay contract of the product's tm_step_replay)   */
+    TMO_SRC_PHILOX  = 2  /* Philox4x32-10, key = seed, counter = (cell, trial, step, block)  */
+};
+
+typedef struct tmo_rng {
+    int32_t kind;
+    int32_t _pad;
+    const double *u;     /* SEQ / REPLAY */
+    uint64_t n_u;        /* length of u */
+    uint64_t pos;        /* SEQ: next index (in/out) */
+    uint64_t stride;     /* REPLAY: uniforms per cell */
+    uint64_t seed;       /* PHILOX */
+    uint32_t trial;      /* PHILOX */
+    uint32_t step;       /* PHILOX (caller increments per step) */
+    uint64_t overflow;   /* out: draws past the end of u / of a cell's slice */
+    uint64_t draws;      /* out: uniforms consumed */
+    /* persistent state of the reference's explicit `norm` object (SEQ mode only) */
+    int32_t norm_saved_available;
+    int32_t _pad2;
+    double norm_saved;
+} tmo_rng;
+
+/* ---- elementary functions of the sampler spec (bit-reproducible: IEEE + fma only) -- */
+double tmo_log(double x);
+double tmo_exp(double x);
+double tmo_lgamma_int(double k);
+void   tmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double tmo_u52_from_bits(uint64_t w);
+
+/* ---- samplers (restating LS) driven by an array of uniforms; *pos advances -------- */
+double tmo_test_normal_pair(const double *u, uint64_t n, uint64_t *pos, double *second);
+long   tmo_test_poisson(const double *u, uint64_t n, uint64_t *pos, double mean);
+double tmo_test_gamma(const double *u, uint64_t n, uint64_t *pos, double shape);
+
+/* ---- one time step of one lattice -------------------------------------------------
+ * f: 1 field (DP) or 3 fields (Rietkerk) of L*L doubles, contiguous SoA [field][i]; updated
+ * in place.  Returns 0, or -1 on bad arguments. */
+int tmo_step(const tmo_params *p, tmo_rng *rng, double *f);
+
+/* Dornic sub-step only (a2/a4): writes rho* into out[L*L] from field prev[L*L]. */
+int tmo_dornic_only(const tmo_params *p, tmo_rng *rng, const double *prev, double *out);
+
+/* reductions (a8): sequential left-to-right sum / L^2 and #{rho>0}; R/:1211,1245 P/:123,145 */
+double tmo_mean(const double *x, int64_t n);
+double tmo_occupied(const double *x, int64_t n);
+
+/* time-bin generator (a10): P/:336-378 = R/:1472-1514. Returns count written (<= cap). */
+int tmo_logarithm10_time_bins(double t_max, double dt, double *out, int cap);
+
+/* running mean / variance over surviving replicates (a9): P/:173-208.
+ * acc: [n][5] = {t, mean, var, n_surv, n_active}; rep: [n][2] = {n_active, mean}; j = replicate index. */
+void tmo_var_mean_incremental_surv_runs(double *acc, const double *rep, int n, int j);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
