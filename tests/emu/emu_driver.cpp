@@ -1,0 +1,134 @@
+// tests/emu/emu_driver.cpp -- TEST TOOL.  C entry points that push one lattice through the
+// product's kernel source on host threads (see tm_cpu_emu.h), with the same argument set-up the
+// C-ABI layer uses (csrc/tm_host_setup.h).  Used by tests/test_kernel_emulation.py to check the
+// marching pipeline, halo logic and decomposition invariance against the oracle without a GPU.
+#include "tm_host_setup.h"
+
+#include <vector>
+
+using namespace tml;
+
+namespace {
+void fill_ghosts(const Geom &g, std::vector<double> &buf)
+{
+    GhostArgs A{g, buf.data()};
+    emu_launch(ghost_cols_kernel, A, 1, 64, 0);
+}
+void pack(const Geom &g, const double *host, std::vector<double> &buf)
+{
+    const int roff = g.wrap ? 0 : kHalo;
+    for (int t = 0; t < g.n_trials; t++)
+        for (int f = 0; f < g.n_fields; f++)
+            for (int r = 0; r < g.nrows; r++)
+                for (int q = 0; q < g.L; q++)
+                    buf[(size_t)t * g.trial_stride + (size_t)f * g.field_stride + (size_t)(r + roff) * g.Lp + kHalo + q] =
+                        host[(((size_t)t * g.n_fields + f) * g.nrows + r) * g.L + q];
+}
+void unpack(const Geom &g, const std::vector<double> &buf, double *host)
+{
+    const int roff = g.wrap ? 0 : kHalo;
+    for (int t = 0; t < g.n_trials; t++)
+        for (int f = 0; f < g.n_fields; f++)
+            for (int r = 0; r < g.nrows; r++)
+                for (int q = 0; q < g.L; q++)
+                    host[(((size_t)t * g.n_fields + f) * g.nrows + r) * g.L + q] =
+                        buf[(size_t)t * g.trial_stride + (size_t)f * g.field_stride + (size_t)(r + roff) * g.Lp + kHalo + q];
+}
+}
+
+extern "C" {
+
+// fields: [n_trials][n_fields][L][L] in/out (whole lattice).  grid <= 0: as many CTAs as an n_sm-SM
+// device would get.  stats_out: [n_trials][8] = sum-derived mean[3], active[3], nonfinite, negative.
+int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int strict, int grid_override,
+             int n_sm, unsigned long long seed, unsigned trial0, unsigned step0,
+             const double *replay_u, unsigned stride, double *stats_out, unsigned long long *counters_out)
+{
+    Geom g{};
+    make_geom(*p, n_trials, 0, p->L, &g);
+    std::vector<double> bufs[2];
+    bufs[0].assign((size_t)g.n_trials * g.trial_stride, 0.0);
+    bufs[1].assign((size_t)g.n_trials * g.trial_stride, 0.0);
+    pack(g, fields, bufs[0]);
+    fill_ghosts(g, bufs[0]);
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    std::vector<double> a_trial(n_trials, p->a);
+    int cur = 0;
+    std::vector<PartialStats> partials;
+    int n_records = 0;
+    for (int s = 0; s < nsteps; s++) {
+        const bool stats = (s == nsteps - 1);
+        if (is_riet(p->model)) {
+            int grid, max_segs;
+            riet_launch_shape(g, n_sm, &grid, &max_segs);
+            if (grid_override > 0) { grid = grid_override; max_segs = (int)(((long long)g.n_trials * g.ns * g.nrows / grid + 1) / g.nrows) + 3; }
+            n_records = grid * max_segs;
+            partials.assign(n_records, PartialStats{});
+            for (auto &r : partials) r.trial = -1;
+            StepArgs A{};
+            A.g = g; A.c = riet_consts(*p);
+            A.in = bufs[cur].data(); A.out = bufs[cur ^ 1].data();
+            A.a_trial = a_trial.data(); A.seed = seed; A.trial0 = trial0; A.step = step0 + s;
+            A.replay_u = replay_u; A.stride = stride;
+            A.partials = partials.data(); A.max_segs = max_segs; A.counters = counters; A.dornic_out = nullptr;
+            const bool det = p->model == TM_MODEL_RIETKERK_DET;
+            const size_t smem = riet_smem_bytes(g.nthreads, det);
+            if (det) {
+                if (strict) emu_launch(riet_step_kernel<true, true, false, true, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<true, false, false, true, false>, A, grid, g.nthreads, smem);
+            } else if (replay_u) {
+                if (strict) emu_launch(riet_step_kernel<false, true, true, true, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<false, false, true, true, false>, A, grid, g.nthreads, smem);
+            } else {
+                if (strict) emu_launch(riet_step_kernel<false, true, false, true, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<false, false, false, true, false>, A, grid, g.nthreads, smem);
+            }
+        } else {
+            std::vector<DpTrial> trials(n_trials);
+            for (auto &t : trials) t.dk = dornic_consts(*p, p->a);
+            const int bpt = grid_override > 0 ? grid_override : 2;
+            n_records = bpt * n_trials;
+            partials.assign(n_records, PartialStats{});
+            for (auto &r : partials) r.trial = -1;
+            DpArgs A{};
+            A.g = g;
+            A.c.dt = p->dt; A.c.dt2 = p->dt / 2.0; A.c.dt6 = p->dt / 6.0; A.c.b = p->b; A.c.c = p->c;
+            A.in = bufs[cur].data(); A.out = bufs[cur ^ 1].data();
+            A.trials = trials.data(); A.seed = seed; A.trial0 = trial0; A.step = step0 + s;
+            A.replay_u = replay_u; A.stride = stride;
+            A.partials = partials.data(); A.counters = counters; A.dornic_out = nullptr; A.blocks_per_trial = bpt;
+            const size_t smem = sizeof(double) * 8 * 64;
+            if (p->model == TM_MODEL_DP) {
+                if (replay_u) emu_launch(dp_step_kernel<kDP, true, true, false>, A, bpt * n_trials, 64, smem);
+                else          emu_launch(dp_step_kernel<kDP, false, true, false>, A, bpt * n_trials, 64, smem);
+            } else {
+                if (replay_u) emu_launch(dp_step_kernel<kDPCubic, true, true, false>, A, bpt * n_trials, 64, smem);
+                else          emu_launch(dp_step_kernel<kDPCubic, false, true, false>, A, bpt * n_trials, 64, smem);
+            }
+        }
+        (void)stats;
+        cur ^= 1;
+    }
+    unpack(g, bufs[cur], fields);
+    if (stats_out && nsteps > 0) {
+        std::vector<TmStatsDev> sd(n_trials);
+        struct FinArgs { const PartialStats *p; int n, nt; double cells; TmStatsDev *out; } F{partials.data(), n_records, n_trials, (double)p->L * p->L, sd.data()};
+        auto fin = [](const FinArgs &f) { stats_finalize_kernel(f.p, f.n, f.nt, f.cells, f.out); };
+        emu_launch(fin, F, 1, (unsigned)n_trials, 0);
+        for (int t = 0; t < n_trials; t++) {
+            for (int f = 0; f < 3; f++) { stats_out[8 * t + f] = sd[t].mean[f]; stats_out[8 * t + 3 + f] = (double)sd[t].active[f]; }
+            stats_out[8 * t + 6] = (double)sd[t].nonfinite; stats_out[8 * t + 7] = (double)sd[t].negative;
+        }
+    }
+    if (counters_out) { counters_out[0] = counters[0]; counters_out[1] = counters[1]; }
+    return 0;
+}
+
+void emu_geometry(const tm_params *p, int n_trials, int *out /* ns, TX, nthreads, Lp */)
+{
+    Geom g{};
+    make_geom(*p, n_trials, 0, p->L, &g);
+    out[0] = g.ns; out[1] = g.TX; out[2] = g.nthreads; out[3] = g.Lp;
+}
+
+}

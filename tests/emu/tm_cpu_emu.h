@@ -1,0 +1,74 @@
+// tests/emu/tm_cpu_emu.h -- TEST TOOL.  Lets the CPU tests run the *product's own kernel source*
+// (trophic_maelstorm_b200/csrc/tm_kernels.cuh) on host threads: one std::thread per CUDA thread,
+// std::barrier for __syncthreads, a memcpy-backed stand-in for the TMA bulk copy + mbarrier.
+// It is not a fallback: nothing under trophic_maelstorm_b200/ can reach it (the kernels header
+// only includes it when compiled by a non-CUDA compiler, which only tests/emu/Makefile does).
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+inline thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+inline thread_local std::barrier<> *emu_block_barrier = nullptr;
+inline thread_local unsigned char *emu_dyn_smem_ptr = nullptr;
+
+inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
+inline unsigned char *tm_emu_dyn_smem() { return emu_dyn_smem_ptr; }
+#define TM_DYN_SMEM(name) unsigned char *name = tm_emu_dyn_smem()
+
+inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
+{
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+
+namespace tml {
+// mbarrier stand-in: the 64-bit word holds {pending bytes : 32 | completed phases : 32}.
+// Only one thread (tid 0) arms and copies, synchronously; waiters acquire-load.
+inline void mbar_init(uint64_t *b, int) { __atomic_store_n(b, 0ull, __ATOMIC_RELEASE); }
+inline void mbar_init_fence() {}
+inline void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    uint64_t v = __atomic_load_n(b, __ATOMIC_ACQUIRE);
+    __atomic_store_n(b, (v & 0xFFFFFFFFull) | ((uint64_t)bytes << 32), __ATOMIC_RELEASE);
+}
+inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
+{
+    std::memcpy(dst, src, bytes);
+    uint64_t v = __atomic_load_n(b, __ATOMIC_ACQUIRE);
+    uint32_t pending = (uint32_t)(v >> 32) - bytes, phase = (uint32_t)v;
+    if (pending == 0) phase++;
+    __atomic_store_n(b, ((uint64_t)pending << 32) | phase, __ATOMIC_RELEASE);
+}
+inline bool mbar_try_wait(uint64_t *b, uint32_t parity)
+{
+    const uint32_t phase = (uint32_t)__atomic_load_n(b, __ATOMIC_ACQUIRE);
+    if ((phase & 1u) != parity) return true;
+    std::this_thread::yield();
+    return false;
+}
+}
+
+// run `kernel(args)` over grid x block on host threads, blocks one after another
+template <class K, class A>
+inline void emu_launch(K kernel, const A &args, unsigned grid, unsigned block, size_t smem_bytes)
+{
+    std::vector<unsigned char> smem(smem_bytes + 256);
+    unsigned char *sbase = (unsigned char *)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
+    for (unsigned b = 0; b < grid; b++) {
+        std::memset(smem.data(), 0xA5, smem.size()); // shared memory starts as garbage
+        std::barrier<> bar((std::ptrdiff_t)block);
+        std::vector<std::thread> th;
+        th.reserve(block);
+        for (unsigned t = 0; t < block; t++)
+            th.emplace_back([&, t, b] {
+                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
+                emu_block_barrier = &bar; emu_dyn_smem_ptr = sbase;
+                kernel(args);
+            });
+        for (auto &x : th) x.join();
+    }
+}

@@ -1,0 +1,130 @@
+"""ctypes view of the CPU oracle (oracle/tm_oracle.h).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+dp = C.POINTER(C.c_double)
+
+SRC_SEQ, SRC_REPLAY, SRC_PHILOX = 0, 1, 2
+
+
+class OParams(C.Structure):
+    _fields_ = [("model", C.c_int32), ("L", C.c_int32)] + [
+        (n, C.c_double) for n in (
+            "dt dx a b c D sigma rc gmax alpha rW W0 d K1 K2 D0 D1 D2 sigma0 clamp_eps clamp_lo").split()]
+
+
+class ORng(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("u", dp), ("n_u", C.c_uint64), ("pos", C.c_uint64),
+                ("stride", C.c_uint64), ("seed", C.c_uint64), ("trial", C.c_uint32), ("step", C.c_uint32),
+                ("overflow", C.c_uint64), ("draws", C.c_uint64), ("norm_saved_available", C.c_int32),
+                ("_pad2", C.c_int32), ("norm_saved", C.c_double)]
+
+
+_lib = None
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+
+
+def oracle():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ORACLE_DIR, "libtm_oracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        L = C.CDLL(path)
+        for n in ("tmo_log", "tmo_exp", "tmo_lgamma_int"):
+            getattr(L, n).restype = C.c_double
+            getattr(L, n).argtypes = [C.c_double]
+        L.tmo_mean.restype = C.c_double
+        L.tmo_mean.argtypes = [dp, C.c_int64]
+        L.tmo_occupied.restype = C.c_double
+        L.tmo_occupied.argtypes = [dp, C.c_int64]
+        L.tmo_step.argtypes = [C.POINTER(OParams), C.POINTER(ORng), dp]
+        L.tmo_dornic_only.argtypes = [C.POINTER(OParams), C.POINTER(ORng), dp, dp]
+        L.tmo_u52_from_bits.restype = C.c_double
+        L.tmo_u52_from_bits.argtypes = [C.c_uint64]
+        L.tmo_test_normal_pair.restype = C.c_double
+        L.tmo_test_normal_pair.argtypes = [dp, C.c_uint64, C.POINTER(C.c_uint64), dp]
+        L.tmo_test_poisson.restype = C.c_long
+        L.tmo_test_poisson.argtypes = [dp, C.c_uint64, C.POINTER(C.c_uint64), C.c_double]
+        L.tmo_test_gamma.restype = C.c_double
+        L.tmo_test_gamma.argtypes = [dp, C.c_uint64, C.POINTER(C.c_uint64), C.c_double]
+        L.tmo_logarithm10_time_bins.argtypes = [C.c_double, C.c_double, dp, C.c_int]
+        L.tmo_var_mean_incremental_surv_runs.argtypes = [dp, dp, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def to_oparams(p):
+    """Product Params -> oracle params (same field names; separate structs on purpose)."""
+    o = OParams()
+    for name, _ in OParams._fields_:
+        setattr(o, name, getattr(p, name))
+    return o
+
+
+def ptr(a):
+    return a.ctypes.data_as(dp)
+
+
+def make_rng(kind, u=None, stride=0, seed=0, trial=0, step=0, pos=0):
+    g = ORng()
+    g.kind = kind
+    if u is not None:
+        g.u = ptr(u)
+        g.n_u = u.size
+    g.pos, g.stride, g.seed, g.trial, g.step = pos, stride, seed, trial, step
+    return g
+
+
+def step(p, rng, fields):
+    """One oracle step in place on fields [n_fields][L*L] (contiguous float64)."""
+    assert fields.flags["C_CONTIGUOUS"] and fields.dtype == np.float64
+    rc = oracle().tmo_step(C.byref(p), C.byref(rng) if rng is not None else None, ptr(fields))
+    assert rc == 0
+    return fields
+
+
+def dornic_only(p, rng, prev):
+    out = np.empty_like(prev)
+    rc = oracle().tmo_dornic_only(C.byref(p), C.byref(rng), ptr(prev), ptr(out))
+    assert rc == 0
+    return out
+
+
+def mean(x):
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    return oracle().tmo_mean(ptr(x), x.size)
+
+
+def occupied(x):
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    return oracle().tmo_occupied(ptr(x), x.size)
+
+
+def synthetic_rietkerk_frame(L, seed=1234, a=0.05, dP=10000.0, fringe=True):
+    """MFT speckle frame of SURVEY 8(d) (init_exprtk_randbiMFTframe rule, R/:474-496), plus an
+    optional empty/fringe band so that every sampler regime is exercised."""
+    rng = np.random.default_rng(seed)
+    n = L * L
+    c, d, rW, Wstar = 1e4, 0.25 / 24, 0.2 / 24, 5.0
+    Vstar = (c / d) * a - rW * Wstar * c / d
+    P = np.full(n, Vstar)
+    P[rng.random(n) < 0.015] = max(dP, 5 * Vstar)
+    P = P.reshape(L, L)
+    if fringe:
+        w = max(2, L // 8)
+        P[:, :w] = 0.0
+        P[:, w:w + max(2, L // 16)] = 10 ** rng.uniform(-5, -1, (L, max(2, L // 16)))
+    f = np.empty((3, L, L))
+    f[0] = P
+    f[1] = Wstar * a
+    f[2] = 120.4744181 * a + 0.58243061
+    return f

@@ -1,0 +1,537 @@
+// tm_lattice.cu -- the extern "C" layer of include/tm_lattice.h over the sm_100a kernels.
+// Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo
+// (fused multiply-adds in the kernels are explicit; see tm_math.cuh).
+#include "../../include/tm_lattice.h"
+#include "tm_kernels.cuh"
+#include "tm_host_setup.h"
+
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace tml;
+
+static thread_local std::string g_create_error;
+
+struct tm_ctx {
+    tm_params p{};
+    Geom g{};
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    bool have_state = false, stats_valid = false, strict = false;
+    std::vector<double> a_host;
+    double *a_dev = nullptr;
+    DpTrial *dp_trials_dev = nullptr;
+    bool trial_consts_dirty = true;
+    PartialStats *partials = nullptr;
+    int n_records = 0, grid = 0, max_segs = 0, dp_blocks_per_trial = 0;
+    TmStatsDev *stats_dev = nullptr;
+    unsigned long long *counters = nullptr;
+    double *replay_dev = nullptr;
+    size_t replay_cap = 0;
+    double *dornic_dev = nullptr;
+    double *halo_dev[2] = {nullptr, nullptr};
+    uint64_t seed = 0, step = 0;
+    uint32_t trial0 = 0;
+    float last_ms = 0.f;
+    int last_launches = 0;
+    std::string err;
+};
+
+#define TM_FAIL(ctx, code, ...)                                             \
+    do {                                                                    \
+        char _b[512];                                                       \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                               \
+        (ctx)->err = _b;                                                    \
+        return (code);                                                      \
+    } while (0)
+
+#define TM_CUDA(ctx, call)                                                                    \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) TM_FAIL(ctx, TM_E_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" {
+
+int tm_abi_version(void) { return TM_ABI_VERSION; }
+
+int tm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *tm_last_error(const tm_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int tm_halo_rows(void) { return kHalo; }
+
+static int create_fail(tm_ctx *c, int code, const char *msg)
+{
+    g_create_error = msg;
+    if (c) { g_create_error += c->err.empty() ? "" : (": " + c->err); tm_destroy(c); }
+    return code;
+}
+
+static int alloc_all(tm_ctx *c)
+{
+    Geom &g = c->g;
+    const size_t nbytes = sizeof(double) * (size_t)g.n_trials * g.trial_stride;
+    for (int s = 0; s < 2; s++) {
+        TM_CUDA(c, cudaMalloc(&c->buf[s], nbytes));
+        TM_CUDA(c, cudaMemsetAsync(c->buf[s], 0, nbytes, c->stream));
+    }
+    TM_CUDA(c, cudaMalloc(&c->a_dev, sizeof(double) * g.n_trials));
+    TM_CUDA(c, cudaMalloc(&c->dp_trials_dev, sizeof(DpTrial) * g.n_trials));
+    TM_CUDA(c, cudaMalloc(&c->stats_dev, sizeof(TmStatsDev) * g.n_trials));
+    TM_CUDA(c, cudaMalloc(&c->counters, sizeof(unsigned long long) * 4));
+    TM_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 4, c->stream));
+    // launch geometry
+    if (is_riet(c->p.model)) {
+        riet_launch_shape(g, c->n_sm, &c->grid, &c->max_segs);
+        c->n_records = c->grid * c->max_segs;
+    } else {
+        const long long ncell = (long long)g.nrows * g.L;
+        long long bpt = (ncell + 256 * 4 - 1) / (256 * 4);
+        const long long cap = (8LL * c->n_sm + g.n_trials - 1) / g.n_trials;
+        if (bpt > cap) bpt = cap;
+        if (bpt < 1) bpt = 1;
+        c->dp_blocks_per_trial = (int)bpt;
+        c->n_records = (int)bpt * g.n_trials;
+    }
+    // the stand-alone stats kernel uses its own (possibly larger) record set
+    {
+        const long long ncell = (long long)g.nrows * g.L;
+        long long bpt = (ncell + 256 * 8 - 1) / (256 * 8);
+        const long long cap = (4LL * c->n_sm + g.n_trials - 1) / g.n_trials;
+        if (bpt > cap) bpt = cap;
+        if (bpt < 1) bpt = 1;
+        const int need = (int)bpt * g.n_trials;
+        if (need > c->n_records) c->n_records = need;
+    }
+    TM_CUDA(c, cudaMalloc(&c->partials, sizeof(PartialStats) * c->n_records));
+    const size_t halo_bytes = sizeof(double) * (size_t)g.n_trials * g.n_fields * kHalo * g.Lp;
+    for (int s = 0; s < 2; s++) TM_CUDA(c, cudaMalloc(&c->halo_dev[s], halo_bytes));
+    return TM_OK;
+}
+
+int tm_create_slab(const tm_params *p, int n_trials, int device, int row0, int nrows, tm_ctx **out)
+{
+    if (!p || !out) return create_fail(nullptr, TM_E_ARG, "tm_create: null argument");
+    *out = nullptr;
+    if (p->model < 0 || p->model > 3) return create_fail(nullptr, TM_E_ARG, "tm_create: unknown model");
+    if (p->L < 8 || p->L > 65535) return create_fail(nullptr, TM_E_ARG, "tm_create: L must be in [8, 65535]");
+    if (n_trials < 1) return create_fail(nullptr, TM_E_ARG, "tm_create: n_trials < 1");
+    if (row0 < 0 || nrows < 1 || row0 + nrows > p->L) return create_fail(nullptr, TM_E_ARG, "tm_create: bad row slab");
+    if (nrows != p->L && nrows < kHalo) return create_fail(nullptr, TM_E_ARG, "tm_create: a slab needs at least 4 rows");
+    if (!(p->dt > 0) || !(p->dx > 0)) return create_fail(nullptr, TM_E_ARG, "tm_create: dt and dx must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return create_fail(nullptr, TM_E_CUDA, "tm_create: no CUDA device (this library has no CPU path)");
+    }
+    if (device < 0 || device >= ndev) return create_fail(nullptr, TM_E_ARG, "tm_create: bad device index");
+    tm_ctx *c = new (std::nothrow) tm_ctx();
+    if (!c) return create_fail(nullptr, TM_E_ARG, "tm_create: out of host memory");
+    c->p = *p; c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) return create_fail(c, TM_E_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return create_fail(c, TM_E_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 9) return create_fail(c, TM_E_CUDA, "tm_create: device lacks TMA bulk copies (needs sm_90+, built for sm_100a)");
+    c->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return create_fail(c, TM_E_CUDA, "cudaStreamCreate failed");
+    if (cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) return create_fail(c, TM_E_CUDA, "cudaEventCreate failed");
+
+    Geom &g = c->g;
+    make_geom(*p, n_trials, row0, nrows, &g);
+    c->a_host.assign(n_trials, p->a);
+    if (alloc_all(c) != TM_OK) return create_fail(c, TM_E_CUDA, "tm_create: device allocation failed");
+
+    // opt in to the large dynamic shared memory the Rietkerk kernel needs
+    if (is_riet(p->model)) {
+        const int smem_s = (int)riet_smem_bytes(g.nthreads, false), smem_d = (int)riet_smem_bytes(g.nthreads, true);
+        bool ok = true;
+#define TM_OPTIN(K, B) ok = ok && (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, B) == cudaSuccess)
+        TM_OPTIN((riet_step_kernel<false, false, false, false, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, false, true, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, false, false, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, false, true, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, true, true, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, true, true, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, false, false, true>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, true, false, true>), smem_s);
+        TM_OPTIN((riet_step_kernel<true, false, false, false, false>), smem_d);
+        TM_OPTIN((riet_step_kernel<true, false, false, true, false>), smem_d);
+        TM_OPTIN((riet_step_kernel<true, true, false, false, false>), smem_d);
+        TM_OPTIN((riet_step_kernel<true, true, false, true, false>), smem_d);
+#undef TM_OPTIN
+        if (!ok) { cudaGetLastError(); return create_fail(c, TM_E_CUDA, "tm_create: cudaFuncSetAttribute(shared memory) failed"); }
+    }
+    *out = c;
+    return TM_OK;
+}
+
+int tm_create(const tm_params *p, int n_trials, int device, tm_ctx **out)
+{
+    return tm_create_slab(p, n_trials, device, 0, p ? p->L : 0, out);
+}
+
+int tm_destroy(tm_ctx *c)
+{
+    if (!c) return TM_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int s = 0; s < 2; s++) { cudaFree(c->buf[s]); cudaFree(c->halo_dev[s]); }
+    cudaFree(c->a_dev); cudaFree(c->dp_trials_dev); cudaFree(c->partials); cudaFree(c->stats_dev);
+    cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+    return TM_OK;
+}
+
+int tm_n_fields(const tm_ctx *c) { return c ? c->g.n_fields : TM_E_ARG; }
+
+int tm_set_trial_a(tm_ctx *c, int trial, double a)
+{
+    if (!c) return TM_E_ARG;
+    if (trial < 0 || trial >= c->g.n_trials) TM_FAIL(c, TM_E_ARG, "tm_set_trial_a: trial %d out of range", trial);
+    c->a_host[trial] = a;
+    c->trial_consts_dirty = true;
+    return TM_OK;
+}
+
+int tm_set_strict(tm_ctx *c, int strict)
+{
+    if (!c) return TM_E_ARG;
+    c->strict = strict != 0;
+    return TM_OK;
+}
+
+static int push_trial_consts(tm_ctx *c)
+{
+    if (!c->trial_consts_dirty) return TM_OK;
+    TM_CUDA(c, cudaMemcpyAsync(c->a_dev, c->a_host.data(), sizeof(double) * c->g.n_trials, cudaMemcpyHostToDevice, c->stream));
+    if (!is_riet(c->p.model)) {
+        std::vector<DpTrial> t(c->g.n_trials);
+        for (int i = 0; i < c->g.n_trials; i++) t[i].dk = dornic_consts(c->p, c->a_host[i]);
+        TM_CUDA(c, cudaMemcpyAsync(c->dp_trials_dev, t.data(), sizeof(DpTrial) * t.size(), cudaMemcpyHostToDevice, c->stream));
+        TM_CUDA(c, cudaStreamSynchronize(c->stream)); // t goes out of scope
+    }
+    c->trial_consts_dirty = false;
+    return TM_OK;
+}
+
+static int fill_ghost_cols(tm_ctx *c, double *buf)
+{
+    GhostArgs A{c->g, buf};
+    const long long n = (long long)c->g.n_trials * c->g.n_fields * c->g.rows_alloc * 8;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 8 * c->n_sm) blocks = 8 * c->n_sm;
+    ghost_cols_kernel<<<blocks, 256, 0, c->stream>>>(A);
+    TM_CUDA(c, cudaGetLastError());
+    return TM_OK;
+}
+
+int tm_upload(tm_ctx *c, const double *host)
+{
+    if (!c || !host) return TM_E_ARG;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    const Geom &g = c->g;
+    const int roff = g.wrap ? 0 : kHalo;
+    // all (trial, field) planes are equally spaced on both sides: one 2-D copy per plane
+    for (int t = 0; t < g.n_trials; t++)
+        for (int f = 0; f < g.n_fields; f++) {
+            double *dst = c->buf[c->cur] + (long long)t * g.trial_stride + (long long)f * g.field_stride + (long long)roff * g.Lp + kHalo;
+            const double *src = host + ((size_t)t * g.n_fields + f) * (size_t)g.nrows * g.L;
+            TM_CUDA(c, cudaMemcpy2DAsync(dst, sizeof(double) * g.Lp, src, sizeof(double) * g.L, sizeof(double) * g.L, g.nrows,
+                                         cudaMemcpyHostToDevice, c->stream));
+        }
+    if (fill_ghost_cols(c, c->buf[c->cur]) != TM_OK) return TM_E_CUDA;
+    c->have_state = true; c->stats_valid = false;
+    return TM_OK;
+}
+
+int tm_download(tm_ctx *c, double *host)
+{
+    if (!c || !host) return TM_E_ARG;
+    if (!c->have_state) TM_FAIL(c, TM_E_STATE, "tm_download: no state uploaded");
+    TM_CUDA(c, cudaSetDevice(c->device));
+    const Geom &g = c->g;
+    const int roff = g.wrap ? 0 : kHalo;
+    for (int t = 0; t < g.n_trials; t++)
+        for (int f = 0; f < g.n_fields; f++) {
+            const double *src = c->buf[c->cur] + (long long)t * g.trial_stride + (long long)f * g.field_stride + (long long)roff * g.Lp + kHalo;
+            double *dst = host + ((size_t)t * g.n_fields + f) * (size_t)g.nrows * g.L;
+            TM_CUDA(c, cudaMemcpy2DAsync(dst, sizeof(double) * g.L, src, sizeof(double) * g.Lp, sizeof(double) * g.L, g.nrows,
+                                         cudaMemcpyDeviceToHost, c->stream));
+        }
+    TM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_seed(tm_ctx *c, uint64_t seed, uint32_t trial0)
+{
+    if (!c) return TM_E_ARG;
+    c->seed = seed; c->trial0 = trial0;
+    return TM_OK;
+}
+int tm_set_step_counter(tm_ctx *c, uint64_t step) { if (!c) return TM_E_ARG; c->step = step; return TM_OK; }
+uint64_t tm_step_counter(const tm_ctx *c) { return c ? c->step : 0; }
+
+// one launch: in = buf[cur] -> out = buf[cur^1]
+static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool dornic_only)
+{
+    const Geom &g = c->g;
+    const tm_params &p = c->p;
+    if (stats) TM_CUDA(c, cudaMemsetAsync(c->partials, 0xFF, sizeof(PartialStats) * c->n_records, c->stream));
+    if (is_riet(p.model)) {
+        StepArgs A{};
+        A.g = g; A.c = riet_consts(p);
+        A.in = c->buf[c->cur]; A.out = c->buf[c->cur ^ 1];
+        A.a_trial = c->a_dev; A.seed = c->seed; A.trial0 = c->trial0; A.step = (unsigned int)c->step;
+        A.replay_u = c->replay_dev; A.stride = stride;
+        A.partials = c->partials; A.max_segs = c->max_segs; A.counters = c->counters; A.dornic_out = c->dornic_dev;
+        const bool det = p.model == TM_MODEL_RIETKERK_DET;
+        const size_t smem = riet_smem_bytes(g.nthreads, det);
+        const dim3 grid(c->grid), block(g.nthreads);
+#define TM_LAUNCH(...) riet_step_kernel<__VA_ARGS__><<<grid, block, smem, c->stream>>>(A)
+        if (det) {
+            if (c->strict) { if (stats) TM_LAUNCH(true, true, false, true, false); else TM_LAUNCH(true, true, false, false, false); }
+            else           { if (stats) TM_LAUNCH(true, false, false, true, false); else TM_LAUNCH(true, false, false, false, false); }
+        } else if (dornic_only) {
+            if (replay) TM_LAUNCH(false, false, true, false, true); else TM_LAUNCH(false, false, false, false, true);
+        } else if (replay) {
+            if (c->strict) TM_LAUNCH(false, true, true, true, false); else TM_LAUNCH(false, false, true, true, false);
+        } else if (c->strict) {
+            if (stats) TM_LAUNCH(false, true, false, true, false); else TM_LAUNCH(false, true, false, false, false);
+        } else {
+            if (stats) TM_LAUNCH(false, false, false, true, false); else TM_LAUNCH(false, false, false, false, false);
+        }
+#undef TM_LAUNCH
+    } else {
+        DpArgs A{};
+        A.g = g;
+        A.c.dt = p.dt; A.c.dt2 = p.dt / 2.0; A.c.dt6 = p.dt / 6.0; A.c.b = p.b; A.c.c = p.c; // P/:1780
+        A.in = c->buf[c->cur]; A.out = c->buf[c->cur ^ 1];
+        A.trials = c->dp_trials_dev; A.seed = c->seed; A.trial0 = c->trial0; A.step = (unsigned int)c->step;
+        A.replay_u = c->replay_dev; A.stride = stride;
+        A.partials = c->partials; A.counters = c->counters; A.dornic_out = c->dornic_dev;
+        A.blocks_per_trial = c->dp_blocks_per_trial;
+        const dim3 grid(c->dp_blocks_per_trial * g.n_trials), block(256);
+        const size_t smem = sizeof(double) * 8 * 256;
+#define TM_LAUNCH(M, ...) dp_step_kernel<M, __VA_ARGS__><<<grid, block, smem, c->stream>>>(A)
+        if (p.model == TM_MODEL_DP) {
+            if (dornic_only) { if (replay) TM_LAUNCH(kDP, true, false, true); else TM_LAUNCH(kDP, false, false, true); }
+            else if (replay) TM_LAUNCH(kDP, true, true, false);
+            else if (stats) TM_LAUNCH(kDP, false, true, false);
+            else TM_LAUNCH(kDP, false, false, false);
+        } else {
+            if (dornic_only) { if (replay) TM_LAUNCH(kDPCubic, true, false, true); else TM_LAUNCH(kDPCubic, false, false, true); }
+            else if (replay) TM_LAUNCH(kDPCubic, true, true, false);
+            else if (stats) TM_LAUNCH(kDPCubic, false, true, false);
+            else TM_LAUNCH(kDPCubic, false, false, false);
+        }
+#undef TM_LAUNCH
+    }
+    TM_CUDA(c, cudaGetLastError());
+    return TM_OK;
+}
+
+static int check_slab_step(tm_ctx *c, const char *who)
+{
+    if (!c->have_state) TM_FAIL(c, TM_E_STATE, "%s: no state uploaded", who);
+    return TM_OK;
+}
+
+int tm_step(tm_ctx *c, int nsteps)
+{
+    if (!c) return TM_E_ARG;
+    if (nsteps < 0) TM_FAIL(c, TM_E_ARG, "tm_step: nsteps < 0");
+    if (check_slab_step(c, "tm_step") != TM_OK) return TM_E_STATE;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    if (push_trial_consts(c) != TM_OK) return TM_E_CUDA;
+    if (!c->g.wrap && nsteps > 1) TM_FAIL(c, TM_E_ARG, "tm_step: a row slab advances one step per halo exchange");
+    TM_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    for (int s = 0; s < nsteps; s++) {
+        const int rc = launch_step(c, s == nsteps - 1, false, 0, false);
+        if (rc != TM_OK) return rc;
+        c->cur ^= 1; c->step++;
+    }
+    TM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->last_launches = nsteps;
+    if (nsteps > 0) c->stats_valid = true;
+    return TM_OK;
+}
+
+static int ensure_replay(tm_ctx *c, size_t n)
+{
+    if (n <= c->replay_cap) return TM_OK;
+    cudaFree(c->replay_dev); c->replay_dev = nullptr; c->replay_cap = 0;
+    TM_CUDA(c, cudaMalloc(&c->replay_dev, sizeof(double) * n));
+    c->replay_cap = n;
+    return TM_OK;
+}
+
+int tm_step_replay(tm_ctx *c, const double *host_uniforms, uint64_t stride)
+{
+    if (!c || !host_uniforms) return TM_E_ARG;
+    if (c->p.model == TM_MODEL_RIETKERK_DET) TM_FAIL(c, TM_E_ARG, "tm_step_replay: the noise-off model draws no uniforms");
+    if (stride < 1 || stride > (1u << 20)) TM_FAIL(c, TM_E_ARG, "tm_step_replay: bad stride");
+    if (check_slab_step(c, "tm_step_replay") != TM_OK) return TM_E_STATE;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    if (push_trial_consts(c) != TM_OK) return TM_E_CUDA;
+    const size_t n = (size_t)c->g.n_trials * c->g.L * c->g.L * stride;
+    if (ensure_replay(c, n) != TM_OK) return TM_E_CUDA;
+    TM_CUDA(c, cudaMemcpyAsync(c->replay_dev, host_uniforms, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    TM_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    const int rc = launch_step(c, true, true, (uint32_t)stride, false);
+    if (rc != TM_OK) return rc;
+    TM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    c->cur ^= 1; c->step++;
+    c->last_launches = 1; c->stats_valid = true;
+    return TM_OK;
+}
+
+int tm_dornic_only(tm_ctx *c, double *host_out)
+{
+    if (!c || !host_out) return TM_E_ARG;
+    if (c->p.model == TM_MODEL_RIETKERK_DET) TM_FAIL(c, TM_E_ARG, "tm_dornic_only: the noise-off model has no Dornic sub-step");
+    if (check_slab_step(c, "tm_dornic_only") != TM_OK) return TM_E_STATE;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    if (push_trial_consts(c) != TM_OK) return TM_E_CUDA;
+    const size_t n = (size_t)c->g.n_trials * c->g.nrows * c->g.L;
+    if (!c->dornic_dev) TM_CUDA(c, cudaMalloc(&c->dornic_dev, sizeof(double) * n));
+    const int rc = launch_step(c, false, false, 0, true);
+    if (rc != TM_OK) return rc;
+    TM_CUDA(c, cudaMemcpyAsync(host_out, c->dornic_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    TM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_halo_bytes(const tm_ctx *c, uint64_t *bytes)
+{
+    if (!c || !bytes) return TM_E_ARG;
+    *bytes = sizeof(double) * (uint64_t)c->g.n_trials * c->g.n_fields * kHalo * c->g.Lp;
+    return TM_OK;
+}
+
+// which = 0: this slab's first 4 rows (the upper neighbour's bottom ghosts); 1: its last 4 rows
+int tm_halo_pack(tm_ctx *c, int which, void **dev_buf)
+{
+    if (!c || !dev_buf || which < 0 || which > 1) return TM_E_ARG;
+    if (c->g.wrap) TM_FAIL(c, TM_E_STATE, "tm_halo_pack: not a slab context");
+    TM_CUDA(c, cudaSetDevice(c->device));
+    const Geom &g = c->g;
+    const long long r = which == 0 ? kHalo : g.nrows; // physical row of the first packed row
+    TM_CUDA(c, cudaMemcpy2DAsync(c->halo_dev[which], sizeof(double) * kHalo * g.Lp,
+                                 c->buf[c->cur] + r * g.Lp, sizeof(double) * g.field_stride,
+                                 sizeof(double) * kHalo * g.Lp, (size_t)g.n_trials * g.n_fields,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+    *dev_buf = c->halo_dev[which];
+    return TM_OK;
+}
+
+// which = 0: fill the ghost rows ABOVE row 0; 1: the ghost rows BELOW the last row
+int tm_halo_unpack(tm_ctx *c, int which, const void *dev_buf)
+{
+    if (!c || !dev_buf || which < 0 || which > 1) return TM_E_ARG;
+    if (c->g.wrap) TM_FAIL(c, TM_E_STATE, "tm_halo_unpack: not a slab context");
+    TM_CUDA(c, cudaSetDevice(c->device));
+    const Geom &g = c->g;
+    const long long r = which == 0 ? 0 : g.nrows + kHalo;
+    TM_CUDA(c, cudaMemcpy2DAsync(c->buf[c->cur] + r * g.Lp, sizeof(double) * g.field_stride,
+                                 dev_buf, sizeof(double) * kHalo * g.Lp,
+                                 sizeof(double) * kHalo * g.Lp, (size_t)g.n_trials * g.n_fields,
+                                 cudaMemcpyDeviceToDevice, c->stream));
+    return TM_OK;
+}
+
+void *tm_cuda_stream(tm_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int tm_sync(tm_ctx *c)
+{
+    if (!c) return TM_E_ARG;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    TM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_measure(tm_ctx *c, tm_stats *out)
+{
+    if (!c || !out) return TM_E_ARG;
+    if (!c->have_state) TM_FAIL(c, TM_E_STATE, "tm_measure: no state uploaded");
+    TM_CUDA(c, cudaSetDevice(c->device));
+    const Geom &g = c->g;
+    int n_records = c->n_records;
+    if (!c->stats_valid) {
+        const long long ncell = (long long)g.nrows * g.L;
+        long long bpt = (ncell + 256 * 8 - 1) / (256 * 8);
+        const long long cap = (4LL * c->n_sm + g.n_trials - 1) / g.n_trials;
+        if (bpt > cap) bpt = cap;
+        if (bpt < 1) bpt = 1;
+        TM_CUDA(c, cudaMemsetAsync(c->partials, 0xFF, sizeof(PartialStats) * c->n_records, c->stream));
+        StatsArgs A{g, c->buf[c->cur], c->partials, (int)bpt};
+        stats_kernel<<<(int)bpt * g.n_trials, 256, sizeof(double) * 8 * 256, c->stream>>>(A);
+        TM_CUDA(c, cudaGetLastError());
+        c->stats_valid = true;
+    }
+    stats_finalize_kernel<<<(g.n_trials + 127) / 128, 128, 0, c->stream>>>(c->partials, n_records, g.n_trials,
+                                                                            (double)((long long)g.nrows * g.L), c->stats_dev);
+    TM_CUDA(c, cudaGetLastError());
+    std::vector<TmStatsDev> h(g.n_trials);
+    TM_CUDA(c, cudaMemcpyAsync(h.data(), c->stats_dev, sizeof(TmStatsDev) * g.n_trials, cudaMemcpyDeviceToHost, c->stream));
+    TM_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < g.n_trials; t++) {
+        for (int f = 0; f < 3; f++) { out[t].mean[f] = h[t].mean[f]; out[t].active[f] = h[t].active[f]; }
+        out[t].nonfinite = h[t].nonfinite; out[t].negative = h[t].negative;
+    }
+    return TM_OK;
+}
+
+int tm_sampler_overflow(tm_ctx *c, uint64_t *count)
+{
+    if (!c || !count) return TM_E_ARG;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    unsigned long long h[4];
+    TM_CUDA(c, cudaMemcpyAsync(h, c->counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    TM_CUDA(c, cudaStreamSynchronize(c->stream));
+    *count = h[0];
+    if (h[1]) TM_FAIL(c, TM_E_CUDA, "TMA pipeline timed out in %llu CTA(s): results are invalid", h[1]);
+    return TM_OK;
+}
+
+int tm_last_step_ms(tm_ctx *c, float *ms, int *n_launches)
+{
+    if (!c || !ms) return TM_E_ARG;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    TM_CUDA(c, cudaEventSynchronize(c->ev1));
+    TM_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    *ms = c->last_ms;
+    if (n_launches) *n_launches = c->last_launches;
+    return TM_OK;
+}
+
+int tm_run_host(tm_ctx *c, double *host_soa, int nsteps, int download, tm_stats *out)
+{
+    int rc = tm_upload(c, host_soa);
+    if (rc != TM_OK) return rc;
+    rc = tm_step(c, nsteps);
+    if (rc != TM_OK) return rc;
+    if (out) { rc = tm_measure(c, out); if (rc != TM_OK) return rc; }
+    if (download) { rc = tm_download(c, host_soa); if (rc != TM_OK) return rc; }
+    return tm_sync(c);
+}
+
+} // extern "C"

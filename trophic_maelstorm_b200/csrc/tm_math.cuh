@@ -1,0 +1,173 @@
+// tm_math.cuh -- elementary functions, Philox and uniforms of the sampler spec.
+//
+// Everything here is built from IEEE-754 +,-,*,/,sqrt, explicit fma and integer bit operations,
+// and the translation unit is compiled with --fmad=false, so results are a pure function of the
+// inputs: identical on every sm_100a launch geometry and on a host compile (tests/emu).
+//
+// Reference call sites these serve: the std:: samplers of P/:1055-1059 and R/:3776-3793
+// (libstdc++ <bits/random.tcc>), the engine std::mt19937_64 of P/:975, R/:3513.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define TM_HD __host__ __device__ __forceinline__
+#else
+#define TM_HD inline
+#endif
+
+namespace tml {
+
+TM_HD uint64_t d2u(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(x);
+#else
+    uint64_t u; __builtin_memcpy(&u, &x, 8); return u;
+#endif
+}
+TM_HD double u2d(uint64_t u)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double x; __builtin_memcpy(&x, &u, 8); return x;
+#endif
+}
+
+// Rejection loops are bounded (spec): never reached with genuine uniforms, but a starved replay
+// buffer or a garbage halo cell must not spin.
+constexpr int kMaxReject = 64;
+constexpr int kMaxProduct = 4096;
+
+// log(x), finite normal x > 0: x = 2^k m, m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(f/(2+f)).
+TM_HD double log_pos(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    if (!(x > 0.0)) return (x == 0.0) ? -INFINITY : NAN;
+    if (x == INFINITY) return x;
+    uint64_t b = d2u(x);
+    int k = (int)(b >> 52) - 1023;
+    const uint64_t mant = b & 0x000FFFFFFFFFFFFFull;
+    if (mant > 0x6A09E667F3BCCull) { b = mant | 0x3FE0000000000000ull; k += 1; }
+    else                           { b = mant | 0x3FF0000000000000ull; }
+    const double f = u2d(b) - 1.0;
+    const double dk = (double)k;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
+    const double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f);
+}
+
+// exp(x): k = rint(x log2 e), two-part reduction, degree-13 Taylor, two-step 2^k scaling.
+TM_HD double exp_any(double x)
+{
+    const double LOG2E = 1.44269504088896338700e+00;
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    if (x != x) return x;
+    if (x > 709.782712893384) return INFINITY;
+    if (x < -745.2) return 0.0;
+    const double kf = rint(x * LOG2E);
+    double r = fma(kf, -ln2_hi, x);
+    r = fma(kf, -ln2_lo, r);
+    double q = 1.0 / 6227020800.0;
+    q = fma(q, r, 1.0 / 479001600.0);
+    q = fma(q, r, 1.0 / 39916800.0);
+    q = fma(q, r, 1.0 / 3628800.0);
+    q = fma(q, r, 1.0 / 362880.0);
+    q = fma(q, r, 1.0 / 40320.0);
+    q = fma(q, r, 1.0 / 5040.0);
+    q = fma(q, r, 1.0 / 720.0);
+    q = fma(q, r, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    double y = 1.0 + fma(r * r, q, r);
+    const int k = (int)kf;
+    const int k1 = k / 2, k2 = k - k1;
+    y *= u2d((uint64_t)(k1 + 1023) << 52);
+    y *= u2d((uint64_t)(k2 + 1023) << 52);
+    return y;
+}
+
+// ln((k-1)!) for k = 1..40, correctly rounded (60-digit decimal arithmetic; these are the same 40
+// mathematical constants the test oracle generates for itself with oracle/gen_tables.py).
+TM_HD double logfact_small(int k)
+{
+    switch (k) {
+    case 1: return 0.0; case 2: return 0.0;
+    case 3: return 0.6931471805599453;  case 4: return 1.791759469228055;
+    case 5: return 3.1780538303479458;  case 6: return 4.787491742782046;
+    case 7: return 6.579251212010101;   case 8: return 8.525161361065415;
+    case 9: return 10.60460290274525;   case 10: return 12.801827480081469;
+    case 11: return 15.104412573075516; case 12: return 17.502307845873887;
+    case 13: return 19.987214495661885; case 14: return 22.552163853123425;
+    case 15: return 25.19122118273868;  case 16: return 27.89927138384089;
+    case 17: return 30.671860106080672; case 18: return 33.50507345013689;
+    case 19: return 36.39544520803305;  case 20: return 39.339884187199495;
+    case 21: return 42.335616460753485; case 22: return 45.38013889847691;
+    case 23: return 48.47118135183523;  case 24: return 51.60667556776438;
+    case 25: return 54.78472939811232;  case 26: return 58.00360522298052;
+    case 27: return 61.261701761002;    case 28: return 64.55753862700634;
+    case 29: return 67.88974313718154;  case 30: return 71.25703896716801;
+    case 31: return 74.65823634883016;  case 32: return 78.0922235533153;
+    case 33: return 81.55795945611504;  case 34: return 85.05446701758152;
+    case 35: return 88.58082754219768;  case 36: return 92.1361756036871;
+    case 37: return 95.7196945421432;   case 38: return 99.33061245478743;
+    case 39: return 102.96819861451381; default: return 106.63176026064346;
+    }
+}
+
+// log Gamma(k) for integer-valued k >= 1 (LS:1280, LS:1388 only ever pass such arguments).
+TM_HD double lgamma_int(double k)
+{
+    if (!(k >= 1.0)) return NAN;
+    if (k <= 40.0) return logfact_small((int)k);
+    const double HALF_LOG_2PI = 0.91893853320467274178;
+    const double ik = 1.0 / k, ik2 = ik * ik;
+    const double ser = ik * fma(ik2, fma(ik2, fma(ik2, -1.0 / 1680.0, 1.0 / 1260.0), -1.0 / 360.0), 1.0 / 12.0);
+    return (fma(k - 0.5, log_pos(k), -k) + HALF_LOG_2PI) + ser;
+}
+
+// Philox4x32-10, counter (c0..c3), key (k0,k1).
+struct u32x4 { uint32_t x, y, z, w; };
+
+TM_HD void mulhilo32(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo)
+{
+#if defined(__CUDA_ARCH__)
+    lo = a * b; hi = __umulhi(a, b);
+#else
+    const uint64_t p = (uint64_t)a * b; lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
+#endif
+}
+
+TM_HD u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo32(0xD2511F53u, c0, h0, l0);
+        mulhilo32(0xCD9E8D57u, c2, h1, l1);
+        c0 = h1 ^ c1 ^ k0; c1 = l1;
+        c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return u32x4{c0, c1, c2, c3};
+}
+
+// 52-bit uniform in [0,1) from the top 52 bits of a 64-bit word.
+TM_HD double u52(uint32_t lo, uint32_t hi)
+{
+    const uint64_t w = ((uint64_t)hi << 32) | lo;
+    return u2d(0x3FF0000000000000ull | (w >> 12)) - 1.0;
+}
+
+} // namespace tml
