@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- lattice site-updates/s of the fused Rietkerk Dornic+RK4 step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU integrator
+
+A "step" is one full Dornic time step (vegetation Dornic sampling + RK4 over P,W,O + clamp +
+reductions) of every site of the workload lattice(s).  N=1 workload: Rietkerk SPB=1, L=4096,
+one trial per GPU (the configuration the metric and the 60 %-of-HBM target are quoted on);
+N>1 shards independent trials over ranks with no data-path collective ("weak").
+
+value  : whole-job site-updates/s, state resident in HBM, device-timed (CUDA events on the
+         kernel's stream), max over ranks.
+e2e    : same metric through tm_run_host(): every step copies the step's input frame from pinned
+         host memory to the device and reads the step's reductions back.
+roofline: algorithmic bytes (48 B per site-update: 3 fields x (8 read + 8 written)) / the average
+         launch duration of the step kernel, against the measured HBM copy bandwidth.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_SITE_UPDATE = 48.0  # Rietkerk SPB=1, 3 fields x (8 B read + 8 B written)
+METRIC = "lattice site-updates/sec (FP64, device-timed), Rietkerk Dornic+RK4 step"
+UNIT = "site-updates/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch(L, trials):
+    """dram bytes per launch from the committed ncu --set full capture, if it matches this workload."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            d = json.load(fh)
+        if d.get("L") == L and d.get("trials") == trials:
+            return float(d["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inside = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
+        for l in inside:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm: the reference's own integrator (oracle/_ref) or, failing that, the oracle port
+# ---------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    """One process = one a-value, like one OpenMP thread of the reference's sweep (R/:4519)."""
+    L, steps, a, seed = args
+    import ctypes as C
+    import numpy as np
+    import oracle_lib as O
+    os.chdir(tempfile.mkdtemp(prefix="tmref_"))
+    frame = np.ascontiguousarray(O.synthetic_rietkerk_frame(L, seed=seed, a=a, fringe=False).reshape(3, -1))
+    so = os.path.join(ROOT, "oracle", "_ref", "libtm_ref_riet.so")
+    dt = 0.1
+    if os.path.exists(so):
+        ref = C.CDLL(so)
+
+        class RP(C.Structure):
+            _fields_ = [(n, C.c_double) for n in "a c gmax alpha rW W0 d K1 K2 D0 D1 D2 sigma0 dt dx".split()]
+        D0 = 0.00025 / 24
+        rp = RP(a, 1e4, 0.05e-3 / 24, 0.2 / 24, 0.2 / 24, 0.2, 0.25 / 24, 5.0, 5000.0, D0, D0, 0.025 / 24,
+                (D0 / 0.01) ** 0.5, dt, 0.1)
+        dp = C.POINTER(C.c_double)
+
+        def run(n):
+            tm_ = np.array([0.0, dt * (n - 1)])
+            ft = np.array([1e300, 1e300])
+            rows = np.zeros((8, 7)); nfr = C.c_int()
+            t0 = time.perf_counter()
+            ref.ref_riet_run(C.byref(rp), L, 1, frame.ctypes.data_as(dp), tm_.ctypes.data_as(dp), 2,
+                             ft.ctypes.data_as(dp), 2, None, C.c_uint64(0), None, None, 0, C.byref(nfr),
+                             rows.ctypes.data_as(dp), 8, None, None)
+            return time.perf_counter() - t0
+        kind = "reference"
+    else:
+        import trophic_maelstorm_b200 as tm
+        op = O.to_oparams(tm.rietkerk_params(L, a=a))
+
+        def run(n):
+            f = frame.copy()
+            t0 = time.perf_counter()
+            for s in range(n):
+                O.step(op, O.make_rng(O.SRC_PHILOX, seed=seed, trial=0, step=s), f)
+            return time.perf_counter() - t0
+        kind = "port"
+    # two run lengths: the difference removes set-up (neighbour tables, frame copies)
+    t_short = run(2)
+    t_long = run(2 + steps)
+    return kind, max(t_long - t_short, 1e-9)
+
+
+def cpu_reference(L, steps, procs):
+    """site-updates/s of the CPU integrator on `procs` cores (one a-value per core)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    jobs = [(L, steps, 0.05 + 0.001 * i, 100 + i) for i in range(procs)]
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    kind = res[0][0]
+    slowest = max(r[1] for r in res)
+    rate = procs * L * L * steps / slowest
+    return {"value": rate, "unit": UNIT, "cores": procs, "kind": kind,
+            "sample": "Rietkerk SPB=1 L=%d lattice per core, %d Dornic+RK4 steps each, %d a-values in parallel "
+                      "(the reference parallelises over a-values only); set-up excluded; wall %.1f s" % (L, steps, procs, wall)}
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    steps = max(1, a.steps)
+    per_step = []
+    base = None
+    for _ in range(a.warmup and 1 or 0):
+        cpu_reference(a.ref_L, 1, cores)
+    t0 = time.perf_counter()
+    base = cpu_reference(a.ref_L, steps, cores)
+    wall = time.perf_counter() - t0
+    v = base["value"]
+    out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup,
+           "ms_per_step": 1e3 * a.L * a.L * a.trials * a.gpus / v, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "config": {"workload": "Rietkerk SPB=1 Dornic+RK4, L=%d, %d trial(s) per GPU; CPU arm times a bounded sample: %s"
+                                  % (a.L, a.trials, base["sample"])},
+           "cpu_baseline": base, "gpu_launches": 0,
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(a):
+    import numpy as np
+    import torch
+    import oracle_lib as O          # only for the synthetic frame rule and the cpu_baseline leg
+    import trophic_maelstorm_b200 as tm
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    L, trials, K, W = a.L, a.trials, a.steps, max(a.warmup, 3)
+    p = tm.rietkerk_params(L)
+    lat = tm.Lattice(p, trials, device=local)
+    lat.seed(20261017, trial0=rank * trials)
+    host = torch.empty((trials, 3, L, L), dtype=torch.float64, pin_memory=True)
+    hnp = host.numpy()
+    for t in range(trials):
+        hnp[t] = O.synthetic_rietkerk_frame(L, seed=1234 + rank * trials + t, fringe=False)
+    lat.upload(hnp)
+
+    def barrier():
+        torch.cuda.synchronize()
+        lat.sync()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lat.step(W)
+    lat.sync()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    barrier()
+    t0 = time.time()
+    lat.step(K)                      # K launches of the fused step kernel on the ctx stream
+    lat.sync()
+    t1 = time.time()
+    ms_dev, n_launch = lat.last_step_ms()   # CUDA events recorded around the K launches
+    barrier()
+    clocks = sampler.stop(t0, t1)
+    ms_dev = maxr(ms_dev)
+    stats = lat.measure()
+    ok = all(s.nonfinite == 0 for s in stats)
+
+    sites_per_step = float(world) * trials * L * L
+    value = sites_per_step * K / (ms_dev * 1e-3)
+    peak, peak_src = measured_peaks()
+    achieved = (trials * L * L * BYTES_PER_SITE_UPDATE) / (ms_dev * 1e-3 / K) / 1e9  # per GPU, GB/s
+
+    # end to end through the host-buffer entry point: H2D of the step's frame + step + D2H of the reductions
+    Ke = max(1, min(K, a.e2e_steps))
+    lat.run_host(hnp, 1, download=False)
+    barrier()
+    te0 = time.perf_counter()
+    for _ in range(Ke):
+        lat.run_host(hnp, 1, download=False)
+    lat.sync()
+    te = maxr(time.perf_counter() - te0)
+    e2e_value = sites_per_step * Ke / te
+    import ctypes as C
+    h2d = trials * 3 * L * L * 8
+    d2h = trials * C.sizeof(tm.Stats)
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Rietkerk SPB=1 (veg/soil-water/surface-water) Dornic+RK4 step, L=%d, %d trial(s) per GPU, "
+                               "a=0.05 dt=0.1, MFT speckle initial frame" % (L, trials),
+                   "parallelism": "independent trials per rank, no data-path collective",
+                   "l2": "state %.0f MiB per GPU (x2 ping-pong) exceeds the 126 MB L2; no flush needed" % (trials * 3 * L * L * 8 / 2**20),
+                   "timing": "CUDA events on the kernel stream around K launches, max over ranks",
+                   "finite": ok},
+        "gpu_launches": n_launch,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic_per_launch(L, trials), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": trials * L * L * BYTES_PER_SITE_UPDATE,
+                     "kernel": "tml::riet_step_kernel<DET=0,STRICT=0,REPLAY=0,STATS,DORNIC_ONLY=0>"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "call": "tm_run_host(ctx, pinned_host_frame, nsteps=1, download=0, stats)"},
+    }
+    if rank == 0 and world == 1 and not a.no_cpu:
+        out["cpu_baseline"] = cpu_reference(a.ref_L, a.ref_steps, host_cores())
+    lat.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=4096)
+    ap.add_argument("--trials", type=int, default=1, help="trials per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-L", type=int, default=512, help="lattice side of the bounded CPU sample")
+    ap.add_argument("--ref-steps", type=int, default=12)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,9 +40,14 @@
 namespace tml {
 
 constexpr int kHalo = 4;            // RK4 dependency cone: 3 stencil applications + the Dornic alpha stencil
-constexpr int kRing = 8;            // TMA input ring slots
-constexpr int kPrefetch = kRing - 2;
-constexpr int kMaxThreads = 384;
+#ifndef TM_MAXTHREADS
+#define TM_MAXTHREADS 384
+#endif
+#ifndef TM_MINBLOCKS
+#define TM_MINBLOCKS 1
+#endif
+constexpr int kMaxThreads = TM_MAXTHREADS;  // CTA size cap (one thread per strip column)
+constexpr int kMinBlocks = TM_MINBLOCKS;    // resident CTAs per SM the register budget is sized for
 
 struct RietConsts {
     double dt, dt2, dt6;
@@ -124,6 +129,21 @@ TM_D bool mbar_wait(uint64_t *b, uint32_t parity)
 // ------------------------------------------------------------------------------------------
 struct F3 { double p, w, o; };
 
+// 1/b for the fast (non-STRICT) RK4 arithmetic, b > 0 and far from the exponent limits:
+// MUFU.RCP64H seed (rel. error 2^-23) + two Newton steps, ~1 ulp, no special-case branches.
+TM_D double rcp_pos(double b)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(r, fma(-b, r, 1.0), r);
+    r = fma(r, fma(-b, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / b;
+#endif
+}
+
 // f_2Dor R/:2376-2382 (DET=false) / f_2D R/:1730-1737 (DET=true); STRICT keeps the reference's
 // operation order so results are bit-identical to the oracle; the fast form shares one reciprocal.
 template <bool DET, bool STRICT>
@@ -143,7 +163,7 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
         f.o = a - c.alpha * (P + c.K2 * c.W0) / (P + c.K2) * O + c.Do * (Ou + Od + Ol + Or_ - 4 * O);
     } else {
         const double wk = W + c.K1, pk = P + c.K2;
-        const double r = 1.0 / (wk * pk);
+        const double r = rcp_pos(wk * pk);
         const double q = (W * P) * (pk * r);                 // W P / (W + K1)
         const double infil = c.alpha * (P + c.K2W0) * (wk * r) * O;
         const double lapW = fma(-4.0, W, (Wu + Wd) + (Wl + Wr));
@@ -162,7 +182,15 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
 template <bool STRICT>
 TM_D double axpy(double a, double x, double y) { return STRICT ? (y + a * x) : fma(a, x, y); }
 
-TM_D double clamp_small(double v, double eps, double lo) { return (v < eps && v >= lo) ? 0.0 : v; }
+// `if (v < eps && v >= lo) v = 0` (R/:4176) with eps > 0 >= lo, on the bit patterns: for v >= +0 the
+// IEEE order is the integer order; for v < 0 the magnitude must not exceed |lo|.  NaN is kept.
+TM_D double clamp_small(double v, double eps, double lo)
+{
+    const uint64_t b = d2u(v), mag = b & 0x7FFFFFFFFFFFFFFFull;
+    const bool neg = (b >> 63) != 0;
+    const bool hit = neg ? (mag <= (d2u(lo) & 0x7FFFFFFFFFFFFFFFull)) : (mag < d2u(eps));
+    return hit ? 0.0 : v;
+}
 
 // ------------------------------------------------------------------------------------------
 // Block-level statistics flush: sum/active/guards of this thread's outputs -> one record
@@ -174,10 +202,13 @@ struct ThreadStats {
     TM_D void add(int f, double v)
     {
         sum[f] += v;
-        const uint64_t b = d2u(v);
-        active[f] += (v > 0) ? 1u : 0u;
-        nonfinite += ((b & 0x7FF0000000000000ull) == 0x7FF0000000000000ull) ? 1u : 0u;
-        negative += (v < 0) ? 1u : 0u;
+        const uint64_t b = d2u(v), mag = b & 0x7FFFFFFFFFFFFFFFull;
+        const bool nf = (b & 0x7FF0000000000000ull) == 0x7FF0000000000000ull;
+        const bool isnan_ = mag > 0x7FF0000000000000ull;
+        const bool neg = (b >> 63) != 0;
+        active[f] += (!neg && mag != 0 && !isnan_) ? 1u : 0u;   // v > 0
+        nonfinite += nf ? 1u : 0u;
+        negative += (neg && mag != 0 && !isnan_) ? 1u : 0u;     // v < 0
     }
 };
 
@@ -206,20 +237,113 @@ TM_D void flush_stats(const ThreadStats &ts, int n_fields, int trial, PartialSta
 // ------------------------------------------------------------------------------------------
 // Rietkerk fused step
 // ------------------------------------------------------------------------------------------
-// shared memory carve-up (doubles unless noted), RW = nthreads + 4 (2 pad each side, 16 B aligned):
-//   ring  [kRing][3][RW]      TMA destination rows (P,W,O); element of thread cx at [cx + 2]
-//   exch  [2][NX][RW]         stage states published for horizontal neighbours, NX = 6 (W1,O1,W2,O2,W3,O3) or 9 (+P1,P2,P3)
-//   scratch [8][nthreads]     statistics flush
-//   mbar  uint64[kRing]
+// shared memory carve-up (doubles unless noted), RW = nthreads + 4 (2 pad each side, 16 B aligned);
+// the element of thread cx sits at [cx + 2] of a row:
+//   in   [kInSlots][3][RW]    TMA destination rows (P,W,O) = stage-0 state, rows j-4 .. j+kPrefetch
+//   st   [3][kStSlots][NF][RW] stage-1/2/3 states (W,O[,P]) of the last kStSlots rows of each front
+//   mbar uint64[kInSlots]
+// (the statistics flush aliases `st`).
+constexpr int kInSlots = 8;
+constexpr int kStSlots = 3;
+constexpr int kPrefetch = 3;
+
+constexpr int kRW = kMaxThreads + 4;   // shared row width: compile-time, so field/neighbour offsets fold into immediates
+
 TM_HD size_t riet_smem_bytes(int nthreads, bool det)
 {
-    const size_t RW = (size_t)nthreads + 4;
-    return sizeof(double) * (kRing * 3 * RW + 2 * (det ? 9 : 6) * RW + 8 * (size_t)nthreads) + sizeof(uint64_t) * kRing + 128;
+    const size_t RW = (size_t)kRW;
+    const size_t nf = det ? 3 : 2;
+    size_t st = 3 * kStSlots * nf * RW;
+    if (st < 8 * (size_t)nthreads) st = 8 * (size_t)nthreads;
+    return sizeof(double) * (kInSlots * 3 * RW + st) + sizeof(uint64_t) * kInSlots + 128;
+}
+
+// The exact-sampler branches (Poisson mean <= 100, Gamma shape <= 100: extinction fringe only) are
+// kept out of line so the marching loop stays small; they redo the cell from its counter, which
+// yields the same value as the inline Gaussian path would have up to the point of divergence.
+#if defined(__CUDACC__)
+__device__ __noinline__
+#else
+inline
+#endif
+double riet_cell_exact(DornicConsts dk, uint32_t cell, uint32_t trial, uint32_t step, unsigned long long seed,
+                       double alpha_i, double rho_i)
+{
+    PhiloxSrc src;
+    src.begin(cell, trial, step, seed);
+    return dornic_cell<kRietkerk>(dk, src, alpha_i, rho_i);
+}
+
+// One candidate of the polar method: uniforms 2k, 2k+1 of the cell's stream (= Philox block k).
+TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t k, uint32_t key0, uint32_t key1,
+                          double &x, double &y, double &r2)
+{
+    const u32x4 o = philox4x32_10(cell, trial, step, k, key0, key1);
+    x = 2.0 * u52(o.x, o.y) - 1.0;
+    y = 2.0 * u52(o.z, o.w) - 1.0;
+    r2 = fma(x, x, y * y);
+    return !(r2 > 1.0 || r2 == 0.0);
+}
+
+// Warp-level polar sampler: the first two std::normal_distribution variates (LS:1811-1848) of the
+// streams of the lanes with `need`.  Every lane first tries block 0 of its own stream; the retries of
+// the ~21 % of lanes whose candidate fell outside the unit disc are then spread over ALL 32 lanes
+// (blocks k, k+1, .. of a rejected lane are evaluated side by side by helper lanes), and each owner
+// takes the lowest accepted block -- exactly the pair a sequential loop over its stream would have
+// accepted, in ~2 warp passes instead of ~3.1 with divergent per-lane loops.
+// Must be called by all 32 lanes of a warp (trial/step/seed warp-uniform).
+TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t step, unsigned long long seed,
+                          double &n_first, double &n_second)
+{
+    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+    double x = 0.5, y = 0.5, r2 = 0.5;
+    bool ok = true;
+#if defined(__CUDA_ARCH__)
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if (need) ok = polar_candidate(cell, trial, step, 0, key0, key1, x, y, r2);
+    unsigned pending = __ballot_sync(full, !ok);
+    uint32_t kbase = 1;
+    while (pending != 0 && kbase < (uint32_t)kMaxReject) {
+        const int F = __popc(pending);
+        const int lg = (F <= 8) ? 2 : (F <= 16) ? 1 : 0;      // 4, 2 or 1 candidate blocks per rejected lane
+        const int per = 1 << lg;
+        const int fi = lane >> lg;                            // which rejected lane this lane helps
+        const bool helper = fi < F;
+        const int src = helper ? (int)__fns(pending, 0, fi + 1) : lane;
+        const uint32_t cell_s = __shfl_sync(full, cell, src);
+        double hx = 0.5, hy = 0.5, hr2 = 2.0;
+        bool hok = false;
+        if (helper) hok = polar_candidate(cell_s, trial, step, kbase + (uint32_t)(lane & (per - 1)), key0, key1, hx, hy, hr2);
+        const unsigned okmask = __ballot_sync(full, hok);
+        int from = lane;
+        bool got = false;
+        if (!ok) {
+            const int rank = __popc(pending & ((1u << lane) - 1u));
+            const unsigned mine = ((per == 32) ? full : ((1u << per) - 1u)) << (rank << lg);
+            const unsigned hit = okmask & mine;
+            if (hit) { from = __ffs((int)hit) - 1; got = true; }
+        }
+        const double sx = __shfl_sync(full, hx, from), sy = __shfl_sync(full, hy, from), sr = __shfl_sync(full, hr2, from);
+        if (got) { x = sx; y = sy; r2 = sr; ok = true; }
+        pending = __ballot_sync(full, !ok);
+        kbase += (uint32_t)per;
+    }
+#else
+    if (need) {
+        uint32_t k = 0;
+        do { ok = polar_candidate(cell, trial, step, k, key0, key1, x, y, r2); } while (!ok && ++k < (uint32_t)kMaxReject);
+    }
+#endif
+    if (!ok) { x = 0.5; y = 0.5; r2 = 0.5; } // bound reached (never with genuine uniforms)
+    const double mult = sqrt(-2.0 * log_pos(r2) / r2);
+    n_second = x * mult;
+    n_first = y * mult;
 }
 
 template <bool DET, bool STRICT, bool REPLAY, bool STATS, bool DORNIC_ONLY>
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(kMaxThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 #else
 void
 #endif
@@ -228,21 +352,22 @@ riet_step_kernel(const StepArgs A)
     const Geom &g = A.g;
     const RietConsts &c = A.c;
     const int tid = threadIdx.x, nthreads = g.nthreads;
-    const int RW = nthreads + 4;
-    constexpr int NX = DET ? 9 : 6;
+    constexpr int RW = kRW;
+    constexpr int NF = DET ? 3 : 2;          // stage fields kept in shared memory: W,O[,P]
 
     TM_DYN_SMEM(smem_raw);
-    double *ring = reinterpret_cast<double *>(smem_raw);
-    double *exch = ring + kRing * 3 * RW;
-    double *scratch = exch + 2 * NX * RW;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(scratch + 8 * nthreads);
+    double *in = reinterpret_cast<double *>(smem_raw);
+    double *st = in + kInSlots * 3 * RW;
+    size_t st_doubles = (size_t)3 * kStSlots * NF * RW;
+    if (st_doubles < 8 * (size_t)nthreads) st_doubles = 8 * (size_t)nthreads;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(st + st_doubles);
 
     if (tid == 0) {
-        for (int s = 0; s < kRing; s++) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < kInSlots; s++) mbar_init(&mbar[s], 1);
         mbar_init_fence();
     }
-    // exchange rows start as zeros so that never-published halo slots are at least finite
-    for (int i = tid; i < 2 * NX * RW; i += nthreads) exch[i] = 0.0;
+    // rings start as zeros so that never-written slots are finite
+    for (int i = tid; i < kInSlots * 3 * RW + 3 * kStSlots * NF * RW; i += nthreads) in[i] = 0.0;
     __syncthreads();
 
     // this CTA's share of the linearised (trial, strip, row) space
@@ -251,8 +376,8 @@ riet_step_kernel(const StepArgs A)
     const long long w1 = total * (blockIdx.x + 1) / gridDim.x;
     const int TXH = g.TX + 2 * kHalo;                 // columns a strip touches
     const uint32_t row_bytes = (uint32_t)(((TXH + 1) & ~1) * sizeof(double));
-    const bool active_thread = tid < TXH;
     const int cx = tid;                               // column within the strip, halo included
+    const bool col_in_strip = cx < TXH;
 
     long long seq = 0;   // rows consumed so far (ring slot / phase bookkeeping)
     int seg_no = 0;
@@ -267,7 +392,8 @@ riet_step_kernel(const StepArgs A)
 
         const int x0 = strip * g.TX;                  // first output column of the strip
         const int gx = x0 - kHalo + cx;               // this thread's lattice column (may be <0 or >=L: ghost)
-        const int xs = x0;                            // padded-layout column of cx = 0 is (x0 - 4) + 4
+        int gxm = gx % g.L; if (gxm < 0) gxm += g.L;  // ... wrapped, for the Philox cell index
+        const bool out_col = (cx >= kHalo) && (cx < kHalo + g.TX) && (gx < g.L);
         const double *inP = A.in + (long long)trial * g.trial_stride;
         const double *inW = inP + g.field_stride, *inO = inW + g.field_stride;
         double *outP = A.out + (long long)trial * g.trial_stride;
@@ -280,153 +406,167 @@ riet_step_kernel(const StepArgs A)
             if (g.wrap) { int r = j % g.L; if (r < 0) r += g.L; return r; }
             return j + kHalo;
         };
-        auto issue = [&](int j, long long n) { // thread 0: stream row j into ring slot n % kRing
-            const int slot = (int)(n % kRing);
-            double *dst = ring + (size_t)slot * 3 * RW + 2;
-            const long long off = prow(j) * g.Lp + xs;
+        auto issue = [&](int j, long long n) { // thread 0: stream row j into input slot n % kInSlots
+            const int slot = (int)(n & (kInSlots - 1));
+            double *dst = in + (size_t)slot * 3 * RW + 2;
+            const long long off = prow(j) * g.Lp + x0;
             mbar_expect_tx(&mbar[slot], 3 * row_bytes);
             bulk_g2s(dst, inP + off, row_bytes, &mbar[slot]);
             bulk_g2s(dst + RW, inW + off, row_bytes, &mbar[slot]);
             bulk_g2s(dst + 2 * RW, inO + off, row_bytes, &mbar[slot]);
         };
         if (tid == 0)
-            for (int k = 0; k < kPrefetch && jlo + k <= jhi; k++) issue(jlo + k, seq + k);
+            for (int k = 0; k <= kPrefetch && jlo + k <= jhi; k++) issue(jlo + k, seq + k);
 
-        // rolling register windows (own column); suffix = row relative to j
-        double Pp_m2 = 0, Pp_m1 = 0;
-        double W0_m4 = 0, W0_m3 = 0, W0_m2 = 0, W0_m1 = 0, O0_m4 = 0, O0_m3 = 0, O0_m2 = 0, O0_m1 = 0;
-        double Ps_m4 = 0, Ps_m3 = 0, Ps_m2 = 0;           // rho* (or P in DET)
-        double W1_m3 = 0, W1_m2 = 0, O1_m3 = 0, O1_m2 = 0, P1_m2 = 0, P1_m3 = 0;
-        double W2_m4 = 0, W2_m3 = 0, O2_m4 = 0, O2_m3 = 0, P2_m3 = 0, P2_m4 = 0;
-        double W3_m5 = 0, W3_m4 = 0, O3_m5 = 0, O3_m4 = 0, P3_m4 = 0, P3_m5 = 0;
+        // global row (mod L) of front 1 and physical row of the commit front, advanced per step
+        int r1 = (g.row0 + jlo - 1) % g.L; if (r1 < 0) r1 += g.L;
+        long long r4 = prow(jlo - 4);
+
+        // the few values that stay in registers (own column): rho* of rows j-4..j-2, the P stage
+        // values, and the running K1+2K2+2K3 sums of the rows between fronts 1 and 4
+        double Ps_m4 = 0, Ps_m3 = 0, Ps_m2 = 0;
+        double P1_m2 = 0, P2_m3 = 0, P3_m4 = 0;
         double aP_m4 = 0, aP_m3 = 0, aP_m2 = 0, aW_m4 = 0, aW_m3 = 0, aW_m2 = 0, aO_m4 = 0, aO_m3 = 0, aO_m2 = 0;
         ThreadStats tstat; tstat.clear();
+        // stage-ring slot offsets (in doubles) of rows j, j-1, j-2 (mod 3), rotated per step
+        int m0 = (int)(seq % kStSlots) * NF * RW, m1 = (int)((seq + 2) % kStSlots) * NF * RW, m2 = (int)((seq + 1) % kStSlots) * NF * RW;
+        double *const stc = st + 2 + cx;
+        const double *const inc = in + 2 + cx;
 
         for (int j = jlo; j <= jhi; j++, seq++) {
-            const int slot = (int)(seq % kRing), pslot = (int)((seq + kRing - 1) % kRing);
-            if (!timeout && !mbar_wait(&mbar[slot], (uint32_t)((seq / kRing) & 1))) timeout = true;
-            const double *rj = ring + (size_t)slot * 3 * RW + 2 + cx;   // row j, this column
-            const double *rp = ring + (size_t)pslot * 3 * RW + 2 + cx;  // row j-1
-            const double *xr = exch + (size_t)((seq + 1) & 1) * NX * RW + 2 + cx; // published at step j-1
-            double *xw = exch + (size_t)(seq & 1) * NX * RW + 2 + cx;
-
-            const bool en1 = (j - 1 >= ya - 3) && (j - 1 <= yb + 2);
-            const bool en2 = (j - 2 >= ya - 2) && (j - 2 <= yb + 1);
-            const bool en3 = (j - 3 >= ya - 1) && (j - 3 <= yb);
-            const bool en4 = (j - 4 >= ya) && (j - 4 <= yb - 1);
-
-            double Pn = 0, Wn = 0, On = 0;
-            if (active_thread) { Pn = rj[0]; Wn = rj[RW]; On = rj[2 * RW]; }
+            const int s0 = (int)(seq & (kInSlots - 1));
+            if (!timeout && !mbar_wait(&mbar[s0], (uint32_t)((seq / kInSlots) & 1))) timeout = true;
+            // stage-0 rows j, j-1, j-2, j-3, j-4 of this column
+            const double *i0 = inc + s0 * (3 * RW);
+            const double *i1 = inc + ((s0 + kInSlots - 1) & (kInSlots - 1)) * (3 * RW);
+            const double *i2 = inc + ((s0 + kInSlots - 2) & (kInSlots - 1)) * (3 * RW);
+            const double *i3 = inc + ((s0 + kInSlots - 3) & (kInSlots - 1)) * (3 * RW);
+            const double *i4 = inc + ((s0 + kInSlots - 4) & (kInSlots - 1)) * (3 * RW);
+            // stage rings: slot of the row a front works on, and of its vertical neighbours
+            // stage rings: row j-back lives in slot (q - back) mod 3, i.e. m0 (back 0,3), m1 (1,4), m2 (2,5)
+            auto sp = [&](int stage, int back) -> double * { // stage 1..3, row j-back
+                const int m = (back % 3 == 0) ? m0 : (back % 3 == 1) ? m1 : m2;
+                return stc + (stage - 1) * (kStSlots * NF * RW) + m;
+            };
 
             // ---- front 1: row j-1 : rho* and K1 -----------------------------------------------
-            double Ps_m1 = 0, W1_m1 = 0, O1_m1 = 0, P1_m1 = 0, aP_m1 = 0, aW_m1 = 0, aO_m1 = 0;
-            if (en1 && active_thread) {
-                const double pl = rp[-1], pr = rp[1];
-                double pstar = Pp_m1;
-                if (!DET) {
-                    const double alpha_i = c.dk.diffc * (Pp_m2 + Pn + pl + pr);
-                    if (!(alpha_i == 0 && Pp_m1 == 0)) {
-                        int lr = g.row0 + (j - 1); // global row of this cell
-                        lr %= g.L; if (lr < 0) lr += g.L;
-                        int lc = gx % g.L; if (lc < 0) lc += g.L;
-                        const uint32_t cell = (uint32_t)lr * (uint32_t)g.L + (uint32_t)lc;
-                        if (REPLAY) {
-                            ReplaySrc src;
-                            src.begin(A.replay_u + ((size_t)trial * g.L * g.L + cell) * A.stride, A.stride);
-                            pstar = dornic_cell<kRietkerk>(c.dk, src, alpha_i, Pp_m1);
-                            if (src.overflow_count() && cx >= kHalo && cx < kHalo + g.TX && gx < g.L && j - 1 >= ya && j - 1 < yb)
-                                atomicAdd(&A.counters[0], (unsigned long long)src.overflow_count());
-                        } else {
-                            PhiloxSrc src;
-                            src.begin(cell, A.trial0 + (uint32_t)trial, A.step, A.seed);
-                            pstar = dornic_cell<kRietkerk>(c.dk, src, alpha_i, Pp_m1);
-                        }
+            const double Pc = i1[0], Pu = i2[0], Pd = i0[0], Pl = i1[-1], Pr = i1[1];
+            double pstar = Pc;
+            if (!DET) {
+                const double alpha_i = c.dk.diffc * (Pu + Pd + Pl + Pr);
+                const bool live = !(alpha_i == 0 && Pc == 0) && col_in_strip; // skip rule R/:3759
+                const uint32_t cell = (uint32_t)r1 * (uint32_t)g.L + (uint32_t)gxm;
+                if (REPLAY) {
+                    if (live) {
+                        ReplaySrc src;
+                        src.begin(A.replay_u + ((size_t)trial * g.L * g.L + cell) * A.stride, A.stride);
+                        pstar = dornic_cell<kRietkerk>(c.dk, src, alpha_i, Pc);
+                        if (src.overflow_count() && out_col && j - 1 >= ya && j - 1 < yb)
+                            atomicAdd(&A.counters[0], (unsigned long long)src.overflow_count());
                     }
-                }
-                Ps_m1 = pstar;
-                if (!DORNIC_ONLY) {
-                    const F3 k1 = rhs<DET, STRICT>(c, a_rain, pstar, W0_m1, O0_m1,
-                                                   W0_m2, Wn, rp[RW - 1], rp[RW + 1],
-                                                   O0_m2, On, rp[2 * RW - 1], rp[2 * RW + 1],
-                                                   Pp_m2, Pn, pl, pr);
-                    P1_m1 = axpy<STRICT>(c.dt2, k1.p, pstar);
-                    W1_m1 = axpy<STRICT>(c.dt2, k1.w, W0_m1);
-                    O1_m1 = axpy<STRICT>(c.dt2, k1.o, O0_m1);
-                    aP_m1 = k1.p; aW_m1 = k1.w; aO_m1 = k1.o;
-                    xw[0] = W1_m1; xw[RW] = O1_m1;
-                    if (DET) xw[6 * RW] = P1_m1;
+                } else {
+                    // Gaussian regime of R/:3773-3789 inline and warp-cooperative; everything else
+                    // (Poisson mean <= 100 or Gamma shape <= 100: the extinction fringe) out of line.
+                    const uint32_t ptrial = A.trial0 + (uint32_t)trial;
+                    const double ziggy = c.dk.ll * Pc;
+                    const double mu1 = (-1.0 + 2.0 * alpha_i * c.dk.sigma2_1) + 1.0; // mu + 1.0 in the reference's order
+                    const bool gauss_n = live && ziggy > 100;
+                    const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
+                    double n_first, n_second;
+                    polar_pair_warp(fastp, cell, ptrial, A.step, A.seed, n_first, n_second);
+                    bool exact = live && !fastp;
+                    if (fastp) {
+                        double gru = mu1, nz = n_first;
+                        if (gauss_n) {
+                            const long long gauss = (long long)fma(n_first, sqrt(ziggy), ziggy);
+                            gru = mu1 + (double)gauss;
+                            nz = n_second;
+                        }
+                        if (gru > 100) pstar = fma(nz, sqrt(gru), gru) / c.dk.lambda;
+                        else exact = true;
+                    }
+                    if (exact) pstar = riet_cell_exact(c.dk, cell, ptrial, A.step, A.seed, alpha_i, Pc);
                 }
             }
             if (DORNIC_ONLY) {
-                if (en1 && active_thread && cx >= kHalo && cx < kHalo + g.TX && gx < g.L && j - 1 >= ya && j - 1 < yb)
-                    A.dornic_out[((size_t)trial * g.nrows + (j - 1)) * g.L + gx] = Ps_m1;
+                if (out_col && j - 1 >= ya && j - 1 < yb)
+                    A.dornic_out[((size_t)trial * g.nrows + (j - 1)) * g.L + gx] = pstar;
             } else {
-                // ---- front 2: row j-2 : K2 ---------------------------------------------------
-                double W2_m2 = 0, O2_m2 = 0, P2_m2 = 0;
-                if (en2 && active_thread) {
-                    const F3 k2 = rhs<DET, STRICT>(c, a_rain, P1_m2, W1_m2, O1_m2,
-                                                   W1_m3, W1_m1, xr[-1], xr[1],
-                                                   O1_m3, O1_m1, xr[RW - 1], xr[RW + 1],
-                                                   P1_m3, P1_m1, DET ? xr[6 * RW - 1] : 0.0, DET ? xr[6 * RW + 1] : 0.0);
-                    P2_m2 = axpy<STRICT>(c.dt2, k2.p, Ps_m2);
-                    W2_m2 = axpy<STRICT>(c.dt2, k2.w, W0_m2);
-                    O2_m2 = axpy<STRICT>(c.dt2, k2.o, O0_m2);
-                    aP_m2 = axpy<STRICT>(2.0, k2.p, aP_m2); aW_m2 = axpy<STRICT>(2.0, k2.w, aW_m2); aO_m2 = axpy<STRICT>(2.0, k2.o, aO_m2);
-                    xw[2 * RW] = W2_m2; xw[3 * RW] = O2_m2;
-                    if (DET) xw[7 * RW] = P2_m2;
+                double *s1w = sp(1, 1);
+                const double W0c = i1[RW], O0c = i1[2 * RW];
+                const F3 k1 = rhs<DET, STRICT>(c, a_rain, pstar, W0c, O0c,
+                                               i2[RW], i0[RW], i1[RW - 1], i1[RW + 1],
+                                               i2[2 * RW], i0[2 * RW], i1[2 * RW - 1], i1[2 * RW + 1],
+                                               Pu, Pd, Pl, Pr);
+                const double P1_m1 = axpy<STRICT>(c.dt2, k1.p, pstar);
+                const double W1_m1 = axpy<STRICT>(c.dt2, k1.w, W0c);
+                const double O1_m1 = axpy<STRICT>(c.dt2, k1.o, O0c);
+                s1w[0] = W1_m1; s1w[RW] = O1_m1;
+                if (DET) s1w[2 * RW] = P1_m1;
+
+                // ---- front 2: row j-2 : K2 (stage-1 rows j-3, j-2 from the ring, j-1 just made) ---
+                const double *s1c = sp(1, 2), *s1u = sp(1, 3);
+                double *s2w = sp(2, 2);
+                const F3 k2 = rhs<DET, STRICT>(c, a_rain, P1_m2, s1c[0], s1c[RW],
+                                               s1u[0], W1_m1, s1c[-1], s1c[1],
+                                               s1u[RW], O1_m1, s1c[RW - 1], s1c[RW + 1],
+                                               DET ? s1u[2 * RW] : 0.0, P1_m1, DET ? s1c[2 * RW - 1] : 0.0, DET ? s1c[2 * RW + 1] : 0.0);
+                const double P2_m2 = axpy<STRICT>(c.dt2, k2.p, Ps_m2);
+                const double W2_m2 = axpy<STRICT>(c.dt2, k2.w, i2[RW]);
+                const double O2_m2 = axpy<STRICT>(c.dt2, k2.o, i2[2 * RW]);
+                s2w[0] = W2_m2; s2w[RW] = O2_m2;
+                if (DET) s2w[2 * RW] = P2_m2;
+                aP_m2 = axpy<STRICT>(2.0, k2.p, aP_m2); aW_m2 = axpy<STRICT>(2.0, k2.w, aW_m2); aO_m2 = axpy<STRICT>(2.0, k2.o, aO_m2);
+
+                // ---- front 3: row j-3 : K3 ---------------------------------------------------------
+                const double *s2c = sp(2, 3), *s2u = sp(2, 4);
+                double *s3w = sp(3, 3);
+                const F3 k3 = rhs<DET, STRICT>(c, a_rain, P2_m3, s2c[0], s2c[RW],
+                                               s2u[0], W2_m2, s2c[-1], s2c[1],
+                                               s2u[RW], O2_m2, s2c[RW - 1], s2c[RW + 1],
+                                               DET ? s2u[2 * RW] : 0.0, P2_m2, DET ? s2c[2 * RW - 1] : 0.0, DET ? s2c[2 * RW + 1] : 0.0);
+                const double P3_m3 = axpy<STRICT>(c.dt, k3.p, Ps_m3);
+                const double W3_m3 = axpy<STRICT>(c.dt, k3.w, i3[RW]);
+                const double O3_m3 = axpy<STRICT>(c.dt, k3.o, i3[2 * RW]);
+                s3w[0] = W3_m3; s3w[RW] = O3_m3;
+                if (DET) s3w[2 * RW] = P3_m3;
+                aP_m3 = axpy<STRICT>(2.0, k3.p, aP_m3); aW_m3 = axpy<STRICT>(2.0, k3.w, aW_m3); aO_m3 = axpy<STRICT>(2.0, k3.o, aO_m3);
+
+                // ---- front 4: row j-4 : K4, commit -------------------------------------------------
+                const double *s3c = sp(3, 4), *s3u = sp(3, 5);
+                const F3 k4 = rhs<DET, STRICT>(c, a_rain, P3_m4, s3c[0], s3c[RW],
+                                               s3u[0], W3_m3, s3c[-1], s3c[1],
+                                               s3u[RW], O3_m3, s3c[RW - 1], s3c[RW + 1],
+                                               DET ? s3u[2 * RW] : 0.0, P3_m3, DET ? s3c[2 * RW - 1] : 0.0, DET ? s3c[2 * RW + 1] : 0.0);
+                double nP = axpy<STRICT>(c.dt6, aP_m4 + k4.p, Ps_m4);
+                double nW = axpy<STRICT>(c.dt6, aW_m4 + k4.w, i4[RW]);
+                double nO = axpy<STRICT>(c.dt6, aO_m4 + k4.o, i4[2 * RW]);
+                if (!DET) { nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo); }
+                if (out_col && j - 4 >= ya) { // (j-4 <= yb-1 always holds: j <= jhi)
+                    const long long ro = r4 * g.Lp;
+                    const int pc = gx + kHalo; // padded-layout column
+                    outP[ro + pc] = nP; outW[ro + pc] = nW; outO[ro + pc] = nO;
+                    if (gx < kHalo) { outP[ro + pc + g.L] = nP; outW[ro + pc + g.L] = nW; outO[ro + pc + g.L] = nO; }
+                    if (gx >= g.L - kHalo) { outP[ro + pc - g.L] = nP; outW[ro + pc - g.L] = nW; outO[ro + pc - g.L] = nO; }
+                    if (STATS) { tstat.add(0, nP); tstat.add(1, nW); tstat.add(2, nO); }
                 }
-                // ---- front 3: row j-3 : K3 ---------------------------------------------------
-                double W3_m3 = 0, O3_m3 = 0, P3_m3 = 0;
-                if (en3 && active_thread) {
-                    const F3 k3 = rhs<DET, STRICT>(c, a_rain, P2_m3, W2_m3, O2_m3,
-                                                   W2_m4, W2_m2, xr[2 * RW - 1], xr[2 * RW + 1],
-                                                   O2_m4, O2_m2, xr[3 * RW - 1], xr[3 * RW + 1],
-                                                   P2_m4, P2_m2, DET ? xr[7 * RW - 1] : 0.0, DET ? xr[7 * RW + 1] : 0.0);
-                    P3_m3 = axpy<STRICT>(c.dt, k3.p, Ps_m3);
-                    W3_m3 = axpy<STRICT>(c.dt, k3.w, W0_m3);
-                    O3_m3 = axpy<STRICT>(c.dt, k3.o, O0_m3);
-                    aP_m3 = axpy<STRICT>(2.0, k3.p, aP_m3); aW_m3 = axpy<STRICT>(2.0, k3.w, aW_m3); aO_m3 = axpy<STRICT>(2.0, k3.o, aO_m3);
-                    xw[4 * RW] = W3_m3; xw[5 * RW] = O3_m3;
-                    if (DET) xw[8 * RW] = P3_m3;
-                }
-                // ---- front 4: row j-4 : K4, commit -------------------------------------------
-                if (en4 && active_thread) {
-                    const F3 k4 = rhs<DET, STRICT>(c, a_rain, P3_m4, W3_m4, O3_m4,
-                                                   W3_m5, W3_m3, xr[4 * RW - 1], xr[4 * RW + 1],
-                                                   O3_m5, O3_m3, xr[5 * RW - 1], xr[5 * RW + 1],
-                                                   P3_m5, P3_m3, DET ? xr[8 * RW - 1] : 0.0, DET ? xr[8 * RW + 1] : 0.0);
-                    double nP = axpy<STRICT>(c.dt6, aP_m4 + k4.p, Ps_m4);
-                    double nW = axpy<STRICT>(c.dt6, aW_m4 + k4.w, W0_m4);
-                    double nO = axpy<STRICT>(c.dt6, aO_m4 + k4.o, O0_m4);
-                    if (!DET) { nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo); }
-                    if (cx >= kHalo && cx < kHalo + g.TX && gx < g.L) {
-                        const long long ro = prow(j - 4) * g.Lp;
-                        const int pc = gx + kHalo; // padded-layout column
-                        outP[ro + pc] = nP; outW[ro + pc] = nW; outO[ro + pc] = nO;
-                        if (gx < kHalo) { outP[ro + pc + g.L] = nP; outW[ro + pc + g.L] = nW; outO[ro + pc + g.L] = nO; }
-                        if (gx >= g.L - kHalo) { outP[ro + pc - g.L] = nP; outW[ro + pc - g.L] = nW; outO[ro + pc - g.L] = nO; }
-                        if (STATS) { tstat.add(0, nP); tstat.add(1, nW); tstat.add(2, nO); }
-                    }
-                }
-                // ---- shift the windows by one row ---------------------------------------------
-                W3_m5 = W3_m4; W3_m4 = W3_m3; O3_m5 = O3_m4; O3_m4 = O3_m3; P3_m5 = P3_m4; P3_m4 = P3_m3;
-                W2_m4 = W2_m3; W2_m3 = W2_m2; O2_m4 = O2_m3; O2_m3 = O2_m2; P2_m4 = P2_m3; P2_m3 = P2_m2;
-                W1_m3 = W1_m2; W1_m2 = W1_m1; O1_m3 = O1_m2; O1_m2 = O1_m1; P1_m3 = P1_m2; P1_m2 = P1_m1;
-                aP_m4 = aP_m3; aP_m3 = aP_m2; aP_m2 = aP_m1; aW_m4 = aW_m3; aW_m3 = aW_m2; aW_m2 = aW_m1;
-                aO_m4 = aO_m3; aO_m3 = aO_m2; aO_m2 = aO_m1;
-                Ps_m4 = Ps_m3; Ps_m3 = Ps_m2; Ps_m2 = Ps_m1;
-                W0_m4 = W0_m3; W0_m3 = W0_m2; O0_m4 = O0_m3; O0_m3 = O0_m2;
+                // ---- shift the register windows by one row -------------------------------------------
+                P3_m4 = P3_m3; P2_m3 = P2_m2; P1_m2 = P1_m1;
+                aP_m4 = aP_m3; aP_m3 = aP_m2; aP_m2 = k1.p; aW_m4 = aW_m3; aW_m3 = aW_m2; aW_m2 = k1.w;
+                aO_m4 = aO_m3; aO_m3 = aO_m2; aO_m2 = k1.o;
+                Ps_m4 = Ps_m3; Ps_m3 = Ps_m2; Ps_m2 = pstar;
             }
-            W0_m2 = W0_m1; W0_m1 = Wn; O0_m2 = O0_m1; O0_m1 = On;
-            Pp_m2 = Pp_m1; Pp_m1 = Pn;
+            r1 = (r1 + 1 == g.L) ? 0 : r1 + 1;
+            { const int t = m0; m0 = m2; m2 = m1; m1 = t; }
+            if (g.wrap) r4 = (r4 + 1 == g.L) ? 0 : r4 + 1; else r4 += 1;
 
             __syncthreads();
-            if (tid == 0 && j + kPrefetch <= jhi) issue(j + kPrefetch, seq + kPrefetch);
+            if (tid == 0 && j + kPrefetch + 1 <= jhi) issue(j + kPrefetch + 1, seq + kPrefetch + 1);
         }
 
         if (STATS && !DORNIC_ONLY) {
             PartialStats *rec = A.partials + (size_t)blockIdx.x * A.max_segs + (seg_no < A.max_segs ? seg_no : A.max_segs - 1);
-            flush_stats(tstat, 3, trial, rec, scratch, tid, nthreads);
+            flush_stats(tstat, 3, trial, rec, st, tid, nthreads);
         }
         seg_no++;
     }

@@ -20,7 +20,7 @@ static thread_local std::string g_create_error;
 struct tm_ctx {
     tm_params p{};
     Geom g{};
-    int device = 0, n_sm = 0;
+    int device = 0, n_sm = 0, riet_occ = 1;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double *buf[2] = {nullptr, nullptr};
@@ -96,7 +96,7 @@ static int alloc_all(tm_ctx *c)
     TM_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 4, c->stream));
     // launch geometry
     if (is_riet(c->p.model)) {
-        riet_launch_shape(g, c->n_sm, &c->grid, &c->max_segs);
+        riet_launch_shape(g, c->n_sm * c->riet_occ, &c->grid, &c->max_segs);
         c->n_records = c->grid * c->max_segs;
     } else {
         const long long ncell = (long long)g.nrows * g.L;
@@ -154,7 +154,6 @@ int tm_create_slab(const tm_params *p, int n_trials, int device, int row0, int n
     Geom &g = c->g;
     make_geom(*p, n_trials, row0, nrows, &g);
     c->a_host.assign(n_trials, p->a);
-    if (alloc_all(c) != TM_OK) return create_fail(c, TM_E_CUDA, "tm_create: device allocation failed");
 
     // opt in to the large dynamic shared memory the Rietkerk kernel needs
     if (is_riet(p->model)) {
@@ -175,7 +174,14 @@ int tm_create_slab(const tm_params *p, int n_trials, int device, int row0, int n
         TM_OPTIN((riet_step_kernel<true, true, false, true, false>), smem_d);
 #undef TM_OPTIN
         if (!ok) { cudaGetLastError(); return create_fail(c, TM_E_CUDA, "tm_create: cudaFuncSetAttribute(shared memory) failed"); }
+        int occ = 1; // resident CTAs per SM of the production variant: the persistent grid fills exactly that
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, riet_step_kernel<false, false, false, false, false>, g.nthreads,
+                                                          p->model == TM_MODEL_RIETKERK_DET ? smem_d : smem_s) != cudaSuccess || occ < 1) {
+            cudaGetLastError(); occ = 1;
+        }
+        c->riet_occ = occ;
     }
+    if (alloc_all(c) != TM_OK) return create_fail(c, TM_E_CUDA, "tm_create: device allocation failed");
     *out = c;
     return TM_OK;
 }
