@@ -68,6 +68,7 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
             StepArgs A{};
             A.g = g; A.c = riet_consts(*p);
             A.in = bufs[cur].data(); A.out = bufs[cur ^ 1].data();
+            A.rk = philox_keys(seed);
             A.a_trial = a_trial.data(); A.seed = seed; A.trial0 = trial0; A.step = step0 + s;
             A.replay_u = replay_u; A.stride = stride;
             A.partials = partials.data(); A.max_segs = max_segs; A.counters = counters; A.dornic_out = nullptr;

@@ -47,6 +47,7 @@ static inline RietConsts riet_consts(const tm_params &p)
     c.d = p.d; c.rc = p.rc; c.W0 = p.W0;
     c.eps = p.clamp_eps; c.lo = p.clamp_lo;
     c.dk = dornic_consts(p, p.a);
+    c.inv_lambda = 1.0 / c.dk.lambda;
     return c;
 }
 
@@ -66,6 +67,15 @@ static inline void choose_strips(int L, int *ns_out, int *tx_out, int *nthreads_
     *ns_out = bns; *tx_out = btx; *nthreads_out = bnt;
 }
 
+
+// the ten Philox4x32-10 round keys of a seed
+static inline PhiloxKeys philox_keys(unsigned long long seed)
+{
+    PhiloxKeys rk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { rk.k[r][0] = k0; rk.k[r][1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return rk;
+}
 
 // fills the layout part of Geom for a slab [row0,row0+nrows) of an L x L lattice
 static inline void make_geom(const tm_params &p, int n_trials, int row0, int nrows, Geom *g)

@@ -41,10 +41,10 @@ namespace tml {
 
 constexpr int kHalo = 4;            // RK4 dependency cone: 3 stencil applications + the Dornic alpha stencil
 #ifndef TM_MAXTHREADS
-#define TM_MAXTHREADS 384
+#define TM_MAXTHREADS 160
 #endif
 #ifndef TM_MINBLOCKS
-#define TM_MINBLOCKS 1
+#define TM_MINBLOCKS 4
 #endif
 constexpr int kMaxThreads = TM_MAXTHREADS;  // CTA size cap (one thread per strip column)
 constexpr int kMinBlocks = TM_MINBLOCKS;    // resident CTAs per SM the register budget is sized for
@@ -57,6 +57,7 @@ struct RietConsts {
     double rc;           // conversion c (DET: rc*gmax is recomputed as the reference does)
     double W0;
     double eps, lo;      // clamp
+    double inv_lambda;   // 1/dk.lambda (FAST arithmetic only)
     DornicConsts dk;
 };
 
@@ -65,6 +66,9 @@ struct Geom {
     int ns, TX, nthreads;        // strips, output columns per strip, CTA size
     long long field_stride, trial_stride; // in doubles
 };
+
+// Philox4x32-10 key schedule: round r uses (k0 + r*0x9E3779B9, k1 + r*0xBB67AE85)
+struct PhiloxKeys { uint32_t k[10][2]; };
 
 struct PartialStats { // one record per (CTA, segment)
     int trial, pad;
@@ -86,6 +90,7 @@ struct StepArgs {
     int max_segs;
     unsigned long long *counters; // [0] sampler/replay overflow, [1] pipeline timeouts
     double *dornic_out;           // DORNIC_ONLY: rho* [n_trials][nrows][L] (unpadded)
+    PhiloxKeys rk;                // the ten round keys of `seed` (host-computed)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -125,17 +130,15 @@ TM_D bool mbar_wait(uint64_t *b, uint32_t parity)
 }
 
 // ------------------------------------------------------------------------------------------
-// Reaction terms
+// Lean FP64 helpers for the FAST (non-STRICT) arithmetic: hardware seed + Newton steps, no
+// special-case branches, ~1 ulp.  Arguments are positive and far from the exponent limits.
+// STRICT mode never uses them (IEEE division / sqrt, bit-identical to the oracle).
 // ------------------------------------------------------------------------------------------
-struct F3 { double p, w, o; };
-
-// 1/b for the fast (non-STRICT) RK4 arithmetic, b > 0 and far from the exponent limits:
-// MUFU.RCP64H seed (rel. error 2^-23) + two Newton steps, ~1 ulp, no special-case branches.
-TM_D double rcp_pos(double b)
+TM_D double rcp_lean(double b)
 {
 #if defined(__CUDA_ARCH__)
     double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));   // MUFU.RCP64H, rel. error 2^-23
     r = fma(r, fma(-b, r, 1.0), r);
     r = fma(r, fma(-b, r, 1.0), r);
     return r;
@@ -143,6 +146,60 @@ TM_D double rcp_pos(double b)
     return 1.0 / b;
 #endif
 }
+TM_D double rsqrt_lean(double a)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a)); // MUFU.RSQ64H
+    const double h = 0.5 * a;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+#else
+    return 1.0 / sqrt(a);
+#endif
+}
+TM_D double sqrt_lean(double a)
+{
+#if defined(__CUDA_ARCH__)
+    const double y = rsqrt_lean(a);
+    double s = a * y;
+    s = fma(fma(-s, s, a), 0.5 * y, s);
+    return s;
+#else
+    return sqrt(a);
+#endif
+}
+// log(x) for x in (0,1] (the polar method's r2), same reduction and polynomial as log_pos but with
+// the lean reciprocal instead of an IEEE division.
+TM_D double log_lean(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+                 Lg7 = 1.479819860511658591e-01;
+    uint64_t b = d2u(x);
+    int k = (int)(b >> 52) - 1023;
+    const uint64_t mant = b & 0x000FFFFFFFFFFFFFull;
+    if (mant > 0x6A09E667F3BCCull) { b = mant | 0x3FE0000000000000ull; k += 1; }
+    else                           { b = mant | 0x3FF0000000000000ull; }
+    const double f = u2d(b) - 1.0;
+    const double dk = (double)k;
+    const double s = f * rcp_lean(2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
+    const double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f);
+}
+
+// ------------------------------------------------------------------------------------------
+// Reaction terms
+// ------------------------------------------------------------------------------------------
+struct F3 { double p, w, o; };
 
 // f_2Dor R/:2376-2382 (DET=false) / f_2D R/:1730-1737 (DET=true); STRICT keeps the reference's
 // operation order so results are bit-identical to the oracle; the fast form shares one reciprocal.
@@ -163,7 +220,7 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
         f.o = a - c.alpha * (P + c.K2 * c.W0) / (P + c.K2) * O + c.Do * (Ou + Od + Ol + Or_ - 4 * O);
     } else {
         const double wk = W + c.K1, pk = P + c.K2;
-        const double r = rcp_pos(wk * pk);
+        const double r = rcp_lean(wk * pk);
         const double q = (W * P) * (pk * r);                 // W P / (W + K1)
         const double infil = c.alpha * (P + c.K2W0) * (wk * r) * O;
         const double lapW = fma(-4.0, W, (Wu + Wd) + (Wl + Wr));
@@ -182,14 +239,12 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
 template <bool STRICT>
 TM_D double axpy(double a, double x, double y) { return STRICT ? (y + a * x) : fma(a, x, y); }
 
-// `if (v < eps && v >= lo) v = 0` (R/:4176) with eps > 0 >= lo, on the bit patterns: for v >= +0 the
-// IEEE order is the integer order; for v < 0 the magnitude must not exceed |lo|.  NaN is kept.
+// `if (v < eps && v >= lo) v = 0` (R/:4176): the first test almost never holds in live cells, so the
+// second is only evaluated behind it.
 TM_D double clamp_small(double v, double eps, double lo)
 {
-    const uint64_t b = d2u(v), mag = b & 0x7FFFFFFFFFFFFFFFull;
-    const bool neg = (b >> 63) != 0;
-    const bool hit = neg ? (mag <= (d2u(lo) & 0x7FFFFFFFFFFFFFFFull)) : (mag < d2u(eps));
-    return hit ? 0.0 : v;
+    if (v < eps) { if (v >= lo) v = 0.0; }
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -255,7 +310,7 @@ TM_HD size_t riet_smem_bytes(int nthreads, bool det)
     const size_t nf = det ? 3 : 2;
     size_t st = 3 * kStSlots * nf * RW;
     if (st < 8 * (size_t)nthreads) st = 8 * (size_t)nthreads;
-    return sizeof(double) * (kInSlots * 3 * RW + st) + sizeof(uint64_t) * kInSlots + 128;
+    return sizeof(double) * (kInSlots * 3 * RW + st) + sizeof(uint64_t) * kInSlots + sizeof(uint32_t) * 32 * (kMaxThreads / 32) + 128;
 }
 
 // The exact-sampler branches (Poisson mean <= 100, Gamma shape <= 100: extinction fringe only) are
@@ -275,12 +330,20 @@ double riet_cell_exact(DornicConsts dk, uint32_t cell, uint32_t trial, uint32_t 
 }
 
 // One candidate of the polar method: uniforms 2k, 2k+1 of the cell's stream (= Philox block k).
-TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t k, uint32_t key0, uint32_t key1,
+TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t k, const PhiloxKeys &rk,
                           double &x, double &y, double &r2)
 {
-    const u32x4 o = philox4x32_10(cell, trial, step, k, key0, key1);
-    x = 2.0 * u52(o.x, o.y) - 1.0;
-    y = 2.0 * u52(o.z, o.w) - 1.0;
+    uint32_t c0 = cell, c1 = trial, c2 = step, c3 = k;
+#pragma unroll
+    for (int r = 0; r < 10; r++) { // same rounds as philox4x32_10(), keys read from the schedule
+        uint32_t h0, l0, h1, l1;
+        mulhilo32(0xD2511F53u, c0, h0, l0);
+        mulhilo32(0xCD9E8D57u, c2, h1, l1);
+        c0 = h1 ^ c1 ^ rk.k[r][0]; c1 = l1;
+        c2 = h0 ^ c3 ^ rk.k[r][1]; c3 = l0;
+    }
+    x = 2.0 * u52(c0, c1) - 1.0;
+    y = 2.0 * u52(c2, c3) - 1.0;
     r2 = fma(x, x, y * y);
     return !(r2 > 1.0 || r2 == 0.0);
 }
@@ -292,16 +355,16 @@ TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t
 // takes the lowest accepted block -- exactly the pair a sequential loop over its stream would have
 // accepted, in ~2 warp passes instead of ~3.1 with divergent per-lane loops.
 // Must be called by all 32 lanes of a warp (trial/step/seed warp-uniform).
-TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t step, unsigned long long seed,
-                          double &n_first, double &n_second)
+template <bool STRICT>
+TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t step, const PhiloxKeys &rk,
+                          uint32_t *warp_scratch, double &n_first, double &n_second)
 {
-    const uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
     double x = 0.5, y = 0.5, r2 = 0.5;
     bool ok = true;
 #if defined(__CUDA_ARCH__)
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    if (need) ok = polar_candidate(cell, trial, step, 0, key0, key1, x, y, r2);
+    if (need) ok = polar_candidate(cell, trial, step, 0, rk, x, y, r2);
     unsigned pending = __ballot_sync(full, !ok);
     uint32_t kbase = 1;
     while (pending != 0 && kbase < (uint32_t)kMaxReject) {
@@ -310,16 +373,19 @@ TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t ste
         const int per = 1 << lg;
         const int fi = lane >> lg;                            // which rejected lane this lane helps
         const bool helper = fi < F;
-        const int src = helper ? (int)__fns(pending, 0, fi + 1) : lane;
-        const uint32_t cell_s = __shfl_sync(full, cell, src);
+        // compact the rejected lanes' cells by rank (warp-private scratch), helpers pick theirs up
+        const int rank = __popc(pending & ((1u << lane) - 1u));
+        if (!ok) warp_scratch[rank] = cell;
+        __syncwarp(full);
+        const uint32_t cell_s = warp_scratch[helper ? fi : 0];
+        __syncwarp(full);
         double hx = 0.5, hy = 0.5, hr2 = 2.0;
         bool hok = false;
-        if (helper) hok = polar_candidate(cell_s, trial, step, kbase + (uint32_t)(lane & (per - 1)), key0, key1, hx, hy, hr2);
+        if (helper) hok = polar_candidate(cell_s, trial, step, kbase + (uint32_t)(lane & (per - 1)), rk, hx, hy, hr2);
         const unsigned okmask = __ballot_sync(full, hok);
         int from = lane;
         bool got = false;
         if (!ok) {
-            const int rank = __popc(pending & ((1u << lane) - 1u));
             const unsigned mine = ((per == 32) ? full : ((1u << per) - 1u)) << (rank << lg);
             const unsigned hit = okmask & mine;
             if (hit) { from = __ffs((int)hit) - 1; got = true; }
@@ -332,11 +398,13 @@ TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t ste
 #else
     if (need) {
         uint32_t k = 0;
-        do { ok = polar_candidate(cell, trial, step, k, key0, key1, x, y, r2); } while (!ok && ++k < (uint32_t)kMaxReject);
+        do { ok = polar_candidate(cell, trial, step, k, rk, x, y, r2); } while (!ok && ++k < (uint32_t)kMaxReject);
     }
 #endif
     if (!ok) { x = 0.5; y = 0.5; r2 = 0.5; } // bound reached (never with genuine uniforms)
-    const double mult = sqrt(-2.0 * log_pos(r2) / r2);
+    double mult;
+    if (STRICT) mult = sqrt(-2.0 * log_pos(r2) / r2);            // LS:1832
+    else        mult = sqrt_lean(-2.0 * log_lean(r2) * rcp_lean(r2));
     n_second = x * mult;
     n_first = y * mult;
 }
@@ -361,6 +429,7 @@ riet_step_kernel(const StepArgs A)
     size_t st_doubles = (size_t)3 * kStSlots * NF * RW;
     if (st_doubles < 8 * (size_t)nthreads) st_doubles = 8 * (size_t)nthreads;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(st + st_doubles);
+    uint32_t *wscratch = reinterpret_cast<uint32_t *>(mbar + kInSlots) + 32 * (tid >> 5); // warp-private
 
     if (tid == 0) {
         for (int s = 0; s < kInSlots; s++) mbar_init(&mbar[s], 1);
@@ -397,7 +466,6 @@ riet_step_kernel(const StepArgs A)
         const double *inP = A.in + (long long)trial * g.trial_stride;
         const double *inW = inP + g.field_stride, *inO = inW + g.field_stride;
         double *outP = A.out + (long long)trial * g.trial_stride;
-        double *outW = outP + g.field_stride, *outO = outW + g.field_stride;
         const double a_rain = A.a_trial[trial];
         const int jlo = ya - kHalo, jhi = yb + kHalo - 1;
 
@@ -473,16 +541,17 @@ riet_step_kernel(const StepArgs A)
                     const bool gauss_n = live && ziggy > 100;
                     const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
                     double n_first, n_second;
-                    polar_pair_warp(fastp, cell, ptrial, A.step, A.seed, n_first, n_second);
+                    polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, n_first, n_second);
                     bool exact = live && !fastp;
                     if (fastp) {
                         double gru = mu1, nz = n_first;
                         if (gauss_n) {
-                            const long long gauss = (long long)fma(n_first, sqrt(ziggy), ziggy);
+                            const long long gauss = (long long)fma(n_first, STRICT ? sqrt(ziggy) : sqrt_lean(ziggy), ziggy);
                             gru = mu1 + (double)gauss;
                             nz = n_second;
                         }
-                        if (gru > 100) pstar = fma(nz, sqrt(gru), gru) / c.dk.lambda;
+                        if (gru > 100) pstar = STRICT ? fma(nz, sqrt(gru), gru) / c.dk.lambda
+                                                      : fma(nz, sqrt_lean(gru), gru) * c.inv_lambda;
                         else exact = true;
                     }
                     if (exact) pstar = riet_cell_exact(c.dk, cell, ptrial, A.step, A.seed, alpha_i, Pc);
@@ -543,11 +612,10 @@ riet_step_kernel(const StepArgs A)
                 double nO = axpy<STRICT>(c.dt6, aO_m4 + k4.o, i4[2 * RW]);
                 if (!DET) { nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo); }
                 if (out_col && j - 4 >= ya) { // (j-4 <= yb-1 always holds: j <= jhi)
-                    const long long ro = r4 * g.Lp;
-                    const int pc = gx + kHalo; // padded-layout column
-                    outP[ro + pc] = nP; outW[ro + pc] = nW; outO[ro + pc] = nO;
-                    if (gx < kHalo) { outP[ro + pc + g.L] = nP; outW[ro + pc + g.L] = nW; outO[ro + pc + g.L] = nO; }
-                    if (gx >= g.L - kHalo) { outP[ro + pc - g.L] = nP; outW[ro + pc - g.L] = nW; outO[ro + pc - g.L] = nO; }
+                    double *po = outP + (r4 * g.Lp + (gx + kHalo)); // padded-layout column gx + 4
+                    po[0] = nP; po[g.field_stride] = nW; po[2 * g.field_stride] = nO;
+                    if (gx < kHalo) { po[g.L] = nP; po[g.field_stride + g.L] = nW; po[2 * g.field_stride + g.L] = nO; }
+                    if (gx >= g.L - kHalo) { po[-g.L] = nP; po[g.field_stride - g.L] = nW; po[2 * g.field_stride - g.L] = nO; }
                     if (STATS) { tstat.add(0, nP); tstat.add(1, nW); tstat.add(2, nO); }
                 }
                 // ---- shift the register windows by one row -------------------------------------------

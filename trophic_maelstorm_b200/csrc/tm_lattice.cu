@@ -166,8 +166,8 @@ int tm_create_slab(const tm_params *p, int n_trials, int device, int row0, int n
         TM_OPTIN((riet_step_kernel<false, true, false, true, false>), smem_s);
         TM_OPTIN((riet_step_kernel<false, false, true, true, false>), smem_s);
         TM_OPTIN((riet_step_kernel<false, true, true, true, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, false, false, false, true>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, false, true, false, true>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, false, false, true>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, true, false, true>), smem_s);
         TM_OPTIN((riet_step_kernel<true, false, false, false, false>), smem_d);
         TM_OPTIN((riet_step_kernel<true, false, false, true, false>), smem_d);
         TM_OPTIN((riet_step_kernel<true, true, false, false, false>), smem_d);
@@ -306,6 +306,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
         StepArgs A{};
         A.g = g; A.c = riet_consts(p);
         A.in = c->buf[c->cur]; A.out = c->buf[c->cur ^ 1];
+        A.rk = philox_keys(c->seed);
         A.a_trial = c->a_dev; A.seed = c->seed; A.trial0 = c->trial0; A.step = (unsigned int)c->step;
         A.replay_u = c->replay_dev; A.stride = stride;
         A.partials = c->partials; A.max_segs = c->max_segs; A.counters = c->counters; A.dornic_out = c->dornic_dev;
@@ -317,7 +318,8 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             if (c->strict) { if (stats) TM_LAUNCH(true, true, false, true, false); else TM_LAUNCH(true, true, false, false, false); }
             else           { if (stats) TM_LAUNCH(true, false, false, true, false); else TM_LAUNCH(true, false, false, false, false); }
         } else if (dornic_only) {
-            if (replay) TM_LAUNCH(false, false, true, false, true); else TM_LAUNCH(false, false, false, false, true);
+            // the Dornic-only entry point is a checking aid: always the STRICT (IEEE) arithmetic
+            if (replay) TM_LAUNCH(false, true, true, false, true); else TM_LAUNCH(false, true, false, false, true);
         } else if (replay) {
             if (c->strict) TM_LAUNCH(false, true, true, true, false); else TM_LAUNCH(false, false, true, true, false);
         } else if (c->strict) {
