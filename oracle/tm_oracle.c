@@ -538,6 +538,14 @@ static int rk4_3field(const tmo_params *p, double *S, int full_rhs)
 /* 6. One full time step                                                              */
 /* ================================================================================== */
 
+/* RK4 alone on a 3-field state: full_rhs = 0 -> RK4_Integrate_Stochastic_1Sp / f_2Dor (R/:2389),
+ * 1 -> RK4_Integrate / f_2D (R/:1753). */
+int tmo_rk4(const tmo_params *p, double *f, int full_rhs)
+{
+    if (!p || !f || p->L < 1) return -1;
+    return rk4_3field(p, f, full_rhs);
+}
+
 int tmo_dornic_only(const tmo_params *p, tmo_rng *rng, const double *prev, double *out)
 {
     if (!p || !rng || !prev || !out || p->L < 1 || p->model == TMO_MODEL_RIETKERK_DET) return -1;

@@ -102,6 +102,9 @@ int tmo_step(const tmo_params *p, tmo_rng *rng, double *f);
 /* Dornic sub-step only (a2/a4): writes rho* into out[L*L] from field prev[L*L]. */
 int tmo_dornic_only(const tmo_params *p, tmo_rng *rng, const double *prev, double *out);
 
+/* RK4 sub-step alone (a6 / a12) on f[3][L*L]: full_rhs = 0 f_2Dor (R/:2389), 1 f_2D (R/:1753). */
+int tmo_rk4(const tmo_params *p, double *f, int full_rhs);
+
 /* reductions (a8): sequential left-to-right sum / L^2 and #{rho>0}; R/:1211,1245 P/:123,145 */
 double tmo_mean(const double *x, int64_t n);
 double tmo_occupied(const double *x, int64_t n);

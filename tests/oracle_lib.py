@@ -47,6 +47,7 @@ def oracle():
         L.tmo_occupied.restype = C.c_double
         L.tmo_occupied.argtypes = [dp, C.c_int64]
         L.tmo_step.argtypes = [C.POINTER(OParams), C.POINTER(ORng), dp]
+        L.tmo_rk4.argtypes = [C.POINTER(OParams), dp, C.c_int]
         L.tmo_dornic_only.argtypes = [C.POINTER(OParams), C.POINTER(ORng), dp, dp]
         L.tmo_u52_from_bits.restype = C.c_double
         L.tmo_u52_from_bits.argtypes = [C.c_uint64]
