@@ -1,0 +1,161 @@
+"""The C++ host layer (trophic_maelstorm_b200/host: the reference's runner signatures over the C ABI)
+on the GPU: (1) its bookkeeping reproduces the reference's row assembly exactly, (2) its ensembles
+agree with ensembles of the unmodified reference (tests/golden/ens_*.npz) within confidence bounds."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import trophic_maelstorm_b200 as tm
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def host():
+    tm.lib()  # libtm_lattice.so first (libtm_host.so links against it)
+    h = C.CDLL(os.path.join(ROOT, "trophic_maelstorm_b200", "libtm_host.so"))
+    h.tmh_set_options.argtypes = [C.c_int, C.c_ulonglong, C.c_int, C.c_char_p]
+    h.tmh_dp_run.argtypes = [C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, dp, dp, C.c_int, dp, C.c_int]
+    h.tmh_riet_run.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.c_int, dp, C.c_int, C.c_char_p, dp, C.c_int]
+    h.tmh_dp_sweep.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_double] * 9 + [C.c_int]
+    return h
+
+
+def dp_rows(host, cubic, L, params, rho0, t_meas, r, seed):
+    host.tmh_set_options(0, seed, 0, None)
+    a, b, c, D, sigma, dt, dx = [float(x) for x in params]
+    rows = np.zeros((4096, 9))
+    tmv = np.ascontiguousarray(t_meas, dtype=np.float64)
+    r0 = np.ascontiguousarray(rho0, dtype=np.float64)
+    n = host.tmh_dp_run(int(cubic), L, a, b, c, D, sigma, dt, dx, r, O.ptr(r0), O.ptr(tmv), len(tmv), O.ptr(rows), 4096)
+    assert n > 0, n
+    off = 3 if cubic else 2
+    return rows[:n, off:off + 6]  # t, mean, var, surv, active, last
+
+
+def test_dp_runner_bookkeeping_matches_reference_semantics(host):
+    """Same seed => same GPU trajectories; the rows must equal the reference's replicate-order
+    accumulation (P/:1074-1098, var_mean_incremental_surv_runs P/:173) applied to them."""
+    L, r, seed = 32, 5, 4242
+    params = (1.0548, 1.0, 0.0, 0.25, 2 ** 0.5, 0.1, 1.0)
+    t_meas = np.array([1.5, 2.0, 3.0, 5.0])
+    rho0 = np.ones(L * L)
+    rows = dp_rows(host, False, L, params, rho0, t_meas, r, seed)
+    # independent replay of the same trials through the ctypes binding
+    lat = tm.Lattice(tm.dp_params(L, a=params[0], b=params[1], D=params[3], sigma=params[4], dt=0.1, dx=1.0), r)
+    lat.seed(seed)
+    lat.upload(np.ones((r, 1, L, L)))
+    tot = int(1.0 / 0.1) + 1 + len(t_meas)
+    series = np.zeros((r, tot, 2)); s = 0
+    t, index = 0.0, 0
+    while t < t_meas[-1] + 0.1:
+        if t <= 1.0 or (index < len(t_meas) and t_meas[index] - 0.05 <= t < t_meas[index] + 0.05):
+            st = lat.measure()
+            for j in range(r):
+                series[j, s] = (st[j].active[0], st[j].mean[0])
+            s += 1
+            if t > 1.0:
+                index += 1
+        lat.step(1)
+        t += 0.1
+    lat.close()
+    acc = np.zeros((tot, 5))
+    acc[:, 1] = series[0, :, 1]; acc[:, 4] = series[0, :, 0]; acc[:, 3] = (series[0, :, 1] > 0)
+    for j in range(1, r):
+        rep = np.ascontiguousarray(series[j])
+        O.oracle().tmo_var_mean_incremental_surv_runs(O.ptr(acc), O.ptr(rep), tot, j)
+    assert np.array_equal(rows[:, 1], acc[:, 1]) and np.array_equal(rows[:, 2], acc[:, 2])
+    assert np.array_equal(rows[:, 3], acc[:, 3]) and np.array_equal(rows[:, 4], acc[:, 4])
+    assert np.allclose(rows[11:, 0], t_meas)
+
+
+def z_scores(ref_series, col, gpu_mean, gpu_n):
+    """per-row z of (gpu ensemble mean - reference ensemble mean), surviving replicates only"""
+    z = []
+    for k in range(ref_series.shape[1]):
+        alive = ref_series[:, k, -1] > 0
+        x = ref_series[alive, k, col]
+        if x.size < 8 or gpu_n[k] < 8:
+            continue
+        se = x.std(ddof=1) * np.sqrt(1.0 / x.size + 1.0 / gpu_n[k])
+        if se == 0.0:  # deterministic row (t = 0): must agree outright
+            assert abs(gpu_mean[k] - x.mean()) <= 1e-12 * abs(x.mean())
+            continue
+        z.append((gpu_mean[k] - x.mean()) / se)
+    return np.array(z)
+
+
+@pytest.mark.parametrize("name,cubic", [("ens_dp_plain", False), ("ens_dp_cubic", True)])
+def test_dp_ensemble_matches_reference(host, name, cubic):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    L, r = int(g["L"]), 256
+    rho0 = np.full(L * L, 0.25 if cubic else 1.0)
+    rows = dp_rows(host, cubic, L, g["params"], rho0, g["t_meas"], r, seed=777)
+    ref = g["series"]                                  # [n_ref][rows][t, mean, active]
+    assert rows.shape[0] == ref.shape[1]
+    z = z_scores(ref, 1, rows[:, 1], rows[:, 3])
+    # rows are strongly correlated in time, so bound the extremes rather than count 5 % exceedances:
+    # P(max |z| > 4.5) is ~1e-4 even for 60 independent rows
+    assert np.abs(z).max() < 4.5 and np.abs(z).mean() < 1.6, (np.abs(z).max(), np.abs(z).mean())
+    # survival probability at the last row: two-proportion z-test
+    p_ref = (ref[:, -1, 2] > 0).mean(); p_gpu = rows[-1, 3] / r
+    pool = (p_ref * ref.shape[0] + p_gpu * r) / (ref.shape[0] + r)
+    se = max(np.sqrt(pool * (1 - pool) * (1.0 / ref.shape[0] + 1.0 / r)), 1e-9)
+    assert abs(p_ref - p_gpu) / se < 4.0 or pool in (0.0, 1.0)
+    if not cubic:
+        # DP decay exponent delta: slope of log<rho> vs log t over t in [5, 100]; CI by bootstrap of the reference
+        t = rows[:, 0]; w = (t >= 5.0) & (rows[:, 1] > 0)
+        slope = lambda y: np.polyfit(np.log(t[w]), np.log(y[w]), 1)[0]
+        d_gpu = slope(rows[:, 1])
+        rng = np.random.default_rng(0)
+        boots = []
+        for _ in range(200):
+            pick = rng.integers(0, ref.shape[0], ref.shape[0])
+            m = np.array([ref[pick][ref[pick][:, k, 2] > 0][:, k, 1].mean() for k in range(ref.shape[1])])
+            boots.append(slope(m))
+        d_ref, se = np.mean(boots), np.std(boots) * np.sqrt(1 + ref.shape[0] / r)
+        assert abs(d_gpu - d_ref) < 3.5 * se + 0.02, (d_gpu, d_ref, se)
+        assert -0.75 < d_gpu < -0.2      # 2-D DP: delta ~ 0.45 near criticality
+
+
+def test_rietkerk_ensemble_matches_reference(host):
+    g = np.load(os.path.join(GOLD, "ens_rietkerk.npz"))
+    L, r = int(g["L"]), 96
+    ref = g["series"]                                  # [n_ref][rows][t, <W>, <O>, <P>, active]
+    init = np.ascontiguousarray(np.tile(g["init"].reshape(1, -1), (r, 1)))
+    tmv = np.ascontiguousarray(g["t_meas"]); ft = np.zeros(1)
+    rows = np.zeros((256, 10))
+    host.tmh_set_options(0, 99, 0, None)
+    n = host.tmh_riet_run(L, float(g["a"]), float(g["dt"]), r, O.ptr(init), O.ptr(tmv), len(tmv), O.ptr(ft), 0, None, O.ptr(rows), 256)
+    assert n == ref.shape[1]
+    rows = rows[:n]                                    # a, r, L, t, <W>, <O>, <P>, var, surv, active
+    nsurv = rows[:, 8]
+    zP = z_scores(ref[:, :, [0, 3, 4]], 1, rows[:, 6], nsurv)
+    assert np.abs(zP[1:]).max() < 4.5, np.abs(zP).max()
+    # deterministic-dominated water fields: means agree to a relative 1e-4 (noise enters only through P)
+    np.testing.assert_allclose(rows[:, 4], ref[:, :, 1].mean(axis=0), rtol=2e-4)
+    np.testing.assert_allclose(rows[:, 5], ref[:, :, 2].mean(axis=0), rtol=2e-4)
+    # active-site counts: ensemble means within bounds
+    zA = z_scores(ref[:, :, [0, 4, 4]], 1, rows[:, 9], nsurv)
+    assert np.abs(zA[1:]).max() < 4.5, np.abs(zA).max()
+
+
+def test_dp_sweep_writes_reference_csv(host, tmp_path):
+    """first_order_critical_exp_delta (P/:2422): file name grammar and column layout of the sweep CSV."""
+    host.tmh_set_options(0, 5, 0, str(tmp_path).encode())
+    rc = host.tmh_dp_sweep(1, 32, 2, 3.0, -0.72, -0.70, -2.0, 1.0, 6.25, 1.0, 0.1, 2.5, 2)
+    assert rc == 0
+    path = tmp_path / "Data" / "SPDP" / "1stOrder_P_c_Delta_DP_G_32_T_3_dt_0.1_c_1_a1_-0.72_a2_-0.7_dx_2.5_Sig_1_R_2.csv"
+    assert path.exists(), list((tmp_path / "Data" / "SPDP").iterdir())
+    lines = path.read_text().splitlines()
+    assert lines[0] == " a , c , L,  t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt "
+    bins = O.oracle().tmo_logarithm10_time_bins(3.0, 0.1, O.ptr(np.zeros(64)), 64)
+    assert len(lines) - 1 == 2 * (11 + bins)
+    first = lines[1].split(",")
+    assert len(first) == 9 and float(first[0]) == -0.72 and float(first[2]) == 32 and float(first[4]) == 0.25

@@ -1,0 +1,426 @@
+// tm_host.cpp -- see tm_host.h.  Bookkeeping follows the reference line by line (citations inline);
+// all numerics happen behind the C ABI on the GPU.
+#include "tm_host.h"
+#include "../../include/tm_lattice.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <sys/stat.h>
+
+namespace tm_b200 {
+
+using std::vector;
+
+Options &options()
+{
+    static Options o = [] {
+        Options x;
+        if (const char *e = getenv("TM_DEVICE")) x.device = atoi(e);
+        if (const char *e = getenv("TM_SEED")) x.seed = strtoull(e, nullptr, 0);
+        if (const char *e = getenv("TM_STRICT")) x.strict = atoi(e) != 0;
+        if (const char *e = getenv("TM_DATA_ROOT")) x.data_root = e;
+        return x;
+    }();
+    return o;
+}
+
+namespace {
+struct Ctx { // RAII over tm_ctx; errors become exceptions like the reference's exit() paths
+    tm_ctx *c = nullptr;
+    Ctx(const tm_params &p, int n_trials)
+    {
+        if (tm_create(&p, n_trials, options().device, &c) != TM_OK)
+            throw std::runtime_error(std::string("tm_create: ") + tm_last_error(nullptr));
+        tm_set_strict(c, options().strict ? 1 : 0);
+    }
+    ~Ctx() { tm_destroy(c); }
+    void ck(int rc, const char *what) { if (rc != TM_OK) throw std::runtime_error(std::string(what) + ": " + tm_last_error(c)); }
+};
+
+void mkdirs(const std::string &path)
+{
+    std::string cur;
+    for (size_t i = 0; i < path.size(); i++) {
+        cur += path[i];
+        if (path[i] == '/' || i + 1 == path.size()) mkdir(cur.c_str(), 0777);
+    }
+}
+
+// The reference decides what happens at each step from the accumulated double `t` (t += dt).
+// Plan = for every loop iteration k: is it a measurement row, and which t_meas index it matched.
+struct StepPlan { vector<int> measure; vector<int> window; vector<double> t; };
+
+// DP schedule, P/:1003-1025: measure every step while t <= 1, then at the t_meas windows.
+StepPlan plan_dp(const vector<double> &t_meas, double dt)
+{
+    StepPlan p;
+    const double t_max = t_meas.back();
+    double t = 0; size_t index = 0;
+    while (t < t_max + dt) {
+        const bool win = index < t_meas.size() && t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0;
+        const bool meas = (t <= 1.0) || win;
+        p.measure.push_back(meas); p.window.push_back(win ? (int)index : -1); p.t.push_back(t);
+        if (meas && t > 1.0) index += 1;
+        t += dt;
+    }
+    return p;
+}
+} // namespace
+
+// ---- bookkeeping ---------------------------------------------------------------------------------
+
+vector<double> linspace(double start, double end, int num) // P/:254-278
+{
+    vector<double> v;
+    if (num == 0) return v;
+    if (num == 1) { v.push_back(start); return v; }
+    const double delta = (end - start) / (num - 1);
+    for (int i = 0; i < num - 1; ++i) v.push_back(start + delta * i);
+    v.push_back(end);
+    return v;
+}
+
+vector<double> logarithm10_time_bins(double t_max, double dt) // P/:336-378
+{
+    vector<double> logspaced;
+    if (t_max <= 1) return logspaced;
+    const double tend_one = static_cast<double>(floor(log10(t_max) * 10.)) / 10.0;
+    double power = 0.0;
+    while (power <= tend_one) {
+        const double t_raw = pow(10, power);
+        double t_fin = static_cast<int>(t_raw / dt) * dt;
+        if (t_fin <= 1.0) t_fin = t_fin + dt;
+        if (logspaced.size() > 0 && t_fin != logspaced[logspaced.size() - 1]) logspaced.push_back(t_fin);
+        else if (logspaced.size() == 0) logspaced.push_back(t_fin);
+        power += 0.04;
+    }
+    const int n = (int)logspaced.size();
+    for (int i = n - 1; i > 0; i--)
+        if (logspaced[i] < logspaced[i - 1] + dt / 2.0) logspaced.erase(logspaced.begin() + i);
+    return logspaced;
+}
+
+void var_mean_incremental_surv_runs(double A[][5], double X[][2], int size) // P/:173-208
+{
+    for (int i = 0; i < size; i++) {
+        int r = A[i][3] + 1;
+        if (X[i][0] == 0.0) break;
+        const double mean_prev = A[i][1];
+        if (A[i][3] == 0.0) {
+            A[i][1] = X[i][1]; A[i][2] = 0.0; A[i][4] = X[i][0];
+        } else {
+            A[i][1] = (X[i][1] + (r - 1) * A[i][1]) / r;
+            A[i][4] = (X[i][0] + (r - 1) * A[i][4]) / r;
+            A[i][2] = (A[i][1] - mean_prev) * (A[i][1] - mean_prev)
+                    + (1 / (r - 1)) * ((r - 2) * A[i][2] + (X[i][1] - A[i][1]) * (X[i][1] - A[i][1])); // integer 1/(r-1), as the reference
+        }
+        A[i][3] = r;
+    }
+}
+
+// ---- DP ------------------------------------------------------------------------------------------
+
+namespace {
+void dp_runner(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[], double a, double b, double c, bool cubic,
+               double D, double sigma, double dt, double dx, int r, int g)
+{
+    if (t_meas.empty() || r < 1) throw std::invalid_argument("percolationDornic_2D: empty t_meas or r < 1");
+    tm_params p{};
+    p.model = cubic ? TM_MODEL_DP_CUBIC : TM_MODEL_DP;
+    p.L = g; p.dt = dt; p.dx = dx; p.a = a; p.b = b; p.c = c; p.D = D; p.sigma = sigma;
+    Ctx ctx(p, r);
+    const size_t n = (size_t)g * g;
+    vector<double> host(n * r);
+    for (int j = 0; j < r; j++) memcpy(&host[n * j], Rh0, n * sizeof(double)); // P/:988-992
+    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
+    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");
+
+    const int tot_iter = static_cast<int>(1.0 / dt) + 1 + (int)t_meas.size(); // P/:949
+    vector<double> acc_(5 * (size_t)tot_iter, 0.0);
+    double (*acc)[5] = reinterpret_cast<double (*)[5]>(acc_.data());
+    int ind = 0;
+    for (double t = 0; t <= 1; t += dt) { if (ind < tot_iter) acc[ind][0] = t; ind += 1; } // P/:961
+    for (size_t i = 0; i < t_meas.size() && ind + (int)i < tot_iter; i++) acc[ind + i][0] = t_meas[i];
+    vector<double> surv_rep(t_meas.size() + 1, 0.0);
+
+    // per-replicate series Rho_M[s] = {N_active, <rho>}; a replicate stops logging once extinct (P/:1021)
+    vector<vector<double>> RhoM(r, vector<double>(2 * (size_t)tot_iter, 0.0));
+    vector<int> s_of(r, 0);
+    vector<char> alive(r, 1);
+    const StepPlan plan = plan_dp(t_meas, dt);
+    vector<tm_stats> st(r);
+    int pending = 0;
+    for (size_t k = 0; k < plan.t.size(); k++) {
+        if (plan.measure[k]) {
+            if (pending) { ctx.ck(tm_step(ctx.c, pending), "tm_step"); pending = 0; }
+            ctx.ck(tm_measure(ctx.c, st.data()), "tm_measure");
+            bool any = false;
+            for (int j = 0; j < r; j++) {
+                if (!alive[j]) continue;
+                if (st[j].nonfinite) { // P/:2022-2060: NaN -> exit(3)
+                    std::cerr << "RK4 BLEW IT: non-finite density in replicate " << j << " at t=" << plan.t[k] << std::endl;
+                    exit(3);
+                }
+                if (plan.window[k] >= 0 && st[j].mean[0] > 0) surv_rep[plan.window[k]] += 1; // P/:1008-1013
+                if (s_of[j] < tot_iter) { RhoM[j][2 * s_of[j]] = (double)st[j].active[0]; RhoM[j][2 * s_of[j] + 1] = st[j].mean[0]; }
+                s_of[j] += 1;
+                if (st[j].active[0] == 0) alive[j] = 0; else any = true;
+            }
+            if (!any) break;
+        }
+        pending += 1; // the Dornic + remainder update of this iteration
+    }
+    // replicate-order accumulation, P/:1074-1098
+    for (int j = 0; j < r; j++) {
+        double (*X)[2] = reinterpret_cast<double (*)[2]>(RhoM[j].data());
+        if (j == 0) {
+            for (int i = 0; i < tot_iter; i++) {
+                acc[i][1] = X[i][1]; acc[i][2] = 0.0; acc[i][4] = X[i][0];
+                if (X[i][1] > 0) acc[i][3] = 1; else if (X[i][1] == 0) acc[i][3] = 0;
+            }
+        } else {
+            var_mean_incremental_surv_runs(acc, X, tot_iter);
+        }
+    }
+    for (int i = 0; i < tot_iter; i++) { // P/:1130-1142, :2139-2149
+        const double last = (i < ind) ? static_cast<double>(r) : surv_rep[i - ind];
+        if (cubic) Rho.push_back({a, c, static_cast<double>(g), acc[i][0], acc[i][1], acc[i][2], acc[i][3], acc[i][4], last});
+        else       Rho.push_back({a, static_cast<double>(g), acc[i][0], acc[i][1], acc[i][2], acc[i][3], acc[i][4], last});
+    }
+}
+} // namespace
+
+void percolationDornic_2D(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[], double /*t_max*/, double a,
+                          double b, double D, double sigma, double dt, double dx, int r, int g)
+{
+    dp_runner(Rho, t_meas, Rh0, a, b, 0.0, false, D, sigma, dt, dx, r, g); // t_max := t_meas.back(), P/:958
+}
+
+void expanded_percolationDornic_2D(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[], double /*t_max*/,
+                                   double a, double b, double c, double D, double sigma, double dt, double dx, int r, int g)
+{
+    dp_runner(Rho, t_meas, Rh0, a, b, c, true, D, sigma, dt, dx, r, g);
+}
+
+namespace {
+void write_dp_csv(const std::string &name, const char *header, const vector<vector<double>> &vec, bool cubic)
+{
+    mkdirs(options().data_root + "/Data/SPDP");
+    std::ofstream out(options().data_root + "/Data/SPDP/" + name);
+    out << header;
+    for (size_t i = 0; i < vec.size(); i++) {
+        const vector<double> &v = vec[i];
+        if (cubic) // P/:2535-2538
+            out << std::setprecision(8) << v[0] << "," << v[1] << "," << v[2] << "," << v[3] << "," << std::setprecision(16) << v[4]
+                << "," << std::setprecision(16) << v[5] << "," << v[6] << "," << std::setprecision(16) << v[7] << "," << v[8] << std::endl;
+        else       // P/:1408-1411
+            out << std::setprecision(8) << v[0] << "," << v[1] << "," << v[2] << "," << std::setprecision(16) << v[3] << ","
+                << std::setprecision(16) << v[4] << "," << v[5] << "," << std::setprecision(16) << v[6] << "," << v[7] << std::endl;
+    }
+}
+} // namespace
+
+void critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b, double D,
+                        double sigma, double dt, double dx, int r, int g) // P/:1309-1421
+{
+    vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = logarithm10_time_bins(t_max, dt);
+    vector<vector<double>> vec;
+    for (size_t i = 0; i < a_space.size(); i++) { // the reference's `omp for` over a-values; here one batch of r trials each
+        vector<vector<double>> rows;
+        percolationDornic_2D(rows, t_measure, Rho_0, t_max, a_space[i], b, D, sigma, dt, dx, r, g);
+        vec.insert(vec.end(), rows.begin(), rows.end());
+    }
+    std::stringstream L, tm, d3, p1, p2, rini, Dm, Sm;
+    L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a_start; p2 << std::setprecision(4) << a_end;
+    rini << r; Dm << std::setprecision(3) << D; Sm << std::setprecision(3) << sigma;
+    write_dp_csv("DEBUG_P_c_Delta_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a1_" + p1.str() + "_a2_" + p2.str()
+                 + "_Sig_" + Sm.str() + "_R_" + rini.str() + ".csv", // P/:1395
+                 " a , L,  t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n", vec, false);
+}
+
+void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b,
+                                    double c, double D, double sigma, double dt, double dx, int r, int g) // P/:2422-2547
+{
+    for (int i = 0; i < g * g; i++) Rho_0[i] = 0.25; // init_constframe(Rho_0, 0.25, g*g), P/:2427
+    vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = logarithm10_time_bins(t_max, dt);
+    vector<vector<double>> vec;
+    for (size_t i = 0; i < a_space.size(); i++) {
+        vector<vector<double>> rows;
+        expanded_percolationDornic_2D(rows, t_measure, Rho_0, t_max, a_space[i], b, c, D, sigma, dt, dx, r, g);
+        vec.insert(vec.end(), rows.begin(), rows.end());
+    }
+    std::stringstream L, coco, tm, d3, p1, p2, rini, Sm, dix;
+    L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a_start; p2 << std::setprecision(4) << a_end;
+    rini << r; Sm << std::setprecision(3) << sigma; coco << std::setprecision(4) << c; dix << std::setprecision(2) << dx;
+    write_dp_csv("1stOrder_P_c_Delta_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_c_" + coco.str() + "_a1_" + p1.str()
+                 + "_a2_" + p2.str() + "_dx_" + dix.str() + "_Sig_" + Sm.str() + "_R_" + rini.str() + ".csv",
+                 " a , c , L,  t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n", vec, true);
+}
+
+// ---- Rietkerk SPB = 1 ----------------------------------------------------------------------------
+
+std::vector<double> frame_tmeas;
+std::string frame_folder;
+
+namespace {
+// splitmix64: the speckle mask of the default initial frame (the reference uses mt19937_64(random_device), R/:420)
+inline unsigned long long splitmix(unsigned long long &s)
+{
+    unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void default_init_frame(double *f, int g, int replicate, double a, double a_c, double dP, const double clow[])
+{
+    // MFT expressions of order_1stoc_test_rietkerk.cpp:144-160 (the driver's strings), SPB = 1 constants :28-37
+    const double c = 10000, gmax = 0.05e-3 / 24.0, d = 0.25 / 24.0, rW = 0.2 / 24.0, alpha = 0.2 / 24.0, W0 = 0.2, K1 = 5;
+    const double Wstar = d * K1 / (c * gmax - d);
+    const double perc = 0.015; // R/:3403
+    const size_t n = (size_t)g * g;
+    unsigned long long s = options().seed ^ (0xA5A5A5A5ull * (unsigned long long)(replicate + 1));
+    double e[6]; // {V_prev, W_prev, O_prev, V, W, O}(a)
+    e[0] = 0; e[1] = (1 / rW) * a; e[2] = (1 / (alpha * W0)) * a;
+    e[3] = (c / d) * a + (-rW * Wstar * c / d); e[4] = Wstar * a - 0; e[5] = 120.4744181 * a + 0.58243061;
+    if (a < a_c) { // R/:450-473
+        const double high = std::max(dP, clow[0] * e[0]);
+        for (size_t i = 0; i < n; i++) f[i] = ((splitmix(s) >> 11) * 0x1.0p-53 < perc) ? high : clow[0] * e[0];
+        for (int sp = 1; sp < Sp; sp++) for (size_t i = 0; i < n; i++) f[sp * n + i] = clow[sp] * e[sp];
+    } else {       // R/:474-496
+        const double high = std::max(dP, clow[Sp] * e[Sp]);
+        for (size_t i = 0; i < n; i++) f[i] = ((splitmix(s) >> 11) * 0x1.0p-53 < perc) ? high : e[Sp];
+        for (int sp = 1; sp < Sp; sp++) for (size_t i = 0; i < n; i++) f[sp * n + i] = clow[sp + Sp] * e[sp + Sp];
+    }
+}
+} // namespace
+
+std::function<void(double *, int, int, double, double, double, const double[])> init_frame = default_init_frame;
+
+void save_frame(D2Vec_Double &Rho_t, const std::string &parendir, const std::string &filenamePattern, double a, double,
+                double, double, double, double, double, int r, int g, std::string header, bool) // R/:2836-2883
+{
+    std::stringstream rini; rini << r;
+    mkdirs(parendir);
+    std::ofstream frame_dp(parendir + filenamePattern + rini.str() + ".csv");
+    if (header == "") header = "a_c,  x,  P(x; t), W(x; t), O(x; t) \n"; // rietkerk_bjork_constants_1Sp.h:6
+    frame_dp << header;
+    for (int i = 0; i < g * g; i++) {
+        frame_dp << a << "," << i;
+        for (size_t s = 0; s < Rho_t.size(); s++) frame_dp << "," << Rho_t[s][i]; // default (6-digit) precision, R/:2866
+        frame_dp << std::endl;
+    }
+}
+
+void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&)[SpB], double (&K)[3],
+                                double sigma[], double a_st, double a_end, double a_c, double (&)[SpB][SpB], double (&)[SpB][SpB],
+                                double (&)[SpB], double (&M)[SpB], double[], int (&)[SpB], double clow[], double dt, double dx,
+                                double dP, int r, int g, double, double)
+{
+    if (t_meas.empty() || r < 1) throw std::invalid_argument("rietkerk_Dornic_2D_MultiSp: empty t_meas or r < 1");
+    tm_params p{};
+    p.model = TM_MODEL_RIETKERK; p.L = g; p.dt = dt; p.dx = dx; p.a = a;
+    p.rc = c; p.gmax = gmax; p.alpha = alpha; p.rW = rW; p.W0 = W0; p.d = M[0]; p.K1 = K[1]; p.K2 = K[2];
+    p.D0 = D[0]; p.D1 = D[1]; p.D2 = D[2]; p.sigma0 = sigma[0];
+    p.clamp_eps = 1.0e-12; p.clamp_lo = -1.0e-80; // R/:3402, :4176
+    Ctx ctx(p, r);
+    const size_t n = (size_t)g * g;
+    vector<double> host(3 * n * r);
+    for (int j = 0; j < r; j++) init_frame(&host[3 * n * j], g, j, a, a_c, dP, clow);
+    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
+    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");
+
+    const int tot_iter = (int)t_meas.size();               // R/:3438
+    const int W_ = 4 * SpB + 3;                            // Sp4_1: {t, <W>, <O>, mean, var, surv, active}
+    vector<vector<double>> acc(tot_iter, vector<double>(W_, 0.0));
+    for (int i = 0; i < tot_iter; i++) acc[i][0] = t_meas[i];
+    vector<vector<double>> RhoM(r, vector<double>(2 * Sp * (size_t)tot_iter, 0.0)); // [index][2s] = N, [2s+1] = mean
+    const double t_end = t_meas.back();
+    vector<tm_stats> st(r);
+    const std::string fdir = frame_folder.empty() ? options().data_root + "/Data/Rietkerk/Frames/Stochastic/1Sp/" : frame_folder;
+
+    double t = 0; int index = 0; size_t frame_index = 0; int pending = 0;
+    while (t < t_end + dt) { // R/:3648
+        const bool meas = index < tot_iter && (t == 0 || (t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0)); // R/:3659
+        const bool snap = frame_index < frame_tmeas.size()
+                       && (t == 0 || (t >= frame_tmeas[frame_index] - dt / 2.0 && t < frame_tmeas[frame_index] + dt / 2.0)); // R/:3736
+        if ((meas || snap) && pending) { ctx.ck(tm_step(ctx.c, pending), "tm_step"); pending = 0; }
+        if (meas) {
+            ctx.ck(tm_measure(ctx.c, st.data()), "tm_measure");
+            for (int j = 0; j < r; j++) {
+                if (st[j].nonfinite) { std::cerr << "RHO NAAN PARATHA in replicate " << j << " at t=" << t << "\n"; exit(3); }
+                for (int s = 0; s < Sp; s++) {
+                    RhoM[j][2 * Sp * index + 2 * s] = (double)st[j].active[s];
+                    RhoM[j][2 * Sp * index + 2 * s + 1] = st[j].mean[s];
+                }
+            }
+            index += 1;
+        }
+        if (snap) {
+            const size_t ftot = frame_tmeas.size();
+            if ((frame_index + 10 >= ftot) || (t >= 50000 && t <= 150000) || (t >= 20 && t <= 15000) || t == 0) { // R/:3739
+                ctx.ck(tm_download(ctx.c, host.data()), "tm_download");
+                for (int j = 0; j < r; j++) {
+                    D2Vec_Double fr(Sp, vector<double>(n));
+                    for (int s = 0; s < Sp; s++) memcpy(fr[s].data(), &host[(3 * j + s) * n], n * sizeof(double));
+                    std::stringstream L, tm, d3, p1, Dm1, dix, a1, a2, dimitri;
+                    L << g; tm << t; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a; dix << std::setprecision(2) << dx;
+                    Dm1 << std::setprecision(3) << D[1]; a1 << a_st; a2 << a_end; dimitri << dP;
+                    const std::string parendir = fdir + a1.str() + "-" + a2.str() + "_dP_" + dimitri.str();
+                    const std::string pattern = "/FRAME_P_c_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
+                                              + "_D1_" + Dm1.str() + "_jID_0_dx_" + dix.str() + "_R_"; // R/:2914
+                    save_frame(fr, parendir, pattern, a, a_st, a_end, t, dt, dx, dP, j, g);
+                }
+            }
+            frame_index += 1;
+        }
+        pending += 1;
+        t += dt;
+    }
+    // replicate-order accumulation: R/:4294-4322 and var_mean_incremental_surv_runs R/:1293-1343
+    for (int j = 0; j < r; j++) {
+        const vector<double> &X = RhoM[j];
+        if (j == 0) {
+            for (int i = 0; i < tot_iter; i++) {
+                const double N = X[2 * Sp * i + 0], mean = X[2 * Sp * i + 1];
+                acc[i][3] = mean; acc[i][4] = 0.0; acc[i][6] = N;
+                if (N > 0) acc[i][5] = 1; else if (N == 0) acc[i][5] = 0;
+                acc[i][1] = X[2 * Sp * i + 2 * (Sp - 2) + 1]; acc[i][2] = X[2 * Sp * i + 2 * (Sp - 1) + 1];
+            }
+            continue;
+        }
+        for (int i = 0; i < tot_iter; i++) { // vegetation: surviving runs only, stops at the first dead bin (R/:1306-1310)
+            const double N = X[2 * Sp * i + 0], mean = X[2 * Sp * i + 1];
+            const int rr = (int)(acc[i][5] + 1);
+            if (N == 0.0) break;
+            const double mean_prev = acc[i][3];
+            if (acc[i][5] == 0.0) { acc[i][3] = mean; acc[i][4] = 0.0; acc[i][6] = N; }
+            else {
+                acc[i][3] = (mean + (rr - 1) * acc[i][3]) / rr;
+                acc[i][6] = (N + (rr - 1) * acc[i][6]) / rr;
+                acc[i][4] = (acc[i][3] - mean_prev) * (acc[i][3] - mean_prev)
+                          + (1 / (rr - 1)) * ((rr - 2) * acc[i][4] + (mean - acc[i][3]) * (mean - acc[i][3])); // int 1/(r-1), R/:1325
+            }
+            acc[i][5] = rr;
+        }
+        for (int i = 0; i < tot_iter; i++) { // soil and surface water: plain running mean over all replicates (R/:1333-1337)
+            acc[i][1] = (X[2 * Sp * i + 2 * (Sp - 2) + 1] + j * acc[i][1]) / (j + 1);
+            acc[i][2] = (X[2 * Sp * i + 2 * (Sp - 1) + 1] + j * acc[i][2]) / (j + 1);
+        }
+    }
+    for (int i = 0; i < tot_iter; i++) { // R/:4361-4372: {a, r, L, t, <W>, <O>, <P>, var, surv, active}
+        vector<double> row = {a, static_cast<double>(r), static_cast<double>(g)};
+        row.insert(row.end(), acc[i].begin(), acc[i].end());
+        Rho.push_back(row);
+    }
+}
+
+} // namespace tm_b200

@@ -1,0 +1,70 @@
+// tm_host.h -- the reference-facing host layer: the reference's own C++ entry points for the
+// Dornic path, same names and argument lists, implemented over the C ABI (include/tm_lattice.h).
+// A reference driver main switches over by including this header, `using namespace tm_b200;`
+// and linking libtm_host.so + libtm_lattice.so.
+//
+//   percolationDornic_2D            Percolation_FD/stochasticSPDP.cpp:940
+//   expanded_percolationDornic_2D   Percolation_FD/stochasticSPDP.cpp:1809
+//   critical_exp_delta              Percolation_FD/stochasticSPDP.cpp:1309
+//   first_order_critical_exp_delta  Percolation_FD/stochasticSPDP.cpp:2422
+//   rietkerk_Dornic_2D_MultiSp      Rietkerk_FD/rietkerk_bjork_basic.cpp:3397   (SPB = 1)
+//   logarithm10_time_bins, linspace, var_mean_incremental_surv_runs, save_frame  (bookkeeping)
+//
+// What is different by construction: replicates run concurrently as trials of one device context
+// instead of a serial `for j<r` loop, and random numbers come from Philox streams keyed by
+// (seed, trial, step, cell) instead of std::mt19937_64 seeded from std::random_device.
+#pragma once
+#include <functional>
+#include <string>
+#include <vector>
+
+namespace tm_b200 {
+
+typedef std::vector<std::vector<double>> D2Vec_Double;
+
+struct Options {
+    int device = 0;
+    unsigned long long seed = 0x5EEDC0DEull; // the reference seeds from std::random_device (P/:973); here it is explicit
+    bool strict = false;                      // reference operation order in the RK4 stages
+    bool quiet = true;                        // the reference's progress chatter on stdout
+    std::string data_root = "..";             // outputs go to <data_root>/Data/... like the reference's "../Data/..."
+};
+Options &options(); // process-wide; env TM_DEVICE, TM_SEED, TM_STRICT, TM_DATA_ROOT override the defaults
+
+// ---- bookkeeping (host) --------------------------------------------------------------------
+std::vector<double> linspace(double start, double end, int num);                 // P/:254
+std::vector<double> logarithm10_time_bins(double t_max, double dt);              // P/:336
+void var_mean_incremental_surv_runs(double t_avg_var_rep_N[][5], double X_curr[][2], int size); // P/:173
+
+// ---- DP --------------------------------------------------------------------------------------
+void percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_meas, double Rh0[],
+                          double t_max, double a, double b, double D, double sigma, double dt, double dx, int r, int g);
+void expanded_percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_meas, double Rh0[],
+                                   double t_max, double a, double b, double c, double D, double sigma, double dt,
+                                   double dx, int r, int g);
+void critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b, double D,
+                        double sigma, double dt, double dx, int r, int g);
+void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b,
+                                    double c, double D, double sigma, double dt, double dx, int r, int g);
+
+// ---- Rietkerk, SPB = 1 (Sp = 3 fields: P, W, O) ---------------------------------------------
+constexpr int Sp = 3, SpB = 1;
+// frame_tmeas (R/ header :130): snapshot times; frames are written by save_frame() in the
+// reference's CSV format.  Empty (default) = no snapshots.
+extern std::vector<double> frame_tmeas;
+extern std::string frame_folder; // default "<data_root>/Data/Rietkerk/Frames/Stochastic/1Sp/"
+// Initial frame of replicate j (3*g*g doubles, fields P,W,O).  Default: the MFT speckle rule of
+// init_exprtk_randbiMFTframe (R/:396-505) with the order_1stoc_test_rietkerk.cpp:144-160 expressions.
+extern std::function<void(double *frame, int g, int replicate, double a, double a_c, double dP, const double clow[])> init_frame;
+
+void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c,
+                                double gmax, double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB],
+                                double (&K)[3], double sigma[], double a_st, double a_end, double a_c,
+                                double (&A)[SpB][SpB], double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB],
+                                double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
+                                int g, double Gstar = -1.0, double Vstar = -1.0);
+void save_frame(D2Vec_Double &Rho_t, const std::string &parendir, const std::string &filenamePattern, double a,
+                double a_st, double a_end, double t, double dt, double dx, double dP, int r, int g,
+                std::string header = "", bool overwrite = false);                 // R/:2836
+
+} // namespace tm_b200

@@ -1,0 +1,83 @@
+// tm_host_capi.cpp -- flat C doors into the C++ host layer (tm_host.h) so the Python tests can
+// drive the reference-signature runners through ctypes.  No logic of its own.
+#include "tm_host.h"
+#include <cmath>
+#include <cstring>
+
+using namespace tm_b200;
+
+extern "C" {
+
+void tmh_set_options(int device, unsigned long long seed, int strict, const char *data_root)
+{
+    options().device = device; options().seed = seed; options().strict = strict != 0;
+    if (data_root) options().data_root = data_root;
+}
+
+int tmh_time_bins(double t_max, double dt, double *out, int cap)
+{
+    std::vector<double> v = logarithm10_time_bins(t_max, dt);
+    if ((int)v.size() > cap) return -1;
+    for (size_t i = 0; i < v.size(); i++) out[i] = v[i];
+    return (int)v.size();
+}
+
+// rows_out[k][9]: the runner's output row, zero padded ({a,(c),L,t,mean,var,surv,active,last})
+int tmh_dp_run(int cubic, int L, double a, double b, double c, double D, double sigma, double dt, double dx, int r,
+               const double *rh0, const double *t_meas, int n_tmeas, double *rows_out, int cap)
+{
+    std::vector<std::vector<double>> Rho;
+    std::vector<double> tm(t_meas, t_meas + n_tmeas), r0(rh0, rh0 + (size_t)L * L);
+    try {
+        if (cubic) expanded_percolationDornic_2D(Rho, tm, r0.data(), tm.back(), a, b, c, D, sigma, dt, dx, r, L);
+        else       percolationDornic_2D(Rho, tm, r0.data(), tm.back(), a, b, D, sigma, dt, dx, r, L);
+    } catch (const std::exception &) { return -2; }
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 9; j++) rows_out[9 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
+    return (int)Rho.size();
+}
+
+int tmh_dp_sweep(int cubic, int L, int div, double t_max, double a_start, double a_end, double b, double c, double D,
+                 double sigma, double dt, double dx, int r)
+{
+    std::vector<double> rho0((size_t)L * L, 1.0); // init_fullframe, P/1storderDP_delta.cpp:45
+    try {
+        if (cubic) first_order_critical_exp_delta(rho0.data(), div, t_max, a_start, a_end, b, c, D, sigma, dt, dx, r, L);
+        else       critical_exp_delta(rho0.data(), div, t_max, a_start, a_end, b, D, sigma, dt, dx, r, L);
+    } catch (const std::exception &) { return -2; }
+    return 0;
+}
+
+// Rietkerk SPB=1 with the order_1stoc_test_rietkerk.cpp constants; init = NULL -> default MFT speckle frame
+int tmh_riet_run(int L, double a, double dt, int r, const double *init, const double *t_meas, int n_tmeas,
+                 const double *frame_t, int n_frame_t, const char *frame_dir, double *rows_out, int cap)
+{
+    double c = 10000, gmax = 0.05e-3 / 24.0, d = 0.25 / 24.0, alpha = 0.2 / 24.0, W0 = 0.2, rW = 0.2 / 24.0, dx = 0.1;
+    double D[Sp] = {0.00025 / 24.0, 0.00025 / 24.0, 0.025 / 24.0};
+    double K[3] = {0, 5, 5000};
+    double sigma[Sp] = {sqrt(D[0] / (dx * dx)), 0, 0};
+    double v[SpB] = {0}, A[SpB][SpB] = {{0}}, H[SpB][SpB] = {{0}}, E[SpB] = {1.0}, M[SpB] = {d}, pR[SpB] = {0.0};
+    int dtV[SpB] = {0};
+    double clow[2 * Sp] = {0, 1, 1, 5, 1, 1};
+    std::vector<double> tm(t_meas, t_meas + n_tmeas);
+    frame_tmeas.assign(frame_t, frame_t + n_frame_t);
+    frame_folder = frame_dir ? frame_dir : "";
+    auto saved = init_frame;
+    const size_t n = (size_t)L * L;
+    if (init) init_frame = [init, n](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + 3 * n * j, 3 * n * sizeof(double)); };
+    D2Vec_Double Rho;
+    int rc = 0;
+    try {
+        rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), a, c, gmax, alpha, rW, W0, D, v, K, sigma, a, a, 1.0 / 24.0, A, H, E, M, pR,
+                                   dtV, clow, dt, dx, 10000.0, r, L);
+    } catch (const std::exception &) { rc = -2; }
+    init_frame = saved;
+    if (rc) return rc;
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 10; j++) rows_out[10 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
+    return (int)Rho.size();
+}
+
+}
