@@ -159,3 +159,20 @@ def test_dp_sweep_writes_reference_csv(host, tmp_path):
     assert len(lines) - 1 == 2 * (11 + bins)
     first = lines[1].split(",")
     assert len(first) == 9 and float(first[0]) == -0.72 and float(first[2]) == 32 and float(first[4]) == 0.25
+
+
+def test_config1_driver_binary(tmp_path):
+    """drivers/dp_first_order_delta: BASELINE config 1 (L=128, a -0.72 -> -0.70, b=-2, c=1) end to end,
+    same stdin protocol and output file as Percolation_FD/1storderDP_delta.cpp."""
+    import subprocess
+    exe = os.path.join(ROOT, "drivers", "dp_first_order_delta")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    env = dict(os.environ, TM_DATA_ROOT=str(tmp_path), TM_SEED="7")
+    out = subprocess.run([exe], input="0.1\n20\n128\n2\n-0.72\n-0.70\n3\n", text=True, capture_output=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    files = list((tmp_path / "Data" / "SPDP").iterdir())
+    assert len(files) == 1 and files[0].name.startswith("1stOrder_P_c_Delta_DP_G_128_T_20_dt_0.1_c_1_a1_-0.72_a2_-0.7_dx_2.5_Sig_1_R_2")
+    rows = np.loadtxt(files[0], delimiter=",", skiprows=1)
+    assert rows.shape[1] == 9 and set(np.round(rows[:, 0], 6)) == {-0.72, -0.71, -0.70}
+    assert np.all(rows[:, 2] == 128) and np.all(rows[rows[:, 3] == 0][:, 4] == 0.25)
+    assert np.all(rows[:, 4] > 0) and np.all(rows[:, 7] <= 128 * 128)

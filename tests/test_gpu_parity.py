@@ -211,3 +211,19 @@ def test_decomposition_invariance():
     assert np.array_equal(got, want)
     for s in slabs:
         s.close()
+
+
+def test_slab_decomposition_over_nccl():
+    """BASELINE config 5 in small: row slabs on 2+ GPUs, halo exchange over NCCL, bit-exact vs one GPU."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)),
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "run_slab_nccl.py"), "256", "5"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "bit_exact=True" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
