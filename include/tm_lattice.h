@@ -98,6 +98,12 @@ int tm_set_trial_a(tm_ctx *, int trial, double a);
  * to the oracle); 0 (default): the fast arrangement (shared reciprocal, fused multiply-adds). */
 int tm_set_strict(tm_ctx *, int strict);
 
+/* Rietkerk model only.  fused != 0 (default): one fused launch per step, 48 B of HBM traffic per site.
+ * fused == 0: each step is two launches -- the vegetation Dornic sweep (one thread per column, 32 warps
+ * per SM) into a rho* scratch field, then the marching RK4 kernel; 64 B per site, ~2 % faster on B200.
+ * Results are bit-identical either way. */
+int tm_set_fused(tm_ctx *, int fused);
+
 /* --- state ----------------------------------------------------------------------------- */
 /* host_soa: double[n_trials][n_fields][nrows][L], n_fields = 1 (DP) or 3 (Rietkerk).
  * Pinned host memory makes these asynchronous-capable; pageable memory works too. */

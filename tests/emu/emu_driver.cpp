@@ -38,6 +38,9 @@ void unpack(const Geom &g, const std::vector<double> &buf, double *host)
 
 extern "C" {
 
+static int g_split = 0;
+void emu_set_split(int s) { g_split = s; } // 1: Dornic kernel + kSrcPre RK kernel (the production pair)
+
 // fields: [n_trials][n_fields][L][L] in/out (whole lattice).  grid <= 0: as many CTAs as an n_sm-SM
 // device would get.  stats_out: [n_trials][8] = sum-derived mean[3], active[3], nonfinite, negative.
 int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int strict, int grid_override,
@@ -80,6 +83,17 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
             } else if (replay_u) {
                 if (strict) emu_launch(riet_step_kernel<false, true, true, true, false>, A, grid, g.nthreads, smem);
                 else        emu_launch(riet_step_kernel<false, false, true, true, false>, A, grid, g.nthreads, smem);
+            } else if (g_split) {
+                std::vector<double> pstar((size_t)g.n_trials * g.field_stride, 0.0);
+                DornicArgs D{};
+                D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.in = A.in; D.pstar = pstar.data();
+                D.seed = seed; D.trial0 = trial0; D.step = step0 + s; D.rk = A.rk; D.row_lo = 0; D.row_hi = g.nrows; D.rows_per_cta = 7;
+                const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32);
+                if (strict) emu_launch(riet_dornic_kernel<true>, D, 3, kDornicThreads, dsmem);
+                else        emu_launch(riet_dornic_kernel<false>, D, 3, kDornicThreads, dsmem);
+                A.pstar = pstar.data();
+                if (strict) emu_launch(riet_step_kernel<false, true, 2, true, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<false, false, 2, true, false>, A, grid, g.nthreads, smem);
             } else {
                 if (strict) emu_launch(riet_step_kernel<false, true, false, true, false>, A, grid, g.nthreads, smem);
                 else        emu_launch(riet_step_kernel<false, false, false, true, false>, A, grid, g.nthreads, smem);
@@ -115,7 +129,7 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
         std::vector<TmStatsDev> sd(n_trials);
         struct FinArgs { const PartialStats *p; int n, nt; double cells; TmStatsDev *out; } F{partials.data(), n_records, n_trials, (double)p->L * p->L, sd.data()};
         auto fin = [](const FinArgs &f) { stats_finalize_kernel(f.p, f.n, f.nt, f.cells, f.out); };
-        emu_launch(fin, F, 1, (unsigned)n_trials, 0);
+        emu_launch(fin, F, (unsigned)n_trials, 32, 32 * 8 * sizeof(double));
         for (int t = 0; t < n_trials; t++) {
             for (int f = 0; f < 3; f++) { stats_out[8 * t + f] = sd[t].mean[f]; stats_out[8 * t + 3 + f] = (double)sd[t].active[f]; }
             stats_out[8 * t + 6] = (double)sd[t].nonfinite; stats_out[8 * t + 7] = (double)sd[t].negative;

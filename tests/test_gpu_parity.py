@@ -57,6 +57,25 @@ def test_rietkerk_strict_bit_exact(L):
     lat.close()
 
 
+def test_split_pair_equals_fused_kernel():
+    """tm_set_fused(0): Dornic sweep + RK4 kernel pair, bit-identical to the fused kernel (strict and fast)."""
+    L = 200
+    p = tm.rietkerk_params(L)
+    frames = np.stack([O.synthetic_rietkerk_frame(L, seed=60 + t) for t in range(2)])
+    out = {}
+    for strict in (True, False):
+        for fused in (True, False):
+            lat = tm.Lattice(p, 2)
+            lat.set_strict(strict); lat.set_fused(fused); lat.seed(5150, trial0=3)
+            lat.upload(frames); lat.step(4)
+            out[(strict, fused)] = lat.download()
+            assert lat.sampler_overflow() == 0
+            lat.close()
+        assert np.array_equal(out[(strict, True)], out[(strict, False)])
+    want = oracle_steps(p, frames[1], 4, 5150, 4)
+    assert np.array_equal(out[(True, False)][1], want)
+
+
 @pytest.mark.parametrize("L", [64, 250])
 def test_rietkerk_fast_per_step(L):
     """Per-step parity (north_star): each GPU step starts from the oracle's state."""

@@ -53,6 +53,21 @@ def test_rietkerk_strict_any_geometry(emu, L, grid):
             assert abs(stats[t, f] - O.mean(got[t, f])) <= 1e-12 * abs(O.mean(got[t, f]))
 
 
+def test_split_pair_equals_fused(emu):
+    """The production pair (riet_dornic_kernel -> rho* scratch -> RK4 kernel) is bit-identical to the fused kernel."""
+    L = 72
+    p = tm.rietkerk_params(L)
+    frames = np.stack([O.synthetic_rietkerk_frame(L, seed=21 + t) for t in range(2)])
+    emu.emu_set_split(1)
+    try:
+        got, stats, cnt = emu_step(emu, p, frames, 2, strict=1, grid=3, seed=77, trial0=2)
+    finally:
+        emu.emu_set_split(0)
+    assert cnt == (0, 0)
+    for t in range(2):
+        assert np.array_equal(got[t], oracle_steps(p, frames[t], 2, 77, 2 + t))
+
+
 def test_result_independent_of_cta_count(emu):
     L = 48
     p = tm.rietkerk_params(L)

@@ -90,6 +90,7 @@ struct StepArgs {
     int max_segs;
     unsigned long long *counters; // [0] sampler/replay overflow, [1] pipeline timeouts
     double *dornic_out;           // DORNIC_ONLY: rho* [n_trials][nrows][L] (unpadded)
+    const double *pstar;          // kSrcPre: rho* in the padded layout, [n_trials][rows_alloc][Lp]
     PhiloxKeys rk;                // the ten round keys of `seed` (host-computed)
 };
 
@@ -409,7 +410,12 @@ TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t ste
     n_first = y * mult;
 }
 
-template <bool DET, bool STRICT, bool REPLAY, bool STATS, bool DORNIC_ONLY>
+// SRC: where rho* comes from -- kSrcPhilox: sampled in front 1 (fused); kSrcReplay: same with host uniforms;
+// kSrcPre: precomputed by riet_dornic_kernel into A.pstar (the split alternative, tm_set_fused(ctx, 0): the
+// long serial sampler chain runs at full occupancy in its own kernel, this one keeps only the RK4 fronts).
+enum { kSrcPhilox = 0, kSrcReplay = 1, kSrcPre = 2 };
+
+template <bool DET, bool STRICT, int SRC, bool STATS, bool DORNIC_ONLY>
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 #else
@@ -479,7 +485,7 @@ riet_step_kernel(const StepArgs A)
             double *dst = in + (size_t)slot * 3 * RW + 2;
             const long long off = prow(j) * g.Lp + x0;
             mbar_expect_tx(&mbar[slot], 3 * row_bytes);
-            bulk_g2s(dst, inP + off, row_bytes, &mbar[slot]);
+            bulk_g2s(dst, (SRC == kSrcPre ? A.pstar + (long long)trial * g.field_stride : inP) + off, row_bytes, &mbar[slot]);
             bulk_g2s(dst + RW, inW + off, row_bytes, &mbar[slot]);
             bulk_g2s(dst + 2 * RW, inO + off, row_bytes, &mbar[slot]);
         };
@@ -520,11 +526,11 @@ riet_step_kernel(const StepArgs A)
             // ---- front 1: row j-1 : rho* and K1 -----------------------------------------------
             const double Pc = i1[0], Pu = i2[0], Pd = i0[0], Pl = i1[-1], Pr = i1[1];
             double pstar = Pc;
-            if (!DET) {
+            if (!DET && SRC != kSrcPre) {
                 const double alpha_i = c.dk.diffc * (Pu + Pd + Pl + Pr);
                 const bool live = !(alpha_i == 0 && Pc == 0) && col_in_strip; // skip rule R/:3759
                 const uint32_t cell = (uint32_t)r1 * (uint32_t)g.L + (uint32_t)gxm;
-                if (REPLAY) {
+                if (SRC == kSrcReplay) {
                     if (live) {
                         ReplaySrc src;
                         src.begin(A.replay_u + ((size_t)trial * g.L * g.L + cell) * A.stride, A.stride);
@@ -639,6 +645,117 @@ riet_step_kernel(const StepArgs A)
         seg_no++;
     }
     if (timeout && tid == 0) atomicAdd(&A.counters[1], 1ull);
+}
+
+// ------------------------------------------------------------------------------------------
+// Rietkerk vegetation Dornic sweep as its own kernel (the split alternative, tm_set_fused(ctx, 0))
+// ------------------------------------------------------------------------------------------
+// One thread per column, marching down a run of rows: the vertical neighbours roll through registers,
+// the horizontal ones come from the neighbouring lanes by shuffle (only the two edge lanes of a warp
+// load theirs), so a cell costs one global load and one store.  No pipeline state beyond that: 64
+// registers, 32 warps per SM, and the long serial chain (Philox -> polar -> log -> sqrt -> trunc -> sqrt)
+// of one warp hides behind seven others.  Writes rho* in the padded layout (ghost columns included) for
+// riet_step_kernel<.., kSrcPre, ..>.  Costs one extra field write + read per site (64 instead of 48 B)
+// on a kernel pair that sits far below the HBM roofline.
+struct DornicArgs {
+    Geom g;
+    DornicConsts dk;
+    double inv_lambda;
+    const double *in;              // state buffer (field 0 = P is read)
+    double *pstar;                 // [n_trials][rows_alloc][Lp]
+    unsigned long long seed;
+    unsigned int trial0, step;
+    PhiloxKeys rk;
+    int row_lo, row_hi;            // lattice-local rows [row_lo, row_hi) to sample (slabs: -3 .. nrows+3)
+    int rows_per_cta;              // rows one CTA marches through
+};
+
+constexpr int kDornicThreads = 256;
+
+template <bool STRICT>
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(kDornicThreads, 4)
+#else
+void
+#endif
+riet_dornic_kernel(const DornicArgs A)
+{
+    const Geom &g = A.g;
+    const DornicConsts &dk = A.dk;
+    const int tid = threadIdx.x;
+    TM_DYN_SMEM(smem_raw);
+    uint32_t *wscratch = reinterpret_cast<uint32_t *>(smem_raw) + 32 * (tid >> 5);
+    // work item = (trial, column block of 256, run of rows_per_cta rows)
+    const int ncb = (g.L + kDornicThreads - 1) / kDornicThreads;
+    const int nrow = A.row_hi - A.row_lo;
+    const int nrun = (nrow + A.rows_per_cta - 1) / A.rows_per_cta;
+    const long long items = (long long)g.n_trials * ncb * nrun;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int run = (int)(it % nrun);
+        const int cb = (int)((it / nrun) % ncb);
+        const int trial = (int)(it / ((long long)nrun * ncb));
+        const int ra = A.row_lo + run * A.rows_per_cta;
+        const int rb = (ra + A.rows_per_cta < A.row_hi) ? ra + A.rows_per_cta : A.row_hi;
+        const int q = cb * kDornicThreads + tid;
+        const bool valid = q < g.L;
+        const int qc = valid ? q : g.L - 1;          // clamped: idle lanes read a legal address
+#if defined(__CUDA_ARCH__)
+        const int lane = tid & 31;
+#endif
+        const uint32_t ptrial = A.trial0 + (uint32_t)trial;
+        const double *P = A.in + (long long)trial * g.trial_stride + kHalo + qc;   // column qc of physical row 0
+        double *O = A.pstar + (long long)trial * g.field_stride + kHalo + qc;
+        auto prow = [&](int r) -> long long { // physical row of lattice-local row r in [-4, nrows+4)
+            if (g.wrap) { if (r < 0) r += g.L; if (r >= g.L) r -= g.L; return r; }
+            return r + kHalo;
+        };
+        double Pu = P[prow(ra - 1) * g.Lp], Pc = P[prow(ra) * g.Lp];
+        int grow = g.row0 + ra; if (grow < 0) grow += g.L; if (grow >= g.L) grow -= g.L;
+        for (int row = ra; row < rb; row++) {
+            const long long pr = prow(row);
+            const double Pd = P[prow(row + 1) * g.Lp];
+            double Pl, Pr;
+#if defined(__CUDA_ARCH__)
+            Pl = __shfl_up_sync(0xffffffffu, Pc, 1);
+            Pr = __shfl_down_sync(0xffffffffu, Pc, 1);
+            if (lane == 0) Pl = P[pr * g.Lp - 1];      // ghost column covers q = 0
+            if (lane == 31 || q == g.L - 1) Pr = P[pr * g.Lp + 1];
+#else
+            Pl = P[pr * g.Lp - 1]; Pr = P[pr * g.Lp + 1];
+#endif
+            // ---- identical to front 1 of the fused kernel -------------------------------------------------
+            double pstar = Pc;
+            const double alpha_i = dk.diffc * (Pu + Pd + Pl + Pr);
+            const bool live = !(alpha_i == 0 && Pc == 0) && valid;            // skip rule R/:3759
+            const uint32_t cell = (uint32_t)grow * (uint32_t)g.L + (uint32_t)qc;
+            const double ziggy = dk.ll * Pc;
+            const double mu1 = (-1.0 + 2.0 * alpha_i * dk.sigma2_1) + 1.0;
+            const bool gauss_n = live && ziggy > 100;
+            const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
+            double n_first, n_second;
+            polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, n_first, n_second);
+            bool exact = live && !fastp;
+            if (fastp) {
+                double gru = mu1, nz = n_first;
+                if (gauss_n) {
+                    const long long gauss = (long long)fma(n_first, STRICT ? sqrt(ziggy) : sqrt_lean(ziggy), ziggy);
+                    gru = mu1 + (double)gauss;
+                    nz = n_second;
+                }
+                if (gru > 100) pstar = STRICT ? fma(nz, sqrt(gru), gru) / dk.lambda : fma(nz, sqrt_lean(gru), gru) * A.inv_lambda;
+                else exact = true;
+            }
+            if (exact) pstar = riet_cell_exact(dk, cell, ptrial, A.step, A.seed, alpha_i, Pc);
+            if (valid) {
+                double *o = O + pr * g.Lp;
+                o[0] = pstar;
+                if (q < kHalo) o[g.L] = pstar;
+                if (q >= g.L - kHalo) o[-g.L] = pstar;
+            }
+            Pu = Pc; Pc = Pd;
+            grow = (grow + 1 == g.L) ? 0 : grow + 1;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -771,7 +888,8 @@ stats_kernel(const StatsArgs A)
 
 struct TmStatsDev { double mean[3]; unsigned long long active[3], nonfinite, negative; };
 
-// one thread per trial sums the partial records in index order
+// one block per trial: thread t adds the records t, t+nthreads, ... in index order, then the per-thread
+// partials are added in thread order -- deterministic for a given launch geometry
 #if defined(__CUDACC__)
 __global__ void
 #else
@@ -779,18 +897,34 @@ inline void
 #endif
 stats_finalize_kernel(const PartialStats *partials, int n_records, int n_trials, double cells, TmStatsDev *out)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x, tid = threadIdx.x, nthreads = blockDim.x;
     if (t >= n_trials) return;
-    TmStatsDev s;
-    for (int f = 0; f < 3; f++) { s.mean[f] = 0.0; s.active[f] = 0; }
-    s.nonfinite = 0; s.negative = 0;
-    for (int i = 0; i < n_records; i++) {
+    TM_DYN_SMEM(smem_raw);
+    double *sh = reinterpret_cast<double *>(smem_raw);                 // [3][nthreads]
+    unsigned long long *shu = reinterpret_cast<unsigned long long *>(sh + 3 * nthreads); // [5][nthreads]
+    double sum[3] = {0.0, 0.0, 0.0};
+    unsigned long long cnt[5] = {0, 0, 0, 0, 0};
+    for (int i = tid; i < n_records; i += nthreads) {
         if (partials[i].trial != t) continue;
-        for (int f = 0; f < 3; f++) { s.mean[f] += partials[i].sum[f]; s.active[f] += partials[i].active[f]; }
-        s.nonfinite += partials[i].nonfinite; s.negative += partials[i].negative;
+        for (int f = 0; f < 3; f++) { sum[f] += partials[i].sum[f]; cnt[f] += partials[i].active[f]; }
+        cnt[3] += partials[i].nonfinite; cnt[4] += partials[i].negative;
     }
-    for (int f = 0; f < 3; f++) s.mean[f] /= cells; // sum/(double)size, R/:1218
-    out[t] = s;
+    for (int f = 0; f < 3; f++) sh[f * nthreads + tid] = sum[f];
+    for (int k = 0; k < 5; k++) shu[k * nthreads + tid] = cnt[k];
+    __syncthreads();
+    if (tid == 0) {
+        TmStatsDev s;
+        for (int f = 0; f < 3; f++) {
+            double a = 0.0; unsigned long long n = 0;
+            for (int i = 0; i < nthreads; i++) { a += sh[f * nthreads + i]; n += shu[f * nthreads + i]; }
+            s.mean[f] = a / cells; // sum/(double)size, R/:1218
+            s.active[f] = n;
+        }
+        unsigned long long nf = 0, ng = 0;
+        for (int i = 0; i < nthreads; i++) { nf += shu[3 * nthreads + i]; ng += shu[4 * nthreads + i]; }
+        s.nonfinite = nf; s.negative = ng;
+        out[t] = s;
+    }
 }
 
 // ghost-column fill after an upload / halo unpack: one thread per (row, 0..7)

@@ -37,11 +37,13 @@ struct tm_ctx {
     double *replay_dev = nullptr;
     size_t replay_cap = 0;
     double *dornic_dev = nullptr;
+    double *pstar_dev = nullptr;   // rho* scratch field of the split Dornic / RK4 kernel pair
+    bool fused = true;             // false: Dornic sweep + RK4 kernel pair instead of the fused kernel
     double *halo_dev[2] = {nullptr, nullptr};
     uint64_t seed = 0, step = 0;
     uint32_t trial0 = 0;
     float last_ms = 0.f;
-    int last_launches = 0;
+    int last_launches = 0, launches_this_call = 0;
     std::string err;
 };
 
@@ -168,6 +170,10 @@ int tm_create_slab(const tm_params *p, int n_trials, int device, int row0, int n
         TM_OPTIN((riet_step_kernel<false, true, true, true, false>), smem_s);
         TM_OPTIN((riet_step_kernel<false, true, false, false, true>), smem_s);
         TM_OPTIN((riet_step_kernel<false, true, true, false, true>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, 2, false, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, 2, true, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, 2, false, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, 2, true, false>), smem_s);
         TM_OPTIN((riet_step_kernel<true, false, false, false, false>), smem_d);
         TM_OPTIN((riet_step_kernel<true, false, false, true, false>), smem_d);
         TM_OPTIN((riet_step_kernel<true, true, false, false, false>), smem_d);
@@ -198,7 +204,7 @@ int tm_destroy(tm_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int s = 0; s < 2; s++) { cudaFree(c->buf[s]); cudaFree(c->halo_dev[s]); }
     cudaFree(c->a_dev); cudaFree(c->dp_trials_dev); cudaFree(c->partials); cudaFree(c->stats_dev);
-    cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev);
+    cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev); cudaFree(c->pstar_dev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -222,6 +228,13 @@ int tm_set_strict(tm_ctx *c, int strict)
 {
     if (!c) return TM_E_ARG;
     c->strict = strict != 0;
+    return TM_OK;
+}
+
+int tm_set_fused(tm_ctx *c, int fused)
+{
+    if (!c) return TM_E_ARG;
+    c->fused = fused != 0;
     return TM_OK;
 }
 
@@ -322,10 +335,38 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             if (replay) TM_LAUNCH(false, true, true, false, true); else TM_LAUNCH(false, true, false, false, true);
         } else if (replay) {
             if (c->strict) TM_LAUNCH(false, true, true, true, false); else TM_LAUNCH(false, false, true, true, false);
-        } else if (c->strict) {
-            if (stats) TM_LAUNCH(false, true, false, true, false); else TM_LAUNCH(false, true, false, false, false);
+        } else if (c->fused) {
+            if (c->strict) { if (stats) TM_LAUNCH(false, true, false, true, false); else TM_LAUNCH(false, true, false, false, false); }
+            else           { if (stats) TM_LAUNCH(false, false, false, true, false); else TM_LAUNCH(false, false, false, false, false); }
         } else {
-            if (stats) TM_LAUNCH(false, false, false, true, false); else TM_LAUNCH(false, false, false, false, false);
+            // alternative: Dornic sweep at full occupancy into a rho* scratch field, then the RK4 fronts only
+            if (!c->pstar_dev) {
+                const size_t nb = sizeof(double) * (size_t)g.n_trials * g.field_stride;
+                TM_CUDA(c, cudaMalloc(&c->pstar_dev, nb));
+                TM_CUDA(c, cudaMemsetAsync(c->pstar_dev, 0, nb, c->stream));
+            }
+            DornicArgs D{};
+            D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.in = A.in; D.pstar = c->pstar_dev;
+            D.seed = c->seed; D.trial0 = c->trial0; D.step = (unsigned int)c->step; D.rk = A.rk;
+            D.row_lo = g.wrap ? 0 : -(kHalo - 1); D.row_hi = g.wrap ? g.nrows : g.nrows + (kHalo - 1);
+            // rows per CTA: enough (trial, column block, run) items for ~2 rounds over 4 resident CTAs per SM
+            const int ncb = (g.L + kDornicThreads - 1) / kDornicThreads, nrow_d = D.row_hi - D.row_lo;
+            long long want_runs = ((long long)c->n_sm * 8 + (long long)g.n_trials * ncb - 1) / ((long long)g.n_trials * ncb);
+            if (want_runs < 1) want_runs = 1;
+            int rpc = (int)((nrow_d + want_runs - 1) / want_runs);
+            if (rpc < 16) rpc = nrow_d < 16 ? nrow_d : 16;
+            D.rows_per_cta = rpc;
+            const long long ditems = (long long)g.n_trials * ncb * ((nrow_d + rpc - 1) / rpc);
+            long long dgrid = ditems;
+            if (dgrid > (long long)c->n_sm * 64) dgrid = (long long)c->n_sm * 64;
+            const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32);
+            if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
+            else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
+            TM_CUDA(c, cudaGetLastError());
+            A.pstar = c->pstar_dev;
+            if (c->strict) { if (stats) TM_LAUNCH(false, true, 2, true, false); else TM_LAUNCH(false, true, 2, false, false); }
+            else           { if (stats) TM_LAUNCH(false, false, 2, true, false); else TM_LAUNCH(false, false, 2, false, false); }
+            c->launches_this_call += 1;
         }
 #undef TM_LAUNCH
     } else {
@@ -371,6 +412,7 @@ int tm_step(tm_ctx *c, int nsteps)
     TM_CUDA(c, cudaSetDevice(c->device));
     if (push_trial_consts(c) != TM_OK) return TM_E_CUDA;
     if (!c->g.wrap && nsteps > 1) TM_FAIL(c, TM_E_ARG, "tm_step: a row slab advances one step per halo exchange");
+    c->launches_this_call = 0;
     TM_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (int s = 0; s < nsteps; s++) {
         const int rc = launch_step(c, s == nsteps - 1, false, 0, false);
@@ -378,7 +420,7 @@ int tm_step(tm_ctx *c, int nsteps)
         c->cur ^= 1; c->step++;
     }
     TM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
-    c->last_launches = nsteps;
+    c->last_launches = nsteps + c->launches_this_call;
     if (nsteps > 0) c->stats_valid = true;
     return TM_OK;
 }
@@ -495,7 +537,7 @@ int tm_measure(tm_ctx *c, tm_stats *out)
         TM_CUDA(c, cudaGetLastError());
         c->stats_valid = true;
     }
-    stats_finalize_kernel<<<(g.n_trials + 127) / 128, 128, 0, c->stream>>>(c->partials, n_records, g.n_trials,
+    stats_finalize_kernel<<<g.n_trials, 128, 128 * 8 * sizeof(double), c->stream>>>(c->partials, n_records, g.n_trials,
                                                                             (double)((long long)g.nrows * g.L), c->stats_dev);
     TM_CUDA(c, cudaGetLastError());
     std::vector<TmStatsDev> h(g.n_trials);

@@ -78,6 +78,7 @@ def lib():
         "tm_destroy": (i, [vp]),
         "tm_set_trial_a": (i, [vp, i, C.c_double]),
         "tm_set_strict": (i, [vp, i]),
+        "tm_set_fused": (i, [vp, i]),
         "tm_upload": (i, [vp, dp]),
         "tm_download": (i, [vp, dp]),
         "tm_n_fields": (i, [vp]),
@@ -107,7 +108,7 @@ def lib():
 
 ABI_SYMBOLS = [
     "tm_abi_version", "tm_device_count", "tm_last_error", "tm_create", "tm_create_slab", "tm_destroy",
-    "tm_set_trial_a", "tm_set_strict", "tm_upload", "tm_download", "tm_n_fields", "tm_seed",
+    "tm_set_trial_a", "tm_set_strict", "tm_set_fused", "tm_upload", "tm_download", "tm_n_fields", "tm_seed",
     "tm_set_step_counter", "tm_step_counter", "tm_step", "tm_step_replay", "tm_dornic_only",
     "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream", "tm_measure",
     "tm_sampler_overflow", "tm_sync", "tm_last_step_ms", "tm_run_host",
@@ -158,6 +159,9 @@ class Lattice:
 
     def set_strict(self, strict=True):
         self._ck(self._l.tm_set_strict(self._ctx, 1 if strict else 0))
+
+    def set_fused(self, fused=True):
+        self._ck(self._l.tm_set_fused(self._ctx, 1 if fused else 0))
 
     def upload(self, fields):
         a = np.ascontiguousarray(fields, dtype=np.float64)
