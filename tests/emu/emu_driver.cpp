@@ -72,6 +72,7 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
             A.g = g; A.c = riet_consts(*p);
             A.in = bufs[cur].data(); A.out = bufs[cur ^ 1].data();
             A.rk = philox_keys(seed);
+            static double logtab[256]; make_log_table(logtab); A.logtab = logtab;
             A.a_trial = a_trial.data(); A.seed = seed; A.trial0 = trial0; A.step = step0 + s;
             A.replay_u = replay_u; A.stride = stride;
             A.partials = partials.data(); A.max_segs = max_segs; A.counters = counters; A.dornic_out = nullptr;
@@ -87,8 +88,8 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
                 std::vector<double> pstar((size_t)g.n_trials * g.field_stride, 0.0);
                 DornicArgs D{};
                 D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.in = A.in; D.pstar = pstar.data();
-                D.seed = seed; D.trial0 = trial0; D.step = step0 + s; D.rk = A.rk; D.row_lo = 0; D.row_hi = g.nrows; D.rows_per_cta = 7;
-                const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32);
+                D.seed = seed; D.trial0 = trial0; D.step = step0 + s; D.rk = A.rk; D.logtab = A.logtab; D.row_lo = 0; D.row_hi = g.nrows; D.rows_per_cta = 7;
+                const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32) + sizeof(double) * 256;
                 if (strict) emu_launch(riet_dornic_kernel<true>, D, 3, kDornicThreads, dsmem);
                 else        emu_launch(riet_dornic_kernel<false>, D, 3, kDornicThreads, dsmem);
                 A.pstar = pstar.data();

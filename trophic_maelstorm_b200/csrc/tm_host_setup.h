@@ -48,6 +48,7 @@ static inline RietConsts riet_consts(const tm_params &p)
     c.eps = p.clamp_eps; c.lo = p.clamp_lo;
     c.dk = dornic_consts(p, p.a);
     c.inv_lambda = 1.0 / c.dk.lambda;
+    c.aK2W0 = c.alpha * c.K2W0; c.cP = -(c.d + 4 * c.Dp); c.cW = -(c.rW + 4 * c.Dw); c.cO = -4 * c.Do;
     return c;
 }
 
@@ -75,6 +76,12 @@ static inline PhiloxKeys philox_keys(unsigned long long seed)
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; r++) { rk.k[r][0] = k0; rk.k[r][1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
     return rk;
+}
+
+// FAST-mode log table: c_i = 1 + (i + 1/2)/128, {1/c_i, log c_i}
+static inline void make_log_table(double *tab /* [128][2] */)
+{
+    for (int i = 0; i < 128; i++) { const double ci = 1.0 + (i + 0.5) / 128.0; tab[2 * i] = 1.0 / ci; tab[2 * i + 1] = std::log(ci); }
 }
 
 // fills the layout part of Geom for a slab [row0,row0+nrows) of an L x L lattice

@@ -58,6 +58,7 @@ struct RietConsts {
     double W0;
     double eps, lo;      // clamp
     double inv_lambda;   // 1/dk.lambda (FAST arithmetic only)
+    double aK2W0, cP, cW, cO; // FAST: alpha*K2*W0, -(d+4Dp), -(rW+4Dw), -4Do
     DornicConsts dk;
 };
 
@@ -92,6 +93,7 @@ struct StepArgs {
     double *dornic_out;           // DORNIC_ONLY: rho* [n_trials][nrows][L] (unpadded)
     const double *pstar;          // kSrcPre: rho* in the padded layout, [n_trials][rows_alloc][Lp]
     PhiloxKeys rk;                // the ten round keys of `seed` (host-computed)
+    const double *logtab;         // device copy of the FAST-mode log table [128][2]
 };
 
 // ------------------------------------------------------------------------------------------
@@ -171,30 +173,25 @@ TM_D double sqrt_lean(double a)
     return sqrt(a);
 #endif
 }
-// log(x) for x in (0,1] (the polar method's r2), same reduction and polynomial as log_pos but with
-// the lean reciprocal instead of an IEEE division.
-TM_D double log_lean(double x)
+// log(x) for x in (0,1] (the polar method's r2), FAST arithmetic: x = 2^k m, m in [1,2); the top 7 mantissa
+// bits pick c_i = 1 + (i + 1/2)/128 from a 128-entry table {1/c_i, log c_i}; r = m/c_i - 1 is below 2^-8 and
+// log m = log c_i + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5 - r^6/6).  No division; ~1e-16 absolute.
+struct LogTab { double invc[128], logc[128]; };
+TM_D double log_lean(double x, const double *tab /* [128][2] = {invc, logc} */)
 {
-    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
-                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
-                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-                 Lg7 = 1.479819860511658591e-01;
-    uint64_t b = d2u(x);
-    int k = (int)(b >> 52) - 1023;
-    const uint64_t mant = b & 0x000FFFFFFFFFFFFFull;
-    if (mant > 0x6A09E667F3BCCull) { b = mant | 0x3FE0000000000000ull; k += 1; }
-    else                           { b = mant | 0x3FF0000000000000ull; }
-    const double f = u2d(b) - 1.0;
-    const double dk = (double)k;
-    const double s = f * rcp_lean(2.0 + f);
-    const double z = s * s;
-    const double w = z * z;
-    const double t1 = w * fma(w, fma(w, Lg6, Lg4), Lg2);
-    const double t2 = z * fma(w, fma(w, fma(w, Lg7, Lg5), Lg3), Lg1);
-    const double R = t2 + t1;
-    const double hfsq = 0.5 * f * f;
-    return dk * ln2_hi - ((hfsq - fma(s, hfsq + R, dk * ln2_lo)) - f);
+    const double ln2 = 6.93147180559945286227e-01;
+    const uint64_t b = d2u(x);
+    const int k = (int)(b >> 52) - 1023;
+    const int i = (int)((b >> 45) & 127);
+    const double m = u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    const double invc = tab[2 * i], logc = tab[2 * i + 1];
+    const double r = fma(m, invc, -1.0);
+    double p = fma(r, -1.0 / 6.0, 1.0 / 5.0);
+    p = fma(r, p, -1.0 / 4.0);
+    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, -0.5);
+    p = fma(r * r, p, r);
+    return fma((double)k, ln2, logc) + p;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -223,16 +220,11 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
         const double wk = W + c.K1, pk = P + c.K2;
         const double r = rcp_lean(wk * pk);
         const double q = (W * P) * (pk * r);                 // W P / (W + K1)
-        const double infil = c.alpha * (P + c.K2W0) * (wk * r) * O;
-        const double lapW = fma(-4.0, W, (Wu + Wd) + (Wl + Wr));
-        const double lapO = fma(-4.0, O, (Ou + Od) + (Ol + Or_));
+        const double infil = fma(c.alpha, P, c.aK2W0) * (wk * r) * O;
         f.p = c.cgmax * q;
-        if (DET) {
-            const double lapP = fma(-4.0, P, (Pu + Pd) + (Pl + Pr));
-            f.p = fma(c.Dp, lapP, fma(-c.d, P, f.p));
-        }
-        f.w = fma(c.Dw, lapW, fma(-c.rW, W, fma(-c.gmax, q, infil)));
-        f.o = fma(c.Do, lapO, a - infil);
+        if (DET) f.p = fma(c.Dp, (Pu + Pd) + (Pl + Pr), fma(c.cP, P, f.p));     // cP = -(d + 4 Dp)
+        f.w = fma(c.Dw, (Wu + Wd) + (Wl + Wr), fma(c.cW, W, fma(-c.gmax, q, infil))); // cW = -(rW + 4 Dw)
+        f.o = fma(c.Do, (Ou + Od) + (Ol + Or_), fma(c.cO, O, a - infil));             // cO = -4 Do
     }
     return f;
 }
@@ -343,8 +335,10 @@ TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t
         c0 = h1 ^ c1 ^ rk.k[r][0]; c1 = l1;
         c2 = h0 ^ c3 ^ rk.k[r][1]; c3 = l0;
     }
-    x = 2.0 * u52(c0, c1) - 1.0;
-    y = 2.0 * u52(c2, c3) - 1.0;
+    // 2u - 1 with u = u52(.): both steps are exact, so (2m) - 3 with m the [1,2) mantissa double is the
+    // same number in one operation: as_double(0x400.. | w >> 12) = 2m
+    x = u2d(0x4000000000000000ull | ((((uint64_t)c1 << 32) | c0) >> 12)) - 3.0;
+    y = u2d(0x4000000000000000ull | ((((uint64_t)c3 << 32) | c2) >> 12)) - 3.0;
     r2 = fma(x, x, y * y);
     return !(r2 > 1.0 || r2 == 0.0);
 }
@@ -358,7 +352,7 @@ TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t
 // Must be called by all 32 lanes of a warp (trial/step/seed warp-uniform).
 template <bool STRICT>
 TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t step, const PhiloxKeys &rk,
-                          uint32_t *warp_scratch, double &n_first, double &n_second)
+                          uint32_t *warp_scratch, const double *logtab, double &n_first, double &n_second)
 {
     double x = 0.5, y = 0.5, r2 = 0.5;
     bool ok = true;
@@ -405,7 +399,7 @@ TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t ste
     if (!ok) { x = 0.5; y = 0.5; r2 = 0.5; } // bound reached (never with genuine uniforms)
     double mult;
     if (STRICT) mult = sqrt(-2.0 * log_pos(r2) / r2);            // LS:1832
-    else        mult = sqrt_lean(-2.0 * log_lean(r2) * rcp_lean(r2));
+    else        mult = sqrt_lean(-2.0 * log_lean(r2, logtab) * rcp_lean(r2));
     n_second = x * mult;
     n_first = y * mult;
 }
@@ -436,6 +430,7 @@ riet_step_kernel(const StepArgs A)
     if (st_doubles < 8 * (size_t)nthreads) st_doubles = 8 * (size_t)nthreads;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(st + st_doubles);
     uint32_t *wscratch = reinterpret_cast<uint32_t *>(mbar + kInSlots) + 32 * (tid >> 5); // warp-private
+    const double *logtab = A.logtab; // 2 KB, read through L1 (shared memory is fully booked by the rings at 4 CTAs/SM)
 
     if (tid == 0) {
         for (int s = 0; s < kInSlots; s++) mbar_init(&mbar[s], 1);
@@ -543,11 +538,12 @@ riet_step_kernel(const StepArgs A)
                     // (Poisson mean <= 100 or Gamma shape <= 100: the extinction fringe) out of line.
                     const uint32_t ptrial = A.trial0 + (uint32_t)trial;
                     const double ziggy = c.dk.ll * Pc;
-                    const double mu1 = (-1.0 + 2.0 * alpha_i * c.dk.sigma2_1) + 1.0; // mu + 1.0 in the reference's order
+                    const double mu1 = STRICT ? (-1.0 + 2.0 * alpha_i * c.dk.sigma2_1) + 1.0  // mu + 1.0 in the reference's order
+                                              : 2.0 * alpha_i * c.dk.sigma2_1;
                     const bool gauss_n = live && ziggy > 100;
                     const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
                     double n_first, n_second;
-                    polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, n_first, n_second);
+                    polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, logtab, n_first, n_second);
                     bool exact = live && !fastp;
                     if (fastp) {
                         double gru = mu1, nz = n_first;
@@ -668,6 +664,7 @@ struct DornicArgs {
     PhiloxKeys rk;
     int row_lo, row_hi;            // lattice-local rows [row_lo, row_hi) to sample (slabs: -3 .. nrows+3)
     int rows_per_cta;              // rows one CTA marches through
+    const double *logtab;          // device copy of the FAST-mode log table [128][2]
 };
 
 constexpr int kDornicThreads = 256;
@@ -685,6 +682,8 @@ riet_dornic_kernel(const DornicArgs A)
     const int tid = threadIdx.x;
     TM_DYN_SMEM(smem_raw);
     uint32_t *wscratch = reinterpret_cast<uint32_t *>(smem_raw) + 32 * (tid >> 5);
+    double *logtab = reinterpret_cast<double *>(reinterpret_cast<uint32_t *>(smem_raw) + 32 * (kDornicThreads / 32)); // [128][2]
+    if (!STRICT) { logtab[tid] = A.logtab[tid]; __syncthreads(); }
     // work item = (trial, column block of 256, run of rows_per_cta rows)
     const int ncb = (g.L + kDornicThreads - 1) / kDornicThreads;
     const int nrow = A.row_hi - A.row_lo;
@@ -729,11 +728,11 @@ riet_dornic_kernel(const DornicArgs A)
             const bool live = !(alpha_i == 0 && Pc == 0) && valid;            // skip rule R/:3759
             const uint32_t cell = (uint32_t)grow * (uint32_t)g.L + (uint32_t)qc;
             const double ziggy = dk.ll * Pc;
-            const double mu1 = (-1.0 + 2.0 * alpha_i * dk.sigma2_1) + 1.0;
+            const double mu1 = STRICT ? (-1.0 + 2.0 * alpha_i * dk.sigma2_1) + 1.0 : 2.0 * alpha_i * dk.sigma2_1;
             const bool gauss_n = live && ziggy > 100;
             const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
             double n_first, n_second;
-            polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, n_first, n_second);
+            polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, logtab, n_first, n_second);
             bool exact = live && !fastp;
             if (fastp) {
                 double gru = mu1, nz = n_first;

@@ -37,6 +37,7 @@ struct tm_ctx {
     double *replay_dev = nullptr;
     size_t replay_cap = 0;
     double *dornic_dev = nullptr;
+    double *logtab_dev = nullptr;  // FAST-mode log table
     double *pstar_dev = nullptr;   // rho* scratch field of the split Dornic / RK4 kernel pair
     bool fused = true;             // false: Dornic sweep + RK4 kernel pair instead of the fused kernel
     double *halo_dev[2] = {nullptr, nullptr};
@@ -94,6 +95,12 @@ static int alloc_all(tm_ctx *c)
     TM_CUDA(c, cudaMalloc(&c->a_dev, sizeof(double) * g.n_trials));
     TM_CUDA(c, cudaMalloc(&c->dp_trials_dev, sizeof(DpTrial) * g.n_trials));
     TM_CUDA(c, cudaMalloc(&c->stats_dev, sizeof(TmStatsDev) * g.n_trials));
+    {
+        double tab[256];
+        make_log_table(tab);
+        TM_CUDA(c, cudaMalloc(&c->logtab_dev, sizeof tab));
+        TM_CUDA(c, cudaMemcpy(c->logtab_dev, tab, sizeof tab, cudaMemcpyHostToDevice));
+    }
     TM_CUDA(c, cudaMalloc(&c->counters, sizeof(unsigned long long) * 4));
     TM_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 4, c->stream));
     // launch geometry
@@ -204,7 +211,7 @@ int tm_destroy(tm_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int s = 0; s < 2; s++) { cudaFree(c->buf[s]); cudaFree(c->halo_dev[s]); }
     cudaFree(c->a_dev); cudaFree(c->dp_trials_dev); cudaFree(c->partials); cudaFree(c->stats_dev);
-    cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev); cudaFree(c->pstar_dev);
+    cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev); cudaFree(c->pstar_dev); cudaFree(c->logtab_dev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -319,7 +326,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
         StepArgs A{};
         A.g = g; A.c = riet_consts(p);
         A.in = c->buf[c->cur]; A.out = c->buf[c->cur ^ 1];
-        A.rk = philox_keys(c->seed);
+        A.rk = philox_keys(c->seed); A.logtab = c->logtab_dev;
         A.a_trial = c->a_dev; A.seed = c->seed; A.trial0 = c->trial0; A.step = (unsigned int)c->step;
         A.replay_u = c->replay_dev; A.stride = stride;
         A.partials = c->partials; A.max_segs = c->max_segs; A.counters = c->counters; A.dornic_out = c->dornic_dev;
@@ -347,7 +354,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             }
             DornicArgs D{};
             D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.in = A.in; D.pstar = c->pstar_dev;
-            D.seed = c->seed; D.trial0 = c->trial0; D.step = (unsigned int)c->step; D.rk = A.rk;
+            D.seed = c->seed; D.trial0 = c->trial0; D.step = (unsigned int)c->step; D.rk = A.rk; D.logtab = c->logtab_dev;
             D.row_lo = g.wrap ? 0 : -(kHalo - 1); D.row_hi = g.wrap ? g.nrows : g.nrows + (kHalo - 1);
             // rows per CTA: enough (trial, column block, run) items for ~2 rounds over 4 resident CTAs per SM
             const int ncb = (g.L + kDornicThreads - 1) / kDornicThreads, nrow_d = D.row_hi - D.row_lo;
@@ -359,7 +366,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             const long long ditems = (long long)g.n_trials * ncb * ((nrow_d + rpc - 1) / rpc);
             long long dgrid = ditems;
             if (dgrid > (long long)c->n_sm * 64) dgrid = (long long)c->n_sm * 64;
-            const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32);
+            const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32) + sizeof(double) * 256;
             if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
             else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
             TM_CUDA(c, cudaGetLastError());
