@@ -62,12 +62,9 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
     for (int s = 0; s < nsteps; s++) {
         const bool stats = (s == nsteps - 1);
         if (is_riet(p->model)) {
-            int grid, max_segs;
-            riet_launch_shape(g, n_sm, &grid, &max_segs);
-            if (grid_override > 0) { grid = grid_override; max_segs = (int)(((long long)g.n_trials * g.ns * g.nrows / grid + 1) / g.nrows) + 3; }
-            n_records = grid * max_segs;
-            partials.assign(n_records, PartialStats{});
-            for (auto &r : partials) r.trial = -1;
+            int grid;
+            riet_launch_shape(g, n_sm, &grid);
+            if (grid_override > 0) grid = grid_override;
             StepArgs A{};
             A.g = g; A.c = riet_consts(*p);
             A.in = bufs[cur].data(); A.out = bufs[cur ^ 1].data();
@@ -75,15 +72,15 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
             static double logtab[256]; make_log_table(logtab); A.logtab = logtab;
             A.a_trial = a_trial.data(); A.seed = seed; A.trial0 = trial0; A.step = step0 + s;
             A.replay_u = replay_u; A.stride = stride;
-            A.partials = partials.data(); A.max_segs = max_segs; A.counters = counters; A.dornic_out = nullptr;
+            A.counters = counters; A.dornic_out = nullptr;
             const bool det = p->model == TM_MODEL_RIETKERK_DET;
             const size_t smem = riet_smem_bytes(g.nthreads, det);
             if (det) {
-                if (strict) emu_launch(riet_step_kernel<true, true, false, true, false>, A, grid, g.nthreads, smem);
-                else        emu_launch(riet_step_kernel<true, false, false, true, false>, A, grid, g.nthreads, smem);
+                if (strict) emu_launch(riet_step_kernel<true, true, kSrcPhilox, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<true, false, kSrcPhilox, false>, A, grid, g.nthreads, smem);
             } else if (replay_u) {
-                if (strict) emu_launch(riet_step_kernel<false, true, true, true, false>, A, grid, g.nthreads, smem);
-                else        emu_launch(riet_step_kernel<false, false, true, true, false>, A, grid, g.nthreads, smem);
+                if (strict) emu_launch(riet_step_kernel<false, true, kSrcReplay, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<false, false, kSrcReplay, false>, A, grid, g.nthreads, smem);
             } else if (g_split) {
                 std::vector<double> pstar((size_t)g.n_trials * g.field_stride, 0.0);
                 DornicArgs D{};
@@ -93,11 +90,19 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
                 if (strict) emu_launch(riet_dornic_kernel<true>, D, 3, kDornicThreads, dsmem);
                 else        emu_launch(riet_dornic_kernel<false>, D, 3, kDornicThreads, dsmem);
                 A.pstar = pstar.data();
-                if (strict) emu_launch(riet_step_kernel<false, true, 2, true, false>, A, grid, g.nthreads, smem);
-                else        emu_launch(riet_step_kernel<false, false, 2, true, false>, A, grid, g.nthreads, smem);
+                if (strict) emu_launch(riet_step_kernel<false, true, kSrcPre, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<false, false, kSrcPre, false>, A, grid, g.nthreads, smem);
             } else {
-                if (strict) emu_launch(riet_step_kernel<false, true, false, true, false>, A, grid, g.nthreads, smem);
-                else        emu_launch(riet_step_kernel<false, false, false, true, false>, A, grid, g.nthreads, smem);
+                if (strict) emu_launch(riet_step_kernel<false, true, kSrcPhilox, false>, A, grid, g.nthreads, smem);
+                else        emu_launch(riet_step_kernel<false, false, kSrcPhilox, false>, A, grid, g.nthreads, smem);
+            }
+            if (stats) { // Rietkerk reductions: the stand-alone pass, as tm_measure() runs it
+                const int bpt = 3;
+                n_records = bpt * n_trials;
+                partials.assign(n_records, PartialStats{});
+                for (auto &r : partials) r.trial = -1;
+                StatsArgs S{g, bufs[cur ^ 1].data(), partials.data(), bpt};
+                emu_launch(stats_kernel, S, bpt * n_trials, 64, sizeof(double) * 8 * 64);
             }
         } else {
             std::vector<DpTrial> trials(n_trials);
@@ -122,7 +127,6 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
                 else          emu_launch(dp_step_kernel<kDPCubic, false, true, false>, A, bpt * n_trials, 64, smem);
             }
         }
-        (void)stats;
         cur ^= 1;
     }
     unpack(g, bufs[cur], fields);

@@ -76,6 +76,44 @@ def test_split_pair_equals_fused_kernel():
     assert np.array_equal(out[(True, False)][1], want)
 
 
+@pytest.mark.parametrize("L,n_trials", [(8, 3), (9, 2), (17, 5), (33, 300)])
+def test_rietkerk_small_and_odd_lattices(L, n_trials):
+    """Edge geometries: minimum L, odd L (ragged strips, odd pitch), many more trials than SMs."""
+    p = tm.rietkerk_params(L)
+    frames = np.stack([O.synthetic_rietkerk_frame(L, seed=100 + t) for t in range(n_trials)])
+    lat = tm.Lattice(p, n_trials)
+    lat.set_strict(True)
+    lat.seed(11, trial0=7)
+    lat.upload(frames)
+    lat.step(2)
+    got = lat.download()
+    st = lat.measure()
+    for t in sorted(set([0, 1, n_trials // 2, n_trials - 1])):
+        want = oracle_steps(p, frames[t], 2, 11, 7 + t)
+        assert np.array_equal(got[t], want), "trial %d" % t
+        assert st[t].active[0] == int(O.occupied(want[0]))
+    lat.close()
+
+
+def test_extinct_lattice_stays_extinct_and_empty_inputs():
+    """All-zero vegetation: the skip rule (R/:3759) draws nothing, P stays exactly 0, water relaxes."""
+    L = 40
+    p = tm.rietkerk_params(L)
+    frame = O.synthetic_rietkerk_frame(L, seed=1)
+    frame[0] = 0.0
+    lat = tm.Lattice(p, 1)
+    lat.seed(3)
+    lat.upload(frame[None])
+    lat.step(5)
+    got = lat.download()[0]
+    assert np.all(got[0] == 0.0)
+    assert np.array_equal(got, oracle_steps(p, frame, 5, 3, 0)) or np.allclose(got, oracle_steps(p, frame, 5, 3, 0), rtol=1e-12)
+    st = lat.measure()
+    assert st[0].active[0] == 0 and st[0].active[1] == L * L
+    lat.step(0)   # zero steps is a no-op
+    lat.close()
+
+
 @pytest.mark.parametrize("L", [64, 250])
 def test_rietkerk_fast_per_step(L):
     """Per-step parity (north_star): each GPU step starts from the oracle's state."""

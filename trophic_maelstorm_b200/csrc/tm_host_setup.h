@@ -97,16 +97,14 @@ static inline void make_geom(const tm_params &p, int n_trials, int row0, int nro
     g->trial_stride = g->field_stride * g->n_fields;
 }
 
-// grid of the persistent Rietkerk kernel (n_cta_slots = SMs x resident CTAs per SM) and the
-// statistics-record budget per CTA
-static inline void riet_launch_shape(const Geom &g, int n_cta_slots, int *grid, int *max_segs)
+// grid of the persistent Rietkerk kernel (n_cta_slots = SMs x resident CTAs per SM)
+static inline void riet_launch_shape(const Geom &g, int n_cta_slots, int *grid)
 {
     const long long total = (long long)g.n_trials * g.ns * g.nrows;
     long long gr = total / 16;
     if (gr < 1) gr = 1;
     if (gr > n_cta_slots) gr = n_cta_slots;
     *grid = (int)gr;
-    *max_segs = (int)((total / gr + 1) / g.nrows) + 3;
 }
 
 } // namespace tml

@@ -1,8 +1,10 @@
 // tm_kernels.cuh -- sm_100a kernels of the Dornic lattice step.
 //
 //   riet_step_kernel   Rietkerk SPB=1: vegetation Dornic (R/:3752-3809) + classical RK4 over
-//                      (P,W,O) with f_2Dor (R/:2359-2440) + clamp/commit (R/:4150-4181) + the
-//                      <rho>_x / active-site reductions (R/:1211,1245), all in ONE pass over HBM.
+//                      (P,W,O) with f_2Dor (R/:2359-2440) + clamp/commit (R/:4150-4181) in ONE pass over HBM.
+//                      (The <rho>_x / active-site reductions, R/:1211,1245, run as stats_kernel when a
+//                      measurement is due: fusing them here cost 0.36 ms per measuring step in register
+//                      spills against 0.08 ms for the separate 403 MB pass -- profiles/README.md.)
 //                      DET=true is the noise-off path: RK4 with the full RHS f_2D (R/:1718-1814).
 //   dp_step_kernel     DP / cubic DP: Dornic (P/:1032-1061) + closed form (P/:1064-1068) or
 //                      pointwise RK4 (P/:1775-1790) + reductions (P/:123,145).
@@ -87,8 +89,6 @@ struct StepArgs {
     unsigned int trial0, step;
     const double *replay_u;       // REPLAY: [n_trials][L*L][stride] (global cell order)
     unsigned int stride;
-    PartialStats *partials;       // [gridDim.x][max_segs]
-    int max_segs;
     unsigned long long *counters; // [0] sampler/replay overflow, [1] pipeline timeouts
     double *dornic_out;           // DORNIC_ONLY: rho* [n_trials][nrows][L] (unpadded)
     const double *pstar;          // kSrcPre: rho* in the padded layout, [n_trials][rows_alloc][Lp]
@@ -292,7 +292,6 @@ TM_D void flush_stats(const ThreadStats &ts, int n_fields, int trial, PartialSta
 //   in   [kInSlots][3][RW]    TMA destination rows (P,W,O) = stage-0 state, rows j-4 .. j+kPrefetch
 //   st   [3][kStSlots][NF][RW] stage-1/2/3 states (W,O[,P]) of the last kStSlots rows of each front
 //   mbar uint64[kInSlots]
-// (the statistics flush aliases `st`).
 constexpr int kInSlots = 8;
 constexpr int kStSlots = 3;
 constexpr int kPrefetch = 3;
@@ -303,8 +302,8 @@ TM_HD size_t riet_smem_bytes(int nthreads, bool det)
 {
     const size_t RW = (size_t)kRW;
     const size_t nf = det ? 3 : 2;
-    size_t st = 3 * kStSlots * nf * RW;
-    if (st < 8 * (size_t)nthreads) st = 8 * (size_t)nthreads;
+    const size_t st = 3 * kStSlots * nf * RW;
+    (void)nthreads;
     return sizeof(double) * (kInSlots * 3 * RW + st) + sizeof(uint64_t) * kInSlots + sizeof(uint32_t) * 32 * (kMaxThreads / 32) + 128;
 }
 
@@ -411,7 +410,7 @@ TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t ste
 // long serial sampler chain runs at full occupancy in its own kernel, this one keeps only the RK4 fronts).
 enum { kSrcPhilox = 0, kSrcReplay = 1, kSrcPre = 2 };
 
-template <bool DET, bool STRICT, int SRC, bool STATS, bool DORNIC_ONLY>
+template <bool DET, bool STRICT, int SRC, bool DORNIC_ONLY>
 #if defined(__CUDACC__)
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 #else
@@ -428,8 +427,7 @@ riet_step_kernel(const StepArgs A)
     TM_DYN_SMEM(smem_raw);
     double *in = reinterpret_cast<double *>(smem_raw);
     double *st = in + kInSlots * 3 * RW;
-    size_t st_doubles = (size_t)3 * kStSlots * NF * RW;
-    if (st_doubles < 8 * (size_t)nthreads) st_doubles = 8 * (size_t)nthreads;
+    const size_t st_doubles = (size_t)3 * kStSlots * NF * RW;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(st + st_doubles);
     uint32_t *wscratch = reinterpret_cast<uint32_t *>(mbar + kInSlots) + 32 * (tid >> 5); // warp-private
     const double *logtab = A.logtab; // 2 KB, read through L1 (shared memory is fully booked by the rings at 4 CTAs/SM)
@@ -452,7 +450,6 @@ riet_step_kernel(const StepArgs A)
     const bool col_in_strip = cx < TXH;
 
     long long seq = 0;   // rows consumed so far (ring slot / phase bookkeeping)
-    int seg_no = 0;
     bool timeout = false;
 
     for (long long w = w0; w < w1;) {
@@ -498,7 +495,6 @@ riet_step_kernel(const StepArgs A)
         double Ps_m4 = 0, Ps_m3 = 0, Ps_m2 = 0;
         double P1_m2 = 0, P2_m3 = 0, P3_m4 = 0;
         double aP_m4 = 0, aP_m3 = 0, aP_m2 = 0, aW_m4 = 0, aW_m3 = 0, aW_m2 = 0, aO_m4 = 0, aO_m3 = 0, aO_m2 = 0;
-        ThreadStats tstat; tstat.clear();
         // stage-ring slot offsets (in doubles) of rows j, j-1, j-2 (mod 3), rotated per step
         int m0 = (int)(seq % kStSlots) * NF * RW, m1 = (int)((seq + 2) % kStSlots) * NF * RW, m2 = (int)((seq + 1) % kStSlots) * NF * RW;
         double *const stc = st + 2 + cx;
@@ -620,7 +616,6 @@ riet_step_kernel(const StepArgs A)
                     po[0] = nP; po[g.field_stride] = nW; po[2 * g.field_stride] = nO;
                     if (gx < kHalo) { po[g.L] = nP; po[g.field_stride + g.L] = nW; po[2 * g.field_stride + g.L] = nO; }
                     if (gx >= g.L - kHalo) { po[-g.L] = nP; po[g.field_stride - g.L] = nW; po[2 * g.field_stride - g.L] = nO; }
-                    if (STATS) { tstat.add(0, nP); tstat.add(1, nW); tstat.add(2, nO); }
                 }
                 // ---- shift the register windows by one row -------------------------------------------
                 P3_m4 = P3_m3; P2_m3 = P2_m2; P1_m2 = P1_m1;
@@ -636,11 +631,6 @@ riet_step_kernel(const StepArgs A)
             if (tid == 0 && j + kPrefetch + 1 <= jhi) issue(j + kPrefetch + 1, seq + kPrefetch + 1);
         }
 
-        if (STATS && !DORNIC_ONLY) {
-            PartialStats *rec = A.partials + (size_t)blockIdx.x * A.max_segs + (seg_no < A.max_segs ? seg_no : A.max_segs - 1);
-            flush_stats(tstat, 3, trial, rec, st, tid, nthreads);
-        }
-        seg_no++;
     }
     if (timeout && tid == 0) atomicAdd(&A.counters[1], 1ull);
 }

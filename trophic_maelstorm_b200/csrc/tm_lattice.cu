@@ -31,7 +31,7 @@ struct tm_ctx {
     DpTrial *dp_trials_dev = nullptr;
     bool trial_consts_dirty = true;
     PartialStats *partials = nullptr;
-    int n_records = 0, grid = 0, max_segs = 0, dp_blocks_per_trial = 0;
+    int n_records = 0, grid = 0, dp_blocks_per_trial = 0;
     TmStatsDev *stats_dev = nullptr;
     unsigned long long *counters = nullptr;
     double *replay_dev = nullptr;
@@ -105,8 +105,8 @@ static int alloc_all(tm_ctx *c)
     TM_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(unsigned long long) * 4, c->stream));
     // launch geometry
     if (is_riet(c->p.model)) {
-        riet_launch_shape(g, c->n_sm * c->riet_occ, &c->grid, &c->max_segs);
-        c->n_records = c->grid * c->max_segs;
+        riet_launch_shape(g, c->n_sm * c->riet_occ, &c->grid);
+        c->n_records = 0;
     } else {
         const long long ncell = (long long)g.nrows * g.L;
         long long bpt = (ncell + 256 * 4 - 1) / (256 * 4);
@@ -169,26 +169,20 @@ int tm_create_slab(const tm_params *p, int n_trials, int device, int row0, int n
         const int smem_s = (int)riet_smem_bytes(g.nthreads, false), smem_d = (int)riet_smem_bytes(g.nthreads, true);
         bool ok = true;
 #define TM_OPTIN(K, B) ok = ok && (cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, B) == cudaSuccess)
-        TM_OPTIN((riet_step_kernel<false, false, false, false, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, false, false, true, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, true, false, false, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, true, false, true, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, false, true, true, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, true, true, true, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, true, false, false, true>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, true, true, false, true>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, false, 2, false, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, false, 2, true, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, true, 2, false, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<false, true, 2, true, false>), smem_s);
-        TM_OPTIN((riet_step_kernel<true, false, false, false, false>), smem_d);
-        TM_OPTIN((riet_step_kernel<true, false, false, true, false>), smem_d);
-        TM_OPTIN((riet_step_kernel<true, true, false, false, false>), smem_d);
-        TM_OPTIN((riet_step_kernel<true, true, false, true, false>), smem_d);
+        TM_OPTIN((riet_step_kernel<false, false, kSrcPhilox, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, kSrcPhilox, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, kSrcReplay, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, kSrcReplay, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, false, kSrcPre, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, kSrcPre, false>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, kSrcPhilox, true>), smem_s);
+        TM_OPTIN((riet_step_kernel<false, true, kSrcReplay, true>), smem_s);
+        TM_OPTIN((riet_step_kernel<true, false, kSrcPhilox, false>), smem_d);
+        TM_OPTIN((riet_step_kernel<true, true, kSrcPhilox, false>), smem_d);
 #undef TM_OPTIN
         if (!ok) { cudaGetLastError(); return create_fail(c, TM_E_CUDA, "tm_create: cudaFuncSetAttribute(shared memory) failed"); }
         int occ = 1; // resident CTAs per SM of the production variant: the persistent grid fills exactly that
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, riet_step_kernel<false, false, false, false, false>, g.nthreads,
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, riet_step_kernel<false, false, kSrcPhilox, false>, g.nthreads,
                                                           p->model == TM_MODEL_RIETKERK_DET ? smem_d : smem_s) != cudaSuccess || occ < 1) {
             cudaGetLastError(); occ = 1;
         }
@@ -321,7 +315,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
 {
     const Geom &g = c->g;
     const tm_params &p = c->p;
-    if (stats) TM_CUDA(c, cudaMemsetAsync(c->partials, 0xFF, sizeof(PartialStats) * c->n_records, c->stream));
+    if (stats && !is_riet(p.model)) TM_CUDA(c, cudaMemsetAsync(c->partials, 0xFF, sizeof(PartialStats) * c->n_records, c->stream));
     if (is_riet(p.model)) {
         StepArgs A{};
         A.g = g; A.c = riet_consts(p);
@@ -329,22 +323,21 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
         A.rk = philox_keys(c->seed); A.logtab = c->logtab_dev;
         A.a_trial = c->a_dev; A.seed = c->seed; A.trial0 = c->trial0; A.step = (unsigned int)c->step;
         A.replay_u = c->replay_dev; A.stride = stride;
-        A.partials = c->partials; A.max_segs = c->max_segs; A.counters = c->counters; A.dornic_out = c->dornic_dev;
+        A.counters = c->counters; A.dornic_out = c->dornic_dev;
         const bool det = p.model == TM_MODEL_RIETKERK_DET;
         const size_t smem = riet_smem_bytes(g.nthreads, det);
         const dim3 grid(c->grid), block(g.nthreads);
 #define TM_LAUNCH(...) riet_step_kernel<__VA_ARGS__><<<grid, block, smem, c->stream>>>(A)
+        (void)stats; // Rietkerk reductions run as stats_kernel on demand (tm_measure)
         if (det) {
-            if (c->strict) { if (stats) TM_LAUNCH(true, true, false, true, false); else TM_LAUNCH(true, true, false, false, false); }
-            else           { if (stats) TM_LAUNCH(true, false, false, true, false); else TM_LAUNCH(true, false, false, false, false); }
+            if (c->strict) TM_LAUNCH(true, true, kSrcPhilox, false); else TM_LAUNCH(true, false, kSrcPhilox, false);
         } else if (dornic_only) {
             // the Dornic-only entry point is a checking aid: always the STRICT (IEEE) arithmetic
-            if (replay) TM_LAUNCH(false, true, true, false, true); else TM_LAUNCH(false, true, false, false, true);
+            if (replay) TM_LAUNCH(false, true, kSrcReplay, true); else TM_LAUNCH(false, true, kSrcPhilox, true);
         } else if (replay) {
-            if (c->strict) TM_LAUNCH(false, true, true, true, false); else TM_LAUNCH(false, false, true, true, false);
+            if (c->strict) TM_LAUNCH(false, true, kSrcReplay, false); else TM_LAUNCH(false, false, kSrcReplay, false);
         } else if (c->fused) {
-            if (c->strict) { if (stats) TM_LAUNCH(false, true, false, true, false); else TM_LAUNCH(false, true, false, false, false); }
-            else           { if (stats) TM_LAUNCH(false, false, false, true, false); else TM_LAUNCH(false, false, false, false, false); }
+            if (c->strict) TM_LAUNCH(false, true, kSrcPhilox, false); else TM_LAUNCH(false, false, kSrcPhilox, false);
         } else {
             // alternative: Dornic sweep at full occupancy into a rho* scratch field, then the RK4 fronts only
             if (!c->pstar_dev) {
@@ -371,8 +364,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
             TM_CUDA(c, cudaGetLastError());
             A.pstar = c->pstar_dev;
-            if (c->strict) { if (stats) TM_LAUNCH(false, true, 2, true, false); else TM_LAUNCH(false, true, 2, false, false); }
-            else           { if (stats) TM_LAUNCH(false, false, 2, true, false); else TM_LAUNCH(false, false, 2, false, false); }
+            if (c->strict) TM_LAUNCH(false, true, kSrcPre, false); else TM_LAUNCH(false, false, kSrcPre, false);
             c->launches_this_call += 1;
         }
 #undef TM_LAUNCH
@@ -428,7 +420,7 @@ int tm_step(tm_ctx *c, int nsteps)
     }
     TM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->last_launches = nsteps + c->launches_this_call;
-    if (nsteps > 0) c->stats_valid = true;
+    if (nsteps > 0) c->stats_valid = !is_riet(c->p.model); // DP kernels fuse the reductions; Rietkerk runs stats_kernel on demand
     return TM_OK;
 }
 
@@ -457,7 +449,7 @@ int tm_step_replay(tm_ctx *c, const double *host_uniforms, uint64_t stride)
     if (rc != TM_OK) return rc;
     TM_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     c->cur ^= 1; c->step++;
-    c->last_launches = 1; c->stats_valid = true;
+    c->last_launches = 1; c->stats_valid = !is_riet(c->p.model);
     return TM_OK;
 }
 
