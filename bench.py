@@ -317,6 +317,30 @@ def run_ours(a):
         print(json.dumps(out), flush=True)
 
 
+def run_dp_extra(a):
+    """Not the headline: DP a-sweep (BASELINE config 4 shape) through the same ABI, for the record."""
+    import numpy as np
+    import trophic_maelstorm_b200 as tm
+    L, n_a, K = a.L if a.L != 4096 else 2048, 8, a.steps
+    p = tm.dp_params(L, a=1.0524, b=1.0, D=0.25, sigma=2 ** 0.5, dt=0.1, dx=1.0)
+    lat = tm.Lattice(p, n_a, device=int(os.environ.get("LOCAL_RANK", "0")))
+    for i, av in enumerate(np.linspace(1.0524, 1.0554, n_a)):
+        lat.set_trial_a(i, float(av))
+    lat.seed(7)
+    lat.upload(np.ones((n_a, 1, L, L)))
+    lat.step(max(a.warmup, 3)); lat.sync()
+    lat.step(K); lat.sync()
+    ms, n = lat.last_step_ms()
+    peak, src = measured_peaks()
+    rate = n_a * L * L * K / (ms * 1e-3)
+    print(json.dumps({"metric": "lattice site-updates/sec (FP64, device-timed), DP Dornic step", "value": rate, "unit": UNIT,
+                      "n_gpus": 1, "steps": K, "ms_per_step": ms / K, "dtype": "f64", "data": "synthetic", "gpu_launches": n,
+                      "config": {"workload": "DP Dornic step (percolationDornic_2D), L=%d, %d a-values in [1.0524,1.0554], rho0=1" % (L, n_a)},
+                      "roofline": {"bound": "hbm", "achieved": rate * 16 / 1e9, "peak": peak, "unit": "GB/s", "frac": rate * 16 / 1e9 / peak,
+                                   "traffic": None, "peak_source": src, "note": "16 B per site-update; RNG/ALU-bound by construction"}}), flush=True)
+    lat.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,7 +353,10 @@ def main():
     ap.add_argument("--ref-L", type=int, default=512, help="lattice side of the bounded CPU sample")
     ap.add_argument("--ref-steps", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp"], help="dp: extra, non-headline line")
     a = ap.parse_args()
+    if a.workload == "dp" and a.impl == "ours":
+        return run_dp_extra(a)
     if a.impl == "reference":
         run_reference_arm(a)
     else:

@@ -176,3 +176,36 @@ def test_config1_driver_binary(tmp_path):
     assert rows.shape[1] == 9 and set(np.round(rows[:, 0], 6)) == {-0.72, -0.71, -0.70}
     assert np.all(rows[:, 2] == 128) and np.all(rows[rows[:, 3] == 0][:, 4] == 0.25)
     assert np.all(rows[:, 4] > 0) and np.all(rows[:, 7] <= 128 * 128)
+
+
+def test_rietkerk_sweep_writes_reference_tree(host, tmp_path):
+    """first_order_critical_exp_delta_stochastic_MultiSp (R/:4379): final table, per-replicate prelim tables and
+    frame snapshots in the reference's directory/file grammar and formats."""
+    host.tmh_riet_sweep.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    host.tmh_set_options(0, 31, 0, str(tmp_path).encode())
+    L, div, r = 32, 2, 2
+    assert host.tmh_riet_sweep(L, div, 3.0, 0.05, 0.06, 0.1, r) == 0
+    root = tmp_path / "Data" / "Rietkerk"
+    table = root / "Stochastic" / "1Sp" / "1stCC_Rietkerk_DiC-NREF-LI_P_c_G_32_T_3_dt_0.1_D1_1.04e-05_a1_0.05_a2_0.06_dx_0.1_R_2.csv"
+    assert table.exists(), list((root / "Stochastic" / "1Sp").iterdir())
+    lines = table.read_text().splitlines()
+    assert lines[0].startswith(" a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r")
+    nbins = O.oracle().tmo_logarithm10_time_bins(3.0, 0.1, O.ptr(np.zeros(64)), 64) + 1     # {0} U log bins
+    rows = np.array([[float(x) for x in l.split(",")] for l in lines[2:]])
+    assert rows.shape == (div * nbins, 10)
+    assert set(np.round(rows[:, 0], 6)) == {0.05, 0.06} and np.all(rows[:, 1] == r) and np.all(rows[:, 2] == L)
+    first = rows[0]                                   # t = 0: the MFT frame, W* a = 5 a, O = 120.47 a + 0.58
+    assert first[3] == 0.0 and abs(first[4] - 0.25) < 1e-12 and abs(first[5] - (120.4744181 * 0.05 + 0.58243061)) < 1e-9
+    assert first[8] == r and first[9] == L * L
+    # frames: t = 0 and the last ten frame_tmeas windows, 6-significant-digit CSV with the frame header
+    fdir = root / "Frames" / "Stochastic" / "1Sp" / "DiC-NREF-LI_0.05-0.06_dP_10000"
+    frames = sorted(p.name for p in fdir.iterdir())
+    assert "FRAME_P_c_DP_G_32_T_0_dt_0.1_a_0.05_D1_1.04e-05_jID_0_dx_0.1_R_0.csv" in frames
+    txt = (fdir / frames[0]).read_text().splitlines()
+    assert txt[0] == "a_c,  x,  P(x; t), W(x; t), O(x; t) " and len(txt) == 1 + L * L and len(txt[1].split(",")) == 5
+    # prelim tables: one per (a, replicate), trailing comma, r+1 in the second column
+    pdir = root / "Prelims" / "Stochastic" / "1Sp" / "DiC-NREF-LI_0.05-0.06_dP_10000"
+    prelims = sorted(p.name for p in pdir.iterdir())
+    assert len(prelims) == div * r and prelims[0].startswith("PRELIM_AGGRAND_P_c_ID_0_DP_G_32_T_")
+    pl = (pdir / prelims[0]).read_text().splitlines()
+    assert pl[1].endswith(",") and pl[1].split(",")[1] in ("1", "2") and len(pl) == 2 + nbins - 1 + 0 or len(pl) >= nbins

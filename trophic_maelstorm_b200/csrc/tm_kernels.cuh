@@ -789,9 +789,9 @@ dp_step_kernel(const DpArgs A)
     double *out = A.out + (long long)trial * g.trial_stride;
     const DornicConsts dk = A.trials[trial].dk;
     ThreadStats tstat; tstat.clear();
-    const long long ncell = (long long)g.nrows * g.L;
-    for (long long i = (long long)blk * nthreads + tid; i < ncell; i += (long long)A.blocks_per_trial * nthreads) {
-        const int r = (int)(i / g.L), q = (int)(i % g.L);
+    // whole rows per block (coalesced along q, no per-cell division)
+    for (int r = blk; r < g.nrows; r += A.blocks_per_trial)
+    for (int q = tid; q < g.L; q += nthreads) {
         long long ru, rd;
         if (g.wrap) { ru = (r == 0) ? g.L - 1 : r - 1; rd = (r == g.L - 1) ? 0 : r + 1; }
         else        { ru = r - 1 + kHalo; rd = r + 1 + kHalo; }
@@ -865,13 +865,11 @@ stats_kernel(const StatsArgs A)
     TM_DYN_SMEM(smem_raw);
     double *scratch = reinterpret_cast<double *>(smem_raw);
     ThreadStats tstat; tstat.clear();
-    const long long ncell = (long long)g.nrows * g.L;
     for (int f = 0; f < g.n_fields; f++) {
-        const double *in = A.in + (long long)trial * g.trial_stride + (long long)f * g.field_stride;
-        for (long long i = (long long)blk * nthreads + tid; i < ncell; i += (long long)A.blocks_per_trial * nthreads) {
-            const int r = (int)(i / g.L), q = (int)(i % g.L);
-            const long long rc = g.wrap ? r : r + kHalo;
-            tstat.add(f, in[rc * g.Lp + q + kHalo]);
+        const double *in = A.in + (long long)trial * g.trial_stride + (long long)f * g.field_stride + kHalo;
+        for (int r = blk; r < g.nrows; r += A.blocks_per_trial) { // whole rows per block: coalesced, no per-element division
+            const double *row = in + (long long)(g.wrap ? r : r + kHalo) * g.Lp;
+            for (int q = tid; q < g.L; q += nthreads) tstat.add(f, row[q]);
         }
     }
     flush_stats(tstat, g.n_fields, trial, A.partials + blockIdx.x, scratch, tid, nthreads);

@@ -108,8 +108,8 @@ static int alloc_all(tm_ctx *c)
         riet_launch_shape(g, c->n_sm * c->riet_occ, &c->grid);
         c->n_records = 0;
     } else {
-        const long long ncell = (long long)g.nrows * g.L;
-        long long bpt = (ncell + 256 * 4 - 1) / (256 * 4);
+        // DP kernels take whole rows per block: at most one block per row, ~8 blocks per SM overall
+        long long bpt = g.nrows;
         const long long cap = (8LL * c->n_sm + g.n_trials - 1) / g.n_trials;
         if (bpt > cap) bpt = cap;
         if (bpt < 1) bpt = 1;
@@ -118,8 +118,7 @@ static int alloc_all(tm_ctx *c)
     }
     // the stand-alone stats kernel uses its own (possibly larger) record set
     {
-        const long long ncell = (long long)g.nrows * g.L;
-        long long bpt = (ncell + 256 * 8 - 1) / (256 * 8);
+        long long bpt = g.nrows;
         const long long cap = (4LL * c->n_sm + g.n_trials - 1) / g.n_trials;
         if (bpt > cap) bpt = cap;
         if (bpt < 1) bpt = 1;
@@ -525,8 +524,7 @@ int tm_measure(tm_ctx *c, tm_stats *out)
     const Geom &g = c->g;
     int n_records = c->n_records;
     if (!c->stats_valid) {
-        const long long ncell = (long long)g.nrows * g.L;
-        long long bpt = (ncell + 256 * 8 - 1) / (256 * 8);
+        long long bpt = g.nrows;
         const long long cap = (4LL * c->n_sm + g.n_trials - 1) / g.n_trials;
         if (bpt > cap) bpt = cap;
         if (bpt < 1) bpt = 1;

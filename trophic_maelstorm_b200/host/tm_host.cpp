@@ -3,6 +3,7 @@
 #include "tm_host.h"
 #include "../../include/tm_lattice.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -319,33 +320,69 @@ void save_frame(D2Vec_Double &Rho_t, const std::string &parendir, const std::str
     }
 }
 
-void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
-                                double alpha, double rW, double W0, double (&D)[Sp], double (&)[SpB], double (&K)[3],
-                                double sigma[], double a_st, double a_end, double a_c, double (&)[SpB][SpB], double (&)[SpB][SpB],
-                                double (&)[SpB], double (&M)[SpB], double[], int (&)[SpB], double clow[], double dt, double dx,
-                                double dP, int r, int g, double, double)
+void save_prelimframe(D2Vec_Double &Rho_t, const std::string &parendir, const std::string &filenamePattern, double a, double,
+                      double, double, double, double, double, int r, int g, std::string header, bool overwrite, bool) // R/:2720-2783
 {
-    if (t_meas.empty() || r < 1) throw std::invalid_argument("rietkerk_Dornic_2D_MultiSp: empty t_meas or r < 1");
+    mkdirs(parendir);
+    std::string filename = parendir + filenamePattern + std::to_string(r) + ".csv";
+    if (!overwrite) { // never overwrite: bump the replicate suffix (R/:2730-2740)
+        int rep = r;
+        struct stat sb;
+        while (stat(filename.c_str(), &sb) == 0) filename = parendir + filenamePattern + std::to_string(++rep) + ".csv";
+    }
+    std::ostringstream oss;
+    oss << (header != "" ? header : std::string("a_c,  x,  P(x; t), W(x; t), O(x; t) \n"));
+    for (size_t i = 0; i < Rho_t.size(); i++) {
+        oss << a << "," << r + 1 << "," << g << ",";
+        for (size_t k = 0; k < Rho_t[i].size(); k++) oss << Rho_t[i][k] << ","; // default precision, trailing comma
+        oss << "\n";
+    }
+    if (FILE *fp = fopen(filename.c_str(), "w")) { fprintf(fp, "%s", oss.str().c_str()); fclose(fp); }
+    else std::cerr << "Error: Could not open PRELIM file " << filename << std::endl;
+}
+
+std::string prefix = "DiC-NREF-LI";                    // R/ header :97
+std::string prelim_folder;                            // default "<data_root>/Data/Rietkerk/Prelims/Stochastic/1Sp/<prefix>_"
+std::string stat_prefix;                              // default "<data_root>/Data/Rietkerk/Stochastic/1Sp/1stCC_Rietkerk_<prefix>_P_c_G_"
+bool write_prelims = true;
+const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"
+                                 " # Active Sites P(x; t), \n"; // rietkerk_bjork_constants_1Sp.h:8-9
+
+namespace {
+// All a-values of a sweep x r replicates as ONE batch of trials (the reference runs a-values on OpenMP threads
+// and replicates serially, R/:4519, :3501); rows come back per a-value in the reference's layout.
+void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values, vector<double> &t_meas, double c, double gmax,
+                double alpha, double rW, double W0, double (&D)[Sp], double (&K)[3], double sigma[], double a_st, double a_end,
+                double a_c, double (&M)[SpB], double clow[], double dt, double dx, double dP, int r, int g)
+{
+    if (t_meas.empty() || r < 1 || a_values.empty()) throw std::invalid_argument("rietkerk_Dornic_2D_MultiSp: empty t_meas, no a-value or r < 1");
+    const int na = (int)a_values.size(), nt = na * r;
     tm_params p{};
-    p.model = TM_MODEL_RIETKERK; p.L = g; p.dt = dt; p.dx = dx; p.a = a;
+    p.model = TM_MODEL_RIETKERK; p.L = g; p.dt = dt; p.dx = dx; p.a = a_values[0];
     p.rc = c; p.gmax = gmax; p.alpha = alpha; p.rW = rW; p.W0 = W0; p.d = M[0]; p.K1 = K[1]; p.K2 = K[2];
     p.D0 = D[0]; p.D1 = D[1]; p.D2 = D[2]; p.sigma0 = sigma[0];
     p.clamp_eps = 1.0e-12; p.clamp_lo = -1.0e-80; // R/:3402, :4176
-    Ctx ctx(p, r);
+    Ctx ctx(p, nt);
     const size_t n = (size_t)g * g;
-    vector<double> host(3 * n * r);
-    for (int j = 0; j < r; j++) init_frame(&host[3 * n * j], g, j, a, a_c, dP, clow);
+    vector<double> host(3 * n * nt);
+    for (int ia = 0; ia < na; ia++)
+        for (int j = 0; j < r; j++) {
+            const int t = ia * r + j;                       // trial id = a-index * r + replicate
+            ctx.ck(tm_set_trial_a(ctx.c, t, a_values[ia]), "tm_set_trial_a");
+            init_frame(&host[3 * n * t], g, t, a_values[ia], a_c, dP, clow);
+        }
     ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
     ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");
 
     const int tot_iter = (int)t_meas.size();               // R/:3438
     const int W_ = 4 * SpB + 3;                            // Sp4_1: {t, <W>, <O>, mean, var, surv, active}
-    vector<vector<double>> acc(tot_iter, vector<double>(W_, 0.0));
-    for (int i = 0; i < tot_iter; i++) acc[i][0] = t_meas[i];
-    vector<vector<double>> RhoM(r, vector<double>(2 * Sp * (size_t)tot_iter, 0.0)); // [index][2s] = N, [2s+1] = mean
+    vector<vector<double>> RhoM(nt, vector<double>(2 * Sp * (size_t)tot_iter, 0.0)); // [index][2s] = N, [2s+1] = mean
     const double t_end = t_meas.back();
-    vector<tm_stats> st(r);
-    const std::string fdir = frame_folder.empty() ? options().data_root + "/Data/Rietkerk/Frames/Stochastic/1Sp/" : frame_folder;
+    vector<tm_stats> st(nt);
+    const std::string fdir = frame_folder.empty() ? options().data_root + "/Data/Rietkerk/Frames/Stochastic/1Sp/" + prefix + "_" : frame_folder;
+    const std::string pdir = prelim_folder.empty() ? options().data_root + "/Data/Rietkerk/Prelims/Stochastic/1Sp/" + prefix + "_" : prelim_folder;
+    std::stringstream a1, a2, dimitri; a1 << a_st; a2 << a_end; dimitri << dP;
+    const std::string subdir = a1.str() + "-" + a2.str() + "_dP_" + dimitri.str();
 
     double t = 0; int index = 0; size_t frame_index = 0; int pending = 0;
     while (t < t_end + dt) { // R/:3648
@@ -355,8 +392,8 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
         if ((meas || snap) && pending) { ctx.ck(tm_step(ctx.c, pending), "tm_step"); pending = 0; }
         if (meas) {
             ctx.ck(tm_measure(ctx.c, st.data()), "tm_measure");
-            for (int j = 0; j < r; j++) {
-                if (st[j].nonfinite) { std::cerr << "RHO NAAN PARATHA in replicate " << j << " at t=" << t << "\n"; exit(3); }
+            for (int j = 0; j < nt; j++) {
+                if (st[j].nonfinite) { std::cerr << "RHO NAAN PARATHA in trial " << j << " at t=" << t << "\n"; exit(3); } // R/:4206-4276
                 for (int s = 0; s < Sp; s++) {
                     RhoM[j][2 * Sp * index + 2 * s] = (double)st[j].active[s];
                     RhoM[j][2 * Sp * index + 2 * s + 1] = st[j].mean[s];
@@ -368,16 +405,16 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
             const size_t ftot = frame_tmeas.size();
             if ((frame_index + 10 >= ftot) || (t >= 50000 && t <= 150000) || (t >= 20 && t <= 15000) || t == 0) { // R/:3739
                 ctx.ck(tm_download(ctx.c, host.data()), "tm_download");
-                for (int j = 0; j < r; j++) {
+                for (int tr = 0; tr < nt; tr++) {
+                    const double a = a_values[tr / r]; const int j = tr % r;
                     D2Vec_Double fr(Sp, vector<double>(n));
-                    for (int s = 0; s < Sp; s++) memcpy(fr[s].data(), &host[(3 * j + s) * n], n * sizeof(double));
-                    std::stringstream L, tm, d3, p1, Dm1, dix, a1, a2, dimitri;
+                    for (int s = 0; s < Sp; s++) memcpy(fr[s].data(), &host[(3 * (size_t)tr + s) * n], n * sizeof(double));
+                    std::stringstream L, tm, d3, p1, Dm1, dix;
                     L << g; tm << t; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a; dix << std::setprecision(2) << dx;
-                    Dm1 << std::setprecision(3) << D[1]; a1 << a_st; a2 << a_end; dimitri << dP;
-                    const std::string parendir = fdir + a1.str() + "-" + a2.str() + "_dP_" + dimitri.str();
+                    Dm1 << std::setprecision(3) << D[1];
                     const std::string pattern = "/FRAME_P_c_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
                                               + "_D1_" + Dm1.str() + "_jID_0_dx_" + dix.str() + "_R_"; // R/:2914
-                    save_frame(fr, parendir, pattern, a, a_st, a_end, t, dt, dx, dP, j, g);
+                    save_frame(fr, fdir + subdir, pattern, a, a_st, a_end, t, dt, dx, dP, j, g);
                 }
             }
             frame_index += 1;
@@ -385,42 +422,125 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
         pending += 1;
         t += dt;
     }
-    // replicate-order accumulation: R/:4294-4322 and var_mean_incremental_surv_runs R/:1293-1343
-    for (int j = 0; j < r; j++) {
-        const vector<double> &X = RhoM[j];
-        if (j == 0) {
-            for (int i = 0; i < tot_iter; i++) {
-                const double N = X[2 * Sp * i + 0], mean = X[2 * Sp * i + 1];
-                acc[i][3] = mean; acc[i][4] = 0.0; acc[i][6] = N;
-                if (N > 0) acc[i][5] = 1; else if (N == 0) acc[i][5] = 0;
-                acc[i][1] = X[2 * Sp * i + 2 * (Sp - 2) + 1]; acc[i][2] = X[2 * Sp * i + 2 * (Sp - 1) + 1];
+    // per a-value: replicate-order accumulation (R/:4294-4322, var_mean_incremental_surv_runs R/:1293-1343)
+    Rho_per_a.assign(na, D2Vec_Double());
+    for (int ia = 0; ia < na; ia++) {
+        const double a = a_values[ia];
+        vector<vector<double>> acc(tot_iter, vector<double>(W_, 0.0));
+        for (int i = 0; i < tot_iter; i++) acc[i][0] = t_meas[i];
+        for (int j = 0; j < r; j++) {
+            const vector<double> &X = RhoM[ia * r + j];
+            if (j == 0) {
+                for (int i = 0; i < tot_iter; i++) {
+                    const double N = X[2 * Sp * i + 0], mean = X[2 * Sp * i + 1];
+                    acc[i][3] = mean; acc[i][4] = 0.0; acc[i][6] = N;
+                    if (N > 0) acc[i][5] = 1; else if (N == 0) acc[i][5] = 0;
+                    acc[i][1] = X[2 * Sp * i + 2 * (Sp - 2) + 1]; acc[i][2] = X[2 * Sp * i + 2 * (Sp - 1) + 1];
+                }
+            } else {
+                for (int i = 0; i < tot_iter; i++) { // vegetation: surviving runs only, stops at the first dead bin (R/:1306-1310)
+                    const double N = X[2 * Sp * i + 0], mean = X[2 * Sp * i + 1];
+                    const int rr = (int)(acc[i][5] + 1);
+                    if (N == 0.0) break;
+                    const double mean_prev = acc[i][3];
+                    if (acc[i][5] == 0.0) { acc[i][3] = mean; acc[i][4] = 0.0; acc[i][6] = N; }
+                    else {
+                        acc[i][3] = (mean + (rr - 1) * acc[i][3]) / rr;
+                        acc[i][6] = (N + (rr - 1) * acc[i][6]) / rr;
+                        acc[i][4] = (acc[i][3] - mean_prev) * (acc[i][3] - mean_prev)
+                                  + (1 / (rr - 1)) * ((rr - 2) * acc[i][4] + (mean - acc[i][3]) * (mean - acc[i][3])); // int 1/(r-1), R/:1325
+                    }
+                    acc[i][5] = rr;
+                }
+                for (int i = 0; i < tot_iter; i++) { // soil and surface water: plain running mean over all replicates (R/:1333-1337)
+                    acc[i][1] = (X[2 * Sp * i + 2 * (Sp - 2) + 1] + j * acc[i][1]) / (j + 1);
+                    acc[i][2] = (X[2 * Sp * i + 2 * (Sp - 1) + 1] + j * acc[i][2]) / (j + 1);
+                }
             }
-            continue;
-        }
-        for (int i = 0; i < tot_iter; i++) { // vegetation: surviving runs only, stops at the first dead bin (R/:1306-1310)
-            const double N = X[2 * Sp * i + 0], mean = X[2 * Sp * i + 1];
-            const int rr = (int)(acc[i][5] + 1);
-            if (N == 0.0) break;
-            const double mean_prev = acc[i][3];
-            if (acc[i][5] == 0.0) { acc[i][3] = mean; acc[i][4] = 0.0; acc[i][6] = N; }
-            else {
-                acc[i][3] = (mean + (rr - 1) * acc[i][3]) / rr;
-                acc[i][6] = (N + (rr - 1) * acc[i][6]) / rr;
-                acc[i][4] = (acc[i][3] - mean_prev) * (acc[i][3] - mean_prev)
-                          + (1 / (rr - 1)) * ((rr - 2) * acc[i][4] + (mean - acc[i][3]) * (mean - acc[i][3])); // int 1/(r-1), R/:1325
+            if (write_prelims) { // the running table after every replicate, R/:4327-4349 (jID is a random number there)
+                std::stringstream L, tm, d3, p1, Dm;
+                L << g; tm << t_end; d3 << std::setprecision(3) << dt; p1 << std::setprecision(5) << a; Dm << std::setprecision(4) << D[2];
+                const std::string pattern = "/PRELIM_AGGRAND_P_c_ID_0_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
+                                          + "_D2_" + Dm.str() + "_R_";
+                save_prelimframe(acc, pdir + subdir, pattern, a, a_st, a_end, t, dt, dx, dP, j, g, prelimheader, true);
             }
-            acc[i][5] = rr;
         }
-        for (int i = 0; i < tot_iter; i++) { // soil and surface water: plain running mean over all replicates (R/:1333-1337)
-            acc[i][1] = (X[2 * Sp * i + 2 * (Sp - 2) + 1] + j * acc[i][1]) / (j + 1);
-            acc[i][2] = (X[2 * Sp * i + 2 * (Sp - 1) + 1] + j * acc[i][2]) / (j + 1);
+        for (int i = 0; i < tot_iter; i++) { // R/:4361-4372: {a, r, L, t, <W>, <O>, <P>, var, surv, active}
+            vector<double> row = {a, static_cast<double>(r), static_cast<double>(g)};
+            row.insert(row.end(), acc[i].begin(), acc[i].end());
+            Rho_per_a[ia].push_back(row);
         }
     }
-    for (int i = 0; i < tot_iter; i++) { // R/:4361-4372: {a, r, L, t, <W>, <O>, <P>, var, surv, active}
-        vector<double> row = {a, static_cast<double>(r), static_cast<double>(g)};
-        row.insert(row.end(), acc[i].begin(), acc[i].end());
-        Rho.push_back(row);
+}
+
+// switchsort_and_bait, R/:1409-1436 (insert_type "linspace", erase = true as the sweep calls it)
+vector<double> switchsort_and_bait(vector<double> vals, double low, double high, int num_points)
+{
+    vals.erase(std::remove_if(vals.begin(), vals.end(), [low, high](double x) { return x >= low && x <= high; }), vals.end());
+    vector<double> lin = linspace(low, high, num_points);
+    vals.insert(vals.end(), lin.begin(), lin.end());
+    std::sort(vals.begin(), vals.end());
+    vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+    return vals;
+}
+} // namespace
+
+void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&)[SpB], double (&K)[3],
+                                double sigma[], double a_st, double a_end, double a_c, double (&)[SpB][SpB], double (&)[SpB][SpB],
+                                double (&)[SpB], double (&M)[SpB], double[], int (&)[SpB], double clow[], double dt, double dx,
+                                double dP, int r, int g, double, double)
+{
+    vector<D2Vec_Double> per_a;
+    riet_batch(per_a, vector<double>{a}, t_meas, c, gmax, alpha, rW, W0, D, K, sigma, a_st, a_end, a_c, M, clow, dt, dx, dP, r, g);
+    Rho.insert(Rho.end(), per_a[0].begin(), per_a[0].end());
+}
+
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&)[SpB], double (&K)[3], double sigma[], double (&)[SpB][SpB],
+                                                       double (&)[SpB][SpB], double (&)[SpB], double (&M)[SpB], double[],
+                                                       int (&)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar, double Vstar) // R/:4379-4617
+{
+    vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = logarithm10_time_bins(t_max, 1 * dt);
+    t_measure.insert(t_measure.begin(), 0.0);                                    // R/:4401
+    std::sort(t_measure.begin(), t_measure.end());
+    t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
+    frame_tmeas = t_measure;                                                       // R/:4424-4459
+    frame_tmeas = switchsort_and_bait(frame_tmeas, 50, 400, 8);
+    frame_tmeas = switchsort_and_bait(frame_tmeas, 400, 1200, 9);
+    if (t_measure[t_measure.size() - 1] > 90000) {
+        vector<double> w1 = linspace(50000, 100000, 26);
+        frame_tmeas.insert(std::upper_bound(frame_tmeas.begin(), frame_tmeas.end(), w1[0]), w1.begin(), w1.end());
+        std::sort(frame_tmeas.begin(), frame_tmeas.end());
+        vector<double> w2 = linspace(80000, 150000, 141);
+        t_measure.insert(std::upper_bound(t_measure.begin(), t_measure.end(), w2[0]), w2.begin(), w2.end());
+        std::sort(t_measure.begin(), t_measure.end());
     }
+    frame_tmeas.erase(std::unique(frame_tmeas.begin(), frame_tmeas.end()), frame_tmeas.end());
+    t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
+
+    vector<D2Vec_Double> per_a;
+    riet_batch(per_a, a_space, t_measure, c, gmax, alpha, rW, W0, D, K, sigma, a_start, a_end, a_c, M, clo, dt, dx, dP, r, g);
+
+    std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;
+    L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r;
+    Dm1 << std::setprecision(3) << D[1]; dix << std::setprecision(2) << dx; geq << std::setprecision(5) << Gstar; veq << std::setprecision(5) << Vstar;
+    const std::string sp = stat_prefix.empty() ? options().data_root + "/Data/Rietkerk/Stochastic/1Sp/1stCC_Rietkerk_" + prefix + "_P_c_G_" : stat_prefix;
+    std::string savefile = sp + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str() + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str();
+    if (Gstar != -1) savefile += "_Geq_" + geq.str() + "_R_" + rini.str() + ".csv";
+    else if (Vstar != -1) savefile += "_Veq_" + veq.str() + "_R_" + rini.str() + ".csv";
+    else savefile += "_R_" + rini.str() + ".csv";
+    mkdirs(savefile.substr(0, savefile.find_last_of('/')));
+    std::ofstream out(savefile);
+    out << prelimheader << "\n";                                                   // R/:4601
+    for (const D2Vec_Double &rows : per_a)
+        for (const vector<double> &v : rows) {
+            for (size_t j = 0; j + 1 < v.size(); j++) out << std::setprecision(16) << v[j] << ",";
+            out << std::setprecision(16) << v[v.size() - 1] << std::endl;
+        }
 }
 
 } // namespace tm_b200

@@ -8,6 +8,7 @@
 //   critical_exp_delta              Percolation_FD/stochasticSPDP.cpp:1309
 //   first_order_critical_exp_delta  Percolation_FD/stochasticSPDP.cpp:2422
 //   rietkerk_Dornic_2D_MultiSp      Rietkerk_FD/rietkerk_bjork_basic.cpp:3397   (SPB = 1)
+//   first_order_critical_exp_delta_stochastic_MultiSp   Rietkerk_FD/rietkerk_bjork_basic.cpp:4379
 //   logarithm10_time_bins, linspace, var_mean_incremental_surv_runs, save_frame  (bookkeeping)
 //
 // What is different by construction: replicates run concurrently as trials of one device context
@@ -66,5 +67,19 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, 
 void save_frame(D2Vec_Double &Rho_t, const std::string &parendir, const std::string &filenamePattern, double a,
                 double a_st, double a_end, double t, double dt, double dx, double dP, int r, int g,
                 std::string header = "", bool overwrite = false);                 // R/:2836
+void save_prelimframe(D2Vec_Double &Rho_t, const std::string &parendir, const std::string &filenamePattern, double a,
+                      double a_st, double a_end, double t, double dt, double dx, double dP, int r, int g,
+                      std::string header = "", bool overwrite = false, bool delete_previous = false); // R/:2720
+// the a-sweep: t_measure = {0} U log10 bins, frame_tmeas with the linear windows, all a-values x replicates as one
+// batch of trials, final table to <stat_prefix><L>_T_..._R_<r>.csv at setprecision(16) (R/:4379-4617)
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar = -1.0, double Vstar = -1.0);
+extern std::string prefix, prelim_folder, stat_prefix; // R/ header :97-108; empty folders = "<data_root>/Data/Rietkerk/..."
+extern bool write_prelims;                             // per-replicate PRELIM_AGGRAND_*.csv (R/:4327-4349)
+extern const std::string prelimheader;                 // rietkerk_bjork_constants_1Sp.h:8-9
 
 } // namespace tm_b200

@@ -63,6 +63,7 @@ int tmh_riet_run(int L, double a, double dt, int r, const double *init, const do
     std::vector<double> tm(t_meas, t_meas + n_tmeas);
     frame_tmeas.assign(frame_t, frame_t + n_frame_t);
     frame_folder = frame_dir ? frame_dir : "";
+    write_prelims = false;
     auto saved = init_frame;
     const size_t n = (size_t)L * L;
     if (init) init_frame = [init, n](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + 3 * n * j, 3 * n * sizeof(double)); };
@@ -78,6 +79,24 @@ int tmh_riet_run(int L, double a, double dt, int r, const double *init, const do
     for (size_t k = 0; k < Rho.size(); k++)
         for (size_t j = 0; j < 10; j++) rows_out[10 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
     return (int)Rho.size();
+}
+
+// the SPB=1 a-sweep with the order_1stoc_test_rietkerk.cpp constants; writes the reference's CSV tree under data_root
+int tmh_riet_sweep(int L, int div, double t_max, double a_start, double a_end, double dt, int r)
+{
+    double c = 10000, gmax = 0.05e-3 / 24.0, d = 0.25 / 24.0, alpha = 0.2 / 24.0, W0 = 0.2, rW = 0.2 / 24.0, dx = 0.1;
+    double D[Sp] = {0.00025 / 24.0, 0.00025 / 24.0, 0.025 / 24.0};
+    double K[3] = {0, 5, 5000};
+    double sigma[Sp] = {sqrt(D[0] / (dx * dx)), 0, 0};
+    double v[SpB] = {0}, A[SpB][SpB] = {{0}}, H[SpB][SpB] = {{0}}, E[SpB] = {1.0}, M[SpB] = {d}, pR[SpB] = {0.0};
+    int dtV[SpB] = {0};
+    double clow[2 * Sp] = {0, 1, 1, 5, 1, 1};
+    frame_folder = ""; prelim_folder = ""; stat_prefix = ""; write_prelims = true;
+    try {
+        first_order_critical_exp_delta_stochastic_MultiSp(div, t_max, a_start, a_end, 1.0 / 24.0, c, gmax, alpha, rW, W0, D, v, K, sigma,
+                                                          A, H, E, M, pR, dtV, clow, dt, dx, 10000.0, r, L);
+    } catch (const std::exception &) { return -2; }
+    return 0;
 }
 
 }
