@@ -75,7 +75,7 @@ class SlabRing:
                d.P2POp(d.irecv, self.as_tensor(self.from_down), self.down),   # its top rows -> my ghost-below
                d.P2POp(d.irecv, self.as_tensor(self.from_up), self.up)]
         for r in d.batch_isend_irecv(ops):
-            r.wait()
+            r.wait()   # NCCL: stream-ordered (returns at once); gloo: blocks until the data is in place
         self.after_comm()
         self.lat.halo_unpack(0, self.from_up)
         self.lat.halo_unpack(1, self.from_down)
@@ -95,9 +95,14 @@ class DevicePtrView:
 
 
 def cuda_slab_ring(lat, dist):
-    """SlabRing over a real `Lattice` slab context: NCCL send/recv on the packed halo buffers."""
+    """SlabRing over a real `Lattice` slab context: NCCL send/recv on the packed halo buffers.
+
+    Everything is enqueued on the context's own CUDA stream (wrapped as a torch ExternalStream), so pack ->
+    send/recv -> unpack -> step are ordered by the stream and the host never blocks between steps.
+    """
     import torch
     n = lat.halo_bytes() // 8
+    stream = torch.cuda.ExternalStream(lat.cuda_stream())
 
     def make_buf():
         return torch.empty(n, dtype=torch.float64, device="cuda")
@@ -117,6 +122,14 @@ def cuda_slab_ring(lat, dist):
         def step(self, n):
             self.lat.step(n)
         def sync(self):
-            self.lat.sync()
+            pass  # stream order is enough: the collectives below run on the same stream
 
-    return SlabRing(_Adapter(lat), dist, make_buf, as_tensor, after_comm=torch.cuda.synchronize)
+    ring = SlabRing(_Adapter(lat), dist, make_buf, as_tensor)
+    plain_exchange = ring.exchange
+
+    def exchange_on_ctx_stream():
+        with torch.cuda.stream(stream):
+            plain_exchange()
+
+    ring.exchange = exchange_on_ctx_stream
+    return ring
