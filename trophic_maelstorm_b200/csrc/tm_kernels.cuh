@@ -489,6 +489,7 @@ riet_step_kernel(const StepArgs A)
         // global row (mod L) of front 1 and physical row of the commit front, advanced per step
         int r1 = (g.row0 + jlo - 1) % g.L; if (r1 < 0) r1 += g.L;
         long long r4 = prow(jlo - 4);
+        double *po_row = outP + (r4 * g.Lp + (gx + kHalo));
 
         // the few values that stay in registers (own column): rho* of rows j-4..j-2, the P stage
         // values, and the running K1+2K2+2K3 sums of the rows between fronts 1 and 4
@@ -499,16 +500,17 @@ riet_step_kernel(const StepArgs A)
         int m0 = (int)(seq % kStSlots) * NF * RW, m1 = (int)((seq + 2) % kStSlots) * NF * RW, m2 = (int)((seq + 1) % kStSlots) * NF * RW;
         double *const stc = st + 2 + cx;
         const double *const inc = in + 2 + cx;
+        // rows j-1 .. j-4 before the first step: the slots the ring bookkeeping assigns them (stale but finite data)
+        const double *i0 = inc + (int)((seq + kInSlots - 1) & (kInSlots - 1)) * (3 * RW);
+        const double *i1 = inc + (int)((seq + kInSlots - 2) & (kInSlots - 1)) * (3 * RW);
+        const double *i2 = inc + (int)((seq + kInSlots - 3) & (kInSlots - 1)) * (3 * RW);
+        const double *i3 = inc + (int)((seq + kInSlots - 4) & (kInSlots - 1)) * (3 * RW), *i4 = i3;
 
         for (int j = jlo; j <= jhi; j++, seq++) {
             const int s0 = (int)(seq & (kInSlots - 1));
             if (!timeout && !mbar_wait(&mbar[s0], (uint32_t)((seq / kInSlots) & 1))) timeout = true;
-            // stage-0 rows j, j-1, j-2, j-3, j-4 of this column
-            const double *i0 = inc + s0 * (3 * RW);
-            const double *i1 = inc + ((s0 + kInSlots - 1) & (kInSlots - 1)) * (3 * RW);
-            const double *i2 = inc + ((s0 + kInSlots - 2) & (kInSlots - 1)) * (3 * RW);
-            const double *i3 = inc + ((s0 + kInSlots - 3) & (kInSlots - 1)) * (3 * RW);
-            const double *i4 = inc + ((s0 + kInSlots - 4) & (kInSlots - 1)) * (3 * RW);
+            // stage-0 rows j, j-1, j-2, j-3, j-4 of this column (pointers rotate with the ring)
+            i4 = i3; i3 = i2; i2 = i1; i1 = i0; i0 = inc + s0 * (3 * RW);
             // stage rings: slot of the row a front works on, and of its vertical neighbours
             // stage rings: row j-back lives in slot (q - back) mod 3, i.e. m0 (back 0,3), m1 (1,4), m2 (2,5)
             auto sp = [&](int stage, int back) -> double * { // stage 1..3, row j-back
@@ -610,9 +612,11 @@ riet_step_kernel(const StepArgs A)
                 double nP = axpy<STRICT>(c.dt6, aP_m4 + k4.p, Ps_m4);
                 double nW = axpy<STRICT>(c.dt6, aW_m4 + k4.w, i4[RW]);
                 double nO = axpy<STRICT>(c.dt6, aO_m4 + k4.o, i4[2 * RW]);
-                if (!DET) { nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo); }
+                if (!DET && fmin(nP, fmin(nW, nO)) < c.eps) { // R/:4176; almost never taken for live cells
+                    nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo);
+                }
                 if (out_col && j - 4 >= ya) { // (j-4 <= yb-1 always holds: j <= jhi)
-                    double *po = outP + (r4 * g.Lp + (gx + kHalo)); // padded-layout column gx + 4
+                    double *po = po_row; // row r4, padded-layout column gx + 4
                     po[0] = nP; po[g.field_stride] = nW; po[2 * g.field_stride] = nO;
                     if (gx < kHalo) { po[g.L] = nP; po[g.field_stride + g.L] = nW; po[2 * g.field_stride + g.L] = nO; }
                     if (gx >= g.L - kHalo) { po[-g.L] = nP; po[g.field_stride - g.L] = nW; po[2 * g.field_stride - g.L] = nO; }
@@ -625,7 +629,7 @@ riet_step_kernel(const StepArgs A)
             }
             r1 = (r1 + 1 == g.L) ? 0 : r1 + 1;
             { const int t = m0; m0 = m2; m2 = m1; m1 = t; }
-            if (g.wrap) r4 = (r4 + 1 == g.L) ? 0 : r4 + 1; else r4 += 1;
+            if (g.wrap && r4 + 1 == g.L) { r4 = 0; po_row -= (long long)(g.L - 1) * g.Lp; } else { r4 += 1; po_row += g.Lp; }
 
             __syncthreads();
             if (tid == 0 && j + kPrefetch + 1 <= jhi) issue(j + kPrefetch + 1, seq + kPrefetch + 1);
