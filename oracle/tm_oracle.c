@@ -106,6 +106,32 @@ double tmo_lgamma_int(double k)
     return (fma(k - 0.5, tmo_log(k), -k) + HALF_LOG_2PI) + ser;
 }
 
+/* sin and cos of (pi/2) a, a in [0,4]: nearest-integer quadrant q (ties to even through the
+ * 1.5*2^52 addition), g = a - q in [-1/2,1/2] exactly, Taylor series of sin/cos((pi/2) g) in g^2
+ * with the coefficients (-1)^k (pi/2)^n / n! rounded to double, quadrant swap / sign by bit
+ * operations.  Own restatement of the spec in DESIGN.md section 3 (Box-Muller angle). */
+void tmo_sincos_quadrants(double a, double *sn, double *cs)
+{
+    static const double S[8] = { 0x1.921fb54442d18p+0, -0x1.4abbce625be53p-1, 0x1.466bc6775aae2p-4,
+        -0x1.32d2cce62bd86p-8, 0x1.50783487ee782p-13, -0x1.e3074fde8871fp-19, 0x1.e8f434d018d63p-25,
+        -0x1.6fadb9f155744p-31 };
+    static const double C[9] = { 1.0, -0x1.3bd3cc9be45dep+0, 0x1.03c1f081b5ac4p-2, -0x1.55d3c7e3cbffap-6,
+        0x1.e1f506891babbp-11, -0x1.a6d1f2a204a8cp-16, 0x1.f9d38a3763cc3p-22, -0x1.b6e24f44b128fp-28,
+        0x1.20c62c2f2d7f5p-34 };
+    const double magic = 6755399441055744.0;
+    volatile double m = a + magic;          /* volatile: the rounding addition must really happen */
+    uint32_t q = (uint32_t)d2u(m);
+    double g = a - (m - magic);
+    double z = g * g;
+    double s = S[7], c = C[8];
+    for (int k = 6; k >= 0; k--) s = fma(z, s, S[k]);
+    s = g * s;
+    for (int k = 7; k >= 0; k--) c = fma(z, c, C[k]);
+    double so = (q & 1u) ? c : s, co = (q & 1u) ? s : c;
+    *sn = u2d(d2u(so) ^ ((uint64_t)(q & 2u) << 62));
+    *cs = u2d(d2u(co) ^ ((uint64_t)((q + 1u) & 2u) << 62));
+}
+
 /* Philox4x32-10 (Salmon et al., SC'11), the counter-based generator that replaces
  * std::mt19937_64 (P/:975, R/:3513) in the product. */
 void tmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
@@ -192,6 +218,20 @@ static double normal01(cstream *s, normal_state *st)
     if (st->saved_available) {
         st->saved_available = 0;
         return st->saved;
+    }
+    if (s->g->kind == TMO_SRC_PHILOX) {
+        /* Product spec, Philox streams only: the N(0,1) law of LS:1811-1848 drawn without its
+         * rejection loop -- Box-Muller on the next two uniforms.  Radius from x = 2 - m, m = 1+u0
+         * with its last mantissa bit set (x in (0,1), never 0 or 1); angle 2 pi u1.  The sequential
+         * and replay sources above keep the reference's polar loop draw for draw. */
+        double u0 = next_u(s), u1 = next_u(s);
+        double xr = 2.0 - u2d(d2u(1.0 + u0) | 1ull);
+        double r = sqrt(-2.0 * tmo_log(xr));
+        double sn, cs;
+        tmo_sincos_quadrants(4.0 * u1, &sn, &cs);
+        st->saved = r * sn;
+        st->saved_available = 1;
+        return r * cs;
     }
     double x, y, r2;
     int it = 0;
@@ -341,6 +381,17 @@ double tmo_test_normal_pair(const double *u, uint64_t n, uint64_t *pos, double *
     double a = normal01(&s, &st);
     *second = normal01(&s, &st);
     *pos = g.pos;
+    return a;
+}
+/* the first two normal variates of the Philox stream of one cell (Box-Muller law of the product spec) */
+double tmo_test_normal_pair_philox(uint64_t seed, uint32_t cell, uint32_t trial, uint32_t step, double *second)
+{
+    tmo_rng g; memset(&g, 0, sizeof g);
+    g.kind = TMO_SRC_PHILOX; g.seed = seed; g.trial = trial; g.step = step;
+    cstream s; cs_begin_cell(&s, &g, cell);
+    normal_state st = {0, 0.0};
+    double a = normal01(&s, &st);
+    *second = normal01(&s, &st);
     return a;
 }
 long tmo_test_poisson(const double *u, uint64_t n, uint64_t *pos, double mean)

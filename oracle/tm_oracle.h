@@ -85,12 +85,14 @@ typedef struct tmo_rng {
 /* ---- elementary functions of the sampler spec (bit-reproducible: IEEE + fma only) -- */
 double tmo_log(double x);
 double tmo_exp(double x);
+void tmo_sincos_quadrants(double a, double *sn, double *cs); /* sin, cos of (pi/2) a, a in [0,4] */
 double tmo_lgamma_int(double k);
 void   tmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double tmo_u52_from_bits(uint64_t w);
 
 /* ---- samplers (restating LS) driven by an array of uniforms; *pos advances -------- */
 double tmo_test_normal_pair(const double *u, uint64_t n, uint64_t *pos, double *second);
+double tmo_test_normal_pair_philox(uint64_t seed, uint32_t cell, uint32_t trial, uint32_t step, double *second);
 long   tmo_test_poisson(const double *u, uint64_t n, uint64_t *pos, double mean);
 double tmo_test_gamma(const double *u, uint64_t n, uint64_t *pos, double shape);
 

@@ -127,6 +127,51 @@ def test_normal_law_and_cache_order():
     assert abs(first - y * mult) <= 4e-16 * abs(first) and abs(second.value - x * mult) <= 4e-16 * abs(second.value)
 
 
+def test_sincos_quadrants_accuracy():
+    """The Box-Muller angle: sin/cos of (pi/2) a on [0,4], <= 2 ulp of the larger component, exact at the axes."""
+    L = O.oracle()
+    rng = np.random.default_rng(5)
+    a = np.concatenate([rng.random(40000) * 4, np.arange(0, 4.01, 0.125), 4 * (1 - 2.0 ** -np.arange(1, 53))])
+    sn, cs = C.c_double(), C.c_double()
+    worst = 0.0
+    for x in a:
+        L.tmo_sincos_quadrants(float(x), C.byref(sn), C.byref(cs))
+        q = round(x)
+        g = x - q                                    # exact
+        s0, c0 = math.sin(math.pi / 2 * g), math.cos(math.pi / 2 * g)
+        want_s, want_c = [(s0, c0), (c0, -s0), (-s0, -c0), (-c0, s0)][q % 4]
+        worst = max(worst, abs(sn.value - want_s) / 2.0 ** -53, abs(cs.value - want_c) / 2.0 ** -53)
+        assert abs(sn.value ** 2 + cs.value ** 2 - 1) < 5e-16
+    assert worst <= 3.0                              # in units of 2^-53 (half an ulp of 1)
+    for q, (ws, wc) in enumerate([(0.0, 1.0), (1.0, 0.0), (0.0, -1.0), (-1.0, 0.0), (0.0, 1.0)]):
+        L.tmo_sincos_quadrants(float(q), C.byref(sn), C.byref(cs))
+        assert (sn.value, cs.value) == (ws, wc)
+
+
+def test_box_muller_law_philox():
+    """Philox streams draw N(0,1) by Box-Muller (no rejection loop): law, pair independence, and the
+    explicit formula on the two uniforms of block 0."""
+    L = O.oracle()
+    a, b = [], []
+    second = C.c_double()
+    for cell in range(60000):
+        a.append(L.tmo_test_normal_pair_philox(77, cell, 3, 9, C.byref(second)))
+        b.append(second.value)
+    a, b = np.array(a), np.array(b)
+    assert stats.kstest(np.concatenate([a, b]), "norm").pvalue > 1e-4
+    assert stats.kstest(a * a + b * b, "chi2", args=(2,)).pvalue > 1e-4
+    assert abs(np.corrcoef(a, b)[0, 1]) < 0.02 and abs(np.corrcoef(a * a, b * b)[0, 1]) < 0.02
+    assert np.isfinite(a).all() and np.isfinite(b).all()
+    out = (C.c_uint32 * 4)()
+    L.tmo_philox4x32_10((C.c_uint32 * 4)(5, 3, 9, 0), (C.c_uint32 * 2)(77, 0), out)
+    u0 = L.tmo_u52_from_bits((out[1] << 32) | out[0])
+    u1 = L.tmo_u52_from_bits((out[3] << 32) | out[2])
+    x = 1.0 - u0 - (0.0 if (int((1.0 + u0) * 2 ** 52) & 1) else 2.0 ** -52)   # last mantissa bit of 1+u0 set
+    r = math.sqrt(-2 * math.log(x))
+    first = L.tmo_test_normal_pair_philox(77, 5, 3, 9, C.byref(second))
+    assert abs(first - r * math.cos(2 * math.pi * u1)) <= 1e-14 and abs(second.value - r * math.sin(2 * math.pi * u1)) <= 1e-14
+
+
 def test_incremental_stats_integer_division_quirk():
     """var_mean_incremental_surv_runs (P/:173-208): `1/(r-1)` is integer division, so the second
     variance term survives only for r == 2 (SURVEY A.5 #1)."""

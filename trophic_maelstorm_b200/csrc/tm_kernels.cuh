@@ -175,7 +175,7 @@ TM_D double sqrt_lean(double a)
     return sqrt(a);
 #endif
 }
-// log(x) for x in (0,1] (the polar method's r2), FAST arithmetic: x = 2^k m, m in [1,2); the top 7 mantissa
+// log(x) for x in (0,1] (the Box-Muller radius uniform), FAST arithmetic: x = 2^k m, m in [1,2); the top 7 mantissa
 // bits pick c_i = 1 + (i + 1/2)/128 from a 128-entry table {1/c_i, log c_i}; r = m/c_i - 1 is below 2^-8 and
 // log m = log c_i + (r - r^2/2 + r^3/3 - r^4/4 + r^5/5 - r^6/6).  No division; ~1e-16 absolute.
 struct LogTab { double invc[128], logc[128]; };
@@ -304,7 +304,7 @@ TM_HD size_t riet_smem_bytes(int nthreads, bool det)
     const size_t nf = det ? 3 : 2;
     const size_t st = 3 * kStSlots * nf * RW;
     (void)nthreads;
-    return sizeof(double) * (kInSlots * 3 * RW + st) + sizeof(uint64_t) * kInSlots + sizeof(uint32_t) * 32 * (kMaxThreads / 32) + 128;
+    return sizeof(double) * (kInSlots * 3 * RW + st) + sizeof(uint64_t) * kInSlots + 128;
 }
 
 // The exact-sampler branches (Poisson mean <= 100, Gamma shape <= 100: extinction fringe only) are
@@ -323,11 +323,14 @@ double riet_cell_exact(DornicConsts dk, uint32_t cell, uint32_t trial, uint32_t 
     return dornic_cell<kRietkerk>(dk, src, alpha_i, rho_i);
 }
 
-// One candidate of the polar method: uniforms 2k, 2k+1 of the cell's stream (= Philox block k).
-TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t k, const PhiloxKeys &rk,
-                          double &x, double &y, double &r2)
+// The Box-Muller pair of a cell's Philox stream: the first two std::normal_distribution variates the
+// generic normal01(PhiloxSrc) would return (uniforms 0 and 1 = Philox block 0), built straight from the
+// block's bits.  Straight-line code, no rejection: every lane of a warp does the same work.
+template <bool STRICT>
+TM_D void gauss_pair(uint32_t cell, uint32_t trial, uint32_t step, const PhiloxKeys &rk, const double *logtab,
+                     double &n_first, double &n_second)
 {
-    uint32_t c0 = cell, c1 = trial, c2 = step, c3 = k;
+    uint32_t c0 = cell, c1 = trial, c2 = step, c3 = 0;
 #pragma unroll
     for (int r = 0; r < 10; r++) { // same rounds as philox4x32_10(), keys read from the schedule
         uint32_t h0, l0, h1, l1;
@@ -336,73 +339,16 @@ TM_D bool polar_candidate(uint32_t cell, uint32_t trial, uint32_t step, uint32_t
         c0 = h1 ^ c1 ^ rk.k[r][0]; c1 = l1;
         c2 = h0 ^ c3 ^ rk.k[r][1]; c3 = l0;
     }
-    // 2u - 1 with u = u52(.): both steps are exact, so (2m) - 3 with m the [1,2) mantissa double is the
-    // same number in one operation: as_double(0x400.. | w >> 12) = 2m
-    x = u2d(0x4000000000000000ull | ((((uint64_t)c1 << 32) | c0) >> 12)) - 3.0;
-    y = u2d(0x4000000000000000ull | ((((uint64_t)c3 << 32) | c2) >> 12)) - 3.0;
-    r2 = fma(x, x, y * y);
-    return !(r2 > 1.0 || r2 == 0.0);
-}
-
-// Warp-level polar sampler: the first two std::normal_distribution variates (LS:1811-1848) of the
-// streams of the lanes with `need`.  Every lane first tries block 0 of its own stream; the retries of
-// the ~21 % of lanes whose candidate fell outside the unit disc are then spread over ALL 32 lanes
-// (blocks k, k+1, .. of a rejected lane are evaluated side by side by helper lanes), and each owner
-// takes the lowest accepted block -- exactly the pair a sequential loop over its stream would have
-// accepted, in ~2 warp passes instead of ~3.1 with divergent per-lane loops.
-// Must be called by all 32 lanes of a warp (trial/step/seed warp-uniform).
-template <bool STRICT>
-TM_D void polar_pair_warp(bool need, uint32_t cell, uint32_t trial, uint32_t step, const PhiloxKeys &rk,
-                          uint32_t *warp_scratch, const double *logtab, double &n_first, double &n_second)
-{
-    double x = 0.5, y = 0.5, r2 = 0.5;
-    bool ok = true;
-#if defined(__CUDA_ARCH__)
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    if (need) ok = polar_candidate(cell, trial, step, 0, rk, x, y, r2);
-    unsigned pending = __ballot_sync(full, !ok);
-    uint32_t kbase = 1;
-    while (pending != 0 && kbase < (uint32_t)kMaxReject) {
-        const int F = __popc(pending);
-        const int lg = (F <= 8) ? 2 : (F <= 16) ? 1 : 0;      // 4, 2 or 1 candidate blocks per rejected lane
-        const int per = 1 << lg;
-        const int fi = lane >> lg;                            // which rejected lane this lane helps
-        const bool helper = fi < F;
-        // compact the rejected lanes' cells by rank (warp-private scratch), helpers pick theirs up
-        const int rank = __popc(pending & ((1u << lane) - 1u));
-        if (!ok) warp_scratch[rank] = cell;
-        __syncwarp(full);
-        const uint32_t cell_s = warp_scratch[helper ? fi : 0];
-        __syncwarp(full);
-        double hx = 0.5, hy = 0.5, hr2 = 2.0;
-        bool hok = false;
-        if (helper) hok = polar_candidate(cell_s, trial, step, kbase + (uint32_t)(lane & (per - 1)), rk, hx, hy, hr2);
-        const unsigned okmask = __ballot_sync(full, hok);
-        int from = lane;
-        bool got = false;
-        if (!ok) {
-            const unsigned mine = ((per == 32) ? full : ((1u << per) - 1u)) << (rank << lg);
-            const unsigned hit = okmask & mine;
-            if (hit) { from = __ffs((int)hit) - 1; got = true; }
-        }
-        const double sx = __shfl_sync(full, hx, from), sy = __shfl_sync(full, hy, from), sr = __shfl_sync(full, hr2, from);
-        if (got) { x = sx; y = sy; r2 = sr; ok = true; }
-        pending = __ballot_sync(full, !ok);
-        kbase += (uint32_t)per;
-    }
-#else
-    if (need) {
-        uint32_t k = 0;
-        do { ok = polar_candidate(cell, trial, step, k, rk, x, y, r2); } while (!ok && ++k < (uint32_t)kMaxReject);
-    }
-#endif
-    if (!ok) { x = 0.5; y = 0.5; r2 = 0.5; } // bound reached (never with genuine uniforms)
-    double mult;
-    if (STRICT) mult = sqrt(-2.0 * log_pos(r2) / r2);            // LS:1832
-    else        mult = sqrt_lean(-2.0 * log_lean(r2, logtab) * rcp_lean(r2));
-    n_second = x * mult;
-    n_first = y * mult;
+    // x = 2 - (1 + u0 | last bit) and a = 4 u1, each in one exact operation from the [1,2) / [4,8) mantissa doubles
+    const double x = 2.0 - u2d(0x3FF0000000000001ull | ((((uint64_t)c1 << 32) | c0) >> 12));
+    const double a = u2d(0x4010000000000000ull | ((((uint64_t)c3 << 32) | c2) >> 12)) - 4.0;
+    double r;
+    if (STRICT) r = sqrt(-2.0 * log_pos(x));
+    else        r = sqrt_lean(fabs(-2.0 * log_lean(x, logtab)) + 0x1p-200); // (the bias keeps a cancelled log off rsqrt(0))
+    double sn, cs;
+    sincos_quadrants(a, sn, cs);
+    n_first = r * cs;
+    n_second = r * sn;
 }
 
 // SRC: where rho* comes from -- kSrcPhilox: sampled in front 1 (fused); kSrcReplay: same with host uniforms;
@@ -429,7 +375,6 @@ riet_step_kernel(const StepArgs A)
     double *st = in + kInSlots * 3 * RW;
     const size_t st_doubles = (size_t)3 * kStSlots * NF * RW;
     uint64_t *mbar = reinterpret_cast<uint64_t *>(st + st_doubles);
-    uint32_t *wscratch = reinterpret_cast<uint32_t *>(mbar + kInSlots) + 32 * (tid >> 5); // warp-private
     const double *logtab = A.logtab; // 2 KB, read through L1 (shared memory is fully booked by the rings at 4 CTAs/SM)
 
     if (tid == 0) {
@@ -534,7 +479,7 @@ riet_step_kernel(const StepArgs A)
                             atomicAdd(&A.counters[0], (unsigned long long)src.overflow_count());
                     }
                 } else {
-                    // Gaussian regime of R/:3773-3789 inline and warp-cooperative; everything else
+                    // Gaussian regime of R/:3773-3789 inline (Box-Muller pair of the cell's stream); everything else
                     // (Poisson mean <= 100 or Gamma shape <= 100: the extinction fringe) out of line.
                     const uint32_t ptrial = A.trial0 + (uint32_t)trial;
                     const double ziggy = c.dk.ll * Pc;
@@ -542,8 +487,8 @@ riet_step_kernel(const StepArgs A)
                                               : 2.0 * alpha_i * c.dk.sigma2_1;
                     const bool gauss_n = live && ziggy > 100;
                     const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
-                    double n_first, n_second;
-                    polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, logtab, n_first, n_second);
+                    double n_first = 0.0, n_second = 0.0;
+                    if (fastp) gauss_pair<STRICT>(cell, ptrial, A.step, A.rk, logtab, n_first, n_second);
                     bool exact = live && !fastp;
                     if (fastp) {
                         double gru = mu1, nz = n_first;
@@ -645,7 +590,7 @@ riet_step_kernel(const StepArgs A)
 // One thread per column, marching down a run of rows: the vertical neighbours roll through registers,
 // the horizontal ones come from the neighbouring lanes by shuffle (only the two edge lanes of a warp
 // load theirs), so a cell costs one global load and one store.  No pipeline state beyond that: 64
-// registers, 32 warps per SM, and the long serial chain (Philox -> polar -> log -> sqrt -> trunc -> sqrt)
+// registers, 32 warps per SM, and the long serial chain (Philox -> log -> sqrt -> sincos -> trunc -> sqrt)
 // of one warp hides behind seven others.  Writes rho* in the padded layout (ghost columns included) for
 // riet_step_kernel<.., kSrcPre, ..>.  Costs one extra field write + read per site (64 instead of 48 B)
 // on a kernel pair that sits far below the HBM roofline.
@@ -677,8 +622,7 @@ riet_dornic_kernel(const DornicArgs A)
     const DornicConsts &dk = A.dk;
     const int tid = threadIdx.x;
     TM_DYN_SMEM(smem_raw);
-    uint32_t *wscratch = reinterpret_cast<uint32_t *>(smem_raw) + 32 * (tid >> 5);
-    double *logtab = reinterpret_cast<double *>(reinterpret_cast<uint32_t *>(smem_raw) + 32 * (kDornicThreads / 32)); // [128][2]
+    double *logtab = reinterpret_cast<double *>(smem_raw); // [128][2]
     if (!STRICT) { logtab[tid] = A.logtab[tid]; __syncthreads(); }
     // work item = (trial, column block of 256, run of rows_per_cta rows)
     const int ncb = (g.L + kDornicThreads - 1) / kDornicThreads;
@@ -727,8 +671,8 @@ riet_dornic_kernel(const DornicArgs A)
             const double mu1 = STRICT ? (-1.0 + 2.0 * alpha_i * dk.sigma2_1) + 1.0 : 2.0 * alpha_i * dk.sigma2_1;
             const bool gauss_n = live && ziggy > 100;
             const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
-            double n_first, n_second;
-            polar_pair_warp<STRICT>(fastp, cell, ptrial, A.step, A.rk, wscratch, logtab, n_first, n_second);
+            double n_first = 0.0, n_second = 0.0;
+            if (fastp) gauss_pair<STRICT>(cell, ptrial, A.step, A.rk, logtab, n_first, n_second);
             bool exact = live && !fastp;
             if (fastp) {
                 double gru = mu1, nz = n_first;

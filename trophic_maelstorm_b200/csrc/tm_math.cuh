@@ -137,6 +137,39 @@ TM_HD double lgamma_int(double k)
     return (fma(k - 0.5, log_pos(k), -k) + HALF_LOG_2PI) + ser;
 }
 
+// sin and cos of (pi/2) a for a in [0,4] -- the angle of the Box-Muller pair (Philox mode, tm_samplers.cuh).
+// q = a rounded to the nearest integer (ties to even, by the 1.5*2^52 addition), g = a - q in [-1/2,1/2]
+// (exact); Taylor series of sin/cos((pi/2) g) in g^2 (truncation < 5e-17), then the quadrant q mod 4
+// swaps / negates.  Pure +,-,*,fma and bit operations: the same bits on every machine.
+TM_HD void sincos_quadrants(double a, double &sn, double &cs)
+{
+    const double magic = 6755399441055744.0; // 1.5 * 2^52
+    const double m = a + magic;
+    const uint32_t q = (uint32_t)d2u(m);
+    const double g = a - (m - magic);
+    const double z = g * g;
+    double s = fma(z, -0x1.6fadb9f155744p-31, 0x1.e8f434d018d63p-25);
+    s = fma(z, s, -0x1.e3074fde8871fp-19);
+    s = fma(z, s, 0x1.50783487ee782p-13);
+    s = fma(z, s, -0x1.32d2cce62bd86p-8);
+    s = fma(z, s, 0x1.466bc6775aae2p-4);
+    s = fma(z, s, -0x1.4abbce625be53p-1);
+    s = fma(z, s, 0x1.921fb54442d18p+0);
+    s = g * s;
+    double c = fma(z, 0x1.20c62c2f2d7f5p-34, -0x1.b6e24f44b128fp-28);
+    c = fma(z, c, 0x1.f9d38a3763cc3p-22);
+    c = fma(z, c, -0x1.a6d1f2a204a8cp-16);
+    c = fma(z, c, 0x1.e1f506891babbp-11);
+    c = fma(z, c, -0x1.55d3c7e3cbffap-6);
+    c = fma(z, c, 0x1.03c1f081b5ac4p-2);
+    c = fma(z, c, -0x1.3bd3cc9be45dep+0);
+    c = fma(z, c, 1.0);
+    const bool swap = (q & 1u) != 0;
+    const double so = swap ? c : s, co = swap ? s : c;
+    sn = u2d(d2u(so) ^ ((uint64_t)(q & 2u) << 62));          // quadrants 2,3: sin < 0
+    cs = u2d(d2u(co) ^ ((uint64_t)((q + 1u) & 2u) << 62));   // quadrants 1,2: cos < 0
+}
+
 // Philox4x32-10, counter (c0..c3), key (k0,k1).
 struct u32x4 { uint32_t x, y, z, w; };
 

@@ -3,7 +3,8 @@
 //
 // The sampling LAWS and the order in which uniforms are consumed follow what the reference gets
 // from libstdc++ (LS = <bits/random.tcc>, GCC 13):
-//   std::normal_distribution  LS:1811-1848   Marsaglia polar, one cached variate
+//   std::normal_distribution  LS:1811-1848   Marsaglia polar, one cached variate (replay mode; a Philox
+//                                            stream draws the same law by Box-Muller, no rejection loop)
 //   std::poisson_distribution LS:1267-1400   product of uniforms (mean < 12), Devroye rejection (>= 12)
 //   std::gamma_distribution   LS:2338-2387   Marsaglia-Tsang, u^(1/alpha) boost for alpha < 1
 // as called per cell at P/:1055-1059 (DP), P/:1957-1979 (cubic DP), R/:3766-3794 (Rietkerk,
@@ -20,6 +21,7 @@ namespace tml {
 // Philox4x32-10: key = seed, counter = (cell, trial, step, block); block b yields uniforms
 // 2b (words 0,1) and 2b+1 (words 2,3).
 struct PhiloxSrc {
+    static constexpr bool kBoxMuller = true;   // normal law of this source: see normal01()
     uint32_t cell, trial, step, k0, k1;
     uint32_t n;       // uniforms handed out so far
     double second;
@@ -42,6 +44,7 @@ struct PhiloxSrc {
 
 // Replay: uniform k of this cell is base[k], k < stride; beyond that 0.75 and a counted overflow.
 struct ReplaySrc {
+    static constexpr bool kBoxMuller = false;  // replay follows the reference's polar loop draw for draw
     const double *base;
     uint32_t stride, n, ovf;
     TM_HD void begin(const double *base_, uint32_t stride_) { base = base_; stride = stride_; n = 0; ovf = 0; }
@@ -64,6 +67,18 @@ template <class Src>
 TM_HD double normal01(Src &s, NormalState &st)
 {
     if (st.have) { st.have = false; return st.saved; }
+    if (Src::kBoxMuller) {
+        // Philox mode: the same N(0,1) law without the rejection loop.  Box-Muller on the next two
+        // uniforms: radius from x = 2 - (1+u0 with its last mantissa bit set), in (0,1); angle 2 pi u1.
+        const double u0 = s.next(), u1 = s.next();
+        const double x = 2.0 - u2d(d2u(1.0 + u0) | 1ull);
+        const double r = sqrt(-2.0 * log_pos(x));
+        double sn, cs;
+        sincos_quadrants(4.0 * u1, sn, cs);
+        st.saved = r * sn;
+        st.have = true;
+        return r * cs;
+    }
     double x, y, r2;
     int it = 0;
     do {
