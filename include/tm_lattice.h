@@ -98,9 +98,10 @@ int tm_set_trial_a(tm_ctx *, int trial, double a);
  * to the oracle); 0 (default): the fast arrangement (shared reciprocal, fused multiply-adds). */
 int tm_set_strict(tm_ctx *, int strict);
 
-/* Rietkerk model only.  fused != 0 (default): one fused launch per step, 48 B of HBM traffic per site.
- * fused == 0: each step is two launches -- the vegetation Dornic sweep (one thread per column, 32 warps
- * per SM) into a rho* scratch field, then the marching RK4 kernel; 64 B per site, ~2 % faster on B200.
+/* Rietkerk model only.  fused == 0 (default): each step is two launches -- the vegetation Dornic sweep (one
+ * thread per column, 32 warps per SM) into a rho* scratch field, then the marching RK4 kernel; 64 B of HBM
+ * traffic per site.  fused != 0: one launch per step, 48 B per site, slower on B200 (both kernels are bound
+ * by FP64/issue slots, not HBM; the fused loop body does not fit the instruction cache once unrolled).
  * Results are bit-identical either way. */
 int tm_set_fused(tm_ctx *, int fused);
 

@@ -106,30 +106,28 @@ double tmo_lgamma_int(double k)
     return (fma(k - 0.5, tmo_log(k), -k) + HALF_LOG_2PI) + ser;
 }
 
-/* sin and cos of (pi/2) a, a in [0,4]: nearest-integer quadrant q (ties to even through the
- * 1.5*2^52 addition), g = a - q in [-1/2,1/2] exactly, Taylor series of sin/cos((pi/2) g) in g^2
- * with the coefficients (-1)^k (pi/2)^n / n! rounded to double, quadrant swap / sign by bit
- * operations.  Own restatement of the spec in DESIGN.md section 3 (Box-Muller angle). */
-void tmo_sincos_quadrants(double a, double *sn, double *cs)
+/* sin and cos of 2 pi a/128, a in [0,128] -- the Box-Muller angle of the product spec (DESIGN.md
+ * section 3): nearest grid point i (ties to even through the 1.5*2^52 addition), g = a - i in
+ * [-1/2,1/2] exactly, b = (pi/64) g; sin b and cos b - 1 by Taylor series in g^2 with the
+ * coefficients (+-)(pi/64)^n / n! (S2, S3, C3 rounded to 21 significant bits, as the spec says), then
+ * the angle addition with {sin, cos}(2 pi i/128) from the correctly rounded table of gen_tables.py. */
+static const double tmo_sincos_tab[256] = {
+#include "tm_sincos_table.inc"
+};
+void tmo_sincos_turn128(double a, double *sn, double *cs)
 {
-    static const double S[8] = { 0x1.921fb54442d18p+0, -0x1.4abbce625be53p-1, 0x1.466bc6775aae2p-4,
-        -0x1.32d2cce62bd86p-8, 0x1.50783487ee782p-13, -0x1.e3074fde8871fp-19, 0x1.e8f434d018d63p-25,
-        -0x1.6fadb9f155744p-31 };
-    static const double C[9] = { 1.0, -0x1.3bd3cc9be45dep+0, 0x1.03c1f081b5ac4p-2, -0x1.55d3c7e3cbffap-6,
-        0x1.e1f506891babbp-11, -0x1.a6d1f2a204a8cp-16, 0x1.f9d38a3763cc3p-22, -0x1.b6e24f44b128fp-28,
-        0x1.20c62c2f2d7f5p-34 };
+    static const double S[4] = { 0x1.921fb54442d18p-5, -0x1.4abbce625be53p-16, 0x1.466bc00000000p-29, -0x1.32d2d00000000p-43 };
+    static const double C[4] = { 0.0, -0x1.3bd3cc9be45dep-10, 0x1.03c1f081b5ac4p-22, -0x1.55d3c00000000p-36 };
     const double magic = 6755399441055744.0;
     volatile double m = a + magic;          /* volatile: the rounding addition must really happen */
-    uint32_t q = (uint32_t)d2u(m);
+    uint32_t i = (uint32_t)d2u(m) & 127u;
     double g = a - (m - magic);
     double z = g * g;
-    double s = S[7], c = C[8];
-    for (int k = 6; k >= 0; k--) s = fma(z, s, S[k]);
-    s = g * s;
-    for (int k = 7; k >= 0; k--) c = fma(z, c, C[k]);
-    double so = (q & 1u) ? c : s, co = (q & 1u) ? s : c;
-    *sn = u2d(d2u(so) ^ ((uint64_t)(q & 2u) << 62));
-    *cs = u2d(d2u(co) ^ ((uint64_t)((q + 1u) & 2u) << 62));
+    double sb = g * fma(z, fma(z, fma(z, S[3], S[2]), S[1]), S[0]);
+    double cb = z * fma(z, fma(z, C[3], C[2]), C[1]);
+    double si = tmo_sincos_tab[2 * i], ci = tmo_sincos_tab[2 * i + 1];
+    *sn = fma(si, cb, fma(ci, sb, si));
+    *cs = fma(ci, cb, fma(-si, sb, ci));
 }
 
 /* Philox4x32-10 (Salmon et al., SC'11), the counter-based generator that replaces
@@ -228,7 +226,7 @@ static double normal01(cstream *s, normal_state *st)
         double xr = 2.0 - u2d(d2u(1.0 + u0) | 1ull);
         double r = sqrt(-2.0 * tmo_log(xr));
         double sn, cs;
-        tmo_sincos_quadrants(4.0 * u1, &sn, &cs);
+        tmo_sincos_turn128(128.0 * u1, &sn, &cs);
         st->saved = r * sn;
         st->saved_available = 1;
         return r * cs;

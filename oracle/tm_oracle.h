@@ -85,7 +85,7 @@ typedef struct tmo_rng {
 /* ---- elementary functions of the sampler spec (bit-reproducible: IEEE + fma only) -- */
 double tmo_log(double x);
 double tmo_exp(double x);
-void tmo_sincos_quadrants(double a, double *sn, double *cs); /* sin, cos of (pi/2) a, a in [0,4] */
+void tmo_sincos_turn128(double a, double *sn, double *cs); /* sin, cos of 2 pi a/128, a in [0,128] */
 double tmo_lgamma_int(double k);
 void   tmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 double tmo_u52_from_bits(uint64_t w);

@@ -84,9 +84,9 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
             } else if (g_split) {
                 std::vector<double> pstar((size_t)g.n_trials * g.field_stride, 0.0);
                 DornicArgs D{};
-                D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.in = A.in; D.pstar = pstar.data();
+                D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.mu_scale = A.c.mu_scale; D.in = A.in; D.pstar = pstar.data();
                 D.seed = seed; D.trial0 = trial0; D.step = step0 + s; D.rk = A.rk; D.logtab = A.logtab; D.row_lo = 0; D.row_hi = g.nrows; D.rows_per_cta = 7;
-                const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32) + sizeof(double) * 256;
+                const size_t dsmem = riet_dornic_smem_bytes();
                 if (strict) emu_launch(riet_dornic_kernel<true>, D, 3, kDornicThreads, dsmem);
                 else        emu_launch(riet_dornic_kernel<false>, D, 3, kDornicThreads, dsmem);
                 A.pstar = pstar.data();

@@ -127,25 +127,45 @@ def test_normal_law_and_cache_order():
     assert abs(first - y * mult) <= 4e-16 * abs(first) and abs(second.value - x * mult) <= 4e-16 * abs(second.value)
 
 
-def test_sincos_quadrants_accuracy():
-    """The Box-Muller angle: sin/cos of (pi/2) a on [0,4], <= 2 ulp of the larger component, exact at the axes."""
+def _sincos_exact(a):
+    """sin, cos of 2 pi a/128 for a double a, in 50-digit decimal arithmetic (a is used exactly)."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 50
+    pi = Decimal("3.14159265358979323846264338327950288419716939937510582097494")
+    q = round(a / 32.0)                                   # quadrant; the remainder is exact
+    x = 2 * pi * (Decimal(a) - 32 * q) / 128
+    s, c, t = Decimal(0), Decimal(0), Decimal(1)
+    for n in range(40):
+        if n % 2 == 0:
+            c += t if (n // 2) % 2 == 0 else -t
+        else:
+            s += t if (n // 2) % 2 == 0 else -t
+        t = t * x / (n + 1)
+    return [(s, c), (c, -s), (-s, -c), (-c, s)][q % 4]
+
+
+def test_sincos_turn128_accuracy():
+    """The Box-Muller angle: sin/cos of 2 pi a/128 on [0,128]: within 2^-52 of the exact value, exact on the axes,
+    and the table the product carries equals the oracle's."""
     L = O.oracle()
     rng = np.random.default_rng(5)
-    a = np.concatenate([rng.random(40000) * 4, np.arange(0, 4.01, 0.125), 4 * (1 - 2.0 ** -np.arange(1, 53))])
+    a = np.concatenate([rng.random(4000) * 128, np.arange(0, 128.01, 0.5), 128 * (1 - 2.0 ** -np.arange(1, 53))])
     sn, cs = C.c_double(), C.c_double()
     worst = 0.0
     for x in a:
-        L.tmo_sincos_quadrants(float(x), C.byref(sn), C.byref(cs))
-        q = round(x)
-        g = x - q                                    # exact
-        s0, c0 = math.sin(math.pi / 2 * g), math.cos(math.pi / 2 * g)
-        want_s, want_c = [(s0, c0), (c0, -s0), (-s0, -c0), (-c0, s0)][q % 4]
-        worst = max(worst, abs(sn.value - want_s) / 2.0 ** -53, abs(cs.value - want_c) / 2.0 ** -53)
-        assert abs(sn.value ** 2 + cs.value ** 2 - 1) < 5e-16
-    assert worst <= 3.0                              # in units of 2^-53 (half an ulp of 1)
+        L.tmo_sincos_turn128(float(x), C.byref(sn), C.byref(cs))
+        ws, wc = _sincos_exact(float(x))
+        worst = max(worst, abs(sn.value - float(ws)), abs(cs.value - float(wc)))
+        assert abs(sn.value ** 2 + cs.value ** 2 - 1) < 6e-16
+    assert worst <= 2.0 ** -52
     for q, (ws, wc) in enumerate([(0.0, 1.0), (1.0, 0.0), (0.0, -1.0), (-1.0, 0.0), (0.0, 1.0)]):
-        L.tmo_sincos_quadrants(float(q), C.byref(sn), C.byref(cs))
+        L.tmo_sincos_turn128(32.0 * q, C.byref(sn), C.byref(cs))
         assert (sn.value, cs.value) == (ws, wc)
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    strip = lambda p: [l.split("/*")[0].strip() for l in open(p) if l.lstrip().startswith(("0x", "-0x"))]
+    assert strip(os.path.join(root, "oracle", "tm_sincos_table.inc")) == \
+        strip(os.path.join(root, "trophic_maelstorm_b200", "csrc", "tm_sincos_table.inc"))
 
 
 def test_box_muller_law_philox():

@@ -48,6 +48,7 @@ static inline RietConsts riet_consts(const tm_params &p)
     c.eps = p.clamp_eps; c.lo = p.clamp_lo;
     c.dk = dornic_consts(p, p.a);
     c.inv_lambda = 1.0 / c.dk.lambda;
+    c.mu_scale = 2.0 * c.dk.diffc * c.dk.sigma2_1;
     c.aK2W0 = c.alpha * c.K2W0; c.cP = -(c.d + 4 * c.Dp); c.cW = -(c.rW + 4 * c.Dw); c.cO = -4 * c.Do;
     return c;
 }

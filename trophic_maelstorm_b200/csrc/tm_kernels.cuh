@@ -60,6 +60,7 @@ struct RietConsts {
     double W0;
     double eps, lo;      // clamp
     double inv_lambda;   // 1/dk.lambda (FAST arithmetic only)
+    double mu_scale;     // 2 (D0/dx^2) / sigma0^2 (FAST arithmetic only)
     double aK2W0, cP, cW, cO; // FAST: alpha*K2*W0, -(d+4Dp), -(rW+4Dw), -4Do
     DornicConsts dk;
 };
@@ -127,6 +128,8 @@ TM_D bool mbar_try_wait(uint64_t *b, uint32_t parity)
 // bounded wait: a lost copy must not hang the GPU; it is counted and the step's output is garbage
 TM_D bool mbar_wait(uint64_t *b, uint32_t parity)
 {
+    if (mbar_try_wait(b, parity)) return true;
+#pragma unroll 1
     for (int i = 0; i < (1 << 24); i++)
         if (mbar_try_wait(b, parity)) return true;
     return false;
@@ -171,6 +174,20 @@ TM_D double sqrt_lean(double a)
     double s = a * y;
     s = fma(fma(-s, s, a), 0.5 * y, s);                      // Heron step on sqrt(a): error squared again, ~1 ulp
     return s;
+#else
+    return sqrt(a);
+#endif
+}
+// sqrt(a) with ONE Newton step on the reciprocal root (rel. error ~1e-13): for the Gaussian Gamma shortcut
+// only, where it multiplies a noise term that is at most 1/10 of the result (R/:3787, shape > 100).
+TM_D double sqrt_lean1(double a)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return a * y;
 #else
     return sqrt(a);
 #endif
@@ -287,14 +304,18 @@ TM_D void flush_stats(const ThreadStats &ts, int n_fields, int trial, PartialSta
 // ------------------------------------------------------------------------------------------
 // Rietkerk fused step
 // ------------------------------------------------------------------------------------------
-// shared memory carve-up (doubles unless noted), RW = nthreads + 4 (2 pad each side, 16 B aligned);
+// shared memory carve-up (doubles unless noted), RW = kMaxThreads + 4 (2 pad each side, 16 B aligned);
 // the element of thread cx sits at [cx + 2] of a row:
-//   in   [kInSlots][3][RW]    TMA destination rows (P,W,O) = stage-0 state, rows j-4 .. j+kPrefetch
-//   st   [3][kStSlots][NF][RW] stage-1/2/3 states (W,O[,P]) of the last kStSlots rows of each front
-//   mbar uint64[kInSlots]
-constexpr int kInSlots = 8;
+//   pr   [kPSlots][RW]           TMA destination, P rows j-2 .. j+3 (stage-0 P = the Dornic input)
+//   wo   [kWoSlots][2][RW]       TMA destination, W and O rows j-4 .. j+4
+//   st   [3][kStSlots][NF][RW]   stage-1/2/3 states (W,O[,P]) of the last kStSlots rows of each front
+//   mbar uint64[kWoSlots]        one per streamed row (its three bulk copies)
+// The marching loop is unrolled by three rows, so a ring slot is (group base that rotates every three
+// rows) + (compile-time offset): kPSlots, kWoSlots and kStSlots are multiples of three.
+constexpr int kPSlots = 6;
+constexpr int kWoSlots = 9;
 constexpr int kStSlots = 3;
-constexpr int kPrefetch = 3;
+constexpr int kLead = 4;               // row j+kLead is requested when row j has been consumed
 
 constexpr int kRW = kMaxThreads + 4;   // shared row width: compile-time, so field/neighbour offsets fold into immediates
 
@@ -302,10 +323,18 @@ TM_HD size_t riet_smem_bytes(int nthreads, bool det)
 {
     const size_t RW = (size_t)kRW;
     const size_t nf = det ? 3 : 2;
-    const size_t st = 3 * kStSlots * nf * RW;
     (void)nthreads;
-    return sizeof(double) * (kInSlots * 3 * RW + st) + sizeof(uint64_t) * kInSlots + 128;
+    return sizeof(double) * RW * (kPSlots + 2 * kWoSlots + 3 * kStSlots * nf) + sizeof(uint64_t) * kWoSlots + 128;
 }
+
+// offset of row j+R (R in [-6,2]) in a ring made of groups of three slots: o0 = group of rows j..j+2,
+// o1 = rows j-3..j-1, o2 = rows j-6..j-4 (group bases, in doubles); ss = doubles per slot
+template <int R>
+TM_D int ring_off(int o0, int o1, int o2, int ss)
+{
+    return (R >= 0) ? o0 + R * ss : (R >= -3) ? o1 + (R + 3) * ss : o2 + (R + 6) * ss;
+}
+template <int N> struct IntC { static constexpr int value = N; };
 
 // The exact-sampler branches (Poisson mean <= 100, Gamma shape <= 100: extinction fringe only) are
 // kept out of line so the marching loop stays small; they redo the cell from its counter, which
@@ -328,7 +357,7 @@ double riet_cell_exact(DornicConsts dk, uint32_t cell, uint32_t trial, uint32_t 
 // block's bits.  Straight-line code, no rejection: every lane of a warp does the same work.
 template <bool STRICT>
 TM_D void gauss_pair(uint32_t cell, uint32_t trial, uint32_t step, const PhiloxKeys &rk, const double *logtab,
-                     double &n_first, double &n_second)
+                     const double *sctab, double &n_first, double &n_second)
 {
     uint32_t c0 = cell, c1 = trial, c2 = step, c3 = 0;
 #pragma unroll
@@ -339,16 +368,50 @@ TM_D void gauss_pair(uint32_t cell, uint32_t trial, uint32_t step, const PhiloxK
         c0 = h1 ^ c1 ^ rk.k[r][0]; c1 = l1;
         c2 = h0 ^ c3 ^ rk.k[r][1]; c3 = l0;
     }
-    // x = 2 - (1 + u0 | last bit) and a = 4 u1, each in one exact operation from the [1,2) / [4,8) mantissa doubles
+    // x = 2 - (1 + u0 | last bit) and a = 128 u1, each in one exact operation from the [1,2) / [128,256) mantissa doubles
     const double x = 2.0 - u2d(0x3FF0000000000001ull | ((((uint64_t)c1 << 32) | c0) >> 12));
-    const double a = u2d(0x4010000000000000ull | ((((uint64_t)c3 << 32) | c2) >> 12)) - 4.0;
+    const double a = u2d(0x4060000000000000ull | ((((uint64_t)c3 << 32) | c2) >> 12)) - 128.0;
     double r;
     if (STRICT) r = sqrt(-2.0 * log_pos(x));
     else        r = sqrt_lean(fabs(-2.0 * log_lean(x, logtab)) + 0x1p-200); // (the bias keeps a cancelled log off rsqrt(0))
     double sn, cs;
-    sincos_quadrants(a, sn, cs);
+    sincos_turn128(a, sctab, sn, cs);
     n_first = r * cs;
     n_second = r * sn;
+}
+
+// rho* of one cell of the Rietkerk vegetation field (R/:3756-3793) from a Philox stream, Gaussian regime only
+// (Poisson mean > 100 and Gamma shape > 100: every cell away from the extinction fringe).  Cells that need the
+// exact samplers come back with needs_exact = true and the caller runs riet_cell_exact() on them OUTSIDE its hot
+// loop where it can: a call inside the loop makes the compiler keep the loop-carried state on the stack.
+// nbsum = sum of the four neighbours; in_range = false for lanes outside the lattice.
+template <bool STRICT>
+TM_D double riet_dornic_value(const DornicConsts &dk, double inv_lambda, double mu_scale, double Pc, double nbsum, bool in_range,
+                              uint32_t cell, uint32_t ptrial, uint32_t step, const PhiloxKeys &rk,
+                              const double *logtab, const double *sctab, bool &needs_exact)
+{
+    const double alpha_i = dk.diffc * nbsum;
+    const bool live = !((STRICT ? alpha_i : nbsum) == 0 && Pc == 0) && in_range;   // skip rule R/:3759
+    const double ziggy = dk.ll * Pc;
+    const double mu1 = STRICT ? (-1.0 + 2.0 * alpha_i * dk.sigma2_1) + 1.0  // mu + 1.0 in the reference's order
+                              : mu_scale * nbsum;                            // 2 (D/dx^2) / sigma^2 folded on the host
+    const bool gauss_n = live && ziggy > 100;
+    const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
+    needs_exact = live && !fastp;
+    double pstar = Pc;
+    if (fastp) {
+        double n_first, n_second;
+        gauss_pair<STRICT>(cell, ptrial, step, rk, logtab, sctab, n_first, n_second);
+        double gru = mu1, nz = n_first;
+        if (gauss_n) {
+            if (STRICT) gru = mu1 + (double)(long long)fma(n_first, sqrt(ziggy), ziggy);   // R/:3776
+            else        gru = mu1 + trunc(fma(n_first, sqrt_lean(ziggy), ziggy));          // same value below 2^63
+            nz = n_second;
+        }
+        if (gru > 100) pstar = STRICT ? fma(nz, sqrt(gru), gru) / dk.lambda : fma(nz, sqrt_lean1(gru), gru) * inv_lambda;
+        else needs_exact = true;
+    }
+    return pstar;
 }
 
 // SRC: where rho* comes from -- kSrcPhilox: sampled in front 1 (fused); kSrcReplay: same with host uniforms;
@@ -369,20 +432,25 @@ riet_step_kernel(const StepArgs A)
     const int tid = threadIdx.x, nthreads = g.nthreads;
     constexpr int RW = kRW;
     constexpr int NF = DET ? 3 : 2;          // stage fields kept in shared memory: W,O[,P]
+    constexpr int kSS = NF * RW;             // stage ring: doubles per slot (row)
+    constexpr int kSG = kStSlots * kSS;      // ... per stage
+    constexpr int kPGrp = 3 * RW;            // P ring: doubles per group of three rows
+    constexpr int kWGrp = 3 * 2 * RW;        // W/O ring: doubles per group of three rows
 
     TM_DYN_SMEM(smem_raw);
-    double *in = reinterpret_cast<double *>(smem_raw);
-    double *st = in + kInSlots * 3 * RW;
-    const size_t st_doubles = (size_t)3 * kStSlots * NF * RW;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(st + st_doubles);
+    double *pr = reinterpret_cast<double *>(smem_raw);
+    double *wo = pr + kPSlots * RW;
+    double *st = wo + kWoSlots * 2 * RW;
+    constexpr int kRingDoubles = (kPSlots + 2 * kWoSlots + 3 * kStSlots * NF) * RW;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(pr + kRingDoubles);
     const double *logtab = A.logtab; // 2 KB, read through L1 (shared memory is fully booked by the rings at 4 CTAs/SM)
 
     if (tid == 0) {
-        for (int s = 0; s < kInSlots; s++) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < kWoSlots; s++) mbar_init(&mbar[s], 1);
         mbar_init_fence();
     }
     // rings start as zeros so that never-written slots are finite
-    for (int i = tid; i < kInSlots * 3 * RW + 3 * kStSlots * NF * RW; i += nthreads) in[i] = 0.0;
+    for (int i = tid; i < kRingDoubles; i += nthreads) pr[i] = 0.0;
     __syncthreads();
 
     // this CTA's share of the linearised (trial, strip, row) space
@@ -394,8 +462,14 @@ riet_step_kernel(const StepArgs A)
     const int cx = tid;                               // column within the strip, halo included
     const bool col_in_strip = cx < TXH;
 
-    long long seq = 0;   // rows consumed so far (ring slot / phase bookkeeping)
+    // ring bookkeeping, advanced every three rows: group bases of rows j..j+2 / j-3..j-1 / j-6..j-4 in the
+    // W/O ring (as group indices 0..2), of rows j..j+2 / j-3..j-1 in the P ring (0..1), and the mbarrier parity
+    int G0 = 0, G1 = 2, G2 = 1, Q0 = 0, Q1 = 1;
+    uint32_t par = 0;
     bool timeout = false;
+    const double *const prc = pr + 2 + cx;
+    const double *const woc = wo + 2 + cx;
+    double *const stc = st + 2 + cx;
 
     for (long long w = w0; w < w1;) {
         const int ts = (int)(w / g.nrows);            // trial*ns + strip
@@ -408,196 +482,196 @@ riet_step_kernel(const StepArgs A)
         const int gx = x0 - kHalo + cx;               // this thread's lattice column (may be <0 or >=L: ghost)
         int gxm = gx % g.L; if (gxm < 0) gxm += g.L;  // ... wrapped, for the Philox cell index
         const bool out_col = (cx >= kHalo) && (cx < kHalo + g.TX) && (gx < g.L);
+        const bool ghost_r = out_col && gx < kHalo, ghost_l = out_col && gx >= g.L - kHalo; // also feeds a ghost column
         const double *inP = A.in + (long long)trial * g.trial_stride;
         const double *inW = inP + g.field_stride, *inO = inW + g.field_stride;
+        const double *srcP = (SRC == kSrcPre) ? A.pstar + (long long)trial * g.field_stride : inP;
         double *outP = A.out + (long long)trial * g.trial_stride;
         const double a_rain = A.a_trial[trial];
         const int jlo = ya - kHalo, jhi = yb + kHalo - 1;
+        const int nit = (jhi - jlo + 1 + 2) / 3 * 3;  // rows marched: padded to the unroll (<= 2 dummy rows, never stored)
 
         // physical row index of lattice-local row j in [-4, nrows+4)
         auto prow = [&](int j) -> long long {
             if (g.wrap) { int r = j % g.L; if (r < 0) r += g.L; return r; }
             return j + kHalo;
         };
-        auto issue = [&](int j, long long n) { // thread 0: stream row j into input slot n % kInSlots
-            const int slot = (int)(n & (kInSlots - 1));
-            double *dst = in + (size_t)slot * 3 * RW + 2;
-            const long long off = prow(j) * g.Lp + x0;
-            mbar_expect_tx(&mbar[slot], 3 * row_bytes);
-            bulk_g2s(dst, (SRC == kSrcPre ? A.pstar + (long long)trial * g.field_stride : inP) + off, row_bytes, &mbar[slot]);
-            bulk_g2s(dst + RW, inW + off, row_bytes, &mbar[slot]);
-            bulk_g2s(dst + 2 * RW, inO + off, row_bytes, &mbar[slot]);
+        // thread 0 streams the rows; row j (clamped to jhi: the dummy rows re-read it) goes into P-ring slot
+        // `pslot` and W/O-ring slot `wslot` (= its mbarrier).  -4 <= j < nrows + 8, so the wrap needs no division.
+        auto issue = [&](int j, int pslot, int wslot) {
+            int r = (j < jhi) ? j : jhi;
+            if (g.wrap) { if (r < 0) r += g.L; else if (r >= g.L) r -= g.L; } else r += kHalo;
+            const long long off = (long long)r * g.Lp + x0;
+            mbar_expect_tx(&mbar[wslot], 3 * row_bytes);
+            bulk_g2s(pr + pslot * RW + 2, srcP + off, row_bytes, &mbar[wslot]);
+            bulk_g2s(wo + wslot * 2 * RW + 2, inW + off, row_bytes, &mbar[wslot]);
+            bulk_g2s(wo + wslot * 2 * RW + RW + 2, inO + off, row_bytes, &mbar[wslot]);
         };
-        if (tid == 0)
-            for (int k = 0; k <= kPrefetch && jlo + k <= jhi; k++) issue(jlo + k, seq + k);
+        if (tid == 0) {
+            issue(jlo, 3 * Q0 + 0, 3 * G0 + 0); issue(jlo + 1, 3 * Q0 + 1, 3 * G0 + 1); issue(jlo + 2, 3 * Q0 + 2, 3 * G0 + 2);
+            if (nit > 3) issue(jlo + 3, 3 * Q1 + 0, 3 * G2 + 0);
+        }
 
-        // global row (mod L) of front 1 and physical row of the commit front, advanced per step
+        // global row (mod L) of front 1 as the Philox cell base, and the output pointer of the commit front
         int r1 = (g.row0 + jlo - 1) % g.L; if (r1 < 0) r1 += g.L;
-        long long r4 = prow(jlo - 4);
-        double *po_row = outP + (r4 * g.Lp + (gx + kHalo));
+        uint32_t cell_row = (uint32_t)r1 * (uint32_t)g.L;
+        int r4 = (int)prow(jlo - 4);
+        double *po_row = outP + ((long long)r4 * g.Lp + (gx + kHalo));
 
         // the few values that stay in registers (own column): rho* of rows j-4..j-2, the P stage
         // values, and the running K1+2K2+2K3 sums of the rows between fronts 1 and 4
         double Ps_m4 = 0, Ps_m3 = 0, Ps_m2 = 0;
         double P1_m2 = 0, P2_m3 = 0, P3_m4 = 0;
         double aP_m4 = 0, aP_m3 = 0, aP_m2 = 0, aW_m4 = 0, aW_m3 = 0, aW_m2 = 0, aO_m4 = 0, aO_m3 = 0, aO_m2 = 0;
-        // stage-ring slot offsets (in doubles) of rows j, j-1, j-2 (mod 3), rotated per step
-        int m0 = (int)(seq % kStSlots) * NF * RW, m1 = (int)((seq + 2) % kStSlots) * NF * RW, m2 = (int)((seq + 1) % kStSlots) * NF * RW;
-        double *const stc = st + 2 + cx;
-        const double *const inc = in + 2 + cx;
-        // rows j-1 .. j-4 before the first step: the slots the ring bookkeeping assigns them (stale but finite data)
-        const double *i0 = inc + (int)((seq + kInSlots - 1) & (kInSlots - 1)) * (3 * RW);
-        const double *i1 = inc + (int)((seq + kInSlots - 2) & (kInSlots - 1)) * (3 * RW);
-        const double *i2 = inc + (int)((seq + kInSlots - 3) & (kInSlots - 1)) * (3 * RW);
-        const double *i3 = inc + (int)((seq + kInSlots - 4) & (kInSlots - 1)) * (3 * RW), *i4 = i3;
 
-        for (int j = jlo; j <= jhi; j++, seq++) {
-            const int s0 = (int)(seq & (kInSlots - 1));
-            if (!timeout && !mbar_wait(&mbar[s0], (uint32_t)((seq / kInSlots) & 1))) timeout = true;
-            // stage-0 rows j, j-1, j-2, j-3, j-4 of this column (pointers rotate with the ring)
-            i4 = i3; i3 = i2; i2 = i1; i1 = i0; i0 = inc + s0 * (3 * RW);
-            // stage rings: slot of the row a front works on, and of its vertical neighbours
-            // stage rings: row j-back lives in slot (q - back) mod 3, i.e. m0 (back 0,3), m1 (1,4), m2 (2,5)
-            auto sp = [&](int stage, int back) -> double * { // stage 1..3, row j-back
-                const int m = (back % 3 == 0) ? m0 : (back % 3 == 1) ? m1 : m2;
-                return stc + (stage - 1) * (kStSlots * NF * RW) + m;
-            };
+        for (int it = 0; it < nit; it += 3) {
+            const int pq0 = Q0 * kPGrp, pq1 = Q1 * kPGrp;
+            const int wg0 = G0 * kWGrp, wg1 = G1 * kWGrp, wg2 = G2 * kWGrp;
 
-            // ---- front 1: row j-1 : rho* and K1 -----------------------------------------------
-            const double Pc = i1[0], Pu = i2[0], Pd = i0[0], Pl = i1[-1], Pr = i1[1];
-            double pstar = Pc;
-            if (!DET && SRC != kSrcPre) {
-                const double alpha_i = c.dk.diffc * (Pu + Pd + Pl + Pr);
-                const bool live = !(alpha_i == 0 && Pc == 0) && col_in_strip; // skip rule R/:3759
-                const uint32_t cell = (uint32_t)r1 * (uint32_t)g.L + (uint32_t)gxm;
-                if (SRC == kSrcReplay) {
-                    if (live) {
-                        ReplaySrc src;
-                        src.begin(A.replay_u + ((size_t)trial * g.L * g.L + cell) * A.stride, A.stride);
-                        pstar = dornic_cell<kRietkerk>(c.dk, src, alpha_i, Pc);
-                        if (src.overflow_count() && out_col && j - 1 >= ya && j - 1 < yb)
-                            atomicAdd(&A.counters[0], (unsigned long long)src.overflow_count());
-                    }
-                } else {
-                    // Gaussian regime of R/:3773-3789 inline (Box-Muller pair of the cell's stream); everything else
-                    // (Poisson mean <= 100 or Gamma shape <= 100: the extinction fringe) out of line.
-                    const uint32_t ptrial = A.trial0 + (uint32_t)trial;
-                    const double ziggy = c.dk.ll * Pc;
-                    const double mu1 = STRICT ? (-1.0 + 2.0 * alpha_i * c.dk.sigma2_1) + 1.0  // mu + 1.0 in the reference's order
-                                              : 2.0 * alpha_i * c.dk.sigma2_1;
-                    const bool gauss_n = live && ziggy > 100;
-                    const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
-                    double n_first = 0.0, n_second = 0.0;
-                    if (fastp) gauss_pair<STRICT>(cell, ptrial, A.step, A.rk, logtab, n_first, n_second);
-                    bool exact = live && !fastp;
-                    if (fastp) {
-                        double gru = mu1, nz = n_first;
-                        if (gauss_n) {
-                            const long long gauss = (long long)fma(n_first, STRICT ? sqrt(ziggy) : sqrt_lean(ziggy), ziggy);
-                            gru = mu1 + (double)gauss;
-                            nz = n_second;
+            auto body = [&](auto U) {
+                constexpr int u = decltype(U)::value;
+                const int j = jlo + it + u;
+                if (!timeout && !mbar_wait(&mbar[3 * G0 + u], par)) timeout = true;
+                // stage-0 rows of this column: P rows j-2..j, W/O rows j-4..j (W at [0], O at [RW])
+                const double *p0 = prc + ring_off<u>(pq0, pq1, pq1, RW);
+                const double *p1 = prc + ring_off<u - 1>(pq0, pq1, pq1, RW);
+                const double *p2 = prc + ring_off<u - 2>(pq0, pq1, pq1, RW);
+                const double *q0 = woc + ring_off<u>(wg0, wg1, wg2, 2 * RW);
+                const double *q1 = woc + ring_off<u - 1>(wg0, wg1, wg2, 2 * RW);
+                const double *q2 = woc + ring_off<u - 2>(wg0, wg1, wg2, 2 * RW);
+                const double *q3 = woc + ring_off<u - 3>(wg0, wg1, wg2, 2 * RW);
+                const double *q4 = woc + ring_off<u - 4>(wg0, wg1, wg2, 2 * RW);
+                // stage rings: row j-back lives in slot (u - back) mod 3 (the segment starts on a multiple of 3)
+                auto sp = [&](int stage, int back) -> double * {
+                    return stc + (stage - 1) * kSG + (((u - back) % 3 + 3) % 3) * kSS;
+                };
+
+                // ---- front 1: row j-1 : rho* and K1 -----------------------------------------------
+                const double Pc = p1[0], Pu = p2[0], Pd = p0[0], Pl = p1[-1], Pr = p1[1];
+                double pstar = Pc;
+                if (!DET && SRC != kSrcPre) {
+                    const uint32_t cell = cell_row + (uint32_t)gxm;
+                    if (SRC == kSrcReplay) {
+                        const double alpha_i = c.dk.diffc * (Pu + Pd + Pl + Pr);
+                        if (!(alpha_i == 0 && Pc == 0) && col_in_strip) { // skip rule R/:3759
+                            ReplaySrc src;
+                            src.begin(A.replay_u + ((size_t)trial * g.L * g.L + cell) * A.stride, A.stride);
+                            pstar = dornic_cell<kRietkerk>(c.dk, src, alpha_i, Pc);
+                            if (src.overflow_count() && out_col && j - 1 >= ya && j - 1 < yb)
+                                atomicAdd(&A.counters[0], (unsigned long long)src.overflow_count());
                         }
-                        if (gru > 100) pstar = STRICT ? fma(nz, sqrt(gru), gru) / c.dk.lambda
-                                                      : fma(nz, sqrt_lean(gru), gru) * c.inv_lambda;
-                        else exact = true;
+                    } else {
+                        const double nbsum = STRICT ? Pu + Pd + Pl + Pr : (Pu + Pd) + (Pl + Pr); // STRICT: the reference's order R/:3756
+                        bool needs_exact;
+                        pstar = riet_dornic_value<STRICT>(c.dk, c.inv_lambda, c.mu_scale, Pc, nbsum, col_in_strip,
+                                                          cell, A.trial0 + (uint32_t)trial, A.step, A.rk, logtab, sincos_table(), needs_exact);
+                        if (needs_exact) // extinction fringe only (the pipeline needs the value now, so the call stays in the loop here)
+                            pstar = riet_cell_exact(c.dk, cell, A.trial0 + (uint32_t)trial, A.step, A.seed, c.dk.diffc * nbsum, Pc);
                     }
-                    if (exact) pstar = riet_cell_exact(c.dk, cell, ptrial, A.step, A.seed, alpha_i, Pc);
                 }
-            }
-            if (DORNIC_ONLY) {
-                if (out_col && j - 1 >= ya && j - 1 < yb)
-                    A.dornic_out[((size_t)trial * g.nrows + (j - 1)) * g.L + gx] = pstar;
-            } else {
-                double *s1w = sp(1, 1);
-                const double W0c = i1[RW], O0c = i1[2 * RW];
-                const F3 k1 = rhs<DET, STRICT>(c, a_rain, pstar, W0c, O0c,
-                                               i2[RW], i0[RW], i1[RW - 1], i1[RW + 1],
-                                               i2[2 * RW], i0[2 * RW], i1[2 * RW - 1], i1[2 * RW + 1],
-                                               Pu, Pd, Pl, Pr);
-                const double P1_m1 = axpy<STRICT>(c.dt2, k1.p, pstar);
-                const double W1_m1 = axpy<STRICT>(c.dt2, k1.w, W0c);
-                const double O1_m1 = axpy<STRICT>(c.dt2, k1.o, O0c);
-                s1w[0] = W1_m1; s1w[RW] = O1_m1;
-                if (DET) s1w[2 * RW] = P1_m1;
+                if (DORNIC_ONLY) {
+                    if (out_col && j - 1 >= ya && j - 1 < yb)
+                        A.dornic_out[((size_t)trial * g.nrows + (j - 1)) * g.L + gx] = pstar;
+                } else {
+                    double *s1w = sp(1, 1);
+                    const double W0c = q1[0], O0c = q1[RW];
+                    const F3 k1 = rhs<DET, STRICT>(c, a_rain, pstar, W0c, O0c,
+                                                   q2[0], q0[0], q1[-1], q1[1],
+                                                   q2[RW], q0[RW], q1[RW - 1], q1[RW + 1],
+                                                   Pu, Pd, Pl, Pr);
+                    const double P1_m1 = axpy<STRICT>(c.dt2, k1.p, pstar);
+                    const double W1_m1 = axpy<STRICT>(c.dt2, k1.w, W0c);
+                    const double O1_m1 = axpy<STRICT>(c.dt2, k1.o, O0c);
+                    s1w[0] = W1_m1; s1w[RW] = O1_m1;
+                    if (DET) s1w[2 * RW] = P1_m1;
 
-                // ---- front 2: row j-2 : K2 (stage-1 rows j-3, j-2 from the ring, j-1 just made) ---
-                const double *s1c = sp(1, 2), *s1u = sp(1, 3);
-                double *s2w = sp(2, 2);
-                const F3 k2 = rhs<DET, STRICT>(c, a_rain, P1_m2, s1c[0], s1c[RW],
-                                               s1u[0], W1_m1, s1c[-1], s1c[1],
-                                               s1u[RW], O1_m1, s1c[RW - 1], s1c[RW + 1],
-                                               DET ? s1u[2 * RW] : 0.0, P1_m1, DET ? s1c[2 * RW - 1] : 0.0, DET ? s1c[2 * RW + 1] : 0.0);
-                const double P2_m2 = axpy<STRICT>(c.dt2, k2.p, Ps_m2);
-                const double W2_m2 = axpy<STRICT>(c.dt2, k2.w, i2[RW]);
-                const double O2_m2 = axpy<STRICT>(c.dt2, k2.o, i2[2 * RW]);
-                s2w[0] = W2_m2; s2w[RW] = O2_m2;
-                if (DET) s2w[2 * RW] = P2_m2;
-                aP_m2 = axpy<STRICT>(2.0, k2.p, aP_m2); aW_m2 = axpy<STRICT>(2.0, k2.w, aW_m2); aO_m2 = axpy<STRICT>(2.0, k2.o, aO_m2);
+                    // ---- front 2: row j-2 : K2 (stage-1 rows j-3, j-2 from the ring, j-1 just made) ---
+                    const double *s1c = sp(1, 2), *s1u = sp(1, 3);
+                    double *s2w = sp(2, 2);
+                    const F3 k2 = rhs<DET, STRICT>(c, a_rain, P1_m2, s1c[0], s1c[RW],
+                                                   s1u[0], W1_m1, s1c[-1], s1c[1],
+                                                   s1u[RW], O1_m1, s1c[RW - 1], s1c[RW + 1],
+                                                   DET ? s1u[2 * RW] : 0.0, P1_m1, DET ? s1c[2 * RW - 1] : 0.0, DET ? s1c[2 * RW + 1] : 0.0);
+                    const double P2_m2 = axpy<STRICT>(c.dt2, k2.p, Ps_m2);
+                    const double W2_m2 = axpy<STRICT>(c.dt2, k2.w, q2[0]);
+                    const double O2_m2 = axpy<STRICT>(c.dt2, k2.o, q2[RW]);
+                    s2w[0] = W2_m2; s2w[RW] = O2_m2;
+                    if (DET) s2w[2 * RW] = P2_m2;
+                    aP_m2 = axpy<STRICT>(2.0, k2.p, aP_m2); aW_m2 = axpy<STRICT>(2.0, k2.w, aW_m2); aO_m2 = axpy<STRICT>(2.0, k2.o, aO_m2);
 
-                // ---- front 3: row j-3 : K3 ---------------------------------------------------------
-                const double *s2c = sp(2, 3), *s2u = sp(2, 4);
-                double *s3w = sp(3, 3);
-                const F3 k3 = rhs<DET, STRICT>(c, a_rain, P2_m3, s2c[0], s2c[RW],
-                                               s2u[0], W2_m2, s2c[-1], s2c[1],
-                                               s2u[RW], O2_m2, s2c[RW - 1], s2c[RW + 1],
-                                               DET ? s2u[2 * RW] : 0.0, P2_m2, DET ? s2c[2 * RW - 1] : 0.0, DET ? s2c[2 * RW + 1] : 0.0);
-                const double P3_m3 = axpy<STRICT>(c.dt, k3.p, Ps_m3);
-                const double W3_m3 = axpy<STRICT>(c.dt, k3.w, i3[RW]);
-                const double O3_m3 = axpy<STRICT>(c.dt, k3.o, i3[2 * RW]);
-                s3w[0] = W3_m3; s3w[RW] = O3_m3;
-                if (DET) s3w[2 * RW] = P3_m3;
-                aP_m3 = axpy<STRICT>(2.0, k3.p, aP_m3); aW_m3 = axpy<STRICT>(2.0, k3.w, aW_m3); aO_m3 = axpy<STRICT>(2.0, k3.o, aO_m3);
+                    // ---- front 3: row j-3 : K3 ---------------------------------------------------------
+                    const double *s2c = sp(2, 3), *s2u = sp(2, 4);
+                    double *s3w = sp(3, 3);
+                    const F3 k3 = rhs<DET, STRICT>(c, a_rain, P2_m3, s2c[0], s2c[RW],
+                                                   s2u[0], W2_m2, s2c[-1], s2c[1],
+                                                   s2u[RW], O2_m2, s2c[RW - 1], s2c[RW + 1],
+                                                   DET ? s2u[2 * RW] : 0.0, P2_m2, DET ? s2c[2 * RW - 1] : 0.0, DET ? s2c[2 * RW + 1] : 0.0);
+                    const double P3_m3 = axpy<STRICT>(c.dt, k3.p, Ps_m3);
+                    const double W3_m3 = axpy<STRICT>(c.dt, k3.w, q3[0]);
+                    const double O3_m3 = axpy<STRICT>(c.dt, k3.o, q3[RW]);
+                    s3w[0] = W3_m3; s3w[RW] = O3_m3;
+                    if (DET) s3w[2 * RW] = P3_m3;
+                    aP_m3 = axpy<STRICT>(2.0, k3.p, aP_m3); aW_m3 = axpy<STRICT>(2.0, k3.w, aW_m3); aO_m3 = axpy<STRICT>(2.0, k3.o, aO_m3);
 
-                // ---- front 4: row j-4 : K4, commit -------------------------------------------------
-                const double *s3c = sp(3, 4), *s3u = sp(3, 5);
-                const F3 k4 = rhs<DET, STRICT>(c, a_rain, P3_m4, s3c[0], s3c[RW],
-                                               s3u[0], W3_m3, s3c[-1], s3c[1],
-                                               s3u[RW], O3_m3, s3c[RW - 1], s3c[RW + 1],
-                                               DET ? s3u[2 * RW] : 0.0, P3_m3, DET ? s3c[2 * RW - 1] : 0.0, DET ? s3c[2 * RW + 1] : 0.0);
-                double nP = axpy<STRICT>(c.dt6, aP_m4 + k4.p, Ps_m4);
-                double nW = axpy<STRICT>(c.dt6, aW_m4 + k4.w, i4[RW]);
-                double nO = axpy<STRICT>(c.dt6, aO_m4 + k4.o, i4[2 * RW]);
-                if (!DET && fmin(nP, fmin(nW, nO)) < c.eps) { // R/:4176; almost never taken for live cells
-                    nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo);
+                    // ---- front 4: row j-4 : K4, commit -------------------------------------------------
+                    const double *s3c = sp(3, 4), *s3u = sp(3, 5);
+                    const F3 k4 = rhs<DET, STRICT>(c, a_rain, P3_m4, s3c[0], s3c[RW],
+                                                   s3u[0], W3_m3, s3c[-1], s3c[1],
+                                                   s3u[RW], O3_m3, s3c[RW - 1], s3c[RW + 1],
+                                                   DET ? s3u[2 * RW] : 0.0, P3_m3, DET ? s3c[2 * RW - 1] : 0.0, DET ? s3c[2 * RW + 1] : 0.0);
+                    double nP = axpy<STRICT>(c.dt6, aP_m4 + k4.p, Ps_m4);
+                    double nW = axpy<STRICT>(c.dt6, aW_m4 + k4.w, q4[0]);
+                    double nO = axpy<STRICT>(c.dt6, aO_m4 + k4.o, q4[RW]);
+                    if (!DET && (nP < c.eps || nW < c.eps || nO < c.eps)) { // R/:4176; almost never taken for live cells
+                        nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo);
+                    }
+                    if (out_col && j - 4 >= ya && j - 4 < yb) {
+                        double *po = po_row; // row r4, padded-layout column gx + 4
+                        po[0] = nP; po[g.field_stride] = nW; po[2 * g.field_stride] = nO;
+                        if (ghost_r) { po[g.L] = nP; po[g.field_stride + g.L] = nW; po[2 * g.field_stride + g.L] = nO; }
+                        if (ghost_l) { po[-g.L] = nP; po[g.field_stride - g.L] = nW; po[2 * g.field_stride - g.L] = nO; }
+                    }
+                    // ---- shift the register windows by one row (renamed away by the unrolling) -------------
+                    P3_m4 = P3_m3; P2_m3 = P2_m2; P1_m2 = P1_m1;
+                    aP_m4 = aP_m3; aP_m3 = aP_m2; aP_m2 = k1.p; aW_m4 = aW_m3; aW_m3 = aW_m2; aW_m2 = k1.w;
+                    aO_m4 = aO_m3; aO_m3 = aO_m2; aO_m2 = k1.o;
+                    Ps_m4 = Ps_m3; Ps_m3 = Ps_m2; Ps_m2 = pstar;
                 }
-                if (out_col && j - 4 >= ya) { // (j-4 <= yb-1 always holds: j <= jhi)
-                    double *po = po_row; // row r4, padded-layout column gx + 4
-                    po[0] = nP; po[g.field_stride] = nW; po[2 * g.field_stride] = nO;
-                    if (gx < kHalo) { po[g.L] = nP; po[g.field_stride + g.L] = nW; po[2 * g.field_stride + g.L] = nO; }
-                    if (gx >= g.L - kHalo) { po[-g.L] = nP; po[g.field_stride - g.L] = nW; po[2 * g.field_stride - g.L] = nO; }
-                }
-                // ---- shift the register windows by one row -------------------------------------------
-                P3_m4 = P3_m3; P2_m3 = P2_m2; P1_m2 = P1_m1;
-                aP_m4 = aP_m3; aP_m3 = aP_m2; aP_m2 = k1.p; aW_m4 = aW_m3; aW_m3 = aW_m2; aW_m2 = k1.w;
-                aO_m4 = aO_m3; aO_m3 = aO_m2; aO_m2 = k1.o;
-                Ps_m4 = Ps_m3; Ps_m3 = Ps_m2; Ps_m2 = pstar;
-            }
-            r1 = (r1 + 1 == g.L) ? 0 : r1 + 1;
-            { const int t = m0; m0 = m2; m2 = m1; m1 = t; }
-            if (g.wrap && r4 + 1 == g.L) { r4 = 0; po_row -= (long long)(g.L - 1) * g.Lp; } else { r4 += 1; po_row += g.Lp; }
+                if (++r1 == g.L) { r1 = 0; cell_row = 0; } else cell_row += (uint32_t)g.L;
+                if (g.wrap && r4 + 1 == g.L) { r4 = 0; po_row -= (long long)(g.L - 1) * g.Lp; } else { r4 += 1; po_row += g.Lp; }
 
-            __syncthreads();
-            if (tid == 0 && j + kPrefetch + 1 <= jhi) issue(j + kPrefetch + 1, seq + kPrefetch + 1);
+                __syncthreads();
+                // row j has been consumed by everyone: request row j+kLead into the slots of rows j-5 (W,O) and j-2 (P)
+                if (tid == 0 && it + u + kLead < nit) {
+                    if (u == 0) issue(j + kLead, 3 * Q1 + 1, 3 * G2 + 1);
+                    else if (u == 1) issue(j + kLead, 3 * Q1 + 2, 3 * G2 + 2);
+                    else issue(j + kLead, 3 * Q0 + 0, 3 * G1 + 0);
+                }
+            };
+            body(IntC<0>()); body(IntC<1>()); body(IntC<2>());
+
+            { const int t = G0; G0 = G2; G2 = G1; G1 = t; }   // next three rows go where rows j-6..j-4 were
+            { const int t = Q0; Q0 = Q1; Q1 = t; }
+            if (G0 == 0) par ^= 1u;
         }
-
     }
     if (timeout && tid == 0) atomicAdd(&A.counters[1], 1ull);
 }
 
 // ------------------------------------------------------------------------------------------
-// Rietkerk vegetation Dornic sweep as its own kernel (the split alternative, tm_set_fused(ctx, 0))
+// Rietkerk vegetation Dornic sweep as its own kernel (the default pairing: this sweep, then the RK4 fronts
+// of riet_step_kernel<.., kSrcPre, ..>; tm_set_fused(ctx, 1) selects the single fused kernel instead)
 // ------------------------------------------------------------------------------------------
-// One thread per column, marching down a run of rows: the vertical neighbours roll through registers,
-// the horizontal ones come from the neighbouring lanes by shuffle (only the two edge lanes of a warp
-// load theirs), so a cell costs one global load and one store.  No pipeline state beyond that: 64
-// registers, 32 warps per SM, and the long serial chain (Philox -> log -> sqrt -> sincos -> trunc -> sqrt)
-// of one warp hides behind seven others.  Writes rho* in the padded layout (ghost columns included) for
-// riet_step_kernel<.., kSrcPre, ..>.  Costs one extra field write + read per site (64 instead of 48 B)
-// on a kernel pair that sits far below the HBM roofline.
+// One thread per column, marching down a run of rows: the centre and upper neighbour roll through registers,
+// the row below and the two horizontal neighbours are plain coalesced loads (L1 hits after the first touch of
+// a line), so a cell costs one HBM read and one HBM write.  No pipeline state beyond that: 64 registers,
+// 32 warps per SM, and the long serial chain (Philox -> log -> sqrt -> sincos -> trunc -> sqrt) of one warp
+// hides behind seven others.  Writes rho* in the padded layout (ghost columns included).  The pair moves 64 B per
+// site-update instead of the fused kernel's 48 B, on kernels that are bound by FP64/issue slots, not by HBM.
 struct DornicArgs {
     Geom g;
     DornicConsts dk;
-    double inv_lambda;
+    double inv_lambda, mu_scale;   // FAST arithmetic: 1/lambda, 2 (D0/dx^2)/sigma0^2
     const double *in;              // state buffer (field 0 = P is read)
     double *pstar;                 // [n_trials][rows_alloc][Lp]
     unsigned long long seed;
@@ -608,22 +682,29 @@ struct DornicArgs {
     const double *logtab;          // device copy of the FAST-mode log table [128][2]
 };
 
+#ifndef TM_DORNIC_MINBLOCKS
+#define TM_DORNIC_MINBLOCKS 4
+#endif
 constexpr int kDornicThreads = 256;
+constexpr uint64_t kExactMarker = 0x7FF8C0DEC0DE0001ull; // a NaN no computation produces: 'redo this cell exactly'
+TM_HD size_t riet_dornic_smem_bytes() { return sizeof(double) * 512; } // log table + sin/cos table
 
 template <bool STRICT>
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(kDornicThreads, 4)
+__global__ void __launch_bounds__(kDornicThreads, TM_DORNIC_MINBLOCKS)
 #else
 void
 #endif
 riet_dornic_kernel(const DornicArgs A)
 {
     const Geom &g = A.g;
-    const DornicConsts &dk = A.dk;
     const int tid = threadIdx.x;
     TM_DYN_SMEM(smem_raw);
     double *logtab = reinterpret_cast<double *>(smem_raw); // [128][2]
-    if (!STRICT) { logtab[tid] = A.logtab[tid]; __syncthreads(); }
+    double *sctab = logtab + 256;                          // [128][2]
+    if (!STRICT) logtab[tid] = A.logtab[tid];
+    sctab[tid] = sincos_table()[tid];
+    __syncthreads();
     // work item = (trial, column block of 256, run of rows_per_cta rows)
     const int ncb = (g.L + kDornicThreads - 1) / kDornicThreads;
     const int nrow = A.row_hi - A.row_lo;
@@ -638,61 +719,56 @@ riet_dornic_kernel(const DornicArgs A)
         const int q = cb * kDornicThreads + tid;
         const bool valid = q < g.L;
         const int qc = valid ? q : g.L - 1;          // clamped: idle lanes read a legal address
-#if defined(__CUDA_ARCH__)
-        const int lane = tid & 31;
-#endif
+        const bool ghost_r = valid && q < kHalo, ghost_l = valid && q >= g.L - kHalo;
         const uint32_t ptrial = A.trial0 + (uint32_t)trial;
-        const double *P = A.in + (long long)trial * g.trial_stride + kHalo + qc;   // column qc of physical row 0
-        double *O = A.pstar + (long long)trial * g.field_stride + kHalo + qc;
-        auto prow = [&](int r) -> long long { // physical row of lattice-local row r in [-4, nrows+4)
+        // physical row of lattice-local row r in [-4, nrows+4): whole lattices wrap, slabs carry ghost rows
+        auto prow = [&](int r) -> int {
             if (g.wrap) { if (r < 0) r += g.L; if (r >= g.L) r -= g.L; return r; }
             return r + kHalo;
         };
-        double Pu = P[prow(ra - 1) * g.Lp], Pc = P[prow(ra) * g.Lp];
+        int pr = prow(ra);
+        const long long col = (long long)kHalo + qc;
+        const double *pin = A.in + (long long)trial * g.trial_stride + (long long)pr * g.Lp + col;   // (row, column qc) of P
+        double *pout = A.pstar + (long long)trial * g.field_stride + (long long)pr * g.Lp + col;
+        double Pu = pin[(long long)(prow(ra - 1) - pr) * g.Lp], Pc = pin[0];
         int grow = g.row0 + ra; if (grow < 0) grow += g.L; if (grow >= g.L) grow -= g.L;
+        uint32_t cell = (uint32_t)grow * (uint32_t)g.L + (uint32_t)qc;
+        int n_exact = 0;
         for (int row = ra; row < rb; row++) {
-            const long long pr = prow(row);
-            const double Pd = P[prow(row + 1) * g.Lp];
-            double Pl, Pr;
-#if defined(__CUDA_ARCH__)
-            Pl = __shfl_up_sync(0xffffffffu, Pc, 1);
-            Pr = __shfl_down_sync(0xffffffffu, Pc, 1);
-            if (lane == 0) Pl = P[pr * g.Lp - 1];      // ghost column covers q = 0
-            if (lane == 31 || q == g.L - 1) Pr = P[pr * g.Lp + 1];
-#else
-            Pl = P[pr * g.Lp - 1]; Pr = P[pr * g.Lp + 1];
-#endif
-            // ---- identical to front 1 of the fused kernel -------------------------------------------------
-            double pstar = Pc;
-            const double alpha_i = dk.diffc * (Pu + Pd + Pl + Pr);
-            const bool live = !(alpha_i == 0 && Pc == 0) && valid;            // skip rule R/:3759
-            const uint32_t cell = (uint32_t)grow * (uint32_t)g.L + (uint32_t)qc;
-            const double ziggy = dk.ll * Pc;
-            const double mu1 = STRICT ? (-1.0 + 2.0 * alpha_i * dk.sigma2_1) + 1.0 : 2.0 * alpha_i * dk.sigma2_1;
-            const bool gauss_n = live && ziggy > 100;
-            const bool fastp = gauss_n || (live && ziggy == 0.0 && mu1 > 100);
-            double n_first = 0.0, n_second = 0.0;
-            if (fastp) gauss_pair<STRICT>(cell, ptrial, A.step, A.rk, logtab, n_first, n_second);
-            bool exact = live && !fastp;
-            if (fastp) {
-                double gru = mu1, nz = n_first;
-                if (gauss_n) {
-                    const long long gauss = (long long)fma(n_first, STRICT ? sqrt(ziggy) : sqrt_lean(ziggy), ziggy);
-                    gru = mu1 + (double)gauss;
-                    nz = n_second;
-                }
-                if (gru > 100) pstar = STRICT ? fma(nz, sqrt(gru), gru) / dk.lambda : fma(nz, sqrt_lean(gru), gru) * A.inv_lambda;
-                else exact = true;
-            }
-            if (exact) pstar = riet_cell_exact(dk, cell, ptrial, A.step, A.seed, alpha_i, Pc);
+            const bool last = g.wrap && pr + 1 == g.L;                      // the row below wraps to physical row 0
+            const long long dn = last ? -(long long)(g.L - 1) * g.Lp : (long long)g.Lp;
+            const double Pd = pin[dn], Pl = pin[-1], Pr = pin[1];           // ghost columns cover q = 0 and q = L-1
+            bool needs_exact;
+            const double nbsum = STRICT ? Pu + Pd + Pl + Pr : (Pu + Pd) + (Pl + Pr);    // STRICT: the reference's order R/:3756
+            double pstar = riet_dornic_value<STRICT>(A.dk, A.inv_lambda, A.mu_scale, Pc, nbsum, valid,
+                                                     cell, ptrial, A.step, A.rk, logtab, sctab, needs_exact);
+            if (needs_exact) { pstar = u2d(kExactMarker); n_exact++; }    // resolved by the second walk below
             if (valid) {
-                double *o = O + pr * g.Lp;
-                o[0] = pstar;
-                if (q < kHalo) o[g.L] = pstar;
-                if (q >= g.L - kHalo) o[-g.L] = pstar;
+                pout[0] = pstar;
+                if (ghost_r) pout[g.L] = pstar;
+                if (ghost_l) pout[-g.L] = pstar;
             }
             Pu = Pc; Pc = Pd;
-            grow = (grow + 1 == g.L) ? 0 : grow + 1;
+            pin += dn; pout += dn;
+            pr = last ? 0 : pr + 1;
+            if (++grow == g.L) { grow = 0; cell = (uint32_t)qc; } else cell += (uint32_t)g.L;
+        }
+        // second walk, extinction fringe only: the cells of this thread's run that need the exact Poisson / Gamma
+        // samplers (marked above) are redone from their counters, out of the hot loop
+        if (n_exact > 0) {
+            for (int row = ra; row < rb; row++) {
+                const int p = prow(row);
+                double *o = A.pstar + (long long)trial * g.field_stride + (long long)p * g.Lp + col;
+                if (d2u(o[0]) != kExactMarker) continue;
+                const double *ic = A.in + (long long)trial * g.trial_stride + (long long)p * g.Lp + col;
+                const double up = ic[(long long)(prow(row - 1) - p) * g.Lp], dn = ic[(long long)(prow(row + 1) - p) * g.Lp];
+                int gr = g.row0 + row; if (gr < 0) gr += g.L; if (gr >= g.L) gr -= g.L;
+                const double alpha_i = A.dk.diffc * (STRICT ? up + dn + ic[-1] + ic[1] : (up + dn) + (ic[-1] + ic[1])); // as in the first walk
+                const double v = riet_cell_exact(A.dk, (uint32_t)gr * (uint32_t)g.L + (uint32_t)qc, ptrial, A.step, A.seed, alpha_i, ic[0]);
+                o[0] = v;
+                if (ghost_r) o[g.L] = v;
+                if (ghost_l) o[-g.L] = v;
+            }
         }
     }
 }

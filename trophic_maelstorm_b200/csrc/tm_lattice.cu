@@ -39,7 +39,7 @@ struct tm_ctx {
     double *dornic_dev = nullptr;
     double *logtab_dev = nullptr;  // FAST-mode log table
     double *pstar_dev = nullptr;   // rho* scratch field of the split Dornic / RK4 kernel pair
-    bool fused = true;             // false: Dornic sweep + RK4 kernel pair instead of the fused kernel
+    bool fused = false;            // default: Dornic sweep + RK4 kernel pair; true: the single fused kernel
     double *halo_dev[2] = {nullptr, nullptr};
     uint64_t seed = 0, step = 0;
     uint32_t trial0 = 0;
@@ -345,7 +345,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
                 TM_CUDA(c, cudaMemsetAsync(c->pstar_dev, 0, nb, c->stream));
             }
             DornicArgs D{};
-            D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.in = A.in; D.pstar = c->pstar_dev;
+            D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.mu_scale = A.c.mu_scale; D.in = A.in; D.pstar = c->pstar_dev;
             D.seed = c->seed; D.trial0 = c->trial0; D.step = (unsigned int)c->step; D.rk = A.rk; D.logtab = c->logtab_dev;
             D.row_lo = g.wrap ? 0 : -(kHalo - 1); D.row_hi = g.wrap ? g.nrows : g.nrows + (kHalo - 1);
             // rows per CTA: enough (trial, column block, run) items for ~2 rounds over 4 resident CTAs per SM
@@ -358,7 +358,7 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             const long long ditems = (long long)g.n_trials * ncb * ((nrow_d + rpc - 1) / rpc);
             long long dgrid = ditems;
             if (dgrid > (long long)c->n_sm * 64) dgrid = (long long)c->n_sm * 64;
-            const size_t dsmem = sizeof(uint32_t) * 32 * (kDornicThreads / 32) + sizeof(double) * 256;
+            const size_t dsmem = riet_dornic_smem_bytes();
             if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
             else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
             TM_CUDA(c, cudaGetLastError());

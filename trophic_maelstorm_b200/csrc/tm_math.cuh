@@ -137,37 +137,47 @@ TM_HD double lgamma_int(double k)
     return (fma(k - 0.5, log_pos(k), -k) + HALF_LOG_2PI) + ser;
 }
 
-// sin and cos of (pi/2) a for a in [0,4] -- the angle of the Box-Muller pair (Philox mode, tm_samplers.cuh).
-// q = a rounded to the nearest integer (ties to even, by the 1.5*2^52 addition), g = a - q in [-1/2,1/2]
-// (exact); Taylor series of sin/cos((pi/2) g) in g^2 (truncation < 5e-17), then the quadrant q mod 4
-// swaps / negates.  Pure +,-,*,fma and bit operations: the same bits on every machine.
-TM_HD void sincos_quadrants(double a, double &sn, double &cs)
+// {sin, cos}(2 pi i/128), the grid of the Box-Muller angle (Philox mode, tm_samplers.cuh).  The kernels that
+// sample in their inner loop stage the table in shared memory; everything else reads this copy.
+#if defined(__CUDACC__)
+__device__ const double kSinCosTabDev[256] = {
+#include "tm_sincos_table.inc"
+};
+#endif
+static const double kSinCosTabHost[256] = {
+#include "tm_sincos_table.inc"
+};
+TM_HD const double *sincos_table()
+{
+#if defined(__CUDA_ARCH__)
+    return kSinCosTabDev;
+#else
+    return kSinCosTabHost;
+#endif
+}
+
+// sin and cos of 2 pi a/128 for a in [0,128]: i = a rounded to the nearest integer (ties to even, by the
+// 1.5*2^52 addition), g = a - i in [-1/2,1/2] (exact), b = (pi/64) g; sin b and cos b - 1 from their Taylor
+// series in g^2 (truncation < 4e-18; the three coefficients whose terms stay below 1e-10 carry 21 significant
+// bits so that they encode as immediates), then the angle addition with the table entry i mod 128.
+// Pure +,-,*,fma and bit operations: the same bits on every machine.
+TM_HD void sincos_turn128(double a, const double *tab, double &sn, double &cs)
 {
     const double magic = 6755399441055744.0; // 1.5 * 2^52
     const double m = a + magic;
-    const uint32_t q = (uint32_t)d2u(m);
+    const uint32_t i = (uint32_t)d2u(m) & 127u;
     const double g = a - (m - magic);
     const double z = g * g;
-    double s = fma(z, -0x1.6fadb9f155744p-31, 0x1.e8f434d018d63p-25);
-    s = fma(z, s, -0x1.e3074fde8871fp-19);
-    s = fma(z, s, 0x1.50783487ee782p-13);
-    s = fma(z, s, -0x1.32d2cce62bd86p-8);
-    s = fma(z, s, 0x1.466bc6775aae2p-4);
-    s = fma(z, s, -0x1.4abbce625be53p-1);
-    s = fma(z, s, 0x1.921fb54442d18p+0);
-    s = g * s;
-    double c = fma(z, 0x1.20c62c2f2d7f5p-34, -0x1.b6e24f44b128fp-28);
-    c = fma(z, c, 0x1.f9d38a3763cc3p-22);
-    c = fma(z, c, -0x1.a6d1f2a204a8cp-16);
-    c = fma(z, c, 0x1.e1f506891babbp-11);
-    c = fma(z, c, -0x1.55d3c7e3cbffap-6);
-    c = fma(z, c, 0x1.03c1f081b5ac4p-2);
-    c = fma(z, c, -0x1.3bd3cc9be45dep+0);
-    c = fma(z, c, 1.0);
-    const bool swap = (q & 1u) != 0;
-    const double so = swap ? c : s, co = swap ? s : c;
-    sn = u2d(d2u(so) ^ ((uint64_t)(q & 2u) << 62));          // quadrants 2,3: sin < 0
-    cs = u2d(d2u(co) ^ ((uint64_t)((q + 1u) & 2u) << 62));   // quadrants 1,2: cos < 0
+    double sb = fma(z, -0x1.32d2d00000000p-43, 0x1.466bc00000000p-29);
+    sb = fma(z, sb, -0x1.4abbce625be53p-16);
+    sb = fma(z, sb, 0x1.921fb54442d18p-5);
+    sb = g * sb;                                              // sin b
+    double cb = fma(z, -0x1.55d3c00000000p-36, 0x1.03c1f081b5ac4p-22);
+    cb = fma(z, cb, -0x1.3bd3cc9be45dep-10);
+    cb = z * cb;                                              // cos b - 1
+    const double si = tab[2 * i], ci = tab[2 * i + 1];
+    sn = fma(si, cb, fma(ci, sb, si));
+    cs = fma(ci, cb, fma(-si, sb, ci));
 }
 
 // Philox4x32-10, counter (c0..c3), key (k0,k1).

@@ -74,7 +74,7 @@ TM_HD double normal01(Src &s, NormalState &st)
         const double x = 2.0 - u2d(d2u(1.0 + u0) | 1ull);
         const double r = sqrt(-2.0 * log_pos(x));
         double sn, cs;
-        sincos_quadrants(4.0 * u1, sn, cs);
+        sincos_turn128(128.0 * u1, sincos_table(), sn, cs);
         st.saved = r * sn;
         st.have = true;
         return r * cs;
