@@ -49,6 +49,7 @@ static inline RietConsts riet_consts(const tm_params &p)
     c.dk = dornic_consts(p, p.a);
     c.inv_lambda = 1.0 / c.dk.lambda;
     c.mu_scale = 2.0 * c.dk.diffc * c.dk.sigma2_1;
+    c.dt2cg = c.dt2 * c.cgmax; c.dtcg = c.dt * c.cgmax; c.dt6cg = c.dt6 * c.cgmax;
     c.aK2W0 = c.alpha * c.K2W0; c.cP = -(c.d + 4 * c.Dp); c.cW = -(c.rW + 4 * c.Dw); c.cO = -4 * c.Do;
     return c;
 }

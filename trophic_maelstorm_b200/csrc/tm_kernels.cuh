@@ -61,6 +61,7 @@ struct RietConsts {
     double eps, lo;      // clamp
     double inv_lambda;   // 1/dk.lambda (FAST arithmetic only)
     double mu_scale;     // 2 (D0/dx^2) / sigma0^2 (FAST arithmetic only)
+    double dt2cg, dtcg, dt6cg; // FAST, Dornic path: dt/2, dt, dt/6 times c*gmax (f_P = c gmax q is carried as q)
     double aK2W0, cP, cW, cO; // FAST: alpha*K2*W0, -(d+4Dp), -(rW+4Dw), -4Do
     DornicConsts dk;
 };
@@ -217,6 +218,7 @@ TM_D double log_lean(double x, const double *tab /* [128][2] = {invc, logc} */)
 // Reaction terms
 // ------------------------------------------------------------------------------------------
 struct F3 { double p, w, o; };
+struct alignas(16) WO { double w, o; };   // one column of a stage row: read and written as one 128-bit access
 
 // f_2Dor R/:2376-2382 (DET=false) / f_2D R/:1730-1737 (DET=true); STRICT keeps the reference's
 // operation order so results are bit-identical to the oracle; the fast form shares one reciprocal.
@@ -240,8 +242,8 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
         const double r = rcp_lean1(wk * pk);
         const double q = (W * P) * (pk * r);                 // W P / (W + K1)
         const double infil = fma(c.alpha, P, c.aK2W0) * (wk * r) * O;
-        f.p = c.cgmax * q;
-        if (DET) f.p = fma(c.Dp, (Pu + Pd) + (Pl + Pr), fma(c.cP, P, f.p));     // cP = -(d + 4 Dp)
+        if (DET) f.p = fma(c.Dp, (Pu + Pd) + (Pl + Pr), fma(c.cP, P, c.cgmax * q));     // cP = -(d + 4 Dp)
+        else     f.p = q;      // f_P / (c gmax): the factor is folded into the step constants dt2cg, dtcg, dt6cg
         f.w = fma(c.Dw, (Wu + Wd) + (Wl + Wr), fma(c.cW, W, fma(-c.gmax, q, infil))); // cW = -(rW + 4 Dw)
         f.o = fma(c.Do, (Ou + Od) + (Ol + Or_), fma(c.cO, O, a - infil));             // cO = -4 Do
     }
@@ -250,6 +252,8 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
 
 template <bool STRICT>
 TM_D double axpy(double a, double x, double y) { return STRICT ? (y + a * x) : fma(a, x, y); }
+
+TM_D int hi32(double v) { return (int)(d2u(v) >> 32); }
 
 // `if (v < eps && v >= lo) v = 0` (R/:4176): the first test almost never holds in live cells, so the
 // second is only evaluated behind it.
@@ -308,7 +312,8 @@ TM_D void flush_stats(const ThreadStats &ts, int n_fields, int trial, PartialSta
 // the element of thread cx sits at [cx + 2] of a row:
 //   pr   [kPSlots][RW]           TMA destination, P rows j-2 .. j+3 (stage-0 P = the Dornic input)
 //   wo   [kWoSlots][2][RW]       TMA destination, W and O rows j-4 .. j+4
-//   st   [3][kStSlots][NF][RW]   stage-1/2/3 states (W,O[,P]) of the last kStSlots rows of each front
+//   st   [3][kStSlots][NF][RW]   stage-1/2/3 states of the last kStSlots rows of each front: a row is [RW] x {W,O}
+//                                interleaved (one 128-bit access per column), then [RW] x P when DET
 //   mbar uint64[kWoSlots]        one per streamed row (its three bulk copies)
 // The marching loop is unrolled by three rows, so a ring slot is (group base that rotates every three
 // rows) + (compile-time offset): kPSlots, kWoSlots and kStSlots are multiples of three.
@@ -461,6 +466,9 @@ riet_step_kernel(const StepArgs A)
     const uint32_t row_bytes = (uint32_t)(((TXH + 1) & ~1) * sizeof(double));
     const int cx = tid;                               // column within the strip, halo included
     const bool col_in_strip = cx < TXH;
+    const int eps_hi = hi32(c.eps);
+    // step sizes of the P equation: in FAST Dornic mode rhs() returns f_P without its constant factor c*gmax
+    const double hP2 = (STRICT || DET) ? c.dt2 : c.dt2cg, hP1 = (STRICT || DET) ? c.dt : c.dtcg, hP6 = (STRICT || DET) ? c.dt6 : c.dt6cg;
 
     // ring bookkeeping, advanced every three rows: group bases of rows j..j+2 / j-3..j-1 / j-6..j-4 in the
     // W/O ring (as group indices 0..2), of rows j..j+2 / j-3..j-1 in the P ring (0..1), and the mbarrier parity
@@ -469,7 +477,6 @@ riet_step_kernel(const StepArgs A)
     bool timeout = false;
     const double *const prc = pr + 2 + cx;
     const double *const woc = wo + 2 + cx;
-    double *const stc = st + 2 + cx;
 
     for (long long w = w0; w < w1;) {
         const int ts = (int)(w / g.nrows);            // trial*ns + strip
@@ -496,9 +503,10 @@ riet_step_kernel(const StepArgs A)
             if (g.wrap) { int r = j % g.L; if (r < 0) r += g.L; return r; }
             return j + kHalo;
         };
-        // thread 0 streams the rows; row j (clamped to jhi: the dummy rows re-read it) goes into P-ring slot
+        // Row streaming by thread 0: lattice-local row j (clamped to jhi: the dummy rows re-read it) goes into P-ring slot
         // `pslot` and W/O-ring slot `wslot` (= its mbarrier).  -4 <= j < nrows + 8, so the wrap needs no division.
         auto issue = [&](int j, int pslot, int wslot) {
+            if (tid != 0) return;
             int r = (j < jhi) ? j : jhi;
             if (g.wrap) { if (r < 0) r += g.L; else if (r >= g.L) r -= g.L; } else r += kHalo;
             const long long off = (long long)r * g.Lp + x0;
@@ -507,10 +515,8 @@ riet_step_kernel(const StepArgs A)
             bulk_g2s(wo + wslot * 2 * RW + 2, inW + off, row_bytes, &mbar[wslot]);
             bulk_g2s(wo + wslot * 2 * RW + RW + 2, inO + off, row_bytes, &mbar[wslot]);
         };
-        if (tid == 0) {
-            issue(jlo, 3 * Q0 + 0, 3 * G0 + 0); issue(jlo + 1, 3 * Q0 + 1, 3 * G0 + 1); issue(jlo + 2, 3 * Q0 + 2, 3 * G0 + 2);
-            if (nit > 3) issue(jlo + 3, 3 * Q1 + 0, 3 * G2 + 0);
-        }
+        issue(jlo, 3 * Q0 + 0, 3 * G0 + 0); issue(jlo + 1, 3 * Q0 + 1, 3 * G0 + 1); issue(jlo + 2, 3 * Q0 + 2, 3 * G0 + 2);
+        if (nit > 3) issue(jlo + 3, 3 * Q1 + 0, 3 * G2 + 0);
 
         // global row (mod L) of front 1 as the Philox cell base, and the output pointer of the commit front
         int r1 = (g.row0 + jlo - 1) % g.L; if (r1 < 0) r1 += g.L;
@@ -542,8 +548,11 @@ riet_step_kernel(const StepArgs A)
                 const double *q3 = woc + ring_off<u - 3>(wg0, wg1, wg2, 2 * RW);
                 const double *q4 = woc + ring_off<u - 4>(wg0, wg1, wg2, 2 * RW);
                 // stage rings: row j-back lives in slot (u - back) mod 3 (the segment starts on a multiple of 3)
-                auto sp = [&](int stage, int back) -> double * {
-                    return stc + (stage - 1) * kSG + (((u - back) % 3 + 3) % 3) * kSS;
+                auto sp = [&](int stage, int back) -> WO * {       // {W,O} of this column
+                    return reinterpret_cast<WO *>(st + (stage - 1) * kSG + (((u - back) % 3 + 3) % 3) * kSS) + 1 + cx;
+                };
+                auto spP = [&](int stage, int back) -> double * {  // P of this column (DET only)
+                    return st + (stage - 1) * kSG + (((u - back) % 3 + 3) % 3) * kSS + 2 * RW + 2 + cx;
                 };
 
                 // ---- front 1: row j-1 : rho* and K1 -----------------------------------------------
@@ -573,56 +582,58 @@ riet_step_kernel(const StepArgs A)
                     if (out_col && j - 1 >= ya && j - 1 < yb)
                         A.dornic_out[((size_t)trial * g.nrows + (j - 1)) * g.L + gx] = pstar;
                 } else {
-                    double *s1w = sp(1, 1);
                     const double W0c = q1[0], O0c = q1[RW];
                     const F3 k1 = rhs<DET, STRICT>(c, a_rain, pstar, W0c, O0c,
                                                    q2[0], q0[0], q1[-1], q1[1],
                                                    q2[RW], q0[RW], q1[RW - 1], q1[RW + 1],
                                                    Pu, Pd, Pl, Pr);
-                    const double P1_m1 = axpy<STRICT>(c.dt2, k1.p, pstar);
+                    const double P1_m1 = axpy<STRICT>(hP2, k1.p, pstar);
                     const double W1_m1 = axpy<STRICT>(c.dt2, k1.w, W0c);
                     const double O1_m1 = axpy<STRICT>(c.dt2, k1.o, O0c);
-                    s1w[0] = W1_m1; s1w[RW] = O1_m1;
-                    if (DET) s1w[2 * RW] = P1_m1;
+                    *sp(1, 1) = WO{W1_m1, O1_m1};
+                    if (DET) *spP(1, 1) = P1_m1;
 
                     // ---- front 2: row j-2 : K2 (stage-1 rows j-3, j-2 from the ring, j-1 just made) ---
-                    const double *s1c = sp(1, 2), *s1u = sp(1, 3);
-                    double *s2w = sp(2, 2);
-                    const F3 k2 = rhs<DET, STRICT>(c, a_rain, P1_m2, s1c[0], s1c[RW],
-                                                   s1u[0], W1_m1, s1c[-1], s1c[1],
-                                                   s1u[RW], O1_m1, s1c[RW - 1], s1c[RW + 1],
-                                                   DET ? s1u[2 * RW] : 0.0, P1_m1, DET ? s1c[2 * RW - 1] : 0.0, DET ? s1c[2 * RW + 1] : 0.0);
-                    const double P2_m2 = axpy<STRICT>(c.dt2, k2.p, Ps_m2);
+                    const WO *s1 = sp(1, 2);
+                    const WO s1c = s1[0], s1l = s1[-1], s1r = s1[1], s1u = *sp(1, 3);
+                    const F3 k2 = rhs<DET, STRICT>(c, a_rain, P1_m2, s1c.w, s1c.o,
+                                                   s1u.w, W1_m1, s1l.w, s1r.w,
+                                                   s1u.o, O1_m1, s1l.o, s1r.o,
+                                                   DET ? *spP(1, 3) : 0.0, P1_m1, DET ? spP(1, 2)[-1] : 0.0, DET ? spP(1, 2)[1] : 0.0);
+                    const double P2_m2 = axpy<STRICT>(hP2, k2.p, Ps_m2);
                     const double W2_m2 = axpy<STRICT>(c.dt2, k2.w, q2[0]);
                     const double O2_m2 = axpy<STRICT>(c.dt2, k2.o, q2[RW]);
-                    s2w[0] = W2_m2; s2w[RW] = O2_m2;
-                    if (DET) s2w[2 * RW] = P2_m2;
+                    *sp(2, 2) = WO{W2_m2, O2_m2};
+                    if (DET) *spP(2, 2) = P2_m2;
                     aP_m2 = axpy<STRICT>(2.0, k2.p, aP_m2); aW_m2 = axpy<STRICT>(2.0, k2.w, aW_m2); aO_m2 = axpy<STRICT>(2.0, k2.o, aO_m2);
 
                     // ---- front 3: row j-3 : K3 ---------------------------------------------------------
-                    const double *s2c = sp(2, 3), *s2u = sp(2, 4);
-                    double *s3w = sp(3, 3);
-                    const F3 k3 = rhs<DET, STRICT>(c, a_rain, P2_m3, s2c[0], s2c[RW],
-                                                   s2u[0], W2_m2, s2c[-1], s2c[1],
-                                                   s2u[RW], O2_m2, s2c[RW - 1], s2c[RW + 1],
-                                                   DET ? s2u[2 * RW] : 0.0, P2_m2, DET ? s2c[2 * RW - 1] : 0.0, DET ? s2c[2 * RW + 1] : 0.0);
-                    const double P3_m3 = axpy<STRICT>(c.dt, k3.p, Ps_m3);
+                    const WO *s2 = sp(2, 3);
+                    const WO s2c = s2[0], s2l = s2[-1], s2r = s2[1], s2u = *sp(2, 4);
+                    const F3 k3 = rhs<DET, STRICT>(c, a_rain, P2_m3, s2c.w, s2c.o,
+                                                   s2u.w, W2_m2, s2l.w, s2r.w,
+                                                   s2u.o, O2_m2, s2l.o, s2r.o,
+                                                   DET ? *spP(2, 4) : 0.0, P2_m2, DET ? spP(2, 3)[-1] : 0.0, DET ? spP(2, 3)[1] : 0.0);
+                    const double P3_m3 = axpy<STRICT>(hP1, k3.p, Ps_m3);
                     const double W3_m3 = axpy<STRICT>(c.dt, k3.w, q3[0]);
                     const double O3_m3 = axpy<STRICT>(c.dt, k3.o, q3[RW]);
-                    s3w[0] = W3_m3; s3w[RW] = O3_m3;
-                    if (DET) s3w[2 * RW] = P3_m3;
+                    *sp(3, 3) = WO{W3_m3, O3_m3};
+                    if (DET) *spP(3, 3) = P3_m3;
                     aP_m3 = axpy<STRICT>(2.0, k3.p, aP_m3); aW_m3 = axpy<STRICT>(2.0, k3.w, aW_m3); aO_m3 = axpy<STRICT>(2.0, k3.o, aO_m3);
 
                     // ---- front 4: row j-4 : K4, commit -------------------------------------------------
-                    const double *s3c = sp(3, 4), *s3u = sp(3, 5);
-                    const F3 k4 = rhs<DET, STRICT>(c, a_rain, P3_m4, s3c[0], s3c[RW],
-                                                   s3u[0], W3_m3, s3c[-1], s3c[1],
-                                                   s3u[RW], O3_m3, s3c[RW - 1], s3c[RW + 1],
-                                                   DET ? s3u[2 * RW] : 0.0, P3_m3, DET ? s3c[2 * RW - 1] : 0.0, DET ? s3c[2 * RW + 1] : 0.0);
-                    double nP = axpy<STRICT>(c.dt6, aP_m4 + k4.p, Ps_m4);
+                    const WO *s3 = sp(3, 4);
+                    const WO s3c = s3[0], s3l = s3[-1], s3r = s3[1], s3u = *sp(3, 5);
+                    const F3 k4 = rhs<DET, STRICT>(c, a_rain, P3_m4, s3c.w, s3c.o,
+                                                   s3u.w, W3_m3, s3l.w, s3r.w,
+                                                   s3u.o, O3_m3, s3l.o, s3r.o,
+                                                   DET ? *spP(3, 5) : 0.0, P3_m3, DET ? spP(3, 4)[-1] : 0.0, DET ? spP(3, 4)[1] : 0.0);
+                    double nP = axpy<STRICT>(hP6, aP_m4 + k4.p, Ps_m4);
                     double nW = axpy<STRICT>(c.dt6, aW_m4 + k4.w, q4[0]);
                     double nO = axpy<STRICT>(c.dt6, aO_m4 + k4.o, q4[RW]);
-                    if (!DET && (nP < c.eps || nW < c.eps || nO < c.eps)) { // R/:4176; almost never taken for live cells
+                    // R/:4176 `if (v < eps && v >= lo) v = 0`, almost never taken for live cells: pre-tested on the high words
+                    // (integer compares; v < eps implies hi(v) <= hi(eps), and a set sign bit compares below)
+                    if (!DET && (hi32(nP) <= eps_hi || hi32(nW) <= eps_hi || hi32(nO) <= eps_hi)) {
                         nP = clamp_small(nP, c.eps, c.lo); nW = clamp_small(nW, c.eps, c.lo); nO = clamp_small(nO, c.eps, c.lo);
                     }
                     if (out_col && j - 4 >= ya && j - 4 < yb) {
@@ -642,7 +653,7 @@ riet_step_kernel(const StepArgs A)
 
                 __syncthreads();
                 // row j has been consumed by everyone: request row j+kLead into the slots of rows j-5 (W,O) and j-2 (P)
-                if (tid == 0 && it + u + kLead < nit) {
+                if (it + u + kLead < nit) {
                     if (u == 0) issue(j + kLead, 3 * Q1 + 1, 3 * G2 + 1);
                     else if (u == 1) issue(j + kLead, 3 * Q1 + 2, 3 * G2 + 2);
                     else issue(j + kLead, 3 * Q0 + 0, 3 * G1 + 0);
