@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py -- lattice site-updates/s of the fused Rietkerk Dornic+RK4 step (BASELINE.json metric).
+"""bench.py -- lattice site-updates/s of the Rietkerk Dornic+RK4 step (BASELINE.json metric).
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU integrator
@@ -13,8 +13,11 @@ value  : whole-job site-updates/s, state resident in HBM, device-timed (CUDA eve
          kernel's stream), max over ranks.
 e2e    : same metric through tm_run_host(): every step copies the step's input frame from pinned
          host memory to the device and reads the step's reductions back.
-roofline: algorithmic bytes (48 B per site-update: 3 fields x (8 read + 8 written)) / the average
-         launch duration of the step kernel, against the measured HBM copy bandwidth.
+roofline: algorithmic bytes (48 B per site-update: 3 fields x (8 read + 8 written), SURVEY 8d) / the average
+         duration of one step, against the measured HBM copy bandwidth.  A step is two launches (the vegetation
+         Dornic sweep, then the RK4 marching kernel); `roofline.kernels` times each of them with CUDA events
+         recorded between the launches in a second, separate pass (tm_set_kernel_timing), with its own
+         algorithmic bytes (16 B and 48 B per site: the pair moves 64 B where a fused kernel would move 48).
 """
 import argparse
 import json
@@ -41,6 +44,18 @@ def measured_peaks():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kernel_lines(sites, ms_dornic, ms_rk4, n, peak):
+    """Per-kernel roofline lines of the pair: algorithmic bytes of each kernel / its own average duration."""
+    out = []
+    for name, ms, bps in (("tml::riet_dornic_kernel<STRICT=0>", ms_dornic, 16.0),
+                          ("tml::riet_step_kernel<DET=0,STRICT=0,SRC=pre,DORNIC_ONLY=0>", ms_rk4, 48.0)):
+        if n > 0 and ms > 0:
+            gbs = sites * bps / (ms * 1e-3 / n) / 1e9
+            out.append({"kernel": name, "ms_per_launch": ms / n, "algorithmic_bytes_per_site": bps,
+                        "achieved": gbs, "frac": gbs / peak, "launches_timed": n})
+    return out
 
 
 def ncu_traffic_per_launch(L, trials):
@@ -251,7 +266,7 @@ def run_ours(a):
     time.sleep(0.25)
     barrier()
     t0 = time.time()
-    lat.step(K)                      # K launches of the fused step kernel on the ctx stream
+    lat.step(K)                      # K steps = 2K launches (Dornic sweep + RK4 kernel) on the ctx stream
     lat.sync()
     t1 = time.time()
     ms_dev, n_launch = lat.last_step_ms()   # CUDA events recorded around the K launches
@@ -266,6 +281,12 @@ def run_ours(a):
     clocks = sampler.stop(t0, t1)
     clocks["window"] = "timed region + 0.5 s of the same launches"
     ms_dev = maxr(ms_dev)
+    # per-kernel durations: a second pass over K steps with an event between the two launches of each step
+    lat.set_kernel_timing(True)
+    lat.step(min(K, 64))
+    lat.sync()
+    ms_dornic, ms_rk4, n_timed = lat.kernel_ms()
+    lat.set_kernel_timing(False)
     stats = lat.measure()
     ok = all(s.nonfinite == 0 for s in stats)
 
@@ -302,8 +323,9 @@ def run_ours(a):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic_per_launch(L, trials), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": trials * L * L * BYTES_PER_SITE_UPDATE,
-                     "kernel": "tml::riet_step_kernel<DET=0,STRICT=0,SRC=philox,DORNIC_ONLY=0>"},
+                     "algorithmic_bytes_per_step": trials * L * L * BYTES_PER_SITE_UPDATE,
+                     "kernel": "one step = tml::riet_dornic_kernel<STRICT=0> + tml::riet_step_kernel<DET=0,STRICT=0,SRC=pre,DORNIC_ONLY=0>",
+                     "kernels": kernel_lines(trials * L * L, ms_dornic, ms_rk4, n_timed, peak)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "call": "tm_run_host(ctx, pinned_host_frame, nsteps=1, download=0, stats)"},
     }

@@ -147,6 +147,13 @@ int tm_sync(tm_ctx *);
  * (CUDA events on the ctx stream), and how many kernels that was. */
 int tm_last_step_ms(tm_ctx *, float *ms, int *n_launches);
 
+/* Rietkerk kernel pair only (measurement aid).  tm_set_kernel_timing(ctx, 1): the following tm_step() calls also
+ * record a CUDA event between the two kernels of each of their first 64 steps; tm_kernel_ms() then returns the device
+ * time summed over those steps of the Dornic sweep (ms[0]) and of the RK4 marching kernel (ms[1]) and the number
+ * of steps they cover.  Off by default: the extra events are not part of a production step. */
+int tm_set_kernel_timing(tm_ctx *, int on);
+int tm_kernel_ms(tm_ctx *, double ms[2], int *n_steps);
+
 /* --- one-call host-buffer form (what a reference runner would call per measurement window):
  * upload host_soa -> nsteps -> stats (-> download when download != 0). */
 int tm_run_host(tm_ctx *, double *host_soa, int nsteps, int download, tm_stats *out);

@@ -17,6 +17,8 @@ using namespace tml;
 
 static thread_local std::string g_create_error;
 
+constexpr int kTimedSteps = 64;
+
 struct tm_ctx {
     tm_params p{};
     Geom g{};
@@ -45,6 +47,9 @@ struct tm_ctx {
     uint32_t trial0 = 0;
     float last_ms = 0.f;
     int last_launches = 0, launches_this_call = 0;
+    bool kernel_timing = false;    // tm_set_kernel_timing: events around each kernel of the pair
+    std::vector<cudaEvent_t> kev;  // [3 * kTimedSteps]: before the Dornic sweep, between, after the RK4 kernel
+    int kev_steps = 0;
     std::string err;
 };
 
@@ -207,6 +212,7 @@ int tm_destroy(tm_ctx *c)
     cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev); cudaFree(c->pstar_dev); cudaFree(c->logtab_dev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    for (auto &e : c->kev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
@@ -359,11 +365,16 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             long long dgrid = ditems;
             if (dgrid > (long long)c->n_sm * 64) dgrid = (long long)c->n_sm * 64;
             const size_t dsmem = riet_dornic_smem_bytes();
+            const bool timed = c->kernel_timing && c->kev_steps < kTimedSteps;
+            cudaEvent_t *ev = timed ? &c->kev[3 * c->kev_steps] : nullptr;
+            if (timed) TM_CUDA(c, cudaEventRecord(ev[0], c->stream));
             if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
             else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
             TM_CUDA(c, cudaGetLastError());
+            if (timed) TM_CUDA(c, cudaEventRecord(ev[1], c->stream));
             A.pstar = c->pstar_dev;
             if (c->strict) TM_LAUNCH(false, true, kSrcPre, false); else TM_LAUNCH(false, false, kSrcPre, false);
+            if (timed) { TM_CUDA(c, cudaEventRecord(ev[2], c->stream)); c->kev_steps++; }
             c->launches_this_call += 1;
         }
 #undef TM_LAUNCH
@@ -411,6 +422,7 @@ int tm_step(tm_ctx *c, int nsteps)
     if (push_trial_consts(c) != TM_OK) return TM_E_CUDA;
     if (!c->g.wrap && nsteps > 1) TM_FAIL(c, TM_E_ARG, "tm_step: a row slab advances one step per halo exchange");
     c->launches_this_call = 0;
+    c->kev_steps = 0;
     TM_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     for (int s = 0; s < nsteps; s++) {
         const int rc = launch_step(c, s == nsteps - 1, false, 0, false);
@@ -556,6 +568,35 @@ int tm_sampler_overflow(tm_ctx *c, uint64_t *count)
     TM_CUDA(c, cudaStreamSynchronize(c->stream));
     *count = h[0];
     if (h[1]) TM_FAIL(c, TM_E_CUDA, "TMA pipeline timed out in %llu CTA(s): results are invalid", h[1]);
+    return TM_OK;
+}
+
+int tm_set_kernel_timing(tm_ctx *c, int on)
+{
+    if (!c) return TM_E_ARG;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    if (on && c->kev.empty()) {
+        c->kev.resize(3 * kTimedSteps);
+        for (auto &e : c->kev) TM_CUDA(c, cudaEventCreate(&e));
+    }
+    c->kernel_timing = on != 0;
+    c->kev_steps = 0;
+    return TM_OK;
+}
+
+int tm_kernel_ms(tm_ctx *c, double ms[2], int *n_steps)
+{
+    if (!c || !ms) return TM_E_ARG;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    ms[0] = ms[1] = 0.0;
+    for (int s = 0; s < c->kev_steps; s++) {
+        float a = 0.f, b = 0.f;
+        TM_CUDA(c, cudaEventSynchronize(c->kev[3 * s + 2]));
+        TM_CUDA(c, cudaEventElapsedTime(&a, c->kev[3 * s], c->kev[3 * s + 1]));
+        TM_CUDA(c, cudaEventElapsedTime(&b, c->kev[3 * s + 1], c->kev[3 * s + 2]));
+        ms[0] += a; ms[1] += b;
+    }
+    if (n_steps) *n_steps = c->kev_steps;
     return TM_OK;
 }
 

@@ -97,6 +97,8 @@ def lib():
         "tm_sampler_overflow": (i, [vp, C.POINTER(u64)]),
         "tm_sync": (i, [vp]),
         "tm_last_step_ms": (i, [vp, C.POINTER(C.c_float), C.POINTER(i)]),
+        "tm_set_kernel_timing": (i, [vp, i]),
+        "tm_kernel_ms": (i, [vp, C.POINTER(C.c_double), C.POINTER(i)]),
         "tm_run_host": (i, [vp, dp, i, i, C.POINTER(Stats)]),
     }
     for name, (res, args) in sig.items():
@@ -111,7 +113,7 @@ ABI_SYMBOLS = [
     "tm_set_trial_a", "tm_set_strict", "tm_set_fused", "tm_upload", "tm_download", "tm_n_fields", "tm_seed",
     "tm_set_step_counter", "tm_step_counter", "tm_step", "tm_step_replay", "tm_dornic_only",
     "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream", "tm_measure",
-    "tm_sampler_overflow", "tm_sync", "tm_last_step_ms", "tm_run_host",
+    "tm_sampler_overflow", "tm_sync", "tm_last_step_ms", "tm_set_kernel_timing", "tm_kernel_ms", "tm_run_host",
 ]
 
 
@@ -211,6 +213,15 @@ class Lattice:
         ms, n = C.c_float(), C.c_int()
         self._ck(self._l.tm_last_step_ms(self._ctx, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def set_kernel_timing(self, on=True):
+        self._ck(self._l.tm_set_kernel_timing(self._ctx, 1 if on else 0))
+
+    def kernel_ms(self):
+        """(ms of the Dornic sweeps, ms of the RK4 kernels, steps covered) of the last step() call."""
+        ms, n = (C.c_double * 2)(), C.c_int()
+        self._ck(self._l.tm_kernel_ms(self._ctx, ms, C.byref(n)))
+        return ms[0], ms[1], n.value
 
     def run_host(self, fields, nsteps, download=True):
         st = (Stats * self.n_trials)()
