@@ -741,16 +741,22 @@ riet_dornic_kernel(const DornicArgs A)
         const long long col = (long long)kHalo + qc;
         const double *pin = A.in + (long long)trial * g.trial_stride + (long long)pr * g.Lp + col;   // (row, column qc) of P
         double *pout = A.pstar + (long long)trial * g.field_stride + (long long)pr * g.Lp + col;
-        double Pu = pin[(long long)(prow(ra - 1) - pr) * g.Lp], Pc = pin[0];
+        // the centre column rolls through registers two rows ahead: the load of row+2 is in flight for a whole
+        // iteration (the L2/HBM latency of the row stream is what this kernel would otherwise wait for)
+        long long dn1 = (long long)(prow(ra + 1) - pr) * g.Lp;              // offset from row to row+1
+        int pr1 = prow(ra + 1);                                              // physical row of row+1
+        double Pu = pin[(long long)(prow(ra - 1) - pr) * g.Lp], Pc = pin[0], Pd = pin[dn1];
+        double Pl = pin[-1], Pr = pin[1];                                    // ghost columns cover q = 0 and q = L-1
         int grow = g.row0 + ra; if (grow < 0) grow += g.L; if (grow >= g.L) grow -= g.L;
         uint32_t cell = (uint32_t)grow * (uint32_t)g.L + (uint32_t)qc;
         int n_exact = 0;
         for (int row = ra; row < rb; row++) {
-            const bool last = g.wrap && pr + 1 == g.L;                      // the row below wraps to physical row 0
-            const long long dn = last ? -(long long)(g.L - 1) * g.Lp : (long long)g.Lp;
-            const double Pd = pin[dn], Pl = pin[-1], Pr = pin[1];           // ghost columns cover q = 0 and q = L-1
-            bool needs_exact;
+            const bool wrap2 = g.wrap && pr1 + 1 == g.L;                     // row+2 wraps to physical row 0
+            const long long dn2 = wrap2 ? -(long long)(g.L - 1) * g.Lp : (long long)g.Lp;
+            double Pn = Pd, Pln = Pl, Prn = Pr;
+            if (row + 1 < rb) { Pn = pin[dn1 + dn2]; Pln = pin[dn1 - 1]; Prn = pin[dn1 + 1]; } // for the next iteration
             const double nbsum = STRICT ? Pu + Pd + Pl + Pr : (Pu + Pd) + (Pl + Pr);    // STRICT: the reference's order R/:3756
+            bool needs_exact;
             double pstar = riet_dornic_value<STRICT>(A.dk, A.inv_lambda, A.mu_scale, Pc, nbsum, valid,
                                                      cell, ptrial, A.step, A.rk, logtab, sctab, needs_exact);
             if (needs_exact) { pstar = u2d(kExactMarker); n_exact++; }    // resolved by the second walk below
@@ -759,9 +765,9 @@ riet_dornic_kernel(const DornicArgs A)
                 if (ghost_r) pout[g.L] = pstar;
                 if (ghost_l) pout[-g.L] = pstar;
             }
-            Pu = Pc; Pc = Pd;
-            pin += dn; pout += dn;
-            pr = last ? 0 : pr + 1;
+            Pu = Pc; Pc = Pd; Pd = Pn; Pl = Pln; Pr = Prn;
+            pin += dn1; pout += dn1;
+            dn1 = dn2; pr1 = wrap2 ? 0 : pr1 + 1;
             if (++grow == g.L) { grow = 0; cell = (uint32_t)qc; } else cell += (uint32_t)g.L;
         }
         // second walk, extinction fringe only: the cells of this thread's run that need the exact Poisson / Gamma
