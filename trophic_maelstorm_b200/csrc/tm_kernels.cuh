@@ -320,6 +320,15 @@ TM_D void flush_stats(const ThreadStats &ts, int n_fields, int trial, PartialSta
 constexpr int kPSlots = 6;
 constexpr int kWoSlots = 9;
 constexpr int kStSlots = 3;
+#ifndef TM_CARRY_U
+#define TM_CARRY_U 1   // upper neighbours of the stage rows carried in registers instead of re-read from shared memory
+#endif
+#ifndef TM_CARRY_C
+#define TM_CARRY_C 1   // ... and the centre values too: only the left/right neighbours come from shared memory
+#endif
+#ifndef TM_CARRY_0
+#define TM_CARRY_0 0   // same for the stage-0 (streamed) W,O rows of front 1: 8 more registers spill at 96 (0.48 ms); at 128
+#endif                 // registers / 3 CTAs per SM it is a wash (0.382 vs 0.379 ms per step), so it stays off
 constexpr int kLead = 4;               // row j+kLead is requested when row j has been consumed
 
 constexpr int kRW = kMaxThreads + 4;   // shared row width: compile-time, so field/neighbour offsets fold into immediates
@@ -529,6 +538,9 @@ riet_step_kernel(const StepArgs A)
         double Ps_m4 = 0, Ps_m3 = 0, Ps_m2 = 0;
         double P1_m2 = 0, P2_m3 = 0, P3_m4 = 0;
         double aP_m4 = 0, aP_m3 = 0, aP_m2 = 0, aW_m4 = 0, aW_m3 = 0, aW_m2 = 0, aO_m4 = 0, aO_m3 = 0, aO_m2 = 0;
+        double w0_m1 = 0, o0_m1 = 0, w0_m2 = 0, o0_m2 = 0;   // stage-0 W,O of this column one and two rows behind the streamed row
+        WO c1_m3 = {0, 0}, c2_m4 = {0, 0}, c3_m5 = {0, 0};   // own-column stage values one row behind each front (its "up")
+        WO n1_m2 = {0, 0}, n2_m3 = {0, 0}, n3_m4 = {0, 0};   // ... and on each front's row (its centre): made by this thread one row ago
 
         for (int it = 0; it < nit; it += 3) {
             const int pq0 = Q0 * kPGrp, pq1 = Q1 * kPGrp;
@@ -582,10 +594,13 @@ riet_step_kernel(const StepArgs A)
                     if (out_col && j - 1 >= ya && j - 1 < yb)
                         A.dornic_out[((size_t)trial * g.nrows + (j - 1)) * g.L + gx] = pstar;
                 } else {
-                    const double W0c = q1[0], O0c = q1[RW];
+                    // stage-0 W,O of this column: the row below is read, centre and upper row were read one and two rows ago
+                    const double W0d = q0[0], O0d = q0[RW];
+                    const double W0c = TM_CARRY_0 ? w0_m1 : q1[0], O0c = TM_CARRY_0 ? o0_m1 : q1[RW];
+                    const double W0u = TM_CARRY_0 ? w0_m2 : q2[0], O0u = TM_CARRY_0 ? o0_m2 : q2[RW];
                     const F3 k1 = rhs<DET, STRICT>(c, a_rain, pstar, W0c, O0c,
-                                                   q2[0], q0[0], q1[-1], q1[1],
-                                                   q2[RW], q0[RW], q1[RW - 1], q1[RW + 1],
+                                                   W0u, W0d, q1[-1], q1[1],
+                                                   O0u, O0d, q1[RW - 1], q1[RW + 1],
                                                    Pu, Pd, Pl, Pr);
                     const double P1_m1 = axpy<STRICT>(hP2, k1.p, pstar);
                     const double W1_m1 = axpy<STRICT>(c.dt2, k1.w, W0c);
@@ -595,21 +610,21 @@ riet_step_kernel(const StepArgs A)
 
                     // ---- front 2: row j-2 : K2 (stage-1 rows j-3, j-2 from the ring, j-1 just made) ---
                     const WO *s1 = sp(1, 2);
-                    const WO s1c = s1[0], s1l = s1[-1], s1r = s1[1], s1u = *sp(1, 3);
+                    const WO s1c = TM_CARRY_C ? n1_m2 : s1[0], s1l = s1[-1], s1r = s1[1], s1u = TM_CARRY_U ? c1_m3 : *sp(1, 3);
                     const F3 k2 = rhs<DET, STRICT>(c, a_rain, P1_m2, s1c.w, s1c.o,
                                                    s1u.w, W1_m1, s1l.w, s1r.w,
                                                    s1u.o, O1_m1, s1l.o, s1r.o,
                                                    DET ? *spP(1, 3) : 0.0, P1_m1, DET ? spP(1, 2)[-1] : 0.0, DET ? spP(1, 2)[1] : 0.0);
                     const double P2_m2 = axpy<STRICT>(hP2, k2.p, Ps_m2);
-                    const double W2_m2 = axpy<STRICT>(c.dt2, k2.w, q2[0]);
-                    const double O2_m2 = axpy<STRICT>(c.dt2, k2.o, q2[RW]);
+                    const double W2_m2 = axpy<STRICT>(c.dt2, k2.w, W0u);
+                    const double O2_m2 = axpy<STRICT>(c.dt2, k2.o, O0u);
                     *sp(2, 2) = WO{W2_m2, O2_m2};
                     if (DET) *spP(2, 2) = P2_m2;
                     aP_m2 = axpy<STRICT>(2.0, k2.p, aP_m2); aW_m2 = axpy<STRICT>(2.0, k2.w, aW_m2); aO_m2 = axpy<STRICT>(2.0, k2.o, aO_m2);
 
                     // ---- front 3: row j-3 : K3 ---------------------------------------------------------
                     const WO *s2 = sp(2, 3);
-                    const WO s2c = s2[0], s2l = s2[-1], s2r = s2[1], s2u = *sp(2, 4);
+                    const WO s2c = TM_CARRY_C ? n2_m3 : s2[0], s2l = s2[-1], s2r = s2[1], s2u = TM_CARRY_U ? c2_m4 : *sp(2, 4);
                     const F3 k3 = rhs<DET, STRICT>(c, a_rain, P2_m3, s2c.w, s2c.o,
                                                    s2u.w, W2_m2, s2l.w, s2r.w,
                                                    s2u.o, O2_m2, s2l.o, s2r.o,
@@ -623,7 +638,7 @@ riet_step_kernel(const StepArgs A)
 
                     // ---- front 4: row j-4 : K4, commit -------------------------------------------------
                     const WO *s3 = sp(3, 4);
-                    const WO s3c = s3[0], s3l = s3[-1], s3r = s3[1], s3u = *sp(3, 5);
+                    const WO s3c = TM_CARRY_C ? n3_m4 : s3[0], s3l = s3[-1], s3r = s3[1], s3u = TM_CARRY_U ? c3_m5 : *sp(3, 5);
                     const F3 k4 = rhs<DET, STRICT>(c, a_rain, P3_m4, s3c.w, s3c.o,
                                                    s3u.w, W3_m3, s3l.w, s3r.w,
                                                    s3u.o, O3_m3, s3l.o, s3r.o,
@@ -643,6 +658,9 @@ riet_step_kernel(const StepArgs A)
                         if (ghost_l) { po[-g.L] = nP; po[g.field_stride - g.L] = nW; po[2 * g.field_stride - g.L] = nO; }
                     }
                     // ---- shift the register windows by one row (renamed away by the unrolling) -------------
+                    w0_m2 = W0c; o0_m2 = O0c; w0_m1 = W0d; o0_m1 = O0d;
+                    c1_m3 = s1c; c2_m4 = s2c; c3_m5 = s3c;   // this row's centre is the next row's upper neighbour
+                    n1_m2 = WO{W1_m1, O1_m1}; n2_m3 = WO{W2_m2, O2_m2}; n3_m4 = WO{W3_m3, O3_m3}; // ... and what was just made, its centre
                     P3_m4 = P3_m3; P2_m3 = P2_m2; P1_m2 = P1_m1;
                     aP_m4 = aP_m3; aP_m3 = aP_m2; aP_m2 = k1.p; aW_m4 = aW_m3; aW_m3 = aW_m2; aW_m2 = k1.w;
                     aO_m4 = aO_m3; aO_m3 = aO_m2; aO_m2 = k1.o;
