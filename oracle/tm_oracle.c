@@ -249,8 +249,41 @@ static double normal01(cstream *s, normal_state *st)
 /* std::poisson_distribution<int>(mean)::operator() for a freshly constructed object
  * (the reference constructs one per cell: P/:1055, R/:3781).  Parameter set-up LS:1267-1296,
  * draw LS:1310-1400: Devroye's rejection for mean >= 12, product of uniforms below. */
+/* Product spec, Philox streams only: Poisson(mean) by inversion on one uniform (mean < 12) or by
+ * Hoermann's PTRS transformed rejection (mean >= 12) -- same law as LS, algorithms that suit a warp
+ * (DESIGN.md section 3).  Own restatement; 1/k comes from an IEEE division, which is what the
+ * product's compile-time table holds. */
+static long poisson_product(cstream *s, double mean)
+{
+    if (mean < 12.0) {
+        double u = next_u(s);
+        double p = tmo_exp(-mean), F = p;
+        int k = 0;
+        while (u > F && k < 64) { k++; p = p * mean * (1.0 / (double)k); F += p; }
+        return k;
+    }
+    double slam = sqrt(mean), loglam = tmo_log(mean);
+    double b = 0.931 + 2.53 * slam;
+    double a = -0.059 + 0.02483 * b;
+    double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+    double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (int it = 0; it < TM_MAX_REJECT; it++) {
+        double U = next_u(s) - 0.5;
+        double V = 1.0 - next_u(s);
+        double us = 0.5 - fabs(U);
+        double kf = floor((2.0 * a / us + b) * U + mean + 0.43);
+        if (us >= 0.07 && V <= vr) return (long)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        if (tmo_log(V) + tmo_log(invalpha) - tmo_log(a / (us * us) + b) <= -mean + kf * loglam - tmo_lgamma_int(kf + 1.0))
+            return (long)kf;
+    }
+    s->g->overflow++;
+    return (long)floor(mean);
+}
+
 static long poisson_draw(cstream *s, double mean)
 {
+    if (s->g->kind == TMO_SRC_PHILOX) return poisson_product(s, mean);
     if (mean >= 12.0) {
         normal_state nd = {0, 0.0}; /* the distribution's own _M_nd, fresh (LS: poisson ctor) */
         /* _M_initialize, LS:1276-1291 */
@@ -391,6 +424,13 @@ double tmo_test_normal_pair_philox(uint64_t seed, uint32_t cell, uint32_t trial,
     double a = normal01(&s, &st);
     *second = normal01(&s, &st);
     return a;
+}
+long tmo_test_poisson_philox(uint64_t seed, uint32_t cell, uint32_t trial, uint32_t step, double mean)
+{
+    tmo_rng g; memset(&g, 0, sizeof g);
+    g.kind = TMO_SRC_PHILOX; g.seed = seed; g.trial = trial; g.step = step;
+    cstream s; cs_begin_cell(&s, &g, cell);
+    return poisson_draw(&s, mean);
 }
 long tmo_test_poisson(const double *u, uint64_t n, uint64_t *pos, double mean)
 {

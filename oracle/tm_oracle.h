@@ -93,6 +93,7 @@ double tmo_u52_from_bits(uint64_t w);
 /* ---- samplers (restating LS) driven by an array of uniforms; *pos advances -------- */
 double tmo_test_normal_pair(const double *u, uint64_t n, uint64_t *pos, double *second);
 double tmo_test_normal_pair_philox(uint64_t seed, uint32_t cell, uint32_t trial, uint32_t step, double *second);
+long   tmo_test_poisson_philox(uint64_t seed, uint32_t cell, uint32_t trial, uint32_t step, double mean);
 long   tmo_test_poisson(const double *u, uint64_t n, uint64_t *pos, double mean);
 double tmo_test_gamma(const double *u, uint64_t n, uint64_t *pos, double shape);
 

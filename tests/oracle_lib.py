@@ -57,6 +57,8 @@ def oracle():
         L.tmo_test_normal_pair_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, dp]
         L.tmo_sincos_turn128.restype = None
         L.tmo_sincos_turn128.argtypes = [C.c_double, dp, dp]
+        L.tmo_test_poisson_philox.restype = C.c_long
+        L.tmo_test_poisson_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double]
         L.tmo_test_poisson.restype = C.c_long
         L.tmo_test_poisson.argtypes = [dp, C.c_uint64, C.POINTER(C.c_uint64), C.c_double]
         L.tmo_test_gamma.restype = C.c_double

@@ -77,6 +77,26 @@ def test_poisson_law(mean):
         assert stats.chisquare(o, e).pvalue > 1e-4
 
 
+@pytest.mark.parametrize("mean", [1e-3, 0.3, 1.0, 5.0, 11.9, 12.0, 30.0, 100.0, 1e4])
+def test_poisson_law_philox(mean):
+    """Philox streams draw Poisson by inversion (< 12) and PTRS transformed rejection (>= 12): same pmf (chi-square)."""
+    L = O.oracle()
+    n = 40000
+    x = np.array([L.tmo_test_poisson_philox(1234, cell, 2, int(mean * 7) % 1000, C.c_double(mean)) for cell in range(n)])
+    assert (x >= 0).all()
+    assert abs(x.mean() - mean) < 5 * math.sqrt(mean / n) + 1e-12
+    assert abs(x.var() - mean) < 0.05 * mean + 5e-3
+    lo, hi = int(stats.poisson.ppf(1e-4, mean)), int(stats.poisson.ppf(1 - 1e-4, mean))
+    ks = np.arange(lo, hi + 1)
+    exp = stats.poisson.pmf(ks, mean) * n
+    obs = np.array([(x == k).sum() for k in ks], dtype=float)
+    keep = exp >= 5
+    if keep.sum() >= 2:
+        o, e = obs[keep], exp[keep]
+        e = e * o.sum() / e.sum()
+        assert stats.chisquare(o, e).pvalue > 1e-4
+
+
 @pytest.mark.parametrize("shape", [1e-3, 0.5, 1.0, 2.5, 10.0, 100.0])
 def test_gamma_law(shape):
     """LS:2352-2387: Marsaglia-Tsang, u^(1/alpha) boost below 1 (KS vs the cdf)."""

@@ -5,7 +5,8 @@
 // from libstdc++ (LS = <bits/random.tcc>, GCC 13):
 //   std::normal_distribution  LS:1811-1848   Marsaglia polar, one cached variate (replay mode; a Philox
 //                                            stream draws the same law by Box-Muller, no rejection loop)
-//   std::poisson_distribution LS:1267-1400   product of uniforms (mean < 12), Devroye rejection (>= 12)
+//   std::poisson_distribution LS:1267-1400   product of uniforms (mean < 12), Devroye rejection (>= 12) (replay mode;
+//                                            a Philox stream draws the same law by inversion / PTRS)
 //   std::gamma_distribution   LS:2338-2387   Marsaglia-Tsang, u^(1/alpha) boost for alpha < 1
 // as called per cell at P/:1055-1059 (DP), P/:1957-1979 (cubic DP), R/:3766-3794 (Rietkerk,
 // with the Gaussian shortcuts above 100).  What differs from the reference is the stream: every
@@ -21,7 +22,7 @@ namespace tml {
 // Philox4x32-10: key = seed, counter = (cell, trial, step, block); block b yields uniforms
 // 2b (words 0,1) and 2b+1 (words 2,3).
 struct PhiloxSrc {
-    static constexpr bool kBoxMuller = true;   // normal law of this source: see normal01()
+    static constexpr bool kProductLaws = true; // this source draws N(0,1) by Box-Muller and Poisson by inversion / PTRS (see below)
     uint32_t cell, trial, step, k0, k1;
     uint32_t n;       // uniforms handed out so far
     double second;
@@ -44,7 +45,7 @@ struct PhiloxSrc {
 
 // Replay: uniform k of this cell is base[k], k < stride; beyond that 0.75 and a counted overflow.
 struct ReplaySrc {
-    static constexpr bool kBoxMuller = false;  // replay follows the reference's polar loop draw for draw
+    static constexpr bool kProductLaws = false; // replay follows the reference's libstdc++ algorithms draw for draw
     const double *base;
     uint32_t stride, n, ovf;
     TM_HD void begin(const double *base_, uint32_t stride_) { base = base_; stride = stride_; n = 0; ovf = 0; }
@@ -67,7 +68,7 @@ template <class Src>
 TM_HD double normal01(Src &s, NormalState &st)
 {
     if (st.have) { st.have = false; return st.saved; }
-    if (Src::kBoxMuller) {
+    if (Src::kProductLaws) {
         // Philox mode: the same N(0,1) law without the rejection loop.  Box-Muller on the next two
         // uniforms: radius from x = 2 - (1+u0 with its last mantissa bit set), in (0,1); angle 2 pi u1.
         const double u0 = s.next(), u1 = s.next();
@@ -93,9 +94,46 @@ TM_HD double normal01(Src &s, NormalState &st)
     return y * mult;
 }
 
+// Poisson(mean) for Philox streams: the same law as std::poisson_distribution with algorithms that suit a warp.
+//   mean < 12 : inversion by sequential search on ONE uniform (libstdc++ multiplies ~mean+1 uniforms: a Philox block
+//               every other iteration, and the warp runs the longest lane's loop);
+//   mean >= 12: Hoermann's transformed rejection PTRS (1993): two uniforms per attempt, ~86 % accepted by the
+//               squeeze without a logarithm, no set-up beyond one sqrt, one log and two divisions (libstdc++'s
+//               Devroye rejection spends ten elementary-function calls on set-up per cell because the reference
+//               constructs a fresh distribution object per cell, P/:1055).
+template <class Src>
+TM_HD long long poisson_product(Src &s, double mean)
+{
+    if (mean < 12.0) {
+        const double u = s.next();
+        double p = exp_any(-mean), F = p;
+        int k = 0;
+        while (u > F && k < 64) { k++; p = p * mean * inv_int(k); F += p; }
+        return k;
+    }
+    const double slam = sqrt(mean), loglam = log_pos(mean);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (int it = 0; it < kMaxReject; it++) {
+        const double U = s.next() - 0.5;
+        const double V = 1.0 - s.next();                       // (0,1]
+        const double us = 0.5 - fabs(U);
+        const double kf = floor((2.0 * a / us + b) * U + mean + 0.43);
+        if (us >= 0.07 && V <= vr) return (long long)kf;
+        if (kf < 0.0 || (us < 0.013 && V > us)) continue;
+        if (log_pos(V) + log_pos(invalpha) - log_pos(a / (us * us) + b) <= -mean + kf * loglam - lgamma_int(kf + 1.0))
+            return (long long)kf;
+    }
+    s.overflowed();
+    return (long long)floor(mean);
+}
+
 template <class Src>
 TM_HD long long poisson_draw(Src &s, double mean)
 {
+    if (Src::kProductLaws) return poisson_product(s, mean);
     if (mean >= 12.0) {
         NormalState nd{false, 0.0};
         const double m = floor(mean);
