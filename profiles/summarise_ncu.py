@@ -39,17 +39,18 @@ def main():
     res["stalled_warps_per_issue_active"] = dict(sorted(stalls.items(), key=lambda kv: -kv[1])[:10])
     src = page(rep, "source")
     h = src[1]
-    ie, so, wf = h.index("Instructions Executed"), h.index("Source"), h.index("L1 Wavefronts Shared")
+    ie, so = h.index("Instructions Executed"), h.index("Source")
+    wf = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else None   # absent when the kernel uses no shared memory
     ops, wfs, total = defaultdict(float), 0.0, 0.0
     for r in src[2:]:
-        if len(r) <= wf:
+        if len(r) <= max(ie, so, wf or 0):
             continue
         toks = r[so].split()
         op = toks[1] if toks and toks[0].startswith("@") and len(toks) > 1 else (toks[0] if toks else "?")
         n = float(r[ie] or 0)
         ops[op.split(".")[0]] += n
         total += n
-        wfs += float(r[wf] or 0)
+        wfs += float(r[wf] or 0) if wf is not None else 0.0
     res["warp_instructions_executed"] = total
     res["shared_wavefronts"] = wfs
     if sites:
