@@ -140,6 +140,16 @@ void *tm_cuda_stream(tm_ctx *);
 /* --- measurement ----------------------------------------------------------------------- */
 /* out[n_trials]; blocks until the stream is idle. */
 int tm_measure(tm_ctx *, tm_stats *out);
+/* Spreading-experiment observables of field 0 about the seed site (c_x, c_y) = (row, column): what the reference's
+ * spreading_exp_Dornic_2D evaluates every step (meansq_spread_of_vector P/:156-169, theborderwall P/:380-390).
+ * out[n_trials]; blocks until the stream is idle. */
+typedef struct tm_spread {
+    uint64_t n_active;      /* N(t) = #{rho > 0} */
+    double   sq_dist;       /* sum over active sites of (p - c_x)^2 + (q - c_y)^2; R^2(t) = sq_dist / N */
+    int32_t  border;        /* 1 when an active site lies on the first/last row or column */
+    int32_t  pad_;
+} tm_spread;
+int tm_measure_spread(tm_ctx *, int c_x, int c_y, tm_spread *out);
 int tm_sampler_overflow(tm_ctx *, uint64_t *count);
 int tm_sync(tm_ctx *);
 

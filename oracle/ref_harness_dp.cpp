@@ -56,6 +56,32 @@ int ref_dp_run(int cubic, int L, double a, double b, double c, double D, double 
     return n;
 }
 
+/* spreading_exp_Dornic_2D (stochasticSPDP.cpp:1145): r replicates from rh0, seed site (c_x, c_y).
+ * rows_out[k] = {thread, a, t, <N>_r, <R2>_r, n_surv} -- the runner's own output rows (:1294-1298). */
+int ref_dp_spread_run(int L, double a, double b, double D, double sigma, double dt, double dx, int r,
+                      const double *rh0, const double *t_meas_in, int n_tmeas, int c_x, int c_y,
+                      const double *u, uint64_t n_u, double *rows_out, int rows_cap,
+                      uint64_t *consumed, uint64_t *overflow)
+{
+    vector<vector<double>> Rho;
+    vector<double> t_meas(t_meas_in, t_meas_in + n_tmeas);
+    vector<double> Rh0(rh0, rh0 + (size_t)L * L);
+    double t_max = t_meas.back();
+    tm_replay_arm(u, n_u);
+    {
+        quiet q;
+        spreading_exp_Dornic_2D(Rho, t_meas, Rh0.data(), t_max, a, b, D, sigma, dt, dx, r, L, c_x, c_y);
+    }
+    if (consumed) *consumed = tm_replay.pos;
+    if (overflow) *overflow = tm_replay.overflow;
+    tm_replay_arm(nullptr, 0);
+    int n = (int)Rho.size();
+    if (n > rows_cap) return -1;
+    for (int k = 0; k < n; k++)
+        for (int j = 0; j < 6; j++) rows_out[6 * k + j] = Rho[k][j];
+    return n;
+}
+
 /* logarithm10_time_bins, stochasticSPDP.cpp:336 */
 int ref_dp_time_bins(double t_max, double dt, double *out, int cap)
 {

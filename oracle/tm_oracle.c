@@ -745,3 +745,33 @@ void tmo_var_mean_incremental_surv_runs(double *acc, const double *rep, int n, i
         A[3] = r;
     }
 }
+
+/* spreading-experiment observables: meansq_spread_of_vector P/:156-169 (N = #{x>0}, sum over them of
+ * (p-c_x)^2 + (q-c_y)^2 with p = i/g, q = i%g) and theborderwall P/:380-390. */
+void tmo_spread_stats(const double *x, int g, int c_x, int c_y, double *sq_dist, int64_t *n_active, int *border)
+{
+    double sq = 0.0; int64_t sum = 0;
+    for (int i = 0; i < g * g; i++)
+        if (x[i] > 0) {
+            int p = i / g, q = i % g;
+            sum += 1;
+            sq += (p - c_x) * (p - c_x) + (q - c_y) * (q - c_y);
+        }
+    *sq_dist = sq; *n_active = sum;
+    int g2 = g * (g - 1), hit = 0;
+    for (int i = 0; i < g && !hit; i++)
+        if (x[i] > 0 || x[g * i] > 0 || x[g2 + i] > 0 || x[g * i + g - 1] > 0) hit = 1;
+    *border = hit;
+}
+
+/* spreading_incremental_surv_runs P/:230-252: acc [n][4] = {t, <N>, <R2>, n_surv}; rep [n][3] = {N, R2, 1} */
+void tmo_spreading_incremental_surv_runs(double *acc, const double *rep, int n)
+{
+    for (int i = 0; i < n; i++) {
+        int r = (int)(acc[4 * i + 3] + 1);
+        if (rep[3 * i] == 0.0) break;
+        acc[4 * i + 1] = (rep[3 * i] + (r - 1) * acc[4 * i + 1]) / r;
+        acc[4 * i + 2] = (rep[3 * i + 1] + (r - 1) * acc[4 * i + 2]) / r;
+        acc[4 * i + 3] = r;
+    }
+}

@@ -119,6 +119,11 @@ int tmo_logarithm10_time_bins(double t_max, double dt, double *out, int cap);
  * acc: [n][5] = {t, mean, var, n_surv, n_active}; rep: [n][2] = {n_active, mean}; j = replicate index. */
 void tmo_var_mean_incremental_surv_runs(double *acc, const double *rep, int n, int j);
 
+/* spreading experiments: meansq_spread_of_vector P/:156 + theborderwall P/:380, and the
+ * replicate accumulation spreading_incremental_surv_runs P/:230. */
+void tmo_spread_stats(const double *x, int g, int c_x, int c_y, double *sq_dist, int64_t *n_active, int *border);
+void tmo_spreading_incremental_surv_runs(double *acc, const double *rep, int n);
+
 #ifdef __cplusplus
 }
 #endif

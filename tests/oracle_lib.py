@@ -64,6 +64,10 @@ def oracle():
         L.tmo_test_gamma.restype = C.c_double
         L.tmo_test_gamma.argtypes = [dp, C.c_uint64, C.POINTER(C.c_uint64), C.c_double]
         L.tmo_logarithm10_time_bins.argtypes = [C.c_double, C.c_double, dp, C.c_int]
+        L.tmo_spread_stats.restype = None
+        L.tmo_spread_stats.argtypes = [dp, C.c_int, C.c_int, C.c_int, dp, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.tmo_spreading_incremental_surv_runs.restype = None
+        L.tmo_spreading_incremental_surv_runs.argtypes = [dp, dp, C.c_int]
         L.tmo_var_mean_incremental_surv_runs.argtypes = [dp, dp, C.c_int, C.c_int]
         _lib = L
     return _lib
@@ -114,6 +118,14 @@ def mean(x):
 def occupied(x):
     x = np.ascontiguousarray(x, dtype=np.float64).ravel()
     return oracle().tmo_occupied(ptr(x), x.size)
+
+
+def spread_stats(x, g, c_x, c_y):
+    """(sum of squared distances, N, border hit) of one g x g field about (c_x, c_y): P/:156 and P/:380."""
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    sq, n, b = C.c_double(), C.c_int64(), C.c_int()
+    oracle().tmo_spread_stats(ptr(x), g, c_x, c_y, C.byref(sq), C.byref(n), C.byref(b))
+    return sq.value, n.value, b.value
 
 
 def synthetic_rietkerk_frame(L, seed=1234, a=0.05, dP=10000.0, fringe=True):

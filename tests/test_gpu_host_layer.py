@@ -209,3 +209,58 @@ def test_rietkerk_sweep_writes_reference_tree(host, tmp_path):
     assert len(prelims) == div * r and prelims[0].startswith("PRELIM_AGGRAND_P_c_ID_0_DP_G_32_T_")
     pl = (pdir / prelims[0]).read_text().splitlines()
     assert pl[1].endswith(",") and pl[1].split(",")[1] in ("1", "2") and len(pl) == 2 + nbins - 1 + 0 or len(pl) >= nbins
+
+
+# ---- spreading experiments: tm_measure_spread + spreading_exp_Dornic_2D ---------------
+
+def test_measure_spread_matches_oracle():
+    """N(t), sum of squared distances about the seed and the border test (P/:156, P/:380): exact (integers)."""
+    L, nt = 64, 5
+    rng = np.random.default_rng(3)
+    f = np.zeros((nt, 1, L, L))
+    f[0, 0, L // 2, L // 2] = 1.0                                   # the solitary seed: N=1, R^2=0, no border
+    f[1, 0] = (rng.random((L, L)) < 0.05) * rng.random((L, L))      # scattered, touches the border
+    f[2, 0, 10:50, 12:40] = (rng.random((40, 28)) < 0.5) * 0.3      # interior blob
+    f[3, 0, L - 1, 7] = 1e-300                                      # a single active site on the last row
+    f[4, 0, 20, 0] = 2.0; f[4, 0, 5, 5] = -1.0                      # first column; a negative site is not active
+    lat = tm.Lattice(tm.dp_params(L, a=1.0548, b=1.0, D=0.25, sigma=2 ** 0.5, dt=0.1, dx=1.0), nt)
+    lat.upload(f)
+    for (cx, cy) in ((L // 2, L // 2), (3, 60)):
+        got = lat.measure_spread(cx, cy)
+        for t in range(nt):
+            sq, n, border = O.spread_stats(f[t, 0], L, cx, cy)
+            assert (got[t].n_active, got[t].sq_dist, got[t].border) == (n, sq, border), t
+    lat.close()
+
+
+def test_spreading_runner_ensemble_matches_reference(host):
+    """spreading_exp_Dornic_2D through the host layer (replicates as one batch of trials) against 320 replicates of the
+    unmodified reference: <N(t)> and <R^2(t)> over surviving runs and P_surv(t) within 4.5 standard errors."""
+    g = np.load(os.path.join(GOLD, "ens_dp_spread.npz"))
+    L, tmv, ref = int(g["L"]), np.ascontiguousarray(g["t_meas"]), g["series"]     # [rep][row][t, N, R2, surv]
+    a, b, D, sigma, dt, dx = [float(x) for x in g["params"]]
+    r = 1024
+    host.tmh_dp_spread_run.argtypes = [C.c_int] + [C.c_double] * 6 + [C.c_int, dp, dp, C.c_int, C.c_int, C.c_int, dp, C.c_int]
+    host.tmh_set_options(0, 99, 0, None)
+    rho0 = np.zeros(L * L); rho0[L * (L // 2) + L // 2] = 1.0
+    rows = np.zeros((4096, 6))
+    n = host.tmh_dp_spread_run(L, a, b, D, sigma, dt, dx, r, O.ptr(rho0), O.ptr(tmv), len(tmv), L // 2, L // 2, O.ptr(rows), 4096)
+    assert n == ref.shape[1], n
+    rows = rows[:n]
+    assert np.allclose(rows[:, 2], ref[0, :, 0])
+    assert rows[0, 3] == 1.0 and rows[0, 4] == 0.0 and rows[0, 5] == r            # t = 0: the seed alone, everyone alive
+    assert (np.diff(rows[:, 5]) <= 0).all()                                        # survival only decreases
+    nref = ref.shape[0]
+    surv_ref = ref[:, :, 3]
+    p_ref, p_gpu = surv_ref.mean(0), rows[:, 5] / r
+    p_pool = (p_ref * nref + p_gpu * r) / (nref + r)                              # pooled: p_ref is exactly 1 at early times
+    se_p = np.sqrt(np.maximum(p_pool * (1 - p_pool), 1e-4) * (1.0 / nref + 1.0 / r))
+    assert (np.abs(p_gpu - p_ref) <= 4.5 * se_p + 1e-12).all(), np.abs(p_gpu - p_ref) / se_p
+    for col, gcol in ((1, 3), (2, 4)):                                             # N(t), R^2(t) over surviving runs
+        for k in range(1, n):
+            alive = surv_ref[:, k] > 0
+            if alive.sum() < 20 or rows[k, 5] < 20:
+                continue
+            x = ref[alive, k, col]
+            se = x.std(ddof=1) * np.sqrt(1.0 / alive.sum() + 1.0 / rows[k, 5])
+            assert abs(rows[k, gcol] - x.mean()) <= 4.5 * se + 1e-9, (col, k, rows[k, gcol], x.mean(), se)

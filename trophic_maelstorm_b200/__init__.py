@@ -8,6 +8,6 @@ There is no CPU path: importing works anywhere (so the symbol table can be check
 compute call fails loudly without the CUDA library and a GPU.
 """
 from .lattice import (  # noqa: F401
-    Lattice, Params, Stats, TmError, lib, lib_path, rietkerk_params, dp_params,
+    Lattice, Params, Stats, Spread, TmError, lib, lib_path, rietkerk_params, dp_params,
     MODEL_DP, MODEL_DP_CUBIC, MODEL_RIETKERK, MODEL_RIETKERK_DET,
 )

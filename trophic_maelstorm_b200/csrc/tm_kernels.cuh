@@ -975,6 +975,38 @@ stats_finalize_kernel(const PartialStats *partials, int n_records, int n_trials,
     }
 }
 
+// Spreading-experiment observables of field 0 (P/:156-169 meansq_spread_of_vector, P/:380-390 theborderwall):
+// per trial the number of active sites N, sum over them of (p-c_x)^2 + (q-c_y)^2 (p = row, q = column), and
+// whether any site of the four border lines is active.  All three are integers (the squared distances are exact
+// in the reference's double sum too, far below 2^53), so 64-bit atomics give an order-independent, exact result.
+struct SpreadArgs { Geom g; const double *in; unsigned long long *acc; /* [n_trials][3] = N, sum r^2, border */ int c_x, c_y, blocks_per_trial; };
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(256)
+#else
+inline void
+#endif
+spread_kernel(const SpreadArgs A)
+{
+    const Geom &g = A.g;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int trial = blockIdx.x / A.blocks_per_trial, blk = blockIdx.x % A.blocks_per_trial;
+    const double *in = A.in + (long long)trial * g.trial_stride + kHalo;
+    unsigned long long n = 0, sq = 0, border = 0;
+    for (int r = blk; r < g.nrows; r += A.blocks_per_trial) {
+        const double *row = in + (long long)(g.wrap ? r : r + kHalo) * g.Lp;
+        const long long p = g.row0 + r, dp = p - A.c_x;
+        for (int q = tid; q < g.L; q += nthreads) {
+            if (row[q] > 0) {
+                const long long dq = q - A.c_y;
+                n += 1; sq += (unsigned long long)(dp * dp + dq * dq);
+                if (p == 0 || p == g.L - 1 || q == 0 || q == g.L - 1) border = 1;
+            }
+        }
+    }
+    if (n) { atomicAdd(&A.acc[3 * trial], n); atomicAdd(&A.acc[3 * trial + 1], sq); }
+    if (border) atomicAdd(&A.acc[3 * trial + 2], 1ull);
+}
+
 // ghost-column fill after an upload / halo unpack: one thread per (row, 0..7)
 struct GhostArgs { Geom g; double *buf; };
 #if defined(__CUDACC__)

@@ -41,6 +41,7 @@ struct tm_ctx {
     double *dornic_dev = nullptr;
     double *logtab_dev = nullptr;  // FAST-mode log table
     double *pstar_dev = nullptr;   // rho* scratch field of the split Dornic / RK4 kernel pair
+    unsigned long long *spread_dev = nullptr; // [n_trials][3] accumulators of tm_measure_spread
     bool fused = false;            // default: Dornic sweep + RK4 kernel pair; true: the single fused kernel
     double *halo_dev[2] = {nullptr, nullptr};
     uint64_t seed = 0, step = 0;
@@ -209,7 +210,7 @@ int tm_destroy(tm_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int s = 0; s < 2; s++) { cudaFree(c->buf[s]); cudaFree(c->halo_dev[s]); }
     cudaFree(c->a_dev); cudaFree(c->dp_trials_dev); cudaFree(c->partials); cudaFree(c->stats_dev);
-    cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev); cudaFree(c->pstar_dev); cudaFree(c->logtab_dev);
+    cudaFree(c->counters); cudaFree(c->replay_dev); cudaFree(c->dornic_dev); cudaFree(c->pstar_dev); cudaFree(c->logtab_dev); cudaFree(c->spread_dev);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto &e : c->kev) cudaEventDestroy(e);
@@ -555,6 +556,30 @@ int tm_measure(tm_ctx *c, tm_stats *out)
     for (int t = 0; t < g.n_trials; t++) {
         for (int f = 0; f < 3; f++) { out[t].mean[f] = h[t].mean[f]; out[t].active[f] = h[t].active[f]; }
         out[t].nonfinite = h[t].nonfinite; out[t].negative = h[t].negative;
+    }
+    return TM_OK;
+}
+
+int tm_measure_spread(tm_ctx *c, int c_x, int c_y, tm_spread *out)
+{
+    if (!c || !out) return TM_E_ARG;
+    if (!c->have_state) TM_FAIL(c, TM_E_STATE, "tm_measure_spread: no state uploaded");
+    TM_CUDA(c, cudaSetDevice(c->device));
+    const Geom &g = c->g;
+    if (!c->spread_dev) TM_CUDA(c, cudaMalloc(&c->spread_dev, sizeof(unsigned long long) * 3 * g.n_trials));
+    TM_CUDA(c, cudaMemsetAsync(c->spread_dev, 0, sizeof(unsigned long long) * 3 * g.n_trials, c->stream));
+    long long bpt = g.nrows;
+    const long long cap = (8LL * c->n_sm + g.n_trials - 1) / g.n_trials;
+    if (bpt > cap) bpt = cap;
+    if (bpt < 1) bpt = 1;
+    SpreadArgs A{g, c->buf[c->cur], c->spread_dev, c_x, c_y, (int)bpt};
+    spread_kernel<<<(int)bpt * g.n_trials, 256, 0, c->stream>>>(A);
+    TM_CUDA(c, cudaGetLastError());
+    std::vector<unsigned long long> h(3 * (size_t)g.n_trials);
+    TM_CUDA(c, cudaMemcpyAsync(h.data(), c->spread_dev, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    TM_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < g.n_trials; t++) {
+        out[t].n_active = h[3 * t]; out[t].sq_dist = (double)h[3 * t + 1]; out[t].border = h[3 * t + 2] ? 1 : 0; out[t].pad_ = 0;
     }
     return TM_OK;
 }

@@ -267,6 +267,116 @@ void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, doubl
                  " a , c , L,  t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n", vec, true);
 }
 
+// ---- DP spreading experiments (P/:1145-1305, :1667-1772) -----------------------------------------
+
+void init_solitarytear(double array[], int length) // P/:90-97
+{
+    for (int i = 0; i < length * length; i++) array[i] = 0;
+    const int lhalf = static_cast<int>(length / 2.0);
+    array[length * lhalf + lhalf] = 1;
+}
+
+void spreading_incremental_surv_runs(double A[][4], double X[][3], int size) // P/:230-252
+{
+    for (int i = 0; i < size; i++) {
+        const int r = static_cast<int>(A[i][3] + 1); // number of surviving replicates
+        if (X[i][0] == 0.0) break;                   // non-surviving run: nothing logged from here on
+        A[i][1] = (X[i][0] + (r - 1) * A[i][1]) / r;
+        A[i][2] = (X[i][1] + (r - 1) * A[i][2]) / r;
+        A[i][3] = r;
+    }
+}
+
+void spreading_exp_Dornic_2D(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[], double /*t_max*/, double a,
+                             double b, double D, double sigma, double dt, double dx, int r, int g, int c_x, int c_y)
+{
+    if (t_meas.empty() || r < 1) throw std::invalid_argument("spreading_exp_Dornic_2D: empty t_meas or r < 1");
+    tm_params p{};
+    p.model = TM_MODEL_DP;
+    p.L = g; p.dt = dt; p.dx = dx; p.a = a; p.b = b; p.c = 0.0; p.D = D; p.sigma = sigma;
+    Ctx ctx(p, r);
+    const size_t n = (size_t)g * g;
+    vector<double> host(n * r);
+    for (int j = 0; j < r; j++) memcpy(&host[n * j], Rh0, n * sizeof(double)); // P/:1188-1192
+    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
+    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");
+
+    const int tot_iter = static_cast<int>(1.0 / dt) + 1 + (int)t_meas.size(); // P/:1153
+    vector<double> acc_(4 * (size_t)tot_iter, 0.0);
+    double (*acc)[4] = reinterpret_cast<double (*)[4]>(acc_.data());
+    int ind = 0;
+    for (double t = 0; t <= 1; t += dt) { if (ind < tot_iter) acc[ind][0] = t; ind += 1; } // P/:1163-1166
+    for (size_t i = 0; i < t_meas.size() && ind + (int)i < tot_iter; i++) acc[ind + i][0] = t_meas[i];
+
+    // per-replicate series Rho_M[s] = {N(t), R^2(t), 1}; replicates run side by side as trials, each one stops at its own
+    // border breach (P/:1201-1212) or extinction (P/:1216-1217) -- later states of a stopped trial are simply ignored
+    vector<vector<double>> RhoM(r, vector<double>(3 * (size_t)tot_iter, 0.0));
+    vector<int> s_of(r, 0);
+    vector<char> alive(r, 1);
+    const StepPlan plan = plan_dp(t_meas, dt);
+    vector<tm_spread> sp(r);
+    int breaches = 0;
+    for (size_t k = 0; k < plan.t.size(); k++) {
+        ctx.ck(tm_measure_spread(ctx.c, c_x, c_y, sp.data()), "tm_measure_spread");
+        bool any = false;
+        for (int j = 0; j < r; j++) {
+            if (!alive[j]) continue;
+            if (sp[j].border) { alive[j] = 0; breaches += 1; continue; }
+            if (plan.measure[k]) {
+                if (sp[j].n_active == 0) { alive[j] = 0; continue; }
+                if (s_of[j] < tot_iter) {
+                    double *row = &RhoM[j][3 * (size_t)s_of[j]];
+                    row[0] = (double)sp[j].n_active; row[1] = sp[j].sq_dist / (double)sp[j].n_active; row[2] = 1.0;
+                }
+                s_of[j] += 1;
+            }
+            any = true;
+        }
+        if (!any) break;
+        ctx.ck(tm_step(ctx.c, 1), "tm_step");
+    }
+    for (int j = 0; j < r; j++) { // replicate-order accumulation, P/:1264-1287
+        double (*X)[3] = reinterpret_cast<double (*)[3]>(RhoM[j].data());
+        if (j == 0) {
+            for (int i = 0; i < tot_iter; i++) {
+                acc[i][1] = X[i][0]; acc[i][2] = X[i][1];
+                if (X[i][0] > 0) acc[i][3] = 1; else if (X[i][0] == 0) acc[i][3] = 0;
+            }
+        } else {
+            spreading_incremental_surv_runs(acc, X, tot_iter);
+        }
+    }
+    for (int i = 0; i < tot_iter; i++) // P/:1294-1298; column 0 is the reference's OpenMP thread number
+        Rho.push_back({0.0, a, acc[i][0], acc[i][1], acc[i][2], acc[i][3]});
+    if (!options().quiet) std::cout << "IN SUMMATION WE HAVE A BREACH COUNT OF:\t" << breaches << std::endl;
+}
+
+void critical_exp_theta_delta(double Rho_0[], int div, double t_max, double a_c, double b, double D, double sigma, double dt,
+                              double dx, int r, int g) // P/:1667-1772
+{
+    init_solitarytear(Rho_0, g);
+    const int c_x = static_cast<int>(g / 2), c_y = c_x;
+    vector<double> t_measure = logarithm10_time_bins(t_max, dt);
+    vector<vector<double>> vec;
+    for (int i = 0; i < div; i++) { // the reference's `omp for` over supra-replicates: div batches of r trials each
+        vector<vector<double>> rows;
+        const unsigned long long seed0 = options().seed;
+        options().seed = seed0 + 0x9E3779B97F4A7C15ull * (unsigned long long)i; // independent batches (the reference reseeds per replicate)
+        spreading_exp_Dornic_2D(rows, t_measure, Rho_0, t_max, a_c, b, D, sigma, dt, dx, r, g, c_x, c_y);
+        options().seed = seed0;
+        vec.insert(vec.end(), rows.begin(), rows.end());
+    }
+    std::stringstream L, tm, d3, p1, rini, Sm;
+    L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << std::setprecision(5) << a_c; rini << r; Sm << std::setprecision(3) << sigma;
+    mkdirs(options().data_root + "/Data/SPDP");
+    std::ofstream out(options().data_root + "/Data/SPDP/SPREADING_P_c_ThDel_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str()
+                      + "_a1_" + p1.str() + "_Sig_" + Sm.str() + "_R_" + rini.str() + ".csv"); // P/:1748-1749
+    out << " #, a , t ,  <N(t)>_r, <MSD(N(t))>_r, <P(t)>_r \n";
+    for (size_t i = 0; i < vec.size(); i++) // P/:1758-1760
+        out << vec[i][0] << "," << vec[i][1] << "," << std::setprecision(16) << vec[i][2] << "," << std::setprecision(16) << vec[i][3]
+            << "," << vec[i][4] << "," << vec[i][5] << std::endl;
+}
+
 // ---- Rietkerk SPB = 1 ----------------------------------------------------------------------------
 
 std::vector<double> frame_tmeas;

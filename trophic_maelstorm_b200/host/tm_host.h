@@ -9,7 +9,10 @@
 //   first_order_critical_exp_delta  Percolation_FD/stochasticSPDP.cpp:2422
 //   rietkerk_Dornic_2D_MultiSp      Rietkerk_FD/rietkerk_bjork_basic.cpp:3397   (SPB = 1)
 //   first_order_critical_exp_delta_stochastic_MultiSp   Rietkerk_FD/rietkerk_bjork_basic.cpp:4379
-//   logarithm10_time_bins, linspace, var_mean_incremental_surv_runs, save_frame  (bookkeeping)
+//   spreading_exp_Dornic_2D         Percolation_FD/stochasticSPDP.cpp:1145   (seed-at-centre runs: N(t), R^2(t), P_surv(t))
+//   critical_exp_theta_delta        Percolation_FD/stochasticSPDP.cpp:1667
+//   logarithm10_time_bins, linspace, var_mean_incremental_surv_runs, spreading_incremental_surv_runs,
+//   init_solitarytear, save_frame  (bookkeeping)
 //
 // What is different by construction: replicates run concurrently as trials of one device context
 // instead of a serial `for j<r` loop, and random numbers come from Philox streams keyed by
@@ -47,6 +50,15 @@ void critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, d
                         double sigma, double dt, double dx, int r, int g);
 void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b,
                                     double c, double D, double sigma, double dt, double dx, int r, int g);
+
+// spreading experiments (theta, z exponents): every replicate starts from Rh0 (a single seed at (c_x, c_y)), stops when
+// an active site reaches the border (theborderwall P/:380) or the lattice is empty; rows {thread, a, t, <N>_r, <R^2>_r, #surv}
+void init_solitarytear(double array[], int length);                                                     // P/:90
+void spreading_incremental_surv_runs(double t_N_R2_rep[][4], double X_curr[][3], int size);             // P/:230
+void spreading_exp_Dornic_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_meas, double Rh0[], double t_max,
+                             double a, double b, double D, double sigma, double dt, double dx, int r, int g, int c_x, int c_y);
+void critical_exp_theta_delta(double Rho_0[], int div, double t_max, double a_c, double b, double D, double sigma, double dt,
+                              double dx, int r, int g);                                                  // P/:1667
 
 // ---- Rietkerk, SPB = 1 (Sp = 3 fields: P, W, O) ---------------------------------------------
 constexpr int Sp = 3, SpB = 1;

@@ -38,6 +38,30 @@ int tmh_dp_run(int cubic, int L, double a, double b, double c, double D, double 
     return (int)Rho.size();
 }
 
+// spreading experiment: rows_out[k][6] = {thread, a, t, <N>_r, <R^2>_r, #surviving}
+int tmh_dp_spread_run(int L, double a, double b, double D, double sigma, double dt, double dx, int r, const double *rh0,
+                      const double *t_meas, int n_tmeas, int c_x, int c_y, double *rows_out, int cap)
+{
+    std::vector<std::vector<double>> Rho;
+    std::vector<double> tm(t_meas, t_meas + n_tmeas), r0(rh0, rh0 + (size_t)L * L);
+    try {
+        spreading_exp_Dornic_2D(Rho, tm, r0.data(), tm.back(), a, b, D, sigma, dt, dx, r, L, c_x, c_y);
+    } catch (const std::exception &) { return -2; }
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 6; j++) rows_out[6 * k + j] = Rho[k][j];
+    return (int)Rho.size();
+}
+
+// the theta/z driver (spreading_exp_test.cpp): writes ../Data/SPDP/SPREADING_P_c_ThDel_DP_G_*.csv under data_root
+int tmh_dp_spread_sweep(int L, int div, double t_max, double a_c, double b, double D, double sigma, double dt, double dx, int r)
+{
+    std::vector<double> rho0((size_t)L * L, 0.0);
+    try { critical_exp_theta_delta(rho0.data(), div, t_max, a_c, b, D, sigma, dt, dx, r, L); }
+    catch (const std::exception &) { return -2; }
+    return 0;
+}
+
 int tmh_dp_sweep(int cubic, int L, int div, double t_max, double a_start, double a_end, double b, double c, double D,
                  double sigma, double dt, double dx, int r)
 {

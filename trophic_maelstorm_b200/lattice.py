@@ -35,6 +35,11 @@ class Stats(C.Structure):
                 ("nonfinite", C.c_uint64), ("negative", C.c_uint64)]
 
 
+class Spread(C.Structure):
+    """struct tm_spread."""
+    _fields_ = [("n_active", C.c_uint64), ("sq_dist", C.c_double), ("border", C.c_int32), ("pad_", C.c_int32)]
+
+
 def rietkerk_params(L, a=0.05, dt=0.1, model=MODEL_RIETKERK, fpe_clamp=False):
     """The SPB=1 constants of Rietkerk_FD/order_1stoc_test_rietkerk.cpp:14,28-37,48."""
     p = Params()
@@ -94,6 +99,7 @@ def lib():
         "tm_halo_unpack": (i, [vp, i, vp]),
         "tm_cuda_stream": (vp, [vp]),
         "tm_measure": (i, [vp, C.POINTER(Stats)]),
+        "tm_measure_spread": (i, [vp, i, i, C.POINTER(Spread)]),
         "tm_sampler_overflow": (i, [vp, C.POINTER(u64)]),
         "tm_sync": (i, [vp]),
         "tm_last_step_ms": (i, [vp, C.POINTER(C.c_float), C.POINTER(i)]),
@@ -112,7 +118,7 @@ ABI_SYMBOLS = [
     "tm_abi_version", "tm_device_count", "tm_last_error", "tm_create", "tm_create_slab", "tm_destroy",
     "tm_set_trial_a", "tm_set_strict", "tm_set_fused", "tm_upload", "tm_download", "tm_n_fields", "tm_seed",
     "tm_set_step_counter", "tm_step_counter", "tm_step", "tm_step_replay", "tm_dornic_only",
-    "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream", "tm_measure",
+    "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream", "tm_measure", "tm_measure_spread",
     "tm_sampler_overflow", "tm_sync", "tm_last_step_ms", "tm_set_kernel_timing", "tm_kernel_ms", "tm_run_host",
 ]
 
@@ -199,6 +205,11 @@ class Lattice:
     def measure(self):
         st = (Stats * self.n_trials)()
         self._ck(self._l.tm_measure(self._ctx, st))
+        return st
+
+    def measure_spread(self, c_x, c_y):
+        st = (Spread * self.n_trials)()
+        self._ck(self._l.tm_measure_spread(self._ctx, int(c_x), int(c_y), st))
         return st
 
     def sampler_overflow(self):
