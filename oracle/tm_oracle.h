@@ -124,6 +124,25 @@ void tmo_var_mean_incremental_surv_runs(double *acc, const double *rep, int n, i
 void tmo_spread_stats(const double *x, int g, int c_x, int c_y, double *sq_dist, int64_t *n_active, int *border);
 void tmo_spreading_incremental_surv_runs(double *acc, const double *rep, int n);
 
+/* ---- FKE movement: oracle/tm_oracle_fke.c ---------------------------------------
+ * advdiff_FKE_MultiSp F/:3614-3695, precompute_gaussian F/:1735, set_global_FKE_params F/:195-262. */
+typedef struct tmo_fke_terms {
+    int32_t L;
+    int32_t bound_D;              /* sig_D_ScaledBounds[s] */
+    int32_t v_row_lo, v_row_hi;   /* advection window rows    [mu_x - lo, mu_x + hi] */
+    int32_t v_col_lo, v_col_hi;   /* advection window columns [mu_y - lo, mu_y + hi] */
+    double mu_vel_prefactor;      /* F/:249 */
+    double epsilon;               /* F/ header :119, 1e-10 */
+} tmo_fke_terms;
+typedef struct tmo_fke_derived {
+    double beta_vel, sigma_D, sigma_vD, mu_vel_prefactor;
+    int32_t bound_D, bound_vD_first, bound_vD_second, pad_;
+} tmo_fke_derived;
+void tmo_fke_precompute_gaussian(double sigma, int Rbound, double *out);
+void tmo_fke_params(double D, double v, double Dt, double dx, int CI, tmo_fke_derived *o);
+int tmo_fke_move(const tmo_fke_terms *t, const double *rho, const double *gamma, const double *v_eff,
+                 const double *gD, const double *gV, double *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,18 @@ class ORng(C.Structure):
                 ("_pad2", C.c_int32), ("norm_saved", C.c_double)]
 
 
+class OFkeTerms(C.Structure):
+    """struct tmo_fke_terms."""
+    _fields_ = [("L", C.c_int32), ("bound_D", C.c_int32), ("v_row_lo", C.c_int32), ("v_row_hi", C.c_int32),
+                ("v_col_lo", C.c_int32), ("v_col_hi", C.c_int32), ("mu_vel_prefactor", C.c_double), ("epsilon", C.c_double)]
+
+
+class OFkeDerived(C.Structure):
+    """struct tmo_fke_derived."""
+    _fields_ = [("beta_vel", C.c_double), ("sigma_D", C.c_double), ("sigma_vD", C.c_double), ("mu_vel_prefactor", C.c_double),
+                ("bound_D", C.c_int32), ("bound_vD_first", C.c_int32), ("bound_vD_second", C.c_int32), ("pad_", C.c_int32)]
+
+
 _lib = None
 
 
@@ -69,6 +81,11 @@ def oracle():
         L.tmo_spreading_incremental_surv_runs.restype = None
         L.tmo_spreading_incremental_surv_runs.argtypes = [dp, dp, C.c_int]
         L.tmo_var_mean_incremental_surv_runs.argtypes = [dp, dp, C.c_int, C.c_int]
+        L.tmo_fke_precompute_gaussian.restype = None
+        L.tmo_fke_precompute_gaussian.argtypes = [C.c_double, C.c_int, dp]
+        L.tmo_fke_params.restype = None
+        L.tmo_fke_params.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(OFkeDerived)]
+        L.tmo_fke_move.argtypes = [C.POINTER(OFkeTerms), dp, dp, dp, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -147,3 +164,29 @@ def synthetic_rietkerk_frame(L, seed=1234, a=0.05, dP=10000.0, fringe=True):
     f[1] = Wstar * a
     f[2] = 120.4744181 * a + 0.58243061
     return f
+
+
+def fke_gaussian(sigma, R):
+    """precompute_gaussian, F/:1735."""
+    out = np.zeros(R + 1)
+    oracle().tmo_fke_precompute_gaussian(sigma, R, ptr(out))
+    return out
+
+
+def fke_params(D, v, Dt, dx, CI=4):
+    """set_global_FKE_params for one species, F/:195-262."""
+    d = OFkeDerived()
+    oracle().tmo_fke_params(D, v, Dt, dx, CI, C.byref(d))
+    return d
+
+
+def fke_move(L, bound_D, rows, cols, prefactor, eps, rho, gamma, veff, gD, gV):
+    """advdiff_FKE_MultiSp for one species, F/:3614; rows/cols = (lo, hi) of the advection window."""
+    t = OFkeTerms(L, bound_D, rows[0], rows[1], cols[0], cols[1], prefactor, eps)
+    rho, gamma, veff = (np.ascontiguousarray(a, dtype=np.float64) for a in (rho, gamma, veff))
+    gD, gV = np.ascontiguousarray(gD, dtype=np.float64), np.ascontiguousarray(gV, dtype=np.float64)
+    assert gD.size >= bound_D + 1 and gV.size >= max(rows + cols) + 1
+    out = np.empty(L * L)
+    rc = oracle().tmo_fke_move(C.byref(t), ptr(rho), ptr(gamma), ptr(veff), ptr(gD), ptr(gV), ptr(out))
+    assert rc == 0
+    return out
