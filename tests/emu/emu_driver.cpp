@@ -3,7 +3,9 @@
 // C-ABI layer uses (csrc/tm_host_setup.h).  Used by tests/test_kernel_emulation.py to check the
 // marching pipeline, halo logic and decomposition invariance against the oracle without a GPU.
 #include "tm_host_setup.h"
+#include "tm_fke.cuh"
 
+#include <cmath>
 #include <vector>
 
 using namespace tml;
@@ -151,4 +153,27 @@ void emu_geometry(const tm_params *p, int n_trials, int *out /* ns, TX, nthreads
     out[0] = g.ns; out[1] = g.TX; out[2] = g.nthreads; out[3] = g.Lp;
 }
 
+// FKE movement of one species through the product's three kernels (csrc/tm_fke.cuh), launch shapes as tm_fke.cu.
+// terms: {L, bD, rlo, rhi, clo, chi}; out [L*L]; maxdisp_out [2].
+int emu_fke_move(const int *terms, double pref, double eps, const double *rho, const double *gamma, const double *veff,
+                 const double *gD, const double *gV, double *out, int *maxdisp_out)
+{
+    FkeArgs A{};
+    A.t.L = terms[0]; A.t.bD = terms[1]; A.t.rlo = terms[2]; A.t.rhi = terms[3]; A.t.clo = terms[4]; A.t.chi = terms[5];
+    A.t.pref = pref; A.t.eps = eps;
+    const size_t n = (size_t)A.t.L * A.t.L;
+    std::vector<double> sA(n), sB(n), sD(n), U1(n), U2(n);
+    std::vector<int> disp(n);
+    int maxdisp[2] = {0, 0};
+    A.rho = rho; A.gamma = gamma; A.veff = veff; A.out = out;
+    A.sA = sA.data(); A.sB = sB.data(); A.sD = sD.data(); A.disp = disp.data(); A.maxdisp = maxdisp;
+    A.U1 = U1.data(); A.U2 = U2.data(); A.gD = gD; A.gV = gV;
+    emu_launch(fke_prepare_kernel, A, 3, 64, 0);
+    const int tiles = (A.t.L + kFkeThreads - 1) / kFkeThreads;
+    emu_launch(fke_cols_kernel, A, (unsigned)(tiles * A.t.L), kFkeThreads, fke_cols_smem_doubles(A.t) * sizeof(double));
+    emu_launch(fke_rows_kernel, A, (unsigned)(tiles * A.t.L), kFkeThreads,
+               (size_t)(A.t.bD + 1 + fke_max3(A.t.rlo, A.t.rhi, 0) + 1) * sizeof(double));
+    maxdisp_out[0] = maxdisp[0]; maxdisp_out[1] = maxdisp[1];
+    return 0;
+}
 }

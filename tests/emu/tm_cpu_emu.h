@@ -25,6 +25,13 @@ inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 
+inline int atomicMax(int *p, int v)
+{
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+
 namespace tml {
 // mbarrier stand-in: the 64-bit word holds {pending bytes : 32 | completed phases : 32}.
 // Only one thread (tid 0) arms and copies, synchronously; waiters acquire-load.

@@ -11,3 +11,4 @@ from .lattice import (  # noqa: F401
     Lattice, Params, Stats, Spread, TmError, lib, lib_path, rietkerk_params, dp_params,
     MODEL_DP, MODEL_DP_CUBIC, MODEL_RIETKERK, MODEL_RIETKERK_DET,
 )
+from .fke import FkeMover, FkeTerms, FKE_ABI_SYMBOLS  # noqa: F401,E402
