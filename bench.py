@@ -363,6 +363,73 @@ def run_dp_extra(a):
     lat.close()
 
 
+def run_fke_extra(a):
+    """Not the headline: the FKE movement step of one consumer species, L x L, through include/tm_fke.h.
+    A "site-update" here = one lattice site moved once.  Algorithmic bytes: rho, gamma (8 B each) and v_eff (16 B) read,
+    rho written (8 B) = 40 B per site; the reference's own CPU advdiff_FKE_MultiSp is timed beside it."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import trophic_maelstorm_b200 as tm
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    L, K, W = a.L, a.steps, max(a.warmup, 3)
+    bD, bV, pref = a.fke_bound_d, a.fke_bound_v, 0.82
+    rng = np.random.default_rng(5)
+    rho = rng.gamma(2.0, 3.0, L * L); rho[rng.random(L * L) < 0.3] = 0.0
+    gamma = rng.random(L * L); veff = (rng.random((L * L, 2)) * 2 - 1) * 1.2
+    gD, gV = O.fke_gaussian(1.0, bD), O.fke_gaussian(1.0, bV)   # stencil tables only (host set-up, as the reference's runner does)
+    m = tm.FkeMover(L, 1, device=0)
+    m.set_terms(0, bD, (bV, bV), (bV, bV), pref, 1e-10, gD, gV)
+    dev = torch.device("cuda:0")
+    d = [torch.from_numpy(x).to(dev) for x in (rho, gamma, veff)]
+    out = torch.empty(L * L, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(W):
+        m.move_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), out.data_ptr())
+    m.sync()
+    tot = 0.0
+    for _ in range(K):   # inputs (537 MB) + scratch exceed the L2 at L = 4096
+        m.move_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), out.data_ptr())
+        ms, n = m.last_ms()
+        tot += ms
+    ms = tot / K
+    t0 = time.perf_counter()
+    for _ in range(3):
+        res = m.move(rho, gamma, veff)
+    te = (time.perf_counter() - t0) / 3
+    peak, src = measured_peaks()
+    rate = L * L / (ms * 1e-3)
+    line = {"metric": "lattice sites moved/sec (FP64, device-timed), FKE movement step", "value": rate, "unit": "sites/s", "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": ms, "dtype": "f64", "data": "synthetic", "gpu_launches": 3 * K,
+            "config": {"workload": "FKE movement (advdiff_FKE_MultiSp / updateMovement), 1 species, L=%d, bound_D=%d, bound_vD=%d, "
+                                   "displacements within +-1" % (L, bD, bV), "max_displacement": list(m.last_displacement(0))},
+            "roofline": {"bound": "hbm", "achieved": rate * 40 / 1e9, "peak": peak, "unit": "GB/s", "frac": rate * 40 / 1e9 / peak,
+                         "traffic": None, "peak_source": src, "note": "40 B per site algorithmic; three passes (prepare, columns, rows)"},
+            "e2e": {"value": L * L / te, "unit": "sites/s", "h2d_bytes_per_step": 32 * L * L, "d2h_bytes_per_step": 8 * L * L,
+                    "call": "tm_fke_move_host (pageable numpy buffers)"}}
+    if not a.no_cpu:
+        Lc = min(L, 1024)
+        sl = lambda x, tail=(): np.ascontiguousarray(x.reshape((L, L) + tail)[:Lc, :Lc]).reshape((Lc * Lc,) + tail)
+        r_, g_, v_ = sl(rho), sl(gamma), sl(veff, (2,))
+        refso = os.path.join(ROOT, "oracle", "_ref", "libtm_ref_fke.so")
+        t0 = time.perf_counter()
+        if os.path.exists(refso):
+            ref = C.CDLL(refso); kind = "reference"
+            ref.ref_fke_override(C.c_int(bD), C.c_int(bV), C.c_int(bV), C.c_double(pref), C.c_int(Lc))
+            o = np.zeros(Lc * Lc); dp = C.POINTER(C.c_double); P = lambda x: x.ctypes.data_as(dp)
+            t0 = time.perf_counter()
+            ref.ref_fke_advdiff(C.c_int(Lc), P(r_), P(g_), P(v_), P(gD), C.c_int(gD.size), P(gV), C.c_int(gV.size), P(o))
+        else:
+            kind = "port"
+            o = O.fke_move(Lc, bD, (bV, bV), (bV, bV), pref, 1e-10, r_, g_, v_, gD, gV)
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": Lc * Lc / tc, "unit": "sites/s", "cores": 1, "kind": kind,
+                                "sample": "advdiff_FKE_MultiSp on the L=%d corner of the same inputs, one call (the reference's loop is serial)" % Lc}
+    print(json.dumps(line), flush=True)
+    m.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,10 +442,14 @@ def main():
     ap.add_argument("--ref-L", type=int, default=512, help="lattice side of the bounded CPU sample")
     ap.add_argument("--ref-steps", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp"], help="dp: extra, non-headline line")
+    ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke"], help="dp, fke: extra, non-headline lines")
+    ap.add_argument("--fke-bound-d", type=int, default=1, help="fke: diffusion window half-width (the SPB=2 driver's constants give 1)")
+    ap.add_argument("--fke-bound-v", type=int, default=1, help="fke: advection window half-width")
     a = ap.parse_args()
     if a.workload == "dp" and a.impl == "ours":
         return run_dp_extra(a)
+    if a.workload == "fke" and a.impl == "ours":
+        return run_fke_extra(a)
     if a.impl == "reference":
         run_reference_arm(a)
     else:

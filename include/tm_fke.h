@@ -43,13 +43,18 @@ typedef struct tm_fke_terms {
 
 typedef struct tm_fke_ctx tm_fke_ctx;
 
-/* L x L periodic lattice, n_species moving species (grazer[, predator]); binds `device` and one stream. */
+/* L x L periodic lattice, n_species moving species (grazer[, predator]); binds `device` and one stream.
+ * The stream is a blocking one: it orders itself against the legacy default stream like the reference's launch
+ * (cudaMemset before it, cudaMemcpy after it, F/:4292-4299). */
 int tm_fke_create(int L, int n_species, int device, tm_fke_ctx **out);
 int tm_fke_destroy(tm_fke_ctx *);
 const char *tm_fke_last_error(const tm_fke_ctx *); /* ctx == NULL: error of the last failed tm_fke_create on this thread */
 
 /* Window bounds, prefactor and the two Gaussian stencils (host pointers) of species s in [0, n_species). */
 int tm_fke_set_terms(tm_fke_ctx *, int s, const tm_fke_terms *t, const double *gauss_D, const double *gauss_V);
+
+/* The same with the stencils already resident on the device (the reference uploads them once per run, F/:3775-3800). */
+int tm_fke_set_terms_device(tm_fke_ctx *, int s, const tm_fke_terms *t, const double *d_gauss_D, const double *d_gauss_V);
 
 /* One movement step of every species with HOST buffers: rho, gamma, rho_out [n_species][L*L]; v_eff [n_species][L*L][2]
  * ({first, second} = {row, column} velocity, the memory layout of std::pair<double,double>).  Uploads, moves, downloads. */

@@ -86,7 +86,7 @@ int tm_fke_create(int L, int n_species, int device, tm_fke_ctx **out)
     cudaDeviceProp prop;
     CR(cudaGetDeviceProperties(&prop, device));
     c->n_sm = prop.multiProcessorCount;
-    CR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CR(cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault));
     CR(cudaEventCreate(&c->ev0)); CR(cudaEventCreate(&c->ev1));
     for (int k = 0; k < 3; k++) CR(cudaMalloc(&c->d_s[k], n * sizeof(double)));
     for (int k = 0; k < 2; k++) CR(cudaMalloc(&c->d_U[k], n * sizeof(double)));
@@ -98,7 +98,19 @@ int tm_fke_create(int L, int n_species, int device, tm_fke_ctx **out)
     return TM_OK;
 }
 
+static int fke_set_terms(tm_fke_ctx *c, int s, const tm_fke_terms *t, const double *gauss_D, const double *gauss_V, cudaMemcpyKind kind);
+
 int tm_fke_set_terms(tm_fke_ctx *c, int s, const tm_fke_terms *t, const double *gauss_D, const double *gauss_V)
+{
+    return fke_set_terms(c, s, t, gauss_D, gauss_V, cudaMemcpyHostToDevice);
+}
+
+int tm_fke_set_terms_device(tm_fke_ctx *c, int s, const tm_fke_terms *t, const double *d_gauss_D, const double *d_gauss_V)
+{
+    return fke_set_terms(c, s, t, d_gauss_D, d_gauss_V, cudaMemcpyDeviceToDevice);
+}
+
+static int fke_set_terms(tm_fke_ctx *c, int s, const tm_fke_terms *t, const double *gauss_D, const double *gauss_V, cudaMemcpyKind kind)
 {
     if (!c) return TM_E_ARG;
     if (!t || !gauss_D || !gauss_V || s < 0 || s >= c->n_species) { c->err = "tm_fke_set_terms: bad argument"; return TM_E_ARG; }
@@ -113,8 +125,8 @@ int tm_fke_set_terms(tm_fke_ctx *c, int s, const tm_fke_terms *t, const double *
     cudaFree(c->d_gD[s]); cudaFree(c->d_gV[s]); c->d_gD[s] = c->d_gV[s] = nullptr;
     FKE_CK(cudaMalloc(&c->d_gD[s], t->n_gauss_D * sizeof(double)));
     FKE_CK(cudaMalloc(&c->d_gV[s], t->n_gauss_V * sizeof(double)));
-    FKE_CK(cudaMemcpy(c->d_gD[s], gauss_D, t->n_gauss_D * sizeof(double), cudaMemcpyHostToDevice));
-    FKE_CK(cudaMemcpy(c->d_gV[s], gauss_V, t->n_gauss_V * sizeof(double), cudaMemcpyHostToDevice));
+    FKE_CK(cudaMemcpy(c->d_gD[s], gauss_D, t->n_gauss_D * sizeof(double), kind));
+    FKE_CK(cudaMemcpy(c->d_gV[s], gauss_V, t->n_gauss_V * sizeof(double), kind));
     c->terms[s] = *t; c->have_terms[s] = 1;
     return TM_OK;
 }
@@ -137,10 +149,7 @@ static int fke_launch_all(tm_fke_ctx *c, const double *d_rho, const double *d_ga
         A.rho = d_rho + s * n; A.gamma = d_gamma + s * n; A.veff = d_veff + 2 * s * n; A.out = d_out + s * n;
         A.sA = c->d_s[0]; A.sB = c->d_s[1]; A.sD = c->d_s[2]; A.disp = c->d_disp; A.maxdisp = c->d_maxdisp + 2 * s;
         A.U1 = c->d_U[0]; A.U2 = c->d_U[1]; A.gD = c->d_gD[s]; A.gV = c->d_gV[s];
-        long long pb = ((long long)n + 255) / 256;
-        const long long cap = (long long)c->n_sm * 8;      // grid-stride: a multiple of the SM count
-        if (pb > cap) pb = cap;
-        fke_prepare_kernel<<<(unsigned)pb, 256, 0, c->stream>>>(A);
+        fke_prepare_kernel<<<(unsigned)c->L, 256, 0, c->stream>>>(A);   // one CTA per lattice row
         const size_t smem_c = fke_cols_smem_doubles(A.t) * sizeof(double);
         const size_t smem_r = (size_t)(A.t.bD + 1 + fke_max3(A.t.rlo, A.t.rhi, 0) + 1) * sizeof(double);
         fke_cols_kernel<<<(unsigned)((long long)tiles * c->L), kFkeThreads, smem_c, c->stream>>>(A);

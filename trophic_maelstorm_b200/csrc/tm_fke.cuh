@@ -66,29 +66,30 @@ TMF_HD int fke_max3(int a, int b, int c) { int m = a > b ? a : b; return m > c ?
 TMF_G void fke_prepare_kernel(const FkeArgs A)
 {
     const int g = A.t.L;
-    const long long n = (long long)g * g;
-    const long long stride = (long long)gridDim.x * blockDim.x;
     int mx = 0, my = 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double r = A.rho[i];
-        double a = 0.0, b = 0.0, d = 0.0;
-        int ex = 0, ey = 0;
-        if (!(r < A.t.eps)) {
-            const double gm = A.gamma[i], gm2 = gm * gm;
-            a = gm2 * r; b = (gm - gm2) * r; d = (1 - gm) * (1 - gm) * r;
-            const int c_i = (int)(i / g), c_j = (int)(i % g);
-            // (int)(round(c + v * prefactor) + g) % g in the reference; a true modulo here (the reference indexes
-            // out of bounds when the left side is negative, i.e. for |v * prefactor| > L)
-            const int mu_x = fke_mod((int)(round(c_i + A.veff[2 * i] * A.t.pref) + g), g);
-            const int mu_y = fke_mod((int)(round(c_j + A.veff[2 * i + 1] * A.t.pref) + g), g);
-            ex = mu_x - c_i; ey = mu_y - c_j;                    // representative in [-(g-1)/2, g/2]
-            if (ex > g / 2) ex -= g; else if (ex < -((g - 1) / 2)) ex += g;
-            if (ey > g / 2) ey -= g; else if (ey < -((g - 1) / 2)) ey += g;
-            const int ax = ex < 0 ? -ex : ex, ay = ey < 0 ? -ey : ey;
-            mx = ax > mx ? ax : mx; my = ay > my ? ay : my;
+    // a CTA walks whole rows (no division to recover (row, column) from a flat index)
+    for (int c_i = blockIdx.x; c_i < g; c_i += gridDim.x) {
+        for (int c_j = threadIdx.x; c_j < g; c_j += blockDim.x) {
+            const int i = c_i * g + c_j;
+            const double r = A.rho[i];
+            double a = 0.0, b = 0.0, d = 0.0;
+            int ex = 0, ey = 0;
+            if (!(r < A.t.eps)) {
+                const double gm = A.gamma[i], gm2 = gm * gm;
+                a = gm2 * r; b = (gm - gm2) * r; d = (1 - gm) * (1 - gm) * r;
+                // (int)(round(c + v * prefactor) + g) % g in the reference; a true modulo here (the reference indexes
+                // out of bounds when the left side is negative, i.e. for |v * prefactor| > L)
+                const int mu_x = fke_mod((int)(round(c_i + A.veff[2 * i] * A.t.pref) + g), g);
+                const int mu_y = fke_mod((int)(round(c_j + A.veff[2 * i + 1] * A.t.pref) + g), g);
+                ex = mu_x - c_i; ey = mu_y - c_j;                    // representative in [-(g-1)/2, g/2]
+                if (ex > g / 2) ex -= g; else if (ex < -((g - 1) / 2)) ex += g;
+                if (ey > g / 2) ey -= g; else if (ey < -((g - 1) / 2)) ey += g;
+                const int ax = ex < 0 ? -ex : ex, ay = ey < 0 ? -ey : ey;
+                mx = ax > mx ? ax : mx; my = ay > my ? ay : my;
+            }
+            A.sA[i] = a; A.sB[i] = b; A.sD[i] = d;
+            A.disp[i] = fke_pack(ex, ey);
         }
-        A.sA[i] = a; A.sB[i] = b; A.sD[i] = d;
-        A.disp[i] = fke_pack(ex, ey);
     }
     if (mx > 0) atomicMax(&A.maxdisp[0], mx);
     if (my > 0) atomicMax(&A.maxdisp[1], my);
@@ -117,26 +118,34 @@ TMF_G void fke_cols_kernel(const FkeArgs A)
     for (int k = tid; k <= t.bD; k += kFkeThreads) gD[k] = A.gD[k];
     for (int k = tid; k < nV; k += kFkeThreads) gV[k] = A.gV[k];
     const int Rx = A.maxdisp[0], Ry = A.maxdisp[1];
-    const long long rowx = (long long)x * g;
+    // Index arithmetic: 32-bit throughout (L <= 32767, so L*L < 2^30) and periodic indices walked with a conditional
+    // wrap -- an integer division and a 64-bit address per candidate source made this pass instruction-bound
+    // (1100 warp instructions per 32 sites, 0.85 ms at L = 4096).  Candidates are read unconditionally and selected,
+    // so the gather has no branches.
+    const int rowx = x * g;
+    const int xs0 = fke_mod(x + Rx, g);                    // first candidate row: x - ex for ex = -Rx
+    const int ybase = fke_mod(y0 - Hc, g);
+    const int *__restrict__ disp = A.disp;
+    const double *__restrict__ sB = A.sB, *__restrict__ sD = A.sD;
     for (int k = tid; k < W; k += kFkeThreads) {
-        const int y = fke_mod(y0 - Hc + k, g);
+        int y = ybase + k; if (y >= g) y %= g;
+        int ys0 = y + Ry; if (ys0 >= g) ys0 -= g;          // first candidate column: y - ey for ey = -Ry  (Ry <= g/2)
         double b = 0.0, c = 0.0, d = 0.0;
         // sources whose displaced copy lands on (x, y): (x - ex, y - ey) with disp == (ex, ey); ex = 0 for T_B, ey = 0 for T_C.
         // The undisplaced axis is NOT tested: term B uses only e_y of the source, term C only e_x (F/:3656, :3672).
-        for (int ey = -Ry; ey <= Ry; ey++) {
-            const long long s = rowx + fke_mod(y - ey, g);
-            if ((A.disp[s] >> 16) == ey) b += A.sB[s];
+        for (int ey = -Ry, ys = ys0; ey <= Ry; ey++) {
+            const int s = rowx + ys;
+            b += ((disp[s] >> 16) == ey) ? sB[s] : 0.0;
+            ys = ys == 0 ? g - 1 : ys - 1;
         }
-        for (int ex = -Rx; ex <= Rx; ex++) {
-            const long long s = (long long)fke_mod(x - ex, g) * g + y;
-            if ((int)(short)(A.disp[s] & 0xFFFF) == ex) c += A.sB[s];
-        }
-        for (int ex = -Rx; ex <= Rx; ex++) {
-            const long long rs = (long long)fke_mod(x - ex, g) * g;
-            for (int ey = -Ry; ey <= Ry; ey++) {
-                const long long s = rs + fke_mod(y - ey, g);
-                if (A.disp[s] == fke_pack(ex, ey)) d += A.sD[s];
+        for (int ex = -Rx, xs = xs0; ex <= Rx; ex++) {
+            const int rs = xs * g;
+            c += ((int)(short)(disp[rs + y] & 0xFFFF) == ex) ? sB[rs + y] : 0.0;
+            for (int ey = -Ry, ys = ys0; ey <= Ry; ey++) {
+                d += (disp[rs + ys] == fke_pack(ex, ey)) ? sD[rs + ys] : 0.0;
+                ys = ys == 0 ? g - 1 : ys - 1;
             }
+            xs = xs == 0 ? g - 1 : xs - 1;
         }
         TA[k] = A.sA[rowx + y]; TB[k] = b; TC[k] = c; TD[k] = d;
     }
@@ -172,9 +181,15 @@ TMF_G void fke_rows_kernel(const FkeArgs A)
     __syncthreads();
     if (y >= g) return;
     double acc = 0.0;
-    for (int d = -t.bD; d <= t.bD; d++) acc += gD[d < 0 ? -d : d] * A.U1[(long long)fke_mod(x - d, g) * g + y];
-    for (int d = -t.rlo; d <= t.rhi; d++) acc += gV[d < 0 ? -d : d] * A.U2[(long long)fke_mod(x - d, g) * g + y];
-    A.out[(long long)x * g + y] = acc;
+    for (int d = -t.bD, xs = fke_mod(x + t.bD, g); d <= t.bD; d++) {       // source row x - d, walked with a conditional wrap
+        acc += gD[d < 0 ? -d : d] * A.U1[xs * g + y];
+        xs = xs == 0 ? g - 1 : xs - 1;
+    }
+    for (int d = -t.rlo, xs = fke_mod(x + t.rlo, g); d <= t.rhi; d++) {
+        acc += gV[d < 0 ? -d : d] * A.U2[xs * g + y];
+        xs = xs == 0 ? g - 1 : xs - 1;
+    }
+    A.out[x * g + y] = acc;
 }
 
 } // namespace tml

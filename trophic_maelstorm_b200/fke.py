@@ -14,7 +14,7 @@ class FkeTerms(C.Structure):
 
 
 FKE_ABI_SYMBOLS = [
-    "tm_fke_create", "tm_fke_destroy", "tm_fke_last_error", "tm_fke_set_terms", "tm_fke_move_host", "tm_fke_move_device",
+    "tm_fke_create", "tm_fke_destroy", "tm_fke_last_error", "tm_fke_set_terms", "tm_fke_set_terms_device", "tm_fke_move_host", "tm_fke_move_device",
     "tm_fke_sync", "tm_fke_cuda_stream", "tm_fke_last_ms", "tm_fke_last_displacement",
 ]
 
@@ -31,6 +31,7 @@ def _lib():
             "tm_fke_destroy": (i, [vp]),
             "tm_fke_last_error": (C.c_char_p, [vp]),
             "tm_fke_set_terms": (i, [vp, i, C.POINTER(FkeTerms), dp, dp]),
+            "tm_fke_set_terms_device": (i, [vp, i, C.POINTER(FkeTerms), vp, vp]),
             "tm_fke_move_host": (i, [vp, dp, dp, dp, dp]),
             "tm_fke_move_device": (i, [vp, vp, vp, vp, vp]),
             "tm_fke_sync": (i, [vp]),

@@ -1,6 +1,7 @@
 // tm_host_capi.cpp -- flat C doors into the C++ host layer (tm_host.h) so the Python tests can
 // drive the reference-signature runners through ctypes.  No logic of its own.
 #include "tm_host.h"
+#include "tm_host_fke.h"
 #include <cmath>
 #include <cstring>
 
@@ -123,4 +124,55 @@ int tmh_riet_sweep(int L, int div, double t_max, double a_start, double a_end, d
     return 0;
 }
 
+// ---- FKE movement (tm_host_fke.h) ------------------------------------------------------------------------------
+// SPB = 2 doors: D[4], v[2], dtAdv[2] as order_2stoc_unity_rietkerk.cpp:202 passes them.
+// out[7] = {beta_vel, sigma_D, sigma_vD.first, mu_vel_prefactor, bound_D, bound_vD.first, bound_vD.second} of species 1
+void tmh_fke_set_params_2sp(const double *D_, const double *v_, const double *dtAdv_, double Dt, double dx, int L, int CI, double *out)
+{
+    double D[4] = {D_[0], D_[1], D_[2], D_[3]}, v[2] = {v_[0], v_[1]}, dtAdv[2] = {dtAdv_[0], dtAdv_[1]};
+    set_global_FKE_params(D, v, dtAdv, Dt, dx, L, CI);     // the reference's call, array sizes deduced
+    const FKEGlobals &G = fke_globals();
+    out[0] = G.beta_vel[1]; out[1] = G.sigma_D[1]; out[2] = G.sigma_vD[1].first; out[3] = G.mu_vel_prefactor[1];
+    out[4] = G.sig_D_ScaledBounds[1]; out[5] = G.sig_vD_ScaledBounds[1].first; out[6] = G.sig_vD_ScaledBounds[1].second;
+}
+
+void tmh_fke_override(int bound_D, int v_first, int v_second, double prefactor)
+{
+    FKEGlobals &G = fke_globals();
+    G.sig_D_ScaledBounds[1] = bound_D; G.sig_vD_ScaledBounds[1] = {v_first, v_second}; G.mu_vel_prefactor[1] = prefactor;
+}
+
+void tmh_fke_precompute_gaussian(double sigma, int Rbound, double *out)
+{
+    const std::vector<double> s = precompute_gaussian(sigma, Rbound);
+    for (int x = 0; x <= Rbound; x++) out[x] = s[x];
+}
+
+// advdiff_FKE_MultiSp with SPB = 2 containers (species 1 moves); returns 0 or -2 on an exception
+int tmh_fke_advdiff_2sp(int g, const double *rho, const double *gamma, const double *v_eff, const double *gD, int nD,
+                        const double *gV, int nV, double *out)
+{
+    const size_t n = (size_t)g * g;
+    D2Vec_Double Rho_t(2, std::vector<double>(n, 0.0)), Rho_tsar(2, std::vector<double>(n, 0.0)), gam(2, std::vector<double>(n, 0.0));
+    D2Vec_Pair_Double veff(2, std::vector<std::pair<double, double>>(n, {0.0, 0.0}));
+    D2Vec_Double sD(2, std::vector<double>(1, 0.0)), sV(2, std::vector<double>(1, 0.0));
+    for (size_t i = 0; i < n; i++) { Rho_t[1][i] = rho[i]; gam[1][i] = gamma[i]; veff[1][i] = {v_eff[2 * i], v_eff[2 * i + 1]}; }
+    sD[1].assign(gD, gD + nD); sV[1].assign(gV, gV + nV);
+    try { advdiff_FKE_MultiSp(Rho_t, Rho_tsar, gam, veff, sD, sV, g); } catch (const std::exception &) { return -2; }
+    for (size_t i = 0; i < n; i++) out[i] = Rho_t[1][i];
+    return 0;
+}
+
+// the -DBARRACUDA seam with caller-owned device pointers (one moving species)
+int tmh_fke_seam_1sp(int L, int bound_D, int bvx, int bvy, double prefactor, void *d_rho, void *d_tsar, void *d_gamma, void *d_veff,
+                     void *d_gD, void *d_gV)
+{
+    const int bD[1] = {bound_D}; const int2_ bV[1] = {{bvx, bvy}}; const double pf[1] = {prefactor}; const int off[1] = {0};
+    if (copyToDeviceConstantMemory_AdvTerms(bD, bV, pf, off, off, 1) != 0) return -1;
+    try {
+        launchAdvDiffKernel_MultiSp((double *)d_rho, (double *)d_tsar, (double *)d_gamma, (std::pair<double, double> *)d_veff,
+                                    (double *)d_gD, (double *)d_gV, L);
+    } catch (const std::exception &) { return -2; }
+    return 0;
+}
 }
