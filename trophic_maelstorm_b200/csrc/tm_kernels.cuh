@@ -755,38 +755,43 @@ riet_dornic_kernel(const DornicArgs A)
             if (g.wrap) { if (r < 0) r += g.L; if (r >= g.L) r -= g.L; return r; }
             return r + kHalo;
         };
-        int pr = prow(ra);
         const long long col = (long long)kHalo + qc;
-        const double *pin = A.in + (long long)trial * g.trial_stride + (long long)pr * g.Lp + col;   // (row, column qc) of P
-        double *pout = A.pstar + (long long)trial * g.field_stride + (long long)pr * g.Lp + col;
-        // the centre column rolls through registers two rows ahead: the load of row+2 is in flight for a whole
-        // iteration (the L2/HBM latency of the row stream is what this kernel would otherwise wait for)
-        long long dn1 = (long long)(prow(ra + 1) - pr) * g.Lp;              // offset from row to row+1
-        int pr1 = prow(ra + 1);                                              // physical row of row+1
-        double Pu = pin[(long long)(prow(ra - 1) - pr) * g.Lp], Pc = pin[0], Pd = pin[dn1];
-        double Pl = pin[-1], Pr = pin[1];                                    // ghost columns cover q = 0 and q = L-1
+        const double *const inT = A.in + (long long)trial * g.trial_stride + col;       // (physical row 0, column qc) of P
+        // rho* has the same row/column layout as a field: its element sits at a fixed offset from the input element
+        const long long odelta = (A.pstar + (long long)trial * g.field_stride) - (A.in + (long long)trial * g.trial_stride);
+        // Three row pointers walk down the column: pc -> row, p1 -> row+1, p2 -> row+2 (physical rows, periodic wrap
+        // applied to p2 only, once per row).  The centre column rolls through registers two rows ahead: the load of
+        // row+2 is in flight for a whole iteration (the L2/HBM latency of the row stream is what this kernel would
+        // otherwise wait for).  The loop is unrolled by two so the pointer and window rotations are renamed away.
+        const double *pc = inT + (long long)prow(ra) * g.Lp, *p1 = inT + (long long)prow(ra + 1) * g.Lp;
+        int pr2 = prow(ra + 2);
+        const double *p2 = inT + (long long)pr2 * g.Lp;
+        const long long wrap_back = (long long)g.L * g.Lp;
+        double Pu = inT[(long long)prow(ra - 1) * g.Lp], Pc = pc[0], Pd = p1[0];
+        double Pl = pc[-1], Pr = pc[1];                                      // ghost columns cover q = 0 and q = L-1
         int grow = g.row0 + ra; if (grow < 0) grow += g.L; if (grow >= g.L) grow -= g.L;
         uint32_t cell = (uint32_t)grow * (uint32_t)g.L + (uint32_t)qc;
         int n_exact = 0;
+#pragma unroll 2
         for (int row = ra; row < rb; row++) {
-            const bool wrap2 = g.wrap && pr1 + 1 == g.L;                     // row+2 wraps to physical row 0
-            const long long dn2 = wrap2 ? -(long long)(g.L - 1) * g.Lp : (long long)g.Lp;
             double Pn = Pd, Pln = Pl, Prn = Pr;
-            if (row + 1 < rb) { Pn = pin[dn1 + dn2]; Pln = pin[dn1 - 1]; Prn = pin[dn1 + 1]; } // for the next iteration
+            if (row + 1 < rb) { Pn = p2[0]; Pln = p1[-1]; Prn = p1[1]; }     // for the next iteration
             const double nbsum = STRICT ? Pu + Pd + Pl + Pr : (Pu + Pd) + (Pl + Pr);    // STRICT: the reference's order R/:3756
             bool needs_exact;
             double pstar = riet_dornic_value<STRICT>(A.dk, A.inv_lambda, A.mu_scale, Pc, nbsum, valid,
                                                      cell, ptrial, A.step, A.rk, logtab, sctab, needs_exact);
             if (needs_exact) { pstar = u2d(kExactMarker); n_exact++; }    // resolved by the second walk below
             if (valid) {
+                double *pout = const_cast<double *>(pc) + odelta;
                 pout[0] = pstar;
                 if (ghost_r) pout[g.L] = pstar;
                 if (ghost_l) pout[-g.L] = pstar;
             }
             Pu = Pc; Pc = Pd; Pd = Pn; Pl = Pln; Pr = Prn;
-            pin += dn1; pout += dn1;
-            dn1 = dn2; pr1 = wrap2 ? 0 : pr1 + 1;
-            if (++grow == g.L) { grow = 0; cell = (uint32_t)qc; } else cell += (uint32_t)g.L;
+            pc = p1; p1 = p2; p2 += g.Lp;
+            if (g.wrap && ++pr2 == g.L) { pr2 = 0; p2 -= wrap_back; }
+            cell += (uint32_t)g.L;
+            if (++grow == g.L) { grow = 0; cell = (uint32_t)qc; }
         }
         // second walk, extinction fringe only: the cells of this thread's run that need the exact Poisson / Gamma
         // samplers (marked above) are redone from their counters, out of the hot loop
