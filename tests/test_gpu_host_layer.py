@@ -205,10 +205,45 @@ def test_rietkerk_sweep_writes_reference_tree(host, tmp_path):
     assert txt[0] == "a_c,  x,  P(x; t), W(x; t), O(x; t) " and len(txt) == 1 + L * L and len(txt[1].split(",")) == 5
     # prelim tables: one per (a, replicate), trailing comma, r+1 in the second column
     pdir = root / "Prelims" / "Stochastic" / "1Sp" / "DiC-NREF-LI_0.05-0.06_dP_10000"
-    prelims = sorted(p.name for p in pdir.iterdir())
+    prelims = sorted(p.name for p in pdir.iterdir() if p.is_file())
     assert len(prelims) == div * r and prelims[0].startswith("PRELIM_AGGRAND_P_c_ID_0_DP_G_32_T_")
     pl = (pdir / prelims[0]).read_text().splitlines()
     assert pl[1].endswith(",") and pl[1].split(",")[1] in ("1", "2") and len(pl) == 2 + nbins - 1 + 0 or len(pl) >= nbins
+
+
+    # time-series checkpoints of every replicate at 60/85/90/95/100 % of the measurement bins (R/:3710, save_prelimfileswrapper R/:3029)
+    ts = sorted(p.name for p in (pdir / "TimeSeries").iterdir())
+    marks = sorted({int(nbins * f) for f in (0.6, 0.85, 0.9, 0.95)} | {nbins - 1})
+    assert len(ts) == div * r * len(marks) and all(n.startswith("PRELIM_TSERIES_P_c_DP_G_32_T_") for n in ts)
+    mine = [n for n in ts if "_dt_0.1_a_0.05_" in n and n.endswith("_R_0.csv")]
+    assert len(mine) == len(marks)
+    tl = max(((pdir / "TimeSeries" / n).read_text().splitlines() for n in mine), key=len)   # the checkpoint at the last bin
+    trow = np.array([[float(x) for x in l.rstrip(",").split(",")] for l in tl[1:]])
+    assert trow.shape == (nbins, 10) and np.all(trow[:, 8] == 1) and np.all(trow[:, 7] == 0)   # one replicate: one survivor, variance 0
+    assert abs(trow[0, 4] - 0.25) < 1e-12
+
+
+@pytest.mark.gpu
+def test_rietkerk_runner_from_burnin_frames(host, tmp_path):
+    """use_burnin_frames (init_burnin_wrapper R/:836): every replicate starts from a saved frame; the t = 0 row of the
+    runner reports that frame's means."""
+    host.tmh_save_frame.argtypes = [C.c_char_p, C.c_char_p, dp, C.c_int, C.c_int, C.c_double]
+    host.tmh_save_frame.restype = None
+    host.tmh_use_burnin.argtypes = [C.c_char_p, C.c_char_p]
+    host.tmh_use_burnin.restype = None
+    L = 32
+    frame = O.synthetic_rietkerk_frame(L, seed=9, fringe=False).reshape(3, -1).copy()
+    host.tmh_save_frame(str(tmp_path).encode(), b"/FRAME_T_76000_a_0.05_R_", O.ptr(frame), L, 0, 0.05)
+    host.tmh_use_burnin(str(tmp_path).encode(), b"/FRAME_T_76000_a_0.05_R_")
+    host.tmh_set_options(0, 5, 0, str(tmp_path).encode())
+    tmv = np.array([0.0, 0.5, 1.0]); rows = np.zeros((64, 10)); ft = np.zeros(1)
+    n = host.tmh_riet_run(L, 0.05, 0.1, 2, None, O.ptr(tmv), len(tmv), O.ptr(ft), 0, None, O.ptr(rows), 64)
+    host.tmh_use_burnin(None, None)
+    assert n == 3
+    back = np.zeros_like(frame)
+    host.tmh_read_frame_csv.argtypes = [C.c_char_p, C.c_int, dp]
+    host.tmh_read_frame_csv(str(tmp_path / "FRAME_T_76000_a_0.05_R_0.csv").encode(), L, O.ptr(back))
+    assert abs(rows[0, 6] - back[0].mean()) <= 1e-12 * back[0].mean() and abs(rows[0, 4] - back[1].mean()) < 1e-12
 
 
 # ---- spreading experiments (SURVEY 8 f4): tm_measure_spread + spreading_exp_Dornic_2D ---------------

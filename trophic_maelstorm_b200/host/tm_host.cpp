@@ -494,6 +494,29 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
     std::stringstream a1, a2, dimitri; a1 << a_st; a2 << a_end; dimitri << dP;
     const std::string subdir = a1.str() + "-" + a2.str() + "_dP_" + dimitri.str();
 
+    vector<char> broke(nt, 0);
+    // save_prelimfileswrapper's table of ONE replicate, R/:3040-3079: var_mean_incremental_surv_runs(temp, Rho_M, index + 1, 0)
+    // on a zeroed table = the vegetation rows up to its first empty bin, the water means everywhere; time in column 0
+    auto write_tseries = [&](const vector<double> &X, const vector<double> &tm_, int idx, double t_now, double a, double a_st_, double a_end_,
+                             double dt_, double dx_, double dP_, double D2, int j, int g_, const std::string &dir) {
+        D2Vec_Double tab(idx + 1, vector<double>(W_, 0.0));
+        for (int i = 0; i <= idx; i++) {
+            const double N = X[2 * Sp * i + 0];
+            if (N == 0.0) break;
+            tab[i][3] = X[2 * Sp * i + 1]; tab[i][4] = 0.0; tab[i][6] = N; tab[i][5] = 1;
+        }
+        for (int i = 0; i <= idx; i++) {
+            tab[i][1] = X[2 * Sp * i + 2 * (Sp - 2) + 1]; tab[i][2] = X[2 * Sp * i + 2 * (Sp - 1) + 1];
+            tab[i][0] = tm_[i];
+        }
+        std::stringstream L, tm, d3, p1;
+        L << g_; tm << t_now; d3 << std::setprecision(3) << dt_; p1 << std::setprecision(5) << a;
+        (void)D2;
+        const std::string pattern = "/PRELIM_TSERIES_P_c_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
+                                  + "_jID_0_R_";   // R/ header :112, R/:3076 (jID = the thread's random ID there)
+        save_prelimframe(tab, dir, pattern, a, a_st_, a_end_, t_now, dt_, dx_, dP_, j, g_, prelimheader, false, false);
+    };
+
     double t = 0; int index = 0; size_t frame_index = 0; int pending = 0;
     while (t < t_end + dt) { // R/:3648
         const bool meas = index < tot_iter && (t == 0 || (t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0)); // R/:3659
@@ -504,9 +527,29 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
             ctx.ck(tm_measure(ctx.c, st.data()), "tm_measure");
             for (int j = 0; j < nt; j++) {
                 if (st[j].nonfinite) { std::cerr << "RHO NAAN PARATHA in trial " << j << " at t=" << t << "\n"; exit(3); } // R/:4206-4276
+                if (broke[j]) continue;   // this replicate left the time loop at an earlier checkpoint: its later rows stay 0 (R/:3714)
                 for (int s = 0; s < Sp; s++) {
                     RhoM[j][2 * Sp * index + 2 * s] = (double)st[j].active[s];
                     RhoM[j][2 * Sp * index + 2 * s + 1] = st[j].mean[s];
+                }
+            }
+            // per-replicate time-series checkpoints, R/:3710-3716 -> save_prelimfileswrapper R/:3029-3140
+            if ((index == int(tot_iter * 0.6) || index == int(tot_iter * 0.85) || index == int(tot_iter * 0.9)
+                                  || index == int(tot_iter * 0.95) || index == int(tot_iter - 1))) {
+                for (int tr = 0; tr < nt; tr++) {
+                    if (broke[tr]) continue;
+                    const double a = a_values[tr / r]; const int j = tr % r;
+                    const bool dead = RhoM[tr][2 * Sp * index + 0] == 0.0;       // no vegetation left: R/:3087
+                    if (write_prelims) write_tseries(RhoM[tr], t_meas, index, t, a, a_st, a_end, dt, dx, dP, D[2], j, g, pdir + subdir + "/TimeSeries");
+                    if (dead) {   // the future checkpoints are written now, with zeros after this time, and the replicate stops
+                        const int range[5] = {int(tot_iter * 0.6), int(tot_iter * 0.85), int(tot_iter * 0.9), int(tot_iter * 0.95), int(tot_iter - 1)};
+                        for (int k = 0; k < 5; k++) {
+                            if (index > range[k] || !write_prelims) continue;
+                            write_tseries(RhoM[tr], t_meas, range[k], t_meas[range[k]], a, a_st, a_end, dt, dx, dP, D[2], j, g,
+                                          pdir + subdir + "/TimeSeries");
+                        }
+                        broke[tr] = 1;
+                    }
                 }
             }
             index += 1;
@@ -651,6 +694,72 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
             for (size_t j = 0; j + 1 < v.size(); j++) out << std::setprecision(16) << v[j] << ",";
             out << std::setprecision(16) << v[v.size() - 1] << std::endl;
         }
+}
+
+
+// ---- burn-in frames (INIT=2): init_csvconstframe R/:909-1015, init_exprtk_readCSVcolumns_frame R/:609-760 ------------
+// Reads one frame CSV in the layout save_frame() writes ("a_c,  x,  P(x; t), W(x; t), O(x; t)": columns located by
+// header name with blanks removed, as R/:665-672 does; a file without a header is taken as a_c, x, P, W, O).
+// frame: 3*g*g doubles (P, W, O).  Returns the number of lattice rows read (g*g on success), -1 if the file cannot be opened,
+// -2 if a named column is missing.
+int read_frame_csv(const std::string &filename, int g, double *frame)
+{
+    std::ifstream in(filename);
+    if (!in.is_open()) { std::cerr << "Error opening file: " << filename << std::endl; return -1; }
+    const size_t n = (size_t)g * g;
+    int col[3] = {2, 3, 4};
+    static const char *names[3] = {"P(x;t)", "W(x;t)", "O(x;t)"};
+    std::string line;
+    size_t row = 0;
+    while (std::getline(in, line)) {
+        if (line.find("a_c") != std::string::npos) {            // header line (R/:941)
+            std::stringstream hs(line); std::string name; int idx = 0; int found[3] = {-1, -1, -1};
+            while (std::getline(hs, name, ',')) {
+                name.erase(std::remove_if(name.begin(), name.end(), [](unsigned char ch) { return std::isspace(ch); }), name.end());
+                for (int k = 0; k < 3; k++) if (name == names[k]) found[k] = idx;
+                idx++;
+            }
+            for (int k = 0; k < 3; k++) { if (found[k] < 0) { std::cerr << "Column missing in CSV file: " << names[k] << " in file " << filename << std::endl; return -2; } col[k] = found[k]; }
+            continue;
+        }
+        if (row >= n) break;
+        std::stringstream ss(line); std::string cell; int idx = 0;
+        while (std::getline(ss, cell, ',')) {
+            for (int k = 0; k < 3; k++)
+                if (idx == col[k]) {
+                    double v = 0;
+                    try { v = std::stod(cell); } catch (const std::exception &) {
+                        std::cerr << "Error: Unable to convert cell value to double. Column index: " << idx << " , for file: " << filename << std::endl;
+                    }
+                    frame[k * n + row] = v;
+                }
+            idx++;
+        }
+        row++;
+    }
+    return (int)row;
+}
+
+void use_default_init_frame() { init_frame = default_init_frame; }
+
+// init_burnin_wrapper R/:836-906: frames "<parendir><pattern><r'>.csv" with r' = (replicate + offset) mod (max replicate + 1);
+// the reference draws the offset from mt19937_64(random_device) (R/:623-631), here it comes from options().seed.
+void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern)
+{
+    init_frame = [parendir, filenamePattern](double *f, int g, int replicate, double, double, double, const double[]) {
+        int maxrep = -1;
+        struct stat sb;
+        while (stat((parendir + filenamePattern + std::to_string(maxrep + 1) + ".csv").c_str(), &sb) == 0) maxrep++;
+        if (maxrep < 0) {
+            std::cerr << "RUN-TIME ERROR: no burn-in frame matches " << parendir << filenamePattern << "<r>.csv. EXITING." << std::endl;
+            exit(5);                                                  // R/:886
+        }
+        unsigned long long s = options().seed ^ 0xB0B1B2B3ull;
+        const int offset = (int)(splitmix(s) % (unsigned long long)(maxrep + 1));
+        const int rr = (replicate + offset) % (maxrep + 1);
+        const int got = read_frame_csv(parendir + filenamePattern + std::to_string(rr) + ".csv", g, f);
+        if (got != g * g) { std::cerr << "RUN-TIME ERROR: burn-in frame has " << got << " rows, expected " << g * g << ". EXITING." << std::endl; exit(5); }
+    };
 }
 
 } // namespace tm_b200

@@ -90,8 +90,14 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
                                                        double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
                                                        int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
                                                        double Gstar = -1.0, double Vstar = -1.0);
+// burn-in frames (the reference's -DINIT=2 path): read_frame_csv parses one frame in save_frame()'s layout
+// (init_csvconstframe R/:909, header matching of init_exprtk_readCSVcolumns_frame R/:609); use_burnin_frames() makes
+// every replicate start from "<parendir><filenamePattern><r>.csv" (init_burnin_wrapper R/:836).
+int read_frame_csv(const std::string &filename, int g, double *frame);
+void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern);
+void use_default_init_frame();   // back to the MFT speckle rule
 extern std::string prefix, prelim_folder, stat_prefix; // R/ header :97-108; empty folders = "<data_root>/Data/Rietkerk/..."
-extern bool write_prelims;                             // per-replicate PRELIM_AGGRAND_*.csv (R/:4327-4349)
+extern bool write_prelims;                             // PRELIM_AGGRAND_*.csv per replicate (R/:4327-4349) and the TimeSeries/PRELIM_TSERIES_* checkpoints (R/:3029)
 extern const std::string prelimheader;                 // rietkerk_bjork_constants_1Sp.h:8-9
 
 } // namespace tm_b200

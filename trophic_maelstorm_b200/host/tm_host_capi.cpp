@@ -175,4 +175,20 @@ int tmh_fke_seam_1sp(int L, int bound_D, int bvx, int bvy, double prefactor, voi
     } catch (const std::exception &) { return -2; }
     return 0;
 }
+
+// ---- burn-in frames -----------------------------------------------------------------------------------------------
+// writes one 3-field frame with save_frame() (6-digit CSV) to <parendir><pattern><r>.csv
+void tmh_save_frame(const char *parendir, const char *pattern, const double *frame, int g, int r, double a)
+{
+    const size_t n = (size_t)g * g;
+    D2Vec_Double fr(Sp, std::vector<double>(n));
+    for (int s = 0; s < Sp; s++) memcpy(fr[s].data(), frame + s * n, n * sizeof(double));
+    save_frame(fr, parendir, pattern, a, a, a, 0.0, 0.1, 0.1, 0.0, r, g);
+}
+int tmh_read_frame_csv(const char *filename, int g, double *frame) { return read_frame_csv(filename, g, frame); }
+// every later Rietkerk run starts from <parendir><pattern><r>.csv (parendir == NULL: back to the MFT speckle default)
+void tmh_use_burnin(const char *parendir, const char *pattern)
+{
+    if (parendir && pattern) use_burnin_frames(parendir, pattern); else use_default_init_frame();
+}
 }
