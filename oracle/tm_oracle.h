@@ -143,6 +143,18 @@ void tmo_fke_params(double D, double v, double Dt, double dx, int CI, tmo_fke_de
 int tmo_fke_move(const tmo_fke_terms *t, const double *rho, const double *gamma, const double *v_eff,
                  const double *gD, const double *gV, double *out);
 
+/* ---- consumer-side operators of the SPB = 2 model (first part): oracle/tm_oracle_consumer.c -------------
+ * calc_gamma_2Sp_NonRefugia R/:2530, f_2Dor_2Sp R/:2445, RK4_Integrate_Stochastic_2Sp R/:2472. */
+typedef struct tmo_cons_params {
+    int32_t L, pad_;
+    double dt, a, c, gmax, alpha, rW, W0, K1, K2;
+    double Dw, Do;            /* Dxd2[2], Dxd2[3] = D[s]/dx^2 of soil and surface water */
+    double A01, H01, E1;      /* A[0][1], H[0][1], E[1] */
+} tmo_cons_params;
+void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
+                          double *gamma);
+int tmo_rk4_2sp(const tmo_cons_params *p, double *f);
+
 #ifdef __cplusplus
 }
 #endif

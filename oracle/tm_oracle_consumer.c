@@ -1,0 +1,81 @@
+/*
+ * oracle/tm_oracle_consumer.c -- CPU ORACLE of two consumer-side operators of the SPB = 2 (vegetation + grazer) model
+ * (first part).  TEST INFRASTRUCTURE, NOT PRODUCT (see tm_oracle.h for who may load this library).
+ *
+ *   calc_gamma_2Sp_NonRefugia        R/:2530-2603   the grazer's perception field gamma (disc average of the vegetation)
+ *   f_2Dor_2Sp                       R/:2445-2470   reaction terms of (P, G, W, O)
+ *   RK4_Integrate_Stochastic_2Sp     R/:2472-2527   classical RK4 over the four fields
+ *   determine_neighbours_Sq4         R/:1609-1628   periodic von-Neumann neighbours
+ * R/ = simulations/Rietkerk_FD/rietkerk_bjork_basic.cpp.
+ *
+ * Parity status: PINNED -- tests/golden/consumer_ops.npz holds outputs of these very functions of the reference compiled
+ * with -DSPB=2 from /root/reference (oracle/Makefile `ref`, oracle/ref_harness_riet2.cpp).
+ */
+#include "tm_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* R/:2530-2603 for the grazer (s = 1, prey s-1 = vegetation).
+ * offsets: the first `new_length` entries {dx, dy} of computeNeighboringSitesCentral(r_max) (R/:1661, sorted by squared
+ * distance), new_length = max(1, int(nVeg_frac^2 * size)) with nVeg_frac clamped to >= 0.35 (R/:2533-2540);
+ * eff = int(fr * fr * new_length) (R/:2569).  gamma is IN/OUT: the reference adds the disc sum onto the value the array
+ * already holds (R/:2581 `gamma[s][i] += ...`, never reset between steps). */
+void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
+                          double *gamma)
+{
+    const double eps = 1.0e-12;                                                     /* R/:2537 */
+    const double rho_inverse = rho_avg_prey >= eps ? 1 / rho_avg_prey : 1 / eps;    /* R/:2548-2549 */
+    for (int i = 0; i < L * L; i++) {
+        const int c_i = i / L, c_j = i % L;
+        if (rho_avg_self < eps) { gamma[i] = 0.0; continue; }                        /* R/:2575 */
+        else if (rho_avg_prey < eps) { gamma[i] = 0.0; continue; }                   /* R/:2577 */
+        for (int k = 0; k < eff; k++) {                                              /* R/:2580-2581, neighbours R/:1700-1702 */
+            const int nx = (c_i + offsets[2 * k] + L) % L, ny = (c_j + offsets[2 * k + 1] + L) % L;
+            gamma[i] += prey[nx * L + ny];
+        }
+        gamma[i] = (gamma[i] * rho_inverse) / (eff);                                 /* R/:2583 */
+        if (gamma[i] > 1) gamma[i] = 1.0;                                            /* R/:2585-2588 */
+        else if (gamma[i] < 0) gamma[i] = 0.0;
+    }
+}
+
+/* f_2Dor_2Sp R/:2445-2470; fields [0]=P, [1]=G, [2]=W, [3]=O */
+static void f_2dor_2sp(const tmo_cons_params *p, double *f, const double *Y)
+{
+    const int g = p->L, n = g * g;
+    const double cgmax = p->c * p->gmax, A01H01 = p->A01 * p->H01, EA1 = p->E1 * p->A01;   /* R/:2452 */
+    const double *P = Y, *G = Y + n, *W = Y + 2 * n, *O = Y + 3 * n;
+    for (int i = 0; i < n; i++) {
+        const int r = i / g, q = i % g;
+        const int up = ((r - 1) % g + g) % g * g + q, dn = ((r + 1) % g + g) % g * g + q;   /* R/:1622-1626 */
+        const int lf = r * g + ((q - 1) % g + g) % g, rt = r * g + ((q + 1) % g + g) % g;
+        f[i] = cgmax * W[i] * P[i] / (W[i] + p->K1) - (p->A01 * P[i] / (1 + A01H01 * P[i])) * G[i];                     /* R/:2460 */
+        f[n + i] = (EA1 * P[i] / (1 + A01H01 * P[i])) * G[i];                                                          /* R/:2462 */
+        f[2 * n + i] = p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i] - p->gmax * W[i] * P[i] / (W[i] + p->K1) - p->rW * W[i]
+                     + (p->Dw) * (W[up] + W[dn] + W[lf] + W[rt] - 4 * W[i]);                                           /* R/:2464-2465 */
+        f[3 * n + i] = p->a - p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i]
+                     + (p->Do) * (O[up] + O[dn] + O[lf] + O[rt] - 4 * O[i]);                                           /* R/:2467-2468 */
+    }
+}
+
+/* RK4_Integrate_Stochastic_2Sp R/:2472-2527: one step in place on f[4][L*L] */
+int tmo_rk4_2sp(const tmo_cons_params *p, double *f)
+{
+    if (!p || p->L < 1) return -1;
+    const size_t n4 = (size_t)4 * p->L * p->L;
+    const double dt2 = p->dt / 2.0, dt6 = p->dt / 6.0;                               /* R/:171 */
+    double *K1 = malloc(sizeof(double) * n4 * 5), *K2 = K1 + n4, *K3 = K2 + n4, *K4 = K3 + n4, *Y = K4 + n4;
+    if (!K1) return -1;
+    f_2dor_2sp(p, K1, f);
+    for (size_t i = 0; i < n4; i++) Y[i] = f[i] + (dt2) * K1[i];
+    f_2dor_2sp(p, K2, Y);
+    for (size_t i = 0; i < n4; i++) Y[i] = f[i] + (dt2) * K2[i];
+    f_2dor_2sp(p, K3, Y);
+    for (size_t i = 0; i < n4; i++) Y[i] = f[i] + (p->dt) * K3[i];
+    f_2dor_2sp(p, K4, Y);
+    for (size_t i = 0; i < n4; i++) f[i] += (dt6) * (K1[i] + 2.0 * K2[i] + 2.0 * K3[i] + K4[i]);   /* R/:2506 */
+    free(K1);
+    return 0;
+}

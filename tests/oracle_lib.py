@@ -37,6 +37,11 @@ class OFkeDerived(C.Structure):
                 ("bound_D", C.c_int32), ("bound_vD_first", C.c_int32), ("bound_vD_second", C.c_int32), ("pad_", C.c_int32)]
 
 
+class OConsParams(C.Structure):
+    """struct tmo_cons_params."""
+    _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1".split()]
+
+
 _lib = None
 
 
@@ -86,6 +91,9 @@ def oracle():
         L.tmo_fke_params.restype = None
         L.tmo_fke_params.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(OFkeDerived)]
         L.tmo_fke_move.argtypes = [C.POINTER(OFkeTerms), dp, dp, dp, dp, dp, dp]
+        L.tmo_gamma_perception.restype = None
+        L.tmo_gamma_perception.argtypes = [C.c_int, dp, C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, dp]
+        L.tmo_rk4_2sp.argtypes = [C.POINTER(OConsParams), dp]
         _lib = L
     return _lib
 
@@ -190,3 +198,31 @@ def fke_move(L, bound_D, rows, cols, prefactor, eps, rho, gamma, veff, gD, gV):
     rc = oracle().tmo_fke_move(C.byref(t), ptr(rho), ptr(gamma), ptr(veff), ptr(gD), ptr(gV), ptr(out))
     assert rc == 0
     return out
+
+
+def cons_params(L, par):
+    """par = {dt, dx, a, c, gmax, alpha, rW, W0, K1, K2, D2, D3, A01, H01, E1} (tests/golden/make_consumer_golden.py)."""
+    dt, dx, a, c, gmax, alpha, rW, W0, K1, K2, D2, D3, A01, H01, E1 = [float(x) for x in par]
+    return OConsParams(L, 0, dt, a, c, gmax, alpha, rW, W0, K1, K2, D2 / (dx * dx), D3 / (dx * dx), A01, H01, E1)
+
+
+def gamma_window(n_central, fr, nveg_frac):
+    """(new_length, eff) of calc_gamma_2Sp_NonRefugia, R/:2533-2540, :2569."""
+    nveg_frac = max(nveg_frac, 0.35)
+    new_length = max(int(nveg_frac * nveg_frac * n_central), 1)
+    return new_length, int(fr * fr * new_length)
+
+
+def gamma_perception(L, prey, offsets, eff, avg_prey, avg_self, gamma0):
+    g = np.ascontiguousarray(gamma0, dtype=np.float64).copy()
+    prey = np.ascontiguousarray(prey, dtype=np.float64)
+    off = np.ascontiguousarray(offsets, dtype=np.int32)
+    oracle().tmo_gamma_perception(L, ptr(prey), off.ctypes.data_as(C.POINTER(C.c_int32)), eff, avg_prey, avg_self, ptr(g))
+    return g
+
+
+def rk4_2sp(p, fields, steps=1):
+    f = np.ascontiguousarray(fields, dtype=np.float64).copy()
+    for _ in range(steps):
+        assert oracle().tmo_rk4_2sp(C.byref(p), ptr(f)) == 0
+    return f

@@ -1,0 +1,35 @@
+"""Consumer-side operators of the SPB = 2 model (first part): the oracle restatement against the reference's own
+outputs (tests/golden/consumer_ops.npz, made by tests/golden/make_consumer_golden.py from oracle/_ref/libtm_ref_riet2.so)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "consumer_ops.npz"))
+
+
+@pytest.mark.parametrize("name", ["gamma_full", "gamma_sparse", "gamma_small", "gamma_dead"])
+def test_gamma_perception_matches_reference(name):
+    L, R, fr, nveg = GOLD[name + "_cfg"]
+    L, R = int(L), int(R)
+    central = GOLD["central_R%d" % R]
+    new_length, eff = O.gamma_window(len(central), float(fr), float(nveg))
+    avg = GOLD[name + "_avg"]
+    got = O.gamma_perception(L, GOLD[name + "_veg"], central[:new_length], eff, avg[0], avg[1], GOLD[name + "_g0"])
+    want = GOLD[name + "_out"]
+    assert np.array_equal(got, want), np.abs(got - want).max()     # same additions in the same order: bit for bit
+    assert got.min() >= 0.0 and got.max() <= 1.0
+
+
+@pytest.mark.parametrize("name", ["rk4_a", "rk4_b"])
+def test_rk4_2sp_matches_reference(name):
+    L, steps = [int(x) for x in GOLD[name + "_cfg"]]
+    p = O.cons_params(L, GOLD["rk4_par"])
+    got = O.rk4_2sp(p, GOLD[name + "_in"], steps)
+    want = GOLD[name + "_out"]
+    # the reference build contracts a*b+c into FMAs, the oracle does not: <= 1e-12 relative (north_star's field tolerance)
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    assert (np.abs(got - want) / scale).max() <= 1e-12
+    assert np.array_equal(got[1] == 0.0, want[1] == 0.0)           # empty grazer sites stay empty (no diffusion in the RK4 part)
