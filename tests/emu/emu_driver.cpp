@@ -4,6 +4,7 @@
 // marching pipeline, halo logic and decomposition invariance against the oracle without a GPU.
 #include "tm_host_setup.h"
 #include "tm_fke.cuh"
+#include "tm_consumer.cuh"
 
 #include <cmath>
 #include <vector>
@@ -174,6 +175,40 @@ int emu_fke_move(const int *terms, double pref, double eps, const double *rho, c
     emu_launch(fke_rows_kernel, A, (unsigned)(tiles * A.t.L), kFkeThreads,
                (size_t)(A.t.bD + 1 + fke_max3(A.t.rlo, A.t.rhi, 0) + 1) * sizeof(double));
     maxdisp_out[0] = maxdisp[0]; maxdisp_out[1] = maxdisp[1];
+    return 0;
+}
+
+// consumer-side operators through the product's kernels (csrc/tm_consumer.cuh), launch shapes as tm_consumer.cu
+int emu_cons_gamma(int L, const double *prey, const int *offsets, int eff, double rho_avg_prey, double rho_avg_self, double *gamma)
+{
+    GammaArgs A{};
+    A.L = L; A.eff = eff; A.prey = prey; A.offsets = offsets; A.gamma = gamma;
+    A.rho_inverse = rho_avg_prey >= 1.0e-12 ? 1 / rho_avg_prey : 1 / 1.0e-12;
+    A.zero = (rho_avg_self < 1.0e-12 || rho_avg_prey < 1.0e-12) ? 1 : 0;
+    const int tiles = (L + kConsThreads - 1) / kConsThreads;
+    emu_launch(cons_gamma_kernel, A, (unsigned)(tiles * L), kConsThreads, sizeof(int) * 2 * eff);
+    return 0;
+}
+
+// par = {dt, a, c, gmax, alpha, rW, W0, K1, K2, Dw, Do, A01, H01, E1}; fields [4][L*L] in/out
+int emu_cons_rk4(int L, const double *par, double *fields, int nsteps)
+{
+    const size_t n4 = (size_t)4 * L * L;
+    std::vector<double> ya(n4), yb(n4), acc(n4);
+    RkStageArgs A{};
+    A.L = L;
+    A.c.dt = par[0]; A.c.dt2 = par[0] / 2.0; A.c.dt6 = par[0] / 6.0;
+    A.c.a = par[1]; A.c.cgmax = par[2] * par[3]; A.c.gmax = par[3]; A.c.alpha = par[4]; A.c.rW = par[5]; A.c.K1 = par[7]; A.c.K2 = par[8];
+    A.c.K2W0 = par[8] * par[6]; A.c.Dw = par[9]; A.c.Do = par[10]; A.c.A01 = par[11]; A.c.A01H01 = par[11] * par[12]; A.c.EA1 = par[13] * par[11];
+    const int tiles = (L + kConsThreads - 1) / kConsThreads;
+    const unsigned grid = (unsigned)(tiles * L);
+    for (int s = 0; s < nsteps; s++) {
+        A.base = fields; A.acc = acc.data(); A.out = fields;
+        A.stage = 1; A.Y = fields; A.Ynext = ya.data(); emu_launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+        A.stage = 2; A.Y = ya.data(); A.Ynext = yb.data(); emu_launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+        A.stage = 3; A.Y = yb.data(); A.Ynext = ya.data(); emu_launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+        A.stage = 4; A.Y = ya.data(); A.Ynext = nullptr; emu_launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+    }
     return 0;
 }
 }

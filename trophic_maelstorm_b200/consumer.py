@@ -1,0 +1,86 @@
+"""ctypes view of include/tm_consumer.h (no numerics live here): consumer-side operators of the SPB = 2 model."""
+import ctypes as C
+
+import numpy as np
+
+from .lattice import TmError, lib
+
+
+class ConsParams(C.Structure):
+    """struct tm_cons_params."""
+    _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1".split()]
+
+
+CONS_ABI_SYMBOLS = ["tm_cons_create", "tm_cons_destroy", "tm_cons_last_error", "tm_cons_rk4_host", "tm_cons_gamma_host", "tm_cons_last_ms"]
+
+_bound = False
+
+
+def _lib():
+    global _bound
+    L = lib()
+    if not _bound:
+        vp, dp, i = C.c_void_p, C.POINTER(C.c_double), C.c_int
+        sig = {
+            "tm_cons_create": (i, [i, i, C.POINTER(vp)]),
+            "tm_cons_destroy": (i, [vp]),
+            "tm_cons_last_error": (C.c_char_p, [vp]),
+            "tm_cons_rk4_host": (i, [vp, C.POINTER(ConsParams), dp, i]),
+            "tm_cons_gamma_host": (i, [vp, dp, C.POINTER(C.c_int32), i, C.c_double, C.c_double, dp]),
+            "tm_cons_last_ms": (i, [vp, C.POINTER(C.c_float), C.POINTER(i)]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _bound = True
+    return L
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class ConsumerOps:
+    """One tm_cons_ctx: perception field and four-field RK4 of the vegetation + grazer model on an L x L lattice."""
+
+    def __init__(self, L, device=0):
+        self._l = _lib()
+        self.L = L
+        self._ctx = C.c_void_p()
+        rc = self._l.tm_cons_create(L, device, C.byref(self._ctx))
+        if rc != 0:
+            self._ctx = C.c_void_p()
+            raise TmError("tm_cons_create failed (%d): %s" % (rc, self._l.tm_cons_last_error(None).decode()))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TmError("tm_cons call failed (%d): %s" % (rc, self._l.tm_cons_last_error(self._ctx).decode()))
+
+    def close(self):
+        if self._ctx:
+            self._l.tm_cons_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def rk4(self, params, fields, nsteps=1):
+        f = np.ascontiguousarray(fields, dtype=np.float64).copy()
+        assert f.size == 4 * self.L * self.L
+        self._ck(self._l.tm_cons_rk4_host(self._ctx, C.byref(params), _dptr(f), nsteps))
+        return f
+
+    def gamma(self, prey, offsets, avg_prey, avg_self, gamma0):
+        g = np.ascontiguousarray(gamma0, dtype=np.float64).copy()
+        prey = np.ascontiguousarray(prey, dtype=np.float64)
+        off = np.ascontiguousarray(offsets, dtype=np.int32)
+        self._ck(self._l.tm_cons_gamma_host(self._ctx, _dptr(prey), off.ctypes.data_as(C.POINTER(C.c_int32)), len(off), avg_prey, avg_self, _dptr(g)))
+        return g
+
+    def last_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        self._ck(self._l.tm_cons_last_ms(self._ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

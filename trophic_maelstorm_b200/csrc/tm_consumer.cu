@@ -1,0 +1,145 @@
+// tm_consumer.cu -- C ABI (include/tm_consumer.h) over the consumer-side kernels (tm_consumer.cuh).  sm_100a only; no CPU path.
+#include "../../include/tm_consumer.h"
+#include "../../include/tm_lattice.h" // TM_E_* codes
+#include "tm_consumer.cuh"
+
+#include <cuda_runtime.h>
+#include <new>
+#include <string>
+
+using namespace tml;
+
+static thread_local std::string g_cons_create_error;
+
+struct tm_cons_ctx {
+    int L = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *d_state = nullptr, *d_ya = nullptr, *d_yb = nullptr, *d_acc = nullptr;   // [4][L*L] each
+    double *d_gamma = nullptr;                                                       // [L*L]
+    int *d_off = nullptr; int off_cap = 0;
+    int n_launches = 0;
+    std::string err;
+};
+
+#define CONS_CK(call)                                                                  \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TM_E_CUDA; } \
+    } while (0)
+
+extern "C" {
+
+const char *tm_cons_last_error(const tm_cons_ctx *c) { return c ? c->err.c_str() : g_cons_create_error.c_str(); }
+
+int tm_cons_destroy(tm_cons_ctx *c)
+{
+    if (!c) return TM_E_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_state); cudaFree(c->d_ya); cudaFree(c->d_yb); cudaFree(c->d_acc); cudaFree(c->d_gamma); cudaFree(c->d_off);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return TM_OK;
+}
+
+int tm_cons_create(int L, int device, tm_cons_ctx **out)
+{
+    if (!out) return TM_E_ARG;
+    *out = nullptr;
+    auto fail = [&](tm_cons_ctx *c, int code, const std::string &msg) { g_cons_create_error = msg; if (c) tm_cons_destroy(c); return code; };
+    if (L < 2 || L > 32767) return fail(nullptr, TM_E_ARG, "tm_cons_create: need 2 <= L <= 32767");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(nullptr, TM_E_CUDA, "tm_cons_create: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(nullptr, TM_E_ARG, "tm_cons_create: bad device index");
+    tm_cons_ctx *c = new (std::nothrow) tm_cons_ctx;
+    if (!c) return fail(nullptr, TM_E_ARG, "tm_cons_create: out of host memory");
+    c->L = L; c->device = device;
+    const size_t n4 = (size_t)4 * L * L * sizeof(double);
+#define CR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, TM_E_CUDA, std::string("tm_cons_create: " #call ": ") + cudaGetErrorString(e_)); } while (0)
+    CR(cudaSetDevice(device));
+    CR(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CR(cudaEventCreate(&c->ev0)); CR(cudaEventCreate(&c->ev1));
+    CR(cudaMalloc(&c->d_state, n4)); CR(cudaMalloc(&c->d_ya, n4)); CR(cudaMalloc(&c->d_yb, n4)); CR(cudaMalloc(&c->d_acc, n4));
+    CR(cudaMalloc(&c->d_gamma, n4 / 4));
+#undef CR
+    *out = c;
+    return TM_OK;
+}
+
+int tm_cons_rk4_host(tm_cons_ctx *c, const tm_cons_params *p, double *fields, int nsteps)
+{
+    if (!c) return TM_E_ARG;
+    if (!p || !fields || nsteps < 0 || p->L != c->L) { c->err = "tm_cons_rk4_host: bad argument (p->L must equal the context's L)"; return TM_E_ARG; }
+    const size_t n4 = (size_t)4 * c->L * c->L * sizeof(double);
+    CONS_CK(cudaSetDevice(c->device));
+    CONS_CK(cudaMemcpyAsync(c->d_state, fields, n4, cudaMemcpyHostToDevice, c->stream));
+    RkStageArgs A{};
+    A.L = c->L;
+    A.c.dt = p->dt; A.c.dt2 = p->dt / 2.0; A.c.dt6 = p->dt / 6.0;               // R/:171
+    A.c.a = p->a; A.c.cgmax = p->c * p->gmax; A.c.gmax = p->gmax; A.c.alpha = p->alpha; A.c.rW = p->rW; A.c.K1 = p->K1; A.c.K2 = p->K2;
+    A.c.K2W0 = p->K2 * p->W0; A.c.Dw = p->Dw; A.c.Do = p->Do;
+    A.c.A01 = p->A01; A.c.A01H01 = p->A01 * p->H01; A.c.EA1 = p->E1 * p->A01;   // R/:2452
+    const int tiles = (c->L + kConsThreads - 1) / kConsThreads;
+    const unsigned grid = (unsigned)((long long)tiles * c->L);
+    CONS_CK(cudaEventRecord(c->ev0, c->stream));
+    c->n_launches = 0;
+    for (int s = 0; s < nsteps; s++) {
+        A.base = c->d_state; A.acc = c->d_acc; A.out = c->d_state;
+        A.stage = 1; A.Y = c->d_state; A.Ynext = c->d_ya; cons_rk4_stage_kernel<<<grid, kConsThreads, 0, c->stream>>>(A);
+        A.stage = 2; A.Y = c->d_ya; A.Ynext = c->d_yb; cons_rk4_stage_kernel<<<grid, kConsThreads, 0, c->stream>>>(A);
+        A.stage = 3; A.Y = c->d_yb; A.Ynext = c->d_ya; cons_rk4_stage_kernel<<<grid, kConsThreads, 0, c->stream>>>(A);
+        A.stage = 4; A.Y = c->d_ya; A.Ynext = nullptr; cons_rk4_stage_kernel<<<grid, kConsThreads, 0, c->stream>>>(A);
+        c->n_launches += 4;
+    }
+    CONS_CK(cudaGetLastError());
+    CONS_CK(cudaEventRecord(c->ev1, c->stream));
+    CONS_CK(cudaMemcpyAsync(fields, c->d_state, n4, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_cons_gamma_host(tm_cons_ctx *c, const double *prey, const int32_t *offsets, int n_offsets, double rho_avg_prey,
+                       double rho_avg_self, double *gamma)
+{
+    if (!c) return TM_E_ARG;
+    if (!prey || !offsets || !gamma || n_offsets < 1 || n_offsets > 10000) { c->err = "tm_cons_gamma_host: bad argument (1 <= n_offsets <= 10000)"; return TM_E_ARG; }
+    const size_t n = (size_t)c->L * c->L * sizeof(double);
+    CONS_CK(cudaSetDevice(c->device));
+    if (n_offsets > c->off_cap) {
+        cudaFree(c->d_off); c->d_off = nullptr; c->off_cap = 0;
+        CONS_CK(cudaMalloc(&c->d_off, sizeof(int) * 2 * n_offsets));
+        c->off_cap = n_offsets;
+    }
+    CONS_CK(cudaMemcpyAsync(c->d_off, offsets, sizeof(int) * 2 * n_offsets, cudaMemcpyHostToDevice, c->stream));
+    CONS_CK(cudaMemcpyAsync(c->d_ya, prey, n, cudaMemcpyHostToDevice, c->stream));     // the stage buffer doubles as the prey field
+    CONS_CK(cudaMemcpyAsync(c->d_gamma, gamma, n, cudaMemcpyHostToDevice, c->stream));
+    const double eps = 1.0e-12;
+    GammaArgs A{};
+    A.L = c->L; A.eff = n_offsets; A.prey = c->d_ya; A.offsets = c->d_off; A.gamma = c->d_gamma;
+    A.rho_inverse = rho_avg_prey >= eps ? 1 / rho_avg_prey : 1 / eps;                  // R/:2548
+    A.zero = (rho_avg_self < eps || rho_avg_prey < eps) ? 1 : 0;                       // R/:2575-2578
+    const int tiles = (c->L + kConsThreads - 1) / kConsThreads;
+    CONS_CK(cudaEventRecord(c->ev0, c->stream));
+    cons_gamma_kernel<<<(unsigned)((long long)tiles * c->L), kConsThreads, sizeof(int) * 2 * n_offsets, c->stream>>>(A);
+    CONS_CK(cudaGetLastError());
+    CONS_CK(cudaEventRecord(c->ev1, c->stream));
+    c->n_launches = 1;
+    CONS_CK(cudaMemcpyAsync(gamma, c->d_gamma, n, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_cons_last_ms(tm_cons_ctx *c, float *ms, int *n_launches)
+{
+    if (!c || !ms) return TM_E_ARG;
+    CONS_CK(cudaSetDevice(c->device));
+    CONS_CK(cudaEventSynchronize(c->ev1));
+    CONS_CK(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    if (n_launches) *n_launches = c->n_launches;
+    return TM_OK;
+}
+
+} // extern "C"
