@@ -7,8 +7,10 @@
  *                        nVeg_frac, r_max, L)   R/:2530-2603 (rietkerk_bjork_basic.h declares the 3-species twin at :371)
  *   tm_cons_rk4_host     replaces RK4_Integrate_Stochastic_2Sp(Rho_t, Rho_tsar, K1..K4, nR2, a, c, gmax, alpha, rW, W0,
  *                        Dxd2, K, A, H, E, t, dt, dx, g)   R/:2472-2527 with f_2Dor_2Sp R/:2445-2470
- * Not yet behind this ABI (remaining): the grazer's Dornic sampling with upwind advection (R/:3908-4114),
- * the predator (SPB = 3) variants, and the SPB >= 2 replicate runner.
+ *   tm_cons_grazer_dornic_host   replaces the grazer's Dornic loop with upwind advection inlined in
+ *                        rietkerk_Dornic_2D_MultiSp, R/:3908-4114 (s = 1)
+ * Not yet behind this ABI (remaining): the predator (SPB = 3) variants and the SPB >= 2 replicate runner that
+ * chains these operators with the vegetation step of include/tm_lattice.h.
  */
 #ifndef TM_CONSUMER_H
 #define TM_CONSUMER_H
@@ -42,6 +44,22 @@ int tm_cons_rk4_host(tm_cons_ctx *, const tm_cons_params *p, double *fields, int
  * value the array holds on entry, as the reference does (R/:2581). */
 int tm_cons_gamma_host(tm_cons_ctx *, const double *prey, const int32_t *offsets, int n_offsets, double rho_avg_prey,
                        double rho_avg_self, double *gamma);
+
+/* The grazer's Dornic update (rho* of species 1).  D, v, M, sigma: D[1], v[1], M[1], sigma[1]; D0_floor = D[0]/dx^2
+ * (diff_coefficient[0], the floor of the advection-corrected diffusion, R/:4014). */
+typedef struct tm_graz_params {
+    int32_t L, pad_;
+    double dt, dx, D, v, M, sigma, D0_floor;
+} tm_graz_params;
+
+/* prev: DRho[1] [L*L]; gamma: [L*L] in/out (clamped at 1 as R/:3915 does); rho_star: [L*L] out; v_eff: [L*L][2] out (the
+ * advection vector drawn for every cell).  Random numbers: replay_u == NULL: Philox4x32-10 keyed by (seed, trial, step,
+ * cell) -- uniform 0 of a cell's stream is its advection direction, the sampler draws follow; otherwise cell i takes its k-th
+ * uniform from replay_u[i*stride + k] (draws past `stride` are counted in *overflow and return 0.75).  The caller applies
+ * the reference's whole-species skip `if (Rhox_avg[s] == 0.0) continue;` (R/:3910). */
+int tm_cons_grazer_dornic_host(tm_cons_ctx *, const tm_graz_params *p, uint64_t seed, uint32_t trial, uint32_t step,
+                               const double *replay_u, uint32_t stride, const double *prev, double *gamma, double *rho_star,
+                               double *v_eff, uint64_t *overflow);
 
 /* Device time (ms) of the kernels of the last call and how many launches that was. */
 int tm_cons_last_ms(tm_cons_ctx *, float *ms, int *n_launches);

@@ -549,6 +549,70 @@ static void dornic_sweep(const tmo_params *p, const dornic_consts *k, tmo_rng *r
     rng->norm_saved = norm_seq.saved;
 }
 
+/* The grazer's Dornic update with upwind advection, R/:3908-4114 (SPB >= 2, species s = 1), for every cell in the
+ * reference's order.  prev = DRho[s] (state of the previous step); gamma[s] is clamped at 1 in place (R/:3915);
+ * veff receives the sampled advection vector {first, second} of every cell (R/:3993-3996: drawn for EVERY cell, before
+ * the skip test); out = rho* (cells skipped by R/:4048 keep prev).  trig_libm != 0: cos/sin of libm on 2*PI*ran as the
+ * reference computes them (sequential mode, pins the restatement); 0: the product's bit-reproducible sincos_turn128. */
+int tmo_grazer_dornic(const tmo_graz_params *p, tmo_rng *rng, const double *prev, double *gamma, double *out, double *veff,
+                      int trig_libm)
+{
+    if (!p || p->L < 1) return -1;
+    const int L = p->L;
+    const double dx = p->dx, dt = p->dt;
+    const double dx2 = dx * dx, dx1 = 1 / dx, dx1_2 = 1 / (dx2), dxb2 = dx / 2.0;   /* R/:3455 */
+    const double sigma2_1 = 1 / (p->sigma * p->sigma);                              /* R/:3463 */
+    double pi = 0.0, p16 = 1.0;                                                     /* the reference's PI, header :241-284 */
+    for (int n = 0; n <= 14; n++) {
+        pi = (1.0 / p16 * (4.0 / (8 * n + 1.0) - 2.0 / (8 * n + 4.0) - 1.0 / (8 * n + 5.0) - 1.0 / (8 * n + 6.0))) + pi;
+        p16 *= 16.0;
+    }
+    cstream s;
+    normal_state norm_cell;
+    normal_state norm_seq = { rng->norm_saved_available, rng->norm_saved };
+    cs_begin_cell(&s, rng, 0);
+    for (int r = 0; r < L; r++) {
+        const int up = ((r - 1) % L + L) % L, dn = ((r + 1) % L + L) % L;
+        for (int q = 0; q < L; q++) {
+            const int lf = ((q - 1) % L + L) % L, rt = ((q + 1) % L + L) % L;
+            const int i = r * L + q;
+            if (gamma[i] > 1) gamma[i] = 1;                                          /* R/:3915 */
+            normal_state *norm = &norm_seq;
+            if (rng->kind != TMO_SRC_SEQ) {
+                cs_begin_cell(&s, rng, (uint64_t)i);
+                norm_cell.saved_available = 0; norm_cell.saved = 0.0;
+                norm = &norm_cell;
+            }
+            const double ran = next_u(&s);                                           /* R/:3993 */
+            double vx, vy;
+            if (trig_libm) { vx = p->v * cos(2 * pi * ran); vy = p->v * sin(2 * pi * ran); }   /* R/:3995 */
+            else { double sn, cs; tmo_sincos_turn128(128.0 * ran, &sn, &cs); vx = p->v * cs; vy = p->v * sn; }
+            veff[2 * i] = vx; veff[2 * i + 1] = vy;
+            const double vx_abs = vx * ((0 < vx) - (vx < 0)), vy_abs = vy * ((0 < vy) - (vy < 0));   /* R/:4000, sgn R/:25 */
+            const double gp = (1 - gamma[i]);
+            double dex = (p->D - (dxb2) * (gp * vx_abs * (1 - dt * dx1 * gp * vx_abs))) * dx1_2;    /* R/:4008 */
+            double dey = (p->D - (dxb2) * (gp * vy_abs * (1 - dt * dx1 * gp * vy_abs))) * dx1_2;    /* R/:4009 */
+            if (dex < p->D0floor) dex = p->D0floor;                                  /* R/:4014-4018 */
+            if (dey < p->D0floor) dey = p->D0floor;
+            const double hx = prev[r * L + ((0 < vx) ? lf : rt)];                    /* nR2[i][1][sgn_index(vx)], R/:30-35 */
+            const double hy = prev[((0 < vy) ? up : dn) * L + q];                    /* nR2[i][0][sgn_index(vy)] */
+            const double alpha_i = gamma[i] * (dey * (prev[up * L + q] + prev[dn * L + q]) + dex * (prev[r * L + lf] + prev[r * L + rt]))
+                                 + dx1 * (gp) * (vx_abs * hx + vy_abs * hy);         /* R/:4044-4046 */
+            if (alpha_i == 0 && prev[i] == 0) { out[i] = prev[i]; continue; }        /* R/:4048 */
+            const double beta = -p->M - 2 * gamma[i] * (dex + dey) - (1 - gamma[i]) * (vx_abs + vy_abs) * dx1;   /* R/:4057 */
+            dornic_consts k;
+            k.beta = beta; k.lambda_exp = trig_libm ? exp((beta) * dt) : tmo_exp((beta) * dt);   /* R/:4059 */
+            k.lambda = 2 * (beta) * (sigma2_1) / (k.lambda_exp - 1.0);
+            k.sigma2 = p->sigma * p->sigma; k.sigma2_1 = sigma2_1; k.diffc = 0.0;
+            tmo_params pm; memset(&pm, 0, sizeof pm); pm.model = TMO_MODEL_RIETKERK;  /* the same sampling ladder as R/:3766-3794 */
+            out[i] = dornic_cell(&pm, &k, &s, norm, alpha_i, prev[i]);               /* R/:4061-4090 */
+        }
+    }
+    rng->norm_saved_available = norm_seq.saved_available;
+    rng->norm_saved = norm_seq.saved;
+    return 0;
+}
+
 /* ================================================================================== */
 /* 5. Deterministic remainders                                                        */
 /* ================================================================================== */

@@ -151,9 +151,18 @@ typedef struct tmo_cons_params {
     double Dw, Do;            /* Dxd2[2], Dxd2[3] = D[s]/dx^2 of soil and surface water */
     double A01, H01, E1;      /* A[0][1], H[0][1], E[1] */
 } tmo_cons_params;
+typedef struct tmo_graz_params {
+    int32_t L, pad_;
+    double dt, dx;
+    double D, v, M, sigma;    /* D[s], v[s], M[s], sigma[s] of the grazer */
+    double D0floor;           /* diff_coefficient[0] = D[0]/dx^2: floor of the advection-corrected diffusion, R/:4014 */
+} tmo_graz_params;
 void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
                           double *gamma);
 int tmo_rk4_2sp(const tmo_cons_params *p, double *f);
+/* the grazer's Dornic update with upwind advection, R/:3908-4114 (defined in tm_oracle.c next to the samplers) */
+int tmo_grazer_dornic(const tmo_graz_params *p, tmo_rng *rng, const double *prev, double *gamma, double *out, double *veff,
+                      int trig_libm);
 
 #ifdef __cplusplus
 }

@@ -211,4 +211,19 @@ int emu_cons_rk4(int L, const double *par, double *fields, int nsteps)
     }
     return 0;
 }
+
+// par = {dt, dx, D, v, M, sigma, D0floor}; replay_u == nullptr: Philox
+int emu_grazer_dornic(int L, const double *par, unsigned long long seed, unsigned trial, unsigned step, const double *replay_u,
+                      unsigned stride, const double *prev, double *gamma, double *out, double *veff, unsigned long long *overflow)
+{
+    GrazerArgs A{};
+    A.L = L; A.dt = par[0]; A.dx = par[1]; A.D = par[2]; A.v = par[3]; A.M = par[4]; A.sigma = par[5]; A.D0floor = par[6];
+    A.prev = prev; A.gamma = gamma; A.out = out; A.veff = veff;
+    A.seed = seed; A.trial = trial; A.step = step; A.replay_u = replay_u; A.stride = stride; A.overflow = overflow;
+    *overflow = 0;
+    const int tiles = (L + kConsThreads - 1) / kConsThreads;
+    if (replay_u) emu_launch(grazer_dornic_kernel<true>, A, (unsigned)(tiles * L), kConsThreads, 0);
+    else          emu_launch(grazer_dornic_kernel<false>, A, (unsigned)(tiles * L), kConsThreads, 0);
+    return 0;
+}
 }

@@ -42,6 +42,11 @@ class OConsParams(C.Structure):
     _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1".split()]
 
 
+class OGrazParams(C.Structure):
+    """struct tmo_graz_params."""
+    _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt dx D v M sigma D0floor".split()]
+
+
 _lib = None
 
 
@@ -94,6 +99,7 @@ def oracle():
         L.tmo_gamma_perception.restype = None
         L.tmo_gamma_perception.argtypes = [C.c_int, dp, C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, dp]
         L.tmo_rk4_2sp.argtypes = [C.POINTER(OConsParams), dp]
+        L.tmo_grazer_dornic.argtypes = [C.POINTER(OGrazParams), C.POINTER(ORng), dp, dp, dp, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -226,3 +232,13 @@ def rk4_2sp(p, fields, steps=1):
     for _ in range(steps):
         assert oracle().tmo_rk4_2sp(C.byref(p), ptr(f)) == 0
     return f
+
+
+def grazer_dornic(p, rng, prev, gamma, trig_libm=False):
+    """-> (rho*, gamma clamped, v_eff [L*L, 2]); the grazer's Dornic update, R/:3908-4114."""
+    n = p.L * p.L
+    prev = np.ascontiguousarray(prev, dtype=np.float64)
+    g = np.ascontiguousarray(gamma, dtype=np.float64).copy()
+    out, veff = np.empty(n), np.empty((n, 2))
+    assert oracle().tmo_grazer_dornic(C.byref(p), C.byref(rng), ptr(prev), ptr(g), ptr(out), ptr(veff), 1 if trig_libm else 0) == 0
+    return out, g, veff

@@ -128,3 +128,91 @@ def test_gpu_consumer_ops_larger_lattices():
     rnd = np.random.default_rng(2).gamma(2.0, 50.0, L * L)
     g = ops.gamma(rnd, central, rnd.mean(), 1.0, np.zeros(L * L))
     assert g.min() >= 0.0 and g.max() <= 1.0 and 0.9 < g.mean() <= 1.0     # disc means scatter around 1; the upper half is clamped
+
+
+# ------------------------------------------------------------------------------------------------ grazer Dornic (R/:3908-4114)
+def grazer_setup(L, seed, sigma=1.0):
+    """Constants of the SPB = 2 driver (order_2stoc_test_rietkerk.cpp: D[1] = 0.01028, v[1] = 0.45427, 20 kg grazer) and a field
+    that exercises every sampler regime: empty regions (skip rule), a thin fringe (exact Poisson/Gamma), dense bulk (Gaussian)."""
+    rng = np.random.default_rng(seed)
+    dx, dt = 0.1, 0.1
+    M = 0.061609 * 20.0 ** -0.25 / 8760.0
+    par = dict(dt=dt, dx=dx, D=0.01028, v=0.45427, M=M, sigma=sigma, D0floor=(0.00025 / 24.0) / (dx * dx))
+    prev = rng.gamma(2.0, 400.0, (L, L))
+    prev[:, : L // 4] = 0.0
+    prev[:, L // 4: L // 4 + 3] = 10 ** rng.uniform(-4, 0, (L, 3))
+    prev[rng.random((L, L)) < 0.05] = 0.0
+    gamma = rng.random(L * L) * 1.1                      # some above 1: clamped (R/:3915)
+    gamma[rng.random(L * L) < 0.1] = 0.0
+    return par, prev.ravel().copy(), gamma
+
+
+def oparams(L, par):
+    return O.OGrazParams(L, 0, *[par[k] for k in "dt dx D v M sigma D0floor".split()])
+
+
+def gparams(L, par):
+    return tm.GrazParams(L, 0, *[par[k] for k in "dt dx D v M sigma D0floor".split()])
+
+
+def emu_grazer(emu, L, par, prev, gamma, seed=0, trial=0, step=0, replay=None, stride=0):
+    flat = np.array([par[k] for k in "dt dx D v M sigma D0floor".split()])
+    g = gamma.copy(); out = np.empty(L * L); veff = np.empty((L * L, 2)); ovf = C.c_ulonglong()
+    emu.emu_grazer_dornic(L, flat.ctypes.data_as(dp), C.c_ulonglong(seed), trial, step,
+                          replay.ctypes.data_as(dp) if replay is not None else None, stride,
+                          prev.ctypes.data_as(dp), g.ctypes.data_as(dp), out.ctypes.data_as(dp), veff.ctypes.data_as(dp), C.byref(ovf))
+    return out, g, veff, ovf.value
+
+
+@pytest.mark.parametrize("L,sigma", [(40, 1.0), (150, 0.3)])
+def test_emulated_grazer_dornic_matches_oracle(emu, L, sigma):
+    par, prev, gamma = grazer_setup(L, 11 + L, sigma)
+    want = O.grazer_dornic(oparams(L, par), O.make_rng(O.SRC_PHILOX, seed=99, trial=2, step=7), prev, gamma)
+    got = emu_grazer(emu, L, par, prev, gamma, seed=99, trial=2, step=7)
+    for a, b in zip(got[:3], want):
+        assert np.array_equal(a, b)
+    assert got[3] == 0
+    stride = 48
+    u = np.random.default_rng(5).random(L * L * stride)
+    want = O.grazer_dornic(oparams(L, par), O.make_rng(O.SRC_REPLAY, u=u, stride=stride), prev, gamma)
+    got = emu_grazer(emu, L, par, prev, gamma, replay=u, stride=stride)
+    for a, b in zip(got[:3], want):
+        assert np.array_equal(a, b)
+
+
+def test_grazer_dornic_oracle_laws():
+    """Structure of the restatement: empty neighbourhoods are skipped, |v_eff| = v, and with advection switched off
+    (gamma = 1) an ensemble mean follows the linear part exp(beta dt) rho + diffusion of the Dornic scheme."""
+    L = 64
+    par, prev, gamma = grazer_setup(L, 3)
+    out, g, veff = O.grazer_dornic(oparams(L, par), O.make_rng(O.SRC_PHILOX, seed=1), prev, gamma)
+    assert g.max() <= 1.0 and np.allclose(np.hypot(veff[:, 0], veff[:, 1]), par["v"], rtol=1e-14)
+    P = prev.reshape(L, L)
+    nb = np.roll(P, 1, 0) + np.roll(P, -1, 0) + np.roll(P, 1, 1) + np.roll(P, -1, 1)
+    dead = (P == 0) & (nb == 0)
+    assert dead.sum() > 100 and np.all(out.reshape(L, L)[dead] == 0.0)
+    assert np.all(out >= 0) and np.isfinite(out).all()
+    flat = np.full(L * L, 500.0)
+    outs = [O.grazer_dornic(oparams(L, par), O.make_rng(O.SRC_PHILOX, seed=s), flat, np.ones(L * L))[0].mean() for s in range(8)]
+    # homogeneous field, gamma = 1: E[rho*] = rho e^{-M dt} (diffusion in = diffusion out); sampling noise ~ sigma sqrt(rho dt)/L
+    assert abs(np.mean(outs) - 500.0 * np.exp(-par["M"] * par["dt"])) < 5 * np.sqrt(500.0 * par["dt"]) / L / np.sqrt(8) + 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,sigma", [(40, 1.0), (150, 0.3), (512, 1.0)])
+def test_gpu_grazer_dornic_matches_oracle(L, sigma):
+    par, prev, gamma = grazer_setup(L, 11 + L, sigma)
+    ops = tm.ConsumerOps(L)
+    want = O.grazer_dornic(oparams(L, par), O.make_rng(O.SRC_PHILOX, seed=99, trial=2, step=7), prev, gamma)
+    got = ops.grazer_dornic(gparams(L, par), prev, gamma, seed=99, trial=2, step=7)
+    for a, b in zip(got[:3], want):
+        assert np.array_equal(a, b)
+    stride = 48
+    u = np.random.default_rng(5).random(L * L * stride)
+    want = O.grazer_dornic(oparams(L, par), O.make_rng(O.SRC_REPLAY, u=u, stride=stride), prev, gamma)
+    got = ops.grazer_dornic(gparams(L, par), prev, gamma, replay=u, stride=stride)
+    for a, b in zip(got[:3], want):
+        assert np.array_equal(a, b)
+    assert got[3] == 0
+    short = ops.grazer_dornic(gparams(L, par), prev, gamma, replay=u[: L * L * 2].copy(), stride=2)
+    assert short[3] > 0                               # a starved replay slice is counted, not hung

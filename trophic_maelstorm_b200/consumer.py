@@ -11,7 +11,13 @@ class ConsParams(C.Structure):
     _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1".split()]
 
 
-CONS_ABI_SYMBOLS = ["tm_cons_create", "tm_cons_destroy", "tm_cons_last_error", "tm_cons_rk4_host", "tm_cons_gamma_host", "tm_cons_last_ms"]
+class GrazParams(C.Structure):
+    """struct tm_graz_params."""
+    _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt dx D v M sigma D0_floor".split()]
+
+
+CONS_ABI_SYMBOLS = ["tm_cons_create", "tm_cons_destroy", "tm_cons_last_error", "tm_cons_rk4_host", "tm_cons_gamma_host",
+                    "tm_cons_grazer_dornic_host", "tm_cons_last_ms"]
 
 _bound = False
 
@@ -27,6 +33,8 @@ def _lib():
             "tm_cons_last_error": (C.c_char_p, [vp]),
             "tm_cons_rk4_host": (i, [vp, C.POINTER(ConsParams), dp, i]),
             "tm_cons_gamma_host": (i, [vp, dp, C.POINTER(C.c_int32), i, C.c_double, C.c_double, dp]),
+            "tm_cons_grazer_dornic_host": (i, [vp, C.POINTER(GrazParams), C.c_uint64, C.c_uint32, C.c_uint32, dp, C.c_uint32, dp, dp, dp, dp,
+                                               C.POINTER(C.c_uint64)]),
             "tm_cons_last_ms": (i, [vp, C.POINTER(C.c_float), C.POINTER(i)]),
         }
         for name, (res, args) in sig.items():
@@ -79,6 +87,21 @@ class ConsumerOps:
         off = np.ascontiguousarray(offsets, dtype=np.int32)
         self._ck(self._l.tm_cons_gamma_host(self._ctx, _dptr(prey), off.ctypes.data_as(C.POINTER(C.c_int32)), len(off), avg_prey, avg_self, _dptr(g)))
         return g
+
+    def grazer_dornic(self, params, prev, gamma, seed=0, trial=0, step=0, replay=None, stride=0):
+        """-> (rho*, gamma clamped, v_eff [L*L, 2], overflow count)."""
+        n = self.L * self.L
+        prev = np.ascontiguousarray(prev, dtype=np.float64)
+        g = np.ascontiguousarray(gamma, dtype=np.float64).copy()
+        out, veff, ovf = np.empty(n), np.empty((n, 2)), C.c_uint64()
+        ru = None
+        if replay is not None:
+            replay = np.ascontiguousarray(replay, dtype=np.float64)
+            assert replay.size == n * stride
+            ru = _dptr(replay)
+        self._ck(self._l.tm_cons_grazer_dornic_host(self._ctx, C.byref(params), seed, trial, step, ru, stride, _dptr(prev), _dptr(g),
+                                                    _dptr(out), _dptr(veff), C.byref(ovf)))
+        return out, g, veff, ovf.value
 
     def last_ms(self):
         ms, n = C.c_float(), C.c_int()

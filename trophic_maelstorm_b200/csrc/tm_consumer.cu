@@ -18,6 +18,8 @@ struct tm_cons_ctx {
     double *d_state = nullptr, *d_ya = nullptr, *d_yb = nullptr, *d_acc = nullptr;   // [4][L*L] each
     double *d_gamma = nullptr;                                                       // [L*L]
     int *d_off = nullptr; int off_cap = 0;
+    double *d_replay = nullptr; size_t replay_cap = 0;
+    unsigned long long *d_ovf = nullptr;
     int n_launches = 0;
     std::string err;
 };
@@ -37,7 +39,7 @@ int tm_cons_destroy(tm_cons_ctx *c)
     if (!c) return TM_E_ARG;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_state); cudaFree(c->d_ya); cudaFree(c->d_yb); cudaFree(c->d_acc); cudaFree(c->d_gamma); cudaFree(c->d_off);
+    cudaFree(c->d_state); cudaFree(c->d_ya); cudaFree(c->d_yb); cudaFree(c->d_acc); cudaFree(c->d_gamma); cudaFree(c->d_off); cudaFree(c->d_replay); cudaFree(c->d_ovf);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -129,6 +131,55 @@ int tm_cons_gamma_host(tm_cons_ctx *c, const double *prey, const int32_t *offset
     c->n_launches = 1;
     CONS_CK(cudaMemcpyAsync(gamma, c->d_gamma, n, cudaMemcpyDeviceToHost, c->stream));
     CONS_CK(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+int tm_cons_grazer_dornic_host(tm_cons_ctx *c, const tm_graz_params *p, uint64_t seed, uint32_t trial, uint32_t step,
+                               const double *replay_u, uint32_t stride, const double *prev, double *gamma, double *rho_star,
+                               double *v_eff, uint64_t *overflow)
+{
+    if (!c) return TM_E_ARG;
+    if (!p || !prev || !gamma || !rho_star || !v_eff || p->L != c->L || (replay_u && stride < 1) || !(p->sigma > 0) || !(p->dx > 0)) {
+        c->err = "tm_cons_grazer_dornic_host: bad argument (p->L must equal the context's L; sigma, dx > 0)"; return TM_E_ARG;
+    }
+    const size_t nn = (size_t)c->L * c->L, n = nn * sizeof(double);
+    CONS_CK(cudaSetDevice(c->device));
+    // staging: d_ya[0] = prev, d_ya[1] = rho*, d_ya[2..3] = v_eff; d_gamma = gamma; d_yb = replay uniforms (grown on demand)
+    double *d_prev = c->d_ya, *d_out = c->d_ya + nn, *d_veff = c->d_ya + 2 * nn;
+    double *d_replay = nullptr;
+    if (replay_u) {
+        const size_t need = nn * stride * sizeof(double);
+        if (need > c->replay_cap) {
+            cudaFree(c->d_replay); c->d_replay = nullptr; c->replay_cap = 0;
+            CONS_CK(cudaMalloc(&c->d_replay, need));
+            c->replay_cap = need;
+        }
+        CONS_CK(cudaMemcpyAsync(c->d_replay, replay_u, need, cudaMemcpyHostToDevice, c->stream));
+        d_replay = c->d_replay;
+    }
+    if (!c->d_ovf) CONS_CK(cudaMalloc(&c->d_ovf, sizeof(unsigned long long)));
+    CONS_CK(cudaMemsetAsync(c->d_ovf, 0, sizeof(unsigned long long), c->stream));
+    CONS_CK(cudaMemcpyAsync(d_prev, prev, n, cudaMemcpyHostToDevice, c->stream));
+    CONS_CK(cudaMemcpyAsync(c->d_gamma, gamma, n, cudaMemcpyHostToDevice, c->stream));
+    GrazerArgs A{};
+    A.L = c->L; A.dt = p->dt; A.dx = p->dx; A.D = p->D; A.v = p->v; A.M = p->M; A.sigma = p->sigma; A.D0floor = p->D0_floor;
+    A.prev = d_prev; A.gamma = c->d_gamma; A.out = d_out; A.veff = d_veff;
+    A.seed = seed; A.trial = trial; A.step = step; A.replay_u = d_replay; A.stride = stride; A.overflow = c->d_ovf;
+    const int tiles = (c->L + kConsThreads - 1) / kConsThreads;
+    const unsigned grid = (unsigned)((long long)tiles * c->L);
+    CONS_CK(cudaEventRecord(c->ev0, c->stream));
+    if (replay_u) grazer_dornic_kernel<true><<<grid, kConsThreads, 0, c->stream>>>(A);
+    else          grazer_dornic_kernel<false><<<grid, kConsThreads, 0, c->stream>>>(A);
+    CONS_CK(cudaGetLastError());
+    CONS_CK(cudaEventRecord(c->ev1, c->stream));
+    c->n_launches = 1;
+    unsigned long long ovf = 0;
+    CONS_CK(cudaMemcpyAsync(rho_star, d_out, n, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaMemcpyAsync(v_eff, d_veff, 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaMemcpyAsync(gamma, c->d_gamma, n, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaMemcpyAsync(&ovf, c->d_ovf, sizeof ovf, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaStreamSynchronize(c->stream));
+    if (overflow) *overflow = ovf;
     return TM_OK;
 }
 

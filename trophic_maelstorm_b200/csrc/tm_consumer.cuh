@@ -8,6 +8,12 @@
 //                          results equal the reference bit for bit.  A CTA = one lattice row x 128 columns; the offset
 //                          list sits in shared memory; prey reads are coalesced along the row and served by L1/L2
 //                          (each prey element is read by |disc| sites: 81 for the SPB=2 driver's radius).
+//   grazer_dornic_kernel   the grazer's Dornic update with upwind advection, R/:3908-4114: per cell one uniform for the
+//                          advection direction (drawn for every cell, before the skip test), the advection-corrected
+//                          diffusion (R/:4008-4018), alpha_i with the upwind neighbours (R/:4044), per-cell beta/lambda
+//                          (an exp per cell, R/:4057-4059), then the same Poisson/Gamma ladder with Gaussian shortcuts as
+//                          the vegetation (dornic_cell<kRietkerk>).  One thread per cell; Philox stream keyed by
+//                          (seed, trial, step, cell) or host-supplied uniforms (replay); bit-identical to the oracle.
 //   cons_rk4_stage_kernel  RK4_Integrate_Stochastic_2Sp R/:2472-2527 with f_2Dor_2Sp R/:2445-2470 over (P, G, W, O): one
 //                          launch per stage.  Stage k reads the stage state Y (5-point neighbours of W and O, periodic),
 //                          writes Y' = Rho_t + h K_k and the running K1 + 2 K2 + 2 K3 (+ K4) in the reference's left-to-
@@ -16,6 +22,8 @@
 //                          the TU is built with --fmad=false), bit-identical to the oracle.
 #pragma once
 #include <stdint.h>
+#include "tm_samplers.cuh"
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define TMC_D __device__ __forceinline__
@@ -64,6 +72,62 @@ TMC_G void cons_gamma_kernel(const GammaArgs A)
     acc = (acc * A.rho_inverse) / (A.eff);
     if (acc > 1) acc = 1.0; else if (acc < 0) acc = 0.0;
     A.gamma[i] = acc;
+}
+
+struct GrazerArgs {
+    int L;
+    double dt, dx, D, v, M, sigma, D0floor;   // D[s], v[s], M[s], sigma[s]; diff_coefficient[0] (R/:4014)
+    const double *prev;                       // DRho[s] [L*L]
+    double *gamma;                            // [L*L] in/out (clamped at 1, R/:3915)
+    double *out, *veff;                       // rho* [L*L]; advection vectors [L*L][2]
+    unsigned long long seed; unsigned int trial, step;
+    const double *replay_u; unsigned int stride;   // REPLAY: [L*L][stride]
+    unsigned long long *overflow;
+};
+
+template <bool REPLAY>
+TMC_G void grazer_dornic_kernel(const GrazerArgs A)
+{
+    const int g = A.L;
+    const int tiles = (g + kConsThreads - 1) / kConsThreads;
+    const int r = (int)(blockIdx.x / tiles), q = (int)(blockIdx.x % tiles) * kConsThreads + (int)threadIdx.x;
+    if (q >= g) return;
+    const int i = r * g + q;
+    const int up = (r == 0 ? g - 1 : r - 1), dn = (r == g - 1 ? 0 : r + 1), lf = (q == 0 ? g - 1 : q - 1), rt = (q == g - 1 ? 0 : q + 1);
+    const double dx2 = A.dx * A.dx, dx1 = 1 / A.dx, dx1_2 = 1 / (dx2), dxb2 = A.dx / 2.0;   // R/:3455
+    const double sigma2_1 = 1 / (A.sigma * A.sigma);
+    double gm = A.gamma[i];
+    if (gm > 1) { gm = 1; A.gamma[i] = gm; }
+    typename std::conditional<REPLAY, ReplaySrc, PhiloxSrc>::type src;
+    if constexpr (REPLAY) src.begin(A.replay_u + (size_t)i * A.stride, A.stride);
+    else src.begin((uint32_t)i, A.trial, A.step, A.seed);
+    const double ran = src.next();                                                         // R/:3993
+    double sn, cs;
+    sincos_turn128(128.0 * ran, sincos_table(), sn, cs);
+    const double vx = A.v * cs, vy = A.v * sn;
+    A.veff[2 * i] = vx; A.veff[2 * i + 1] = vy;
+    const double vx_abs = vx * ((0 < vx) - (vx < 0)), vy_abs = vy * ((0 < vy) - (vy < 0));
+    const double gp = (1 - gm);
+    double dex = (A.D - (dxb2) * (gp * vx_abs * (1 - A.dt * dx1 * gp * vx_abs))) * dx1_2;
+    double dey = (A.D - (dxb2) * (gp * vy_abs * (1 - A.dt * dx1 * gp * vy_abs))) * dx1_2;
+    if (dex < A.D0floor) dex = A.D0floor;
+    if (dey < A.D0floor) dey = A.D0floor;
+    const double *P = A.prev;
+    const double hx = P[r * g + ((0 < vx) ? lf : rt)], hy = P[((0 < vy) ? up : dn) * g + q];
+    const double alpha_i = gm * (dey * (P[up * g + q] + P[dn * g + q]) + dex * (P[r * g + lf] + P[r * g + rt]))
+                         + dx1 * (gp) * (vx_abs * hx + vy_abs * hy);
+    const double rho_i = P[i];
+    double res = rho_i;
+    if (!(alpha_i == 0 && rho_i == 0)) {
+        const double beta = -A.M - 2 * gm * (dex + dey) - (1 - gm) * (vx_abs + vy_abs) * dx1;
+        const double lambda_exp = exp_any((beta) * A.dt);
+        DornicConsts k;
+        k.lambda = 2 * (beta) * (sigma2_1) / (lambda_exp - 1.0);
+        k.ll = k.lambda * lambda_exp; k.sigma2 = A.sigma * A.sigma; k.sigma2_1 = sigma2_1; k.diffc = 0.0;
+        res = dornic_cell<kRietkerk>(k, src, alpha_i, rho_i);
+    }
+    A.out[i] = res;
+    if (src.overflow_count()) atomicAdd(A.overflow, (unsigned long long)src.overflow_count());
 }
 
 struct ConsConsts {
