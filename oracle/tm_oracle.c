@@ -749,6 +749,45 @@ int tmo_step(const tmo_params *p, tmo_rng *rng, double *f)
     return 0;
 }
 
+/* One full time step of the SPB = 2 (vegetation + grazer) runner, R/:3752-4183:
+ *   vegetation Dornic R/:3752-3809 -> spatial means of DRho, vegetation cover factor R/:3813-3824 ->
+ *   calc_gamma_2Sp_NonRefugia R/:3844 -> grazer Dornic R/:3908-4114 (skipped when <G> == 0, R/:3910) ->
+ *   RK4_Integrate_Stochastic_2Sp R/:4137 -> clamp + commit R/:4150-4181.
+ * f: [4][L*L] = P, G, W, O (DRho == Rho_dt on entry, as after a commit); gamma: the grazer's gamma array (state: the
+ * reference never resets it); central: the full distance-sorted disc list of computeNeighboringSitesCentral(int(r_max));
+ * fr_graz = pR[1]/(dx r_max_effective) (R/:3409).  veff (may be NULL): the grazer's advection vectors of this step. */
+int tmo_step_2sp(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_cons_params *pc, const int32_t *central, int n_central,
+                 double fr_graz, tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm)
+{
+    if (!pveg || !pg || !pc || pveg->L != pg->L || pveg->L != pc->L) return -1;
+    const int L = pveg->L;
+    const int64_t n = (int64_t)L * L;
+    double *work = malloc(sizeof(double) * (size_t)n * 8);
+    if (!work) return -1;
+    double *D = work, *vtmp = work + 4 * n, *gout = work + 6 * n, *vout = work + 7 * n;   /* DRho copy, v_eff, rho*_G, rho*_P */
+    memcpy(D, f, sizeof(double) * (size_t)n * 4);
+    dornic_consts k;
+    derive_consts(pveg, &k);
+    dornic_sweep(pveg, &k, rng, D, vout);                                               /* vegetation, R/:3752-3809 */
+    const double avg_veg = tmo_mean(D, n), avg_graz = tmo_mean(D + n, n);               /* R/:3813-3818 */
+    const double num_veg = tmo_occupied(D, n);
+    double nR_fac = 1 - num_veg / (L * L);                                              /* R/:3822 */
+    if (nR_fac < 0.35) nR_fac = 0.35;
+    int new_length = (int)(nR_fac * nR_fac * n_central);                                /* R/:2539 */
+    if (new_length < 1) new_length = 1;
+    const int eff = (int)(fr_graz * fr_graz * new_length);                              /* R/:2569 */
+    tmo_gamma_perception(L, D, central, eff, avg_veg, avg_graz, gamma);                 /* R/:3844 */
+    if (avg_graz == 0.0) memcpy(gout, D + n, sizeof(double) * (size_t)n);               /* R/:3910 */
+    else if (tmo_grazer_dornic(pg, rng, D + n, gamma, gout, veff ? veff : vtmp, trig_libm)) { free(work); return -1; }
+    memcpy(f, vout, sizeof(double) * (size_t)n);
+    memcpy(f + n, gout, sizeof(double) * (size_t)n);
+    if (tmo_rk4_2sp(pc, f)) { free(work); return -1; }                                  /* R/:4137 */
+    for (int64_t i = 0; i < 4 * n; i++)
+        if (f[i] < pveg->clamp_eps && f[i] >= pveg->clamp_lo) f[i] = 0.0;               /* R/:4176 */
+    free(work);
+    return 0;
+}
+
 /* ================================================================================== */
 /* 7. Reductions and host-side bookkeeping                                            */
 /* ================================================================================== */

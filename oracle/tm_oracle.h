@@ -163,6 +163,9 @@ int tmo_rk4_2sp(const tmo_cons_params *p, double *f);
 /* the grazer's Dornic update with upwind advection, R/:3908-4114 (defined in tm_oracle.c next to the samplers) */
 int tmo_grazer_dornic(const tmo_graz_params *p, tmo_rng *rng, const double *prev, double *gamma, double *out, double *veff,
                       int trig_libm);
+/* one full time step of the SPB = 2 runner (R/:3752-4183) on f[4][L*L] = P, G, W, O; see tm_oracle.c */
+int tmo_step_2sp(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_cons_params *pc, const int32_t *central, int n_central,
+                 double fr_graz, tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm);
 
 #ifdef __cplusplus
 }

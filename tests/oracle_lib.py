@@ -100,6 +100,8 @@ def oracle():
         L.tmo_gamma_perception.argtypes = [C.c_int, dp, C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, dp]
         L.tmo_rk4_2sp.argtypes = [C.POINTER(OConsParams), dp]
         L.tmo_grazer_dornic.argtypes = [C.POINTER(OGrazParams), C.POINTER(ORng), dp, dp, dp, dp, C.c_int]
+        L.tmo_step_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OGrazParams), C.POINTER(OConsParams), C.POINTER(C.c_int32), C.c_int,
+                                   C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -242,3 +244,27 @@ def grazer_dornic(p, rng, prev, gamma, trig_libm=False):
     out, veff = np.empty(n), np.empty((n, 2))
     assert oracle().tmo_grazer_dornic(C.byref(p), C.byref(rng), ptr(prev), ptr(g), ptr(out), ptr(veff), 1 if trig_libm else 0) == 0
     return out, g, veff
+
+
+def runner2_params(L, par):
+    """(vegetation, grazer, RK4) oracle parameter blocks from the SPB = 2 runner vector of tests/golden/make_runner2_golden.py:
+    {a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, sigma0, sigma1, v1, aij, hij, ej, m1, pR1, dt, dx}."""
+    a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, s0, s1, v1, aij, hij, ej, m1, pR1, dt, dx = [float(x) for x in par]
+    pv = OParams()
+    pv.model, pv.L, pv.dt, pv.dx, pv.a = 2, L, dt, dx, a
+    pv.rc, pv.gmax, pv.alpha, pv.rW, pv.W0, pv.d, pv.K1, pv.K2 = c, gmax, alpha, rW, W0, d, K1, K2
+    pv.D0, pv.D1, pv.D2, pv.sigma0, pv.clamp_eps, pv.clamp_lo = D0, D2, D3, s0, 1e-12, -1e-80
+    pg = OGrazParams(L, 0, dt, dx, D1, v1, m1, s1, D0 / (dx * dx))
+    pc = OConsParams(L, 0, dt, a, c, gmax, alpha, rW, W0, K1, K2, D2 / (dx * dx), D3 / (dx * dx), aij, hij, ej)
+    r_max = pR1 / dx                       # r_max_effective = max(pR)/dx, R/:3405
+    return pv, pg, pc, int(r_max), pR1 / (dx * r_max)
+
+
+def step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=False):
+    """One SPB = 2 runner step in place on f [4][L*L] and gamma [L*L]; returns the grazer's advection vectors."""
+    cen = np.ascontiguousarray(central, dtype=np.int32)
+    veff = np.zeros((pv.L * pv.L, 2))
+    rc = oracle().tmo_step_2sp(C.byref(pv), C.byref(pg), C.byref(pc), cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen), fr,
+                               C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0)
+    assert rc == 0
+    return veff
