@@ -66,4 +66,10 @@ def test_spb2_runner_frames_match_reference(name):
             fi += 1
         O.step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=True)
         t += dt
+    t_max = dt * len(times)                       # t_meas.back() of the golden run (make_runner2_golden.py)
+    while t < t_max + dt:                         # the runner's loop condition, R/:3648
+        O.step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=True)
+        t += dt
     assert rng.overflow == 0
+    # every uniform the runner drew in its time loop is accounted for; its last one names the output file (jID, R/:4343)
+    assert rng.pos == int(RUN2[name + "_consumed"]) - 1
