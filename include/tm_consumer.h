@@ -9,8 +9,8 @@
  *                        Dxd2, K, A, H, E, t, dt, dx, g)   R/:2472-2527 with f_2Dor_2Sp R/:2445-2470
  *   tm_cons_grazer_dornic_host   replaces the grazer's Dornic loop with upwind advection inlined in
  *                        rietkerk_Dornic_2D_MultiSp, R/:3908-4114 (s = 1)
- * Not yet behind this ABI (remaining): the predator (SPB = 3) variants and the SPB >= 2 replicate runner that
- * chains these operators with the vegetation step of include/tm_lattice.h.
+ *   tm_cons_step2_*      the whole SPB = 2 time step resident on the device (below)
+ * Not yet behind this ABI (remaining): the predator (SPB = 3) variants.
  */
 #ifndef TM_CONSUMER_H
 #define TM_CONSUMER_H
@@ -60,6 +60,34 @@ typedef struct tm_graz_params {
 int tm_cons_grazer_dornic_host(tm_cons_ctx *, const tm_graz_params *p, uint64_t seed, uint32_t trial, uint32_t step,
                                const double *replay_u, uint32_t stride, const double *prev, double *gamma, double *rho_star,
                                double *v_eff, uint64_t *overflow);
+
+/* ---- The SPB = 2 time step, resident on the device ------------------------------------------------------------------
+ * Replaces the body of the time loop of rietkerk_Dornic_2D_MultiSp compiled with -DSPB=2, R/:3752-4183: vegetation Dornic
+ * (R/:3752-3809) -> spatial means and vegetation cover of DRho (R/:3813-3824) -> calc_gamma_2Sp_NonRefugia (R/:3844) ->
+ * grazer Dornic with upwind advection (R/:3908-4114; skipped when <G> == 0, R/:3910) -> RK4_Integrate_Stochastic_2Sp
+ * (R/:4137) -> clamp and commit (R/:4150-4181).  Nine launches per step on the context's stream and no host round trip: the
+ * scalars the reference derives between its loops (<P>, <G>, cover -> disc size) are reduced on the device and read there.
+ * The means come from a fixed summation tree, not the reference's left-to-right sum: reproducible, a few ulp from the
+ * sequential value (gamma inherits that: <= 1e-13 relative).
+ *
+ * setup: veg = the vegetation's constants as the SPB = 1 step takes them (struct tm_params of tm_lattice.h: L, dt, dx, d,
+ *   D0, sigma0, clamp_eps, clamp_lo are read); pg, pc as above; central = the full distance-sorted disc list
+ *   computeNeighboringSitesCentral(int(r_max)) as [n_central][2] = {row offset, column offset}; fr_graz = pR[1] /
+ *   (dx r_max_effective) (R/:3409).  upload: fields [4][L*L] = P, G, W, O; gamma [L*L] or NULL (zeros; the reference never
+ *   resets the array between steps, so it is state).
+ * run: nsteps steps with Philox streams keyed (seed, trial, step0 + s, cell); the grazer's streams use seed ^
+ *   0x9E3779B97F4A7C15.  Asynchronous: returns after enqueueing.  replay: ONE step with host-supplied uniforms, cell i of
+ *   the vegetation / the grazer taking its k-th from u_veg[i*stride + k] / u_graz[i*stride + k].
+ * download (synchronises): any of fields [4][L*L], gamma [L*L], v_eff [L*L][2] (the last step's advection vectors),
+ *   means[4] = {<P>, <G>, #{P > 0}, disc offsets summed} of the state the LAST step started from, overflow (replay draws
+ *   past `stride`, cumulative since upload) may be NULL. */
+struct tm_params;
+int tm_cons_step2_setup(tm_cons_ctx *, const struct tm_params *veg, const tm_graz_params *pg, const tm_cons_params *pc,
+                        const int32_t *central, int n_central, double fr_graz);
+int tm_cons_step2_upload(tm_cons_ctx *, const double *fields, const double *gamma);
+int tm_cons_step2_run(tm_cons_ctx *, uint64_t seed, uint32_t trial, uint32_t step0, int nsteps);
+int tm_cons_step2_replay(tm_cons_ctx *, const double *u_veg, const double *u_graz, uint32_t stride);
+int tm_cons_step2_download(tm_cons_ctx *, double *fields, double *gamma, double *v_eff, double *means, uint64_t *overflow);
 
 /* Device time (ms) of the kernels of the last call and how many launches that was. */
 int tm_cons_last_ms(tm_cons_ctx *, float *ms, int *n_launches);

@@ -778,7 +778,21 @@ int tmo_step_2sp(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_co
     const int eff = (int)(fr_graz * fr_graz * new_length);                              /* R/:2569 */
     tmo_gamma_perception(L, D, central, eff, avg_veg, avg_graz, gamma);                 /* R/:3844 */
     if (avg_graz == 0.0) memcpy(gout, D + n, sizeof(double) * (size_t)n);               /* R/:3910 */
-    else if (tmo_grazer_dornic(pg, rng, D + n, gamma, gout, veff ? veff : vtmp, trig_libm)) { free(work); return -1; }
+    else if (rng->kind == TMO_SRC_SEQ) {                                                /* the reference's single generator */
+        if (tmo_grazer_dornic(pg, rng, D + n, gamma, gout, veff ? veff : vtmp, trig_libm)) { free(work); return -1; }
+    } else {
+        /* per-cell streams: the two species of a cell must not share one.  REPLAY: the grazer's slices follow the
+         * vegetation's L*L slices in u; PHILOX: the grazer's key is seed ^ 0x9E3779B97F4A7C15 (the product's
+         * kGrazerSeedSalt, tm_consumer.cuh). */
+        tmo_rng gr = *rng;
+        gr.overflow = 0; gr.draws = 0;
+        if (rng->kind == TMO_SRC_REPLAY) {
+            const uint64_t skip = (uint64_t)n * rng->stride;
+            gr.u = rng->u + skip; gr.n_u = rng->n_u > skip ? rng->n_u - skip : 0;
+        } else gr.seed = rng->seed ^ 0x9E3779B97F4A7C15ull;
+        if (tmo_grazer_dornic(pg, &gr, D + n, gamma, gout, veff ? veff : vtmp, trig_libm)) { free(work); return -1; }
+        rng->overflow += gr.overflow; rng->draws += gr.draws;
+    }
     memcpy(f, vout, sizeof(double) * (size_t)n);
     memcpy(f + n, gout, sizeof(double) * (size_t)n);
     if (tmo_rk4_2sp(pc, f)) { free(work); return -1; }                                  /* R/:4137 */

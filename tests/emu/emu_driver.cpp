@@ -226,4 +226,31 @@ int emu_grazer_dornic(int L, const double *par, unsigned long long seed, unsigne
     else          emu_launch(grazer_dornic_kernel<false>, A, (unsigned)(tiles * L), kConsThreads, 0);
     return 0;
 }
+
+// nsteps SPB = 2 runner steps through the product's launch chain (cons_step2_enqueue), launch shapes as tm_consumer.cu.
+// par2 = {dt, dx, d, D0, sigma0, clamp_eps, clamp_lo, gD, gv, gM, gsigma, gD0floor, fr}; cpar as emu_cons_rk4's par.
+// u_veg/u_graz == nullptr: Philox (seed, trial, step0 + s); else one replay step.  dyn_out[4] = {<P>, <G>, #{P>0}, eff} of the
+// state the last step started from.
+int emu_cons_step2(int L, const double *par2, const double *cpar, const int *central, int n_central, unsigned long long seed,
+                   unsigned trial, unsigned step0, int nsteps, const double *u_veg, const double *u_graz, unsigned stride,
+                   double *fields, double *gamma, double *veff, double *dyn_out, unsigned long long *overflow)
+{
+    const size_t n = (size_t)L * L;
+    const ConsConsts cc = cons_consts(cpar[0], cpar[1], cpar[2], cpar[3], cpar[4], cpar[5], cpar[6], cpar[7], cpar[8], cpar[9], cpar[10],
+                                      cpar[11], cpar[12], cpar[13]);
+    const Step2Consts k = step2_consts(L, n_central, par2[12], par2[0], par2[1], par2[2], par2[3], par2[4], par2[5], par2[6], par2[7],
+                                       par2[8], par2[9], par2[10], par2[11], cc);
+    std::vector<double> star(2 * n), ya(4 * n), yb(4 * n), acc(4 * n), part(3 * kConsReduceBlocks);
+    Step2Dyn dyn{};
+    Step2Buffers b{};
+    b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.replay_veg = u_veg; b.replay_graz = u_graz; b.stride = stride;
+    *overflow = 0;
+    auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
+    for (int s = 0; s < nsteps; s++) cons_step2_enqueue(launch, k, b, seed, trial, step0 + (unsigned)s);
+    const double cells = (double)L * (double)L;
+    dyn_out[0] = dyn.sum_veg / cells; dyn_out[1] = dyn.sum_graz / cells; dyn_out[2] = dyn.occ_veg; dyn_out[3] = (double)dyn.eff;
+    return 0;
+}
 }

@@ -1,0 +1,191 @@
+"""The SPB = 2 (vegetation + grazer) time step resident on the device (tm_cons_step2_*): vegetation Dornic ->
+device-side means/cover -> perception field -> grazer Dornic with upwind advection -> four-field RK4 -> clamp.
+
+The oracle's tmo_step_2sp is pinned on the reference's rietkerk_Dornic_2D_MultiSp compiled with -DSPB=2
+(tests/test_consumer_oracle.py, tests/golden/runner_2sp.npz).  Here the product's launch chain is compared with it on
+per-cell streams (Philox and replay): CPU = the kernel SOURCE on host threads (tests/emu), GPU (-m gpu) = the C ABI.
+Tolerance: occupancy exact; values <= 1e-12 relative -- the spatial means come from a fixed summation tree instead of the
+reference's left-to-right sum (a few ulp), everything else shares every operation with the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import trophic_maelstorm_b200 as tm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "consumer_ops.npz"))
+RUN2 = np.load(os.path.join(HERE, "golden", "runner_2sp.npz"))
+dp = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    return C.CDLL(os.path.join(HERE, "emu", "libtm_emu.so"))
+
+
+def setup(L, seed, graz_scale=1.0):
+    """Runner constants of the SPB = 2 golden (the driver's), an L x L frame in the golden's regime."""
+    par = RUN2["mixed_par"].astype(np.float64)
+    pv, pg, pc, R, fr = O.runner2_params(L, par)
+    central = np.ascontiguousarray(GOLD["central_R%d" % R], dtype=np.int32)
+    init = RUN2["mixed_init"]
+    rng = np.random.default_rng(seed)
+    f = np.empty((4, L * L))
+    for s in range(4):
+        f[s] = rng.choice(init[s], L * L)
+    f[1] *= graz_scale
+    return par, pv, pg, pc, central, fr, f
+
+
+def product_params(L, par):
+    a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, s0, s1, v1, aij, hij, ej, m1, pR1, dt, dx = [float(x) for x in par]
+    veg = tm.rietkerk_params(L, a=a, dt=dt)
+    veg.dx, veg.rc, veg.gmax, veg.alpha, veg.rW, veg.W0, veg.d, veg.K1, veg.K2 = dx, c, gmax, alpha, rW, W0, d, K1, K2
+    veg.D0, veg.D1, veg.D2, veg.sigma0, veg.clamp_eps, veg.clamp_lo = D0, D2, D3, s0, 1e-12, -1e-80
+    graz = tm.GrazParams(L, 0, dt, dx, D1, v1, m1, s1, D0 / (dx * dx))
+    cons = tm.ConsParams(L, 0, dt, a, c, gmax, alpha, rW, W0, K1, K2, D2 / (dx * dx), D3 / (dx * dx), aij, hij, ej)
+    return veg, graz, cons
+
+
+def emu_step2(emu, L, par, central, fr, f, gamma, nsteps=1, seed=0, trial=0, step0=0, u_veg=None, u_graz=None, stride=0):
+    a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, s0, s1, v1, aij, hij, ej, m1, pR1, dt, dx = [float(x) for x in par]
+    par2 = np.array([dt, dx, d, D0, s0, 1e-12, -1e-80, D1, v1, m1, s1, D0 / (dx * dx), fr])
+    cpar = np.array([dt, a, c, gmax, alpha, rW, W0, K1, K2, D2 / (dx * dx), D3 / (dx * dx), aij, hij, ej])
+    f, g = f.copy(), gamma.copy()
+    veff, dyn, ovf = np.zeros((L * L, 2)), np.zeros(4), C.c_ulonglong()
+    emu.emu_cons_step2(L, par2.ctypes.data_as(dp), cpar.ctypes.data_as(dp), central.ctypes.data_as(C.POINTER(C.c_int)), len(central),
+                       C.c_ulonglong(seed), trial, step0, nsteps, None if u_veg is None else u_veg.ctypes.data_as(dp),
+                       None if u_graz is None else u_graz.ctypes.data_as(dp), stride, f.ctypes.data_as(dp), g.ctypes.data_as(dp),
+                       veff.ctypes.data_as(dp), dyn.ctypes.data_as(dp), C.byref(ovf))
+    return f, g, veff, dyn, ovf.value
+
+
+def oracle_steps(pv, pg, pc, central, fr, f, gamma, nsteps, seed=0, trial=0, step0=0, u=None, stride=0):
+    f, g = f.copy(), gamma.copy()
+    veff = None
+    for s in range(nsteps):
+        rng = O.make_rng(O.SRC_PHILOX, seed=seed, trial=trial, step=step0 + s) if u is None else O.make_rng(O.SRC_REPLAY, u=u, stride=stride)
+        veff = O.step_2sp(pv, pg, pc, central, fr, rng, f, g)
+        assert rng.overflow == 0
+    return f, g, veff
+
+
+def check(got, want, what):
+    gf, gg, gv = got
+    wf, wg, wv = want
+    for s in (0, 1):
+        assert np.array_equal(gf[s] > 0, wf[s] > 0), "%s: occupancy of field %d" % (what, s)
+    scale = np.maximum(np.abs(wf), 1e-300)
+    err = np.abs(gf - wf) / scale
+    err[(wf == 0) & (gf == 0)] = 0
+    assert err.max() <= 1e-12, "%s: fields %.3e" % (what, err.max())
+    assert np.abs(gg - wg).max() <= 1e-13, "%s: gamma" % what
+    assert np.array_equal(gv, wv), "%s: advection vectors" % what
+
+
+@pytest.mark.parametrize("L,nsteps", [(20, 3), (48, 2)])
+def test_emulated_step2_philox_matches_oracle(emu, L, nsteps):
+    par, pv, pg, pc, central, fr, f = setup(L, 5 + L)
+    gamma = np.zeros(L * L)
+    want = oracle_steps(pv, pg, pc, central, fr, f, gamma, nsteps, seed=77, trial=3, step0=10)
+    got = emu_step2(emu, L, par, central, fr, f, gamma, nsteps=nsteps, seed=77, trial=3, step0=10)
+    check(got[:3], want, "philox L=%d" % L)
+    assert got[4] == 0
+
+
+def test_emulated_step2_replay_matches_oracle(emu):
+    L, stride = 24, 64
+    par, pv, pg, pc, central, fr, f = setup(L, 9)
+    gamma = np.random.default_rng(2).random(L * L) * 0.5
+    u = np.random.default_rng(4).random(2 * L * L * stride)
+    want = oracle_steps(pv, pg, pc, central, fr, f, gamma, 1, u=u, stride=stride)
+    got = emu_step2(emu, L, par, central, fr, f, gamma, u_veg=u[: L * L * stride], u_graz=u[L * L * stride:], stride=stride)
+    check(got[:3], want, "replay")
+    assert got[4] == 0
+
+
+def test_emulated_step2_without_grazers_skips_their_loop(emu):
+    """<G> == 0: the grazer's loop is skipped (R/:3910) -- G stays zero, nothing is drawn for it, gamma is zeroed."""
+    L = 20
+    par, pv, pg, pc, central, fr, f = setup(L, 1, graz_scale=0.0)
+    gamma = np.full(L * L, 0.25)
+    want = oracle_steps(pv, pg, pc, central, fr, f, gamma, 2, seed=5)
+    got = emu_step2(emu, L, par, central, fr, f, gamma, nsteps=2, seed=5)
+    check((got[0], got[1], want[2]), want, "no grazers")
+    assert not got[0][1].any() and not got[1].any() and not got[2].any()
+
+
+def test_step2_device_scalars_follow_the_reference_rules(emu):
+    """The device-side scalars: <P>, <G> to a few ulp of the sequential sums, cover count exact, disc size by R/:2539, 2569."""
+    L = 32
+    par, pv, pg, pc, central, fr, f = setup(L, 3)
+    got = emu_step2(emu, L, par, central, fr, f, np.zeros(L * L), nsteps=1, seed=1)
+    mP, mG, occ, eff = got[3]
+    assert abs(mP - O.mean(f[0])) <= 1e-13 * abs(mP) and abs(mG - O.mean(f[1])) <= 1e-13 * abs(mG)
+    assert occ == O.occupied(f[0])
+    nfac = max(1 - occ / (L * L), 0.35)
+    assert eff == O.gamma_window(len(central), fr, nfac)[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,nsteps", [(20, 3), (150, 3), (512, 2)])
+def test_gpu_step2_philox_matches_oracle(L, nsteps):
+    par, pv, pg, pc, central, fr, f = setup(L, 5 + L)
+    gamma = np.zeros(L * L)
+    want = oracle_steps(pv, pg, pc, central, fr, f, gamma, nsteps, seed=77, trial=3, step0=10)
+    ops = tm.ConsumerOps(L)
+    ops.step2_setup(*product_params(L, par), central, fr)
+    ops.step2_upload(f, gamma)
+    ops.step2_run(77, trial=3, step0=10, nsteps=nsteps)
+    gf, gg, gv, means, ovf = ops.step2_download()
+    check((gf, gg, gv), want, "gpu philox L=%d" % L)
+    assert ovf == 0
+    ms, launches = ops.last_ms()
+    assert launches == 9 * nsteps and ms > 0
+    ops.close()
+
+
+@pytest.mark.gpu
+def test_gpu_step2_replay_and_empty_grazers():
+    L, stride = 64, 64
+    par, pv, pg, pc, central, fr, f = setup(L, 9)
+    gamma = np.random.default_rng(2).random(L * L) * 0.5
+    u = np.random.default_rng(4).random(2 * L * L * stride)
+    want = oracle_steps(pv, pg, pc, central, fr, f, gamma, 1, u=u, stride=stride)
+    ops = tm.ConsumerOps(L)
+    ops.step2_setup(*product_params(L, par), central, fr)
+    ops.step2_upload(f, gamma)
+    ops.step2_replay(u[: L * L * stride], u[L * L * stride:], stride)
+    gf, gg, gv, means, ovf = ops.step2_download()
+    check((gf, gg, gv), want, "gpu replay")
+    assert ovf == 0
+    f0 = f.copy(); f0[1] = 0.0
+    want = oracle_steps(pv, pg, pc, central, fr, f0, gamma, 2, seed=5)
+    ops.step2_upload(f0, gamma)
+    ops.step2_run(5, nsteps=2)
+    gf, gg, gv, means, ovf = ops.step2_download()
+    check((gf, gg, want[2]), want, "gpu no grazers")
+    assert not gf[1].any() and not gg.any() and means[1] == 0.0
+    ops.close()
+
+
+@pytest.mark.gpu
+def test_gpu_step2_matches_emulation_and_is_reproducible():
+    """Two runs of the resident stepper give identical bits (fixed summation tree, counter-based streams)."""
+    L = 256
+    par, pv, pg, pc, central, fr, f = setup(L, 12)
+    ops = tm.ConsumerOps(L)
+    ops.step2_setup(*product_params(L, par), central, fr)
+    outs = []
+    for _ in range(2):
+        ops.step2_upload(f, None)
+        ops.step2_run(123, nsteps=5)
+        outs.append(ops.step2_download())
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.isfinite(outs[0][0]).all() and (outs[0][0] >= 0).all()
+    ops.close()

@@ -3,7 +3,7 @@ import ctypes as C
 
 import numpy as np
 
-from .lattice import TmError, lib
+from .lattice import Params, TmError, lib
 
 
 class ConsParams(C.Structure):
@@ -17,7 +17,8 @@ class GrazParams(C.Structure):
 
 
 CONS_ABI_SYMBOLS = ["tm_cons_create", "tm_cons_destroy", "tm_cons_last_error", "tm_cons_rk4_host", "tm_cons_gamma_host",
-                    "tm_cons_grazer_dornic_host", "tm_cons_last_ms"]
+                    "tm_cons_grazer_dornic_host", "tm_cons_last_ms", "tm_cons_step2_setup", "tm_cons_step2_upload", "tm_cons_step2_run",
+                    "tm_cons_step2_replay", "tm_cons_step2_download"]
 
 _bound = False
 
@@ -36,6 +37,11 @@ def _lib():
             "tm_cons_grazer_dornic_host": (i, [vp, C.POINTER(GrazParams), C.c_uint64, C.c_uint32, C.c_uint32, dp, C.c_uint32, dp, dp, dp, dp,
                                                C.POINTER(C.c_uint64)]),
             "tm_cons_last_ms": (i, [vp, C.POINTER(C.c_float), C.POINTER(i)]),
+            "tm_cons_step2_setup": (i, [vp, C.POINTER(Params), C.POINTER(GrazParams), C.POINTER(ConsParams), C.POINTER(C.c_int32), i, C.c_double]),
+            "tm_cons_step2_upload": (i, [vp, dp, dp]),
+            "tm_cons_step2_run": (i, [vp, C.c_uint64, C.c_uint32, C.c_uint32, i]),
+            "tm_cons_step2_replay": (i, [vp, dp, dp, C.c_uint32]),
+            "tm_cons_step2_download": (i, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint64)]),
         }
         for name, (res, args) in sig.items():
             f = getattr(L, name)
@@ -102,6 +108,34 @@ class ConsumerOps:
         self._ck(self._l.tm_cons_grazer_dornic_host(self._ctx, C.byref(params), seed, trial, step, ru, stride, _dptr(prev), _dptr(g),
                                                     _dptr(out), _dptr(veff), C.byref(ovf)))
         return out, g, veff, ovf.value
+
+    # ---- the SPB = 2 time step resident on the device (tm_cons_step2_*) ----
+    def step2_setup(self, veg, graz, cons, central, fr):
+        cen = np.ascontiguousarray(central, dtype=np.int32)
+        self._ck(self._l.tm_cons_step2_setup(self._ctx, C.byref(veg), C.byref(graz), C.byref(cons), cen.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             len(cen), fr))
+
+    def step2_upload(self, fields, gamma=None):
+        f = np.ascontiguousarray(fields, dtype=np.float64)
+        assert f.size == 4 * self.L * self.L
+        g = None if gamma is None else np.ascontiguousarray(gamma, dtype=np.float64)
+        self._ck(self._l.tm_cons_step2_upload(self._ctx, _dptr(f), None if g is None else _dptr(g)))
+
+    def step2_run(self, seed, trial=0, step0=0, nsteps=1):
+        self._ck(self._l.tm_cons_step2_run(self._ctx, seed, trial, step0, nsteps))
+
+    def step2_replay(self, u_veg, u_graz, stride):
+        n = self.L * self.L
+        uv, ug = np.ascontiguousarray(u_veg, dtype=np.float64), np.ascontiguousarray(u_graz, dtype=np.float64)
+        assert uv.size == n * stride and ug.size == n * stride
+        self._ck(self._l.tm_cons_step2_replay(self._ctx, _dptr(uv), _dptr(ug), stride))
+
+    def step2_download(self):
+        """-> (fields [4, L*L], gamma, v_eff [L*L, 2], means {<P>, <G>, #{P>0}, eff} of the last step's entry state, overflow)."""
+        n = self.L * self.L
+        f, g, v, m, ovf = np.empty((4, n)), np.empty(n), np.empty((n, 2)), np.empty(4), C.c_uint64()
+        self._ck(self._l.tm_cons_step2_download(self._ctx, _dptr(f), _dptr(g), _dptr(v), _dptr(m), C.byref(ovf)))
+        return f, g, v, m, ovf.value
 
     def last_ms(self):
         ms, n = C.c_float(), C.c_int()

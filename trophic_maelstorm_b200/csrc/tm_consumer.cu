@@ -20,6 +20,12 @@ struct tm_cons_ctx {
     int *d_off = nullptr; int off_cap = 0;
     double *d_replay = nullptr; size_t replay_cap = 0;
     unsigned long long *d_ovf = nullptr;
+    // the resident SPB = 2 stepper (tm_cons_step2_*)
+    bool step2_ready = false;
+    Step2Consts k2{};
+    double *d_star = nullptr, *d_veff = nullptr, *d_part = nullptr;
+    Step2Dyn *d_dyn = nullptr;
+    int *d_central = nullptr;
     int n_launches = 0;
     std::string err;
 };
@@ -29,6 +35,24 @@ struct tm_cons_ctx {
         cudaError_t e_ = (call);                                                       \
         if (e_ != cudaSuccess) { c->err = std::string(#call) + ": " + cudaGetErrorString(e_); return TM_E_CUDA; } \
     } while (0)
+
+namespace {
+struct CudaLaunch {
+    cudaStream_t st;
+    template <class K, class A> void operator()(K kernel, const A &args, unsigned grid, unsigned block, size_t smem) const
+    {
+        kernel<<<grid, block, smem, st>>>(args);
+    }
+};
+
+static Step2Buffers step2_buffers(tm_cons_ctx *c)
+{
+    Step2Buffers b{};
+    b.state = c->d_state; b.star = c->d_star; b.ya = c->d_ya; b.yb = c->d_yb; b.acc = c->d_acc; b.gamma = c->d_gamma; b.veff = c->d_veff;
+    b.part = c->d_part; b.dyn = c->d_dyn; b.central = c->d_central; b.overflow = c->d_ovf;
+    return b;
+}
+} // namespace
 
 extern "C" {
 
@@ -40,6 +64,7 @@ int tm_cons_destroy(tm_cons_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_state); cudaFree(c->d_ya); cudaFree(c->d_yb); cudaFree(c->d_acc); cudaFree(c->d_gamma); cudaFree(c->d_off); cudaFree(c->d_replay); cudaFree(c->d_ovf);
+    cudaFree(c->d_star); cudaFree(c->d_veff); cudaFree(c->d_part); cudaFree(c->d_dyn); cudaFree(c->d_central);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -124,6 +149,7 @@ int tm_cons_gamma_host(tm_cons_ctx *c, const double *prey, const int32_t *offset
     A.rho_inverse = rho_avg_prey >= eps ? 1 / rho_avg_prey : 1 / eps;                  // R/:2548
     A.zero = (rho_avg_self < eps || rho_avg_prey < eps) ? 1 : 0;                       // R/:2575-2578
     const int tiles = (c->L + kConsThreads - 1) / kConsThreads;
+    CONS_CK(cudaFuncSetAttribute(cons_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 10000 * (int)sizeof(int)));
     CONS_CK(cudaEventRecord(c->ev0, c->stream));
     cons_gamma_kernel<<<(unsigned)((long long)tiles * c->L), kConsThreads, sizeof(int) * 2 * n_offsets, c->stream>>>(A);
     CONS_CK(cudaGetLastError());
@@ -179,6 +205,115 @@ int tm_cons_grazer_dornic_host(tm_cons_ctx *c, const tm_graz_params *p, uint64_t
     CONS_CK(cudaMemcpyAsync(gamma, c->d_gamma, n, cudaMemcpyDeviceToHost, c->stream));
     CONS_CK(cudaMemcpyAsync(&ovf, c->d_ovf, sizeof ovf, cudaMemcpyDeviceToHost, c->stream));
     CONS_CK(cudaStreamSynchronize(c->stream));
+    if (overflow) *overflow = ovf;
+    return TM_OK;
+}
+
+// ---- resident SPB = 2 stepper ---------------------------------------------------------------------------------------
+
+int tm_cons_step2_setup(tm_cons_ctx *c, const tm_params *veg, const tm_graz_params *pg, const tm_cons_params *pc,
+                        const int32_t *central, int n_central, double fr_graz)
+{
+    if (!c) return TM_E_ARG;
+    if (!veg || !pg || !pc || !central || veg->L != c->L || pg->L != c->L || pc->L != c->L || n_central < 1 || n_central > 10000 ||
+        !(fr_graz >= 0 && fr_graz <= 1) || !(pg->sigma > 0) || !(veg->sigma0 > 0) || !(veg->dx > 0)) {
+        c->err = "tm_cons_step2_setup: bad argument (all three L must equal the context's; 1 <= n_central <= 10000; 0 <= fr <= 1; sigma, dx > 0)";
+        return TM_E_ARG;
+    }
+    CONS_CK(cudaSetDevice(c->device));
+    const size_t nn = (size_t)c->L * c->L;
+    if (!c->d_star) CONS_CK(cudaMalloc(&c->d_star, 2 * nn * sizeof(double)));
+    if (!c->d_veff) CONS_CK(cudaMalloc(&c->d_veff, 2 * nn * sizeof(double)));
+    if (!c->d_part) CONS_CK(cudaMalloc(&c->d_part, sizeof(double) * 3 * kConsReduceBlocks));
+    if (!c->d_dyn) CONS_CK(cudaMalloc(&c->d_dyn, sizeof(Step2Dyn)));
+    if (!c->d_ovf) CONS_CK(cudaMalloc(&c->d_ovf, sizeof(unsigned long long)));
+    cudaFree(c->d_central); c->d_central = nullptr;
+    CONS_CK(cudaMalloc(&c->d_central, sizeof(int) * 2 * n_central));
+    CONS_CK(cudaMemcpyAsync(c->d_central, central, sizeof(int) * 2 * n_central, cudaMemcpyHostToDevice, c->stream));
+    CONS_CK(cudaMemsetAsync(c->d_ovf, 0, sizeof(unsigned long long), c->stream));
+    CONS_CK(cudaMemsetAsync(c->d_veff, 0, 2 * nn * sizeof(double), c->stream));
+    CONS_CK(cudaMemsetAsync(c->d_gamma, 0, nn * sizeof(double), c->stream));
+    CONS_CK(cudaFuncSetAttribute(cons_gamma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 10000 * (int)sizeof(int)));
+    CONS_CK(cudaStreamSynchronize(c->stream));   // `central` is the caller's again
+    const ConsConsts cc = cons_consts(pc->dt, pc->a, pc->c, pc->gmax, pc->alpha, pc->rW, pc->W0, pc->K1, pc->K2, pc->Dw, pc->Do,
+                                      pc->A01, pc->H01, pc->E1);
+    c->k2 = step2_consts(c->L, n_central, fr_graz, veg->dt, veg->dx, veg->d, veg->D0, veg->sigma0, veg->clamp_eps, veg->clamp_lo,
+                         pg->D, pg->v, pg->M, pg->sigma, pg->D0_floor, cc);
+    c->step2_ready = true;
+    return TM_OK;
+}
+
+int tm_cons_step2_upload(tm_cons_ctx *c, const double *fields, const double *gamma)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->step2_ready || !fields) { c->err = "tm_cons_step2_upload: call tm_cons_step2_setup first; fields must not be NULL"; return TM_E_ARG; }
+    const size_t n = (size_t)c->L * c->L * sizeof(double);
+    CONS_CK(cudaSetDevice(c->device));
+    CONS_CK(cudaMemcpyAsync(c->d_state, fields, 4 * n, cudaMemcpyHostToDevice, c->stream));
+    if (gamma) CONS_CK(cudaMemcpyAsync(c->d_gamma, gamma, n, cudaMemcpyHostToDevice, c->stream));
+    else CONS_CK(cudaMemsetAsync(c->d_gamma, 0, n, c->stream));
+    CONS_CK(cudaMemsetAsync(c->d_ovf, 0, sizeof(unsigned long long), c->stream));
+    CONS_CK(cudaStreamSynchronize(c->stream));
+    return TM_OK;
+}
+
+
+int tm_cons_step2_run(tm_cons_ctx *c, uint64_t seed, uint32_t trial, uint32_t step0, int nsteps)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->step2_ready || nsteps < 0) { c->err = "tm_cons_step2_run: call tm_cons_step2_setup first; nsteps >= 0"; return TM_E_ARG; }
+    CONS_CK(cudaSetDevice(c->device));
+    const Step2Buffers b = step2_buffers(c);
+    CONS_CK(cudaEventRecord(c->ev0, c->stream));
+    for (int s = 0; s < nsteps; s++) cons_step2_enqueue(CudaLaunch{c->stream}, c->k2, b, seed, trial, step0 + (uint32_t)s);
+    CONS_CK(cudaGetLastError());
+    CONS_CK(cudaEventRecord(c->ev1, c->stream));
+    c->n_launches = kStep2Launches * nsteps;
+    return TM_OK;
+}
+
+int tm_cons_step2_replay(tm_cons_ctx *c, const double *u_veg, const double *u_graz, uint32_t stride)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->step2_ready || !u_veg || !u_graz || stride < 1) { c->err = "tm_cons_step2_replay: call tm_cons_step2_setup first; both uniform arrays and stride >= 1 are required"; return TM_E_ARG; }
+    CONS_CK(cudaSetDevice(c->device));
+    const size_t need = (size_t)c->L * c->L * stride * sizeof(double);
+    if (2 * need > c->replay_cap) {
+        cudaFree(c->d_replay); c->d_replay = nullptr; c->replay_cap = 0;
+        CONS_CK(cudaMalloc(&c->d_replay, 2 * need));
+        c->replay_cap = 2 * need;
+    }
+    CONS_CK(cudaMemcpyAsync(c->d_replay, u_veg, need, cudaMemcpyHostToDevice, c->stream));
+    CONS_CK(cudaMemcpyAsync((char *)c->d_replay + need, u_graz, need, cudaMemcpyHostToDevice, c->stream));
+    Step2Buffers b = step2_buffers(c);
+    b.replay_veg = c->d_replay; b.replay_graz = (const double *)((char *)c->d_replay + need); b.stride = stride;
+    CONS_CK(cudaEventRecord(c->ev0, c->stream));
+    cons_step2_enqueue(CudaLaunch{c->stream}, c->k2, b, 0, 0, 0);
+    CONS_CK(cudaGetLastError());
+    CONS_CK(cudaEventRecord(c->ev1, c->stream));
+    c->n_launches = kStep2Launches;
+    CONS_CK(cudaStreamSynchronize(c->stream));   // the uniform arrays are the caller's again
+    return TM_OK;
+}
+
+int tm_cons_step2_download(tm_cons_ctx *c, double *fields, double *gamma, double *v_eff, double *means, uint64_t *overflow)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->step2_ready) { c->err = "tm_cons_step2_download: call tm_cons_step2_setup first"; return TM_E_ARG; }
+    const size_t n = (size_t)c->L * c->L * sizeof(double);
+    CONS_CK(cudaSetDevice(c->device));
+    unsigned long long ovf = 0;
+    Step2Dyn d{};
+    if (fields) CONS_CK(cudaMemcpyAsync(fields, c->d_state, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (gamma) CONS_CK(cudaMemcpyAsync(gamma, c->d_gamma, n, cudaMemcpyDeviceToHost, c->stream));
+    if (v_eff) CONS_CK(cudaMemcpyAsync(v_eff, c->d_veff, 2 * n, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaMemcpyAsync(&d, c->d_dyn, sizeof d, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaMemcpyAsync(&ovf, c->d_ovf, sizeof ovf, cudaMemcpyDeviceToHost, c->stream));
+    CONS_CK(cudaStreamSynchronize(c->stream));
+    if (means) {
+        const double cells = (double)c->L * (double)c->L;
+        means[0] = d.sum_veg / cells; means[1] = d.sum_graz / cells; means[2] = d.occ_veg; means[3] = (double)d.eff;
+    }
     if (overflow) *overflow = ovf;
     return TM_OK;
 }

@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include "tm_samplers.cuh"
 #include <type_traits>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define TMC_D __device__ __forceinline__
@@ -40,6 +41,84 @@ namespace tml {
 
 constexpr int kConsThreads = 128;
 
+// Scalars of one SPB = 2 runner step that the reference derives on the host between its loops (R/:3813-3824, 2533-2578,
+// 3910).  Here a two-kernel reduction leaves them in device memory and the following kernels read them there, so a
+// whole time step is enqueued without a host round trip.
+struct Step2Dyn {
+    double sum_veg, sum_graz, occ_veg;   // sums over DRho[0], DRho[1]; #{DRho[0] > 0}
+    double rho_inverse;                  // 1 / max(<veg>, 1e-12)                          R/:2548
+    int eff;                             // disc offsets summed: int(fr^2 * new_length)    R/:2539, 2569
+    int zero;                            // <grazer> or <veg> below 1e-12: gamma = 0       R/:2575-2578
+    int skip_graz;                       // <grazer> == 0: the grazer's Dornic loop is skipped, R/:3910
+    int pad_;
+};
+
+constexpr int kConsReduceThreads = 256;
+constexpr int kConsReduceBlocks = 296;   // two CTAs per SM; the summation tree below is fixed by these two constants
+
+struct ReduceArgs {
+    long long n;                 // L*L
+    const double *P, *G;         // DRho[0], DRho[1]
+    double *part;                // [gridDim.x][3]
+};
+
+// mean_of_vector / occupied_sites_of_vector (R/:1211, 1245) of the vegetation and the grazer as block partials.  The
+// reference sums left to right; this is a fixed tree (thread-strided partials of a contiguous chunk, pairwise in shared
+// memory, then block partials in order), reproducible run to run and machine to machine but rounded differently from the
+// sequential sum: <rho> differs by a few ulp (tests: <= 1e-13 relative), the integer count is exact.
+TMC_G void cons_reduce_kernel(const ReduceArgs A)
+{
+    TMC_SMEM(smem_raw);
+    double *sh = reinterpret_cast<double *>(smem_raw);
+    const int tid = threadIdx.x, T = kConsReduceThreads;
+    const long long chunk = (A.n + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * chunk;
+    long long hi = lo + chunk;
+    if (hi > A.n) hi = A.n;
+    double sp = 0.0, sg = 0.0, oc = 0.0;
+    for (long long i = lo + tid; i < hi; i += T) {
+        const double p = A.P[i];
+        sp += p; sg += A.G[i];
+        if (p > 0) oc += 1;
+    }
+    sh[tid] = sp; sh[T + tid] = sg; sh[2 * T + tid] = oc;
+    __syncthreads();
+    for (int s = T / 2; s > 0; s >>= 1) {
+        if (tid < s) { sh[tid] += sh[tid + s]; sh[T + tid] += sh[T + tid + s]; sh[2 * T + tid] += sh[2 * T + tid + s]; }
+        __syncthreads();
+    }
+    if (tid == 0) { A.part[3 * blockIdx.x] = sh[0]; A.part[3 * blockIdx.x + 1] = sh[T]; A.part[3 * blockIdx.x + 2] = sh[2 * T]; }
+}
+
+struct FinalizeArgs {
+    int L, nblocks, n_central;   // n_central: length of the full disc list of computeNeighboringSitesCentral(int(r_max))
+    double fr;                   // pR[1] / (dx r_max_effective), R/:3409
+    const double *part;
+    Step2Dyn *dyn;
+};
+
+TMC_G void cons_finalize_kernel(const FinalizeArgs A)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double sp = 0.0, sg = 0.0, oc = 0.0;
+    for (int b = 0; b < A.nblocks; b++) { sp += A.part[3 * b]; sg += A.part[3 * b + 1]; oc += A.part[3 * b + 2]; }
+    const double eps = 1.0e-12;                                       // R/:2537
+    const double cells = (double)A.L * (double)A.L;
+    const double avg_veg = sp / cells, avg_graz = sg / cells;        // R/:3813-3818
+    double nR_fac = 1 - oc / (A.L * A.L);                             // R/:3822
+    if (nR_fac < 0.35) nR_fac = 0.35;
+    int new_length = (int)(nR_fac * nR_fac * A.n_central);            // R/:2539
+    if (new_length < 1) new_length = 1;
+    Step2Dyn d;
+    d.sum_veg = sp; d.sum_graz = sg; d.occ_veg = oc;
+    d.eff = (int)(A.fr * A.fr * new_length);                          // R/:2569
+    d.rho_inverse = avg_veg >= eps ? 1 / avg_veg : 1 / eps;           // R/:2548
+    d.zero = (avg_graz < eps || avg_veg < eps) ? 1 : 0;               // R/:2575-2578
+    d.skip_graz = (avg_graz == 0.0) ? 1 : 0;                          // R/:3910
+    d.pad_ = 0;
+    *A.dyn = d;
+}
+
 struct GammaArgs {
     int L, eff;                  // lattice side; number of disc offsets summed (R/:2569)
     const double *prey;          // [L*L] Rho_t[s-1]
@@ -47,10 +126,18 @@ struct GammaArgs {
     double rho_inverse;          // 1 / max(<prey>, 1e-12)  (R/:2548)
     int zero;                    // <self> or <prey> below 1e-12: gamma = 0 everywhere (R/:2575-2578)
     double *gamma;               // [L*L] in/out
+    const Step2Dyn *dyn;         // non-null: eff, rho_inverse and zero come from the device-side scalars of this step
+                                 // (the launch reserves shared memory for `eff` offsets = the upper bound)
 };
 
-TMC_G void cons_gamma_kernel(const GammaArgs A)
+TMC_G void cons_gamma_kernel(const GammaArgs A_in)
 {
+    GammaArgs A = A_in;
+    if (A.dyn) {
+        const Step2Dyn d = *A.dyn;
+        if (d.eff < A.eff) A.eff = d.eff;          // d.eff <= fr^2 n_central by construction
+        A.rho_inverse = d.rho_inverse; A.zero = d.zero;
+    }
     const int g = A.L, tid = threadIdx.x;
     const int tiles = (g + kConsThreads - 1) / kConsThreads;
     const int c_i = (int)(blockIdx.x / tiles), c_j = (int)(blockIdx.x % tiles) * kConsThreads + tid;
@@ -83,9 +170,13 @@ struct GrazerArgs {
     unsigned long long seed; unsigned int trial, step;
     const double *replay_u; unsigned int stride;   // REPLAY: [L*L][stride]
     unsigned long long *overflow;
+    DornicConsts veg;                         // VEG variant: the vegetation's constants (R/:3461-3463), same for every cell
+    const Step2Dyn *dyn;                      // non-null and dyn->skip_graz: rho* = prev, nothing drawn (R/:3910)
 };
 
-template <bool REPLAY>
+// VEG = true: the vegetation's Dornic loop R/:3752-3809 on an unpadded field (no advection, no direction draw, constant
+// beta/lambda, alpha_i = (D0/dx^2) (up + down + left + right) in the reference's order): the first kernel of the SPB = 2 step.
+template <bool REPLAY, bool VEG = false>
 TMC_G void grazer_dornic_kernel(const GrazerArgs A)
 {
     const int g = A.L;
@@ -96,11 +187,22 @@ TMC_G void grazer_dornic_kernel(const GrazerArgs A)
     const int up = (r == 0 ? g - 1 : r - 1), dn = (r == g - 1 ? 0 : r + 1), lf = (q == 0 ? g - 1 : q - 1), rt = (q == g - 1 ? 0 : q + 1);
     const double dx2 = A.dx * A.dx, dx1 = 1 / A.dx, dx1_2 = 1 / (dx2), dxb2 = A.dx / 2.0;   // R/:3455
     const double sigma2_1 = 1 / (A.sigma * A.sigma);
-    double gm = A.gamma[i];
-    if (gm > 1) { gm = 1; A.gamma[i] = gm; }
     typename std::conditional<REPLAY, ReplaySrc, PhiloxSrc>::type src;
     if constexpr (REPLAY) src.begin(A.replay_u + (size_t)i * A.stride, A.stride);
     else src.begin((uint32_t)i, A.trial, A.step, A.seed);
+    if constexpr (VEG) {
+        const double *P = A.prev;
+        const double alpha_i = A.veg.diffc * (P[up * g + q] + P[dn * g + q] + P[r * g + lf] + P[r * g + rt]);   // R/:3756
+        const double rho_i = P[i];
+        double res = rho_i;
+        if (!(alpha_i == 0 && rho_i == 0)) res = dornic_cell<kRietkerk>(A.veg, src, alpha_i, rho_i);          // R/:3759-3793
+        A.out[i] = res;
+        if (src.overflow_count()) atomicAdd(A.overflow, (unsigned long long)src.overflow_count());
+        return;
+    }
+    if (A.dyn && A.dyn->skip_graz) { A.out[i] = A.prev[i]; return; }
+    double gm = A.gamma[i];
+    if (gm > 1) { gm = 1; A.gamma[i] = gm; }
     const double ran = src.next();                                                         // R/:3993
     double sn, cs;
     sincos_turn128(128.0 * ran, sincos_table(), sn, cs);
@@ -139,10 +241,13 @@ struct RkStageArgs {
     int L, stage;                // stage 1..4
     ConsConsts c;
     const double *base;          // Rho_t   [4][L*L]  (P, G, W, O)
+    const double *base_pg;       // non-null: fields 0, 1 of Rho_t (the two rho* of this step) live here as [2][L*L]
     const double *Y;             // stage state (== base for stage 1)
     double *Ynext;               // next stage state (stages 1-3)
     double *acc;                 // K1 (+ 2 K2 (+ 2 K3)) [4][L*L]
     double *out;                 // stage 4: the committed state (may alias base)
+    int clamp;                   // stage 4: apply `if (v < eps && v >= lo) v = 0` (R/:4176) to the committed values
+    double eps, lo;
 };
 
 // f_2Dor_2Sp R/:2460-2468 at one site, the reference's operation order
@@ -165,15 +270,120 @@ TMC_G void cons_rk4_stage_kernel(const RkStageArgs A)
     const int up = (r == 0 ? g - 1 : r - 1) * g + q, dn = (r == g - 1 ? 0 : r + 1) * g + q;      // R/:1622-1626
     const int lf = r * g + (q == 0 ? g - 1 : q - 1), rt = r * g + (q == g - 1 ? 0 : q + 1);
     const double *Y = A.Y, *W = Y + 2 * n, *O = Y + 3 * n;
+    const double *B01 = A.base_pg ? A.base_pg : A.base;
+    const double *Ypg = (A.stage == 1 && A.base_pg) ? A.base_pg : Y;
     double f[4];
-    cons_rhs(A.c, Y[i], Y[n + i], W[i], O[i], W[up], W[dn], W[lf], W[rt], O[up], O[dn], O[lf], O[rt], f);
+    cons_rhs(A.c, Ypg[i], Ypg[n + i], W[i], O[i], W[up], W[dn], W[lf], W[rt], O[up], O[dn], O[lf], O[rt], f);
     const double h = A.stage == 3 ? A.c.dt : A.c.dt2;
     for (int s = 0; s < 4; s++) {
         const int k = s * n + i;
-        if (A.stage == 1) { A.acc[k] = f[s]; A.Ynext[k] = A.base[k] + (h) * f[s]; }
-        else if (A.stage < 4) { A.acc[k] = A.acc[k] + 2.0 * f[s]; A.Ynext[k] = A.base[k] + (h) * f[s]; }
-        else A.out[k] = A.base[k] + (A.c.dt6) * (A.acc[k] + f[s]);    // Rho_t += dt6 (K1 + 2 K2 + 2 K3 + K4), R/:2506
+        const double b = s < 2 ? B01[k] : A.base[k];
+        if (A.stage == 1) { A.acc[k] = f[s]; A.Ynext[k] = b + (h) * f[s]; }
+        else if (A.stage < 4) { A.acc[k] = A.acc[k] + 2.0 * f[s]; A.Ynext[k] = b + (h) * f[s]; }
+        else {
+            double v = b + (A.c.dt6) * (A.acc[k] + f[s]);     // Rho_t += dt6 (K1 + 2 K2 + 2 K3 + K4), R/:2506
+            if (A.clamp && v < A.eps && v >= A.lo) v = 0.0;           // R/:4176
+            A.out[k] = v;
+        }
     }
 }
+
+// ---- one SPB = 2 runner step as a chain of launches (host side; shared by tm_consumer.cu and tests/emu) ----------------
+struct Step2Consts {
+    int L, n_central;            // n_central: length of the full disc list (the gamma kernel's shared-memory bound)
+    double fr;                   // pR[1] / (dx r_max_effective)
+    DornicConsts veg;            // R/:3461-3463
+    double dt, dx, D, v, M, sigma, D0floor;   // the grazer's (GrazerArgs)
+    ConsConsts c;
+    double eps, lo;              // clamp R/:4176
+};
+
+struct Step2Buffers {
+    double *state;               // [4][n] P, G, W, O: Rho_dt == DRho between steps
+    double *star;                // [2][n] rho* of P and G
+    double *ya, *yb, *acc;       // [4][n] each
+    double *gamma, *veff;        // [n], [n][2]
+    double *part;                // [kConsReduceBlocks][3]
+    Step2Dyn *dyn;
+    const int *central;          // [n_central][2]
+    unsigned long long *overflow;
+    const double *replay_veg, *replay_graz;   // both null: Philox; else [n][stride] each
+    unsigned int stride;
+};
+
+// The grazer's Philox streams use the seed with this constant xor-ed in, so that the two species of a cell draw from
+// different streams (the vegetation keeps the plain seed: its rho* equals the SPB = 1 step's for the same seed).
+constexpr unsigned long long kGrazerSeedSalt = 0x9E3779B97F4A7C15ull;
+
+// host-side constants of a step from the runner's arguments (R/:3455-3480), shared by the C ABI and the emulator
+inline Step2Consts step2_consts(int L, int n_central, double fr, double dt, double dx, double d, double D0, double sigma0,
+                                double clamp_eps, double clamp_lo, double gD, double gv, double gM, double gsigma, double gD0floor,
+                                const ConsConsts &c)
+{
+    Step2Consts k{};
+    k.L = L; k.n_central = n_central; k.fr = fr;
+    const double dx2 = dx * dx;
+    const double beta = -d - 4 * D0 / dx2;                            // R/:3461
+    const double lambda_exp = exp(beta * dt);
+    k.veg.lambda = 2 * beta / (sigma0 * sigma0 * (lambda_exp - 1.0)); // R/:3462
+    k.veg.diffc = D0 / dx2;
+    k.veg.sigma2 = sigma0 * sigma0;
+    k.veg.sigma2_1 = 1 / (sigma0 * sigma0);
+    k.veg.ll = k.veg.lambda * lambda_exp;
+    k.dt = dt; k.dx = dx; k.D = gD; k.v = gv; k.M = gM; k.sigma = gsigma; k.D0floor = gD0floor;
+    k.c = c; k.eps = clamp_eps; k.lo = clamp_lo;
+    return k;
+}
+
+inline ConsConsts cons_consts(double dt, double a, double c, double gmax, double alpha, double rW, double W0, double K1, double K2,
+                              double Dw, double Do, double A01, double H01, double E1)
+{
+    ConsConsts k{};
+    k.dt = dt; k.dt2 = dt / 2.0; k.dt6 = dt / 6.0;                    // R/:171
+    k.a = a; k.cgmax = c * gmax; k.gmax = gmax; k.alpha = alpha; k.rW = rW; k.K1 = K1; k.K2 = K2;
+    k.K2W0 = K2 * W0; k.Dw = Dw; k.Do = Do;
+    k.A01 = A01; k.A01H01 = A01 * H01; k.EA1 = E1 * A01;              // R/:2452
+    return k;
+}
+
+// launch(kernel, args, grid, block, dynamic shared bytes); order and arguments as the reference's loop body R/:3752-4183:
+// vegetation Dornic -> means and cover of DRho -> perception field -> grazer Dornic -> four RK4 stages (clamp in the last)
+template <class Launch>
+inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, const Step2Buffers &b, unsigned long long seed,
+                               unsigned int trial, unsigned int step)
+{
+    const int L = k.L;
+    const long long n = (long long)L * L;
+    const int tiles = (L + kConsThreads - 1) / kConsThreads;
+    const unsigned grid = (unsigned)((long long)tiles * L);
+    const bool replay = b.replay_veg != nullptr;
+    GrazerArgs V{};
+    V.L = L; V.dt = k.dt; V.dx = k.dx; V.D = k.D; V.v = k.v; V.M = k.M; V.sigma = k.sigma; V.D0floor = k.D0floor;
+    V.prev = b.state; V.gamma = b.gamma; V.out = b.star; V.veff = b.veff;
+    V.seed = seed; V.trial = trial; V.step = step; V.replay_u = b.replay_veg; V.stride = b.stride; V.overflow = b.overflow;
+    V.veg = k.veg; V.dyn = nullptr;
+    if (replay) launch(grazer_dornic_kernel<true, true>, V, grid, kConsThreads, 0);
+    else        launch(grazer_dornic_kernel<false, true>, V, grid, kConsThreads, 0);
+    ReduceArgs R{n, b.state, b.state + n, b.part};
+    launch(cons_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 3 * kConsReduceThreads);
+    FinalizeArgs F{L, kConsReduceBlocks, k.n_central, k.fr, b.part, b.dyn};
+    launch(cons_finalize_kernel, F, 1, 32, 0);
+    GammaArgs G{};
+    G.L = L; G.eff = k.n_central; G.prey = b.state; G.offsets = b.central; G.gamma = b.gamma; G.dyn = b.dyn;
+    launch(cons_gamma_kernel, G, grid, kConsThreads, sizeof(int) * 2 * k.n_central);
+    GrazerArgs Z = V;
+    Z.prev = b.state + n; Z.out = b.star + n; Z.replay_u = b.replay_graz; Z.dyn = b.dyn;
+    Z.seed = seed ^ kGrazerSeedSalt;
+    if (replay) launch(grazer_dornic_kernel<true, false>, Z, grid, kConsThreads, 0);
+    else        launch(grazer_dornic_kernel<false, false>, Z, grid, kConsThreads, 0);
+    RkStageArgs A{};
+    A.L = L; A.c = k.c; A.base = b.state; A.base_pg = b.star; A.acc = b.acc; A.out = b.state;
+    A.clamp = 1; A.eps = k.eps; A.lo = k.lo;
+    A.stage = 1; A.Y = b.state; A.Ynext = b.ya; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+    A.stage = 2; A.Y = b.ya; A.Ynext = b.yb; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+    A.stage = 3; A.Y = b.yb; A.Ynext = b.ya; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+    A.stage = 4; A.Y = b.ya; A.Ynext = nullptr; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+}
+constexpr int kStep2Launches = 9;
 
 } // namespace tml
