@@ -305,6 +305,16 @@ def run_ours(a):
     lat.sync()
     te = maxr(time.perf_counter() - te0)
     e2e_value = sites_per_step * Ke / te
+    # the same entry point at the reference runner's own granularity: the frame goes in once per call
+    # (rietkerk_Dornic_2D_MultiSp takes the initial frame and t_max, R/:3397), then `runner_steps` time steps, reductions back
+    Kr = max(1, a.runner_steps)
+    lat.run_host(hnp, 2, download=False)
+    barrier()
+    tr0 = time.perf_counter()
+    for _ in range(2):
+        lat.run_host(hnp, Kr, download=False)
+    lat.sync()
+    tr = maxr(time.perf_counter() - tr0)
     import ctypes as C
     h2d = trials * 3 * L * L * 8
     d2h = trials * C.sizeof(tm.Stats)
@@ -328,6 +338,10 @@ def run_ours(a):
                      "kernels": kernel_lines(trials * L * L, ms_dornic, ms_rk4, n_timed, peak)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "call": "tm_run_host(ctx, pinned_host_frame, nsteps=1, download=0, stats)"},
+        "e2e_runner": {"value": sites_per_step * Kr * 2 / tr, "unit": UNIT, "calls": 2, "steps_per_call": Kr,
+                       "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h,
+                       "call": "tm_run_host(ctx, pinned_host_frame, nsteps=%d, download=0, stats): the frame is copied in once per "
+                               "call, as the reference's runner takes one initial frame and t_max; not the headline e2e" % Kr},
     }
     if rank == 0 and world == 1 and not a.no_cpu:
         out["cpu_baseline"] = cpu_reference(a.ref_L, a.ref_steps, host_cores())
@@ -430,6 +444,60 @@ def run_fke_extra(a):
     m.close()
 
 
+def run_spb2_extra(a):
+    """Not the headline: the vegetation + grazer (SPB = 2) time step resident on the device (include/tm_consumer.h
+    tm_cons_step2_*): nine launches per step.  Algorithmic bytes: four fields read and written once = 64 B per site-update."""
+    import numpy as np
+    import trophic_maelstorm_b200 as tm
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    L, K, W = a.L, a.steps, max(a.warmup, 3)
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "runner_2sp.npz"))
+    cons = np.load(os.path.join(ROOT, "tests", "golden", "consumer_ops.npz"))
+    par = gold["mixed_par"].astype(np.float64)
+    pa, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, s0, s1, v1, aij, hij, ej, m1, pR1, dt, dx = [float(x) for x in par]
+    R = int(pR1 / dx)
+    central = np.ascontiguousarray(cons["central_R%d" % R], dtype=np.int32)
+    fr = pR1 / (dx * (pR1 / dx))
+    veg = tm.rietkerk_params(L, a=pa, dt=dt)
+    veg.dx, veg.rc, veg.gmax, veg.alpha, veg.rW, veg.W0, veg.d, veg.K1, veg.K2 = dx, c, gmax, alpha, rW, W0, d, K1, K2
+    veg.D0, veg.D1, veg.D2, veg.sigma0 = D0, D2, D3, s0
+    graz = tm.GrazParams(L, 0, dt, dx, D1, v1, m1, s1, D0 / (dx * dx))
+    cp = tm.ConsParams(L, 0, dt, pa, c, gmax, alpha, rW, W0, K1, K2, D2 / (dx * dx), D3 / (dx * dx), aij, hij, ej)
+    rng = np.random.default_rng(7)
+    init = gold["mixed_init"]
+    f = np.stack([rng.choice(init[s_], L * L) for s_ in range(4)])
+    ops = tm.ConsumerOps(L)
+    ops.step2_setup(veg, graz, cp, central, fr)
+    ops.step2_upload(f, None)
+    ops.step2_run(1, nsteps=W)
+    ops.step2_download()
+    ops.step2_run(1, step0=W, nsteps=K)
+    ms, n = ops.last_ms()
+    fields = ops.step2_download()[0]
+    peak, src = measured_peaks()
+    rate = L * L * K / (ms * 1e-3)
+    line = {"metric": "lattice site-updates/sec (FP64, device-timed), vegetation + grazer (SPB=2) Dornic+RK4 step", "value": rate,
+            "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "dtype": "f64", "data": "synthetic", "gpu_launches": n,
+            "config": {"workload": "SPB=2 runner step (rietkerk_Dornic_2D_MultiSp -DSPB=2 loop body), L=%d, perception disc of %d sites"
+                                   % (L, len(central)), "finite": bool(np.isfinite(fields).all())},
+            "roofline": {"bound": "hbm", "achieved": rate * 64 / 1e9, "peak": peak, "unit": "GB/s", "frac": rate * 64 / 1e9 / peak,
+                         "traffic": None, "peak_source": src, "note": "64 B per site-update algorithmic; nine launches per step"}}
+    if not a.no_cpu:
+        Lc = 256
+        pv, pg, pc, _, _ = O.runner2_params(Lc, par)
+        fc = np.stack([rng.choice(init[s_], Lc * Lc) for s_ in range(4)])
+        g = np.zeros(Lc * Lc)
+        t0 = time.perf_counter()
+        for s_ in range(3):
+            O.step_2sp(pv, pg, pc, central, fr, O.make_rng(O.SRC_PHILOX, seed=1, step=s_), fc, g)
+        tc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 3 * Lc * Lc / tc, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "oracle tmo_step_2sp, L=%d, 3 steps, one thread" % Lc}
+    print(json.dumps(line), flush=True)
+    ops.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -439,10 +507,11 @@ def main():
     ap.add_argument("--L", type=int, default=4096)
     ap.add_argument("--trials", type=int, default=1, help="trials per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--runner-steps", type=int, default=100)
     ap.add_argument("--ref-L", type=int, default=512, help="lattice side of the bounded CPU sample")
     ap.add_argument("--ref-steps", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke"], help="dp, fke: extra, non-headline lines")
+    ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke", "spb2"], help="dp, fke, spb2: extra, non-headline lines")
     ap.add_argument("--fke-bound-d", type=int, default=1, help="fke: diffusion window half-width (the SPB=2 driver's constants give 1)")
     ap.add_argument("--fke-bound-v", type=int, default=1, help="fke: advection window half-width")
     a = ap.parse_args()
@@ -450,6 +519,8 @@ def main():
         return run_dp_extra(a)
     if a.workload == "fke" and a.impl == "ours":
         return run_fke_extra(a)
+    if a.workload == "spb2" and a.impl == "ours":
+        return run_spb2_extra(a)
     if a.impl == "reference":
         run_reference_arm(a)
     else:

@@ -1,0 +1,42 @@
+// tm_host_2sp.h -- reference-facing host layer for the vegetation + grazer model (SPB = 2, Sp = 4 fields P, G, W, O):
+// the reference's runner signature over the resident device stepper of include/tm_consumer.h.
+//
+//   rietkerk_Dornic_2D_MultiSp       Rietkerk_FD/rietkerk_bjork_basic.cpp:3397 compiled with -DSPB=2
+//   computeNeighboringSitesCentral   Rietkerk_FD/rietkerk_bjork_basic.cpp:1661
+//   var_mean_incremental_surv_runs   Rietkerk_FD/rietkerk_bjork_basic.cpp:1293 (SpB species blocks + the two water columns)
+//
+// The reference compiles one binary per SPB with the same function names; here the SPB = 2 set lives in its own
+// namespace (tm_b200::spb2) so that both can be linked into one program.  Kept from the reference: the measurement
+// schedule from the accumulated t += dt (R/:3648, 3659), Rho_M = {#occupied, <rho>} per field from left-to-right sums of
+// the downloaded frame (mean_of_vector R/:1211), the stop of a replicate whose vegetation is gone at a checkpoint bin
+// (R/:3710-3716), the replicate-order running mean/variance with the integer 1/(r-1) (R/:1325), and the row layout
+// {a, r, L, t, <W>, <O>, then per living species <rho>, var, #surviving, #active} (R/:4361-4372).  Not carried over: the
+// runner's CSV side outputs (frames, prelim tables, movement averages Rho_Mov) -- the SPB = 1 layer has those writers.
+#pragma once
+#include <functional>
+#include <utility>
+#include <vector>
+
+namespace tm_b200 { namespace spb2 {
+
+using D2Vec_Double = std::vector<std::vector<double>>;
+constexpr int Sp = 4, SpB = 2;
+
+// Initial frame of replicate j: 4*g*g doubles (P, G, W, O).  The reference builds it from exprtk expression strings
+// (init_exprtk_randbiMFTframe R/:396); here the caller supplies the rule.  Must be set before the runner is called.
+extern std::function<void(double *frame, int g, int replicate, double a, double a_c, double dP, const double clow[])> init_frame;
+// Optional observer called at every measurement bin with the downloaded frame (4*g*g) -- what the reference's frame
+// writers see; used by the tests.
+extern std::function<void(int replicate, int index, double t, const double *frame)> on_measure;
+
+std::vector<std::pair<int, int>> computeNeighboringSitesCentral(int R);
+void var_mean_incremental_surv_runs(D2Vec_Double &t_avg_var_rep_N, const D2Vec_Double &X_curr, int size, int j);
+
+void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c,
+                                double gmax, double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB],
+                                double (&K)[3], double sigma[], double a_st, double a_end, double a_c,
+                                double (&A)[SpB][SpB], double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB],
+                                double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
+                                int g, double Gstar = -1.0, double Vstar = -1.0);
+
+}} // namespace tm_b200::spb2

@@ -2,7 +2,9 @@
 // drive the reference-signature runners through ctypes.  No logic of its own.
 #include "tm_host.h"
 #include "tm_host_fke.h"
+#include "tm_host_2sp.h"
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 using namespace tm_b200;
@@ -190,5 +192,47 @@ int tmh_read_frame_csv(const char *filename, int g, double *frame) { return read
 void tmh_use_burnin(const char *parendir, const char *pattern)
 {
     if (parendir && pattern) use_burnin_frames(parendir, pattern); else use_default_init_frame();
+}
+
+// SPB = 2 runner (tm_host_2sp.h).  par = {a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, sigma0, sigma1, v1, aij, hij, ej,
+// m1, pR1, dt, dx} (the vector of tests/golden/make_runner2_golden.py); init: [n_init][4][L*L], replicate j starts from frame
+// j % n_init; rows_out[k][14]; frames_out (may be NULL): [r][n_tmeas][4][L*L], the frame seen at every measurement bin.
+int tmh_riet2_run(int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
+                  double *rows_out, int cap, double *frames_out)
+{
+    namespace s2 = tm_b200::spb2;
+    double D[s2::Sp] = {par[9], par[10], par[11], par[12]};
+    double K[3] = {0.0, par[7], par[8]};
+    double sigma[s2::Sp] = {par[13], par[14], 0, 0};
+    double v[s2::SpB] = {0, par[15]};
+    double A[s2::SpB][s2::SpB] = {{0, par[16]}, {par[16], 0}}, H[s2::SpB][s2::SpB] = {{0, par[17]}, {par[17], 0}};
+    double E[s2::SpB] = {1.0, par[18]}, M[s2::SpB] = {par[6], par[19]}, pR[s2::Sp] = {0.0, par[20]};
+    int dtV[s2::SpB] = {0, 1};
+    double clow[2 * s2::Sp] = {0, 1, 1, 1, 5, 1, 1, 1};
+    const size_t n4 = (size_t)4 * L * L;
+    s2::init_frame = [=](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + (size_t)(j % n_init) * n4, n4 * sizeof(double)); };
+    if (frames_out)
+        s2::on_measure = [=](int j, int index, double, const double *f) { memcpy(frames_out + ((size_t)j * n_tmeas + index) * n4, f, n4 * sizeof(double)); };
+    else s2::on_measure = nullptr;
+    s2::D2Vec_Double Rho;
+    std::vector<double> tm(t_meas, t_meas + n_tmeas);
+    try {
+        s2::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+                                       1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[21], par[22], 10000.0, r, L);
+    } catch (const std::exception &e) { fprintf(stderr, "tmh_riet2_run: %s\n", e.what()); return -2; }
+    s2::on_measure = nullptr;
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 14; j++) rows_out[14 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
+    return (int)Rho.size();
+}
+
+// the disc list of tm_b200::spb2::computeNeighboringSitesCentral as [n][2]; returns n (or -1 when cap is too small). Host only.
+int tmh_central_sites(int R, int *out, int cap)
+{
+    const auto v = tm_b200::spb2::computeNeighboringSitesCentral(R);
+    if ((int)v.size() > cap) return -1;
+    for (size_t k = 0; k < v.size(); k++) { out[2 * k] = v[k].first; out[2 * k + 1] = v[k].second; }
+    return (int)v.size();
 }
 }
