@@ -759,6 +759,16 @@ int tmo_step(const tmo_params *p, tmo_rng *rng, double *f)
 int tmo_step_2sp(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_cons_params *pc, const int32_t *central, int n_central,
                  double fr_graz, tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm)
 {
+    return tmo_step_2sp_means(pveg, pg, pc, central, n_central, fr_graz, rng, f, gamma, veff, trig_libm, NULL);
+}
+
+/* The same step with the two spatial means {<P>, <G>} of DRho supplied by the caller (means != NULL) instead of the
+ * left-to-right sums: the product sums in a fixed tree (a few ulp away), and some of the grazer's formulas are
+ * ill-conditioned in gamma (D - dx/2 (1-gamma)|v|(...) cancels, R/:4008), so the tests compare bit for bit given the
+ * product's two scalars and check those scalars against tmo_mean separately. */
+int tmo_step_2sp_means(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_cons_params *pc, const int32_t *central, int n_central,
+                       double fr_graz, tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm, const double *means)
+{
     if (!pveg || !pg || !pc || pveg->L != pg->L || pveg->L != pc->L) return -1;
     const int L = pveg->L;
     const int64_t n = (int64_t)L * L;
@@ -769,7 +779,7 @@ int tmo_step_2sp(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_co
     dornic_consts k;
     derive_consts(pveg, &k);
     dornic_sweep(pveg, &k, rng, D, vout);                                               /* vegetation, R/:3752-3809 */
-    const double avg_veg = tmo_mean(D, n), avg_graz = tmo_mean(D + n, n);               /* R/:3813-3818 */
+    const double avg_veg = means ? means[0] : tmo_mean(D, n), avg_graz = means ? means[1] : tmo_mean(D + n, n);   /* R/:3813-3818 */
     const double num_veg = tmo_occupied(D, n);
     double nR_fac = 1 - num_veg / (L * L);                                              /* R/:3822 */
     if (nR_fac < 0.35) nR_fac = 0.35;

@@ -166,6 +166,9 @@ int tmo_grazer_dornic(const tmo_graz_params *p, tmo_rng *rng, const double *prev
 /* one full time step of the SPB = 2 runner (R/:3752-4183) on f[4][L*L] = P, G, W, O; see tm_oracle.c */
 int tmo_step_2sp(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_cons_params *pc, const int32_t *central, int n_central,
                  double fr_graz, tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm);
+/* ... with {<P>, <G>} of the entry state supplied by the caller (NULL: the left-to-right sums) */
+int tmo_step_2sp_means(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_cons_params *pc, const int32_t *central, int n_central,
+                       double fr_graz, tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm, const double *means);
 
 #ifdef __cplusplus
 }

@@ -102,6 +102,7 @@ def oracle():
         L.tmo_grazer_dornic.argtypes = [C.POINTER(OGrazParams), C.POINTER(ORng), dp, dp, dp, dp, C.c_int]
         L.tmo_step_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OGrazParams), C.POINTER(OConsParams), C.POINTER(C.c_int32), C.c_int,
                                    C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int]
+        L.tmo_step_2sp_means.argtypes = L.tmo_step_2sp.argtypes + [dp]
         _lib = L
     return _lib
 
@@ -260,11 +261,13 @@ def runner2_params(L, par):
     return pv, pg, pc, int(r_max), pR1 / (dx * r_max)
 
 
-def step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=False):
-    """One SPB = 2 runner step in place on f [4][L*L] and gamma [L*L]; returns the grazer's advection vectors."""
+def step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=False, means=None):
+    """One SPB = 2 runner step in place on f [4][L*L] and gamma [L*L]; returns the grazer's advection vectors.
+    means = (<P>, <G>) of the entry state replaces the left-to-right sums (tmo_step_2sp_means)."""
     cen = np.ascontiguousarray(central, dtype=np.int32)
     veff = np.zeros((pv.L * pv.L, 2))
-    rc = oracle().tmo_step_2sp(C.byref(pv), C.byref(pg), C.byref(pc), cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen), fr,
-                               C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0)
+    m = None if means is None else np.array([means[0], means[1]], dtype=np.float64)
+    rc = oracle().tmo_step_2sp_means(C.byref(pv), C.byref(pg), C.byref(pc), cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen), fr,
+                                     C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0, None if m is None else ptr(m))
     assert rc == 0
     return veff

@@ -4,8 +4,12 @@ device-side means/cover -> perception field -> grazer Dornic with upwind advecti
 The oracle's tmo_step_2sp is pinned on the reference's rietkerk_Dornic_2D_MultiSp compiled with -DSPB=2
 (tests/test_consumer_oracle.py, tests/golden/runner_2sp.npz).  Here the product's launch chain is compared with it on
 per-cell streams (Philox and replay): CPU = the kernel SOURCE on host threads (tests/emu), GPU (-m gpu) = the C ABI.
-Tolerance: occupancy exact; values <= 1e-12 relative -- the spatial means come from a fixed summation tree instead of the
-reference's left-to-right sum (a few ulp), everything else shares every operation with the oracle."""
+Parity statement, in two parts: (1) the two spatial means <P>, <G> the step derives on the device come from a fixed
+summation tree instead of the reference's left-to-right sum and agree with it to <= max(1e-13, 8 sqrt(n) ulp) -- the
+sequential sum's own rounding grows like sqrt(n); (2) GIVEN those two scalars
+(tmo_step_2sp_means) every field, gamma and the advection vectors equal the oracle BIT FOR BIT, step after step.  The
+free-running comparison (oracle with its own sums) is kept at small sizes (<= 1e-12): the grazer's advection-corrected
+diffusion D - dx/2 (1-gamma)|v|(...) (R/:4008) cancels in some cells and amplifies the few-ulp difference of gamma."""
 import ctypes as C
 import os
 import subprocess
@@ -75,6 +79,23 @@ def oracle_steps(pv, pg, pc, central, fr, f, gamma, nsteps, seed=0, trial=0, ste
     return f, g, veff
 
 
+def stepwise_bit_parity(one_step, pv, pg, pc, central, fr, f, gamma, nsteps, seed=0, trial=0, step0=0):
+    """one_step(f, gamma, step) -> (f', gamma', v_eff, means[4]) runs ONE product step.  The oracle follows with the product's
+    two means; states must stay identical bit for bit."""
+    fo, go = f.copy(), gamma.copy()
+    fp, gp = f.copy(), gamma.copy()
+    for s in range(nsteps):
+        mP, mG = O.mean(fo[0]), O.mean(fo[1])
+        occ = O.occupied(fo[0])
+        fp, gp, vp, dyn = one_step(fp, gp, step0 + s)
+        # a left-to-right sum of n terms carries ~sqrt(n) ulp of its own rounding; the tree sum is the more accurate of the two
+        tol = max(1e-13, 8 * np.sqrt(fo[0].size) * 2.0 ** -53)
+        assert abs(dyn[0] - mP) <= tol * abs(mP) and abs(dyn[1] - mG) <= tol * abs(mG) and dyn[2] == occ
+        vo = O.step_2sp(pv, pg, pc, central, fr, O.make_rng(O.SRC_PHILOX, seed=seed, trial=trial, step=step0 + s), fo, go, means=(dyn[0], dyn[1]))
+        assert np.array_equal(fp, fo.reshape(fp.shape)), "step %d: fields differ in %d cells" % (s, np.count_nonzero(fp != fo.reshape(fp.shape)))
+        assert np.array_equal(gp, go) and np.array_equal(vp, vo)
+
+
 def check(got, want, what, flips=0):
     """flips: cells allowed beyond 1e-12.  The tree-summed <P> is a few ulp from the sequential sum, gamma inherits that, and
     where the grazer's Gaussian Poisson shortcut truncates `long(norm*sqrt(z)+z)` (R/:3776 form) right at an integer, one
@@ -99,6 +120,12 @@ def test_emulated_step2_philox_matches_oracle(emu, L, nsteps):
     got = emu_step2(emu, L, par, central, fr, f, gamma, nsteps=nsteps, seed=77, trial=3, step0=10)
     check(got[:3], want, "philox L=%d" % L)
     assert got[4] == 0
+
+    def one(fp, gp, step):
+        r = emu_step2(emu, L, par, central, fr, fp, gp, nsteps=1, seed=77, trial=3, step0=step)
+        return r[0], r[1], r[2], r[3]
+    if L <= 20:
+        stepwise_bit_parity(one, pv, pg, pc, central, fr, f, gamma, nsteps, seed=77, trial=3, step0=10)
 
 
 def test_emulated_step2_replay_matches_oracle(emu):
@@ -146,10 +173,22 @@ def test_gpu_step2_philox_matches_oracle(L, nsteps):
     ops.step2_upload(f, gamma)
     ops.step2_run(77, trial=3, step0=10, nsteps=nsteps)
     gf, gg, gv, means, ovf = ops.step2_download()
-    check((gf, gg, gv), want, "gpu philox L=%d" % L, flips=0 if L < 256 else 8 * nsteps)
+    if L < 256:
+        check((gf, gg, gv), want, "gpu philox L=%d" % L)
+    else:   # free-running at size: cells where R/:4008 cancels amplify the few-ulp difference of the means
+        err = np.abs(gf - want[0]) / np.maximum(np.abs(want[0]), 1e-300)
+        err[(want[0] == 0) & (gf == 0)] = 0
+        assert np.mean(err <= 1e-12) > 0.999 and err.max() < 1e-8
     assert ovf == 0
     ms, launches = ops.last_ms()
     assert launches == 9 * nsteps and ms > 0
+
+    def one(fp, gp, step):
+        ops.step2_upload(fp, gp)
+        ops.step2_run(77, trial=3, step0=step, nsteps=1)
+        r = ops.step2_download()
+        return r[0], r[1], r[2], r[3]
+    stepwise_bit_parity(one, pv, pg, pc, central, fr, f, gamma, nsteps, seed=77, trial=3, step0=10)
     ops.close()
 
 

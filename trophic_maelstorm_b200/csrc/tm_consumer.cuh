@@ -99,9 +99,18 @@ struct FinalizeArgs {
 
 TMC_G void cons_finalize_kernel(const FinalizeArgs A)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // 32 threads: lane l sums partials l, l+32, ... in order, then the 32 lane sums are added in lane order by lane 0
+    // (a fixed tree again; through shared memory so that the host-thread emulation runs the same code)
+    TMC_SMEM(smem_raw);
+    double *sh = reinterpret_cast<double *>(smem_raw);
+    const int lane = threadIdx.x;
     double sp = 0.0, sg = 0.0, oc = 0.0;
-    for (int b = 0; b < A.nblocks; b++) { sp += A.part[3 * b]; sg += A.part[3 * b + 1]; oc += A.part[3 * b + 2]; }
+    for (int b = lane; b < A.nblocks; b += 32) { sp += A.part[3 * b]; sg += A.part[3 * b + 1]; oc += A.part[3 * b + 2]; }
+    sh[lane] = sp; sh[32 + lane] = sg; sh[64 + lane] = oc;
+    __syncthreads();
+    if (lane != 0) return;
+    sp = 0.0; sg = 0.0; oc = 0.0;
+    for (int l = 0; l < 32; l++) { sp += sh[l]; sg += sh[32 + l]; oc += sh[64 + l]; }
     const double eps = 1.0e-12;                                       // R/:2537
     const double cells = (double)A.L * (double)A.L;
     const double avg_veg = sp / cells, avg_graz = sg / cells;        // R/:3813-3818
@@ -367,7 +376,7 @@ inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, const Step
     ReduceArgs R{n, b.state, b.state + n, b.part};
     launch(cons_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 3 * kConsReduceThreads);
     FinalizeArgs F{L, kConsReduceBlocks, k.n_central, k.fr, b.part, b.dyn};
-    launch(cons_finalize_kernel, F, 1, 32, 0);
+    launch(cons_finalize_kernel, F, 1, 32, sizeof(double) * 96);
     GammaArgs G{};
     G.L = L; G.eff = k.n_central; G.prey = b.state; G.offsets = b.central; G.gamma = b.gamma; G.dyn = b.dyn;
     launch(cons_gamma_kernel, G, grid, kConsThreads, sizeof(int) * 2 * k.n_central);
