@@ -199,16 +199,16 @@ TM_D double sqrt_lean1(double a)
 struct LogTab { double invc[128], logc[128]; };
 TM_D double log_lean(double x, const double *tab /* [128][2] = {invc, logc} */)
 {
-    const double ln2 = 6.93147180559945286227e-01;
+    const double ln2 = TM_MC(0, 6.93147180559945286227e-01);
     const uint64_t b = d2u(x);
     const int k = (int)(b >> 52) - 1023;
     const int i = (int)((b >> 45) & 127);
     const double m = u2d((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
     const double invc = tab[2 * i], logc = tab[2 * i + 1];
     const double r = fma(m, invc, -1.0);
-    double p = fma(r, -1.0 / 6.0, 1.0 / 5.0);
+    double p = fma(r, TM_MC(1, -1.0 / 6.0), TM_MC(2, 1.0 / 5.0));
     p = fma(r, p, -1.0 / 4.0);
-    p = fma(r, p, 1.0 / 3.0);
+    p = fma(r, p, TM_MC(3, 1.0 / 3.0));
     p = fma(r, p, -0.5);
     p = fma(r * r, p, r);
     return fma((double)k, ln2, logc) + p;

@@ -161,6 +161,20 @@ TM_HD const double *sincos_table()
 // series in g^2 (truncation < 4e-18; the three coefficients whose terms stay below 1e-10 carry 21 significant
 // bits so that they encode as immediates), then the angle addition with the table entry i mod 128.
 // Pure +,-,*,fma and bit operations: the same bits on every machine.
+// Full-width FP64 constants of the hot sampler path.  As literals each costs two move instructions per use (a 64-bit
+// immediate does not fit an FP64 instruction unless its low word is zero); from the constant bank they are plain operands.
+// Same bits either way (the host build, and the oracle's own copy, use the literals).
+#if defined(__CUDACC__)
+static __constant__ double kMathC[8] = {
+    6.93147180559945286227e-01, -1.0 / 6.0, 1.0 / 5.0, 1.0 / 3.0,
+    -0x1.4abbce625be53p-16, 0x1.921fb54442d18p-5, 0x1.03c1f081b5ac4p-22, -0x1.3bd3cc9be45dep-10 };
+#endif
+#if defined(__CUDA_ARCH__)
+#define TM_MC(i, lit) kMathC[i]
+#else
+#define TM_MC(i, lit) (lit)
+#endif
+
 TM_HD void sincos_turn128(double a, const double *tab, double &sn, double &cs)
 {
     const double magic = 6755399441055744.0; // 1.5 * 2^52
@@ -169,11 +183,11 @@ TM_HD void sincos_turn128(double a, const double *tab, double &sn, double &cs)
     const double g = a - (m - magic);
     const double z = g * g;
     double sb = fma(z, -0x1.32d2d00000000p-43, 0x1.466bc00000000p-29);
-    sb = fma(z, sb, -0x1.4abbce625be53p-16);
-    sb = fma(z, sb, 0x1.921fb54442d18p-5);
+    sb = fma(z, sb, TM_MC(4, -0x1.4abbce625be53p-16));
+    sb = fma(z, sb, TM_MC(5, 0x1.921fb54442d18p-5));
     sb = g * sb;                                              // sin b
-    double cb = fma(z, -0x1.55d3c00000000p-36, 0x1.03c1f081b5ac4p-22);
-    cb = fma(z, cb, -0x1.3bd3cc9be45dep-10);
+    double cb = fma(z, -0x1.55d3c00000000p-36, TM_MC(6, 0x1.03c1f081b5ac4p-22));
+    cb = fma(z, cb, TM_MC(7, -0x1.3bd3cc9be45dep-10));
     cb = z * cb;                                              // cos b - 1
     const double si = tab[2 * i], ci = tab[2 * i + 1];
     sn = fma(si, cb, fma(ci, sb, si));
