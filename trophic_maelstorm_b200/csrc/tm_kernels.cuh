@@ -772,26 +772,36 @@ riet_dornic_kernel(const DornicArgs A)
         int grow = g.row0 + ra; if (grow < 0) grow += g.L; if (grow >= g.L) grow -= g.L;
         uint32_t cell = (uint32_t)grow * (uint32_t)g.L + (uint32_t)qc;
         int n_exact = 0;
+        // The periodic wraps (of the prefetch pointer: row+2 reaching physical row L; of the global row that keys the Philox
+        // cell) are uniform events that happen at most once or twice per run: the rows between them are marched by an inner
+        // loop with no wrap tests at all, the events are applied between inner loops.
+        for (int row = ra; row < rb;) {
+            int n_safe = rb - row;
+            if (g.wrap && g.L - pr2 < n_safe) n_safe = g.L - pr2;
+            if (g.L - grow < n_safe) n_safe = g.L - grow;
+            const int row_end = row + n_safe;
 #pragma unroll 2
-        for (int row = ra; row < rb; row++) {
-            double Pn = Pd, Pln = Pl, Prn = Pr;
-            if (row + 1 < rb) { Pn = p2[0]; Pln = p1[-1]; Prn = p1[1]; }     // for the next iteration
-            const double nbsum = STRICT ? Pu + Pd + Pl + Pr : (Pu + Pd) + (Pl + Pr);    // STRICT: the reference's order R/:3756
-            bool needs_exact;
-            double pstar = riet_dornic_value<STRICT>(A.dk, A.inv_lambda, A.mu_scale, Pc, nbsum, valid,
-                                                     cell, ptrial, A.step, A.rk, logtab, sctab, needs_exact);
-            if (needs_exact) { pstar = u2d(kExactMarker); n_exact++; }    // resolved by the second walk below
-            if (valid) {
-                double *pout = const_cast<double *>(pc) + odelta;
-                pout[0] = pstar;
-                if (ghost_r) pout[g.L] = pstar;
-                if (ghost_l) pout[-g.L] = pstar;
+            for (; row < row_end; row++) {
+                double Pn = Pd, Pln = Pl, Prn = Pr;
+                if (row + 1 < rb) { Pn = p2[0]; Pln = p1[-1]; Prn = p1[1]; }     // for the next iteration
+                const double nbsum = STRICT ? Pu + Pd + Pl + Pr : (Pu + Pd) + (Pl + Pr);    // STRICT: the reference's order R/:3756
+                bool needs_exact;
+                double pstar = riet_dornic_value<STRICT>(A.dk, A.inv_lambda, A.mu_scale, Pc, nbsum, valid,
+                                                         cell, ptrial, A.step, A.rk, logtab, sctab, needs_exact);
+                if (needs_exact) { pstar = u2d(kExactMarker); n_exact++; }    // resolved by the second walk below
+                if (valid) {
+                    double *pout = const_cast<double *>(pc) + odelta;
+                    pout[0] = pstar;
+                    if (ghost_r) pout[g.L] = pstar;
+                    if (ghost_l) pout[-g.L] = pstar;
+                }
+                Pu = Pc; Pc = Pd; Pd = Pn; Pl = Pln; Pr = Prn;
+                pc = p1; p1 = p2; p2 += g.Lp;
+                cell += (uint32_t)g.L;
             }
-            Pu = Pc; Pc = Pd; Pd = Pn; Pl = Pln; Pr = Prn;
-            pc = p1; p1 = p2; p2 += g.Lp;
-            if (g.wrap && ++pr2 == g.L) { pr2 = 0; p2 -= wrap_back; }
-            cell += (uint32_t)g.L;
-            if (++grow == g.L) { grow = 0; cell = (uint32_t)qc; }
+            pr2 += n_safe; grow += n_safe;
+            if (g.wrap && pr2 == g.L) { pr2 = 0; p2 -= wrap_back; }
+            if (grow == g.L) { grow = 0; cell = (uint32_t)qc; }
         }
         // second walk, extinction fringe only: the cells of this thread's run that need the exact Poisson / Gamma
         // samplers (marked above) are redone from their counters, out of the hot loop
