@@ -714,6 +714,10 @@ struct DornicArgs {
 #ifndef TM_DORNIC_MINBLOCKS
 #define TM_DORNIC_MINBLOCKS 4
 #endif
+#ifndef TM_DORNIC_UNROLL
+#define TM_DORNIC_UNROLL 4
+#endif
+constexpr int kDornicUnroll = TM_DORNIC_UNROLL;
 constexpr int kDornicThreads = 256;
 constexpr uint64_t kExactMarker = 0x7FF8C0DEC0DE0001ull; // a NaN no computation produces: 'redo this cell exactly'
 TM_HD size_t riet_dornic_smem_bytes() { return sizeof(double) * 512; } // log table + sin/cos table
@@ -780,7 +784,7 @@ riet_dornic_kernel(const DornicArgs A)
             if (g.wrap && g.L - pr2 < n_safe) n_safe = g.L - pr2;
             if (g.L - grow < n_safe) n_safe = g.L - grow;
             const int row_end = row + n_safe;
-#pragma unroll 2
+#pragma unroll (kDornicUnroll)
             for (; row < row_end; row++) {
                 double Pn = Pd, Pln = Pl, Prn = Pr;
                 if (row + 1 < rb) { Pn = p2[0]; Pln = p1[-1]; Prn = p1[1]; }     // for the next iteration
