@@ -417,13 +417,21 @@ TM_D double riet_dornic_value(const DornicConsts &dk, double inv_lambda, double 
         double n_first, n_second;
         gauss_pair<STRICT>(cell, ptrial, step, rk, logtab, sctab, n_first, n_second);
         double gru = mu1, nz = n_first;
-        if (gauss_n) {
-            if (STRICT) gru = mu1 + (double)(long long)fma(n_first, sqrt(ziggy), ziggy);   // R/:3776
-            else        gru = mu1 + trunc(fma(n_first, sqrt_lean(ziggy), ziggy));          // same value below 2^63
-            nz = n_second;
+        if (STRICT) {
+            if (gauss_n) { gru = mu1 + (double)(long long)fma(n_first, sqrt(ziggy), ziggy); nz = n_second; }   // R/:3776
+            if (gru > 100) pstar = fma(nz, sqrt(gru), gru) / dk.lambda;
+            else needs_exact = true;
+        } else {
+            // branch-free: both Gaussian shortcuts are evaluated and selected (a lane that takes neither discards a NaN/garbage
+            // value); in the bulk every lane takes both, so the branches only cost convergence bookkeeping
+            const double g2 = mu1 + trunc(fma(n_first, sqrt_lean(ziggy), ziggy));              // same value below 2^63
+            gru = gauss_n ? g2 : mu1;
+            nz = gauss_n ? n_second : n_first;
+            const double v = fma(nz, sqrt_lean1(gru), gru) * inv_lambda;
+            const bool ok = gru > 100;
+            pstar = ok ? v : Pc;
+            needs_exact = !ok;
         }
-        if (gru > 100) pstar = STRICT ? fma(nz, sqrt(gru), gru) / dk.lambda : fma(nz, sqrt_lean1(gru), gru) * inv_lambda;
-        else needs_exact = true;
     }
     return pstar;
 }
