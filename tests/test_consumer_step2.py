@@ -337,3 +337,34 @@ def test_gpu_spb2_runner_rows_and_frames():
     want[:, 6:10] = T[:, 3:7]
     want[:, 10:14] = T[:, 7:11]
     assert np.array_equal(rows[:n], want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,nsteps", [(256, 4), (2048, 2)])
+def test_gpu_step2_without_grazers_equals_the_spb1_step(L, nsteps):
+    """Size-independent link between the two pinned paths: with G == 0 the vegetation + grazer step reduces to the SPB = 1
+    Rietkerk step (f_2Dor_2Sp R/:2460-2468 with G = 0 is f_2Dor R/:2376-2382 term by term; the vegetation keeps its Philox
+    streams), so the resident SPB = 2 stepper and the strict SPB = 1 lattice kernels -- different kernels, different data
+    layouts -- must agree bit for bit on P, W, O from the same seed."""
+    par = RUN2["mixed_par"].astype(np.float64)
+    veg, graz, cons = product_params(L, par)
+    R = int(float(par[20]) / float(par[22]))
+    central = np.ascontiguousarray(GOLD["central_R%d" % R], dtype=np.int32)
+    frame = O.synthetic_rietkerk_frame(L, seed=77)                      # [3, L, L] = P, W, O with an extinction fringe
+    f4 = np.zeros((4, L * L))
+    f4[0], f4[2], f4[3] = frame[0].ravel(), frame[1].ravel(), frame[2].ravel()
+    ops = tm.ConsumerOps(L)
+    ops.step2_setup(veg, graz, cons, central, 1.0)
+    ops.step2_upload(f4, None)
+    ops.step2_run(99, trial=5, step0=0, nsteps=nsteps)
+    got = ops.step2_download()[0]
+    ops.close()
+    lat = tm.Lattice(veg, 1, device=0)
+    lat.set_strict(True)
+    lat.seed(99, trial0=5)
+    lat.upload(frame[None])
+    lat.step(nsteps)
+    want = lat.download()[0].reshape(3, L * L)
+    lat.close()
+    assert not got[1].any()
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[1]) and np.array_equal(got[3], want[2])
