@@ -41,13 +41,31 @@ constexpr int kMaxReject = 64;
 constexpr int kMaxProduct = 4096;
 
 // log(x), finite normal x > 0: x = 2^k m, m in [sqrt(1/2), sqrt(2)), log m = 2 atanh(f/(2+f)).
+// Full-width FP64 constants of log_pos / exp_any.  As literals each use costs two move instructions on the device (a 64-bit
+// immediate only fits an FP64 instruction when its low word is zero); read from the constant bank they are plain operands.
+// TM_KC(table, index, literal): the table entry on the device, the literal on the host -- the same bits (each table is
+// initialised from the very same literals).
+#define TM_LOG_CONSTS 6.93147180369123816490e-01, 1.90821492927058770002e-10, 6.666666666666735130e-01, 3.999999999940941908e-01, \
+    2.857142874366239149e-01, 2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01
+#define TM_EXP_CONSTS 1.44269504088896338700e+00, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, \
+    1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0
+#if defined(__CUDACC__)
+static __constant__ double kLogC[9] = { TM_LOG_CONSTS };
+static __constant__ double kExpC[12] = { TM_EXP_CONSTS };
+#endif
+#if defined(__CUDA_ARCH__)
+#define TM_KC(tab, i, lit) tab[i]
+#else
+#define TM_KC(tab, i, lit) (lit)
+#endif
+
 TM_HD double log_pos(double x)
 {
-    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
-    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
-                 Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
-                 Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-                 Lg7 = 1.479819860511658591e-01;
+    const double ln2_hi = TM_KC(kLogC, 0, 6.93147180369123816490e-01), ln2_lo = TM_KC(kLogC, 1, 1.90821492927058770002e-10);
+    const double Lg1 = TM_KC(kLogC, 2, 6.666666666666735130e-01), Lg2 = TM_KC(kLogC, 3, 3.999999999940941908e-01),
+                 Lg3 = TM_KC(kLogC, 4, 2.857142874366239149e-01), Lg4 = TM_KC(kLogC, 5, 2.222219843214978396e-01),
+                 Lg5 = TM_KC(kLogC, 6, 1.818357216161805012e-01), Lg6 = TM_KC(kLogC, 7, 1.531383769920937332e-01),
+                 Lg7 = TM_KC(kLogC, 8, 1.479819860511658591e-01);
     if (!(x > 0.0)) return (x == 0.0) ? -INFINITY : NAN;
     if (x == INFINITY) return x;
     uint64_t b = d2u(x);
@@ -70,25 +88,25 @@ TM_HD double log_pos(double x)
 // exp(x): k = rint(x log2 e), two-part reduction, degree-13 Taylor, two-step 2^k scaling.
 TM_HD double exp_any(double x)
 {
-    const double LOG2E = 1.44269504088896338700e+00;
-    const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+    const double LOG2E = TM_KC(kExpC, 0, 1.44269504088896338700e+00);
+    const double ln2_hi = TM_KC(kLogC, 0, 6.93147180369123816490e-01), ln2_lo = TM_KC(kLogC, 1, 1.90821492927058770002e-10);
     if (x != x) return x;
     if (x > 709.782712893384) return INFINITY;
     if (x < -745.2) return 0.0;
     const double kf = rint(x * LOG2E);
     double r = fma(kf, -ln2_hi, x);
     r = fma(kf, -ln2_lo, r);
-    double q = 1.0 / 6227020800.0;
-    q = fma(q, r, 1.0 / 479001600.0);
-    q = fma(q, r, 1.0 / 39916800.0);
-    q = fma(q, r, 1.0 / 3628800.0);
-    q = fma(q, r, 1.0 / 362880.0);
-    q = fma(q, r, 1.0 / 40320.0);
-    q = fma(q, r, 1.0 / 5040.0);
-    q = fma(q, r, 1.0 / 720.0);
-    q = fma(q, r, 1.0 / 120.0);
-    q = fma(q, r, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
+    double q = TM_KC(kExpC, 1, 1.0 / 6227020800.0);
+    q = fma(q, r, TM_KC(kExpC, 2, 1.0 / 479001600.0));
+    q = fma(q, r, TM_KC(kExpC, 3, 1.0 / 39916800.0));
+    q = fma(q, r, TM_KC(kExpC, 4, 1.0 / 3628800.0));
+    q = fma(q, r, TM_KC(kExpC, 5, 1.0 / 362880.0));
+    q = fma(q, r, TM_KC(kExpC, 6, 1.0 / 40320.0));
+    q = fma(q, r, TM_KC(kExpC, 7, 1.0 / 5040.0));
+    q = fma(q, r, TM_KC(kExpC, 8, 1.0 / 720.0));
+    q = fma(q, r, TM_KC(kExpC, 9, 1.0 / 120.0));
+    q = fma(q, r, TM_KC(kExpC, 10, 1.0 / 24.0));
+    q = fma(q, r, TM_KC(kExpC, 11, 1.0 / 6.0));
     q = fma(q, r, 0.5);
     double y = 1.0 + fma(r * r, q, r);
     const int k = (int)kf;
