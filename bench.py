@@ -446,7 +446,7 @@ def run_fke_extra(a):
 
 def run_spb2_extra(a):
     """Not the headline: the vegetation + grazer (SPB = 2) time step resident on the device (include/tm_consumer.h
-    tm_cons_step2_*): nine launches per step.  Algorithmic bytes: four fields read and written once = 64 B per site-update."""
+    tm_cons_step2_*): six launches per step.  Algorithmic bytes: four fields read and written once = 64 B per site-update."""
     import numpy as np
     import trophic_maelstorm_b200 as tm
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -482,7 +482,7 @@ def run_spb2_extra(a):
             "config": {"workload": "SPB=2 runner step (rietkerk_Dornic_2D_MultiSp -DSPB=2 loop body), L=%d, perception disc of %d sites"
                                    % (L, len(central)), "finite": bool(np.isfinite(fields).all())},
             "roofline": {"bound": "hbm", "achieved": rate * 64 / 1e9, "peak": peak, "unit": "GB/s", "frac": rate * 64 / 1e9 / peak,
-                         "traffic": None, "peak_source": src, "note": "64 B per site-update algorithmic; nine launches per step"}}
+                         "traffic": None, "peak_source": src, "note": "64 B per site-update algorithmic; six launches per step"}}
     if not a.no_cpu:
         Lc = 256
         pv, pg, pc, _, _ = O.runner2_params(Lc, par)

@@ -65,7 +65,7 @@ int tm_cons_grazer_dornic_host(tm_cons_ctx *, const tm_graz_params *p, uint64_t 
  * Replaces the body of the time loop of rietkerk_Dornic_2D_MultiSp compiled with -DSPB=2, R/:3752-4183: vegetation Dornic
  * (R/:3752-3809) -> spatial means and vegetation cover of DRho (R/:3813-3824) -> calc_gamma_2Sp_NonRefugia (R/:3844) ->
  * grazer Dornic with upwind advection (R/:3908-4114; skipped when <G> == 0, R/:3910) -> RK4_Integrate_Stochastic_2Sp
- * (R/:4137) -> clamp and commit (R/:4150-4181).  Nine launches per step on the context's stream and no host round trip: the
+ * (R/:4137) -> clamp and commit (R/:4150-4181).  Six launches per step on the context's stream and no host round trip: the
  * scalars the reference derives between its loops (<P>, <G>, cover -> disc size) are reduced on the device and read there.
  * The means come from a fixed summation tree, not the reference's left-to-right sum: reproducible, a few ulp from the
  * sequential value (gamma inherits that: <= 1e-13 relative).
@@ -85,6 +85,9 @@ struct tm_params;
 int tm_cons_step2_setup(tm_cons_ctx *, const struct tm_params *veg, const tm_graz_params *pg, const tm_cons_params *pc,
                         const int32_t *central, int n_central, double fr_graz);
 int tm_cons_step2_upload(tm_cons_ctx *, const double *fields, const double *gamma);
+/* RK4 part of the step: 0 (default) = one launch for the four stages and the clamp (tile-fused, six launches per step);
+ * 1 = one launch per stage (nine per step).  Bit-identical results; the second form is kept as the cross-check. */
+int tm_cons_step2_set_rk4_stages(tm_cons_ctx *, int on);
 int tm_cons_step2_run(tm_cons_ctx *, uint64_t seed, uint32_t trial, uint32_t step0, int nsteps);
 int tm_cons_step2_replay(tm_cons_ctx *, const double *u_veg, const double *u_graz, uint32_t stride);
 int tm_cons_step2_download(tm_cons_ctx *, double *fields, double *gamma, double *v_eff, double *means, uint64_t *overflow);

@@ -233,7 +233,7 @@ int emu_grazer_dornic(int L, const double *par, unsigned long long seed, unsigne
 // state the last step started from.
 int emu_cons_step2(int L, const double *par2, const double *cpar, const int *central, int n_central, unsigned long long seed,
                    unsigned trial, unsigned step0, int nsteps, const double *u_veg, const double *u_graz, unsigned stride,
-                   double *fields, double *gamma, double *veff, double *dyn_out, unsigned long long *overflow)
+                   double *fields, double *gamma, double *veff, double *dyn_out, unsigned long long *overflow, int rk4_stages)
 {
     const size_t n = (size_t)L * L;
     const ConsConsts cc = cons_consts(cpar[0], cpar[1], cpar[2], cpar[3], cpar[4], cpar[5], cpar[6], cpar[7], cpar[8], cpar[9], cpar[10],
@@ -245,10 +245,11 @@ int emu_cons_step2(int L, const double *par2, const double *cpar, const int *cen
     Step2Buffers b{};
     b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
     b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
-    b.replay_veg = u_veg; b.replay_graz = u_graz; b.stride = stride;
+    b.replay_veg = u_veg; b.replay_graz = u_graz; b.stride = stride; b.rk4_stages = rk4_stages;
     *overflow = 0;
     auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
     for (int s = 0; s < nsteps; s++) cons_step2_enqueue(launch, k, b, seed, trial, step0 + (unsigned)s);
+    if (b.state != fields) std::memcpy(fields, b.state, sizeof(double) * 4 * n);   // the fused RK4 ping-pongs state and ya
     const double cells = (double)L * (double)L;
     dyn_out[0] = dyn.sum_veg / cells; dyn_out[1] = dyn.sum_graz / cells; dyn_out[2] = dyn.occ_veg; dyn_out[3] = (double)dyn.eff;
     return 0;

@@ -56,7 +56,7 @@ def product_params(L, par):
     return veg, graz, cons
 
 
-def emu_step2(emu, L, par, central, fr, f, gamma, nsteps=1, seed=0, trial=0, step0=0, u_veg=None, u_graz=None, stride=0):
+def emu_step2(emu, L, par, central, fr, f, gamma, nsteps=1, seed=0, trial=0, step0=0, u_veg=None, u_graz=None, stride=0, rk4_stages=0):
     a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, s0, s1, v1, aij, hij, ej, m1, pR1, dt, dx = [float(x) for x in par]
     par2 = np.array([dt, dx, d, D0, s0, 1e-12, -1e-80, D1, v1, m1, s1, D0 / (dx * dx), fr])
     cpar = np.array([dt, a, c, gmax, alpha, rW, W0, K1, K2, D2 / (dx * dx), D3 / (dx * dx), aij, hij, ej])
@@ -65,7 +65,7 @@ def emu_step2(emu, L, par, central, fr, f, gamma, nsteps=1, seed=0, trial=0, ste
     emu.emu_cons_step2(L, par2.ctypes.data_as(dp), cpar.ctypes.data_as(dp), central.ctypes.data_as(C.POINTER(C.c_int)), len(central),
                        C.c_ulonglong(seed), trial, step0, nsteps, None if u_veg is None else u_veg.ctypes.data_as(dp),
                        None if u_graz is None else u_graz.ctypes.data_as(dp), stride, f.ctypes.data_as(dp), g.ctypes.data_as(dp),
-                       veff.ctypes.data_as(dp), dyn.ctypes.data_as(dp), C.byref(ovf))
+                       veff.ctypes.data_as(dp), dyn.ctypes.data_as(dp), C.byref(ovf), rk4_stages)
     return f, g, veff, dyn, ovf.value
 
 
@@ -181,7 +181,7 @@ def test_gpu_step2_philox_matches_oracle(L, nsteps):
         assert np.mean(err <= 1e-12) > 0.999 and err.max() < 1e-8
     assert ovf == 0
     ms, launches = ops.last_ms()
-    assert launches == 9 * nsteps and ms > 0
+    assert launches == 6 * nsteps and ms > 0
 
     def one(fp, gp, step):
         ops.step2_upload(fp, gp)
@@ -368,3 +368,33 @@ def test_gpu_step2_without_grazers_equals_the_spb1_step(L, nsteps):
     lat.close()
     assert not got[1].any()
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[2], want[1]) and np.array_equal(got[3], want[2])
+
+
+@pytest.mark.parametrize("L", [20, 50])
+def test_emulated_fused_rk4_equals_the_four_stage_launches(emu, L):
+    """cons_rk4_fused_kernel (all four stages + clamp in one tile-fused launch, the default) against the four
+    cons_rk4_stage_kernel launches: identical bits (L = 20 is smaller than a tile's cone: the periodic wrap maps several
+    cone cells onto one lattice cell; L = 50 has partial edge tiles)."""
+    par, pv, pg, pc, central, fr, f = setup(L, 70 + L)
+    gamma = np.zeros(L * L)
+    a = emu_step2(emu, L, par, central, fr, f, gamma, nsteps=2, seed=3, rk4_stages=0)
+    b = emu_step2(emu, L, par, central, fr, f, gamma, nsteps=2, seed=3, rk4_stages=1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L,nsteps", [(20, 3), (333, 3), (1024, 2)])
+def test_gpu_fused_rk4_equals_the_four_stage_launches(L, nsteps):
+    par, pv, pg, pc, central, fr, f = setup(L, 70 + L)
+    ops = tm.ConsumerOps(L)
+    ops.step2_setup(*product_params(L, par), central, fr)
+    outs = []
+    for staged in (0, 1):
+        ops.step2_set_rk4_stages(staged)
+        ops.step2_upload(f, None)
+        ops.step2_run(3, nsteps=nsteps)
+        outs.append(ops.step2_download())
+        assert ops.last_ms()[1] == (9 if staged else 6) * nsteps
+    ops.close()
+    for k in range(3):
+        assert np.array_equal(outs[0][k], outs[1][k])

@@ -18,7 +18,7 @@ class GrazParams(C.Structure):
 
 CONS_ABI_SYMBOLS = ["tm_cons_create", "tm_cons_destroy", "tm_cons_last_error", "tm_cons_rk4_host", "tm_cons_gamma_host",
                     "tm_cons_grazer_dornic_host", "tm_cons_last_ms", "tm_cons_step2_setup", "tm_cons_step2_upload", "tm_cons_step2_run",
-                    "tm_cons_step2_replay", "tm_cons_step2_download"]
+                    "tm_cons_step2_replay", "tm_cons_step2_download", "tm_cons_step2_set_rk4_stages"]
 
 _bound = False
 
@@ -41,6 +41,7 @@ def _lib():
             "tm_cons_step2_upload": (i, [vp, dp, dp]),
             "tm_cons_step2_run": (i, [vp, C.c_uint64, C.c_uint32, C.c_uint32, i]),
             "tm_cons_step2_replay": (i, [vp, dp, dp, C.c_uint32]),
+            "tm_cons_step2_set_rk4_stages": (i, [vp, i]),
             "tm_cons_step2_download": (i, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint64)]),
         }
         for name, (res, args) in sig.items():
@@ -120,6 +121,9 @@ class ConsumerOps:
         assert f.size == 4 * self.L * self.L
         g = None if gamma is None else np.ascontiguousarray(gamma, dtype=np.float64)
         self._ck(self._l.tm_cons_step2_upload(self._ctx, _dptr(f), None if g is None else _dptr(g)))
+
+    def step2_set_rk4_stages(self, on):
+        self._ck(self._l.tm_cons_step2_set_rk4_stages(self._ctx, 1 if on else 0))
 
     def step2_run(self, seed, trial=0, step0=0, nsteps=1):
         self._ck(self._l.tm_cons_step2_run(self._ctx, seed, trial, step0, nsteps))

@@ -22,6 +22,7 @@ struct tm_cons_ctx {
     unsigned long long *d_ovf = nullptr;
     // the resident SPB = 2 stepper (tm_cons_step2_*)
     bool step2_ready = false;
+    int rk4_stages = 0;            // tm_cons_step2_set_rk4_stages
     Step2Consts k2{};
     double *d_star = nullptr, *d_veff = nullptr, *d_part = nullptr;
     Step2Dyn *d_dyn = nullptr;
@@ -50,6 +51,7 @@ static Step2Buffers step2_buffers(tm_cons_ctx *c)
     Step2Buffers b{};
     b.state = c->d_state; b.star = c->d_star; b.ya = c->d_ya; b.yb = c->d_yb; b.acc = c->d_acc; b.gamma = c->d_gamma; b.veff = c->d_veff;
     b.part = c->d_part; b.dyn = c->d_dyn; b.central = c->d_central; b.overflow = c->d_ovf;
+    b.rk4_stages = c->rk4_stages;
     return b;
 }
 } // namespace
@@ -243,6 +245,13 @@ int tm_cons_step2_setup(tm_cons_ctx *c, const tm_params *veg, const tm_graz_para
     return TM_OK;
 }
 
+int tm_cons_step2_set_rk4_stages(tm_cons_ctx *c, int on)
+{
+    if (!c) return TM_E_ARG;
+    c->rk4_stages = on ? 1 : 0;
+    return TM_OK;
+}
+
 int tm_cons_step2_upload(tm_cons_ctx *c, const double *fields, const double *gamma)
 {
     if (!c) return TM_E_ARG;
@@ -263,12 +272,13 @@ int tm_cons_step2_run(tm_cons_ctx *c, uint64_t seed, uint32_t trial, uint32_t st
     if (!c) return TM_E_ARG;
     if (!c->step2_ready || nsteps < 0) { c->err = "tm_cons_step2_run: call tm_cons_step2_setup first; nsteps >= 0"; return TM_E_ARG; }
     CONS_CK(cudaSetDevice(c->device));
-    const Step2Buffers b = step2_buffers(c);
+    Step2Buffers b = step2_buffers(c);
     CONS_CK(cudaEventRecord(c->ev0, c->stream));
     for (int s = 0; s < nsteps; s++) cons_step2_enqueue(CudaLaunch{c->stream}, c->k2, b, seed, trial, step0 + (uint32_t)s);
+    c->d_state = b.state; c->d_ya = b.ya;            // the fused RK4 ping-pongs the state between these two
     CONS_CK(cudaGetLastError());
     CONS_CK(cudaEventRecord(c->ev1, c->stream));
-    c->n_launches = kStep2Launches * nsteps;
+    c->n_launches = step2_launches(b) * nsteps;
     return TM_OK;
 }
 
@@ -289,9 +299,10 @@ int tm_cons_step2_replay(tm_cons_ctx *c, const double *u_veg, const double *u_gr
     b.replay_veg = c->d_replay; b.replay_graz = (const double *)((char *)c->d_replay + need); b.stride = stride;
     CONS_CK(cudaEventRecord(c->ev0, c->stream));
     cons_step2_enqueue(CudaLaunch{c->stream}, c->k2, b, 0, 0, 0);
+    c->d_state = b.state; c->d_ya = b.ya;
     CONS_CK(cudaGetLastError());
     CONS_CK(cudaEventRecord(c->ev1, c->stream));
-    c->n_launches = kStep2Launches;
+    c->n_launches = step2_launches(b);
     CONS_CK(cudaStreamSynchronize(c->stream));   // the uniform arrays are the caller's again
     return TM_OK;
 }

@@ -297,6 +297,87 @@ TMC_G void cons_rk4_stage_kernel(const RkStageArgs A)
     }
 }
 
+// All four RK4 stages of RK4_Integrate_Stochastic_2Sp (R/:2472-2527) and the clamp (R/:4176) in ONE launch: a CTA owns a
+// kT x kT tile of the lattice and recomputes the RK4 dependency cone around it (three stencil applications: the stage-k
+// values are made on a (kT + 8 - 2k)^2 region).  One thread per cell of the (kT+6)^2 stage-1 region keeps its own P, G, base
+// values and running K sums in registers; only the W, O stage values -- the two fields with a Laplacian -- pass through two
+// ping-pong shared-memory tiles.  Per cell the arithmetic is the stage kernels' (cons_rhs, then `b + h f` / `acc + 2 f` /
+// `b + dt6 (acc + f)` in the reference's order), so results are bit-identical to the four-launch form; HBM traffic drops from
+// 68 field passes to ~8 (tile halos are L2 hits).
+constexpr int kFuseT = 26;                 // tile side
+constexpr int kFuseE = kFuseT + 6;         // stage-1 region side (one thread per cell)
+constexpr int kFuseS = kFuseT + 8;         // shared tile side (stage-0 W, O incl. the outer ring)
+constexpr int kFuseThreads = 1024;         // >= kFuseE^2 = 900 and >= the ring loaders
+
+struct RkFusedArgs {
+    int L;
+    ConsConsts c;
+    const double *base;          // W, O at [2][L*L], [3][L*L] of this [4][L*L] block (P, G there are ignored when base_pg != null)
+    const double *base_pg;       // rho* of P and G as [2][L*L] (null: fields 0, 1 of base)
+    double *out;                 // [4][L*L]; must NOT alias base: a tile reads W, O of its neighbours' cells
+    int clamp; double eps, lo;
+};
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(kFuseThreads) cons_rk4_fused_kernel(const RkFusedArgs A)
+#else
+void cons_rk4_fused_kernel(const RkFusedArgs A)
+#endif
+{
+    TMC_SMEM(smem_raw);
+    double *SW0 = reinterpret_cast<double *>(smem_raw), *SO0 = SW0 + kFuseS * kFuseS;
+    double *SW1 = SO0 + kFuseS * kFuseS, *SO1 = SW1 + kFuseS * kFuseS;
+    const int g = A.L, n = g * g, tid = threadIdx.x;
+    const int tiles = (g + kFuseT - 1) / kFuseT;
+    const int ty0 = (int)(blockIdx.x / tiles) * kFuseT, tx0 = (int)(blockIdx.x % tiles) * kFuseT;
+    auto wrap = [g](int v) { v %= g; if (v < 0) v += g; return v; };
+    // stage-0 W, O of the (kT+8)^2 region into shared memory
+    for (int k = tid; k < kFuseS * kFuseS; k += kFuseThreads) {
+        const int sy = k / kFuseS, sx = k % kFuseS;
+        const int i = wrap(ty0 - 4 + sy) * g + wrap(tx0 - 4 + sx);
+        SW0[k] = A.base[2 * n + i]; SO0[k] = A.base[3 * n + i];
+    }
+    const bool mine = tid < kFuseE * kFuseE;
+    const int ey = mine ? tid / kFuseE : 0, ex = mine ? tid % kFuseE : 0;       // position in the stage-1 region
+    const int sc = (ey + 1) * kFuseS + (ex + 1);                                 // ... and in the shared tiles
+    const int gy = wrap(ty0 - 3 + ey), gx = wrap(tx0 - 3 + ex);
+    const int i = gy * g + gx;
+    const double *B01 = A.base_pg ? A.base_pg : A.base;
+    const double bP = B01[i], bG = B01[n + i];
+    __syncthreads();
+    const double bW = SW0[sc], bO = SO0[sc];
+    double yP = bP, yG = bG, yW = bW, yO = bO, acc[4] = {0, 0, 0, 0};
+    for (int stage = 1; stage <= 4; stage++) {
+        const double *RW = (stage & 1) ? SW0 : SW1, *RO = (stage & 1) ? SO0 : SO1;   // read tiles of this stage
+        double *WW = (stage & 1) ? SW1 : SW0, *WO_ = (stage & 1) ? SO1 : SO0;        // ... written for the next
+        const int m = stage - 1;                                                     // region shrinks by one ring per stage
+        const bool in = mine && ey >= m && ey < kFuseE - m && ex >= m && ex < kFuseE - m;
+        if (in) {
+            double f[4];
+            cons_rhs(A.c, yP, yG, yW, yO, RW[sc - kFuseS], RW[sc + kFuseS], RW[sc - 1], RW[sc + 1],
+                     RO[sc - kFuseS], RO[sc + kFuseS], RO[sc - 1], RO[sc + 1], f);
+            const double h = stage == 3 ? A.c.dt : A.c.dt2;
+            const double b[4] = {bP, bG, bW, bO};
+            if (stage < 4) {
+                double y[4];
+                for (int s = 0; s < 4; s++) {
+                    acc[s] = stage == 1 ? f[s] : acc[s] + 2.0 * f[s];
+                    y[s] = b[s] + (h) * f[s];
+                }
+                yP = y[0]; yG = y[1]; yW = y[2]; yO = y[3];
+                WW[sc] = yW; WO_[sc] = yO;
+            } else if (ty0 + (ey - 3) < g && tx0 + (ex - 3) < g) {                   // the tile's own cells inside the lattice
+                for (int s = 0; s < 4; s++) {
+                    double v = b[s] + (A.c.dt6) * (acc[s] + f[s]);                   // R/:2506
+                    if (A.clamp && v < A.eps && v >= A.lo) v = 0.0;                  // R/:4176
+                    A.out[s * n + i] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- one SPB = 2 runner step as a chain of launches (host side; shared by tm_consumer.cu and tests/emu) ----------------
 struct Step2Consts {
     int L, n_central;            // n_central: length of the full disc list (the gamma kernel's shared-memory bound)
@@ -318,6 +399,8 @@ struct Step2Buffers {
     unsigned long long *overflow;
     const double *replay_veg, *replay_graz;   // both null: Philox; else [n][stride] each
     unsigned int stride;
+    int rk4_stages;              // 1: the four-launch RK4 (kept as the cross-check); 0: cons_rk4_fused_kernel, which writes the
+                                 // new state into `ya` -- cons_step2_enqueue then swaps `state` and `ya`
 };
 
 // The grazer's Philox streams use the seed with this constant xor-ed in, so that the two species of a cell draw from
@@ -358,7 +441,7 @@ inline ConsConsts cons_consts(double dt, double a, double c, double gmax, double
 // launch(kernel, args, grid, block, dynamic shared bytes); order and arguments as the reference's loop body R/:3752-4183:
 // vegetation Dornic -> means and cover of DRho -> perception field -> grazer Dornic -> four RK4 stages (clamp in the last)
 template <class Launch>
-inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, const Step2Buffers &b, unsigned long long seed,
+inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, Step2Buffers &b, unsigned long long seed,
                                unsigned int trial, unsigned int step)
 {
     const int L = k.L;
@@ -385,6 +468,14 @@ inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, const Step
     Z.seed = seed ^ kGrazerSeedSalt;
     if (replay) launch(grazer_dornic_kernel<true, false>, Z, grid, kConsThreads, 0);
     else        launch(grazer_dornic_kernel<false, false>, Z, grid, kConsThreads, 0);
+    if (!b.rk4_stages) {
+        RkFusedArgs F4{};
+        F4.L = L; F4.c = k.c; F4.base = b.state; F4.base_pg = b.star; F4.out = b.ya; F4.clamp = 1; F4.eps = k.eps; F4.lo = k.lo;
+        const int ft = (L + kFuseT - 1) / kFuseT;
+        launch(cons_rk4_fused_kernel, F4, (unsigned)(ft * ft), kFuseThreads, sizeof(double) * 4 * kFuseS * kFuseS);
+        double *t = b.state; b.state = b.ya; b.ya = t;
+        return;
+    }
     RkStageArgs A{};
     A.L = L; A.c = k.c; A.base = b.state; A.base_pg = b.star; A.acc = b.acc; A.out = b.state;
     A.clamp = 1; A.eps = k.eps; A.lo = k.lo;
@@ -393,6 +484,6 @@ inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, const Step
     A.stage = 3; A.Y = b.yb; A.Ynext = b.ya; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
     A.stage = 4; A.Y = b.ya; A.Ynext = nullptr; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
 }
-constexpr int kStep2Launches = 9;
+inline int step2_launches(const Step2Buffers &b) { return b.rk4_stages ? 9 : 6; }
 
 } // namespace tml
