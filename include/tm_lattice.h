@@ -168,6 +168,12 @@ int tm_kernel_ms(tm_ctx *, double ms[2], int *n_steps);
  * upload host_soa -> nsteps -> stats (-> download when download != 0). */
 int tm_run_host(tm_ctx *, double *host_soa, int nsteps, int download, tm_stats *out);
 
+/* The noise-off DP path: nsteps classical RK4 steps of drho/dt = a rho - b rho^2 + D lap4(rho) (fourth-order nine-point-cross
+ * Laplacian, periodic) in place on rho[L*L] -- replaces the time-loop body of percNoDiff_2D, Percolation_FD/stochasticSPDP.cpp:
+ * 549-662 (fP_2D :516-529, determine_neighbours_R2 :394-414).  Self-contained: uploads the host field, steps on `device`,
+ * downloads; ms (may be NULL) receives the device time of the 4*nsteps launches.  Bit-identical to the oracle. */
+int tm_dp_noise_off_host(int device, int L, double a, double b, double D, double dt, double dx, double *rho, int nsteps, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

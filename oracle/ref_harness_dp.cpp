@@ -100,4 +100,21 @@ void ref_dp_rk4(int L, double a, double b, double c, double D, double t, double 
     for (size_t i = 0; i < R.size(); i++) rho[i] = R[i];
 }
 
+/* percNoDiff_2D (stochasticSPDP.cpp:549): the noise-off runner (one replicate whatever r is).  rows_out[k] = the runner's own
+ * rows {a, replicate, t, cell, rho} (:643).  Returns the number of rows, or -1.  Its arrays live on the stack (g*g*10 ints +
+ * 4*g*g doubles): keep g small. */
+int ref_dp_noise_off(int L, double a, double b, double D, double dt, double dx, const double *rh0, const double *t_stop_in,
+                     int n_tstop, double t_max, double *rows_out, int rows_cap)
+{
+    vector<vector<double>> Rho;
+    vector<double> t_stop(t_stop_in, t_stop_in + n_tstop);
+    vector<double> Rh0(rh0, rh0 + (size_t)L * L);
+    { quiet q; percNoDiff_2D(Rho, t_stop, Rh0.data(), t_max, a, b, D, dt, dx, 1, L); }
+    const int n = (int)Rho.size();
+    if (n > rows_cap) return -1;
+    for (int k = 0; k < n; k++)
+        for (int j = 0; j < 5; j++) rows_out[5 * k + j] = Rho[k][j];
+    return n;
+}
+
 }

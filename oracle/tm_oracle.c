@@ -813,6 +813,45 @@ int tmo_step_2sp_means(const tmo_params *pveg, const tmo_graz_params *pg, const 
 }
 
 /* ================================================================================== */
+/* 6b. The noise-off DP path: percNoDiff_2D P/:549-662                                  */
+/* ================================================================================== */
+/* fP_2D P/:516-529 with determine_neighbours_R2 P/:394-414 ([0][j]: rows p-2..p+2 of column q; [1][j]: columns q-2..q+2
+ * of row p; periodic) */
+static void fP_2D(double *f, const double *R, int g, double a, double b, double D, double dx)
+{
+    for (int i = 0; i < g * g; i++) {
+        const int p = i / g, q = i % g;
+        int v[5], h[5];
+        for (int j = 0; j < 5; j++) {
+            const int k = j - 2;
+            v[j] = ((p + k) % g + g) % g * g + q;
+            h[j] = p * g + ((q + k) % g + g) % g;
+        }
+        f[i] = a * R[i] - b * R[i] * R[i] - D * (1 / (12.0 * dx * dx)) * (1 * (R[v[0]] + R[v[4]] + R[h[0]] + R[h[4]])
+               - 16 * (R[v[1]] + R[v[3]] + R[h[1]] + R[h[3]]) + 60 * R[v[2]]);
+    }
+}
+
+/* one RK4 step of percNoDiff_2D's time loop (P/:591-621) in place on rho[L*L] */
+int tmo_dp_noise_off_step(int L, double a, double b, double D, double dt, double dx, double *rho)
+{
+    if (L < 1 || !rho) return -1;
+    const int n = L * L;
+    double *K1 = malloc(sizeof(double) * (size_t)n * 5), *K2 = K1 + n, *K3 = K2 + n, *K4 = K3 + n, *M = K4 + n;
+    if (!K1) return -1;
+    fP_2D(K1, rho, L, a, b, D, dx);
+    for (int i = 0; i < n; i++) M[i] = rho[i] + (dt / 2.0) * K1[i];
+    fP_2D(K2, M, L, a, b, D, dx);
+    for (int i = 0; i < n; i++) M[i] = rho[i] + (dt / 2.0) * K2[i];
+    fP_2D(K3, M, L, a, b, D, dx);
+    for (int i = 0; i < n; i++) M[i] = rho[i] + (dt) * K3[i];
+    fP_2D(K4, M, L, a, b, D, dx);
+    for (int i = 0; i < n; i++) rho[i] += (dt / 6.0) * (K1[i] + 2 * K2[i] + 2 * K3[i] + K4[i]);
+    free(K1);
+    return 0;
+}
+
+/* ================================================================================== */
 /* 7. Reductions and host-side bookkeeping                                            */
 /* ================================================================================== */
 

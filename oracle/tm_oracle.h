@@ -160,6 +160,8 @@ typedef struct tmo_graz_params {
 void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
                           double *gamma);
 int tmo_rk4_2sp(const tmo_cons_params *p, double *f);
+/* the noise-off DP path: one RK4 step of percNoDiff_2D (P/:549-662, fP_2D P/:516-529) in place on rho[L*L] */
+int tmo_dp_noise_off_step(int L, double a, double b, double D, double dt, double dx, double *rho);
 /* the grazer's Dornic update with upwind advection, R/:3908-4114 (defined in tm_oracle.c next to the samplers) */
 int tmo_grazer_dornic(const tmo_graz_params *p, tmo_rng *rng, const double *prev, double *gamma, double *out, double *veff,
                       int trig_libm);

@@ -5,6 +5,7 @@
 #include "tm_host_setup.h"
 #include "tm_fke.cuh"
 #include "tm_consumer.cuh"
+#include "tm_dpdet.cuh"
 
 #include <cmath>
 #include <vector>
@@ -252,6 +253,15 @@ int emu_cons_step2(int L, const double *par2, const double *cpar, const int *cen
     if (b.state != fields) std::memcpy(fields, b.state, sizeof(double) * 4 * n);   // the fused RK4 ping-pongs state and ya
     const double cells = (double)L * (double)L;
     dyn_out[0] = dyn.sum_veg / cells; dyn_out[1] = dyn.sum_graz / cells; dyn_out[2] = dyn.occ_veg; dyn_out[3] = (double)dyn.eff;
+    return 0;
+}
+// nsteps RK4 steps of the noise-off DP path through the product's stage kernel (csrc/tm_dpdet.cuh), in place on rho[L*L]
+int emu_dp_noise_off(int L, double a, double b, double D, double dt, double dx, double *rho, int nsteps)
+{
+    const size_t n = (size_t)L * L;
+    std::vector<double> ya(n), yb(n), acc(n);
+    auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
+    for (int s = 0; s < nsteps; s++) dp_det_step_enqueue(launch, L, a, b, D, dt, dx, rho, ya.data(), yb.data(), acc.data());
     return 0;
 }
 }

@@ -103,6 +103,7 @@ def oracle():
         L.tmo_step_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OGrazParams), C.POINTER(OConsParams), C.POINTER(C.c_int32), C.c_int,
                                    C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int]
         L.tmo_step_2sp_means.argtypes = L.tmo_step_2sp.argtypes + [dp]
+        L.tmo_dp_noise_off_step.argtypes = [C.c_int] + [C.c_double] * 5 + [dp]
         _lib = L
     return _lib
 
@@ -271,3 +272,11 @@ def step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=False, means=None
                                      C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0, None if m is None else ptr(m))
     assert rc == 0
     return veff
+
+
+def dp_noise_off(L, a, b, D, dt, dx, rho, nsteps):
+    """nsteps RK4 steps of percNoDiff_2D's time loop (tmo_dp_noise_off_step) on a copy of rho."""
+    r = np.ascontiguousarray(rho, dtype=np.float64).copy()
+    for _ in range(nsteps):
+        assert oracle().tmo_dp_noise_off_step(L, a, b, D, dt, dx, ptr(r)) == 0
+    return r

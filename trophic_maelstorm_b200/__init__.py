@@ -8,7 +8,7 @@ There is no CPU path: importing works anywhere (so the symbol table can be check
 compute call fails loudly without the CUDA library and a GPU.
 """
 from .lattice import (  # noqa: F401
-    Lattice, Params, Stats, Spread, TmError, lib, lib_path, rietkerk_params, dp_params,
+    Lattice, Params, Stats, Spread, TmError, lib, lib_path, rietkerk_params, dp_params, dp_noise_off,
     MODEL_DP, MODEL_DP_CUBIC, MODEL_RIETKERK, MODEL_RIETKERK_DET,
 )
 from .fke import FkeMover, FkeTerms, FKE_ABI_SYMBOLS  # noqa: F401,E402

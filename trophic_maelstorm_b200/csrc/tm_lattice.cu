@@ -4,6 +4,7 @@
 #include "../../include/tm_lattice.h"
 #include "tm_kernels.cuh"
 #include "tm_host_setup.h"
+#include "tm_dpdet.cuh"
 
 #include <cuda_runtime.h>
 #include <cmath>
@@ -633,6 +634,40 @@ int tm_last_step_ms(tm_ctx *c, float *ms, int *n_launches)
     TM_CUDA(c, cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     *ms = c->last_ms;
     if (n_launches) *n_launches = c->last_launches;
+    return TM_OK;
+}
+
+int tm_dp_noise_off_host(int device, int L, double a, double b, double D, double dt, double dx, double *rho, int nsteps, float *ms)
+{
+    auto fail = [&](int code, const std::string &msg) { g_create_error = msg; return code; };
+    if (!rho || L < 1 || L > 32767 || nsteps < 0 || !(dx > 0)) return fail(TM_E_ARG, "tm_dp_noise_off_host: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(TM_E_CUDA, "tm_dp_noise_off_host: no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return fail(TM_E_ARG, "tm_dp_noise_off_host: bad device index");
+    const size_t nb = sizeof(double) * (size_t)L * L;
+    double *d[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t err = cudaSetDevice(device);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreate(&e0);
+    if (err == cudaSuccess) err = cudaEventCreate(&e1);
+    for (int k = 0; k < 4 && err == cudaSuccess; k++) err = cudaMalloc(&d[k], nb);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(d[0], rho, nb, cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) {
+        cudaEventRecord(e0, st);
+        auto launch = [st](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { kernel<<<grid, block, smem, st>>>(args); };
+        for (int s = 0; s < nsteps; s++) dp_det_step_enqueue(launch, L, a, b, D, dt, dx, d[0], d[1], d[2], d[3]);
+        cudaEventRecord(e1, st);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(rho, d[0], nb, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err == cudaSuccess && ms) err = cudaEventElapsedTime(ms, e0, e1);
+    for (int k = 0; k < 4; k++) cudaFree(d[k]);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    if (err != cudaSuccess) return fail(TM_E_CUDA, std::string("tm_dp_noise_off_host: ") + cudaGetErrorString(err));
     return TM_OK;
 }
 

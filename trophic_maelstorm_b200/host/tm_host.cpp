@@ -638,6 +638,33 @@ vector<double> switchsort_and_bait(vector<double> vals, double low, double high,
 }
 } // namespace
 
+// percNoDiff_2D P/:549-662.  The steps between two logging windows run as one device batch (tm_dp_noise_off_host); the
+// window test is the reference's, on the accumulated t += dt (P/:638), and `s` cycles through t_stop as there (P/:646).
+void percNoDiff_2D(vector<vector<double>> &Rho, vector<double> &t_stop, double Rh0[], double t_max, double a, double b, double D,
+                   double dt, double dx, int /*r*/, int g)
+{
+    const size_t n = (size_t)g * g;
+    vector<double> Rho_dt(Rh0, Rh0 + n);
+    double t = 0; int s = 0; int pending = 0;
+    const int j = 0;
+    auto flush = [&]() {
+        if (!pending) return;
+        const int rc = tm_dp_noise_off_host(options().device, g, a, b, D, dt, dx, Rho_dt.data(), pending, nullptr);
+        if (rc != 0) throw std::runtime_error(std::string("tm_dp_noise_off_host: ") + tm_last_error(nullptr));
+        pending = 0;
+    };
+    while (t < t_max + dt) {
+        pending += 1;
+        t += dt;
+        if (!t_stop.empty() && t > t_stop[s] - dt / 2.0 && t <= t_stop[s] + dt / 2.0) {
+            flush();
+            for (size_t k = 0; k < n; k++) Rho.push_back({a, static_cast<double>(j), t, static_cast<double>(k), Rho_dt[k]});
+            s = (s + 1) % (int)t_stop.size();
+        }
+    }
+    flush();
+}
+
 void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
                                 double alpha, double rW, double W0, double (&D)[Sp], double (&)[SpB], double (&K)[3],
                                 double sigma[], double a_st, double a_end, double a_c, double (&)[SpB][SpB], double (&)[SpB][SpB],

@@ -43,6 +43,10 @@ void var_mean_incremental_surv_runs(double t_avg_var_rep_N[][5], double X_curr[]
 // ---- DP --------------------------------------------------------------------------------------
 void percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_meas, double Rh0[],
                           double t_max, double a, double b, double D, double sigma, double dt, double dx, int r, int g);
+// noise-off runner, P/:549-662: classical RK4 over fP_2D (fourth-order Laplacian), ONE replicate whatever r is (the reference's
+// loop is `for (j = 0; j < 1; j++)`); rows {a, replicate, t, cell, rho(cell)} for every cell at every t_stop window
+void percNoDiff_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_stop, double Rh0[], double t_max, double a,
+                   double b, double D, double dt, double dx, int r, int g);
 void expanded_percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_meas, double Rh0[],
                                    double t_max, double a, double b, double c, double D, double sigma, double dt,
                                    double dx, int r, int g);

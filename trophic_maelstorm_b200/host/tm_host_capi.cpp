@@ -235,4 +235,16 @@ int tmh_central_sites(int R, int *out, int cap)
     for (size_t k = 0; k < v.size(); k++) { out[2 * k] = v[k].first; out[2 * k + 1] = v[k].second; }
     return (int)v.size();
 }
+// percNoDiff_2D: rows_out[k][5] = {a, replicate, t, cell, rho}
+int tmh_dp_noise_off(int L, double a, double b, double D, double dt, double dx, const double *rh0, const double *t_stop, int n_tstop,
+                     double t_max, double *rows_out, int cap)
+{
+    std::vector<std::vector<double>> Rho;
+    std::vector<double> ts(t_stop, t_stop + n_tstop), r0(rh0, rh0 + (size_t)L * L);
+    try { percNoDiff_2D(Rho, ts, r0.data(), t_max, a, b, D, dt, dx, 1, L); } catch (const std::exception &) { return -2; }
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 5; j++) rows_out[5 * k + j] = Rho[k][j];
+    return (int)Rho.size();
+}
 }

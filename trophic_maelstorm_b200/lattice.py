@@ -98,6 +98,7 @@ def lib():
         "tm_halo_pack": (i, [vp, i, C.POINTER(vp)]),
         "tm_halo_unpack": (i, [vp, i, vp]),
         "tm_cuda_stream": (vp, [vp]),
+        "tm_dp_noise_off_host": (i, [i, i] + [C.c_double] * 5 + [dp, i, C.POINTER(C.c_float)]),
         "tm_measure": (i, [vp, C.POINTER(Stats)]),
         "tm_measure_spread": (i, [vp, i, i, C.POINTER(Spread)]),
         "tm_sampler_overflow": (i, [vp, C.POINTER(u64)]),
@@ -120,11 +121,23 @@ ABI_SYMBOLS = [
     "tm_set_step_counter", "tm_step_counter", "tm_step", "tm_step_replay", "tm_dornic_only",
     "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream", "tm_measure", "tm_measure_spread",
     "tm_sampler_overflow", "tm_sync", "tm_last_step_ms", "tm_set_kernel_timing", "tm_kernel_ms", "tm_run_host",
+    "tm_dp_noise_off_host",
 ]
 
 
 def _dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def dp_noise_off(L, a, b, D, dt, dx, rho, nsteps, device=0):
+    """tm_dp_noise_off_host: nsteps RK4 steps of the noise-off DP path (percNoDiff_2D) -> (rho', device ms)."""
+    r = np.ascontiguousarray(rho, dtype=np.float64).copy()
+    assert r.size == L * L
+    ms = C.c_float()
+    rc = lib().tm_dp_noise_off_host(device, L, a, b, D, dt, dx, _dptr(r), nsteps, C.byref(ms))
+    if rc != 0:
+        raise TmError("tm_dp_noise_off_host failed (%d): %s" % (rc, lib().tm_last_error(None).decode()))
+    return r, ms.value
 
 
 class Lattice:
