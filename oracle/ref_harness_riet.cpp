@@ -45,6 +45,17 @@ void init_exprtk_randbiMFTframe(D2Vec_Double &array, int size, double, double, d
         for (int i = 0; i < size; i++) array[s][i] = g_init[(size_t)s * size + i];
 }
 
+/* replaces rietkerk_bjork_basic.cpp:272 (speckle frame from mt19937_64(random_device)): the noise-off wrapper's initial frame.
+ * Replicate j of a ref_riet_det_run call starts from frame j of the caller's stack. */
+thread_local int g_det_replicate = 0;
+void init_randconstframe(D2Vec_Double &array, int Sp_, int size, double, double[], double[])
+{
+    const double *f = g_init + (size_t)g_det_replicate * Sp_ * size;
+    for (int s = 0; s < Sp_; s++)
+        for (int i = 0; i < size; i++) array[s][i] = f[(size_t)s * size + i];
+    g_det_replicate++;
+}
+
 /* replaces rietkerk_bjork_basic.cpp:2836 (6-significant-digit CSV snapshot writer) */
 void save_frame(D2Vec_Double &Rho_t, const string &, const string &, double, double, double,
                 double t, double, double, double, int, int g, string, bool)
@@ -156,5 +167,30 @@ void ref_riet_rk4_det(const ref_riet_params *p, int L, int nsteps, double *f)
 /* mean_of_vector / occupied_sites_of_vector (:1211, :1245) */
 double ref_riet_mean(const double *x, int n) { vector<double> v(x, x + n); return mean_of_vector(v, n); }
 double ref_riet_occupied(const double *x, int n) { vector<double> v(x, x + n); return occupied_sites_of_vector(v, n); }
+
+/* RK4_Wrapper_2D (rietkerk_bjork_basic.cpp:1816): the noise-off runner, r replicates starting from init[r][3][L*L].
+ * par = {a, c, gmax, alpha, d, rW, W0, D0, D1, D2, K1, K2, dt, dx, dP}.  rows_out[k][10] = the runner's own output rows
+ * {a, r, L, t, <W>, <O>, <P>, var, #surviving, #active} (:2139-2146).  Returns the number of rows, or -1. */
+int ref_riet_det_run(const double *par, int L, int r, const double *init, const double *t_meas_in, int n_tmeas,
+                     double *rows_out, int rows_cap)
+{
+    double D[Sp] = {par[7], par[8], par[9]};
+    double K[3] = {0.0, par[10], par[11]};
+    vector<double> t_meas(t_meas_in, t_meas_in + n_tmeas);
+    D2Vec_Double Rho;
+    g_init = init; g_det_replicate = 0; g_frames = nullptr;
+    set_global_system_params(par[12], par[13]);
+    {
+        quiet q;
+        RK4_Wrapper_2D(Rho, t_meas, t_meas.back(), par[0], par[1], par[2], par[3], par[4], par[5], par[6], D, K, par[0], par[0],
+                       par[12], par[13], par[14], r, L);
+    }
+    g_init = nullptr;
+    const int n = (int)Rho.size();
+    if (n > rows_cap) return -1;
+    for (int k = 0; k < n; k++)
+        for (int j = 0; j < 10; j++) rows_out[10 * k + j] = j < (int)Rho[k].size() ? Rho[k][j] : 0.0;
+    return n;
+}
 
 }

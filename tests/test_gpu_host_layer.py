@@ -299,3 +299,37 @@ def test_spreading_runner_ensemble_matches_reference(host):
             x = ref[alive, k, col]
             se = x.std(ddof=1) * np.sqrt(1.0 / alive.sum() + 1.0 / rows[k, 5])
             assert abs(rows[k, gcol] - x.mean()) <= 4.5 * se + 1e-9, (col, k, rows[k, gcol], x.mean(), se)
+
+
+# ---- the noise-off Rietkerk runner RK4_Wrapper_2D (R/:1816-2166) -------------------------------------------
+HERE = os.path.dirname(os.path.abspath(__file__))
+DETRUN = np.load(os.path.join(HERE, "golden", "riet_det_runner.npz"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["alive", "one_dead"])
+def test_noise_off_runner_rows_match_the_reference(name):
+    """tm_b200::RK4_Wrapper_2D (the reference's argument list) from the same initial frames as the UNMODIFIED reference runner
+    (tests/golden/make_riet_det_runner_golden.py): the same rows -- measured at every step while t <= 1 and in the t_meas
+    windows of the accumulated t += dt; times, surviving runs and active sites exact; means <= 1e-12; the running variance
+    (a difference of nearly equal means) to its conditioning.  `one_dead`: a replicate without vegetation leaves its water
+    entries at zero (the reference's `break`, R/:1953) and drops out of the surviving-run statistics."""
+    host = C.CDLL(os.path.join(os.path.dirname(HERE), "trophic_maelstorm_b200", "libtm_host.so"))
+    dp = C.POINTER(C.c_double)
+    host.tmh_riet_det_run.argtypes = [dp, C.c_int, C.c_int, dp, dp, C.c_int, dp, C.c_int]
+    host.tmh_set_options.argtypes = [C.c_int, C.c_ulonglong, C.c_int, C.c_char_p]
+    host.tmh_set_options(0, 1, 0, None)
+    par, L, frames, tm_, want = DETRUN[name + "_par"], int(DETRUN[name + "_L"]), DETRUN[name + "_frames"], DETRUN[name + "_tmeas"], DETRUN[name + "_rows"]
+    frames = np.ascontiguousarray(frames)
+    rows = np.zeros((len(want) + 8, 10))
+    n = host.tmh_riet_det_run(par.ctypes.data_as(dp), L, len(frames), frames.ctypes.data_as(dp), tm_.ctypes.data_as(dp), len(tm_),
+                              rows.ctypes.data_as(dp), len(rows))
+    assert n == len(want)
+    got = rows[:n]
+    assert np.array_equal(got[:, [0, 1, 2, 3, 8, 9]], want[:, [0, 1, 2, 3, 8, 9]])          # a, r, L, t, #surviving, #active
+    for col in (4, 5, 6):
+        assert np.abs(got[:, col] - want[:, col]).max() <= 1e-12 * np.abs(want[:, col]).max(), col
+    assert np.allclose(got[:, 7], want[:, 7], rtol=5e-3, atol=1e-13 * np.abs(want[:, 6]).max() ** 2)
+    # the default initial frame (no frames supplied): the reference's speckle rule around the analytic steady state
+    n2 = host.tmh_riet_det_run(par.ctypes.data_as(dp), L, 2, None, tm_.ctypes.data_as(dp), len(tm_), rows.ctypes.data_as(dp), len(rows))
+    assert n2 == len(want) and np.all(rows[:n2, 8] == 2) and np.isfinite(rows[:n2]).all()

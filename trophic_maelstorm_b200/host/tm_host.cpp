@@ -638,6 +638,102 @@ vector<double> switchsort_and_bait(vector<double> vals, double low, double high,
 }
 } // namespace
 
+// ---- RK4_Wrapper_2D R/:1816-2166: the noise-off Rietkerk runner ------------------------------------------------------
+static void default_init_frame_noise_off(double *f, int g, int replicate, double perc, const double c_high[], const double c_low[])
+{
+    const size_t n = (size_t)g * g;
+    unsigned long long s = options().seed ^ (0xD37ull + 0x9E3779B97F4A7C15ull * (unsigned long long)(replicate + 1));
+    for (size_t i = 0; i < n; i++) {
+        const double u = (double)(splitmix(s) >> 11) * (1.0 / 9007199254740992.0);
+        for (int k = 0; k < Sp; k++) f[k * n + i] = (u <= perc) ? c_high[k] : c_low[k];             // R/:283-290
+    }
+}
+std::function<void(double *, int, int, double, const double[], const double[])> init_frame_noise_off = default_init_frame_noise_off;
+
+void RK4_Wrapper_2D(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax, double alpha,
+                    double d, double rW, double W0, double (&D)[Sp], double (&K)[3], double /*a_st*/, double /*a_end*/, double dt,
+                    double dx, double dP, int r, int g)
+{
+    if (t_meas.empty() || r < 1) throw std::invalid_argument("RK4_Wrapper_2D: empty t_meas or r < 1");
+    const int n_meas = (int)t_meas.size();
+    const int tot_iter = static_cast<int>(1.0 / dt) + 1 + n_meas;                                   // R/:1832
+    const double t_max = t_meas[n_meas - 1];                                                        // R/:1833
+    const int W_ = 4 * (Sp - 2) + 3;
+    D2Vec_Double acc(tot_iter, vector<double>(W_, 0.0));
+    int ind = 0;
+    for (double t = 0; t <= 1; t += dt) { if (ind < tot_iter) acc[ind][0] = t; ind += 1; }          // R/:1840-1841
+    for (int i = 0; i < n_meas; i++) if (ind + i < tot_iter) acc[ind + i][0] = t_meas[i];           // R/:1842-1843
+
+    const double beta = c * gmax - d;                                                               // R/:1851
+    double p0istar, p0jstar, p0mstar;                                                               // R/:1855-1866
+    if (a < 1) { p0istar = 0.0; p0jstar = a / rW; p0mstar = a / (alpha * W0); }
+    else { p0jstar = d * K[1] / beta; p0istar = (c / d) * (a - rW * p0jstar); p0mstar = (a / alpha) * (p0istar + K[2]) / (p0istar + K[2] * W0); }
+    const double perc = 0.015;
+    const double c_high[Sp] = {p0istar + dP, p0jstar, p0mstar}, c_low[Sp] = {p0istar, p0jstar, p0mstar};   // R/:1914
+
+    tm_params p{};
+    p.model = TM_MODEL_RIETKERK_DET; p.L = g; p.dt = dt; p.dx = dx; p.a = a;
+    p.rc = c; p.gmax = gmax; p.alpha = alpha; p.rW = rW; p.W0 = W0; p.d = d; p.K1 = K[1]; p.K2 = K[2];
+    p.D0 = D[0]; p.D1 = D[1]; p.D2 = D[2]; p.sigma0 = 1.0;
+    Ctx ctx(p, r);                                         // the r replicates advance together as one batch of trials
+    const size_t n = (size_t)g * g;
+    vector<double> host(3 * n * r);
+    for (int j = 0; j < r; j++) init_frame_noise_off(&host[3 * n * j], g, j, perc, c_high, c_low);
+    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
+
+    vector<D2Vec_Double> RhoM(r, D2Vec_Double(tot_iter, vector<double>(2 * Sp, 0.0)));
+    vector<tm_stats> st(r);
+    double t = 0; int index = 0, iter_index = 0, pending = 0;
+    while (t < t_max + dt) {                                                                        // R/:1938
+        const bool window = index < n_meas && t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0;
+        if (t <= 1.0 || window) {                                                                   // R/:1940
+            if (pending) { ctx.ck(tm_step(ctx.c, pending), "tm_step"); pending = 0; }
+            ctx.ck(tm_measure(ctx.c, st.data()), "tm_measure");
+            for (int j = 0; j < r; j++) {
+                if (iter_index >= tot_iter) break;
+                for (int s = 0; s < Sp; s++) {
+                    RhoM[j][iter_index][2 * s] = (double)st[j].active[s]; RhoM[j][iter_index][2 * s + 1] = st[j].mean[s];
+                    if (st[j].active[s] == 0 && s == 0) break;                                      // R/:1953: the water entries stay 0
+                }
+            }
+            iter_index += 1;
+            if (t > 1.0) index += 1;                                                                // R/:1987
+        }
+        pending += 1;
+        t += dt;
+    }
+    for (int j = 0; j < r; j++) {                                                                   // R/:2058-2083
+        const D2Vec_Double &X = RhoM[j];
+        if (j == 0) {
+            for (int i = 0; i < tot_iter; i++) {
+                acc[i][3] = X[i][1]; acc[i][4] = 0.0; acc[i][6] = X[i][0];
+                if (X[i][0] > 0) acc[i][5] = 1; else if (X[i][0] == 0) acc[i][5] = 0;
+                acc[i][1] = X[i][2 * 1 + 1]; acc[i][2] = X[i][2 * 2 + 1];
+            }
+            continue;
+        }
+        for (int i = 0; i < tot_iter; i++) {                                                        // var_mean_incremental_surv_runs R/:1293
+            const int rr = (int)(acc[i][5] + 1);
+            if (X[i][0] == 0.0) break;
+            const double mean_prev = acc[i][3];
+            if (acc[i][5] == 0.0) { acc[i][3] = X[i][1]; acc[i][4] = 0.0; acc[i][6] = X[i][0]; }
+            else {
+                acc[i][3] = (X[i][1] + (rr - 1) * acc[i][3]) / rr;
+                acc[i][6] = (X[i][0] + (rr - 1) * acc[i][6]) / rr;
+                acc[i][4] = (acc[i][3] - mean_prev) * (acc[i][3] - mean_prev)
+                          + (1 / (rr - 1)) * ((rr - 2) * acc[i][4] + (X[i][1] - acc[i][3]) * (X[i][1] - acc[i][3]));   // int 1/(r-1)
+            }
+            acc[i][5] = rr;
+        }
+        for (int i = 0; i < tot_iter; i++) {
+            acc[i][1] = (X[i][2 * (Sp - 2) + 1] + (j)*acc[i][1]) / (j + 1);
+            acc[i][2] = (X[i][2 * (Sp - 1) + 1] + (j)*acc[i][2]) / (j + 1);
+        }
+    }
+    for (int i = 0; i < tot_iter; i++)                                                              // R/:2137-2146
+        Rho.push_back({a, static_cast<double>(r), static_cast<double>(g), acc[i][0], acc[i][1], acc[i][2], acc[i][3], acc[i][4], acc[i][5], acc[i][6]});
+}
+
 // percNoDiff_2D P/:549-662.  The steps between two logging windows run as one device batch (tm_dp_noise_off_host); the
 // window test is the reference's, on the accumulated t += dt (P/:638), and `s` cycles through t_stop as there (P/:646).
 void percNoDiff_2D(vector<vector<double>> &Rho, vector<double> &t_stop, double Rh0[], double t_max, double a, double b, double D,

@@ -74,6 +74,15 @@ extern std::string frame_folder; // default "<data_root>/Data/Rietkerk/Frames/St
 // init_exprtk_randbiMFTframe (R/:396-505) with the order_1stoc_test_rietkerk.cpp:144-160 expressions.
 extern std::function<void(double *frame, int g, int replicate, double a, double a_c, double dP, const double clow[])> init_frame;
 
+// Noise-off runner, R/:1816-2166: classical RK4 over the full right-hand side f_2D (R/:1718), r replicates, measured at
+// every step while t <= 1 and then in the t_meas windows; rows {a, r, L, t, <W>, <O>, <P>, var, #surviving, #active}.
+// Initial frame of replicate j: init_frame_noise_off (3*g*g doubles P, W, O); default = the reference's speckle rule
+// init_randconstframe (R/:272: every cell is c_high with probability 0.015, else c_low, all three fields together) around
+// the analytic steady state (R/:1855-1866), the mask drawn from options().seed instead of mt19937_64(random_device).
+extern std::function<void(double *frame, int g, int replicate, double perc, const double c_high[], const double c_low[])> init_frame_noise_off;
+void RK4_Wrapper_2D(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c, double gmax, double alpha,
+                    double d, double rW, double W0, double (&D)[Sp], double (&K)[3], double a_st, double a_end, double dt, double dx,
+                    double dP, int r, int g);
 void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c,
                                 double gmax, double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB],
                                 double (&K)[3], double sigma[], double a_st, double a_end, double a_c,

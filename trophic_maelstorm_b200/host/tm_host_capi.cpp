@@ -247,4 +247,25 @@ int tmh_dp_noise_off(int L, double a, double b, double D, double dt, double dx, 
         for (size_t j = 0; j < 5; j++) rows_out[5 * k + j] = Rho[k][j];
     return (int)Rho.size();
 }
+// RK4_Wrapper_2D: par = {a, c, gmax, alpha, d, rW, W0, D0, D1, D2, K1, K2, dt, dx, dP}; init (may be NULL: the default speckle
+// rule) = r frames [r][3][L*L]; rows_out[k][10]
+int tmh_riet_det_run(const double *par, int L, int r, const double *init, const double *t_meas, int n_tmeas, double *rows_out, int cap)
+{
+    double D[Sp] = {par[7], par[8], par[9]};
+    double K[3] = {0.0, par[10], par[11]};
+    const size_t n3 = (size_t)3 * L * L;
+    auto saved = init_frame_noise_off;
+    if (init) init_frame_noise_off = [=](double *f, int, int j, double, const double[], const double[]) { memcpy(f, init + (size_t)j * n3, n3 * sizeof(double)); };
+    D2Vec_Double Rho;
+    std::vector<double> tm(t_meas, t_meas + n_tmeas);
+    int rc = 0;
+    try { RK4_Wrapper_2D(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], par[6], D, K, par[0], par[0], par[12], par[13], par[14], r, L); }
+    catch (const std::exception &e) { fprintf(stderr, "tmh_riet_det_run: %s\n", e.what()); rc = -2; }
+    init_frame_noise_off = saved;
+    if (rc) return rc;
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 10; j++) rows_out[10 * k + j] = Rho[k][j];
+    return (int)Rho.size();
+}
 }
