@@ -333,3 +333,28 @@ def test_noise_off_runner_rows_match_the_reference(name):
     # the default initial frame (no frames supplied): the reference's speckle rule around the analytic steady state
     n2 = host.tmh_riet_det_run(par.ctypes.data_as(dp), L, 2, None, tm_.ctypes.data_as(dp), len(tm_), rows.ctypes.data_as(dp), len(rows))
     assert n2 == len(want) and np.all(rows[:n2, 8] == 2) and np.isfinite(rows[:n2]).all()
+
+
+@pytest.mark.gpu
+def test_noise_off_sweep_writes_the_reference_csv(tmp_path):
+    """first_order_critical_exp_delta (R/:2170, the noise-off a-sweep): one CSV in the reference's place, header and
+    16-digit rows {a, r, L, t, <W>, <O>, <P>, var, #surviving, #active}, a-values in order, (1/dt + 1 + #bins) rows each."""
+    host = C.CDLL(os.path.join(os.path.dirname(HERE), "trophic_maelstorm_b200", "libtm_host.so"))
+    host.tmh_set_options.argtypes = [C.c_int, C.c_ulonglong, C.c_int, C.c_char_p]
+    host.tmh_riet_det_sweep.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    host.tmh_set_options(0, 9, 0, str(tmp_path).encode())
+    L, div, t_max, dt, r = 32, 2, 3.0, 0.1, 2
+    assert host.tmh_riet_det_sweep(L, div, t_max, 0.05, 0.06, dt, r) == 0
+    d = tmp_path / "Data" / "Rietkerk" / "Non-Stochastic"
+    files = list(d.glob("1stOrderCC_Rietkerk_P_c_Delta_DP_G_32_T_3_dt_0.1_D0_*_a1_0.05_a2_0.06_dx_0.1_gmax_*_alpha_*_R_2.csv"))
+    assert len(files) == 1, list(d.iterdir())
+    lines = files[0].read_text().splitlines()
+    assert lines[0].startswith(" a , r, L, t , <<W(x; t)>_x>_r")
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in lines[1:]])
+    n_bins = len(O.time_bins(t_max, dt)) if hasattr(O, "time_bins") else None
+    per_a = len(rows) // div
+    assert rows.shape[1] == 10 and len(rows) == per_a * div and (n_bins is None or per_a == int(1.0 / dt) + 1 + n_bins)
+    assert np.all(rows[:per_a, 0] == 0.05) and np.all(rows[per_a:, 0] == 0.06) and np.all(rows[:, 1] == r) and np.all(rows[:, 2] == L)
+    # a < 1: the steady state without vegetation plus 1.5 % speckles of dP (R/:1857, 1914); diffusion spreads them over the lattice
+    assert np.all(rows[:, 8] == r) and np.all(np.diff(rows[:per_a, 3]) > 0)
+    assert 0 < rows[0, 9] < 0.05 * L * L and np.all(np.diff(rows[:per_a, 9]) >= 0) and rows[per_a - 1, 9] == L * L

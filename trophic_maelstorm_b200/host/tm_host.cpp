@@ -734,6 +734,33 @@ void RK4_Wrapper_2D(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/,
         Rho.push_back({a, static_cast<double>(r), static_cast<double>(g), acc[i][0], acc[i][1], acc[i][2], acc[i][3], acc[i][4], acc[i][5], acc[i][6]});
 }
 
+// first_order_critical_exp_delta R/:2170-2345 (the noise-off sweep): a-values in turn (the reference spreads them over OpenMP
+// threads and concatenates in a-order), each a batch of r replicates
+void first_order_critical_exp_delta(int div, double t_max, double a_start, double a_end, double c, double gmax, double alpha, double d,
+                                    double rW, double W0, double (&D)[Sp], double (&K)[3], double dt, double dx, double dP, int r, int g)
+{
+    vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = logarithm10_time_bins(t_max, dt);
+    D2Vec_Double vec;
+    for (size_t i = 0; i < a_space.size(); i++) {
+        D2Vec_Double rows;
+        RK4_Wrapper_2D(rows, t_measure, t_max, a_space[i], c, gmax, alpha, d, rW, W0, D, K, a_start, a_end, dt, dx, dP, r, g);
+        vec.insert(vec.end(), rows.begin(), rows.end());
+    }
+    std::stringstream L, coco, tm, d3, p1, p2, rini, Dm0, Dm1, gm, alph, dix;
+    L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r; alph << alpha;
+    Dm0 << std::setprecision(3) << D[0]; Dm1 << std::setprecision(3) << D[1]; gm << gmax; coco << std::setprecision(4) << c; dix << std::setprecision(2) << dx;
+    const std::string dir = options().data_root + "/Data/Rietkerk/Non-Stochastic";
+    mkdirs(dir);
+    std::ofstream out(dir + "/1stOrderCC_Rietkerk_P_c_Delta_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D0_" + Dm0.str() + "_D1_" + Dm1.str()
+                      + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str() + "_gmax_" + gm.str() + "_alpha_" + alph.str() + "_R_" + rini.str() + ".csv");   // R/:2320
+    out << " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<Rho0(x; t)>_x>_r, Var[<Rho0(t)>_x]_r, # Surviving Runs, # Active Sites" << "\n";   // R/:2327
+    for (size_t i = 0; i < vec.size(); i++) {
+        for (size_t j = 0; j + 1 < vec[i].size(); j++) out << std::setprecision(16) << vec[i][j] << ",";
+        out << std::setprecision(16) << vec[i][vec[i].size() - 1] << std::endl;
+    }
+}
+
 // percNoDiff_2D P/:549-662.  The steps between two logging windows run as one device batch (tm_dp_noise_off_host); the
 // window test is the reference's, on the accumulated t += dt (P/:638), and `s` cycles through t_stop as there (P/:646).
 void percNoDiff_2D(vector<vector<double>> &Rho, vector<double> &t_stop, double Rh0[], double t_max, double a, double b, double D,

@@ -83,6 +83,10 @@ extern std::function<void(double *frame, int g, int replicate, double perc, cons
 void RK4_Wrapper_2D(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c, double gmax, double alpha,
                     double d, double rW, double W0, double (&D)[Sp], double (&K)[3], double a_st, double a_end, double dt, double dx,
                     double dP, int r, int g);
+// noise-off a-sweep, R/:2170-2345 (driver order_test_rietkerk.cpp:182): RK4_Wrapper_2D per a-value, one CSV
+// "<data_root>/Data/Rietkerk/Non-Stochastic/1stOrderCC_Rietkerk_P_c_Delta_DP_G_<L>_T_<T>_dt_..._R_<r>.csv" at setprecision(16)
+void first_order_critical_exp_delta(int div, double t_max, double a_start, double a_end, double c, double gmax, double alpha, double d,
+                                    double rW, double W0, double (&D)[Sp], double (&K)[3], double dt, double dx, double dP, int r, int g);
 void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c,
                                 double gmax, double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB],
                                 double (&K)[3], double sigma[], double a_st, double a_end, double a_c,

@@ -268,4 +268,13 @@ int tmh_riet_det_run(const double *par, int L, int r, const double *init, const 
         for (size_t j = 0; j < 10; j++) rows_out[10 * k + j] = Rho[k][j];
     return (int)Rho.size();
 }
+// the noise-off sweep (first_order_critical_exp_delta, Rietkerk): SPB = 1 driver constants, writes its CSV under data_root
+int tmh_riet_det_sweep(int L, int div, double t_max, double a_start, double a_end, double dt, int r)
+{
+    double D[Sp] = {0.00025 / 24.0, 0.00025 / 24.0, 0.025 / 24.0}, K[3] = {0.0, 5.0, 5000.0};
+    try {
+        first_order_critical_exp_delta(div, t_max, a_start, a_end, 1e4, 0.05e-3 / 24, 0.2 / 24, 0.25 / 24, 0.2 / 24, 0.2, D, K, dt, 0.1, 10000.0, r, L);
+    } catch (const std::exception &e) { fprintf(stderr, "tmh_riet_det_sweep: %s\n", e.what()); return -2; }
+    return 0;
+}
 }
