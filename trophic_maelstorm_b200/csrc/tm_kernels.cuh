@@ -761,6 +761,7 @@ riet_dornic_kernel(const DornicArgs A)
         const bool valid = q < g.L;
         const int qc = valid ? q : g.L - 1;          // clamped: idle lanes read a legal address
         const bool ghost_r = valid && q < kHalo, ghost_l = valid && q >= g.L - kHalo;
+        const bool edge_cta = (cb == 0) || (cb == ncb - 1);
         const uint32_t ptrial = A.trial0 + (uint32_t)trial;
         // physical row of lattice-local row r in [-4, nrows+4): whole lattices wrap, slabs carry ghost rows
         auto prow = [&](int r) -> int {
@@ -804,8 +805,10 @@ riet_dornic_kernel(const DornicArgs A)
                 if (valid) {
                     double *pout = const_cast<double *>(pc) + odelta;
                     pout[0] = pstar;
-                    if (ghost_r) pout[g.L] = pstar;
-                    if (ghost_l) pout[-g.L] = pstar;
+                    if (edge_cta) {                                   // uniform: only the first and last column blocks feed ghost columns
+                        if (ghost_r) pout[g.L] = pstar;
+                        if (ghost_l) pout[-g.L] = pstar;
+                    }
                 }
                 Pu = Pc; Pc = Pd; Pd = Pn; Pl = Pln; Pr = Prn;
                 pc = p1; p1 = p2; p2 += g.Lp;
