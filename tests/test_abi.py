@@ -63,3 +63,34 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 assert "tm_oracle" not in txt and "oracle_lib" not in txt and "libtm_oracle" not in txt, os.path.join(d, f)
+
+
+def _header_names(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_fke_and_consumer_headers_are_exported_too():
+    """include/tm_fke.h and include/tm_consumer.h: every declared entry point is exported and bound by the ctypes views."""
+    lib = tm.lib()
+    for header, bound in (("tm_fke.h", tm.FKE_ABI_SYMBOLS), ("tm_consumer.h", tm.CONS_ABI_SYMBOLS)):
+        names = _header_names(header)
+        assert names, header
+        for n in names:
+            assert hasattr(lib, n), "libtm_lattice.so does not export %s (%s)" % (n, header)
+        assert sorted(bound) == names, "python binding list out of sync with %s" % header
+
+
+def test_other_entry_points_have_no_cpu_fallback_either():
+    """The consumer-side stepper, the FKE mover and the noise-off DP path fail loudly without a device."""
+    lib = tm.lib()
+    if lib.tm_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    import numpy as np
+    with pytest.raises(tm.TmError, match="no CUDA device"):
+        tm.ConsumerOps(32)
+    with pytest.raises(tm.TmError, match="no CUDA device"):
+        tm.FkeMover(32, 1, device=0)
+    with pytest.raises(tm.TmError, match="no CUDA device"):
+        tm.dp_noise_off(8, 1.0, 1.0, 0.1, 0.1, 1.0, np.ones(64), 1)
