@@ -398,3 +398,27 @@ def test_gpu_fused_rk4_equals_the_four_stage_launches(L, nsteps):
     ops.close()
     for k in range(3):
         assert np.array_equal(outs[0][k], outs[1][k])
+
+
+@pytest.mark.gpu
+def test_gpu_spb2_sweep_writes_the_reference_csv(tmp_path):
+    """tm_b200::spb2::first_order_critical_exp_delta_stochastic_MultiSp (R/:4379 compiled with -DSPB=2): one CSV in the
+    reference's place with the 2Sp header and 16-digit rows of 14 columns, a-values in order, one row per time bin."""
+    L, r, div, t_max = 20, 2, 2, 2.0
+    par = RUN2["mixed_par"].astype(np.float64)
+    inits = np.stack([setup(L, 90 + j)[6] for j in range(r)])
+    h = host_lib()
+    h.tmh_riet2_sweep.argtypes = [C.c_int, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int]
+    h.tmh_set_options(0, 7, 0, str(tmp_path).encode())
+    assert h.tmh_riet2_sweep(L, par.ctypes.data_as(dp), div, t_max, 0.05, 0.06, r, inits.ctypes.data_as(dp), r) == 0
+    d = tmp_path / "Data" / "Rietkerk" / "Stochastic" / "2Sp"
+    files = list(d.glob("1stCC_Rietkerk_*_P_c_G_20_T_2_dt_0.1_D1_*_a1_0.05_a2_0.06_dx_0.1_R_2.csv"))
+    assert len(files) == 1, list(d.iterdir())
+    lines = files[0].read_text().splitlines()
+    assert "<<G(x; t)>_x>_r" in lines[0] and lines[1].strip() == ""
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in lines[2:]])
+    per_a = len(rows) // div
+    assert rows.shape[1] == 14 and per_a * div == len(rows) and per_a >= 2
+    assert np.all(rows[:per_a, 0] == 0.05) and np.all(rows[per_a:, 0] == 0.06) and np.all(rows[:, 1] == r) and np.all(rows[:, 2] == L)
+    assert rows[0, 3] == 0.0 and np.all(np.diff(rows[:per_a, 3]) > 0) and np.isfinite(rows).all()
+    assert np.all(rows[:, 8] <= r) and np.all(rows[:, 9] <= L * L)

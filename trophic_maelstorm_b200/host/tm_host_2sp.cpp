@@ -6,6 +6,10 @@
 
 #include <algorithm>
 #include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <sstream>
+#include <sys/stat.h>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -152,6 +156,48 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
         for (int s = 0; s < Sp - 2; s++)
             Rho[Rho.size() - 1].insert(Rho[Rho.size() - 1].end(), {rho_rep_avg_var[i][4 * s + 3], rho_rep_avg_var[i][4 * s + 4],
                                                                    rho_rep_avg_var[i][4 * s + 5], rho_rep_avg_var[i][4 * s + 6]});
+    }
+}
+
+const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"
+                                 " # Active Sites P(x; t), <<G(x; t)>_x>_r, Var[<G(x; t)>_x]_r, # Surviving Runs G(x; t), # Active Sites G(x; t), \n";
+
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar, double Vstar)
+{
+    vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = logarithm10_time_bins(t_max, 1 * dt);
+    t_measure.insert(t_measure.begin(), 0.0);                                        // R/:4401
+    std::sort(t_measure.begin(), t_measure.end());
+    t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
+    D2Vec_Double vec;
+    for (size_t i = 0; i < a_space.size(); i++) {                                   // a-values in order (OpenMP threads in the reference, R/:4509)
+        D2Vec_Double rows;
+        rietkerk_Dornic_2D_MultiSp(rows, t_measure, t_max, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_start, a_end, a_c, A, H, E, M,
+                                   pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
+        vec.insert(vec.end(), rows.begin(), rows.end());
+    }
+    std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;
+    L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r;
+    Dm1 << std::setprecision(3) << D[1]; dix << std::setprecision(2) << dx; geq << std::setprecision(5) << Gstar; veq << std::setprecision(5) << Vstar;
+    const std::string dir = options().data_root + "/Data/Rietkerk/Stochastic/2Sp";
+    std::string path;
+    for (size_t k = 1; k <= dir.size(); k++)                                         // mkdir -p
+        if (k == dir.size() || dir[k] == '/') { path = dir.substr(0, k); mkdir(path.c_str(), 0777); }
+    std::string savefile = dir + "/1stCC_Rietkerk_" + prefix + "_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
+                         + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str();                                    // R/:4582
+    if (Gstar != -1) savefile += "_Geq_" + geq.str() + "_R_" + rini.str() + ".csv";
+    else if (Vstar != -1) savefile += "_Veq_" + veq.str() + "_R_" + rini.str() + ".csv";
+    else savefile += "_R_" + rini.str() + ".csv";
+    std::ofstream out(savefile);
+    out << prelimheader << "\n";                                                     // R/:4601
+    for (size_t i = 0; i < vec.size(); i++) {
+        for (size_t j = 0; j + 1 < vec[i].size(); j++) out << std::setprecision(16) << vec[i][j] << ",";
+        out << std::setprecision(16) << vec[i][vec[i].size() - 1] << std::endl;
     }
 }
 

@@ -14,6 +14,7 @@
 // runner's CSV side outputs (frames, prelim tables, movement averages Rho_Mov) -- the SPB = 1 layer has those writers.
 #pragma once
 #include <functional>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -38,5 +39,16 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, 
                                 double (&A)[SpB][SpB], double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB],
                                 double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
                                 int g, double Gstar = -1.0, double Vstar = -1.0);
+
+// The a-sweep driver entry, R/:4379-4617 compiled with -DSPB=2: runner per a-value, one CSV
+// "<data_root>/Data/Rietkerk/Stochastic/2Sp/1stCC_Rietkerk_<prefix>_P_c_G_<L>_T_<T>_dt_..._R_<r>.csv" with the reference's
+// 2Sp header (rietkerk_bjork_constants_2Sp.h:10-11) and 16-digit rows.
+extern const std::string prelimheader;
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar = -1.0, double Vstar = -1.0);
 
 }} // namespace tm_b200::spb2

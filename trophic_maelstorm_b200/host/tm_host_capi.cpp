@@ -277,4 +277,25 @@ int tmh_riet_det_sweep(int L, int div, double t_max, double a_start, double a_en
     } catch (const std::exception &e) { fprintf(stderr, "tmh_riet_det_sweep: %s\n", e.what()); return -2; }
     return 0;
 }
+// SPB = 2 a-sweep (tm_b200::spb2::first_order_critical_exp_delta_stochastic_MultiSp); par as tmh_riet2_run; writes its CSV
+int tmh_riet2_sweep(int L, const double *par, int div, double t_max, double a_start, double a_end, int r, const double *init, int n_init)
+{
+    namespace s2 = tm_b200::spb2;
+    double D[s2::Sp] = {par[9], par[10], par[11], par[12]};
+    double K[3] = {0.0, par[7], par[8]};
+    double sigma[s2::Sp] = {par[13], par[14], 0, 0};
+    double v[s2::SpB] = {0, par[15]};
+    double A[s2::SpB][s2::SpB] = {{0, par[16]}, {par[16], 0}}, H[s2::SpB][s2::SpB] = {{0, par[17]}, {par[17], 0}};
+    double E[s2::SpB] = {1.0, par[18]}, M[s2::SpB] = {par[6], par[19]}, pR[s2::Sp] = {0.0, par[20]};
+    int dtV[s2::SpB] = {0, 1};
+    double clow[2 * s2::Sp] = {0, 1, 1, 1, 5, 1, 1, 1};
+    const size_t n4 = (size_t)4 * L * L;
+    s2::init_frame = [=](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + (size_t)(j % n_init) * n4, n4 * sizeof(double)); };
+    s2::on_measure = nullptr;
+    try {
+        s2::first_order_critical_exp_delta_stochastic_MultiSp(div, t_max, a_start, a_end, 1.0 / 24.0, par[1], par[2], par[3], par[4], par[5], D, v, K,
+                                                              sigma, A, H, E, M, pR, dtV, clow, par[21], par[22], 10000.0, r, L);
+    } catch (const std::exception &e) { fprintf(stderr, "tmh_riet2_sweep: %s\n", e.what()); return -2; }
+    return 0;
+}
 }
