@@ -347,7 +347,8 @@ void cons_rk4_fused_kernel(const RkFusedArgs A)
     __syncthreads();
     const double bW = SW0[sc], bO = SO0[sc];
     double yP = bP, yG = bG, yW = bW, yO = bO, acc[4] = {0, 0, 0, 0};
-    for (int stage = 1; stage <= 4; stage++) {
+#pragma unroll
+    for (int stage = 1; stage <= 4; stage++) {       // unrolled: the ping-pong tiles, region tests and step sizes resolve statically
         const double *RW = (stage & 1) ? SW0 : SW1, *RO = (stage & 1) ? SO0 : SO1;   // read tiles of this stage
         double *WW = (stage & 1) ? SW1 : SW0, *WO_ = (stage & 1) ? SO1 : SO0;        // ... written for the next
         const int m = stage - 1;                                                     // region shrinks by one ring per stage
