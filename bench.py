@@ -392,7 +392,11 @@ def run_fke_extra(a):
     rng = np.random.default_rng(5)
     rho = rng.gamma(2.0, 3.0, L * L); rho[rng.random(L * L) < 0.3] = 0.0
     gamma = rng.random(L * L); veff = (rng.random((L * L, 2)) * 2 - 1) * 1.2
-    gD, gV = O.fke_gaussian(1.0, bD), O.fke_gaussian(1.0, bV)   # stencil tables only (host set-up, as the reference's runner does)
+    def stencil(sigma, R):      # a normalised half-Gaussian table [0..R] (set-up of the product arm: numpy only, nothing from oracle/)
+        k = np.arange(R + 1, dtype=np.float64)
+        g = np.exp(-0.5 * (k / sigma) ** 2)
+        return np.ascontiguousarray(g / (g[0] + 2.0 * g[1:].sum()))
+    gD, gV = stencil(1.0, bD), stencil(1.0, bV)
     m = tm.FkeMover(L, 1, device=0)
     m.set_terms(0, bD, (bV, bV), (bV, bV), pref, 1e-10, gD, gV)
     dev = torch.device("cuda:0")
