@@ -219,6 +219,7 @@ int emu_grazer_dornic(int L, const double *par, unsigned long long seed, unsigne
 {
     GrazerArgs A{};
     A.L = L; A.dt = par[0]; A.dx = par[1]; A.D = par[2]; A.v = par[3]; A.M = par[4]; A.sigma = par[5]; A.D0floor = par[6];
+    grazer_derive(A);
     A.prev = prev; A.gamma = gamma; A.out = out; A.veff = veff;
     A.seed = seed; A.trial = trial; A.step = step; A.replay_u = replay_u; A.stride = stride; A.overflow = overflow;
     *overflow = 0;

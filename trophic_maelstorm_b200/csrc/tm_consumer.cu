@@ -191,6 +191,7 @@ int tm_cons_grazer_dornic_host(tm_cons_ctx *c, const tm_graz_params *p, uint64_t
     CONS_CK(cudaMemcpyAsync(c->d_gamma, gamma, n, cudaMemcpyHostToDevice, c->stream));
     GrazerArgs A{};
     A.L = c->L; A.dt = p->dt; A.dx = p->dx; A.D = p->D; A.v = p->v; A.M = p->M; A.sigma = p->sigma; A.D0floor = p->D0_floor;
+    grazer_derive(A);
     A.prev = d_prev; A.gamma = c->d_gamma; A.out = d_out; A.veff = d_veff;
     A.seed = seed; A.trial = trial; A.step = step; A.replay_u = d_replay; A.stride = stride; A.overflow = c->d_ovf;
     const int tiles = (c->L + kConsThreads - 1) / kConsThreads;

@@ -173,6 +173,8 @@ TMC_G void cons_gamma_kernel(const GammaArgs A_in)
 struct GrazerArgs {
     int L;
     double dt, dx, D, v, M, sigma, D0floor;   // D[s], v[s], M[s], sigma[s]; diff_coefficient[0] (R/:4014)
+    double dx1, dx1_2, dxb2, sigma2_1;        // 1/dx, 1/dx^2, dx/2, 1/sigma^2 (R/:3455, 3463): set by grazer_derive() on the host --
+                                              // the same IEEE operations the kernel used to repeat in every thread
     const double *prev;                       // DRho[s] [L*L]
     double *gamma;                            // [L*L] in/out (clamped at 1, R/:3915)
     double *out, *veff;                       // rho* [L*L]; advection vectors [L*L][2]
@@ -182,6 +184,13 @@ struct GrazerArgs {
     DornicConsts veg;                         // VEG variant: the vegetation's constants (R/:3461-3463), same for every cell
     const Step2Dyn *dyn;                      // non-null and dyn->skip_graz: rho* = prev, nothing drawn (R/:3910)
 };
+
+inline void grazer_derive(GrazerArgs &A)
+{
+    const double dx2 = A.dx * A.dx;
+    A.dx1 = 1 / A.dx; A.dx1_2 = 1 / (dx2); A.dxb2 = A.dx / 2.0;                              // R/:3455
+    A.sigma2_1 = 1 / (A.sigma * A.sigma);                                                     // R/:3463
+}
 
 // VEG = true: the vegetation's Dornic loop R/:3752-3809 on an unpadded field (no advection, no direction draw, constant
 // beta/lambda, alpha_i = (D0/dx^2) (up + down + left + right) in the reference's order): the first kernel of the SPB = 2 step.
@@ -194,8 +203,7 @@ TMC_G void grazer_dornic_kernel(const GrazerArgs A)
     if (q >= g) return;
     const int i = r * g + q;
     const int up = (r == 0 ? g - 1 : r - 1), dn = (r == g - 1 ? 0 : r + 1), lf = (q == 0 ? g - 1 : q - 1), rt = (q == g - 1 ? 0 : q + 1);
-    const double dx2 = A.dx * A.dx, dx1 = 1 / A.dx, dx1_2 = 1 / (dx2), dxb2 = A.dx / 2.0;   // R/:3455
-    const double sigma2_1 = 1 / (A.sigma * A.sigma);
+    const double dx1 = A.dx1, dx1_2 = A.dx1_2, dxb2 = A.dxb2, sigma2_1 = A.sigma2_1;        // grazer_derive()
     typename std::conditional<REPLAY, ReplaySrc, PhiloxSrc>::type src;
     if constexpr (REPLAY) src.begin(A.replay_u + (size_t)i * A.stride, A.stride);
     else src.begin((uint32_t)i, A.trial, A.step, A.seed);
@@ -452,6 +460,7 @@ inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, Step2Buffe
     const bool replay = b.replay_veg != nullptr;
     GrazerArgs V{};
     V.L = L; V.dt = k.dt; V.dx = k.dx; V.D = k.D; V.v = k.v; V.M = k.M; V.sigma = k.sigma; V.D0floor = k.D0floor;
+    grazer_derive(V);
     V.prev = b.state; V.gamma = b.gamma; V.out = b.star; V.veff = b.veff;
     V.seed = seed; V.trial = trial; V.step = step; V.replay_u = b.replay_veg; V.stride = b.stride; V.overflow = b.overflow;
     V.veg = k.veg; V.dyn = nullptr;
