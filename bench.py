@@ -126,7 +126,7 @@ def _ref_worker(args):
     import oracle_lib as O
     os.chdir(tempfile.mkdtemp(prefix="tmref_"))
     frame = np.ascontiguousarray(O.synthetic_rietkerk_frame(L, seed=seed, a=a, fringe=False).reshape(3, -1))
-    so = os.path.join(ROOT, "oracle", "_ref", "libtm_ref_riet.so")
+    so = ref_riet_so()
     dt = 0.1
     if os.path.exists(so):
         ref = C.CDLL(so)
@@ -160,14 +160,50 @@ def _ref_worker(args):
             return time.perf_counter() - t0
         kind = "port"
     # two run lengths: the difference removes set-up (neighbour tables, frame copies)
-    t_short = run(2)
-    t_long = run(2 + steps)
+    t_short = run(1)
+    t_long = run(1 + steps)
     return kind, max(t_long - t_short, 1e-9)
+
+
+def ref_riet_so():
+    """The unmodified reference compiled here by oracle/Makefile (it cannot be rebuilt on the GPU host: /root/reference
+    does not travel).  Two builds travel: -march=x86-64-v4 (AVX-512; what -march=native gives on the Xeon hosts of this
+    pool) and -march=x86-64-v3; the best one this host can execute is used."""
+    d = os.path.join(ROOT, "oracle", "_ref")
+    try:
+        with open("/proc/cpuinfo") as fh:
+            flags = fh.read()
+    except Exception:
+        flags = ""
+    v4 = os.path.join(d, "libtm_ref_riet_v4.so")
+    if os.path.exists(v4) and all(f in flags for f in ("avx512f", "avx512bw", "avx512vl", "avx512dq", "avx512cd")):
+        return v4
+    return os.path.join(d, "libtm_ref_riet.so")
+
+
+def ref_procs_for(L, cores):
+    """How many L x L reference runners fit in host memory at once (the runner holds ~21 fields plus nested-vector
+    neighbour tables: ~390 B per site, measured 1.6 GB at L = 2048)."""
+    need = 400.0 * L * L + 3e8
+    try:
+        import psutil
+        avail = float(psutil.virtual_memory().available)
+        try:
+            with open("/sys/fs/cgroup/memory.max") as fh:
+                lim = fh.read().strip()
+            if lim != "max":
+                avail = min(avail, float(lim) * 0.9)
+        except Exception:
+            pass
+    except Exception:
+        avail = 16e9
+    return int(max(1, min(cores, (0.6 * avail) // need)))
 
 
 def cpu_reference(L, steps, procs):
     """site-updates/s of the CPU integrator on `procs` cores (one a-value per core)."""
     import multiprocessing as mp
+    procs = ref_procs_for(L, procs)
     ctx = mp.get_context("spawn")
     jobs = [(L, steps, 0.05 + 0.001 * i, 100 + i) for i in range(procs)]
     t0 = time.perf_counter()
@@ -179,7 +215,9 @@ def cpu_reference(L, steps, procs):
     rate = procs * L * L * steps / slowest
     return {"value": rate, "unit": UNIT, "cores": procs, "kind": kind,
             "sample": "Rietkerk SPB=1 L=%d lattice per core, %d Dornic+RK4 steps each, %d a-values in parallel "
-                      "(the reference parallelises over a-values only); set-up excluded; wall %.1f s" % (L, steps, procs, wall)}
+                      "(the reference parallelises over a-values only, R/:4509; as many as fit in host memory); set-up excluded; "
+                      "wall %.1f s; %s (g++ -O3, no -fopenmp: g++ 13 rejects R/:2621 under it; built in the build container, "
+                      "/root/reference does not travel to the GPU host)" % (L, steps, procs, wall, os.path.basename(ref_riet_so()) if kind == "reference" else "oracle port")}
 
 
 def host_cores():
@@ -189,25 +227,31 @@ def host_cores():
         return max(1, os.cpu_count() or 1)
 
 
+def workload_config(L, trials):
+    """The `config` object: the same in both arms (the reference arm times THIS workload, see cpu_baseline.sample)."""
+    return {"workload": "Rietkerk SPB=1 (veg/soil-water/surface-water) Dornic+RK4 step, L=%d, %d trial(s) per GPU, "
+                        "a=0.05 dt=0.1, MFT speckle initial frame" % (L, trials),
+            "parallelism": "independent trials per rank, no data-path collective",
+            "l2": ("state %.0f MiB per GPU (x2 ping-pong) exceeds the 126 MB L2; no flush needed" if trials * 3 * L * L * 8 > 126e6 else
+                   "state %.0f MiB per GPU fits the 126 MB L2 (not the headline configuration); no flush") % (trials * 3 * L * L * 8 / 2**20)}
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
     steps = max(1, a.steps)
-    per_step = []
-    base = None
-    for _ in range(a.warmup and 1 or 0):
-        cpu_reference(a.ref_L, 1, cores)
-    t0 = time.perf_counter()
-    base = cpu_reference(a.ref_L, steps, cores)
-    wall = time.perf_counter() - t0
+    # Same configuration as the product arm: L x L lattices of the named L (one per host core that fits in memory, the
+    # reference's own a-value parallelism), `steps` time steps each after the runner's first (warm-up) step; the set-up
+    # (neighbour tables, frame copies) is excluded by differencing two run lengths.  At L = 4096 a step costs ~2 s per core.
+    ref_L = a.ref_L or a.L
+    base = cpu_reference(ref_L, steps, cores)
     v = base["value"]
     out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup,
            "ms_per_step": 1e3 * a.L * a.L * a.trials * a.gpus / v, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-           "config": {"workload": "Rietkerk SPB=1 Dornic+RK4, L=%d, %d trial(s) per GPU; CPU arm times a bounded sample: %s"
-                                  % (a.L, a.trials, base["sample"])},
+           "config": workload_config(a.L, a.trials),
            "cpu_baseline": base, "gpu_launches": 0,
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -271,16 +315,20 @@ def run_ours(a):
     t1 = time.time()
     ms_dev, n_launch = lat.last_step_ms()   # CUDA events recorded around the K launches
     barrier()
-    # the timed region is only K x 0.6 ms: keep the same kernel running (untimed) for ~0.5 s so that
-    # nvidia-smi (100 ms period) sees the clocks and throttle reasons under this load
-    t_probe = time.time()
-    while time.time() - t_probe < 0.5:
-        lat.step(50)
+    # Sustained figure: the K-step region is only a few ms, a real run is 1e5-1e6 steps.  The same launches run back to
+    # back for >= --sustain-s seconds in chunks of 256 steps (device time per chunk from the same CUDA events), the
+    # clock sampler covers the whole window, and the line carries both numbers.
+    sus_ms, sus_steps, t_probe = 0.0, 0, time.time()
+    while time.time() - t_probe < max(a.sustain_s, 0.5):
+        lat.step(256)
         lat.sync()
+        ms_c, _ = lat.last_step_ms()
+        sus_ms += ms_c; sus_steps += 256
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
-    clocks["window"] = "timed region + 0.5 s of the same launches"
+    clocks["window"] = "the K timed steps + %.1f s of the same launches back to back (the sustained window)" % (t1 - t_probe)
     ms_dev = maxr(ms_dev)
+    sus_ms = maxr(sus_ms)
     # per-kernel durations: a second pass over K steps with an event between the two launches of each step
     lat.set_kernel_timing(True)
     lat.step(min(K, 64))
@@ -318,17 +366,23 @@ def run_ours(a):
     import ctypes as C
     h2d = trials * 3 * L * L * 8
     d2h = trials * C.sizeof(tm.Stats)
+    # what bounds e2e: the host->device link.  Measured here, in the same process and at the same N (all ranks copy at
+    # once, as they do in the e2e loop): the bare upload of the same pinned frame through the same call.
+    lat.upload(hnp)
+    barrier()
+    tu0 = time.perf_counter()
+    for _ in range(3):
+        lat.upload(hnp)
+    tu = maxr((time.perf_counter() - tu0) / 3)
+    h2d_gbs = h2d / tu / 1e9
+    e2e_ceiling = sites_per_step / (tu + (ms_dev * 1e-3 / K))   # serial upload + step, no overlap
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Rietkerk SPB=1 (veg/soil-water/surface-water) Dornic+RK4 step, L=%d, %d trial(s) per GPU, "
-                               "a=0.05 dt=0.1, MFT speckle initial frame" % (L, trials),
-                   "parallelism": "independent trials per rank, no data-path collective",
-                   "l2": "state %.0f MiB per GPU (x2 ping-pong) exceeds the 126 MB L2; no flush needed" % (trials * 3 * L * L * 8 / 2**20),
-                   "timing": "CUDA events on the kernel stream around K launches, max over ranks",
-                   "finite": ok},
+        "config": workload_config(L, trials),
+        "timing": "CUDA events on the kernel stream around K steps, max over ranks", "finite": ok,
         "gpu_launches": n_launch,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -336,15 +390,27 @@ def run_ours(a):
                      "algorithmic_bytes_per_step": trials * L * L * BYTES_PER_SITE_UPDATE,
                      "kernel": "one step = tml::riet_dornic_kernel<STRICT=0> + tml::riet_step_kernel<DET=0,STRICT=0,SRC=pre,DORNIC_ONLY=0>",
                      "kernels": kernel_lines(trials * L * L, ms_dornic, ms_rk4, n_timed, peak)},
+        "sustained": {"value": sites_per_step * sus_steps / (sus_ms * 1e-3), "unit": UNIT, "steps": sus_steps,
+                      "device_seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / sus_steps,
+                      "frac": (trials * L * L * BYTES_PER_SITE_UPDATE) / (sus_ms * 1e-3 / sus_steps) / 1e9 / peak,
+                      "vs_burst": (sus_ms / sus_steps) / (ms_dev / K),
+                      "note": "same launches back to back, CUDA events per 256-step chunk, max over ranks; clocks.sm_mhz is the median "
+                              "over this window"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": Ke, "call": "tm_run_host(ctx, pinned_host_frame, nsteps=1, download=0, stats)"},
+                "steps": Ke, "call": "tm_run_host(ctx, pinned_host_frame, nsteps=1, download=0, stats)",
+                "h2d_gbs_measured": h2d_gbs, "link_bound_value": e2e_ceiling, "frac_of_link_bound": e2e_value / e2e_ceiling,
+                "note": "bounded by the host->device copy of the 3 L x L planes (measured rate beside it, all ranks copying at "
+                        "once); link_bound_value = sites / (upload time + device step time)"},
         "e2e_runner": {"value": sites_per_step * Kr * 2 / tr, "unit": UNIT, "calls": 2, "steps_per_call": Kr,
                        "h2d_bytes_per_call": h2d, "d2h_bytes_per_call": d2h,
                        "call": "tm_run_host(ctx, pinned_host_frame, nsteps=%d, download=0, stats): the frame is copied in once per "
                                "call, as the reference's runner takes one initial frame and t_max; not the headline e2e" % Kr},
     }
     if rank == 0 and world == 1 and not a.no_cpu:
-        out["cpu_baseline"] = cpu_reference(a.ref_L, a.ref_steps, host_cores())
+        # same configuration (L x L lattices of the workload's L, as many as fit in host memory), bounded to 2 steps;
+        # and the round-1 sample (cache-friendly L = 512, one lattice per core) beside it
+        out["cpu_baseline"] = cpu_reference(a.ref_L or L, a.ref_steps, host_cores())
+        out["cpu_baseline_small_lattice"] = cpu_reference(512, 12, host_cores())
     lat.close()
     if dist is not None:
         dist.barrier()
@@ -512,8 +578,9 @@ def main():
     ap.add_argument("--trials", type=int, default=1, help="trials per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--runner-steps", type=int, default=100)
-    ap.add_argument("--ref-L", type=int, default=512, help="lattice side of the bounded CPU sample")
-    ap.add_argument("--ref-steps", type=int, default=12)
+    ap.add_argument("--ref-L", type=int, default=0, help="lattice side of the CPU sample (0: the workload's own L)")
+    ap.add_argument("--ref-steps", type=int, default=2, help="time steps of the cpu_baseline leg of the product arm")
+    ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke", "spb2"], help="dp, fke, spb2: extra, non-headline lines")
     ap.add_argument("--fke-bound-d", type=int, default=1, help="fke: diffusion window half-width (the SPB=2 driver's constants give 1)")

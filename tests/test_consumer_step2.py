@@ -294,7 +294,7 @@ def running_table(rho_m, t_meas):
 @pytest.mark.gpu
 def test_gpu_spb2_runner_rows_and_frames():
     """rietkerk_Dornic_2D_MultiSp (SPB = 2 signature) over the resident stepper: the frames it measures equal the oracle's
-    stepped from the same Philox streams (seed = options().seed, trial = replicate, step = steps since t = 0), and its
+    stepped from the same Philox streams (seed = stream_seed(options().seed, a), trial = replicate, step = steps since t = 0), and its
     output rows are the reference's bookkeeping of those frames (left-to-right means, running mean/variance over
     surviving replicates with the integer 1/(r-1), row layout R/:4361-4372)."""
     L, r, seed = 24, 3, 4242
@@ -303,6 +303,9 @@ def test_gpu_spb2_runner_rows_and_frames():
     t_meas = np.array([0.0, 0.2, 0.5, 0.9, 1.0])
     h = host_lib()
     h.tmh_set_options(0, seed, 0, None)
+    h.tmh_stream_seed.restype = C.c_ulonglong
+    h.tmh_stream_seed.argtypes = [C.c_ulonglong, C.c_double]
+    key = h.tmh_stream_seed(seed, float(par[0]))       # the runner keys its streams by (TM_SEED, a): tm_host.h stream_seed
     rows = np.zeros((16, 14))
     frames = np.zeros((r, len(t_meas), 4, L * L))
     n = h.tmh_riet2_run(L, par.ctypes.data_as(dp), r, inits.ctypes.data_as(dp), r, t_meas.ctypes.data_as(dp), len(t_meas),
@@ -326,7 +329,7 @@ def test_gpu_spb2_runner_rows_and_frames():
                 for s_ in range(4):
                     X[index, 2 * s_], X[index, 2 * s_ + 1] = O.occupied(got[s_]), O.mean(got[s_])
                 index += 1
-            O.step_2sp(pv, pg, pc, central, fr, O.make_rng(O.SRC_PHILOX, seed=seed, trial=j, step=step), f, g)
+            O.step_2sp(pv, pg, pc, central, fr, O.make_rng(O.SRC_PHILOX, seed=key, trial=j, step=step), f, g)
             step += 1
             t += dt
         rho_m.append(X)

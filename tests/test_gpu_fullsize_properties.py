@@ -96,3 +96,163 @@ def test_dp_L2048_sweep_extinction_is_absorbing_and_monotone_in_a():
     act = [st[i].active[0] for i in range(len(avals))]
     assert act[0] < act[1] < act[2] < act[3] and all(s.nonfinite == 0 and s.negative == 0 for s in st)
     lat.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The BENCHMARKED variant (FAST arithmetic, Dornic sweep + RK4 kernel pair, Philox streams) against the CPU
+# oracle at BASELINE's own sizes.  Tolerance (north_star): <= 1e-12 relative in FP64.  The one documented
+# exception: a 1-ulp difference in the argument of the Gaussian-Poisson truncation `long(norm*sqrt(z)+z)`
+# (R/:3776, z ~ 1.6e8) moves the count by one, a ~6e-9 relative jump of rho*, expected in ~3e-8 of the cells
+# per step.  Such cells are counted and bounded, never ignored.
+# ---------------------------------------------------------------------------------------------------------
+FLIP_RATE = 3e-8       # predicted truncation flips per cell and step
+FLIP_JUMP = 1e-6       # no cell may differ by more than this (a flip is ~1/g ~ 6e-9 relative)
+
+
+def _flip_budget(cells_steps):
+    """upper bound on flipped cells: Poisson mean FLIP_RATE * cells_steps, P(exceed) < 1e-9"""
+    lam = FLIP_RATE * cells_steps
+    return int(lam + 7.0 * np.sqrt(lam) + 8)
+
+
+def _oracle_step(p, state, seed, trial, step):
+    op = O.to_oparams(p)
+    f = np.ascontiguousarray(state, dtype=np.float64).copy()
+    O.step(op, O.make_rng(O.SRC_PHILOX, seed=seed, trial=trial, step=step), f.reshape(3, -1))
+    return f
+
+
+def _compare_fast(got, want, what):
+    """-> number of cells beyond 1e-12 (all fields); asserts the jump bound and the occupancy pattern"""
+    bad = 0
+    for f in range(3):
+        scale = np.maximum(np.abs(want[f]), 1e-12 * np.abs(want[f]).max())
+        err = np.abs(got[f] - want[f]) / scale
+        assert err.max() <= FLIP_JUMP, "%s field %d: max rel err %.3e" % (what, f, err.max())
+        bad += int((err > 1e-12).sum())
+    assert np.array_equal(got[0] > 0, want[0] > 0), what + ": occupancy pattern differs"
+    return bad
+
+
+def test_L1024_fast_pair_matches_oracle_per_step():
+    """config 2/3 shape: L = 1024, 2 trials, 2 steps of the benchmarked FAST pair, each step started from the
+    oracle's state (per-step parity, north_star), fringe frame so that every sampler regime is present."""
+    L, n_trials, seed = 1024, 2, 90210
+    p = tm.rietkerk_params(L)
+    state = np.stack([O.synthetic_rietkerk_frame(L, seed=500 + t, fringe=True) for t in range(n_trials)])
+    lat = tm.Lattice(p, n_trials)
+    lat.seed(seed, trial0=3)
+    bad = 0
+    for s in range(2):
+        lat.upload(state); lat.set_step_counter(s); lat.step(1)
+        got = lat.download()
+        assert lat.sampler_overflow() == 0
+        for t in range(n_trials):
+            state[t] = _oracle_step(p, state[t], seed, 3 + t, s)
+            bad += _compare_fast(got[t], state[t], "step %d trial %d" % (s, t))
+    lat.close()
+    assert bad <= 3 * _flip_budget(2 * n_trials * L * L), bad   # a flipped rho* shows in P, W and O of that cell
+
+
+def test_L4096_fast_pair_matches_oracle_one_step():
+    """The bench configuration itself (L = 4096, one trial, FAST pair, the bench's frame rule): one step against the oracle."""
+    L, seed = 4096, 20261017
+    p = tm.rietkerk_params(L)
+    frame = O.synthetic_rietkerk_frame(L, seed=1234, fringe=False)
+    lat = tm.Lattice(p, 1)
+    lat.seed(seed)
+    lat.upload(frame[None]); lat.step(1)
+    got = lat.download()[0]
+    st = lat.measure()[0]
+    assert lat.sampler_overflow() == 0
+    lat.close()
+    want = _oracle_step(p, frame, seed, 0, 0)
+    bad = _compare_fast(got, want, "L=4096")
+    assert bad <= 3 * _flip_budget(L * L), bad
+    for f in range(3):
+        assert st.active[f] == int(O.occupied(want[f]))
+        assert abs(st.mean[f] - O.mean(want[f])) <= 1e-12 * abs(O.mean(want[f]))
+
+
+def test_L4096_strict_vs_fast_flip_count():
+    """GPU STRICT (bit-identical to the oracle at every size the oracle is run) against GPU FAST at L = 4096 on the
+    fringe frame: <= 1e-12 everywhere except the predicted truncation flips, whose COUNT is asserted (4 independent
+    single steps: 6.7e7 cell-steps, ~2 flips expected)."""
+    L, seed, nrep = 4096, 606, 4
+    p = tm.rietkerk_params(L)
+    frame = O.synthetic_rietkerk_frame(L, seed=2, fringe=True)
+    out = {}
+    for strict in (True, False):
+        lat = tm.Lattice(p, 1)
+        lat.set_strict(strict); lat.seed(seed)
+        res = []
+        for s in range(nrep):
+            lat.upload(frame[None]); lat.set_step_counter(s); lat.step(1)
+            res.append(lat.download()[0])
+        assert lat.sampler_overflow() == 0
+        lat.close()
+        out[strict] = res
+    flipped = 0
+    for s in range(nrep):
+        scaleP = np.maximum(np.abs(out[True][s][0]), 1e-12 * np.abs(out[True][s][0]).max())
+        errP = np.abs(out[False][s][0] - out[True][s][0]) / scaleP
+        flipped += int((errP > 1e-12).sum())
+        _compare_fast(out[False][s], out[True][s], "rep %d" % s)
+    assert flipped <= _flip_budget(nrep * L * L), flipped
+
+
+def test_dp_L2048_sweep_matches_reference_ensemble():
+    """BASELINE config 4 at full size: 8 a-values near criticality at L = 2048, rho0 = 1, t_max = 100 (1000 steps), 4 GPU
+    replicates per a-value, against ONE replicate per a-value of the unmodified reference (tests/golden/ens_dp_L2048.npz,
+    made by tests/golden/make_dp_config4_golden.py).  A 4.2 M-site lattice self-averages, so single trajectories are
+    comparable: the replicate-to-replicate spread s(t) of <rho>(t) is measured from the GPU replicates (variance averaged
+    over a 15-row window) and the reference must sit within 6 s sqrt(1 + 1/4) of the GPU mean at every row (north_star's 95 %
+    CI is 2 s; the rows are strongly correlated in time and there are ~500 of them, so the extreme is what is bounded);
+    the decay exponent delta = -dlog<rho>/dlog t over t in [10, 100] must agree with the reference's at every a-value
+    within 0.012, decrease with a, and bracket 2+1-D DP's 0.4505; and every lattice survives."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ens_dp_L2048.npz"))
+    L, dt, avals, t_meas, ref = int(g["L"]), float(g["dt"]), g["a_values"], g["t_meas"], g["series"]
+    b, D, sigma, _, dx = [float(x) for x in g["params"]]
+    nrep, na = 4, len(avals)
+    nt = na * nrep
+    p = tm.dp_params(L, a=float(avals[0]), b=b, D=D, sigma=sigma, dt=dt, dx=dx)
+    lat = tm.Lattice(p, nt)
+    for i, a in enumerate(avals):
+        for j in range(nrep):
+            lat.set_trial_a(i * nrep + j, float(a))
+    lat.seed(424242)
+    lat.upload(np.ones((nt, 1, L, L)))
+    # the reference runner's measurement schedule: every step while t <= 1, then the t_meas windows (P/:1016-1025)
+    rows, t, index = [], 0.0, 0
+    while t < t_meas[-1] + dt:
+        if t <= 1.0 or (index < len(t_meas) and t_meas[index] - dt / 2 <= t < t_meas[index] + dt / 2):
+            st = lat.measure()
+            rows.append([t] + [st[k].mean[0] for k in range(nt)] + [float(st[k].active[0]) for k in range(nt)])
+            if t > 1.0:
+                index += 1
+        lat.step(1)
+        t += dt
+    assert lat.sampler_overflow() == 0
+    lat.close()
+    rows = np.array(rows)
+    assert rows.shape[0] == ref.shape[1], (rows.shape, ref.shape)
+    assert np.allclose(rows[:, 0], ref[0, :, 0], atol=1e-9)
+    gm = rows[:, 1:1 + nt].reshape(-1, na, nrep)
+    assert np.all(rows[:, 1 + nt:] > 0) and np.all(ref[:, :, 2] > 0)      # nobody dies at this size
+    worst = 0.0
+    for i in range(na):
+        mean = gm[:, i].mean(axis=1)
+        var = np.convolve(gm[:, i].var(axis=1, ddof=1), np.ones(15) / 15, mode="same")
+        ok = var > 0                                                      # t = 0 is deterministic
+        assert np.allclose(ref[i, ~ok, 1], mean[~ok], rtol=1e-12)
+        z = np.abs(ref[i, ok, 1] - mean[ok]) / np.sqrt(var[ok] * (1 + 1.0 / nrep))
+        worst = max(worst, float(z.max()))
+    assert worst < 6.0, worst
+    tt = rows[:, 0]; w = tt >= 10.0
+    slope = lambda y: -np.polyfit(np.log(tt[w]), np.log(y[w]), 1)[0]
+    d_gpu = np.array([slope(gm[:, i].mean(axis=1)) for i in range(na)])
+    d_ref = np.array([slope(ref[i, :, 1]) for i in range(na)])
+    assert np.abs(d_gpu - d_ref).max() < 0.012, (d_gpu, d_ref)
+    assert np.all(np.diff(d_gpu) < 0), d_gpu                              # larger a decays more slowly
+    assert d_gpu.min() - 0.03 < 0.4505 < d_gpu.max() + 0.03, d_gpu

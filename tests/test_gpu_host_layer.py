@@ -24,6 +24,8 @@ def host():
     h.tmh_dp_run.argtypes = [C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, dp, dp, C.c_int, dp, C.c_int]
     h.tmh_riet_run.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, dp, dp, C.c_int, dp, C.c_int, C.c_char_p, dp, C.c_int]
     h.tmh_dp_sweep.argtypes = [C.c_int, C.c_int, C.c_int] + [C.c_double] * 9 + [C.c_int]
+    h.tmh_stream_seed.restype = C.c_ulonglong
+    h.tmh_stream_seed.argtypes = [C.c_ulonglong, C.c_double]
     return h
 
 
@@ -49,7 +51,7 @@ def test_dp_runner_bookkeeping_matches_reference_semantics(host):
     rows = dp_rows(host, False, L, params, rho0, t_meas, r, seed)
     # independent replay of the same trials through the ctypes binding
     lat = tm.Lattice(tm.dp_params(L, a=params[0], b=params[1], D=params[3], sigma=params[4], dt=0.1, dx=1.0), r)
-    lat.seed(seed)
+    lat.seed(host.tmh_stream_seed(seed, params[0]))      # the runner keys its streams by (TM_SEED, a): tm_host.h stream_seed
     lat.upload(np.ones((r, 1, L, L)))
     tot = int(1.0 / 0.1) + 1 + len(t_meas)
     series = np.zeros((r, tot, 2)); s = 0

@@ -188,9 +188,13 @@ def test_dp_bit_exact(cubic, L):
     lat.close()
 
 
-@pytest.mark.parametrize("model", ["riet", "dp", "cubic"])
+@pytest.mark.parametrize("model", ["riet", "dp", "cubic", "riet_fast"])
 def test_replay_host_uniforms(model):
-    """Replay mode: host-supplied uniforms, fixed per-cell stride, one step."""
+    """Replay mode: host-supplied uniforms, fixed per-cell stride, one step.  `riet_fast` is the same replay through the
+    FAST arithmetic (the benchmarked kernels' arithmetic): north_star's replay criterion, <= 1e-12."""
+    fast = model == "riet_fast"
+    if fast:
+        model = "riet"
     L, stride = 48, 96
     rng = np.random.default_rng(21)
     if model == "riet":
@@ -204,7 +208,7 @@ def test_replay_host_uniforms(model):
         frame = rng.random((1, L, L)) * 1.5; frame[0, :, :10] = 0
     u = (rng.integers(0, 2 ** 52, L * L * stride, dtype=np.uint64).astype(np.float64)) * 2.0 ** -52
     lat = tm.Lattice(p, 1)
-    lat.set_strict(True)
+    lat.set_strict(not fast)
     lat.upload(frame[None])
     lat.step_replay(u, stride)
     got = lat.download()[0]
@@ -213,7 +217,14 @@ def test_replay_host_uniforms(model):
     want = frame.copy()
     O.step(O.to_oparams(p), org, want.reshape(want.shape[0], -1))
     assert org.overflow == 0
-    assert np.array_equal(got, want), rel_err(got, want)
+    if fast:
+        for f in range(3):
+            scale = np.maximum(np.abs(want[f]), 1e-12 * np.abs(want[f]).max())
+            err = np.abs(got[f] - want[f]) / scale
+            assert err.max() <= RTOL, "field %d: %.3e" % (f, err.max())   # 2304 cells: no truncation flip expected (3e-8 per cell)
+        assert np.array_equal(got[0] > 0, want[0] > 0)
+    else:
+        assert np.array_equal(got, want), rel_err(got, want)
     lat.close()
 
 

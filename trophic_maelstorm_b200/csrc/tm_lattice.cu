@@ -552,8 +552,13 @@ int tm_measure(tm_ctx *c, tm_stats *out)
                                                                             (double)((long long)g.nrows * g.L), c->stats_dev);
     TM_CUDA(c, cudaGetLastError());
     std::vector<TmStatsDev> h(g.n_trials);
+    unsigned long long hc[4] = {0, 0, 0, 0};
     TM_CUDA(c, cudaMemcpyAsync(h.data(), c->stats_dev, sizeof(TmStatsDev) * g.n_trials, cudaMemcpyDeviceToHost, c->stream));
+    TM_CUDA(c, cudaMemcpyAsync(hc, c->counters, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
     TM_CUDA(c, cudaStreamSynchronize(c->stream));
+    // a lost bulk copy (bounded mbarrier wait) leaves garbage rows: every measurement carries the check, so no runner
+    // can log statistics of an invalid state
+    if (hc[1]) TM_FAIL(c, TM_E_CUDA, "TMA pipeline timed out in %llu CTA(s): the state is invalid", hc[1]);
     for (int t = 0; t < g.n_trials; t++) {
         for (int f = 0; f < 3; f++) { out[t].mean[f] = h[t].mean[f]; out[t].active[f] = h[t].active[f]; }
         out[t].nonfinite = h[t].nonfinite; out[t].negative = h[t].negative;

@@ -32,6 +32,15 @@ Options &options()
     return o;
 }
 
+unsigned long long stream_seed(unsigned long long seed, double a)
+{
+    unsigned long long bits;
+    memcpy(&bits, &a, sizeof bits);
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (bits | 1ull);     // splitmix64 finaliser over (seed, a)
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
 namespace {
 struct Ctx { // RAII over tm_ctx; errors become exceptions like the reference's exit() paths
     tm_ctx *c = nullptr;
@@ -141,7 +150,7 @@ void dp_runner(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[]
     vector<double> host(n * r);
     for (int j = 0; j < r; j++) memcpy(&host[n * j], Rh0, n * sizeof(double)); // P/:988-992
     ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
-    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");
+    ctx.ck(tm_seed(ctx.c, stream_seed(options().seed, a), 0), "tm_seed");
 
     const int tot_iter = static_cast<int>(1.0 / dt) + 1 + (int)t_meas.size(); // P/:949
     vector<double> acc_(5 * (size_t)tot_iter, 0.0);
@@ -299,7 +308,7 @@ void spreading_exp_Dornic_2D(vector<vector<double>> &Rho, vector<double> &t_meas
     vector<double> host(n * r);
     for (int j = 0; j < r; j++) memcpy(&host[n * j], Rh0, n * sizeof(double)); // P/:1188-1192
     ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
-    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");
+    ctx.ck(tm_seed(ctx.c, stream_seed(options().seed, a), 0), "tm_seed");
 
     const int tot_iter = static_cast<int>(1.0 / dt) + 1 + (int)t_meas.size(); // P/:1153
     vector<double> acc_(4 * (size_t)tot_iter, 0.0);
@@ -482,7 +491,7 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
             init_frame(&host[3 * n * t], g, t, a_values[ia], a_c, dP, clow);
         }
     ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
-    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");
+    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");   // trial id = a-index * r + replicate: every (a, replicate) has its own stream
 
     const int tot_iter = (int)t_meas.size();               // R/:3438
     const int W_ = 4 * SpB + 3;                            // Sp4_1: {t, <W>, <O>, mean, var, surv, active}

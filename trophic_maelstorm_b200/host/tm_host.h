@@ -35,6 +35,13 @@ struct Options {
 };
 Options &options(); // process-wide; env TM_DEVICE, TM_SEED, TM_STRICT, TM_DATA_ROOT override the defaults
 
+// The Philox key a runner hands to the device for control parameter `a`: options().seed mixed with the bit pattern of a.
+// The reference seeds every replicate of every a-value from std::random_device (P/:973, R/:3511), so the a-values of a
+// sweep are statistically independent; a fixed key would give trials 0..r-1 the same (seed, trial, step, cell) counters
+// at every a-value.  The mix depends on (seed, a) only -- not on call order or on which GPU runs the a-value -- so a
+// sweep is reproducible and identical on 1 or 8 GPUs.  Runs meant to be independent need different TM_SEED values.
+unsigned long long stream_seed(unsigned long long seed, double a);
+
 // ---- bookkeeping (host) --------------------------------------------------------------------
 std::vector<double> linspace(double start, double end, int num);                 // P/:254
 std::vector<double> logarithm10_time_bins(double t_max, double dt);              // P/:336

@@ -122,7 +122,7 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
         while (t < t_end + dt) {                                                      // R/:3648
             const bool meas = index < tot_iter && (t == 0 || (t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0));   // R/:3659
             if (meas) {
-                if (pending) { ctx.ck(tm_cons_step2_run(ctx.c, options().seed, (uint32_t)j, step, pending), "tm_cons_step2_run"); step += pending; pending = 0; }
+                if (pending) { ctx.ck(tm_cons_step2_run(ctx.c, stream_seed(options().seed, a), (uint32_t)j, step, pending), "tm_cons_step2_run"); step += pending; pending = 0; }
                 ctx.ck(tm_cons_step2_download(ctx.c, frame.data(), nullptr, nullptr, nullptr, nullptr), "tm_cons_step2_download");
                 for (int s = 0; s < Sp; s++) {
                     const double *f = &frame[s * n];

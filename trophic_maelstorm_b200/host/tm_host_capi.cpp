@@ -17,6 +17,8 @@ void tmh_set_options(int device, unsigned long long seed, int strict, const char
     if (data_root) options().data_root = data_root;
 }
 
+unsigned long long tmh_stream_seed(unsigned long long seed, double a) { return stream_seed(seed, a); }
+
 int tmh_time_bins(double t_max, double dt, double *out, int cap)
 {
     std::vector<double> v = logarithm10_time_bins(t_max, dt);
