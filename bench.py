@@ -319,7 +319,7 @@ def run_ours(a):
     # back for >= --sustain-s seconds in chunks of 256 steps (device time per chunk from the same CUDA events), the
     # clock sampler covers the whole window, and the line carries both numbers.
     sus_ms, sus_steps, t_probe = 0.0, 0, time.time()
-    while time.time() - t_probe < max(a.sustain_s, 0.5):
+    while time.time() - t_probe < max(a.sustain_s, 0.1):
         lat.step(256)
         lat.sync()
         ms_c, _ = lat.last_step_ms()

@@ -81,6 +81,11 @@ typedef struct tm_stats {
 /* --- lifecycle ------------------------------------------------------------------------ */
 int tm_abi_version(void);
 int tm_device_count(void);                  /* 0 when no CUDA device is visible */
+/* Sizing aids of the ensemble scheduler (the reference's `#pragma omp parallel for` over a-values,
+ * Rietkerk_FD/rietkerk_bjork_basic.cpp:4509-4542, has no memory limit to respect; a device context does):
+ * free / total memory of a device, and the device bytes a context of n_trials whole lattices of *p will allocate. */
+int tm_device_mem(int device, uint64_t *free_bytes, uint64_t *total_bytes);
+int tm_ctx_bytes(const tm_params *p, int n_trials, uint64_t *bytes);
 const char *tm_last_error(const tm_ctx *);  /* ctx == NULL: error of the last failed tm_create on this thread */
 
 /* n_trials independent lattices (replicates and/or a-values) advanced by every launch.

@@ -45,6 +45,8 @@ def main():
     for r in src[2:]:
         if len(r) <= max(ie, so, wf or 0):
             continue
+        if r[ie] == "Instructions Executed":   # a second captured launch starts here: the summary is of the first
+            break
         toks = r[so].split()
         op = toks[1] if toks and toks[0].startswith("@") and len(toks) > 1 else (toks[0] if toks else "?")
         n = float(r[ie] or 0)

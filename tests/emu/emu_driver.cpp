@@ -43,7 +43,7 @@ void unpack(const Geom &g, const std::vector<double> &buf, double *host)
 extern "C" {
 
 static int g_split = 0;
-void emu_set_split(int s) { g_split = s; } // 1: Dornic kernel + kSrcPre RK kernel (the production pair)
+void emu_set_split(int s) { g_split = s; } // 1: Dornic kernel + kSrcPre marching kernel; 2: Dornic kernel + riet_rk4_kernel (the production pair)
 
 // fields: [n_trials][n_fields][L][L] in/out (whole lattice).  grid <= 0: as many CTAs as an n_sm-SM
 // device would get.  stats_out: [n_trials][8] = sum-derived mean[3], active[3], nonfinite, negative.
@@ -91,9 +91,22 @@ int emu_step(const tm_params *p, int n_trials, double *fields, int nsteps, int s
                 D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.mu_scale = A.c.mu_scale; D.in = A.in; D.pstar = pstar.data();
                 D.seed = seed; D.trial0 = trial0; D.step = step0 + s; D.rk = A.rk; D.logtab = A.logtab; D.row_lo = 0; D.row_hi = g.nrows; D.rows_per_cta = 7;
                 const size_t dsmem = riet_dornic_smem_bytes();
+                if (g_split == 2) { // the production pair uses the two-column sweep
+                    if (strict) emu_launch(riet_dornic2_kernel<true>, D, 3, kDornic2Threads, dsmem);
+                    else        emu_launch(riet_dornic2_kernel<false>, D, 3, kDornic2Threads, dsmem);
+                } else
                 if (strict) emu_launch(riet_dornic_kernel<true>, D, 3, kDornicThreads, dsmem);
                 else        emu_launch(riet_dornic_kernel<false>, D, 3, kDornicThreads, dsmem);
                 A.pstar = pstar.data();
+                if (g_split == 2) { // the production pair: Dornic sweep + the two-column RK4 kernel (tm_rk4.cuh)
+                    Rk4Args R{};
+                    R.g = g; R.c = A.c; R.in = A.in; R.pstar = pstar.data(); R.out = A.out; R.a_trial = A.a_trial; R.counters = counters;
+                    int grid2;
+                    rk4_launch_shape(g, n_sm, &R, &grid2);
+                    if (grid_override > 0) grid2 = grid_override;
+                    if (strict) emu_launch(riet_rk4_kernel<true>, R, grid2, kRkThreads, riet_rk4_smem_bytes());
+                    else        emu_launch(riet_rk4_kernel<false>, R, grid2, kRkThreads, riet_rk4_smem_bytes());
+                } else
                 if (strict) emu_launch(riet_step_kernel<false, true, kSrcPre, false>, A, grid, g.nthreads, smem);
                 else        emu_launch(riet_step_kernel<false, false, kSrcPre, false>, A, grid, g.nthreads, smem);
             } else {

@@ -33,26 +33,36 @@ inline int atomicMax(int *p, int v)
 }
 
 namespace tml {
-// mbarrier stand-in: the 64-bit word holds {pending bytes : 32 | completed phases : 32}.
-// Only one thread (tid 0) arms and copies, synchronously; waiters acquire-load.
-inline void mbar_init(uint64_t *b, int) { __atomic_store_n(b, 0ull, __ATOMIC_RELEASE); }
-inline void mbar_init_fence() {}
-inline void mbar_expect_tx(uint64_t *b, uint32_t bytes)
+// mbarrier stand-in.  The 64-bit word holds {completed phases : 24 | expected arrivals : 8 | pending arrivals : 8 |
+// pending transaction bytes : 24}; a phase completes when both pending counts reach zero (arrivals are then re-armed),
+// as the hardware object does.  Bulk copies are synchronous memcpys that complete their bytes at once; every update is
+// a compare-and-swap, so several issuing threads may share one barrier.
+inline uint64_t emu_mbar_pack(uint64_t phase, uint64_t count, uint64_t arr, uint64_t tx)
 {
-    uint64_t v = __atomic_load_n(b, __ATOMIC_ACQUIRE);
-    __atomic_store_n(b, (v & 0xFFFFFFFFull) | ((uint64_t)bytes << 32), __ATOMIC_RELEASE);
+    return (phase << 40) | (count << 32) | (arr << 24) | tx;
 }
+inline void mbar_init(uint64_t *b, int count) { __atomic_store_n(b, emu_mbar_pack(0, (uint64_t)count, (uint64_t)count, 0), __ATOMIC_RELEASE); }
+inline void mbar_init_fence() {}
+inline void emu_mbar_update(uint64_t *b, int d_arr, long long d_tx)
+{
+    uint64_t old = __atomic_load_n(b, __ATOMIC_ACQUIRE), neu;
+    do {
+        uint64_t phase = old >> 40, count = (old >> 32) & 0xFF, arr = (old >> 24) & 0xFF, tx = old & 0xFFFFFF;
+        arr -= (uint64_t)d_arr; tx = (uint64_t)((long long)tx + d_tx);
+        if (arr == 0 && tx == 0) { phase = (phase + 1) & 0xFFFFFF; arr = count; }
+        neu = emu_mbar_pack(phase, count, arr, tx);
+    } while (!__atomic_compare_exchange_n(b, &old, neu, true, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE));
+}
+inline void mbar_expect_tx(uint64_t *b, uint32_t bytes) { emu_mbar_update(b, 1, (long long)bytes); } // arrive.expect_tx
+inline void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes) { emu_mbar_update(b, 1, (long long)bytes); }
 inline void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
 {
     std::memcpy(dst, src, bytes);
-    uint64_t v = __atomic_load_n(b, __ATOMIC_ACQUIRE);
-    uint32_t pending = (uint32_t)(v >> 32) - bytes, phase = (uint32_t)v;
-    if (pending == 0) phase++;
-    __atomic_store_n(b, ((uint64_t)pending << 32) | phase, __ATOMIC_RELEASE);
+    emu_mbar_update(b, 0, -(long long)bytes);
 }
 inline bool mbar_try_wait(uint64_t *b, uint32_t parity)
 {
-    const uint32_t phase = (uint32_t)__atomic_load_n(b, __ATOMIC_ACQUIRE);
+    const uint32_t phase = (uint32_t)(__atomic_load_n(b, __ATOMIC_ACQUIRE) >> 40);
     if ((phase & 1u) != parity) return true;
     std::this_thread::yield();
     return false;

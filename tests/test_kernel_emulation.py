@@ -123,3 +123,52 @@ def test_replay_mode(emu):
     want = frame.copy()
     O.step(O.to_oparams(p), org, want.reshape(3, -1))
     assert np.array_equal(got[0], want)
+
+
+# ---- the production pair: riet_dornic_kernel + the two-column RK4 kernel (csrc/tm_rk4.cuh) -------------------------
+def emu_pair(emu, *args, **kw):
+    emu.emu_set_split(2)
+    try:
+        return emu_step(emu, *args, **kw)
+    finally:
+        emu.emu_set_split(0)
+
+
+@pytest.mark.parametrize("L,grid,nt", [(24, 1, 2), (33, 2, 1), (72, 3, 2), (251, 5, 1), (300, 7, 1), (520, 6, 1)])
+def test_rk4_pair_strict_any_geometry(emu, L, grid, nt):
+    """One strip (L <= 248), odd L (scalar commit path, odd pitch), two and three strips, several row segments per strip."""
+    p = tm.rietkerk_params(L)
+    frames = np.stack([O.synthetic_rietkerk_frame(L, seed=31 + t) for t in range(nt)])
+    nsteps = 2 if L < 300 else 1
+    got, stats, cnt = emu_pair(emu, p, frames, nsteps, strict=1, grid=grid, seed=909, trial0=4)
+    assert cnt == (0, 0)
+    for t in range(nt):
+        want = oracle_steps(p, frames[t], nsteps, 909, 4 + t)
+        assert np.array_equal(got[t], want), (L, t, np.abs(got[t] - want).max())
+        for f in range(3):
+            assert stats[t, 3 + f] == O.occupied(got[t, f])
+
+
+def test_rk4_pair_fast_equals_fused_fast_and_tolerance(emu):
+    """FAST arithmetic: the pair and the single fused kernel share rhs<> and the update expressions, so they agree bit for
+    bit; both are within 1e-12 of the oracle."""
+    L = 64
+    p = tm.rietkerk_params(L)
+    frame = O.synthetic_rietkerk_frame(L, seed=3)
+    a, _, cnt = emu_pair(emu, p, frame[None], 2, strict=0, grid=3, seed=5)
+    b, _, _ = emu_step(emu, p, frame[None], 2, strict=0, grid=2, seed=5)
+    assert cnt == (0, 0) and np.array_equal(a, b)
+    one, _, _ = emu_pair(emu, p, frame[None], 1, strict=0, grid=2, seed=5)
+    want = oracle_steps(p, frame, 1, 5, 0)
+    for f in range(3):
+        scale = np.maximum(np.abs(want[f]), 1e-12 * np.abs(want[f]).max())
+        assert np.max(np.abs(one[0, f] - want[f]) / scale) <= 1e-12
+
+
+def test_rk4_pair_independent_of_cta_count(emu):
+    L = 96
+    p = tm.rietkerk_params(L)
+    frame = O.synthetic_rietkerk_frame(L, seed=2)[None]
+    a, _, _ = emu_pair(emu, p, frame, 3, strict=0, grid=1, seed=9)
+    b, _, _ = emu_pair(emu, p, frame, 3, strict=0, grid=11, seed=9)
+    assert np.array_equal(a, b)

@@ -4,6 +4,7 @@
 #pragma once
 #include "../../include/tm_lattice.h"
 #include "tm_kernels.cuh"
+#include "tm_rk4.cuh"
 #include <cmath>
 
 namespace tml {
@@ -50,6 +51,7 @@ static inline RietConsts riet_consts(const tm_params &p)
     c.inv_lambda = 1.0 / c.dk.lambda;
     c.mu_scale = 2.0 * c.dk.diffc * c.dk.sigma2_1;
     c.dt2cg = c.dt2 * c.cgmax; c.dtcg = c.dt * c.cgmax; c.dt6cg = c.dt6 * c.cgmax;
+    c.aKap = c.alpha * c.K2 * (1.0 - c.W0);
     c.aK2W0 = c.alpha * c.K2W0; c.cP = -(c.d + 4 * c.Dp); c.cW = -(c.rW + 4 * c.Dw); c.cO = -4 * c.Do;
     return c;
 }
@@ -93,10 +95,26 @@ static inline void make_geom(const tm_params &p, int n_trials, int row0, int nro
     g->rows_alloc = g->wrap ? nrows : nrows + 2 * kHalo;
     g->n_trials = n_trials; g->n_fields = is_riet(p.model) ? 3 : 1;
     choose_strips(g->L, &g->ns, &g->TX, &g->nthreads);
-    const int need_cols = g->ns * g->TX + 2 * kHalo + 2;
+    int need_cols = g->ns * g->TX + 2 * kHalo + 2;
+    {   // the two-column RK4 kernel (tm_rk4.cuh) has its own strips: its last strip must end inside the padded row
+        int ns2, tx2;
+        choose_strips2(g->L, &ns2, &tx2);
+        if (ns2 * tx2 + 2 * kHalo > need_cols) need_cols = ns2 * tx2 + 2 * kHalo;
+    }
     g->Lp = ((need_cols > g->L + 2 * kHalo ? need_cols : g->L + 2 * kHalo) + 15) / 16 * 16;
     g->field_stride = (long long)g->rows_alloc * g->Lp;
     g->trial_stride = g->field_stride * g->n_fields;
+}
+
+// arguments and grid of the two-column RK4 kernel (n_cta_slots = SMs x resident CTAs per SM)
+static inline void rk4_launch_shape(const Geom &g, int n_cta_slots, Rk4Args *A, int *grid)
+{
+    choose_strips2(g.L, &A->ns2, &A->TX2);
+    const long long total = (long long)g.n_trials * A->ns2 * g.nrows;
+    long long gr = total / 16;                       // at least 16 rows per CTA: 8 of every segment's rows are recomputed halo
+    if (gr < 1) gr = 1;
+    if (gr > n_cta_slots) gr = n_cta_slots;
+    *grid = (int)gr;
 }
 
 // grid of the persistent Rietkerk kernel (n_cta_slots = SMs x resident CTAs per SM)

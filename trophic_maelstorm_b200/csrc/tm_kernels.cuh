@@ -51,6 +51,12 @@ constexpr int kHalo = 4;            // RK4 dependency cone: 3 stencil applicatio
 constexpr int kMaxThreads = TM_MAXTHREADS;  // CTA size cap (one thread per strip column)
 constexpr int kMinBlocks = TM_MINBLOCKS;    // resident CTAs per SM the register budget is sized for
 
+#ifndef TM_RHS_TWO_RCP
+#define TM_RHS_TWO_RCP 1
+#endif
+#ifndef TM_STEP_ISSUERS
+#define TM_STEP_ISSUERS 1
+#endif
 struct RietConsts {
     double dt, dt2, dt6;
     double cgmax, gmax, alpha, K1, K2, K2W0, rW;
@@ -63,6 +69,7 @@ struct RietConsts {
     double mu_scale;     // 2 (D0/dx^2) / sigma0^2 (FAST arithmetic only)
     double dt2cg, dtcg, dt6cg; // FAST, Dornic path: dt/2, dt, dt/6 times c*gmax (f_P = c gmax q is carried as q)
     double aK2W0, cP, cW, cO; // FAST: alpha*K2*W0, -(d+4Dp), -(rW+4Dw), -4Do
+    double aKap;              // FAST: alpha*K2*(1-W0)
     DornicConsts dk;
 };
 
@@ -238,10 +245,18 @@ TM_D F3 rhs(const RietConsts &c, double a, double P, double W, double O,
             + c.Dw * (Wu + Wd + Wl + Wr - 4 * W);
         f.o = a - c.alpha * (P + c.K2 * c.W0) / (P + c.K2) * O + c.Do * (Ou + Od + Ol + Or_ - 4 * O);
     } else {
+        // two MUFU-seeded reciprocals (one Newton step each): 10 FP64 operations for the two quotients where one shared
+        // reciprocal of (W + K1)(P + K2) takes 12; alpha (P + K2 W0)/(P + K2) = alpha - alpha K2 (1 - W0)/(P + K2)
+#if TM_RHS_TWO_RCP
+        const double r1 = rcp_lean1(W + c.K1), r2 = rcp_lean1(P + c.K2);
+        const double q = (W * P) * r1;                       // W P / (W + K1)
+        const double infil = O * fma(-c.aKap, r2, c.alpha);
+#else
         const double wk = W + c.K1, pk = P + c.K2;
         const double r = rcp_lean1(wk * pk);
         const double q = (W * P) * (pk * r);                 // W P / (W + K1)
         const double infil = fma(c.alpha, P, c.aK2W0) * (wk * r) * O;
+#endif
         if (DET) f.p = fma(c.Dp, (Pu + Pd) + (Pl + Pr), fma(c.cP, P, c.cgmax * q));     // cP = -(d + 4 Dp)
         else     f.p = q;      // f_P / (c gmax): the factor is folded into the step constants dt2cg, dtcg, dt6cg
         f.w = fma(c.Dw, (Wu + Wd) + (Wl + Wr), fma(c.cW, W, fma(-c.gmax, q, infil))); // cW = -(rW + 4 Dw)
@@ -467,8 +482,12 @@ riet_step_kernel(const StepArgs A)
     uint64_t *mbar = reinterpret_cast<uint64_t *>(pr + kRingDoubles);
     const double *logtab = A.logtab; // 2 KB, read through L1 (shared memory is fully booked by the rings at 4 CTAs/SM)
 
+    // TM_STEP_ISSUERS=3: a row's three bulk copies issued by three different threads (lane 0 of warps 0, 1, 2: rho*/P, W, O), each
+    // with its own arrive.expect_tx on the row's mbarrier (count 3).  Measured slower than the single issuer (RK4 kernel 0.257 vs
+    // 0.208 ms at L=4096, profiles/README.md round 2): the issue path lands on three warps' row bodies instead of one.  Default 1.
+    const int n_issuers = (TM_STEP_ISSUERS == 3 && nthreads >= 96) ? 3 : 1;
     if (tid == 0) {
-        for (int s = 0; s < kWoSlots; s++) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < kWoSlots; s++) mbar_init(&mbar[s], n_issuers);
         mbar_init_fence();
     }
     // rings start as zeros so that never-written slots are finite
@@ -523,14 +542,21 @@ riet_step_kernel(const StepArgs A)
         // Row streaming by thread 0: lattice-local row j (clamped to jhi: the dummy rows re-read it) goes into P-ring slot
         // `pslot` and W/O-ring slot `wslot` (= its mbarrier).  -4 <= j < nrows + 8, so the wrap needs no division.
         auto issue = [&](int j, int pslot, int wslot) {
-            if (tid != 0) return;
+            if ((tid & 31) != 0 || tid >= 32 * n_issuers) return;
             int r = (j < jhi) ? j : jhi;
             if (g.wrap) { if (r < 0) r += g.L; else if (r >= g.L) r -= g.L; } else r += kHalo;
             const long long off = (long long)r * g.Lp + x0;
-            mbar_expect_tx(&mbar[wslot], 3 * row_bytes);
-            bulk_g2s(pr + pslot * RW + 2, srcP + off, row_bytes, &mbar[wslot]);
-            bulk_g2s(wo + wslot * 2 * RW + 2, inW + off, row_bytes, &mbar[wslot]);
-            bulk_g2s(wo + wslot * 2 * RW + RW + 2, inO + off, row_bytes, &mbar[wslot]);
+            if (n_issuers == 1) {
+                mbar_expect_tx(&mbar[wslot], 3 * row_bytes);
+                bulk_g2s(pr + pslot * RW + 2, srcP + off, row_bytes, &mbar[wslot]);
+                bulk_g2s(wo + wslot * 2 * RW + 2, inW + off, row_bytes, &mbar[wslot]);
+                bulk_g2s(wo + wslot * 2 * RW + RW + 2, inO + off, row_bytes, &mbar[wslot]);
+            } else {
+                const int f = tid >> 5;   // 0: rho*/P, 1: W, 2: O
+                mbar_expect_tx(&mbar[wslot], row_bytes);
+                bulk_g2s(f == 0 ? pr + pslot * RW + 2 : wo + wslot * 2 * RW + (f - 1) * RW + 2,
+                         (f == 0 ? srcP : f == 1 ? inW : inO) + off, row_bytes, &mbar[wslot]);
+            }
         };
         issue(jlo, 3 * Q0 + 0, 3 * G0 + 0); issue(jlo + 1, 3 * Q0 + 1, 3 * G0 + 1); issue(jlo + 2, 3 * Q0 + 2, 3 * G0 + 2);
         if (nit > 3) issue(jlo + 3, 3 * Q1 + 0, 3 * G2 + 0);

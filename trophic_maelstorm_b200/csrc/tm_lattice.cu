@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -44,6 +45,9 @@ struct tm_ctx {
     double *pstar_dev = nullptr;   // rho* scratch field of the split Dornic / RK4 kernel pair
     unsigned long long *spread_dev = nullptr; // [n_trials][3] accumulators of tm_measure_spread
     bool fused = false;            // default: Dornic sweep + RK4 kernel pair; true: the single fused kernel
+    int rk4_kind = 1;              // RK4 kernel of the pair: 2 = riet_rk4_kernel (two columns per thread, tm_rk4.cuh), 1 = riet_step_kernel<kSrcPre>
+    int rk4_occ = 1;               // resident CTAs per SM of riet_rk4_kernel
+    int dornic_kind = 1;           // Dornic sweep: 2 = riet_dornic2_kernel (two columns per thread), 1 = riet_dornic_kernel
     double *halo_dev[2] = {nullptr, nullptr};
     uint64_t seed = 0, step = 0;
     uint32_t trial0 = 0;
@@ -78,6 +82,32 @@ int tm_device_count(void)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
+}
+
+int tm_device_mem(int device, uint64_t *free_bytes, uint64_t *total_bytes)
+{
+    if (!free_bytes || !total_bytes) return TM_E_ARG;
+    int cur = 0;
+    size_t f = 0, t = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) {
+        cudaGetLastError();
+        g_create_error = "tm_device_mem: no such CUDA device";
+        return TM_E_CUDA;
+    }
+    cudaSetDevice(cur);
+    *free_bytes = f; *total_bytes = t;
+    return TM_OK;
+}
+
+int tm_ctx_bytes(const tm_params *p, int n_trials, uint64_t *bytes)
+{
+    if (!p || !bytes || n_trials < 1 || p->L < 8) return TM_E_ARG;
+    Geom g{};
+    make_geom(*p, n_trials, 0, p->L, &g);
+    const uint64_t state = sizeof(double) * (uint64_t)g.n_trials * (uint64_t)g.trial_stride;
+    const uint64_t pstar = is_riet(p->model) ? sizeof(double) * (uint64_t)g.n_trials * (uint64_t)g.field_stride : 0;
+    *bytes = 2 * state + pstar + (uint64_t)n_trials * 512 + (1u << 20);   // two ping-pong sides, the rho* scratch field, per-trial records
+    return TM_OK;
 }
 
 const char *tm_last_error(const tm_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
@@ -193,6 +223,18 @@ int tm_create_slab(const tm_params *p, int n_trials, int device, int row0, int n
             cudaGetLastError(); occ = 1;
         }
         c->riet_occ = occ;
+        const int smem_r = (int)riet_rk4_smem_bytes();
+        if (cudaFuncSetAttribute(riet_rk4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r) != cudaSuccess ||
+            cudaFuncSetAttribute(riet_rk4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r) != cudaSuccess) {
+            cudaGetLastError(); return create_fail(c, TM_E_CUDA, "tm_create: cudaFuncSetAttribute(shared memory, riet_rk4_kernel) failed");
+        }
+        int occ2 = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, riet_rk4_kernel<false>, kRkThreads, smem_r) != cudaSuccess || occ2 < 1) {
+            cudaGetLastError(); occ2 = 1;
+        }
+        c->rk4_occ = occ2;
+        if (const char *e = getenv("TM_RK4_KIND")) c->rk4_kind = atoi(e) == 1 ? 1 : 2;   // kernel-variant experiments only
+        if (const char *e = getenv("TM_DORNIC_KIND")) c->dornic_kind = atoi(e) == 1 ? 1 : 2;
     }
     if (alloc_all(c) != TM_OK) return create_fail(c, TM_E_CUDA, "tm_create: device allocation failed");
     *out = c;
@@ -357,7 +399,8 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             D.seed = c->seed; D.trial0 = c->trial0; D.step = (unsigned int)c->step; D.rk = A.rk; D.logtab = c->logtab_dev;
             D.row_lo = g.wrap ? 0 : -(kHalo - 1); D.row_hi = g.wrap ? g.nrows : g.nrows + (kHalo - 1);
             // rows per CTA: enough (trial, column block, run) items for ~2 rounds over 4 resident CTAs per SM
-            const int ncb = (g.L + kDornicThreads - 1) / kDornicThreads, nrow_d = D.row_hi - D.row_lo;
+            const int dcols = c->dornic_kind == 2 ? kDornic2Cols : kDornicThreads;   // columns per CTA
+            const int ncb = (g.L + dcols - 1) / dcols, nrow_d = D.row_hi - D.row_lo;
             long long want_runs = ((long long)c->n_sm * 8 + (long long)g.n_trials * ncb - 1) / ((long long)g.n_trials * ncb);
             if (want_runs < 1) want_runs = 1;
             int rpc = (int)((nrow_d + want_runs - 1) / want_runs);
@@ -370,11 +413,24 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
             const bool timed = c->kernel_timing && c->kev_steps < kTimedSteps;
             cudaEvent_t *ev = timed ? &c->kev[3 * c->kev_steps] : nullptr;
             if (timed) TM_CUDA(c, cudaEventRecord(ev[0], c->stream));
-            if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
-            else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
+            if (c->dornic_kind == 2) {
+                if (c->strict) riet_dornic2_kernel<true><<<(unsigned)dgrid, kDornic2Threads, dsmem, c->stream>>>(D);
+                else           riet_dornic2_kernel<false><<<(unsigned)dgrid, kDornic2Threads, dsmem, c->stream>>>(D);
+            } else {
+                if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
+                else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
+            }
             TM_CUDA(c, cudaGetLastError());
             if (timed) TM_CUDA(c, cudaEventRecord(ev[1], c->stream));
             A.pstar = c->pstar_dev;
+            if (c->rk4_kind == 2) {
+                Rk4Args R{};
+                R.g = g; R.c = A.c; R.in = A.in; R.pstar = c->pstar_dev; R.out = A.out; R.a_trial = c->a_dev; R.counters = c->counters;
+                int grid2 = 1;
+                rk4_launch_shape(g, c->n_sm * c->rk4_occ, &R, &grid2);
+                if (c->strict) riet_rk4_kernel<true><<<grid2, kRkThreads, riet_rk4_smem_bytes(), c->stream>>>(R);
+                else           riet_rk4_kernel<false><<<grid2, kRkThreads, riet_rk4_smem_bytes(), c->stream>>>(R);
+            } else
             if (c->strict) TM_LAUNCH(false, true, kSrcPre, false); else TM_LAUNCH(false, false, kSrcPre, false);
             if (timed) { TM_CUDA(c, cudaEventRecord(ev[2], c->stream)); c->kev_steps++; }
             c->launches_this_call += 1;

@@ -11,8 +11,10 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <sys/stat.h>
 
 namespace tm_b200 {
@@ -23,7 +25,9 @@ Options &options()
 {
     static Options o = [] {
         Options x;
-        if (const char *e = getenv("TM_DEVICE")) x.device = atoi(e);
+        if (const char *e = getenv("TM_DEVICE")) { x.device = atoi(e); x.n_devices = 1; }   // one named GPU
+        if (const char *e = getenv("TM_DEVICES")) x.n_devices = atoi(e);                    // GPUs device .. device + n - 1 (0: all visible)
+        if (const char *e = getenv("TM_MAX_TRIALS_PER_CTX")) x.max_trials_per_ctx = atoi(e);
         if (const char *e = getenv("TM_SEED")) x.seed = strtoull(e, nullptr, 0);
         if (const char *e = getenv("TM_STRICT")) x.strict = atoi(e) != 0;
         if (const char *e = getenv("TM_DATA_ROOT")) x.data_root = e;
@@ -41,12 +45,58 @@ unsigned long long stream_seed(unsigned long long seed, double a)
     return z ^ (z >> 31);
 }
 
+// ---- the ensemble scheduler ---------------------------------------------------------------------------
+// The reference spreads the a-values of a sweep over OpenMP threads (`#pragma omp parallel for`, R/:4509-4542,
+// P/:2462-2488) and runs the replicates of an a-value one after the other.  Here the independent units -- a-values for the DP
+// sweeps, contiguous chunks of (a-value, replicate) trials for the Rietkerk sweep -- are dealt round-robin to the visible GPUs:
+// one host thread and one tm_ctx per GPU at a time, no device-to-device traffic, and all order-dependent host arithmetic
+// (replicate-order running mean/variance, row order of the CSVs) done after the join, so the outputs do not depend on the
+// number of GPUs.
+thread_local int tl_device = -1;      // the GPU of the calling worker thread (-1: options().device)
+
+int current_device() { return tl_device >= 0 ? tl_device : options().device; }
+
+std::vector<int> device_list()
+{
+    const Options &o = options();
+    const int visible = tm_device_count();
+    int n = o.n_devices > 0 ? o.n_devices : visible - o.device;
+    if (n < 1) n = 1;
+    std::vector<int> d;
+    for (int i = 0; i < n && (visible == 0 || o.device + i < visible); i++) d.push_back(o.device + i);
+    if (d.empty()) d.push_back(o.device);
+    return d;
+}
+
+void for_each_on_devices(int n_items, const std::function<void(int)> &fn)
+{
+    const std::vector<int> devs = device_list();
+    const int nd = (int)std::min<size_t>(devs.size(), (size_t)std::max(n_items, 1));
+    if (nd <= 1 || tl_device >= 0) {          // one GPU, or already inside a worker: run in place
+        const int saved = tl_device;
+        if (tl_device < 0) tl_device = devs[0];
+        try { for (int i = 0; i < n_items; i++) fn(i); } catch (...) { tl_device = saved; throw; }
+        tl_device = saved;
+        return;
+    }
+    std::exception_ptr err; std::mutex m;
+    std::vector<std::thread> th;
+    for (int d = 0; d < nd; d++)
+        th.emplace_back([&, d] {
+            tl_device = devs[d];
+            try { for (int i = d; i < n_items; i += nd) fn(i); }
+            catch (...) { std::lock_guard<std::mutex> g(m); if (!err) err = std::current_exception(); }
+        });
+    for (auto &t : th) t.join();
+    if (err) std::rethrow_exception(err);
+}
+
 namespace {
 struct Ctx { // RAII over tm_ctx; errors become exceptions like the reference's exit() paths
     tm_ctx *c = nullptr;
     Ctx(const tm_params &p, int n_trials)
     {
-        if (tm_create(&p, n_trials, options().device, &c) != TM_OK)
+        if (tm_create(&p, n_trials, current_device(), &c) != TM_OK)
             throw std::runtime_error(std::string("tm_create: ") + tm_last_error(nullptr));
         tm_set_strict(c, options().strict ? 1 : 0);
     }
@@ -243,11 +293,11 @@ void critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, d
     vector<double> a_space = linspace(a_start, a_end, div);
     vector<double> t_measure = logarithm10_time_bins(t_max, dt);
     vector<vector<double>> vec;
-    for (size_t i = 0; i < a_space.size(); i++) { // the reference's `omp for` over a-values; here one batch of r trials each
-        vector<vector<double>> rows;
-        percolationDornic_2D(rows, t_measure, Rho_0, t_max, a_space[i], b, D, sigma, dt, dx, r, g);
-        vec.insert(vec.end(), rows.begin(), rows.end());
-    }
+    vector<vector<vector<double>>> per_a(a_space.size());
+    for_each_on_devices((int)a_space.size(), [&](int i) { // the reference's `omp for` over a-values; here one batch of r trials each, one GPU per a-value at a time
+        percolationDornic_2D(per_a[i], t_measure, Rho_0, t_max, a_space[i], b, D, sigma, dt, dx, r, g);
+    });
+    for (const auto &rows : per_a) vec.insert(vec.end(), rows.begin(), rows.end());
     std::stringstream L, tm, d3, p1, p2, rini, Dm, Sm;
     L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a_start; p2 << std::setprecision(4) << a_end;
     rini << r; Dm << std::setprecision(3) << D; Sm << std::setprecision(3) << sigma;
@@ -263,11 +313,11 @@ void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, doubl
     vector<double> a_space = linspace(a_start, a_end, div);
     vector<double> t_measure = logarithm10_time_bins(t_max, dt);
     vector<vector<double>> vec;
-    for (size_t i = 0; i < a_space.size(); i++) {
-        vector<vector<double>> rows;
-        expanded_percolationDornic_2D(rows, t_measure, Rho_0, t_max, a_space[i], b, c, D, sigma, dt, dx, r, g);
-        vec.insert(vec.end(), rows.begin(), rows.end());
-    }
+    vector<vector<vector<double>>> per_a(a_space.size());
+    for_each_on_devices((int)a_space.size(), [&](int i) {
+        expanded_percolationDornic_2D(per_a[i], t_measure, Rho_0, t_max, a_space[i], b, c, D, sigma, dt, dx, r, g);
+    });
+    for (const auto &rows : per_a) vec.insert(vec.end(), rows.begin(), rows.end());
     std::stringstream L, coco, tm, d3, p1, p2, rini, Sm, dix;
     L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a_start; p2 << std::setprecision(4) << a_end;
     rini << r; Sm << std::setprecision(3) << sigma; coco << std::setprecision(4) << c; dix << std::setprecision(2) << dx;
@@ -481,23 +531,12 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
     p.rc = c; p.gmax = gmax; p.alpha = alpha; p.rW = rW; p.W0 = W0; p.d = M[0]; p.K1 = K[1]; p.K2 = K[2];
     p.D0 = D[0]; p.D1 = D[1]; p.D2 = D[2]; p.sigma0 = sigma[0];
     p.clamp_eps = 1.0e-12; p.clamp_lo = -1.0e-80; // R/:3402, :4176
-    Ctx ctx(p, nt);
     const size_t n = (size_t)g * g;
-    vector<double> host(3 * n * nt);
-    for (int ia = 0; ia < na; ia++)
-        for (int j = 0; j < r; j++) {
-            const int t = ia * r + j;                       // trial id = a-index * r + replicate
-            ctx.ck(tm_set_trial_a(ctx.c, t, a_values[ia]), "tm_set_trial_a");
-            init_frame(&host[3 * n * t], g, t, a_values[ia], a_c, dP, clow);
-        }
-    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
-    ctx.ck(tm_seed(ctx.c, options().seed, 0), "tm_seed");   // trial id = a-index * r + replicate: every (a, replicate) has its own stream
 
     const int tot_iter = (int)t_meas.size();               // R/:3438
     const int W_ = 4 * SpB + 3;                            // Sp4_1: {t, <W>, <O>, mean, var, surv, active}
     vector<vector<double>> RhoM(nt, vector<double>(2 * Sp * (size_t)tot_iter, 0.0)); // [index][2s] = N, [2s+1] = mean
     const double t_end = t_meas.back();
-    vector<tm_stats> st(nt);
     const std::string fdir = frame_folder.empty() ? options().data_root + "/Data/Rietkerk/Frames/Stochastic/1Sp/" + prefix + "_" : frame_folder;
     const std::string pdir = prelim_folder.empty() ? options().data_root + "/Data/Rietkerk/Prelims/Stochastic/1Sp/" + prefix + "_" : prelim_folder;
     std::stringstream a1, a2, dimitri; a1 << a_st; a2 << a_end; dimitri << dP;
@@ -526,6 +565,20 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
         save_prelimframe(tab, dir, pattern, a, a_st_, a_end_, t_now, dt_, dx_, dP_, j, g_, prelimheader, false, false);
     };
 
+    // One chunk = the contiguous global trial ids [c0, c1) (trial id = a-index * r + replicate) in one device context on the
+    // calling worker's GPU.  The Philox key is (seed, global trial id, step, cell) and the initial frame is drawn from the
+    // global trial id, so a trial's trajectory does not depend on the chunking or on the GPU it lands on.
+    auto run_chunk = [&](int c0, int c1) {
+    const int nc = c1 - c0;
+    Ctx ctx(p, nc);
+    vector<double> host(3 * n * nc);
+    for (int tr = c0; tr < c1; tr++) {
+        ctx.ck(tm_set_trial_a(ctx.c, tr - c0, a_values[tr / r]), "tm_set_trial_a");
+        init_frame(&host[3 * n * (tr - c0)], g, tr, a_values[tr / r], a_c, dP, clow);
+    }
+    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
+    ctx.ck(tm_seed(ctx.c, options().seed, (uint32_t)c0), "tm_seed");
+    vector<tm_stats> st(nc);
     double t = 0; int index = 0; size_t frame_index = 0; int pending = 0;
     while (t < t_end + dt) { // R/:3648
         const bool meas = index < tot_iter && (t == 0 || (t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0)); // R/:3659
@@ -534,18 +587,18 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
         if ((meas || snap) && pending) { ctx.ck(tm_step(ctx.c, pending), "tm_step"); pending = 0; }
         if (meas) {
             ctx.ck(tm_measure(ctx.c, st.data()), "tm_measure");
-            for (int j = 0; j < nt; j++) {
-                if (st[j].nonfinite) { std::cerr << "RHO NAAN PARATHA in trial " << j << " at t=" << t << "\n"; exit(3); } // R/:4206-4276
+            for (int j = c0; j < c1; j++) {
                 if (broke[j]) continue;   // this replicate left the time loop at an earlier checkpoint: its later rows stay 0 (R/:3714)
+                if (st[j - c0].nonfinite) { std::cerr << "RHO NAAN PARATHA in trial " << j << " at t=" << t << "\n"; exit(3); } // R/:4206-4276
                 for (int s = 0; s < Sp; s++) {
-                    RhoM[j][2 * Sp * index + 2 * s] = (double)st[j].active[s];
-                    RhoM[j][2 * Sp * index + 2 * s + 1] = st[j].mean[s];
+                    RhoM[j][2 * Sp * index + 2 * s] = (double)st[j - c0].active[s];
+                    RhoM[j][2 * Sp * index + 2 * s + 1] = st[j - c0].mean[s];
                 }
             }
             // per-replicate time-series checkpoints, R/:3710-3716 -> save_prelimfileswrapper R/:3029-3140
             if ((index == int(tot_iter * 0.6) || index == int(tot_iter * 0.85) || index == int(tot_iter * 0.9)
                                   || index == int(tot_iter * 0.95) || index == int(tot_iter - 1))) {
-                for (int tr = 0; tr < nt; tr++) {
+                for (int tr = c0; tr < c1; tr++) {
                     if (broke[tr]) continue;
                     const double a = a_values[tr / r]; const int j = tr % r;
                     const bool dead = RhoM[tr][2 * Sp * index + 0] == 0.0;       // no vegetation left: R/:3087
@@ -567,10 +620,11 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
             const size_t ftot = frame_tmeas.size();
             if ((frame_index + 10 >= ftot) || (t >= 50000 && t <= 150000) || (t >= 20 && t <= 15000) || t == 0) { // R/:3739
                 ctx.ck(tm_download(ctx.c, host.data()), "tm_download");
-                for (int tr = 0; tr < nt; tr++) {
+                for (int tr = c0; tr < c1; tr++) {
+                    if (broke[tr]) continue;   // the reference left this replicate's time loop (R/:3714): no further frames of it
                     const double a = a_values[tr / r]; const int j = tr % r;
                     D2Vec_Double fr(Sp, vector<double>(n));
-                    for (int s = 0; s < Sp; s++) memcpy(fr[s].data(), &host[(3 * (size_t)tr + s) * n], n * sizeof(double));
+                    for (int s = 0; s < Sp; s++) memcpy(fr[s].data(), &host[(3 * (size_t)(tr - c0) + s) * n], n * sizeof(double));
                     std::stringstream L, tm, d3, p1, Dm1, dix;
                     L << g; tm << t; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a; dix << std::setprecision(2) << dx;
                     Dm1 << std::setprecision(3) << D[1];
@@ -584,6 +638,27 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
         pending += 1;
         t += dt;
     }
+    };  // run_chunk
+
+    // chunks: an equal share per GPU, capped by what fits in the free memory of a GPU (2 ping-pong states + the rho* scratch
+    // field per trial) and by options().max_trials_per_ctx; dealt round-robin, a GPU works through its chunks in order
+    {
+        const int ndev = (int)device_list().size();
+        long long cap = (nt + ndev - 1) / ndev;
+        uint64_t need = 0, free_b = 0, total_b = 0;
+        if (tm_ctx_bytes(&p, 1, &need) == TM_OK && tm_device_mem(current_device(), &free_b, &total_b) == TM_OK && need > 0) {
+            const long long fit = (long long)((free_b * 0.9) / (double)need);
+            if (fit >= 1 && fit < cap) cap = fit;
+        }
+        if (options().max_trials_per_ctx > 0 && options().max_trials_per_ctx < cap) cap = options().max_trials_per_ctx;
+        if (cap < 1) cap = 1;
+        const int n_chunks = (int)((nt + cap - 1) / cap);
+        for_each_on_devices(n_chunks, [&](int k) {
+            const long long c0 = (long long)nt * k / n_chunks, c1 = (long long)nt * (k + 1) / n_chunks;
+            run_chunk((int)c0, (int)c1);
+        });
+    }
+    const double t = t_end;   // the reference's loop variable after the time loop (file names below)
     // per a-value: replicate-order accumulation (R/:4294-4322, var_mean_incremental_surv_runs R/:1293-1343)
     Rho_per_a.assign(na, D2Vec_Double());
     for (int ia = 0; ia < na; ia++) {
@@ -781,7 +856,7 @@ void percNoDiff_2D(vector<vector<double>> &Rho, vector<double> &t_stop, double R
     const int j = 0;
     auto flush = [&]() {
         if (!pending) return;
-        const int rc = tm_dp_noise_off_host(options().device, g, a, b, D, dt, dx, Rho_dt.data(), pending, nullptr);
+        const int rc = tm_dp_noise_off_host(current_device(), g, a, b, D, dt, dx, Rho_dt.data(), pending, nullptr);
         if (rc != 0) throw std::runtime_error(std::string("tm_dp_noise_off_host: ") + tm_last_error(nullptr));
         pending = 0;
     };

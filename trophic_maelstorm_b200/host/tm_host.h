@@ -29,6 +29,8 @@ typedef std::vector<std::vector<double>> D2Vec_Double;
 struct Options {
     int device = 0;
     unsigned long long seed = 0x5EEDC0DEull; // the reference seeds from std::random_device (P/:973); here it is explicit
+    int n_devices = 0;                        // GPUs device .. device + n_devices - 1 share a sweep (0: every visible GPU from `device` on)
+    int max_trials_per_ctx = 0;               // cap on the trials one device context holds (0: from the free device memory)
     bool strict = false;                      // reference operation order in the RK4 stages
     bool quiet = true;                        // the reference's progress chatter on stdout
     std::string data_root = "..";             // outputs go to <data_root>/Data/... like the reference's "../Data/..."
@@ -41,6 +43,13 @@ Options &options(); // process-wide; env TM_DEVICE, TM_SEED, TM_STRICT, TM_DATA_
 // at every a-value.  The mix depends on (seed, a) only -- not on call order or on which GPU runs the a-value -- so a
 // sweep is reproducible and identical on 1 or 8 GPUs.  Runs meant to be independent need different TM_SEED values.
 unsigned long long stream_seed(unsigned long long seed, double a);
+
+// The ensemble scheduler (the reference's `#pragma omp parallel for` over a-values, R/:4509-4542, P/:2462-2488): runs
+// fn(0) .. fn(n_items - 1), item i on GPU device_list()[i mod #GPUs], one host thread per GPU, items of a GPU in
+// increasing order.  Inside fn every tm_create of this layer binds current_device().
+std::vector<int> device_list();
+int current_device();
+void for_each_on_devices(int n_items, const std::function<void(int)> &fn);
 
 // ---- bookkeeping (host) --------------------------------------------------------------------
 std::vector<double> linspace(double start, double end, int num);                 // P/:254

@@ -107,7 +107,7 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     pc.Dw = D[2] / (dx * dx); pc.Do = D[3] / (dx * dx); pc.A01 = A[0][1]; pc.H01 = H[0][1]; pc.E1 = E[1];               // R/:3463-3480
 
     Ctx ctx;
-    if (tm_cons_create(g, options().device, &ctx.c) != 0) throw std::runtime_error(std::string("tm_cons_create: ") + tm_cons_last_error(nullptr));
+    if (tm_cons_create(g, current_device(), &ctx.c) != 0) throw std::runtime_error(std::string("tm_cons_create: ") + tm_cons_last_error(nullptr));
     ctx.ck(tm_cons_step2_setup(ctx.c, &veg, &pg, &pc, central.data(), (int)nb.size(), fr_graz), "tm_cons_step2_setup");
 
     D2Vec_Double rho_rep_avg_var(tot_iter, vector<double>(W_, 0.0));

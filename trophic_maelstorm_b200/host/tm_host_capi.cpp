@@ -13,8 +13,15 @@ extern "C" {
 
 void tmh_set_options(int device, unsigned long long seed, int strict, const char *data_root)
 {
-    options().device = device; options().seed = seed; options().strict = strict != 0;
+    options().device = device; options().n_devices = 1; options().seed = seed; options().strict = strict != 0;
     if (data_root) options().data_root = data_root;
+}
+
+// the GPUs a sweep is spread over: `first` .. `first + count - 1` (count = 0: every visible GPU from `first` on), and the
+// cap on trials per device context (0: from the free device memory)
+void tmh_set_devices(int first, int count, int max_trials_per_ctx)
+{
+    options().device = first; options().n_devices = count; options().max_trials_per_ctx = max_trials_per_ctx;
 }
 
 unsigned long long tmh_stream_seed(unsigned long long seed, double a) { return stream_seed(seed, a); }

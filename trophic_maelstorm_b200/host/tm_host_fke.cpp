@@ -94,7 +94,7 @@ struct ThreadCtx {
     {
         if (ctx && (L != L_ || n != n_)) { tm_fke_destroy(ctx); ctx = nullptr; }
         if (!ctx) {
-            if (tm_fke_create(L_, n_, options().device, &ctx) != 0)
+            if (tm_fke_create(L_, n_, current_device(), &ctx) != 0)
                 throw std::runtime_error(std::string("tm_fke_create: ") + tm_fke_last_error(nullptr));
             L = L_; n = n_;
         }

@@ -77,6 +77,8 @@ def lib():
     sig = {
         "tm_abi_version": (i, []),
         "tm_device_count": (i, []),
+        "tm_device_mem": (i, [i, C.POINTER(u64), C.POINTER(u64)]),
+        "tm_ctx_bytes": (i, [C.POINTER(Params), i, C.POINTER(u64)]),
         "tm_last_error": (C.c_char_p, [vp]),
         "tm_create": (i, [C.POINTER(Params), i, i, C.POINTER(vp)]),
         "tm_create_slab": (i, [C.POINTER(Params), i, i, i, i, C.POINTER(vp)]),
@@ -116,7 +118,7 @@ def lib():
 
 
 ABI_SYMBOLS = [
-    "tm_abi_version", "tm_device_count", "tm_last_error", "tm_create", "tm_create_slab", "tm_destroy",
+    "tm_abi_version", "tm_device_count", "tm_device_mem", "tm_ctx_bytes", "tm_last_error", "tm_create", "tm_create_slab", "tm_destroy",
     "tm_set_trial_a", "tm_set_strict", "tm_set_fused", "tm_upload", "tm_download", "tm_n_fields", "tm_seed",
     "tm_set_step_counter", "tm_step_counter", "tm_step", "tm_step_replay", "tm_dornic_only",
     "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream", "tm_measure", "tm_measure_spread",
