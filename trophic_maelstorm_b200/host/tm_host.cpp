@@ -28,6 +28,10 @@ Options &options()
         if (const char *e = getenv("TM_DEVICE")) { x.device = atoi(e); x.n_devices = 1; }   // one named GPU
         if (const char *e = getenv("TM_DEVICES")) x.n_devices = atoi(e);                    // GPUs device .. device + n - 1 (0: all visible)
         if (const char *e = getenv("TM_MAX_TRIALS_PER_CTX")) x.max_trials_per_ctx = atoi(e);
+        if (const char *e = getenv("TM_DEVICE_LIST")) {                                        // explicit worker list, e.g. 0,1,2,3
+            std::stringstream ss(e); std::string tok;
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) x.device_ids.push_back(atoi(tok.c_str()));
+        }
         if (const char *e = getenv("TM_SEED")) x.seed = strtoull(e, nullptr, 0);
         if (const char *e = getenv("TM_STRICT")) x.strict = atoi(e) != 0;
         if (const char *e = getenv("TM_DATA_ROOT")) x.data_root = e;
@@ -59,6 +63,7 @@ int current_device() { return tl_device >= 0 ? tl_device : options().device; }
 std::vector<int> device_list()
 {
     const Options &o = options();
+    if (!o.device_ids.empty()) return o.device_ids;
     const int visible = tm_device_count();
     int n = o.n_devices > 0 ? o.n_devices : visible - o.device;
     if (n < 1) n = 1;
@@ -514,6 +519,24 @@ std::string prefix = "DiC-NREF-LI";                    // R/ header :97
 std::string prelim_folder;                            // default "<data_root>/Data/Rietkerk/Prelims/Stochastic/1Sp/<prefix>_"
 std::string stat_prefix;                              // default "<data_root>/Data/Rietkerk/Stochastic/1Sp/1stCC_Rietkerk_<prefix>_P_c_G_"
 bool write_prelims = true;
+
+void set_Prefix(const std::string &user_prefix, double mG, double mP) // R/:113-135
+{
+    prefix = user_prefix;
+    mG = (mG == int(mG)) ? int(mG) : std::round(mG * 100) / 100;
+    mP = (mP == int(mP)) ? int(mP) : std::round(mP * 100) / 100;
+    std::ostringstream g_, p_;
+    g_ << std::defaultfloat << mG; p_ << std::defaultfloat << mP;
+    std::string sp = std::to_string(SpB) + "Sp";
+    if (mG > 0.0 && mP > 0.0) sp += "_mG_" + g_.str() + "_mP_" + p_.str();
+    else if (mG > 0.0 && mP == 0.0) sp += "_mG_" + g_.str();
+    const std::string root = options().data_root + "/Data/Rietkerk/";
+    frame_folder = root + "Frames/Stochastic/" + sp + "/" + prefix + "_";
+    prelim_folder = root + "Prelims/Stochastic/" + sp + "/" + prefix + "_";
+    stat_prefix = root + "Stochastic/1stOrderCC_Rietkerk_" + prefix + "_P_c_G_";
+}
+
+void recursive_dir_create(const std::string &path) { mkdirs(path); }
 const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"
                                  " # Active Sites P(x; t), \n"; // rietkerk_bjork_constants_1Sp.h:8-9
 
@@ -522,7 +545,7 @@ namespace {
 // and replicates serially, R/:4519, :3501); rows come back per a-value in the reference's layout.
 void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values, vector<double> &t_meas, double c, double gmax,
                 double alpha, double rW, double W0, double (&D)[Sp], double (&K)[3], double sigma[], double a_st, double a_end,
-                double a_c, double (&M)[SpB], double clow[], double dt, double dx, double dP, int r, int g)
+                double a_c, double (&M)[SpB], double clow[], double dt, double dx, double dP, int r, int g, double Gstar, double Vstar)
 {
     if (t_meas.empty() || r < 1 || a_values.empty()) throw std::invalid_argument("rietkerk_Dornic_2D_MultiSp: empty t_meas, no a-value or r < 1");
     const int na = (int)a_values.size(), nt = na * r;
@@ -540,7 +563,11 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
     const std::string fdir = frame_folder.empty() ? options().data_root + "/Data/Rietkerk/Frames/Stochastic/1Sp/" + prefix + "_" : frame_folder;
     const std::string pdir = prelim_folder.empty() ? options().data_root + "/Data/Rietkerk/Prelims/Stochastic/1Sp/" + prefix + "_" : prelim_folder;
     std::stringstream a1, a2, dimitri; a1 << a_st; a2 << a_end; dimitri << dP;
-    const std::string subdir = a1.str() + "-" + a2.str() + "_dP_" + dimitri.str();
+    std::string subdir = a1.str() + "-" + a2.str() + "_dP_" + dimitri.str();
+    {   // R/:2907-2912, :4224, :4269, :4337: the equilibrium tag of the run folders
+        std::stringstream geq, veq; geq << std::setprecision(5) << Gstar; veq << std::setprecision(5) << Vstar;
+        if (Gstar != -1) subdir += "_Geq_" + geq.str(); else if (Vstar != -1) subdir += "_Veq_" + veq.str();
+    }
 
     vector<char> broke(nt, 0);
     // save_prelimfileswrapper's table of ONE replicate, R/:3040-3079: var_mean_incremental_surv_runs(temp, Rho_M, index + 1, 0)
@@ -876,10 +903,10 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
                                 double alpha, double rW, double W0, double (&D)[Sp], double (&)[SpB], double (&K)[3],
                                 double sigma[], double a_st, double a_end, double a_c, double (&)[SpB][SpB], double (&)[SpB][SpB],
                                 double (&)[SpB], double (&M)[SpB], double[], int (&)[SpB], double clow[], double dt, double dx,
-                                double dP, int r, int g, double, double)
+                                double dP, int r, int g, double Gstar, double Vstar)
 {
     vector<D2Vec_Double> per_a;
-    riet_batch(per_a, vector<double>{a}, t_meas, c, gmax, alpha, rW, W0, D, K, sigma, a_st, a_end, a_c, M, clow, dt, dx, dP, r, g);
+    riet_batch(per_a, vector<double>{a}, t_meas, c, gmax, alpha, rW, W0, D, K, sigma, a_st, a_end, a_c, M, clow, dt, dx, dP, r, g, Gstar, Vstar);
     Rho.insert(Rho.end(), per_a[0].begin(), per_a[0].end());
 }
 
@@ -910,7 +937,7 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
     t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
 
     vector<D2Vec_Double> per_a;
-    riet_batch(per_a, a_space, t_measure, c, gmax, alpha, rW, W0, D, K, sigma, a_start, a_end, a_c, M, clo, dt, dx, dP, r, g);
+    riet_batch(per_a, a_space, t_measure, c, gmax, alpha, rW, W0, D, K, sigma, a_start, a_end, a_c, M, clo, dt, dx, dP, r, g, Gstar, Vstar);
 
     std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;
     L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r;

@@ -31,6 +31,8 @@ struct Options {
     unsigned long long seed = 0x5EEDC0DEull; // the reference seeds from std::random_device (P/:973); here it is explicit
     int n_devices = 0;                        // GPUs device .. device + n_devices - 1 share a sweep (0: every visible GPU from `device` on)
     int max_trials_per_ctx = 0;               // cap on the trials one device context holds (0: from the free device memory)
+    std::vector<int> device_ids;              // explicit worker list (overrides device / n_devices); an id may repeat: that GPU then
+                                              // serves two workers at once (env TM_DEVICE_LIST=0,1,1)
     bool strict = false;                      // reference operation order in the RK4 stages
     bool quiet = true;                        // the reference's progress chatter on stdout
     std::string data_root = "..";             // outputs go to <data_root>/Data/... like the reference's "../Data/..."
@@ -129,6 +131,9 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
 int read_frame_csv(const std::string &filename, int g, double *frame);
 void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern);
 void use_default_init_frame();   // back to the MFT speckle rule
+// set_Prefix (R/:113-135): prefix and the three output locations derived from it, "<data_root>/Data/Rietkerk/..." for the reference's "../Data/Rietkerk/..."
+void set_Prefix(const std::string &user_prefix, double mG = 0.0, double mP = 0.0);
+void recursive_dir_create(const std::string &path);    // R/: mkdir -p
 extern std::string prefix, prelim_folder, stat_prefix; // R/ header :97-108; empty folders = "<data_root>/Data/Rietkerk/..."
 extern bool write_prelims;                             // PRELIM_AGGRAND_*.csv per replicate (R/:4327-4349) and the TimeSeries/PRELIM_TSERIES_* checkpoints (R/:3029)
 extern const std::string prelimheader;                 // rietkerk_bjork_constants_1Sp.h:8-9

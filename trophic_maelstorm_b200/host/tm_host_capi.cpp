@@ -13,7 +13,7 @@ extern "C" {
 
 void tmh_set_options(int device, unsigned long long seed, int strict, const char *data_root)
 {
-    options().device = device; options().n_devices = 1; options().seed = seed; options().strict = strict != 0;
+    options().device = device; options().n_devices = 1; options().device_ids.clear(); options().seed = seed; options().strict = strict != 0;
     if (data_root) options().data_root = data_root;
 }
 
@@ -22,6 +22,13 @@ void tmh_set_options(int device, unsigned long long seed, int strict, const char
 void tmh_set_devices(int first, int count, int max_trials_per_ctx)
 {
     options().device = first; options().n_devices = count; options().max_trials_per_ctx = max_trials_per_ctx;
+    options().device_ids.clear();
+}
+
+// explicit worker list (an id may repeat: two workers on one GPU); n = 0 clears it
+void tmh_set_device_list(const int *ids, int n)
+{
+    options().device_ids.assign(ids, ids + (n > 0 ? n : 0));
 }
 
 unsigned long long tmh_stream_seed(unsigned long long seed, double a) { return stream_seed(seed, a); }
