@@ -412,10 +412,161 @@ def run_ours(a):
         out["cpu_baseline"] = cpu_reference(a.ref_L or L, a.ref_steps, host_cores())
         out["cpu_baseline_small_lattice"] = cpu_reference(512, 12, host_cores())
     lat.close()
+    if not a.no_slab:
+        # BASELINE config 5 beside the headline, so that every N of a scaling run carries it: ONE L=16384 lattice over the N GPUs
+        # of this run (strong scaling; N=1 is the undivided lattice, the base of the speed-up)
+        torch.cuda.empty_cache()
+        # the headline above is already measured: if this extra section does not finish in time (a stuck transport), the line is
+        # printed without it and every rank leaves
+        def give_up():
+            if rank == 0:
+                out["slab_L16384"] = {"error": "the row-slab section did not finish within %d s; skipped" % a.slab_budget_s}
+                print(json.dumps(out), flush=True)
+            os._exit(0)
+        dog = threading.Timer(a.slab_budget_s, give_up)
+        dog.daemon = True
+        dog.start()
+        try:
+            sl = slab_measure(a, 16384, 10, 3, rank, world, local, dist)
+            if rank == 0:
+                out["slab_L16384"] = {k: sl[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config", "check", "comm", "e2e", "finite")}
+        except Exception as e:   # the headline must still be printed
+            if rank == 0:
+                out["slab_L16384"] = {"error": "%s: %s" % (type(e).__name__, e)}
+        dog.cancel()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        # the line is out; a rank that failed above must not keep the others in the closing barrier for long
+        bye = threading.Timer(60, lambda: os._exit(0))
+        bye.daemon = True
+        bye.start()
+        dist.barrier()
+        dist.destroy_process_group()
+        bye.cancel()
+
+
+def slab_measure(a, L, K, W, rank, world, local, dist):
+    """BASELINE config 5: ONE Rietkerk lattice of side L cut into `world` row slabs (include/tm_slab.h), strong scaling.
+    Returns the dict rank 0 prints (None on the other ranks).  world == 1 is the undivided lattice on one GPU: the base of the
+    speed-up.  Three schedules are timed over the same K steps: overlapped (the product), serial (exchange, then the whole slab:
+    the round-1 schedule) and the overlapped schedule with the transfers left out (what the compute alone costs)."""
+    import numpy as np
+    import torch
+    import oracle_lib as O
+    import trophic_maelstorm_b200 as tm
+    from trophic_maelstorm_b200 import slab as S
+
+    p = tm.rietkerk_params(L)
+    ring = S.SlabRing(p, 1, local, dist if world > 1 else None)
+    # the frame: the L=1024 MFT speckle tile repeated periodically (a valid periodic L x L frame; every rank builds only its rows)
+    T = 1024 if L % 1024 == 0 else L
+    tile = O.synthetic_rietkerk_frame(T, seed=4242, fringe=False)
+    rows = (np.arange(ring.row0, ring.row0 + ring.nrows) % T)
+    host = torch.empty((1, 3, ring.nrows, L), dtype=torch.float64, pin_memory=True)
+    host.numpy()[0] = np.tile(tile[:, rows, :], (1, 1, L // T))
+    ring.seed(20261018)
+    if world > 1 and a.slab_reserve_sms > 0:
+        ring.reserve_sms(a.slab_reserve_sms)
+    if world > 1:
+        ring.set_transport(S.PEER_COPY if a.slab_transport == "peer" else S.NCCL)
+
+    def barrier():
+        ring.sync()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(mode, steps):
+        tm.lib().tm_set_step_counter(ring._ctx(), 0)
+        ring.upload(host.numpy())
+        ring.run(W, mode)
+        barrier()
+        ring.run(steps, mode)
+        ring.sync()
+        ms = maxr(ring.last_ms())
+        barrier()
+        return ms / steps
+
+    ms_overlap = timed(S.OVERLAP, K)
+    st = ring.measure()[0]
+    active, mean_p = int(st.active[0]), float(st.mean[0]) * ring.nrows / L
+    finite = st.nonfinite == 0
+    if world > 1:
+        t = torch.tensor([active, mean_p, 0.0 if finite else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        active, mean_p, finite = int(t[0].item()), float(t[1].item()), t[2].item() == 0.0
+    ms_serial = timed(S.SERIAL, K) if world > 1 else ms_overlap
+    ms_nocomm = timed(S.NOCOMM, K) if world > 1 else ms_overlap
+    # the schedule a production ring keeps is the faster of the two on this box (a one-off calibration of a few steps): with the
+    # copy-engine transport the overlapped one (nothing competes for CTA slots), with NCCL's send/recv kernels the serial one
+    best_mode, ms_best = (S.OVERLAP, ms_overlap) if ms_overlap <= ms_serial else (S.SERIAL, ms_serial)
+    # the user's call with host buffers: this rank's rows up, K steps, the reductions back
+    barrier()
+    t0 = time.perf_counter()
+    tm.lib().tm_set_step_counter(ring._ctx(), 0)
+    ring.upload(host.numpy())
+    ring.run(K, best_mode)
+    ring.measure()
+    te = maxr(time.perf_counter() - t0)
+    comm = ring.comm_bytes_per_step()
+    ring.close()
+    peak, peak_src = measured_peaks()
+    sites = float(L) * L
+    value = sites / (ms_best * 1e-3)
+    return None if rank != 0 else {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_best,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Rietkerk SPB=1 Dornic+RK4 step, ONE lattice L=%d cut into %d row slab(s) of %d rows, 4 halo rows x 3 fields "
+                               "per neighbour per step over %s (libtm_slab.so)" % (L, world, L // world, "CUDA IPC peer copies on the copy engines + stream-ordered flags"
+                                                                                 if a.slab_transport == "peer" else "ncclSend/ncclRecv"),
+                   "parallelism": "row slabs, periodic ring, halo traffic behind the inner rows' update" if world > 1 else "one GPU, undivided lattice",
+                   "l2": "slab state %.0f MiB per GPU (x2 ping-pong) exceeds the 126 MB L2" % (3 * ring.nrows * L * 8 / 2 ** 20)},
+        "timing": "CUDA events on each rank's main stream around K steps (the join with the band/comm stream included), max over ranks",
+        "finite": bool(finite), "gpu_launches": (6 if world > 1 else 2) * K,
+        "check": {"active_sites": active, "mean_P": mean_p, "note": "the same for every number of slabs (bit-identical fields; the mean is summed per rank)"},
+        "roofline": {"bound": "hbm", "achieved": sites * BYTES_PER_SITE_UPDATE / world / (ms_best * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": sites * BYTES_PER_SITE_UPDATE / world / (ms_best * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "note": "per GPU: its slab's 48 B per site-update over the step time"},
+        "comm": {"transport": a.slab_transport, "schedule": "overlapped" if best_mode == S.OVERLAP else "serial",
+                 "bytes_sent_per_step_per_rank": comm, "ms_per_step_overlapped": ms_overlap, "ms_per_step_serial_schedule": ms_serial,
+                 "ms_per_step_without_transfers": ms_nocomm, "exposed_ms_per_step": ms_best - ms_nocomm,
+                 "note": "value is the faster schedule; exposed = that schedule minus the band/inner schedule with the transfers left out"},
+        "e2e": {"value": sites * K / te, "unit": UNIT, "h2d_bytes_per_step": 3 * ring.nrows * L * 8 / K, "d2h_bytes_per_step": 64.0 / K,
+                "steps": K, "call": "tm_upload(rows of this rank) + tm_slab_run(K) + tm_measure: the frame goes in once per call "
+                                    "(a slab ring keeps its state resident between exchanges), wall clock, max over ranks"},
+    }
+
+
+def run_slab(a):
+    import torch
+    rank, local, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = a.L if a.L != 4096 else 16384
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.time()
+    out = slab_measure(a, L, a.steps, max(a.warmup, 3), rank, world, local, dist)
+    clocks = sampler.stop(t0, time.time())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
+        out["clocks"] = clocks
         print(json.dumps(out), flush=True)
 
 
@@ -582,7 +733,14 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=2, help="time steps of the cpu_baseline leg of the product arm")
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke", "spb2"], help="dp, fke, spb2: extra, non-headline lines")
+    ap.add_argument("--no-slab", action="store_true", help="skip the L=16384 row-slab line (BASELINE config 5) the default run carries under 'slab_L16384'")
+    ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke", "spb2", "slab"],
+                    help="dp, fke, spb2: extra, non-headline lines; slab: BASELINE config 5, one L=16384 lattice over the ranks (strong scaling)")
+    ap.add_argument("--slab-transport", default="nccl", choices=["peer", "nccl"],
+                    help="slab: halo transport (nccl: ncclSend/ncclRecv, measured on 2, 4 and 8 GPUs; peer: CUDA IPC copies on the copy engines, "
+                         "measured on 2 and 4 GPUs only)")
+    ap.add_argument("--slab-budget-s", type=int, default=150, help="wall-clock budget of the slab section of the default run")
+    ap.add_argument("--slab-reserve-sms", type=int, default=0, help="slab: SMs' worth of CTA slots the inner RK4 launch leaves to the band and transport kernels")
     ap.add_argument("--fke-bound-d", type=int, default=1, help="fke: diffusion window half-width (the SPB=2 driver's constants give 1)")
     ap.add_argument("--fke-bound-v", type=int, default=1, help="fke: advection window half-width")
     a = ap.parse_args()
@@ -592,6 +750,8 @@ def main():
         return run_fke_extra(a)
     if a.workload == "spb2" and a.impl == "ours":
         return run_spb2_extra(a)
+    if a.workload == "slab" and a.impl == "ours":
+        return run_slab(a)
     if a.impl == "reference":
         run_reference_arm(a)
     else:

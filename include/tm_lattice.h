@@ -142,6 +142,26 @@ int tm_halo_pack(tm_ctx *, int which, void **dev_buf);
 int tm_halo_unpack(tm_ctx *, int which, const void *dev_buf);
 void *tm_cuda_stream(tm_ctx *);
 
+/* Overlapped slab stepping (BASELINE config 5: "Rietkerk L=16384 single trial domain-decomposed across 2/4/8 GPUs with
+ * NVLink halo exchange"; the reference has no counterpart, its lattice lives in one address space).  One step =
+ *   tm_slab_step_begin : the two boundary bands (tm_slab_band_rows() rows each) of the NEW state, on tm_slab_comm_stream()
+ *   <transport>        : on that stream, send the new edge rows / receive the new ghost rows (tm_slab_halo_ptrs, next = 1);
+ *                        include/tm_slab.h does this with ncclSend / ncclRecv
+ *   tm_slab_step_end   : the inner rows on the main stream, concurrently with the two items above.
+ * tm_slab_join makes the main stream wait for the band stream before tm_measure / tm_download / tm_step.
+ * Results are bit-identical to tm_step on the undivided lattice. */
+int tm_slab_band_rows(void);
+int tm_state_buffers(tm_ctx *, void **buf0, void **buf1, uint64_t *bytes, int *cur, int *row_doubles, int *rows_alloc);
+void *tm_slab_comm_stream(tm_ctx *);
+int tm_slab_reserve_sms(tm_ctx *, int n_sm);
+int tm_slab_halo_ptrs(tm_ctx *, int next, int side, int trial, int field, void **send_ptr, void **recv_ptr, uint64_t *bytes);
+int tm_slab_step_begin(tm_ctx *);
+int tm_slab_step_end(tm_ctx *);
+int tm_slab_join(tm_ctx *);
+/* Copy-engine transport for slab contexts of one process (cudaMemcpyPeerAsync over NVLink): dst fetches its ghost rows from its
+ * two ring neighbours.  next != 0: inside an open overlapped step of all three (between _begin and _end); 0: the current state. */
+int tm_slab_pull_halos(tm_ctx *dst, tm_ctx *up, tm_ctx *down, int next);
+
 /* --- measurement ----------------------------------------------------------------------- */
 /* out[n_trials]; blocks until the stream is idle. */
 int tm_measure(tm_ctx *, tm_stats *out);

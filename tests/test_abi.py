@@ -94,3 +94,17 @@ def test_other_entry_points_have_no_cpu_fallback_either():
         tm.FkeMover(32, 1, device=0)
     with pytest.raises(tm.TmError, match="no CUDA device"):
         tm.dp_noise_off(8, 1.0, 1.0, 0.1, 0.1, 1.0, np.ones(64), 1)
+
+
+def test_slab_library_exports_every_declared_symbol():
+    """include/tm_slab.h -> libtm_slab.so (links libtm_lattice.so and libnccl.so.2); creating a ring without a GPU fails loudly."""
+    from trophic_maelstorm_b200 import slab as S
+    lib = S.lib()
+    names = [n for n in _header_names("tm_slab.h")]
+    assert names == sorted(S.SLAB_ABI_SYMBOLS), (names, sorted(S.SLAB_ABI_SYMBOLS))
+    for n in names:
+        assert hasattr(lib, n), "libtm_slab.so does not export %s" % n
+    assert S.partition(16384, 8, 7) == (14336, 2048) and S.partition(10, 3, 0) == (0, 4) and S.partition(10, 3, 2) == (7, 3)
+    if tm.lib().tm_device_count() == 0:
+        with pytest.raises(tm.TmError, match="no CUDA device"):
+            S.LocalSlabRing(tm.rietkerk_params(64), 1, [0, 0], transport=S.PEER_COPY)

@@ -49,6 +49,12 @@ struct tm_ctx {
     int rk4_occ = 1;               // resident CTAs per SM of riet_rk4_kernel
     int dornic_kind = 1;           // Dornic sweep: 2 = riet_dornic2_kernel (two columns per thread), 1 = riet_dornic_kernel
     double *halo_dev[2] = {nullptr, nullptr};
+    // overlapped slab stepping (tm_slab_step_begin / _end): boundary bands and the halo traffic on their own high-priority stream
+    cudaStream_t band_stream = nullptr;
+    cudaEvent_t ev_band[2] = {nullptr, nullptr}, ev_inner[2] = {nullptr, nullptr}, ev_join = nullptr, ev_main = nullptr;
+    double *pstar_band_dev = nullptr;   // rho* scratch of the band launches (the inner launch's rows overlap theirs by 3)
+    int slab_parity = 0, slab_reserve_sm = 0;
+    bool slab_open = false, slab_fresh = true;   // fresh: the main stream may hold work the band stream has not been ordered after
     uint64_t seed = 0, step = 0;
     uint32_t trial0 = 0;
     float last_ms = 0.f;
@@ -257,6 +263,11 @@ int tm_destroy(tm_ctx *c)
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     for (auto &e : c->kev) cudaEventDestroy(e);
+    if (c->band_stream) { cudaStreamSynchronize(c->band_stream); cudaStreamDestroy(c->band_stream); }
+    for (int s = 0; s < 2; s++) { if (c->ev_band[s]) cudaEventDestroy(c->ev_band[s]); if (c->ev_inner[s]) cudaEventDestroy(c->ev_inner[s]); }
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    cudaFree(c->pstar_band_dev);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
     delete c;
@@ -359,6 +370,66 @@ int tm_seed(tm_ctx *c, uint64_t seed, uint32_t trial0)
 int tm_set_step_counter(tm_ctx *c, uint64_t step) { if (!c) return TM_E_ARG; c->step = step; return TM_OK; }
 uint64_t tm_step_counter(const tm_ctx *c) { return c ? c->step : 0; }
 
+// The production pair (Dornic sweep into rho*, then the RK4 kernel) on lattice-local rows [ra, rb) of the context's slab, on
+// `stream`, with at most n_slots resident CTAs for the RK4 kernel.  A row view is the same kernels on shifted base pointers
+// with nrows = rb - ra and row0 advanced by ra (the Philox cell index is global, so the values do not depend on the cut); the
+// whole slab is the view [0, nrows).  ev (3 events) brackets the two launches when kernel timing is on.
+static int launch_pair_view(tm_ctx *c, const StepArgs &A0, int ra, int rb, double *pstar, cudaStream_t stream, int n_slots, cudaEvent_t *ev)
+{
+    StepArgs A = A0;
+    Geom &g = A.g;
+    const long long shift = (long long)ra * g.Lp;
+    if (ra != 0 || rb != g.nrows) {
+        if (g.wrap) TM_FAIL(c, TM_E_STATE, "row views need a slab context");
+        g.row0 += ra; g.nrows = rb - ra;
+    }
+    A.in = A0.in + shift; A.out = A0.out + shift; A.pstar = pstar + shift;
+    DornicArgs D{};
+    D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.mu_scale = A.c.mu_scale; D.in = A.in; D.pstar = pstar + shift;
+    D.seed = c->seed; D.trial0 = c->trial0; D.step = (unsigned int)c->step; D.rk = A.rk; D.logtab = c->logtab_dev;
+    D.row_lo = g.wrap ? 0 : -(kHalo - 1); D.row_hi = g.wrap ? g.nrows : g.nrows + (kHalo - 1);
+    // rows per CTA: enough (trial, column block, run) items for ~2 rounds over 4 resident CTAs per SM
+    const int dcols = c->dornic_kind == 2 ? kDornic2Cols : kDornicThreads;   // columns per CTA
+    const int ncb = (g.L + dcols - 1) / dcols, nrow_d = D.row_hi - D.row_lo;
+    long long want_runs = ((long long)c->n_sm * 8 + (long long)g.n_trials * ncb - 1) / ((long long)g.n_trials * ncb);
+    if (want_runs < 1) want_runs = 1;
+    int rpc = (int)((nrow_d + want_runs - 1) / want_runs);
+    if (rpc < 16) rpc = nrow_d < 16 ? nrow_d : 16;
+    D.rows_per_cta = rpc;
+    const long long ditems = (long long)g.n_trials * ncb * ((nrow_d + rpc - 1) / rpc);
+    long long dgrid = ditems;
+    if (dgrid > (long long)c->n_sm * 64) dgrid = (long long)c->n_sm * 64;
+    const size_t dsmem = riet_dornic_smem_bytes();
+    if (ev) TM_CUDA(c, cudaEventRecord(ev[0], stream));
+    if (c->dornic_kind == 2) {
+        if (c->strict) riet_dornic2_kernel<true><<<(unsigned)dgrid, kDornic2Threads, dsmem, stream>>>(D);
+        else           riet_dornic2_kernel<false><<<(unsigned)dgrid, kDornic2Threads, dsmem, stream>>>(D);
+    } else {
+        if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, stream>>>(D);
+        else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, stream>>>(D);
+    }
+    TM_CUDA(c, cudaGetLastError());
+    if (ev) TM_CUDA(c, cudaEventRecord(ev[1], stream));
+    if (c->rk4_kind == 2) {
+        Rk4Args R{};
+        R.g = g; R.c = A.c; R.in = A.in; R.pstar = A.pstar; R.out = A.out; R.a_trial = c->a_dev; R.counters = c->counters;
+        int grid2 = 1;
+        rk4_launch_shape(g, c->n_sm * c->rk4_occ, &R, &grid2);
+        if (c->strict) riet_rk4_kernel<true><<<grid2, kRkThreads, riet_rk4_smem_bytes(), stream>>>(R);
+        else           riet_rk4_kernel<false><<<grid2, kRkThreads, riet_rk4_smem_bytes(), stream>>>(R);
+    } else {
+        int grid = 1;
+        riet_launch_shape(g, n_slots, &grid);
+        const size_t smem = riet_smem_bytes(g.nthreads, false);
+        if (c->strict) riet_step_kernel<false, true, kSrcPre, false><<<grid, g.nthreads, smem, stream>>>(A);
+        else           riet_step_kernel<false, false, kSrcPre, false><<<grid, g.nthreads, smem, stream>>>(A);
+    }
+    TM_CUDA(c, cudaGetLastError());
+    if (ev) TM_CUDA(c, cudaEventRecord(ev[2], stream));
+    c->launches_this_call += 1;
+    return TM_OK;
+}
+
 // one launch: in = buf[cur] -> out = buf[cur^1]
 static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool dornic_only)
 {
@@ -388,52 +459,16 @@ static int launch_step(tm_ctx *c, bool stats, bool replay, uint32_t stride, bool
         } else if (c->fused) {
             if (c->strict) TM_LAUNCH(false, true, kSrcPhilox, false); else TM_LAUNCH(false, false, kSrcPhilox, false);
         } else {
-            // alternative: Dornic sweep at full occupancy into a rho* scratch field, then the RK4 fronts only
+            // Dornic sweep at full occupancy into a rho* scratch field, then the RK4 fronts only
             if (!c->pstar_dev) {
                 const size_t nb = sizeof(double) * (size_t)g.n_trials * g.field_stride;
                 TM_CUDA(c, cudaMalloc(&c->pstar_dev, nb));
                 TM_CUDA(c, cudaMemsetAsync(c->pstar_dev, 0, nb, c->stream));
             }
-            DornicArgs D{};
-            D.g = g; D.dk = A.c.dk; D.inv_lambda = A.c.inv_lambda; D.mu_scale = A.c.mu_scale; D.in = A.in; D.pstar = c->pstar_dev;
-            D.seed = c->seed; D.trial0 = c->trial0; D.step = (unsigned int)c->step; D.rk = A.rk; D.logtab = c->logtab_dev;
-            D.row_lo = g.wrap ? 0 : -(kHalo - 1); D.row_hi = g.wrap ? g.nrows : g.nrows + (kHalo - 1);
-            // rows per CTA: enough (trial, column block, run) items for ~2 rounds over 4 resident CTAs per SM
-            const int dcols = c->dornic_kind == 2 ? kDornic2Cols : kDornicThreads;   // columns per CTA
-            const int ncb = (g.L + dcols - 1) / dcols, nrow_d = D.row_hi - D.row_lo;
-            long long want_runs = ((long long)c->n_sm * 8 + (long long)g.n_trials * ncb - 1) / ((long long)g.n_trials * ncb);
-            if (want_runs < 1) want_runs = 1;
-            int rpc = (int)((nrow_d + want_runs - 1) / want_runs);
-            if (rpc < 16) rpc = nrow_d < 16 ? nrow_d : 16;
-            D.rows_per_cta = rpc;
-            const long long ditems = (long long)g.n_trials * ncb * ((nrow_d + rpc - 1) / rpc);
-            long long dgrid = ditems;
-            if (dgrid > (long long)c->n_sm * 64) dgrid = (long long)c->n_sm * 64;
-            const size_t dsmem = riet_dornic_smem_bytes();
             const bool timed = c->kernel_timing && c->kev_steps < kTimedSteps;
-            cudaEvent_t *ev = timed ? &c->kev[3 * c->kev_steps] : nullptr;
-            if (timed) TM_CUDA(c, cudaEventRecord(ev[0], c->stream));
-            if (c->dornic_kind == 2) {
-                if (c->strict) riet_dornic2_kernel<true><<<(unsigned)dgrid, kDornic2Threads, dsmem, c->stream>>>(D);
-                else           riet_dornic2_kernel<false><<<(unsigned)dgrid, kDornic2Threads, dsmem, c->stream>>>(D);
-            } else {
-                if (c->strict) riet_dornic_kernel<true><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
-                else           riet_dornic_kernel<false><<<(unsigned)dgrid, kDornicThreads, dsmem, c->stream>>>(D);
-            }
-            TM_CUDA(c, cudaGetLastError());
-            if (timed) TM_CUDA(c, cudaEventRecord(ev[1], c->stream));
-            A.pstar = c->pstar_dev;
-            if (c->rk4_kind == 2) {
-                Rk4Args R{};
-                R.g = g; R.c = A.c; R.in = A.in; R.pstar = c->pstar_dev; R.out = A.out; R.a_trial = c->a_dev; R.counters = c->counters;
-                int grid2 = 1;
-                rk4_launch_shape(g, c->n_sm * c->rk4_occ, &R, &grid2);
-                if (c->strict) riet_rk4_kernel<true><<<grid2, kRkThreads, riet_rk4_smem_bytes(), c->stream>>>(R);
-                else           riet_rk4_kernel<false><<<grid2, kRkThreads, riet_rk4_smem_bytes(), c->stream>>>(R);
-            } else
-            if (c->strict) TM_LAUNCH(false, true, kSrcPre, false); else TM_LAUNCH(false, false, kSrcPre, false);
-            if (timed) { TM_CUDA(c, cudaEventRecord(ev[2], c->stream)); c->kev_steps++; }
-            c->launches_this_call += 1;
+            const int rc = launch_pair_view(c, A, 0, g.nrows, c->pstar_dev, c->stream, c->n_sm * c->riet_occ, timed ? &c->kev[3 * c->kev_steps] : nullptr);
+            if (rc != TM_OK) return rc;
+            if (timed) c->kev_steps++;
         }
 #undef TM_LAUNCH
     } else {
@@ -573,6 +608,205 @@ int tm_halo_unpack(tm_ctx *c, int which, const void *dev_buf)
                                  dev_buf, sizeof(double) * kHalo * g.Lp,
                                  sizeof(double) * kHalo * g.Lp, (size_t)g.n_trials * g.n_fields,
                                  cudaMemcpyDeviceToDevice, c->stream));
+    return TM_OK;
+}
+
+// ---- overlapped slab stepping (BASELINE config 5) ------------------------------------------------------------
+// One step of a row slab as three pieces: the two boundary bands (first and last kBand rows) on a high-priority stream, the halo
+// traffic of the NEW state behind them on the same stream (the caller's NCCL send/recv, tm_slab.cpp), and the inner rows on the
+// context's main stream at the same time.  Step n, state n -> n + 1 (buffers alternate):
+//     band stream:  wait inner(n-1) | band(n) | record ev_band[n&1] | <caller: send new edge rows, receive new ghost rows>
+//     main stream:  wait band(n-1)  | inner(n) | record ev_inner[n&1]
+// band(n) reads rows -4 .. kBand+3 of state n: its ghost rows arrived in order on the band stream, rows kBand.. come from
+// inner(n-1).  inner(n) reads rows kBand-4 ..: band rows of state n come from band(n-1).  Writes into the buffer that held
+// state n-1 are behind the same two waits.
+constexpr int kBand = 8;
+
+int tm_slab_band_rows(void) { return kBand; }
+
+static int slab_prepare(tm_ctx *c)
+{
+    if (c->band_stream) return TM_OK;
+    int lo = 0, hi = 0;
+    TM_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    TM_CUDA(c, cudaStreamCreateWithPriority(&c->band_stream, cudaStreamNonBlocking, hi));
+    for (int s = 0; s < 2; s++) {
+        TM_CUDA(c, cudaEventCreateWithFlags(&c->ev_band[s], cudaEventDisableTiming));
+        TM_CUDA(c, cudaEventCreateWithFlags(&c->ev_inner[s], cudaEventDisableTiming));
+    }
+    TM_CUDA(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    TM_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    const size_t nb = sizeof(double) * (size_t)c->g.n_trials * c->g.field_stride;
+    if (!c->pstar_dev) { TM_CUDA(c, cudaMalloc(&c->pstar_dev, nb)); TM_CUDA(c, cudaMemsetAsync(c->pstar_dev, 0, nb, c->stream)); }
+    TM_CUDA(c, cudaMalloc(&c->pstar_band_dev, nb));
+    TM_CUDA(c, cudaMemsetAsync(c->pstar_band_dev, 0, nb, c->stream));
+    return TM_OK;
+}
+
+void *tm_slab_comm_stream(tm_ctx *c)
+{
+    if (!c || c->g.wrap) return nullptr;
+    cudaSetDevice(c->device);
+    if (slab_prepare(c) != TM_OK) return nullptr;
+    return (void *)c->band_stream;
+}
+
+// the two state buffers (whole cudaMalloc allocations: what cudaIpcGetMemHandle wants), the index of the current one, and the
+// layout a peer needs to address this slab's rows: padded row length and rows per field plane
+int tm_state_buffers(tm_ctx *c, void **buf0, void **buf1, uint64_t *bytes, int *cur, int *row_doubles, int *rows_alloc)
+{
+    if (!c) return TM_E_ARG;
+    if (buf0) *buf0 = c->buf[0];
+    if (buf1) *buf1 = c->buf[1];
+    if (bytes) *bytes = sizeof(double) * (uint64_t)c->g.n_trials * (uint64_t)c->g.trial_stride;
+    if (cur) *cur = c->cur;
+    if (row_doubles) *row_doubles = c->g.Lp;
+    if (rows_alloc) *rows_alloc = c->g.rows_alloc;
+    return TM_OK;
+}
+
+// SMs' worth of resident-CTA slots the inner RK4 launch leaves free (room for the band kernels and the transport's own kernels)
+int tm_slab_reserve_sms(tm_ctx *c, int n_sm)
+{
+    if (!c || n_sm < 0 || n_sm >= c->n_sm) return TM_E_ARG;
+    c->slab_reserve_sm = n_sm;
+    return TM_OK;
+}
+
+// Edge rows to send and ghost rows to fill, of the state being made by the open step (next != 0; between tm_slab_step_begin
+// and tm_slab_step_end) or of the current state (next == 0).  side 0 = top: send rows 0..3, ghosts above; side 1 = bottom:
+// send the last four rows, ghosts below.  A (trial, field) plane's four rows are contiguous: *bytes each.
+int tm_slab_halo_ptrs(tm_ctx *c, int next, int side, int trial, int field, void **send_ptr, void **recv_ptr, uint64_t *bytes)
+{
+    if (!c || !send_ptr || !recv_ptr || !bytes || side < 0 || side > 1) return TM_E_ARG;
+    const Geom &g = c->g;
+    if (g.wrap) TM_FAIL(c, TM_E_STATE, "tm_slab_halo_ptrs: not a slab context");
+    if (trial < 0 || trial >= g.n_trials || field < 0 || field >= g.n_fields) TM_FAIL(c, TM_E_ARG, "tm_slab_halo_ptrs: no such plane");
+    double *base = c->buf[next ? c->cur ^ 1 : c->cur] + (long long)trial * g.trial_stride + (long long)field * g.field_stride;
+    const long long rs = side == 0 ? kHalo : g.nrows, rr = side == 0 ? 0 : g.nrows + kHalo;   // physical rows
+    *send_ptr = base + rs * g.Lp; *recv_ptr = base + rr * g.Lp;
+    *bytes = sizeof(double) * (uint64_t)kHalo * g.Lp;
+    return TM_OK;
+}
+
+static int slab_args(tm_ctx *c, StepArgs *A)
+{
+    const tm_params &p = c->p;
+    A->g = c->g; A->c = riet_consts(p);
+    A->in = c->buf[c->cur]; A->out = c->buf[c->cur ^ 1];
+    A->rk = philox_keys(c->seed); A->logtab = c->logtab_dev;
+    A->a_trial = c->a_dev; A->seed = c->seed; A->trial0 = c->trial0; A->step = (unsigned int)c->step;
+    A->counters = c->counters;
+    return TM_OK;
+}
+
+int tm_slab_step_begin(tm_ctx *c)
+{
+    if (!c) return TM_E_ARG;
+    const Geom &g = c->g;
+    if (g.wrap || c->p.model != TM_MODEL_RIETKERK) TM_FAIL(c, TM_E_STATE, "tm_slab_step_begin: needs a Rietkerk row-slab context");
+    if (g.nrows < 2 * kBand + 2 * kHalo) TM_FAIL(c, TM_E_STATE, "tm_slab_step_begin: a slab needs at least %d rows", 2 * kBand + 2 * kHalo);
+    if (c->slab_open) TM_FAIL(c, TM_E_STATE, "tm_slab_step_begin: the previous step is still open");
+    if (check_slab_step(c, "tm_slab_step_begin") != TM_OK) return TM_E_STATE;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    if (push_trial_consts(c) != TM_OK) return TM_E_CUDA;
+    if (slab_prepare(c) != TM_OK) return TM_E_CUDA;
+    const int par = c->slab_parity;
+    if (c->slab_fresh) {   // everything queued so far on the main stream (uploads, plain steps, a join) precedes this band launch
+        TM_CUDA(c, cudaEventRecord(c->ev_inner[par ^ 1], c->stream));
+        TM_CUDA(c, cudaEventRecord(c->ev_band[par ^ 1], c->band_stream));
+        c->slab_fresh = false;
+    }
+    StepArgs A{};
+    slab_args(c, &A);
+    c->launches_this_call = 0;
+    TM_CUDA(c, cudaStreamWaitEvent(c->band_stream, c->ev_inner[par ^ 1], 0));
+    int rc = launch_pair_view(c, A, 0, kBand, c->pstar_band_dev, c->band_stream, c->n_sm * c->riet_occ, nullptr);
+    if (rc == TM_OK) rc = launch_pair_view(c, A, g.nrows - kBand, g.nrows, c->pstar_band_dev, c->band_stream, c->n_sm * c->riet_occ, nullptr);
+    if (rc != TM_OK) return rc;
+    TM_CUDA(c, cudaEventRecord(c->ev_band[par], c->band_stream));
+    c->slab_open = true;
+    return TM_OK;
+}
+
+int tm_slab_step_end(tm_ctx *c)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->slab_open) TM_FAIL(c, TM_E_STATE, "tm_slab_step_end: no open step");
+    const Geom &g = c->g;
+    TM_CUDA(c, cudaSetDevice(c->device));
+    const int par = c->slab_parity;
+    StepArgs A{};
+    slab_args(c, &A);
+    TM_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_band[par ^ 1], 0));
+    const int rc = launch_pair_view(c, A, kBand, g.nrows - kBand, c->pstar_dev, c->stream, (c->n_sm - c->slab_reserve_sm) * c->riet_occ, nullptr);
+    if (rc != TM_OK) return rc;
+    TM_CUDA(c, cudaEventRecord(c->ev_inner[par], c->stream));
+    c->slab_open = false; c->slab_parity ^= 1;
+    c->cur ^= 1; c->step++;
+    c->stats_valid = false;
+    c->last_launches = 6;
+    return TM_OK;
+}
+
+// after the last overlapped step: the main stream waits for the band stream (band rows and ghost rows of the final state), so
+// that tm_measure / tm_download / tm_step on the main stream see a complete slab
+int tm_slab_join(tm_ctx *c)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->band_stream) return TM_OK;
+    if (c->slab_open) TM_FAIL(c, TM_E_STATE, "tm_slab_join: a step is open");
+    TM_CUDA(c, cudaSetDevice(c->device));
+    TM_CUDA(c, cudaEventRecord(c->ev_join, c->band_stream));
+    TM_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->slab_fresh = true;
+    return TM_OK;
+}
+
+// Copy-engine transport of the slab ring for contexts of ONE process (cudaMemcpyPeerAsync over NVLink: no SM is involved, so the
+// transfers cannot compete with the inner launch for CTA slots).  Pull model: `dst` fetches its ghost rows above from `up`'s last
+// four rows and its ghost rows below from `down`'s first four.  next != 0: inside an open overlapped step of all three, on dst's band
+// stream, behind the neighbours' band launches of this step; next == 0: the current state, on dst's main stream, behind whatever
+// the neighbours' main streams hold now.  The neighbours' rows are not overwritten before dst has read them: their step after
+// next needs ghost rows that dst sends only after its own next band launch, which follows this copy in stream order.
+int tm_slab_pull_halos(tm_ctx *dst, tm_ctx *up, tm_ctx *down, int next)
+{
+    if (!dst || !up || !down) return TM_E_ARG;
+    const Geom &g = dst->g;
+    if (g.wrap || up->g.wrap || down->g.wrap) TM_FAIL(dst, TM_E_STATE, "tm_slab_pull_halos: not slab contexts");
+    if (up->g.Lp != g.Lp || down->g.Lp != g.Lp || up->g.n_trials != g.n_trials || down->g.n_trials != g.n_trials)
+        TM_FAIL(dst, TM_E_ARG, "tm_slab_pull_halos: slabs of different lattices");
+    TM_CUDA(dst, cudaSetDevice(dst->device));
+    if (slab_prepare(dst) != TM_OK) return TM_E_CUDA;
+    cudaStream_t st = next ? dst->band_stream : dst->stream;
+    tm_ctx *nb[2] = {up, down};
+    for (int k = 0; k < 2; k++) {
+        tm_ctx *src = nb[k];
+        if (src->device != dst->device) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess) cudaGetLastError();   // already enabled, or no direct path: the copy still works (staged)
+        }
+        if (next) {
+            if (!src->slab_open) TM_FAIL(dst, TM_E_STATE, "tm_slab_pull_halos: the neighbour has no open step");
+            TM_CUDA(dst, cudaStreamWaitEvent(st, src->ev_band[src->slab_parity], 0));
+        } else if (src != dst) {
+            TM_CUDA(dst, cudaSetDevice(src->device));
+            if (slab_prepare(src) != TM_OK) return TM_E_CUDA;
+            TM_CUDA(dst, cudaEventRecord(src->ev_main, src->stream));
+            TM_CUDA(dst, cudaSetDevice(dst->device));
+            TM_CUDA(dst, cudaStreamWaitEvent(st, src->ev_main, 0));
+        }
+        const Geom &sg = src->g;
+        const long long rs = k == 0 ? sg.nrows : kHalo;            // up: its last four rows; down: its first four (physical rows)
+        const long long rr = k == 0 ? 0 : g.nrows + kHalo;         // my ghost rows above / below
+        const double *sb = src->buf[next ? src->cur ^ 1 : src->cur];
+        double *db = dst->buf[next ? dst->cur ^ 1 : dst->cur];
+        for (int t = 0; t < g.n_trials; t++)
+            for (int f = 0; f < g.n_fields; f++)
+                TM_CUDA(dst, cudaMemcpyPeerAsync(db + (long long)t * g.trial_stride + (long long)f * g.field_stride + rr * g.Lp, dst->device,
+                                                 sb + (long long)t * sg.trial_stride + (long long)f * sg.field_stride + rs * sg.Lp, src->device,
+                                                 sizeof(double) * kHalo * g.Lp, st));
+    }
     return TM_OK;
 }
 

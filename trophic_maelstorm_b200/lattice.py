@@ -100,6 +100,15 @@ def lib():
         "tm_halo_pack": (i, [vp, i, C.POINTER(vp)]),
         "tm_halo_unpack": (i, [vp, i, vp]),
         "tm_cuda_stream": (vp, [vp]),
+        "tm_slab_band_rows": (i, []),
+        "tm_state_buffers": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64), C.POINTER(i), C.POINTER(i), C.POINTER(i)]),
+        "tm_slab_comm_stream": (vp, [vp]),
+        "tm_slab_reserve_sms": (i, [vp, i]),
+        "tm_slab_halo_ptrs": (i, [vp, i, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)]),
+        "tm_slab_step_begin": (i, [vp]),
+        "tm_slab_step_end": (i, [vp]),
+        "tm_slab_join": (i, [vp]),
+        "tm_slab_pull_halos": (i, [vp, vp, vp, i]),
         "tm_dp_noise_off_host": (i, [i, i] + [C.c_double] * 5 + [dp, i, C.POINTER(C.c_float)]),
         "tm_measure": (i, [vp, C.POINTER(Stats)]),
         "tm_measure_spread": (i, [vp, i, i, C.POINTER(Spread)]),
@@ -121,7 +130,9 @@ ABI_SYMBOLS = [
     "tm_abi_version", "tm_device_count", "tm_device_mem", "tm_ctx_bytes", "tm_last_error", "tm_create", "tm_create_slab", "tm_destroy",
     "tm_set_trial_a", "tm_set_strict", "tm_set_fused", "tm_upload", "tm_download", "tm_n_fields", "tm_seed",
     "tm_set_step_counter", "tm_step_counter", "tm_step", "tm_step_replay", "tm_dornic_only",
-    "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream", "tm_measure", "tm_measure_spread",
+    "tm_halo_rows", "tm_halo_bytes", "tm_halo_pack", "tm_halo_unpack", "tm_cuda_stream",
+    "tm_slab_band_rows", "tm_state_buffers", "tm_slab_comm_stream", "tm_slab_reserve_sms", "tm_slab_halo_ptrs", "tm_slab_step_begin", "tm_slab_step_end",
+    "tm_slab_join", "tm_slab_pull_halos", "tm_measure", "tm_measure_spread",
     "tm_sampler_overflow", "tm_sync", "tm_last_step_ms", "tm_set_kernel_timing", "tm_kernel_ms", "tm_run_host",
     "tm_dp_noise_off_host",
 ]
