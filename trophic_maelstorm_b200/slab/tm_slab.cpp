@@ -215,8 +215,10 @@ static int ipc_setup(tm_slab *s)
         g_write32 = (cu_memop32_fn)f;
         if (!g_wait32 || !g_write32) return fail(s, TM_E_CUDA, "stream memory operations are not available");
     }
-    SL_CUDA(s, cudaMalloc(&s->flags, 64));
-    SL_CUDA(s, cudaMemset(s->flags, 0, 64));
+    // a whole 2 MiB block of its own: smaller allocations are carved out of shared blocks, and it is the block that an IPC handle
+    // exports (CUDA programming guide, interprocess communication)
+    SL_CUDA(s, cudaMalloc(&s->flags, 2u << 20));
+    SL_CUDA(s, cudaMemset(s->flags, 0, 2u << 20));
     IpcCard mine;
     memset(&mine, 0, sizeof mine);
     void *b0, *b1; uint64_t bytes; int row_doubles;
