@@ -88,6 +88,17 @@ int tm_cons_step2_upload(tm_cons_ctx *, const double *fields, const double *gamm
 /* RK4 part of the step: 0 (default) = one launch for the four stages and the clamp (tile-fused, six launches per step);
  * 1 = one launch per stage (nine per step).  Bit-identical results; the second form is kept as the cross-check. */
 int tm_cons_step2_set_rk4_stages(tm_cons_ctx *, int on);
+/* Rietkerk_FPE flavour of the resident step: the body of the time loop of rietkerk_DorFPE_2D_MultiSp compiled with -DSPB=2,
+ * Rietkerk_FPE/rietkerk_bjork_FKE.cpp:4094-4462 -- perception field with calc_gamma_vel_2Sp_NonRefugia's rules (:2534-2607: a
+ * vanished consumer gets gamma = 1) -> vegetation Dornic (:4154-4211) -> four-field RK4 over f_DorFKE_2Sp (:2449-2531: the grazer's
+ * mortality M1 sits in the reaction terms) -> advdiff_FKE_MultiSp on the grazer (:4308; the gather-form kernels of tm_fke.h, on the
+ * device-resident field: the reference's per-step cudaMemcpy pair :4282-4299 has no counterpart) -> clamp `v < eps && v >= lo`
+ * with the veg->clamp_eps / clamp_lo given to setup (1e-10 and 0 in the reference, :4458).  The grazer has no Dornic update and
+ * the advection vectors keep what the context holds (zeros after setup: the two-species runner never assigns them).
+ * t: the grazer's movement windows and stencil sizes (struct tm_fke_terms of tm_fke.h, CPU-path convention F/:3640-3641);
+ * gauss_D / gauss_V: its two stencils (host).  Ten launches per step.  t == NULL switches back to the Rietkerk_FD flavour. */
+struct tm_fke_terms;
+int tm_cons_step2_set_fpe(tm_cons_ctx *, const struct tm_fke_terms *t, const double *gauss_D, const double *gauss_V, double M1);
 int tm_cons_step2_run(tm_cons_ctx *, uint64_t seed, uint32_t trial, uint32_t step0, int nsteps);
 int tm_cons_step2_replay(tm_cons_ctx *, const double *u_veg, const double *u_graz, uint32_t stride);
 int tm_cons_step2_download(tm_cons_ctx *, double *fields, double *gamma, double *v_eff, double *means, uint64_t *overflow);

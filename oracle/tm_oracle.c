@@ -812,6 +812,38 @@ int tmo_step_2sp_means(const tmo_params *pveg, const tmo_graz_params *pg, const 
     return 0;
 }
 
+/* One time step of the Rietkerk_FPE runner compiled with -DSPB=2, rietkerk_DorFPE_2D_MultiSp F/:4094-4462 (see tm_oracle.h). */
+int tmo_step_fpe_2sp(const tmo_params *pveg, const tmo_cons_params *pc, double M1, const tmo_fke_terms *ft, const double *gD,
+                     const double *gV, const int32_t *central, int n_central, double fr_graz, tmo_rng *rng, double *f, double *gamma,
+                     const double *veff, const double *means)
+{
+    if (!pveg || !pc || !ft || pveg->L != pc->L || pveg->L != ft->L) return -1;
+    const int L = pveg->L;
+    const int64_t n = (int64_t)L * L;
+    double *work = malloc(sizeof(double) * (size_t)n * 6);
+    if (!work) return -1;
+    double *D = work, *vout = work + 4 * n, *moved = work + 5 * n;                       /* DRho copy, rho*_P, moved grazers */
+    memcpy(D, f, sizeof(double) * (size_t)n * 4);
+    const double avg_veg = means ? means[0] : tmo_mean(D, n), avg_graz = means ? means[1] : tmo_mean(D + n, n);   /* F/:4101-4106 */
+    const double num_veg = tmo_occupied(D, n);
+    double nR_fac = 1 - num_veg / (L * L);                                               /* F/:4110 */
+    if (nR_fac < 0.35) nR_fac = 0.35;
+    const int new_length = (int)(nR_fac * nR_fac * n_central);                           /* F/:2543 (no lower bound here) */
+    const int eff = (int)(fr_graz * fr_graz * new_length);                               /* F/:2572 */
+    tmo_gamma_perception_fpe(L, D, central, eff, avg_veg, avg_graz, gamma);              /* F/:4117 */
+    dornic_consts k;
+    derive_consts(pveg, &k);
+    dornic_sweep(pveg, &k, rng, D, vout);                                                /* vegetation only, F/:4154-4211 */
+    memcpy(f, vout, sizeof(double) * (size_t)n);
+    if (tmo_rk4_fpe_2sp(pc, M1, f)) { free(work); return -1; }                           /* F/:4240 */
+    if (tmo_fke_move(ft, f + n, gamma, veff, gD, gV, moved)) { free(work); return -1; }  /* F/:4303-4308 */
+    memcpy(f + n, moved, sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < 4 * n; i++)
+        if (f[i] < ft->epsilon && f[i] >= 0.0) f[i] = 0.0;                               /* F/:4458 */
+    free(work);
+    return 0;
+}
+
 /* ================================================================================== */
 /* 6b. The noise-off DP path: percNoDiff_2D P/:549-662                                  */
 /* ================================================================================== */

@@ -160,6 +160,19 @@ typedef struct tmo_graz_params {
 void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
                           double *gamma);
 int tmo_rk4_2sp(const tmo_cons_params *p, double *f);
+/* Rietkerk_FPE flavours (F/ = simulations/Rietkerk_FPE/rietkerk_bjork_FKE.cpp): calc_gamma_vel_2Sp_NonRefugia F/:2534,
+ * RK4_Integrate_Stochastic_2Sp over f_DorFKE_2Sp F/:2449-2531 (grazer mortality M1 in the reaction terms) */
+void tmo_gamma_perception_fpe(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
+                              double *gamma);
+int tmo_rk4_fpe_2sp(const tmo_cons_params *p, double M1, double *f);
+/* One time step of rietkerk_DorFPE_2D_MultiSp compiled with -DSPB=2 (F/:4094-4462) on f[4][L*L] = P, G, W, O: means and cover of the
+ * entry state -> perception field (F/:4117) -> vegetation Dornic (F/:4154-4211) -> four-field RK4 without movement terms (F/:4240)
+ * -> FKE movement of the grazer (advdiff_FKE_MultiSp, F/:4308) -> clamp `v < eps && v >= 0 -> 0` (F/:4458).  The grazer has NO Dornic
+ * update here.  gamma: state (never reset); veff [L*L][2]: the advection vectors the movement step reads (the 2-species runner
+ * never assigns them: zeros); gD, gV: the two Gaussian stencils of ft; means (may be NULL): {<P>, <G>} of the entry state. */
+int tmo_step_fpe_2sp(const tmo_params *pveg, const tmo_cons_params *pc, double M1, const tmo_fke_terms *ft, const double *gD,
+                     const double *gV, const int32_t *central, int n_central, double fr_graz, tmo_rng *rng, double *f, double *gamma,
+                     const double *veff, const double *means);
 /* the noise-off DP path: one RK4 step of percNoDiff_2D (P/:549-662, fP_2D P/:516-529) in place on rho[L*L] */
 int tmo_dp_noise_off_step(int L, double a, double b, double D, double dt, double dx, double *rho);
 /* the grazer's Dornic update with upwind advection, R/:3908-4114 (defined in tm_oracle.c next to the samplers) */

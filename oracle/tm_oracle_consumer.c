@@ -22,14 +22,14 @@
  * distance), new_length = max(1, int(nVeg_frac^2 * size)) with nVeg_frac clamped to >= 0.35 (R/:2533-2540);
  * eff = int(fr * fr * new_length) (R/:2569).  gamma is IN/OUT: the reference adds the disc sum onto the value the array
  * already holds (R/:2581 `gamma[s][i] += ...`, never reset between steps). */
-void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
-                          double *gamma)
+static void gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
+                             double *gamma, double self_gone)
 {
     const double eps = 1.0e-12;                                                     /* R/:2537 */
     const double rho_inverse = rho_avg_prey >= eps ? 1 / rho_avg_prey : 1 / eps;    /* R/:2548-2549 */
     for (int i = 0; i < L * L; i++) {
         const int c_i = i / L, c_j = i % L;
-        if (rho_avg_self < eps) { gamma[i] = 0.0; continue; }                        /* R/:2575 */
+        if (rho_avg_self < eps) { gamma[i] = self_gone; continue; }                  /* R/:2575 (0.0); F/:2579 (1.0) */
         else if (rho_avg_prey < eps) { gamma[i] = 0.0; continue; }                   /* R/:2577 */
         for (int k = 0; k < eff; k++) {                                              /* R/:2580-2581, neighbours R/:1700-1702 */
             const int nx = (c_i + offsets[2 * k] + L) % L, ny = (c_j + offsets[2 * k + 1] + L) % L;
@@ -41,8 +41,23 @@ void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int
     }
 }
 
-/* f_2Dor_2Sp R/:2445-2470; fields [0]=P, [1]=G, [2]=W, [3]=O */
-static void f_2dor_2sp(const tmo_cons_params *p, double *f, const double *Y)
+void tmo_gamma_perception(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
+                          double *gamma)
+{
+    gamma_perception(L, prey, offsets, eff, rho_avg_prey, rho_avg_self, gamma, 0.0);
+}
+
+/* calc_gamma_vel_2Sp_NonRefugia F/:2534-2607 (Rietkerk_FPE): the same disc average; a vanished consumer gets gamma = 1 (F/:2579),
+ * and the function assigns no velocities (v_eff keeps what it held). */
+void tmo_gamma_perception_fpe(int L, const double *prey, const int32_t *offsets, int eff, double rho_avg_prey, double rho_avg_self,
+                              double *gamma)
+{
+    gamma_perception(L, prey, offsets, eff, rho_avg_prey, rho_avg_self, gamma, 1.0);
+}
+
+/* f_2Dor_2Sp R/:2445-2470; fields [0]=P, [1]=G, [2]=W, [3]=O.  fpe != 0: f_DorFKE_2Sp F/:2449-2474, which differs by the grazer's
+ * mortality term -M[1] G (F/:2466; in Rietkerk_FD it sits in the grazer's Dornic beta instead) */
+static void f_2dor_2sp(const tmo_cons_params *p, double *f, const double *Y, int fpe, double M1)
 {
     const int g = p->L, n = g * g;
     const double cgmax = p->c * p->gmax, A01H01 = p->A01 * p->H01, EA1 = p->E1 * p->A01;   /* R/:2452 */
@@ -53,6 +68,7 @@ static void f_2dor_2sp(const tmo_cons_params *p, double *f, const double *Y)
         const int lf = r * g + ((q - 1) % g + g) % g, rt = r * g + ((q + 1) % g + g) % g;
         f[i] = cgmax * W[i] * P[i] / (W[i] + p->K1) - (p->A01 * P[i] / (1 + A01H01 * P[i])) * G[i];                     /* R/:2460 */
         f[n + i] = (EA1 * P[i] / (1 + A01H01 * P[i])) * G[i];                                                          /* R/:2462 */
+        if (fpe) f[n + i] = (EA1 * P[i] / (1 + A01H01 * P[i])) * G[i] - M1 * G[i];                                     /* F/:2466 */
         f[2 * n + i] = p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i] - p->gmax * W[i] * P[i] / (W[i] + p->K1) - p->rW * W[i]
                      + (p->Dw) * (W[up] + W[dn] + W[lf] + W[rt] - 4 * W[i]);                                           /* R/:2464-2465 */
         f[3 * n + i] = p->a - p->alpha * (P[i] + p->K2 * p->W0) / (P[i] + p->K2) * O[i]
@@ -61,20 +77,25 @@ static void f_2dor_2sp(const tmo_cons_params *p, double *f, const double *Y)
 }
 
 /* RK4_Integrate_Stochastic_2Sp R/:2472-2527: one step in place on f[4][L*L] */
-int tmo_rk4_2sp(const tmo_cons_params *p, double *f)
+static int rk4_2sp(const tmo_cons_params *p, double *f, int fpe, double M1);
+int tmo_rk4_2sp(const tmo_cons_params *p, double *f) { return rk4_2sp(p, f, 0, 0.0); }
+/* RK4_Integrate_Stochastic_2Sp of Rietkerk_FPE, F/:2476-2531, over f_DorFKE_2Sp */
+int tmo_rk4_fpe_2sp(const tmo_cons_params *p, double M1, double *f) { return rk4_2sp(p, f, 1, M1); }
+
+static int rk4_2sp(const tmo_cons_params *p, double *f, int fpe, double M1)
 {
     if (!p || p->L < 1) return -1;
     const size_t n4 = (size_t)4 * p->L * p->L;
     const double dt2 = p->dt / 2.0, dt6 = p->dt / 6.0;                               /* R/:171 */
     double *K1 = malloc(sizeof(double) * n4 * 5), *K2 = K1 + n4, *K3 = K2 + n4, *K4 = K3 + n4, *Y = K4 + n4;
     if (!K1) return -1;
-    f_2dor_2sp(p, K1, f);
+    f_2dor_2sp(p, K1, f, fpe, M1);
     for (size_t i = 0; i < n4; i++) Y[i] = f[i] + (dt2) * K1[i];
-    f_2dor_2sp(p, K2, Y);
+    f_2dor_2sp(p, K2, Y, fpe, M1);
     for (size_t i = 0; i < n4; i++) Y[i] = f[i] + (dt2) * K2[i];
-    f_2dor_2sp(p, K3, Y);
+    f_2dor_2sp(p, K3, Y, fpe, M1);
     for (size_t i = 0; i < n4; i++) Y[i] = f[i] + (p->dt) * K3[i];
-    f_2dor_2sp(p, K4, Y);
+    f_2dor_2sp(p, K4, Y, fpe, M1);
     for (size_t i = 0; i < n4; i++) f[i] += (dt6) * (K1[i] + 2.0 * K2[i] + 2.0 * K3[i] + K4[i]);   /* R/:2506 */
     free(K1);
     return 0;

@@ -183,11 +183,8 @@ int emu_fke_move(const int *terms, double pref, double eps, const double *rho, c
     A.rho = rho; A.gamma = gamma; A.veff = veff; A.out = out;
     A.sA = sA.data(); A.sB = sB.data(); A.sD = sD.data(); A.disp = disp.data(); A.maxdisp = maxdisp;
     A.U1 = U1.data(); A.U2 = U2.data(); A.gD = gD; A.gV = gV;
-    emu_launch(fke_prepare_kernel, A, 3, 64, 0);
-    const int tiles = (A.t.L + kFkeThreads - 1) / kFkeThreads;
-    emu_launch(fke_cols_kernel, A, (unsigned)(tiles * A.t.L), kFkeThreads, fke_cols_smem_doubles(A.t) * sizeof(double));
-    emu_launch(fke_rows_kernel, A, (unsigned)(tiles * A.t.L), kFkeThreads,
-               (size_t)(A.t.bD + 1 + fke_max3(A.t.rlo, A.t.rhi, 0) + 1) * sizeof(double));
+    auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
+    fke_move_enqueue(launch, A);   // the product's launch shapes (tm_fke.cuh)
     maxdisp_out[0] = maxdisp[0]; maxdisp_out[1] = maxdisp[1];
     return 0;
 }
@@ -265,6 +262,37 @@ int emu_cons_step2(int L, const double *par2, const double *cpar, const int *cen
     auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
     for (int s = 0; s < nsteps; s++) cons_step2_enqueue(launch, k, b, seed, trial, step0 + (unsigned)s);
     if (b.state != fields) std::memcpy(fields, b.state, sizeof(double) * 4 * n);   // the fused RK4 ping-pongs state and ya
+    const double cells = (double)L * (double)L;
+    dyn_out[0] = dyn.sum_veg / cells; dyn_out[1] = dyn.sum_graz / cells; dyn_out[2] = dyn.occ_veg; dyn_out[3] = (double)dyn.eff;
+    return 0;
+}
+// The Rietkerk_FPE flavour of the same step (cons_step2_enqueue with k.fpe: the product's own orchestration).  fke = {bound_D, v_row_lo,
+// v_row_hi, v_col_lo, v_col_hi}; pref, eps: mu_vel_prefactor, epsilon; gD, gV: the grazer's stencils; M1: its mortality.  The clamp
+// constants are par2[5], par2[6] (1e-10 and 0 for the reference's runner).  veff is read, not written.
+int emu_cons_step2_fpe(int L, const double *par2, const double *cpar, const int *central, int n_central, unsigned long long seed,
+                       unsigned trial, unsigned step0, int nsteps, const double *u_veg, unsigned stride, const int *fke, double pref,
+                       double eps, const double *gD, const double *gV, double M1, double *fields, double *gamma, double *veff,
+                       double *dyn_out, unsigned long long *overflow, int rk4_stages)
+{
+    const size_t n = (size_t)L * L;
+    ConsConsts cc = cons_consts(cpar[0], cpar[1], cpar[2], cpar[3], cpar[4], cpar[5], cpar[6], cpar[7], cpar[8], cpar[9], cpar[10],
+                                cpar[11], cpar[12], cpar[13]);
+    cc.fpe = 1; cc.M1 = M1;
+    Step2Consts k = step2_consts(L, n_central, par2[12], par2[0], par2[1], par2[2], par2[3], par2[4], par2[5], par2[6], par2[7],
+                                 par2[8], par2[9], par2[10], par2[11], cc);
+    k.fpe = 1;
+    k.fke.L = L; k.fke.bD = fke[0]; k.fke.rlo = fke[1]; k.fke.rhi = fke[2]; k.fke.clo = fke[3]; k.fke.chi = fke[4]; k.fke.pref = pref; k.fke.eps = eps;
+    std::vector<double> star(2 * n), ya(4 * n), yb(4 * n), acc(4 * n), part(3 * kConsReduceBlocks);
+    Step2Dyn dyn{};
+    Step2Buffers b{};
+    b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.replay_veg = u_veg; b.replay_graz = u_veg; b.stride = stride; b.rk4_stages = rk4_stages;   // the grazer draws nothing in this flavour
+    b.fke_gD = gD; b.fke_gV = gV;
+    *overflow = 0;
+    auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
+    for (int s = 0; s < nsteps; s++) cons_step2_enqueue(launch, k, b, seed, trial, step0 + (unsigned)s);
+    if (b.state != fields) std::memcpy(fields, b.state, sizeof(double) * 4 * n);
     const double cells = (double)L * (double)L;
     dyn_out[0] = dyn.sum_veg / cells; dyn_out[1] = dyn.sum_graz / cells; dyn_out[2] = dyn.occ_veg; dyn_out[3] = (double)dyn.eff;
     return 0;

@@ -103,6 +103,11 @@ def oracle():
         L.tmo_step_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OGrazParams), C.POINTER(OConsParams), C.POINTER(C.c_int32), C.c_int,
                                    C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int]
         L.tmo_step_2sp_means.argtypes = L.tmo_step_2sp.argtypes + [dp]
+        L.tmo_step_fpe_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OConsParams), C.c_double, C.POINTER(OFkeTerms), dp, dp,
+                                       C.POINTER(C.c_int32), C.c_int, C.c_double, C.POINTER(ORng), dp, dp, dp, dp]
+        L.tmo_rk4_fpe_2sp.argtypes = [C.POINTER(OConsParams), C.c_double, dp]
+        L.tmo_gamma_perception_fpe.argtypes = [C.c_int, dp, C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, dp]
+        L.tmo_gamma_perception_fpe.restype = None
         L.tmo_dp_noise_off_step.argtypes = [C.c_int] + [C.c_double] * 5 + [dp]
         _lib = L
     return _lib
@@ -272,6 +277,30 @@ def step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=False, means=None
                                      C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0, None if m is None else ptr(m))
     assert rc == 0
     return veff
+
+
+def fpe_runner_params(L, par, derived):
+    """Oracle parameter blocks of the Rietkerk_FPE SPB = 2 runner from the vector of tests/golden/make_fpe_runner_golden.py
+    ({...runner2 vector..., dtAdv1}) and the constants set_global_FKE_params derived for the grazer
+    ({beta_vel, sigma_D, sigma_vD, mu_vel_prefactor, bound_D, bound_vD.first, bound_vD.second, epsilon}).
+    Returns (vegetation, RK4, M1, movement terms, gD, gV, disc radius, radius fraction)."""
+    pv, _, pc, R, fr = runner2_params(L, par[:23])
+    pv.clamp_eps, pv.clamp_lo = float(derived[7]), 0.0                       # F/:4458
+    bD, b1, b2 = int(derived[4]), int(derived[5]), int(derived[6])
+    terms = OFkeTerms(L, bD, b1, b2, b1, b2, float(derived[3]), float(derived[7]))   # CPU path: (.first, .second) on both axes, F/:3640
+    sigma1 = float(par[14])
+    return pv, pc, float(par[19]), terms, fke_gaussian(sigma1, bD), fke_gaussian(sigma1, b1), R, fr   # stencils: F/:3769-3771
+
+
+def step_fpe_2sp(pv, pc, M1, terms, gD, gV, central, fr, rng, f, gamma, veff=None, means=None):
+    """One Rietkerk_FPE SPB = 2 runner step (tmo_step_fpe_2sp) in place on f [4][L*L] and gamma [L*L]."""
+    cen = np.ascontiguousarray(central, dtype=np.int32)
+    if veff is None:
+        veff = np.zeros((pv.L * pv.L, 2))
+    m = None if means is None else np.array([means[0], means[1]], dtype=np.float64)
+    rc = oracle().tmo_step_fpe_2sp(C.byref(pv), C.byref(pc), M1, C.byref(terms), ptr(gD), ptr(gV), cen.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   len(cen), fr, C.byref(rng), ptr(f), ptr(gamma), ptr(veff), None if m is None else ptr(m))
+    assert rc == 0
 
 
 def dp_noise_off(L, a, b, D, dt, dx, rho, nsteps):

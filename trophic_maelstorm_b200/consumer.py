@@ -18,7 +18,7 @@ class GrazParams(C.Structure):
 
 CONS_ABI_SYMBOLS = ["tm_cons_create", "tm_cons_destroy", "tm_cons_last_error", "tm_cons_rk4_host", "tm_cons_gamma_host",
                     "tm_cons_grazer_dornic_host", "tm_cons_last_ms", "tm_cons_step2_setup", "tm_cons_step2_upload", "tm_cons_step2_run",
-                    "tm_cons_step2_replay", "tm_cons_step2_download", "tm_cons_step2_set_rk4_stages"]
+                    "tm_cons_step2_replay", "tm_cons_step2_download", "tm_cons_step2_set_rk4_stages", "tm_cons_step2_set_fpe"]
 
 _bound = False
 
@@ -42,6 +42,7 @@ def _lib():
             "tm_cons_step2_run": (i, [vp, C.c_uint64, C.c_uint32, C.c_uint32, i]),
             "tm_cons_step2_replay": (i, [vp, dp, dp, C.c_uint32]),
             "tm_cons_step2_set_rk4_stages": (i, [vp, i]),
+            "tm_cons_step2_set_fpe": (i, [vp, vp, dp, dp, C.c_double]),
             "tm_cons_step2_download": (i, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint64)]),
         }
         for name, (res, args) in sig.items():
@@ -124,6 +125,15 @@ class ConsumerOps:
 
     def step2_set_rk4_stages(self, on):
         self._ck(self._l.tm_cons_step2_set_rk4_stages(self._ctx, 1 if on else 0))
+
+    def step2_set_fpe(self, terms, gauss_D, gauss_V, M1):
+        """Rietkerk_FPE flavour of the step (tm_cons_step2_set_fpe); terms: fke.FkeTerms, or None for the Rietkerk_FD flavour."""
+        if terms is None:
+            self._ck(self._l.tm_cons_step2_set_fpe(self._ctx, None, None, None, 0.0))
+            return
+        gD, gV = np.ascontiguousarray(gauss_D, dtype=np.float64), np.ascontiguousarray(gauss_V, dtype=np.float64)
+        assert gD.size >= terms.n_gauss_D and gV.size >= terms.n_gauss_V
+        self._ck(self._l.tm_cons_step2_set_fpe(self._ctx, C.cast(C.byref(terms), C.c_void_p), _dptr(gD), _dptr(gV), float(M1)))
 
     def step2_run(self, seed, trial=0, step0=0, nsteps=1):
         self._ck(self._l.tm_cons_step2_run(self._ctx, seed, trial, step0, nsteps))

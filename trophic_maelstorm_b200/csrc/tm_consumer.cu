@@ -1,6 +1,7 @@
 // tm_consumer.cu -- C ABI (include/tm_consumer.h) over the consumer-side kernels (tm_consumer.cuh).  sm_100a only; no CPU path.
 #include "../../include/tm_consumer.h"
 #include "../../include/tm_lattice.h" // TM_E_* codes
+#include "../../include/tm_fke.h"     // tm_fke_terms
 #include "tm_consumer.cuh"
 
 #include <cuda_runtime.h>
@@ -27,6 +28,7 @@ struct tm_cons_ctx {
     double *d_star = nullptr, *d_veff = nullptr, *d_part = nullptr;
     Step2Dyn *d_dyn = nullptr;
     int *d_central = nullptr;
+    double *d_fke_gD = nullptr, *d_fke_gV = nullptr;   // FPE flavour: the grazer's movement stencils
     int n_launches = 0;
     std::string err;
 };
@@ -52,6 +54,7 @@ static Step2Buffers step2_buffers(tm_cons_ctx *c)
     b.state = c->d_state; b.star = c->d_star; b.ya = c->d_ya; b.yb = c->d_yb; b.acc = c->d_acc; b.gamma = c->d_gamma; b.veff = c->d_veff;
     b.part = c->d_part; b.dyn = c->d_dyn; b.central = c->d_central; b.overflow = c->d_ovf;
     b.rk4_stages = c->rk4_stages;
+    b.fke_gD = c->d_fke_gD; b.fke_gV = c->d_fke_gV;
     return b;
 }
 } // namespace
@@ -67,6 +70,7 @@ int tm_cons_destroy(tm_cons_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_state); cudaFree(c->d_ya); cudaFree(c->d_yb); cudaFree(c->d_acc); cudaFree(c->d_gamma); cudaFree(c->d_off); cudaFree(c->d_replay); cudaFree(c->d_ovf);
     cudaFree(c->d_star); cudaFree(c->d_veff); cudaFree(c->d_part); cudaFree(c->d_dyn); cudaFree(c->d_central);
+    cudaFree(c->d_fke_gD); cudaFree(c->d_fke_gV);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -246,6 +250,34 @@ int tm_cons_step2_setup(tm_cons_ctx *c, const tm_params *veg, const tm_graz_para
     return TM_OK;
 }
 
+int tm_cons_step2_set_fpe(tm_cons_ctx *c, const tm_fke_terms *t, const double *gauss_D, const double *gauss_V, double M1)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->step2_ready) { c->err = "tm_cons_step2_set_fpe: call tm_cons_step2_setup first"; return TM_E_ARG; }
+    if (!t) {                                      // back to the Rietkerk_FD flavour
+        c->k2.fpe = 0; c->k2.c.fpe = 0; c->k2.c.M1 = 0.0;
+        return TM_OK;
+    }
+    const int vmax = fke_max3(fke_max3(t->v_row_lo, t->v_row_hi, t->v_col_lo), t->v_col_hi, 0);
+    if (!gauss_D || !gauss_V || t->bound_D < 0 || t->v_row_lo < 0 || t->v_row_hi < 0 || t->v_col_lo < 0 || t->v_col_hi < 0 ||
+        t->bound_D > kFkeMaxBound || vmax > kFkeMaxBound || t->n_gauss_D < t->bound_D + 1 || t->n_gauss_V < vmax + 1) {
+        c->err = "tm_cons_step2_set_fpe: window bounds must lie in [0, 512] and the stencils must cover them";
+        return TM_E_ARG;
+    }
+    CONS_CK(cudaSetDevice(c->device));
+    CONS_CK(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_fke_gD); cudaFree(c->d_fke_gV); c->d_fke_gD = c->d_fke_gV = nullptr;
+    CONS_CK(cudaMalloc(&c->d_fke_gD, t->n_gauss_D * sizeof(double)));
+    CONS_CK(cudaMalloc(&c->d_fke_gV, t->n_gauss_V * sizeof(double)));
+    CONS_CK(cudaMemcpy(c->d_fke_gD, gauss_D, t->n_gauss_D * sizeof(double), cudaMemcpyHostToDevice));
+    CONS_CK(cudaMemcpy(c->d_fke_gV, gauss_V, t->n_gauss_V * sizeof(double), cudaMemcpyHostToDevice));
+    FkeTerms &f = c->k2.fke;
+    f.L = c->L; f.bD = t->bound_D; f.rlo = t->v_row_lo; f.rhi = t->v_row_hi; f.clo = t->v_col_lo; f.chi = t->v_col_hi;
+    f.pref = t->mu_vel_prefactor; f.eps = t->epsilon;
+    c->k2.fpe = 1; c->k2.c.fpe = 1; c->k2.c.M1 = M1;
+    return TM_OK;
+}
+
 int tm_cons_step2_set_rk4_stages(tm_cons_ctx *c, int on)
 {
     if (!c) return TM_E_ARG;
@@ -279,7 +311,7 @@ int tm_cons_step2_run(tm_cons_ctx *c, uint64_t seed, uint32_t trial, uint32_t st
     c->d_state = b.state; c->d_ya = b.ya;            // the fused RK4 ping-pongs the state between these two
     CONS_CK(cudaGetLastError());
     CONS_CK(cudaEventRecord(c->ev1, c->stream));
-    c->n_launches = step2_launches(b) * nsteps;
+    c->n_launches = step2_launches(b, c->k2.fpe) * nsteps;
     return TM_OK;
 }
 
@@ -303,7 +335,7 @@ int tm_cons_step2_replay(tm_cons_ctx *c, const double *u_veg, const double *u_gr
     c->d_state = b.state; c->d_ya = b.ya;
     CONS_CK(cudaGetLastError());
     CONS_CK(cudaEventRecord(c->ev1, c->stream));
-    c->n_launches = step2_launches(b);
+    c->n_launches = step2_launches(b, c->k2.fpe);
     CONS_CK(cudaStreamSynchronize(c->stream));   // the uniform arrays are the caller's again
     return TM_OK;
 }

@@ -23,6 +23,7 @@
 #pragma once
 #include <stdint.h>
 #include "tm_samplers.cuh"
+#include "tm_fke.cuh"      // the FPE flavour of the step moves the grazer with the FKE kernels
 #include <type_traits>
 #include <math.h>
 
@@ -49,8 +50,9 @@ struct Step2Dyn {
     double rho_inverse;                  // 1 / max(<veg>, 1e-12)                          R/:2548
     int eff;                             // disc offsets summed: int(fr^2 * new_length)    R/:2539, 2569
     int zero;                            // <grazer> or <veg> below 1e-12: gamma = 0       R/:2575-2578
-    int skip_graz;                       // <grazer> == 0: the grazer's Dornic loop is skipped, R/:3910
-    int pad_;
+    int skip_graz;                       // <grazer> == 0: the grazer's Dornic loop is skipped, R/:3910 (FPE flavour: always)
+    int one;                             // FPE flavour: <grazer> below 1e-12: gamma = 1           F/:2579
+    int maxdisp[2];                      // FPE flavour: largest |displacement| of the movement step (fke_prepare_kernel), zeroed every step
 };
 
 constexpr int kConsReduceThreads = 256;
@@ -95,6 +97,7 @@ struct FinalizeArgs {
     double fr;                   // pR[1] / (dx r_max_effective), R/:3409
     const double *part;
     Step2Dyn *dyn;
+    int fpe;                     // Rietkerk_FPE flavour: calc_gamma_vel_2Sp_NonRefugia F/:2534-2607
 };
 
 TMC_G void cons_finalize_kernel(const FinalizeArgs A)
@@ -117,14 +120,20 @@ TMC_G void cons_finalize_kernel(const FinalizeArgs A)
     double nR_fac = 1 - oc / (A.L * A.L);                             // R/:3822
     if (nR_fac < 0.35) nR_fac = 0.35;
     int new_length = (int)(nR_fac * nR_fac * A.n_central);            // R/:2539
-    if (new_length < 1) new_length = 1;
+    if (new_length < 1 && !A.fpe) new_length = 1;                     // R/:2540; the FPE twin has no such line (F/:2543)
     Step2Dyn d;
     d.sum_veg = sp; d.sum_graz = sg; d.occ_veg = oc;
     d.eff = (int)(A.fr * A.fr * new_length);                          // R/:2569
     d.rho_inverse = avg_veg >= eps ? 1 / avg_veg : 1 / eps;           // R/:2548
     d.zero = (avg_graz < eps || avg_veg < eps) ? 1 : 0;               // R/:2575-2578
     d.skip_graz = (avg_graz == 0.0) ? 1 : 0;                          // R/:3910
-    d.pad_ = 0;
+    d.one = 0;
+    if (A.fpe) {                                                      // F/:2578-2581: a vanished consumer gets gamma = 1
+        d.one = avg_graz < eps ? 1 : 0;
+        d.zero = (!d.one && avg_veg < eps) ? 1 : 0;
+        d.skip_graz = 1;                                              // the grazer has no Dornic update in Rietkerk_FPE: rho* = rho
+    }
+    d.maxdisp[0] = 0; d.maxdisp[1] = 0;
     *A.dyn = d;
 }
 
@@ -134,6 +143,7 @@ struct GammaArgs {
     const int *offsets;          // [eff][2] = {dx (rows), dy (columns)}
     double rho_inverse;          // 1 / max(<prey>, 1e-12)  (R/:2548)
     int zero;                    // <self> or <prey> below 1e-12: gamma = 0 everywhere (R/:2575-2578)
+    int one;                     // FPE flavour, <self> below 1e-12: gamma = 1 everywhere (F/:2579)
     double *gamma;               // [L*L] in/out
     const Step2Dyn *dyn;         // non-null: eff, rho_inverse and zero come from the device-side scalars of this step
                                  // (the launch reserves shared memory for `eff` offsets = the upper bound)
@@ -145,7 +155,7 @@ TMC_G void cons_gamma_kernel(const GammaArgs A_in)
     if (A.dyn) {
         const Step2Dyn d = *A.dyn;
         if (d.eff < A.eff) A.eff = d.eff;          // d.eff <= fr^2 n_central by construction
-        A.rho_inverse = d.rho_inverse; A.zero = d.zero;
+        A.rho_inverse = d.rho_inverse; A.zero = d.zero; A.one = d.one;
     }
     const int g = A.L, tid = threadIdx.x;
     const int tiles = (g + kConsThreads - 1) / kConsThreads;
@@ -156,6 +166,7 @@ TMC_G void cons_gamma_kernel(const GammaArgs A_in)
     __syncthreads();
     if (c_j >= g) return;
     const int i = c_i * g + c_j;
+    if (A.one) { A.gamma[i] = 1.0; return; }
     if (A.zero) { A.gamma[i] = 0.0; return; }
     double acc = A.gamma[i];
     for (int k = 0; k < A.eff; k++) {
@@ -252,6 +263,8 @@ TMC_G void grazer_dornic_kernel(const GrazerArgs A)
 struct ConsConsts {
     double dt, dt2, dt6;
     double a, cgmax, gmax, alpha, rW, K1, K2, K2W0, Dw, Do, A01, A01H01, EA1;
+    double M1;                   // FPE flavour: the grazer's mortality, in the reaction terms (f_DorFKE_2Sp F/:2466)
+    int fpe, pad_;
 };
 
 struct RkStageArgs {
@@ -273,6 +286,7 @@ TMC_D void cons_rhs(const ConsConsts &c, double P, double G, double W, double O,
 {
     f[0] = c.cgmax * W * P / (W + c.K1) - (c.A01 * P / (1 + c.A01H01 * P)) * G;
     f[1] = (c.EA1 * P / (1 + c.A01H01 * P)) * G;
+    if (c.fpe) f[1] = (c.EA1 * P / (1 + c.A01H01 * P)) * G - c.M1 * G;   // f_DorFKE_2Sp F/:2466
     f[2] = c.alpha * (P + c.K2W0) / (P + c.K2) * O - c.gmax * W * P / (W + c.K1) - c.rW * W + (c.Dw) * (Wu + Wd + Wl + Wr - 4 * W);
     f[3] = c.a - c.alpha * (P + c.K2W0) / (P + c.K2) * O + (c.Do) * (Ou + Od + Ol + Or_ - 4 * O);
 }
@@ -394,7 +408,9 @@ struct Step2Consts {
     DornicConsts veg;            // R/:3461-3463
     double dt, dx, D, v, M, sigma, D0floor;   // the grazer's (GrazerArgs)
     ConsConsts c;
-    double eps, lo;              // clamp R/:4176
+    double eps, lo;              // clamp R/:4176 (FPE flavour: 1e-10 and 0, F/:4458)
+    int fpe;                     // 0: rietkerk_Dornic_2D_MultiSp (Rietkerk_FD); 1: rietkerk_DorFPE_2D_MultiSp (Rietkerk_FPE), below
+    FkeTerms fke;                // FPE flavour: the grazer's movement windows (set_global_FKE_params F/:195)
 };
 
 struct Step2Buffers {
@@ -410,7 +426,27 @@ struct Step2Buffers {
     unsigned int stride;
     int rk4_stages;              // 1: the four-launch RK4 (kept as the cross-check); 0: cons_rk4_fused_kernel, which writes the
                                  // new state into `ya` -- cons_step2_enqueue then swaps `state` and `ya`
+    const double *fke_gD, *fke_gV;   // FPE flavour: the grazer's two Gaussian stencils (device)
 };
+
+// FPE flavour, last launch of a step: the moved grazer field replaces field 1, then `v < eps && v >= lo -> 0` on all four (F/:4458)
+struct FpeCommitArgs {
+    long long n;
+    double *state;               // [4][n]
+    const double *moved;         // [n]
+    double eps, lo;
+};
+
+TMC_G void cons_fpe_commit_kernel(const FpeCommitArgs A)
+{
+    const long long i = (long long)blockIdx.x * kConsThreads + threadIdx.x;
+    if (i >= A.n) return;
+    for (int s = 0; s < 4; s++) {
+        double v = s == 1 ? A.moved[i] : A.state[s * A.n + i];
+        if (v < A.eps && v >= A.lo) v = 0.0;
+        A.state[s * A.n + i] = v;
+    }
+}
 
 // The grazer's Philox streams use the seed with this constant xor-ed in, so that the two species of a cell draw from
 // different streams (the vegetation keeps the plain seed: its rho* equals the SPB = 1 step's for the same seed).
@@ -468,7 +504,7 @@ inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, Step2Buffe
     else        launch(grazer_dornic_kernel<false, true>, V, grid, kConsThreads, 0);
     ReduceArgs R{n, b.state, b.state + n, b.part};
     launch(cons_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 3 * kConsReduceThreads);
-    FinalizeArgs F{L, kConsReduceBlocks, k.n_central, k.fr, b.part, b.dyn};
+    FinalizeArgs F{L, kConsReduceBlocks, k.n_central, k.fr, b.part, b.dyn, k.fpe};
     launch(cons_finalize_kernel, F, 1, 32, sizeof(double) * 96);
     GammaArgs G{};
     G.L = L; G.eff = k.n_central; G.prey = b.state; G.offsets = b.central; G.gamma = b.gamma; G.dyn = b.dyn;
@@ -478,22 +514,35 @@ inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, Step2Buffe
     Z.seed = seed ^ kGrazerSeedSalt;
     if (replay) launch(grazer_dornic_kernel<true, false>, Z, grid, kConsThreads, 0);
     else        launch(grazer_dornic_kernel<false, false>, Z, grid, kConsThreads, 0);
+    // Rietkerk_FD clamps in the RK4 commit (R/:4176); Rietkerk_FPE moves the grazer first and clamps after (F/:4308, :4458)
     if (!b.rk4_stages) {
         RkFusedArgs F4{};
-        F4.L = L; F4.c = k.c; F4.base = b.state; F4.base_pg = b.star; F4.out = b.ya; F4.clamp = 1; F4.eps = k.eps; F4.lo = k.lo;
+        F4.L = L; F4.c = k.c; F4.base = b.state; F4.base_pg = b.star; F4.out = b.ya; F4.clamp = k.fpe ? 0 : 1; F4.eps = k.eps; F4.lo = k.lo;
         const int ft = (L + kFuseT - 1) / kFuseT;
         launch(cons_rk4_fused_kernel, F4, (unsigned)(ft * ft), kFuseThreads, sizeof(double) * 4 * kFuseS * kFuseS);
         double *t = b.state; b.state = b.ya; b.ya = t;
-        return;
+    } else {
+        RkStageArgs A{};
+        A.L = L; A.c = k.c; A.base = b.state; A.base_pg = b.star; A.acc = b.acc; A.out = b.state;
+        A.clamp = k.fpe ? 0 : 1; A.eps = k.eps; A.lo = k.lo;
+        A.stage = 1; A.Y = b.state; A.Ynext = b.ya; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+        A.stage = 2; A.Y = b.ya; A.Ynext = b.yb; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+        A.stage = 3; A.Y = b.yb; A.Ynext = b.ya; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+        A.stage = 4; A.Y = b.ya; A.Ynext = nullptr; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
     }
-    RkStageArgs A{};
-    A.L = L; A.c = k.c; A.base = b.state; A.base_pg = b.star; A.acc = b.acc; A.out = b.state;
-    A.clamp = 1; A.eps = k.eps; A.lo = k.lo;
-    A.stage = 1; A.Y = b.state; A.Ynext = b.ya; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
-    A.stage = 2; A.Y = b.ya; A.Ynext = b.yb; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
-    A.stage = 3; A.Y = b.yb; A.Ynext = b.ya; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
-    A.stage = 4; A.Y = b.ya; A.Ynext = nullptr; launch(cons_rk4_stage_kernel, A, grid, kConsThreads, 0);
+    if (!k.fpe) return;
+    // advdiff_FKE_MultiSp (F/:4308) on the grazer field the RK4 left: three launches (tm_fke.cuh), scratch in the buffers the RK4 is
+    // done with (yb: the three source masses and U1; acc: the moved field, U2, the displacements), then the commit + clamp
+    FkeArgs M{};
+    M.t = k.fke;
+    M.rho = b.state + n; M.gamma = b.gamma; M.veff = b.veff; M.out = b.acc;
+    M.sA = b.yb; M.sB = b.yb + n; M.sD = b.yb + 2 * n; M.U1 = b.yb + 3 * n; M.U2 = b.acc + n;
+    M.disp = reinterpret_cast<int *>(b.acc + 2 * n); M.maxdisp = b.dyn->maxdisp;
+    M.gD = b.fke_gD; M.gV = b.fke_gV;
+    fke_move_enqueue(launch, M);
+    FpeCommitArgs C{n, b.state, b.acc, k.eps, k.lo};
+    launch(cons_fpe_commit_kernel, C, (unsigned)((n + kConsThreads - 1) / kConsThreads), kConsThreads, 0);
 }
-inline int step2_launches(const Step2Buffers &b) { return b.rk4_stages ? 9 : 6; }
+inline int step2_launches(const Step2Buffers &b, int fpe = 0) { return (b.rk4_stages ? 9 : 6) + (fpe ? 4 : 0); }
 
 } // namespace tml

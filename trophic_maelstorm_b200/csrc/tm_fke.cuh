@@ -26,7 +26,7 @@
 #if defined(__CUDACC__)
 #define TMF_D __device__ __forceinline__
 #define TMF_HD __host__ __device__ inline
-#define TMF_G __global__
+#define TMF_G static __global__   // static: tm_fke.cu and tm_consumer.cu (the FPE flavour of the step) each compile their own copy
 #define TMF_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #else
 #include "tm_cpu_emu.h" // tests/emu only: runs the same source on host threads
@@ -190,6 +190,19 @@ TMF_G void fke_rows_kernel(const FkeArgs A)
         xs = xs == 0 ? g - 1 : xs - 1;
     }
     A.out[x * g + y] = acc;
+}
+
+// the three launches of one species' movement step (host side; shared by tm_fke.cu, the FPE flavour of the consumer stepper and
+// tests/emu): launch(kernel, args, grid, block, dynamic shared bytes).  A.maxdisp must hold zeros on entry.
+template <class Launch>
+inline void fke_move_enqueue(Launch &&launch, const FkeArgs &A)
+{
+    const int L = A.t.L;
+    const int tiles = (L + kFkeThreads - 1) / kFkeThreads;
+    launch(fke_prepare_kernel, A, (unsigned)L, 256, 0);   // one CTA per lattice row
+    launch(fke_cols_kernel, A, (unsigned)((long long)tiles * L), kFkeThreads, fke_cols_smem_doubles(A.t) * sizeof(double));
+    launch(fke_rows_kernel, A, (unsigned)((long long)tiles * L), kFkeThreads,
+           (size_t)(A.t.bD + 1 + fke_max3(A.t.rlo, A.t.rhi, 0) + 1) * sizeof(double));
 }
 
 } // namespace tml

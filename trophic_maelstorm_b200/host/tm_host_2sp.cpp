@@ -1,6 +1,8 @@
 // tm_host_2sp.cpp -- see tm_host_2sp.h.  All numerics run in libtm_lattice.so (tm_cons_step2_*); this file is bookkeeping.
 #include "tm_host_2sp.h"
 #include "tm_host.h"
+#include "tm_host_fke.h"
+#include "../../include/tm_fke.h"
 #include "../../include/tm_consumer.h"
 #include "../../include/tm_lattice.h"
 
@@ -77,14 +79,18 @@ double mean_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i
 double occupied_sites_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i = 0; i < n; ++i) if (x[i] > 0) s += 1; return s; }   // R/:1245
 } // namespace
 
-void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
-                                double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
-                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
-                                double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
-                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+namespace {
+// The two replicate runners share everything but the device step: fpe == false: rietkerk_Dornic_2D_MultiSp (Rietkerk_FD, R/:3397);
+// fpe == true: rietkerk_DorFPE_2D_MultiSp (Rietkerk_FPE, F/:3697), whose step moves the grazer with the FKE kernels instead of a
+// Dornic update and clamps at epsilon = 1e-10 (F/:4458).
+void run_2sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, double c, double gmax,
+             double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
+             double sigma[], double a_c, double (&A)[SpB][SpB],
+             double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
+             double clow[], double dt, double dx, double dP, int r, int g)
 {
     if (!init_frame) throw std::runtime_error("tm_b200::spb2::init_frame is not set");
-    if (dtV[1] != 1 && dtV[1] != 0) throw std::runtime_error("spb2 runner: only dtV[1] == 1 (grazer updated every step) is built");
+    if (!fpe && dtV[1] != 1 && dtV[1] != 0) throw std::runtime_error("spb2 runner: only dtV[1] == 1 (grazer updated every step) is built");
     const int tot_iter = (int)t_meas.size();
     const double t_end = t_meas.back();                                               // R/:3439
     const size_t n = (size_t)g * g;
@@ -100,6 +106,7 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     veg.model = TM_MODEL_RIETKERK; veg.L = g; veg.dt = dt; veg.dx = dx; veg.a = a;
     veg.rc = c; veg.gmax = gmax; veg.alpha = alpha; veg.rW = rW; veg.W0 = W0; veg.d = M[0]; veg.K1 = K[1]; veg.K2 = K[2];
     veg.D0 = D[0]; veg.D1 = D[2]; veg.D2 = D[3]; veg.sigma0 = sigma[0]; veg.clamp_eps = 1.0e-12; veg.clamp_lo = -1.0e-80;   // R/:4176
+    if (fpe) { veg.clamp_eps = fke_globals().epsilon; veg.clamp_lo = 0.0; }                                                 // F/:4458
     tm_graz_params pg{};
     pg.L = g; pg.dt = dt; pg.dx = dx; pg.D = D[1]; pg.v = v[1]; pg.M = M[1]; pg.sigma = sigma[1]; pg.D0_floor = D[0] / (dx * dx);   // R/:4014
     tm_cons_params pc{};
@@ -109,6 +116,19 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     Ctx ctx;
     if (tm_cons_create(g, current_device(), &ctx.c) != 0) throw std::runtime_error(std::string("tm_cons_create: ") + tm_cons_last_error(nullptr));
     ctx.ck(tm_cons_step2_setup(ctx.c, &veg, &pg, &pc, central.data(), (int)nb.size(), fr_graz), "tm_cons_step2_setup");
+    if (fpe) {
+        // the grazer's movement windows and stencils as the runner builds them (F/:3760-3772) from set_global_FKE_params' globals
+        const FKEGlobals &G = fke_globals();
+        if (G.SpB != SpB || G.L != g) throw std::runtime_error("rietkerk_DorFPE_2D_MultiSp: call set_global_FKE_params(D, v, dtAdv, Dt, dx, g) first");
+        const vector<double> gD = precompute_gaussian(sigma[1], G.sig_D_ScaledBounds[1]);
+        const vector<double> gV = precompute_gaussian(sigma[1], G.sig_vD_ScaledBounds[1].first);
+        tm_fke_terms t{};
+        t.bound_D = G.sig_D_ScaledBounds[1];
+        t.v_row_lo = t.v_col_lo = G.sig_vD_ScaledBounds[1].first; t.v_row_hi = t.v_col_hi = G.sig_vD_ScaledBounds[1].second;   // CPU path, F/:3640-3641
+        t.n_gauss_D = (int)gD.size(); t.n_gauss_V = (int)gV.size();
+        t.mu_vel_prefactor = G.mu_vel_prefactor[1]; t.epsilon = G.epsilon;
+        ctx.ck(tm_cons_step2_set_fpe(ctx.c, &t, gD.data(), gV.data(), M[1]), "tm_cons_step2_set_fpe");
+    }
 
     D2Vec_Double rho_rep_avg_var(tot_iter, vector<double>(W_, 0.0));
     for (int i = 0; i < tot_iter; i++) rho_rep_avg_var[i][0] = t_meas[i];            // R/:3484-3487
@@ -159,15 +179,36 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     }
 }
 
+} // namespace
+
+void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
+                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
+                                double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
+                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+{
+    run_2sp(false, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g);
+}
+
+void rietkerk_DorFPE_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
+                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
+                                double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
+                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+{
+    run_2sp(true, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g);
+}
+
 const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"
                                  " # Active Sites P(x; t), <<G(x; t)>_x>_r, Var[<G(x; t)>_x]_r, # Surviving Runs G(x; t), # Active Sites G(x; t), \n";
 
-void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
-                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
-                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
-                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
-                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
-                                                       double Gstar, double Vstar)
+namespace {
+void sweep_2sp(bool fpe, int div, double t_max, double a_start, double a_end, double a_c, double c,
+               double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+               double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+               double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+               int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+               double Gstar, double Vstar)
 {
     vector<double> a_space = linspace(a_start, a_end, div);
     vector<double> t_measure = logarithm10_time_bins(t_max, 1 * dt);
@@ -175,21 +216,23 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
     std::sort(t_measure.begin(), t_measure.end());
     t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
     D2Vec_Double vec;
-    for (size_t i = 0; i < a_space.size(); i++) {                                   // a-values in order (OpenMP threads in the reference, R/:4509)
-        D2Vec_Double rows;
-        rietkerk_Dornic_2D_MultiSp(rows, t_measure, t_max, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_start, a_end, a_c, A, H, E, M,
-                                   pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
-        vec.insert(vec.end(), rows.begin(), rows.end());
-    }
+    vector<D2Vec_Double> per_a(a_space.size());
+    for_each_on_devices((int)a_space.size(), [&](int i) {   // the reference's `omp for` over a-values (R/:4509, F/:4795): one GPU per a-value at a time
+        vector<double> tm_i = t_measure;
+        run_2sp(fpe, per_a[i], tm_i, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g);
+    });
+    for (const D2Vec_Double &rows : per_a) vec.insert(vec.end(), rows.begin(), rows.end());
     std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;
     L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r;
     Dm1 << std::setprecision(3) << D[1]; dix << std::setprecision(2) << dx; geq << std::setprecision(5) << Gstar; veq << std::setprecision(5) << Vstar;
-    const std::string dir = options().data_root + "/Data/Rietkerk/Stochastic/2Sp";
+    // Rietkerk_FD's header default: "../Data/Rietkerk/Stochastic/2Sp/1stCC_Rietkerk_<prefix>_P_c_G_"; Rietkerk_FPE's set_Prefix (F/:143-165):
+    // "../Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_"
+    const std::string dir = options().data_root + (fpe ? "/Data/Rietkerk/Stochastic" : "/Data/Rietkerk/Stochastic/2Sp");
     std::string path;
     for (size_t k = 1; k <= dir.size(); k++)                                         // mkdir -p
         if (k == dir.size() || dir[k] == '/') { path = dir.substr(0, k); mkdir(path.c_str(), 0777); }
-    std::string savefile = dir + "/1stCC_Rietkerk_" + prefix + "_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
-                         + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str();                                    // R/:4582
+    std::string savefile = dir + (fpe ? "/1stOrderCC_Rietkerk_" : "/1stCC_Rietkerk_") + prefix + "_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
+                         + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str();                                    // R/:4582, F/:4852
     if (Gstar != -1) savefile += "_Geq_" + geq.str() + "_R_" + rini.str() + ".csv";
     else if (Vstar != -1) savefile += "_Veq_" + veq.str() + "_R_" + rini.str() + ".csv";
     else savefile += "_R_" + rini.str() + ".csv";
@@ -199,6 +242,27 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
         for (size_t j = 0; j + 1 < vec[i].size(); j++) out << std::setprecision(16) << vec[i][j] << ",";
         out << std::setprecision(16) << vec[i][vec[i].size() - 1] << std::endl;
     }
+}
+} // namespace
+
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar, double Vstar)
+{
+    sweep_2sp(false, div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, v, K, sigma, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
+}
+
+void first_order_critical_exp_delta_stochastic_MultiSp_FPE(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                           double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                           double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                           double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                           int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                           double Gstar, double Vstar)
+{
+    sweep_2sp(true, div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, v, K, sigma, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
 }
 
 }} // namespace tm_b200::spb2

@@ -12,6 +12,7 @@
 // (R/:3710-3716), the replicate-order running mean/variance with the integer 1/(r-1) (R/:1325), and the row layout
 // {a, r, L, t, <W>, <O>, then per living species <rho>, var, #surviving, #active} (R/:4361-4372).  Not carried over: the
 // runner's CSV side outputs (frames, prelim tables, movement averages Rho_Mov) -- the SPB = 1 layer has those writers.
+// The Rietkerk_FPE runner of the same model (rietkerk_DorFPE_2D_MultiSp) is here too: same bookkeeping, different device step.
 #pragma once
 #include <functional>
 #include <string>
@@ -40,7 +41,27 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, 
                                 double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
                                 int g, double Gstar = -1.0, double Vstar = -1.0);
 
-// The a-sweep driver entry, R/:4379-4617 compiled with -DSPB=2: runner per a-value, one CSV
+// The Rietkerk_FPE twin, Rietkerk_FPE/rietkerk_bjork_FKE.cpp:3697 compiled with -DSPB=2: same signature, same bookkeeping; its device
+// step (tm_cons_step2_set_fpe) has no grazer Dornic update, carries the grazer's mortality in the RK4 reaction terms, moves the
+// grazer with the FKE kernels on the device-resident field (the reference's -DBARRACUDA seam copies three fields to the device and
+// one back every step, F/:4282-4299) and clamps at epsilon = 1e-10.  Call tm_b200::set_global_FKE_params (tm_host_fke.h) first, as
+// the reference's drivers do (order_2stoc_unity_rietkerk.cpp:202): the movement windows and stencils come from its globals.
+void rietkerk_DorFPE_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c,
+                                double gmax, double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB],
+                                double (&K)[3], double sigma[], double a_st, double a_end, double a_c,
+                                double (&A)[SpB][SpB], double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB],
+                                double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
+                                int g, double Gstar = -1.0, double Vstar = -1.0);
+// its a-sweep (first_order_critical_exp_delta_stochastic_MultiSp of Rietkerk_FPE, F/:4665): CSV
+// "<data_root>/Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_<L>_T_..._R_<r>.csv" (set_Prefix F/:143-165)
+void first_order_critical_exp_delta_stochastic_MultiSp_FPE(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                           double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                           double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                           double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                           int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                           double Gstar = -1.0, double Vstar = -1.0);
+
+// The a-sweep driver entry, R/:4379-4617 compiled with -DSPB=2 (a-values dealt over the visible GPUs, tm_host.h): runner per a-value, one CSV
 // "<data_root>/Data/Rietkerk/Stochastic/2Sp/1stCC_Rietkerk_<prefix>_P_c_G_<L>_T_<T>_dt_..._R_<r>.csv" with the reference's
 // 2Sp header (rietkerk_bjork_constants_2Sp.h:10-11) and 16-digit rows.
 extern const std::string prelimheader;

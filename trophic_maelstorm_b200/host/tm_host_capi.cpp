@@ -314,4 +314,44 @@ int tmh_riet2_sweep(int L, const double *par, int div, double t_max, double a_st
     } catch (const std::exception &e) { fprintf(stderr, "tmh_riet2_sweep: %s\n", e.what()); return -2; }
     return 0;
 }
+
+// Rietkerk_FPE, SPB = 2: rietkerk_DorFPE_2D_MultiSp (sweep != 0: its a-sweep over [a_start, a_end] in `div` values, CSV under data_root).
+// par = the tmh_riet2_run vector plus par[23] = dtAdv[1]; set_global_FKE_params is called as the reference's driver does
+// (order_2stoc_unity_rietkerk.cpp:202, CI = 4, Dt_analytic = dt).  rows_out / frames_out as tmh_riet2_run (ignored by the sweep).
+int tmh_fpe2_run(int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
+                 double *rows_out, int cap, double *frames_out, int sweep, int div, double a_start, double a_end)
+{
+    namespace s2 = tm_b200::spb2;
+    double D[s2::Sp] = {par[9], par[10], par[11], par[12]};
+    double K[3] = {0.0, par[7], par[8]};
+    double sigma[s2::Sp] = {par[13], par[14], 0, 0};
+    double v[s2::SpB] = {0, par[15]};
+    double A[s2::SpB][s2::SpB] = {{0, par[16]}, {par[16], 0}}, H[s2::SpB][s2::SpB] = {{0, par[17]}, {par[17], 0}};
+    double E[s2::SpB] = {1.0, par[18]}, M[s2::SpB] = {par[6], par[19]}, pR[s2::Sp] = {0.0, par[20]};
+    double dtAdv[s2::SpB] = {0.0, par[23]};
+    int dtV[s2::SpB] = {0, 1};
+    double clow[2 * s2::Sp] = {0, 1, 1, 1, 5, 1, 1, 1};
+    const size_t n4 = (size_t)4 * L * L;
+    s2::init_frame = [=](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + (size_t)(j % n_init) * n4, n4 * sizeof(double)); };
+    if (frames_out && !sweep)
+        s2::on_measure = [=](int j, int index, double, const double *f) { memcpy(frames_out + ((size_t)j * n_tmeas + index) * n4, f, n4 * sizeof(double)); };
+    else s2::on_measure = nullptr;
+    s2::D2Vec_Double Rho;
+    try {
+        set_global_FKE_params(D, v, dtAdv, par[21], par[22], L, 4);
+        if (sweep) {
+            s2::first_order_critical_exp_delta_stochastic_MultiSp_FPE(div, t_meas[n_tmeas - 1], a_start, a_end, 1.0 / 24.0, par[1], par[2], par[3], par[4],
+                                                                      par[5], D, v, K, sigma, A, H, E, M, pR, dtV, clow, par[21], par[22], 10000.0, r, L);
+            return 0;
+        }
+        std::vector<double> tm(t_meas, t_meas + n_tmeas);
+        s2::rietkerk_DorFPE_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+                                       1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[21], par[22], 10000.0, r, L);
+    } catch (const std::exception &e) { fprintf(stderr, "tmh_fpe2_run: %s\n", e.what()); s2::on_measure = nullptr; return -2; }
+    s2::on_measure = nullptr;
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 14; j++) rows_out[14 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
+    return (int)Rho.size();
+}
 }
