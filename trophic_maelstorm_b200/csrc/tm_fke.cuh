@@ -79,8 +79,13 @@ TMF_G void fke_prepare_kernel(const FkeArgs A)
                 a = gm2 * r; b = (gm - gm2) * r; d = (1 - gm) * (1 - gm) * r;
                 // (int)(round(c + v * prefactor) + g) % g in the reference; a true modulo here (the reference indexes
                 // out of bounds when the left side is negative, i.e. for |v * prefactor| > L)
-                const int mu_x = fke_mod((int)(round(c_i + A.veff[2 * i] * A.t.pref) + g), g);
-                const int mu_y = fke_mod((int)(round(c_j + A.veff[2 * i + 1] * A.t.pref) + g), g);
+                // a non-finite or absurd shift (|v * prefactor| >= 1e9 cells: the reference's int conversion is undefined there)
+                // moves nothing instead of indexing from garbage
+                double sx = A.veff[2 * i] * A.t.pref, sy = A.veff[2 * i + 1] * A.t.pref;
+                if (!(sx > -1.0e9 && sx < 1.0e9)) sx = 0.0;
+                if (!(sy > -1.0e9 && sy < 1.0e9)) sy = 0.0;
+                const int mu_x = fke_mod((int)(round(c_i + sx) + g), g);
+                const int mu_y = fke_mod((int)(round(c_j + sy) + g), g);
                 ex = mu_x - c_i; ey = mu_y - c_j;                    // representative in [-(g-1)/2, g/2]
                 if (ex > g / 2) ex -= g; else if (ex < -((g - 1) / 2)) ex += g;
                 if (ey > g / 2) ey -= g; else if (ey < -((g - 1) / 2)) ey += g;

@@ -90,7 +90,11 @@ void run_2sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, doub
              double clow[], double dt, double dx, double dP, int r, int g)
 {
     if (!init_frame) throw std::runtime_error("tm_b200::spb2::init_frame is not set");
-    if (!fpe && dtV[1] != 1 && dtV[1] != 0) throw std::runtime_error("spb2 runner: only dtV[1] == 1 (grazer updated every step) is built");
+    // dtV[s] (the drivers' round(dtv/dt), R/ order_2stoc_test_rietkerk.cpp): in the two-species runners as shipped it only feeds
+    // dtV_counter (R/:3637-3654), which is read by the three-species perception functions (R/:3212, 3324) and by the -DLOCUST_WIND
+    // build's direction sampling (R/:3972-3990).  Without that macro the direction is drawn at every step (R/:3992-3995), so any
+    // dtV gives the same two-species run: accepted and unused here, as there.
+    (void)dtV;
     const int tot_iter = (int)t_meas.size();
     const double t_end = t_meas.back();                                               // R/:3439
     const size_t n = (size_t)g * g;

@@ -12,6 +12,8 @@
 // (R/:3710-3716), the replicate-order running mean/variance with the integer 1/(r-1) (R/:1325), and the row layout
 // {a, r, L, t, <W>, <O>, then per living species <rho>, var, #surviving, #active} (R/:4361-4372).  Not carried over: the
 // runner's CSV side outputs (frames, prelim tables, movement averages Rho_Mov) -- the SPB = 1 layer has those writers.
+// dtV[s] is accepted and has no effect, as in the reference's two-species build (only its -DLOCUST_WIND variant and the three-species
+// perception functions read the counter it feeds).
 // The Rietkerk_FPE runner of the same model (rietkerk_DorFPE_2D_MultiSp) is here too: same bookkeeping, different device step.
 #pragma once
 #include <functional>
