@@ -812,6 +812,60 @@ int tmo_step_2sp_means(const tmo_params *pveg, const tmo_graz_params *pg, const 
     return 0;
 }
 
+/* One time step of the SPB = 3 runner (vegetation + grazer + predator), rietkerk_Dornic_2D_MultiSp compiled with -DSPB=3, R/:3752-4183:
+ * vegetation Dornic -> means of DRho[0..2] and the vegetation cover (R/:3813-3824) -> calc_gamma_3Sp_NonRefugia (R/:3850) -> the
+ * consumers' Dornic loop for s = 1, 2 (R/:3908-4114; a species with <rho> == 0 is skipped, R/:3910) -> RK4_Integrate_Stochastic_MultiSp
+ * (R/:4135) -> clamp (R/:4176).  Per-cell streams: the grazer's and the predator's keys are the seed xor 0x9E3779B97F4A7C15 and
+ * 0xD1B54A32D192ED03 (PHILOX); their replay slices follow the vegetation's (REPLAY).  SEQ: the reference's single generator. */
+int tmo_step_3sp(const tmo_params *pveg, const tmo_graz_params *pg1, const tmo_graz_params *pg2, const tmo_cons3_params *pc,
+                 const int32_t *central, int n_central, double fr1, double fr2, tmo_rng *rng, double *f, double *gamma, double *veff,
+                 int trig_libm, const double *means)
+{
+    if (!pveg || !pg1 || !pg2 || !pc || pveg->L != pg1->L || pveg->L != pg2->L || pveg->L != pc->L) return -1;
+    const int L = pveg->L;
+    const int64_t n = (int64_t)L * L;
+    double *work = malloc(sizeof(double) * (size_t)n * 12);
+    if (!work) return -1;
+    double *D = work, *vtmp = work + 5 * n, *cout_ = work + 9 * n, *vout = work + 11 * n;   /* DRho copy, v_eff x2, rho* of G and Pr, rho*_P */
+    memcpy(D, f, sizeof(double) * (size_t)n * 5);
+    dornic_consts k;
+    derive_consts(pveg, &k);
+    dornic_sweep(pveg, &k, rng, D, vout);                                               /* vegetation, R/:3752-3809 */
+    double avg[3];
+    for (int s = 0; s < 3; s++) avg[s] = means ? means[s] : tmo_mean(D + s * n, n);      /* R/:3813-3818 */
+    const double num_veg = tmo_occupied(D, n);
+    double nR_fac = 1 - num_veg / (L * L);                                              /* R/:3822 */
+    if (nR_fac < 0.35) nR_fac = 0.35;
+    int new_length = (int)(nR_fac * nR_fac * n_central);                                /* R/:3162 */
+    if (new_length < 1) new_length = 1;
+    tmo_gamma_3sp(L, D, D + n, D + 2 * n, central, new_length, fr1, fr2, avg, gamma, gamma + n);   /* R/:3850 */
+    const tmo_graz_params *pg[3] = {NULL, pg1, pg2};
+    const uint64_t salt[3] = {0, 0x9E3779B97F4A7C15ull, 0xD1B54A32D192ED03ull};
+    for (int s = 1; s <= 2; s++) {
+        double *out = cout_ + (s - 1) * n, *ve = veff ? veff + 2 * (s - 1) * n : vtmp + 2 * (s - 1) * n;
+        if (avg[s] == 0.0) { memcpy(out, D + s * n, sizeof(double) * (size_t)n); continue; }   /* R/:3910 */
+        if (rng->kind == TMO_SRC_SEQ) {
+            if (tmo_grazer_dornic(pg[s], rng, D + s * n, gamma + (s - 1) * n, out, ve, trig_libm)) { free(work); return -1; }
+        } else {
+            tmo_rng gr = *rng;
+            gr.overflow = 0; gr.draws = 0;
+            if (rng->kind == TMO_SRC_REPLAY) {
+                const uint64_t skip = (uint64_t)s * n * rng->stride;
+                gr.u = rng->u + skip; gr.n_u = rng->n_u > skip ? rng->n_u - skip : 0;
+            } else gr.seed = rng->seed ^ salt[s];
+            if (tmo_grazer_dornic(pg[s], &gr, D + s * n, gamma + (s - 1) * n, out, ve, trig_libm)) { free(work); return -1; }
+            rng->overflow += gr.overflow; rng->draws += gr.draws;
+        }
+    }
+    memcpy(f, vout, sizeof(double) * (size_t)n);
+    memcpy(f + n, cout_, sizeof(double) * (size_t)n * 2);
+    if (tmo_rk4_3sp(pc, f)) { free(work); return -1; }                                  /* R/:4135 */
+    for (int64_t i = 0; i < 5 * n; i++)
+        if (f[i] < pveg->clamp_eps && f[i] >= pveg->clamp_lo) f[i] = 0.0;               /* R/:4176 */
+    free(work);
+    return 0;
+}
+
 /* One time step of the Rietkerk_FPE runner compiled with -DSPB=2, rietkerk_DorFPE_2D_MultiSp F/:4094-4462 (see tm_oracle.h). */
 int tmo_step_fpe_2sp(const tmo_params *pveg, const tmo_cons_params *pc, double M1, const tmo_fke_terms *ft, const double *gD,
                      const double *gV, const int32_t *central, int n_central, double fr_graz, tmo_rng *rng, double *f, double *gamma,

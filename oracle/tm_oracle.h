@@ -185,6 +185,27 @@ int tmo_step_2sp(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_co
 int tmo_step_2sp_means(const tmo_params *pveg, const tmo_graz_params *pg, const tmo_cons_params *pc, const int32_t *central, int n_central,
                        double fr_graz, tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm, const double *means);
 
+
+/* ---- the SPB = 3 model (vegetation + grazer + predator): fields [0]=P, [1]=G, [2]=Pr, [3]=W, [4]=O -----------------
+ * f_2Dor_3Sp R/:2607-2650, RK4_Integrate_Stochastic_MultiSp R/:2652-2720, calc_gamma_3Sp_NonRefugia R/:3153-3268, and the time-loop
+ * body of rietkerk_Dornic_2D_MultiSp compiled with -DSPB=3 (R/:3752-4183: the consumers' Dornic loop R/:3908-4114 runs for s = 1, 2). */
+typedef struct tmo_cons3_params {
+    int32_t L, pad_;
+    double dt, a, c, gmax, alpha, rW, W0, K1, K2;
+    double Dw, Do;                 /* Dxd2[3], Dxd2[4] = D[s]/dx^2 of soil and surface water */
+    double A01, H01, E1;           /* A[0][1], H[0][1], E[1]: grazer on vegetation */
+    double A12, H12, E2;           /* A[1][2], H[1][2], E[2]: predator on grazer */
+} tmo_cons3_params;
+/* veg, graz, pred: DRho[0..2]; offsets: the distance-sorted disc list; new_length: its prefix after the vegetation-cover cut (R/:3162);
+ * fr1, fr2: the two radius fractions; avg[3]: spatial means; gamma1, gamma2 [L*L]: OUT (assigned, not accumulated: R/:3239, 3248) */
+void tmo_gamma_3sp(int L, const double *veg, const double *graz, const double *pred, const int32_t *offsets, int new_length,
+                   double fr1, double fr2, const double *avg, double *gamma1, double *gamma2);
+int tmo_rk4_3sp(const tmo_cons3_params *p, double *f);
+/* one time step on f[5][L*L]; gamma [2][L*L] (grazer, predator); veff (may be NULL) [2][L*L][2]; means (may be NULL): {<P>, <G>, <Pr>} */
+int tmo_step_3sp(const tmo_params *pveg, const tmo_graz_params *pg1, const tmo_graz_params *pg2, const tmo_cons3_params *pc,
+                 const int32_t *central, int n_central, double fr1, double fr2, tmo_rng *rng, double *f, double *gamma, double *veff,
+                 int trig_libm, const double *means);
+
 #ifdef __cplusplus
 }
 #endif

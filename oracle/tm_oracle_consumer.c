@@ -100,3 +100,94 @@ static int rk4_2sp(const tmo_cons_params *p, double *f, int fpe, double M1)
     free(K1);
     return 0;
 }
+
+
+/* ==================================================================================================================== */
+/* SPB = 3: vegetation + grazer + predator                                                                              */
+/* ==================================================================================================================== */
+/* calc_gamma_3Sp_NonRefugia R/:3153-3268.  The caller passes new_length = max(1, int(nVeg_frac^2 * size)) (R/:3162-3163). */
+void tmo_gamma_3sp(int L, const double *veg, const double *graz, const double *pred, const int32_t *offsets, int new_length,
+                   double fr1, double fr2, const double *avg, double *gamma1, double *gamma2)
+{
+    const double eps = 1.0e-12;                                                      /* R/:3160 */
+    double rho_inverse[3];
+    for (int s = 0; s < 3; s++) rho_inverse[s] = avg[s] >= eps ? 1 / avg[s] : 1 / eps;   /* R/:3171-3172 */
+    const double fr[3] = {0.0, fr1, fr2};
+    double *gam[3] = {NULL, gamma1, gamma2};
+    const double *fld[3] = {veg, graz, pred};
+    for (int i = 0; i < L * L; i++) {
+        const int c_i = i / L, c_j = i % L;
+        for (int s = 1; s <= 2; s++) {                                               /* the order of rfrac does not matter */
+            if (fr[s] == 0.0) continue;                                              /* R/:3201 */
+            int eff = (int)(fr[s] * fr[s] * new_length);                             /* R/:3199 */
+            if (eff < 1 && fr[s] > 0) eff = 1;                                       /* R/:3204 */
+            if (avg[s] < eps) { gam[s][i] = 0.0; continue; }                         /* R/:3206 */
+            else if (avg[s - 1] < eps) { gam[s][i] = 0.0; continue; }                /* R/:3208 */
+            double gamma_sum = 0.0;
+            const double *prey = fld[s - 1];
+            if (s == 1) {
+                if (avg[2] < eps) {                                                  /* no predators left, R/:3221 */
+                    for (int k = 0; k < eff; k++) {
+                        const int nx = (c_i + offsets[2 * k] + L) % L, ny = (c_j + offsets[2 * k + 1] + L) % L;
+                        gamma_sum += prey[nx * L + ny];
+                    }
+                } else {
+                    for (int k = 0; k < eff; k++) {                                  /* R/:3232: vegetation discounted by the predators there */
+                        const int nx = (c_i + offsets[2 * k] + L) % L, ny = (c_j + offsets[2 * k + 1] + L) % L;
+                        gamma_sum += prey[nx * L + ny] * (1 - pred[nx * L + ny] * rho_inverse[2]);
+                    }
+                }
+                gam[s][i] = (gamma_sum * rho_inverse[s - 1]) / (eff);                /* R/:3239 */
+            } else {
+                for (int k = 0; k < eff; k++) {
+                    const int nx = (c_i + offsets[2 * k] + L) % L, ny = (c_j + offsets[2 * k + 1] + L) % L;
+                    gamma_sum += prey[nx * L + ny];
+                }
+                gam[s][i] = (gamma_sum / (eff)) * rho_inverse[s - 1];                /* R/:3248 */
+            }
+            if (gam[s][i] > 1) gam[s][i] = 1.0;                                      /* R/:3251-3254 */
+            else if (gam[s][i] < 0) gam[s][i] = 0.0;
+        }
+    }
+}
+
+/* f_2Dor_3Sp R/:2607-2650 */
+static void f_2dor_3sp(const tmo_cons3_params *p, double *f, const double *Y)
+{
+    const int g = p->L, n = g * g;
+    const double cgmax = p->c * p->gmax, K2W0 = p->K2 * p->W0, A01H01 = p->A01 * p->H01, A12H12 = p->A12 * p->H12;   /* R/:2614 */
+    const double EA1 = p->E1 * p->A01, EA2 = p->E2 * p->A12;                                                         /* R/:2616 */
+    const double *P = Y, *G = Y + n, *R = Y + 2 * n, *W = Y + 3 * n, *O = Y + 4 * n;
+    for (int i = 0; i < n; i++) {
+        const int r = i / g, q = i % g;
+        const int up = ((r - 1) % g + g) % g * g + q, dn = ((r + 1) % g + g) % g * g + q;   /* R/:1622-1626 */
+        const int lf = r * g + ((q - 1) % g + g) % g, rt = r * g + ((q + 1) % g + g) % g;
+        f[i] = cgmax * W[i] * P[i] / (W[i] + p->K1) - (p->A01 * P[i] / (1 + A01H01 * P[i])) * G[i];                     /* R/:2633 */
+        f[n + i] = (EA1 * P[i] / (1 + A01H01 * P[i])) * G[i] - p->A12 * G[i] / (1 + A12H12 * G[i]) * R[i];              /* R/:2635-2636 */
+        f[2 * n + i] = (EA2 * G[i] / (1 + A12H12 * G[i])) * R[i];                                                      /* R/:2638 */
+        f[3 * n + i] = p->alpha * (P[i] + K2W0) / (P[i] + p->K2) * O[i] - p->gmax * W[i] * P[i] / (W[i] + p->K1) - p->rW * W[i]
+                     + (p->Dw) * (W[up] + W[dn] + W[lf] + W[rt] - 4 * W[i]);                                           /* R/:2640-2641 */
+        f[4 * n + i] = p->a - p->alpha * (P[i] + K2W0) / (P[i] + p->K2) * O[i]
+                     + (p->Do) * (O[up] + O[dn] + O[lf] + O[rt] - 4 * O[i]);                                           /* R/:2643-2644 */
+    }
+}
+
+/* RK4_Integrate_Stochastic_MultiSp R/:2652-2720: one step in place on f[5][L*L] */
+int tmo_rk4_3sp(const tmo_cons3_params *p, double *f)
+{
+    if (!p || p->L < 1) return -1;
+    const size_t n5 = (size_t)5 * p->L * p->L;
+    const double dt2 = p->dt / 2.0, dt6 = p->dt / 6.0;
+    double *K1 = malloc(sizeof(double) * n5 * 5), *K2 = K1 + n5, *K3 = K2 + n5, *K4 = K3 + n5, *Y = K4 + n5;
+    if (!K1) return -1;
+    f_2dor_3sp(p, K1, f);
+    for (size_t i = 0; i < n5; i++) Y[i] = f[i] + (dt2) * K1[i];
+    f_2dor_3sp(p, K2, Y);
+    for (size_t i = 0; i < n5; i++) Y[i] = f[i] + (dt2) * K2[i];
+    f_2dor_3sp(p, K3, Y);
+    for (size_t i = 0; i < n5; i++) Y[i] = f[i] + (p->dt) * K3[i];
+    f_2dor_3sp(p, K4, Y);
+    for (size_t i = 0; i < n5; i++) f[i] += (dt6) * (K1[i] + 2.0 * K2[i] + 2.0 * K3[i] + K4[i]);   /* R/:2691 */
+    free(K1);
+    return 0;
+}

@@ -42,6 +42,12 @@ class OConsParams(C.Structure):
     _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1".split()]
 
 
+class OCons3Params(C.Structure):
+    """struct tmo_cons3_params."""
+    _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in
+                                                         "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1 A12 H12 E2".split()]
+
+
 class OGrazParams(C.Structure):
     """struct tmo_graz_params."""
     _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in "dt dx D v M sigma D0floor".split()]
@@ -103,6 +109,11 @@ def oracle():
         L.tmo_step_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OGrazParams), C.POINTER(OConsParams), C.POINTER(C.c_int32), C.c_int,
                                    C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int]
         L.tmo_step_2sp_means.argtypes = L.tmo_step_2sp.argtypes + [dp]
+        L.tmo_gamma_3sp.argtypes = [C.c_int, dp, dp, dp, C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, dp, dp, dp]
+        L.tmo_gamma_3sp.restype = None
+        L.tmo_rk4_3sp.argtypes = [C.POINTER(OCons3Params), dp]
+        L.tmo_step_3sp.argtypes = [C.POINTER(OParams), C.POINTER(OGrazParams), C.POINTER(OGrazParams), C.POINTER(OCons3Params),
+                                   C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int, dp]
         L.tmo_step_fpe_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OConsParams), C.c_double, C.POINTER(OFkeTerms), dp, dp,
                                        C.POINTER(C.c_int32), C.c_int, C.c_double, C.POINTER(ORng), dp, dp, dp, dp]
         L.tmo_rk4_fpe_2sp.argtypes = [C.POINTER(OConsParams), C.c_double, dp]
@@ -275,6 +286,34 @@ def step_2sp(pv, pg, pc, central, fr, rng, f, gamma, trig_libm=False, means=None
     m = None if means is None else np.array([means[0], means[1]], dtype=np.float64)
     rc = oracle().tmo_step_2sp_means(C.byref(pv), C.byref(pg), C.byref(pc), cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen), fr,
                                      C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0, None if m is None else ptr(m))
+    assert rc == 0
+    return veff
+
+
+def runner3_params(L, par):
+    """(vegetation, grazer, predator, RK4) oracle parameter blocks from the SPB = 3 runner vector of tests/golden/make_runner3_golden.py:
+    {a, c, gmax, alpha, rW, W0, d, K1, K2, D0..D4, sigma0..2, v1, v2, aij, hij, ej, ajm, hjm, em, m1, m2, pR1, pR2, dt, dx}.
+    Returns (pv, pg1, pg2, pc, disc radius, fr1, fr2)."""
+    (a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, D4, s0, s1, s2, v1, v2, aij, hij, ej, ajm, hjm, em, m1, m2, pR1, pR2,
+     dt, dx) = [float(x) for x in par]
+    pv = OParams()
+    pv.model, pv.L, pv.dt, pv.dx, pv.a = 2, L, dt, dx, a
+    pv.rc, pv.gmax, pv.alpha, pv.rW, pv.W0, pv.d, pv.K1, pv.K2 = c, gmax, alpha, rW, W0, d, K1, K2
+    pv.D0, pv.D1, pv.D2, pv.sigma0, pv.clamp_eps, pv.clamp_lo = D0, D3, D4, s0, 1e-12, -1e-80
+    pg1 = OGrazParams(L, 0, dt, dx, D1, v1, m1, s1, D0 / (dx * dx))
+    pg2 = OGrazParams(L, 0, dt, dx, D2, v2, m2, s2, D0 / (dx * dx))
+    pc = OCons3Params(L, 0, dt, a, c, gmax, alpha, rW, W0, K1, K2, D3 / (dx * dx), D4 / (dx * dx), aij, hij, ej, ajm, hjm, em)
+    r_max = max(pR1, pR2) / dx                 # r_max_effective, R/:3405
+    return pv, pg1, pg2, pc, int(r_max), pR1 / (dx * r_max), pR2 / (dx * r_max)
+
+
+def step_3sp(pv, pg1, pg2, pc, central, fr1, fr2, rng, f, gamma, trig_libm=False, means=None):
+    """One SPB = 3 runner step in place on f [5][L*L] and gamma [2][L*L]; returns the two consumers' advection vectors [2][L*L][2]."""
+    cen = np.ascontiguousarray(central, dtype=np.int32)
+    veff = np.zeros((2, pv.L * pv.L, 2))
+    m = None if means is None else np.array(means, dtype=np.float64)
+    rc = oracle().tmo_step_3sp(C.byref(pv), C.byref(pg1), C.byref(pg2), C.byref(pc), cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen),
+                               fr1, fr2, C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0, None if m is None else ptr(m))
     assert rc == 0
     return veff
 
