@@ -5,6 +5,7 @@
 #include "tm_host_setup.h"
 #include "tm_fke.cuh"
 #include "tm_consumer.cuh"
+#include "tm_consumer3.cuh"
 #include "tm_dpdet.cuh"
 
 #include <cmath>
@@ -295,6 +296,34 @@ int emu_cons_step2_fpe(int L, const double *par2, const double *cpar, const int 
     if (b.state != fields) std::memcpy(fields, b.state, sizeof(double) * 4 * n);
     const double cells = (double)L * (double)L;
     dyn_out[0] = dyn.sum_veg / cells; dyn_out[1] = dyn.sum_graz / cells; dyn_out[2] = dyn.occ_veg; dyn_out[3] = (double)dyn.eff;
+    return 0;
+}
+// The SPB = 3 (vegetation + grazer + predator) step through the product's launch chain (csrc/tm_consumer3.cuh).
+// par3 = {dt, dx, d, D0, sigma0, clamp_eps, clamp_lo, D1, D2, v1, v2, M1, M2, sigma1, sigma2, D0floor, fr1, fr2};
+// cpar = {dt, a, c, gmax, alpha, rW, W0, K1, K2, Dw, Do, A01, H01, E1, A12, H12, E2}; fields [5][L*L], gamma [2][L*L], veff [2][L*L][2];
+// u_* == nullptr: Philox (seed, trial, step0 + s), else one replay step; dyn_out[6] = {<P>, <G>, <Pr>, #{P>0}, eff1, eff2}.
+int emu_cons_step3(int L, const double *par3, const double *cpar, const int *central, int n_central, unsigned long long seed,
+                   unsigned trial, unsigned step0, int nsteps, const double *u_veg, const double *u_graz, const double *u_pred,
+                   unsigned stride, double *fields, double *gamma, double *veff, double *dyn_out, unsigned long long *overflow)
+{
+    const size_t n = (size_t)L * L;
+    const Cons3Consts cc = cons3_consts(cpar[0], cpar[1], cpar[2], cpar[3], cpar[4], cpar[5], cpar[6], cpar[7], cpar[8], cpar[9], cpar[10],
+                                        cpar[11], cpar[12], cpar[13], cpar[14], cpar[15], cpar[16]);
+    const double gD[2] = {par3[7], par3[8]}, gv[2] = {par3[9], par3[10]}, gM[2] = {par3[11], par3[12]}, gs[2] = {par3[13], par3[14]};
+    const Step3Consts k = step3_consts(L, n_central, par3[16], par3[17], par3[0], par3[1], par3[2], par3[3], par3[4], par3[5], par3[6],
+                                       gD, gv, gM, gs, par3[15], cc);
+    std::vector<double> star(3 * n), ya(5 * n), yb(5 * n), acc(5 * n), part(4 * kConsReduceBlocks);
+    Step3Dyn dyn{};
+    Step3Buffers b{};
+    b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.replay[0] = u_veg; b.replay[1] = u_graz; b.replay[2] = u_pred; b.stride = stride;
+    *overflow = 0;
+    auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
+    for (int s = 0; s < nsteps; s++) cons_step3_enqueue(launch, k, b, seed, trial, step0 + (unsigned)s);
+    const double cells = (double)L * (double)L;
+    for (int s = 0; s < 3; s++) dyn_out[s] = dyn.sum[s] / cells;
+    dyn_out[3] = dyn.occ_veg; dyn_out[4] = (double)dyn.eff[0]; dyn_out[5] = (double)dyn.eff[1];
     return 0;
 }
 // nsteps RK4 steps of the noise-off DP path through the product's stage kernel (csrc/tm_dpdet.cuh), in place on rho[L*L]

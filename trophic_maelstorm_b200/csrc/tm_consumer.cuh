@@ -194,6 +194,7 @@ struct GrazerArgs {
     unsigned long long *overflow;
     DornicConsts veg;                         // VEG variant: the vegetation's constants (R/:3461-3463), same for every cell
     const Step2Dyn *dyn;                      // non-null and dyn->skip_graz: rho* = prev, nothing drawn (R/:3910)
+    const int *skip_flag;                     // non-null and *skip_flag != 0: the same (the SPB = 3 step keeps one flag per consumer)
 };
 
 inline void grazer_derive(GrazerArgs &A)
@@ -228,7 +229,7 @@ TMC_G void grazer_dornic_kernel(const GrazerArgs A)
         if (src.overflow_count()) atomicAdd(A.overflow, (unsigned long long)src.overflow_count());
         return;
     }
-    if (A.dyn && A.dyn->skip_graz) { A.out[i] = A.prev[i]; return; }
+    if ((A.dyn && A.dyn->skip_graz) || (A.skip_flag && *A.skip_flag)) { A.out[i] = A.prev[i]; return; }
     double gm = A.gamma[i];
     if (gm > 1) { gm = 1; A.gamma[i] = gm; }
     const double ran = src.next();                                                         // R/:3993
