@@ -74,7 +74,7 @@ def _header_names(header):
 def test_fke_and_consumer_headers_are_exported_too():
     """include/tm_fke.h and include/tm_consumer.h: every declared entry point is exported and bound by the ctypes views."""
     lib = tm.lib()
-    for header, bound in (("tm_fke.h", tm.FKE_ABI_SYMBOLS), ("tm_consumer.h", tm.CONS_ABI_SYMBOLS)):
+    for header, bound in (("tm_fke.h", tm.FKE_ABI_SYMBOLS), ("tm_consumer.h", tm.CONS_ABI_SYMBOLS), ("tm_consumer3.h", tm.CONS3_ABI_SYMBOLS)):
         names = _header_names(header)
         assert names, header
         for n in names:

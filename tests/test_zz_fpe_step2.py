@@ -81,15 +81,15 @@ def follow(one_step, pv, pc, M1, terms, gD, gV, central, fr, f, nsteps, seed):
 
 @pytest.mark.parametrize("rk4_stages", [0, 1])
 def test_emulated_fpe_step_follows_the_oracle(emu, rk4_stages):
-    L = 20
+    L = 16
     par, derived, pv, pc, M1, terms, gD, gV, central, fr, f = setup(L, 7)
     follow(lambda f_, g_, s: emu_step(emu, L, par, derived, central, fr, gD, gV, f_, g_, s, 99, rk4_stages),
-           pv, pc, M1, terms, gD, gV, central, fr, f, 3, 99)
+           pv, pc, M1, terms, gD, gV, central, fr, f, 2, 99)
 
 
 def test_emulated_fpe_step_without_grazers_and_without_vegetation(emu):
     """<G> = 0: gamma = 1 everywhere (F/:2579), nothing moves; <P> = 0 with grazers: gamma = 0 (F/:2581), pure advective spreading"""
-    L = 16
+    L = 14
     for gs, vs in ((0.0, 1.0), (1.0, 0.0)):
         par, derived, pv, pc, M1, terms, gD, gV, central, fr, f = setup(L, 11, graz_scale=gs, veg_scale=vs)
         fp, gp = follow(lambda f_, g_, s: emu_step(emu, L, par, derived, central, fr, gD, gV, f_, g_, s, 5, 0),

@@ -12,4 +12,5 @@ from .lattice import (  # noqa: F401
     MODEL_DP, MODEL_DP_CUBIC, MODEL_RIETKERK, MODEL_RIETKERK_DET,
 )
 from .fke import FkeMover, FkeTerms, FKE_ABI_SYMBOLS  # noqa: F401,E402
-from .consumer import ConsumerOps, ConsParams, GrazParams, CONS_ABI_SYMBOLS  # noqa: F401,E402
+from .consumer import (ConsumerOps, ConsParams, GrazParams, CONS_ABI_SYMBOLS,   # noqa: F401,E402
+                       ConsumerOps3, Cons3Params, CONS3_ABI_SYMBOLS)

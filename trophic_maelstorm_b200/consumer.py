@@ -155,3 +155,98 @@ class ConsumerOps:
         ms, n = C.c_float(), C.c_int()
         self._ck(self._l.tm_cons_last_ms(self._ctx, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+# ---- SPB = 3 (vegetation + grazer + predator): include/tm_consumer3.h ---------------------------------------------------------------
+class Cons3Params(C.Structure):
+    """struct tm_cons3_params."""
+    _fields_ = [("L", C.c_int32), ("pad_", C.c_int32)] + [(n, C.c_double) for n in
+                                                         "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1 A12 H12 E2".split()]
+
+
+CONS3_ABI_SYMBOLS = ["tm_cons3_create", "tm_cons3_destroy", "tm_cons3_last_error", "tm_cons3_setup", "tm_cons3_upload", "tm_cons3_run",
+                     "tm_cons3_replay", "tm_cons3_download", "tm_cons3_last_ms"]
+_bound3 = False
+
+
+def _lib3():
+    global _bound3
+    L = lib()
+    if not _bound3:
+        vp, dp, i = C.c_void_p, C.POINTER(C.c_double), C.c_int
+        sig = {
+            "tm_cons3_create": (i, [i, i, C.POINTER(vp)]),
+            "tm_cons3_destroy": (i, [vp]),
+            "tm_cons3_last_error": (C.c_char_p, [vp]),
+            "tm_cons3_setup": (i, [vp, C.POINTER(Params), C.POINTER(GrazParams), C.POINTER(GrazParams), C.POINTER(Cons3Params),
+                                   C.POINTER(C.c_int32), i, C.c_double, C.c_double]),
+            "tm_cons3_upload": (i, [vp, dp, dp]),
+            "tm_cons3_run": (i, [vp, C.c_uint64, C.c_uint32, C.c_uint32, i]),
+            "tm_cons3_replay": (i, [vp, dp, dp, dp, C.c_uint32]),
+            "tm_cons3_download": (i, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint64)]),
+            "tm_cons3_last_ms": (i, [vp, C.POINTER(C.c_float), C.POINTER(i)]),
+        }
+        for name, (res, args) in sig.items():
+            f = getattr(L, name)
+            f.restype, f.argtypes = res, args
+        _bound3 = True
+    return L
+
+
+class ConsumerOps3:
+    """One tm_cons3_ctx: the vegetation + grazer + predator time step resident on the device."""
+
+    def __init__(self, L, device=0):
+        self._l = _lib3()
+        self.L = L
+        self._ctx = C.c_void_p()
+        rc = self._l.tm_cons3_create(L, device, C.byref(self._ctx))
+        if rc != 0:
+            self._ctx = C.c_void_p()
+            raise TmError("tm_cons3_create failed (%d): %s" % (rc, self._l.tm_cons3_last_error(None).decode()))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TmError("tm_cons3 call failed (%d): %s" % (rc, self._l.tm_cons3_last_error(self._ctx).decode()))
+
+    def close(self):
+        if self._ctx:
+            self._l.tm_cons3_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def setup(self, veg, graz, pred, cons, central, fr_graz, fr_pred):
+        cen = np.ascontiguousarray(central, dtype=np.int32)
+        self._ck(self._l.tm_cons3_setup(self._ctx, C.byref(veg), C.byref(graz), C.byref(pred), C.byref(cons),
+                                        cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen), fr_graz, fr_pred))
+
+    def upload(self, fields, gamma=None):
+        f = np.ascontiguousarray(fields, dtype=np.float64)
+        assert f.size == 5 * self.L * self.L
+        g = None if gamma is None else np.ascontiguousarray(gamma, dtype=np.float64)
+        self._ck(self._l.tm_cons3_upload(self._ctx, _dptr(f), None if g is None else _dptr(g)))
+
+    def run(self, seed, trial=0, step0=0, nsteps=1):
+        self._ck(self._l.tm_cons3_run(self._ctx, seed, trial, step0, nsteps))
+
+    def replay(self, u_veg, u_graz, u_pred, stride):
+        us = [np.ascontiguousarray(x, dtype=np.float64) for x in (u_veg, u_graz, u_pred)]
+        assert all(x.size == self.L * self.L * stride for x in us)
+        self._ck(self._l.tm_cons3_replay(self._ctx, _dptr(us[0]), _dptr(us[1]), _dptr(us[2]), stride))
+
+    def download(self):
+        """-> (fields [5, L*L], gamma [2, L*L], v_eff [2, L*L, 2], means {<P>, <G>, <Pr>, #{P>0}, eff1, eff2}, overflow)."""
+        n = self.L * self.L
+        f, g, v, m, ovf = np.empty((5, n)), np.empty((2, n)), np.empty((2, n, 2)), np.empty(6), C.c_uint64()
+        self._ck(self._l.tm_cons3_download(self._ctx, _dptr(f), _dptr(g), _dptr(v), _dptr(m), C.byref(ovf)))
+        return f, g, v, m, ovf.value
+
+    def last_ms(self):
+        ms, n = C.c_float(), C.c_int()
+        self._ck(self._l.tm_cons3_last_ms(self._ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

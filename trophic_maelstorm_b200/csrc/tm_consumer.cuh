@@ -29,7 +29,7 @@
 
 #if defined(__CUDACC__)
 #define TMC_D __device__ __forceinline__
-#define TMC_G __global__
+#define TMC_G static __global__   // static: tm_consumer.cu and tm_consumer3.cu each compile their own copy
 #define TMC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #else
 #include "tm_cpu_emu.h" // tests/emu only
@@ -342,7 +342,7 @@ struct RkFusedArgs {
 };
 
 #if defined(__CUDACC__)
-__global__ void __launch_bounds__(kFuseThreads) cons_rk4_fused_kernel(const RkFusedArgs A)
+static __global__ void __launch_bounds__(kFuseThreads) cons_rk4_fused_kernel(const RkFusedArgs A)
 #else
 void cons_rk4_fused_kernel(const RkFusedArgs A)
 #endif

@@ -1,0 +1,196 @@
+// tm_host_3sp.cpp -- see tm_host_3sp.h.  Host bookkeeping only; the lattice numerics go through include/tm_consumer3.h.
+#include "tm_host_3sp.h"
+#include "tm_host.h"
+#include "tm_host_2sp.h"   // computeNeighboringSitesCentral (R/:1661, the same for every SPB)
+#include "../../include/tm_consumer3.h"
+#include "../../include/tm_lattice.h"
+
+#include <algorithm>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <sys/stat.h>
+
+namespace tm_b200 { namespace spb3 {
+
+using std::vector;
+
+std::function<void(double *, int, int, double, double, double, const double[])> init_frame;
+std::function<void(int, int, double, const double *)> on_measure;
+
+// R/:1293-1343 with SpB = 3 species blocks and the two water columns
+void var_mean_incremental_surv_runs(D2Vec_Double &T, const D2Vec_Double &X, int size, int j)
+{
+    vector<double> mean_prev(size);
+    for (int s = 0; s < SpB; s++)
+        for (int i = 0; i < size; i++) {
+            const int r = (int)(T[i][4 * s + 5] + 1);
+            if (X[i][2 * s + 0] == 0.0) break;
+            mean_prev[i] = T[i][4 * s + 3];
+            if (T[i][4 * s + 5] == 0.0) {
+                T[i][4 * s + 3] = X[i][2 * s + 1]; T[i][4 * s + 4] = 0.0; T[i][4 * s + 6] = X[i][2 * s + 0];
+            } else {
+                T[i][4 * s + 3] = (X[i][2 * s + 1] + (r - 1) * T[i][4 * s + 3]) / r;
+                T[i][4 * s + 6] = (X[i][2 * s + 0] + (r - 1) * T[i][4 * s + 6]) / r;
+                T[i][4 * s + 4] = (T[i][4 * s + 3] - mean_prev[i]) * (T[i][4 * s + 3] - mean_prev[i])
+                                + (1 / (r - 1)) * ((r - 2) * T[i][4 * s + 4]
+                                                   + (X[i][2 * s + 1] - T[i][4 * s + 3]) * (X[i][2 * s + 1] - T[i][4 * s + 3]));   // int 1/(r-1)
+            }
+            T[i][4 * s + 5] = r;
+        }
+    for (int i = 0; i < size; i++) {
+        T[i][1] = (X[i][2 * (Sp - 2) + 1] + (j)*T[i][1]) / (j + 1);
+        T[i][2] = (X[i][2 * (Sp - 1) + 1] + (j)*T[i][2]) / (j + 1);
+    }
+}
+
+namespace {
+struct Ctx {
+    tm_cons3_ctx *c = nullptr;
+    ~Ctx() { if (c) tm_cons3_destroy(c); }
+    void ck(int rc, const char *what)
+    {
+        if (rc != 0) throw std::runtime_error(std::string(what) + ": " + tm_cons3_last_error(c));
+    }
+};
+double mean_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i = 0; i < n; ++i) s += x[i]; return s / (double)n; }   // R/:1211
+double occupied_sites_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i = 0; i < n; ++i) if (x[i] > 0) s += 1; return s; }   // R/:1245
+} // namespace
+
+void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
+                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
+                                double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
+                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+{
+    if (!init_frame) throw std::runtime_error("tm_b200::spb3::init_frame is not set");
+    (void)dtV;   // see the header
+    const int tot_iter = (int)t_meas.size();
+    const double t_end = t_meas.back();                                               // R/:3439
+    const size_t n = (size_t)g * g;
+    const int Sp2 = 2 * Sp, W_ = 4 * SpB + 3;
+
+    const double r_max_effective = (*std::max_element(pR, pR + SpB)) / dx;            // R/:3405
+    const double fr_graz = pR[1] / (dx * r_max_effective), fr_pred = pR[2] / (dx * r_max_effective);   // R/:3409
+    const vector<std::pair<int, int>> nb = spb2::computeNeighboringSitesCentral(int(r_max_effective));   // R/:3417
+    vector<int32_t> central(2 * nb.size());
+    for (size_t k = 0; k < nb.size(); k++) { central[2 * k] = nb[k].first; central[2 * k + 1] = nb[k].second; }
+
+    tm_params veg{};
+    veg.model = TM_MODEL_RIETKERK; veg.L = g; veg.dt = dt; veg.dx = dx; veg.a = a;
+    veg.rc = c; veg.gmax = gmax; veg.alpha = alpha; veg.rW = rW; veg.W0 = W0; veg.d = M[0]; veg.K1 = K[1]; veg.K2 = K[2];
+    veg.D0 = D[0]; veg.D1 = D[3]; veg.D2 = D[4]; veg.sigma0 = sigma[0]; veg.clamp_eps = 1.0e-12; veg.clamp_lo = -1.0e-80;   // R/:4176
+    tm_graz_params pg[2];
+    for (int s = 1; s <= 2; s++) {
+        tm_graz_params &q = pg[s - 1];
+        q = tm_graz_params{};
+        q.L = g; q.dt = dt; q.dx = dx; q.D = D[s]; q.v = v[s]; q.M = M[s]; q.sigma = sigma[s]; q.D0_floor = D[0] / (dx * dx);   // R/:4014
+    }
+    tm_cons3_params pc{};
+    pc.L = g; pc.dt = dt; pc.a = a; pc.c = c; pc.gmax = gmax; pc.alpha = alpha; pc.rW = rW; pc.W0 = W0; pc.K1 = K[1]; pc.K2 = K[2];
+    pc.Dw = D[3] / (dx * dx); pc.Do = D[4] / (dx * dx);                               // R/:3463-3480
+    pc.A01 = A[0][1]; pc.H01 = H[0][1]; pc.E1 = E[1]; pc.A12 = A[1][2]; pc.H12 = H[1][2]; pc.E2 = E[2];
+
+    Ctx ctx;
+    if (tm_cons3_create(g, current_device(), &ctx.c) != 0) throw std::runtime_error(std::string("tm_cons3_create: ") + tm_cons3_last_error(nullptr));
+    ctx.ck(tm_cons3_setup(ctx.c, &veg, &pg[0], &pg[1], &pc, central.data(), (int)nb.size(), fr_graz, fr_pred), "tm_cons3_setup");
+
+    D2Vec_Double rho_rep_avg_var(tot_iter, vector<double>(W_, 0.0));
+    for (int i = 0; i < tot_iter; i++) rho_rep_avg_var[i][0] = t_meas[i];            // R/:3484-3487
+    vector<double> frame(Sp * n);
+    const unsigned long long key = stream_seed(options().seed, a);
+
+    for (int j = 0; j < r; j++) {
+        init_frame(frame.data(), g, j, a, a_c, dP, clow);
+        ctx.ck(tm_cons3_upload(ctx.c, frame.data(), nullptr), "tm_cons3_upload");     // gamma starts as zeros (R/:3523)
+        D2Vec_Double Rho_M(tot_iter, vector<double>(Sp2, 0.0));
+        double t = 0; int index = 0; int pending = 0; uint32_t step = 0;
+        while (t < t_end + dt) {                                                      // R/:3648
+            const bool meas = index < tot_iter && (t == 0 || (t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0));   // R/:3659
+            if (meas) {
+                if (pending) { ctx.ck(tm_cons3_run(ctx.c, key, (uint32_t)j, step, pending), "tm_cons3_run"); step += pending; pending = 0; }
+                ctx.ck(tm_cons3_download(ctx.c, frame.data(), nullptr, nullptr, nullptr, nullptr), "tm_cons3_download");
+                for (int s = 0; s < Sp; s++) {
+                    const double *f = &frame[s * n];
+                    for (size_t i = 0; i < n; i++)
+                        if (f[i] != f[i]) { std::cerr << "RHO NAAN PARATHA in field " << s << " at t=" << t << "\n"; exit(3); }   // R/:4156
+                    Rho_M[index][2 * s] = occupied_sites_of_vector(f, n); Rho_M[index][2 * s + 1] = mean_of_vector(f, n);   // R/:3662-3668
+                }
+                if (on_measure) on_measure(j, index, t, frame.data());
+                const bool checkpoint = index == int(tot_iter * 0.6) || index == int(tot_iter * 0.85) || index == int(tot_iter * 0.9)
+                                     || index == int(tot_iter * 0.95) || index == int(tot_iter - 1);
+                const bool dead = Rho_M[index][0] == 0.0;
+                index += 1;
+                if (checkpoint && dead) break;   // save_prelimfileswrapper's break_flag: all vegetation dead, R/:3087, 3714
+            }
+            pending += 1;
+            t += dt;
+        }
+        if (j == 0) {                                                                 // R/:4294-4316
+            for (int i = 0; i < tot_iter; i++) {
+                for (int s = 0; s < SpB; s++) {
+                    rho_rep_avg_var[i][4 * s + 3] = Rho_M[i][2 * s + 1]; rho_rep_avg_var[i][4 * s + 4] = 0.0;
+                    rho_rep_avg_var[i][4 * s + 6] = Rho_M[i][2 * s];
+                    if (Rho_M[i][2 * s] > 0) rho_rep_avg_var[i][4 * s + 5] = 1; else if (Rho_M[i][2 * s] == 0) rho_rep_avg_var[i][4 * s + 5] = 0;
+                }
+                rho_rep_avg_var[i][1] = Rho_M[i][2 * (Sp - 2) + 1]; rho_rep_avg_var[i][2] = Rho_M[i][2 * (Sp - 1) + 1];
+            }
+        } else var_mean_incremental_surv_runs(rho_rep_avg_var, Rho_M, tot_iter, j);   // R/:4321
+    }
+    for (int i = 0; i < tot_iter; i++) {                                              // R/:4361-4372
+        Rho.push_back({a, static_cast<double>(r), static_cast<double>(g), rho_rep_avg_var[i][0], rho_rep_avg_var[i][1], rho_rep_avg_var[i][2]});
+        for (int s = 0; s < Sp - 2; s++)
+            Rho[Rho.size() - 1].insert(Rho[Rho.size() - 1].end(), {rho_rep_avg_var[i][4 * s + 3], rho_rep_avg_var[i][4 * s + 4],
+                                                                   rho_rep_avg_var[i][4 * s + 5], rho_rep_avg_var[i][4 * s + 6]});
+    }
+}
+
+const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"
+                                 " # Active Sites P(x; t), <<G(x; t)>_x>_r, Var[<G(x; t)>_x]_r, # Surviving Runs G(x; t), # Active Sites G(x; t),"
+                                 "<<Pr(x; t)>_x>_r, Var[<Pr(x; t)>_x]_r, # Surviving Runs Pr(x; t), # Active Sites Pr(x; t), \n";   // constants_3Sp.h:10-12
+
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar, double Vstar)
+{
+    vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = logarithm10_time_bins(t_max, 1 * dt);
+    t_measure.insert(t_measure.begin(), 0.0);                                        // R/:4401
+    std::sort(t_measure.begin(), t_measure.end());
+    t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
+    vector<D2Vec_Double> per_a(a_space.size());
+    for_each_on_devices((int)a_space.size(), [&](int i) {   // the reference's `omp for` over a-values (R/:4509): one GPU per a-value at a time
+        vector<double> tm_i = t_measure;
+        rietkerk_Dornic_2D_MultiSp(per_a[i], tm_i, t_max, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_start, a_end, a_c, A, H, E, M,
+                                   pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
+    });
+    D2Vec_Double vec;
+    for (const D2Vec_Double &rows : per_a) vec.insert(vec.end(), rows.begin(), rows.end());
+    std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;
+    L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r;
+    Dm1 << std::setprecision(3) << D[1]; dix << std::setprecision(2) << dx; geq << std::setprecision(5) << Gstar; veq << std::setprecision(5) << Vstar;
+    const std::string dir = options().data_root + "/Data/Rietkerk/Stochastic/3Sp";
+    std::string path;
+    for (size_t k = 1; k <= dir.size(); k++)                                         // mkdir -p
+        if (k == dir.size() || dir[k] == '/') { path = dir.substr(0, k); mkdir(path.c_str(), 0777); }
+    std::string savefile = dir + "/1stCC_Rietkerk_" + prefix + "_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
+                         + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str();                                    // R/:4582
+    if (Gstar != -1) savefile += "_Geq_" + geq.str() + "_R_" + rini.str() + ".csv";
+    else if (Vstar != -1) savefile += "_Veq_" + veq.str() + "_R_" + rini.str() + ".csv";
+    else savefile += "_R_" + rini.str() + ".csv";
+    std::ofstream out(savefile);
+    out << prelimheader << "\n";                                                     // R/:4601
+    for (size_t i = 0; i < vec.size(); i++) {
+        for (size_t j = 0; j + 1 < vec[i].size(); j++) out << std::setprecision(16) << vec[i][j] << ",";
+        out << std::setprecision(16) << vec[i][vec[i].size() - 1] << std::endl;
+    }
+}
+
+}} // namespace tm_b200::spb3

@@ -3,6 +3,7 @@
 #include "tm_host.h"
 #include "tm_host_fke.h"
 #include "tm_host_2sp.h"
+#include "tm_host_3sp.h"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -352,6 +353,46 @@ int tmh_fpe2_run(int L, const double *par, int r, const double *init, int n_init
     if ((int)Rho.size() > cap) return -1;
     for (size_t k = 0; k < Rho.size(); k++)
         for (size_t j = 0; j < 14; j++) rows_out[14 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
+    return (int)Rho.size();
+}
+
+// SPB = 3: tm_b200::spb3::rietkerk_Dornic_2D_MultiSp (sweep != 0: its a-sweep, CSV under data_root).  par = the 31-entry vector of
+// tests/golden/make_runner3_golden.py {a, c, gmax, alpha, rW, W0, d, K1, K2, D0..D4, sigma0..2, v1, v2, aij, hij, ej, ajm, hjm, em, m1, m2,
+// pR1, pR2, dt, dx}; init: n_init frames [5][L*L], replicate j starts from frame j % n_init; rows_out[k][18]; frames_out (may be NULL):
+// [r][n_tmeas][5][L*L].
+int tmh_riet3_run(int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
+                  double *rows_out, int cap, double *frames_out, int sweep, int div, double a_start, double a_end)
+{
+    namespace s3 = tm_b200::spb3;
+    double D[s3::Sp] = {par[9], par[10], par[11], par[12], par[13]};
+    double K[3] = {0.0, par[7], par[8]};
+    double sigma[s3::Sp] = {par[14], par[15], par[16], 0, 0};
+    double v[s3::SpB] = {0, par[17], par[18]};
+    double A[s3::SpB][s3::SpB] = {{0, par[19], 0}, {par[19], 0, par[22]}, {0, par[22], 0}};
+    double H[s3::SpB][s3::SpB] = {{0, par[20], 0}, {par[20], 0, par[23]}, {0, par[23], 0}};
+    double E[s3::SpB] = {1.0, par[21], par[24]}, M[s3::SpB] = {par[6], par[25], par[26]}, pR[s3::Sp] = {0.0, par[27], par[28], 0.0, 0.0};
+    int dtV[s3::SpB] = {0, 1, 1};
+    double clow[2 * s3::Sp] = {0, 1, 1, 1, 1, 5, 1, 1, 1, 1};
+    const size_t n5 = (size_t)5 * L * L;
+    s3::init_frame = [=](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + (size_t)(j % n_init) * n5, n5 * sizeof(double)); };
+    if (frames_out && !sweep)
+        s3::on_measure = [=](int j, int index, double, const double *f) { memcpy(frames_out + ((size_t)j * n_tmeas + index) * n5, f, n5 * sizeof(double)); };
+    else s3::on_measure = nullptr;
+    s3::D2Vec_Double Rho;
+    try {
+        if (sweep) {
+            s3::first_order_critical_exp_delta_stochastic_MultiSp(div, t_meas[n_tmeas - 1], a_start, a_end, 1.0 / 24.0, par[1], par[2], par[3], par[4],
+                                                                  par[5], D, v, K, sigma, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
+            return 0;
+        }
+        std::vector<double> tm(t_meas, t_meas + n_tmeas);
+        s3::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+                                       1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
+    } catch (const std::exception &e) { fprintf(stderr, "tmh_riet3_run: %s\n", e.what()); s3::on_measure = nullptr; return -2; }
+    s3::on_measure = nullptr;
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (size_t j = 0; j < 18; j++) rows_out[18 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
     return (int)Rho.size();
 }
 }
