@@ -69,23 +69,29 @@ inline bool mbar_try_wait(uint64_t *b, uint32_t parity)
 }
 }
 
-// run `kernel(args)` over grid x block on host threads, blocks one after another
+// run `kernel(args)` over grid x block on host threads, blocks one after another.  One set of `block` threads walks all blocks
+// (a thread per (block, thread) pair made the reduction kernels' 296 x 256 launches the bulk of the CPU suite's time); between two
+// blocks everybody meets at a second barrier, whose completion step re-poisons the shared memory.
 template <class K, class A>
 inline void emu_launch(K kernel, const A &args, unsigned grid, unsigned block, size_t smem_bytes)
 {
     std::vector<unsigned char> smem(smem_bytes + 256);
     unsigned char *sbase = (unsigned char *)(((uintptr_t)smem.data() + 127) & ~(uintptr_t)127);
-    for (unsigned b = 0; b < grid; b++) {
-        std::memset(smem.data(), 0xA5, smem.size()); // shared memory starts as garbage
-        std::barrier<> bar((std::ptrdiff_t)block);
-        std::vector<std::thread> th;
-        th.reserve(block);
-        for (unsigned t = 0; t < block; t++)
-            th.emplace_back([&, t, b] {
-                threadIdx.x = t; blockIdx.x = b; blockDim.x = block; gridDim.x = grid;
-                emu_block_barrier = &bar; emu_dyn_smem_ptr = sbase;
+    std::memset(smem.data(), 0xA5, smem.size()); // shared memory starts as garbage
+    std::barrier<> bar((std::ptrdiff_t)block);
+    auto repoison = [&]() noexcept { std::memset(smem.data(), 0xA5, smem.size()); };
+    std::barrier<decltype(repoison)> next_block((std::ptrdiff_t)block, repoison);
+    std::vector<std::thread> th;
+    th.reserve(block);
+    for (unsigned t = 0; t < block; t++)
+        th.emplace_back([&, t] {
+            threadIdx.x = t; blockDim.x = block; gridDim.x = grid;
+            emu_block_barrier = &bar; emu_dyn_smem_ptr = sbase;
+            for (unsigned b = 0; b < grid; b++) {
+                blockIdx.x = b;
                 kernel(args);
-            });
-        for (auto &x : th) x.join();
-    }
+                next_block.arrive_and_wait();
+            }
+        });
+    for (auto &x : th) x.join();
 }
