@@ -866,6 +866,110 @@ int tmo_step_3sp(const tmo_params *pveg, const tmo_graz_params *pg1, const tmo_g
     return 0;
 }
 
+/* One time step of the Rietkerk_FPE runner compiled with -DSPB=3, rietkerk_DorFPE_2D_MultiSp F/:4094-4462 (see tm_oracle.h). */
+int tmo_step_fpe_3sp(const tmo_params *pveg, const tmo_cons3_params *pc, const double *M, const double *v, const tmo_fke_terms *ft,
+                     const double *const *gD, const double *const *gV, const int32_t *central, int n_central, double fr1, double fr2,
+                     tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm, const double *means)
+{
+    if (!pveg || !pc || !ft || pveg->L != pc->L || pveg->L != ft[0].L || pveg->L != ft[1].L) return -1;
+    const int L = pveg->L;
+    const int64_t n = (int64_t)L * L;
+    double *work = malloc(sizeof(double) * (size_t)n * 8);
+    if (!work) return -1;
+    double *D = work, *vout = work + 5 * n, *moved = work + 6 * n;                       /* DRho copy, rho*_P, moved consumers [2][n] */
+    memcpy(D, f, sizeof(double) * (size_t)n * 5);
+    double avg[3];
+    for (int s = 0; s < 3; s++) avg[s] = means ? means[s] : tmo_mean(D + s * n, n);      /* F/:4101-4106 */
+    const double num_veg = tmo_occupied(D, n);
+    double nR_fac = 1 - num_veg / (L * L);                                               /* F/:4110 */
+    if (nR_fac < 0.35) nR_fac = 0.35;
+    int new_length = (int)(nR_fac * nR_fac * n_central);                                 /* F/:3380 */
+    if (new_length < 1) new_length = 1;                                                  /* F/:3381 */
+    /* --- calc_gamma_vel_3Sp_NonRefugia, F/:3371-3483 --- */
+    {
+        const double eps = 1.0e-12;
+        double rho_inverse[3];
+        for (int s = 0; s < 3; s++) rho_inverse[s] = avg[s] >= eps ? 1 / avg[s] : 1 / eps;
+        const double fr[3] = {0.0, fr1, fr2}, vel[3] = {0.0, v[0], v[1]};
+        int order[3] = {0, 1, 2};                                                        /* rfrac sorted by decreasing radius, F/:3745 */
+        for (int a_ = 0; a_ < 3; a_++)
+            for (int b_ = a_ + 1; b_ < 3; b_++)
+                if (fr[order[b_]] > fr[order[a_]]) { const int t_ = order[a_]; order[a_] = order[b_]; order[b_] = t_; }
+        double pi = 0.0, p16 = 1.0;                                                      /* the reference's PI, header :241-284 */
+        for (int q = 0; q <= 14; q++) {
+            pi = (1.0 / p16 * (4.0 / (8 * q + 1.0) - 2.0 / (8 * q + 4.0) - 1.0 / (8 * q + 5.0) - 1.0 / (8 * q + 6.0))) + pi;
+            p16 *= 16.0;
+        }
+        tmo_rng dir = *rng;                                                              /* the direction uniforms' source */
+        if (rng->kind == TMO_SRC_PHILOX) dir.seed = rng->seed ^ 0xA0761D6478BD642Full;
+        else if (rng->kind == TMO_SRC_REPLAY) {
+            const uint64_t skip = (uint64_t)n * rng->stride;
+            dir.u = rng->u + skip; dir.n_u = rng->n_u > skip ? rng->n_u - skip : 0;
+        }
+        tmo_rng *dsrc = rng->kind == TMO_SRC_SEQ ? rng : &dir;
+        if (dsrc == &dir) { dir.overflow = 0; dir.draws = 0; }
+        cstream cs;
+        cs_begin_cell(&cs, dsrc, 0);
+        const double *fld[3] = {D, D + n, D + 2 * n};
+        for (int i = 0; i < L * L; i++) {
+            const int c_i = i / L, c_j = i % L;
+            if (dsrc->kind != TMO_SRC_SEQ) cs_begin_cell(&cs, dsrc, (uint64_t)i);
+            for (int o = 0; o < 3; o++) {
+                const int s = order[o];
+                int eff = (int)(fr[s] * fr[s] * new_length);                             /* F/:3413 */
+                const double ran = next_u(&cs);                                          /* F/:3421: every species, the vegetation too */
+                if (s >= 1) {
+                    double vx, vy;
+                    if (trig_libm) { vx = vel[s] * cos(2 * pi * ran); vy = vel[s] * sin(2 * pi * ran); }   /* F/:3424 */
+                    else { double sn, csn; tmo_sincos_turn128(128.0 * ran, &sn, &csn); vx = vel[s] * csn; vy = vel[s] * sn; }
+                    veff[2 * ((s - 1) * n + i)] = vx; veff[2 * ((s - 1) * n + i) + 1] = vy;
+                }
+                if (fr[s] == 0.0) continue;                                              /* F/:3426 */
+                if (eff < 1 && fr[s] > 0) eff = 1;                                       /* F/:3428 */
+                double *g = gamma + (s - 1) * n;
+                if (avg[s] < eps) { g[i] = 1.0; continue; }                              /* F/:3430 */
+                else if (avg[s - 1] < eps) { g[i] = 0.0; continue; }                     /* F/:3432 */
+                const double *prey = fld[s - 1];
+                if (s == 1) {
+                    if (avg[2] < eps) {
+                        for (int k = 0; k < eff; k++) {
+                            const int nx = (c_i + central[2 * k] + L) % L, ny = (c_j + central[2 * k + 1] + L) % L;
+                            g[i] += prey[nx * L + ny];                                   /* F/:3440: accumulated onto the old value */
+                        }
+                    } else {
+                        for (int k = 0; k < eff; k++) {
+                            const int nx = (c_i + central[2 * k] + L) % L, ny = (c_j + central[2 * k + 1] + L) % L;
+                            g[i] += prey[nx * L + ny] * (1 - fld[2][nx * L + ny] * rho_inverse[2]);   /* F/:3447 */
+                        }
+                    }
+                    g[i] = (g[i] * rho_inverse[s - 1]) / (eff);                          /* F/:3450 */
+                } else {
+                    for (int k = 0; k < eff; k++) {
+                        const int nx = (c_i + central[2 * k] + L) % L, ny = (c_j + central[2 * k + 1] + L) % L;
+                        g[i] += prey[nx * L + ny];
+                    }
+                    g[i] = (g[i] / (eff)) * rho_inverse[s - 1];                          /* F/:3456 */
+                }
+                if (g[i] > 1) g[i] = 1.0; else if (g[i] < 0) g[i] = 0.0;                 /* F/:3459-3462 */
+            }
+        }
+        if (dsrc == &dir) { rng->overflow += dir.overflow; rng->draws += dir.draws; }
+    }
+    dornic_consts k;
+    derive_consts(pveg, &k);
+    dornic_sweep(pveg, &k, rng, D, vout);                                                /* vegetation only, F/:4154-4211 */
+    memcpy(f, vout, sizeof(double) * (size_t)n);
+    if (tmo_rk4_fpe_3sp(pc, M[0], M[1], f)) { free(work); return -1; }                   /* F/:4238 */
+    for (int s = 1; s <= 2; s++) {                                                       /* advdiff_FKE_MultiSp, F/:4308 */
+        if (tmo_fke_move(&ft[s - 1], f + s * n, gamma + (s - 1) * n, veff + 2 * (s - 1) * n, gD[s - 1], gV[s - 1], moved + (s - 1) * n)) { free(work); return -1; }
+    }
+    memcpy(f + n, moved, sizeof(double) * (size_t)n * 2);
+    for (int64_t i = 0; i < 5 * n; i++)
+        if (f[i] < ft[0].epsilon && f[i] >= 0.0) f[i] = 0.0;                             /* F/:4458 */
+    free(work);
+    return 0;
+}
+
 /* One time step of the Rietkerk_FPE runner compiled with -DSPB=2, rietkerk_DorFPE_2D_MultiSp F/:4094-4462 (see tm_oracle.h). */
 int tmo_step_fpe_2sp(const tmo_params *pveg, const tmo_cons_params *pc, double M1, const tmo_fke_terms *ft, const double *gD,
                      const double *gV, const int32_t *central, int n_central, double fr_graz, tmo_rng *rng, double *f, double *gamma,

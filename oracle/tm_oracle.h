@@ -205,6 +205,17 @@ int tmo_rk4_3sp(const tmo_cons3_params *p, double *f);
 int tmo_step_3sp(const tmo_params *pveg, const tmo_graz_params *pg1, const tmo_graz_params *pg2, const tmo_cons3_params *pc,
                  const int32_t *central, int n_central, double fr1, double fr2, tmo_rng *rng, double *f, double *gamma, double *veff,
                  int trig_libm, const double *means);
+int tmo_rk4_fpe_3sp(const tmo_cons3_params *p, double M1, double M2, double *f);
+/* One time step of rietkerk_DorFPE_2D_MultiSp compiled with -DSPB=3 (F/:4094-4462) on f[5][L*L]: means and cover of the entry state ->
+ * calc_gamma_vel_3Sp_NonRefugia (F/:3371-3483: per site and species, in the order of decreasing perception radius, ONE uniform for a new
+ * advection direction -- the vegetation's draw included -- then the perception field, ACCUMULATED onto its old value, a vanished
+ * consumer getting gamma = 1) -> vegetation Dornic -> five-field RK4 over f_DorFKE_3Sp -> FKE movement of grazer and predator -> clamp.
+ * M, v: {grazer, predator}; ft[2], gD[2], gV[2]: their movement terms and stencils; gamma [2][L*L] and veff [2][L*L][2] are state.
+ * Per-cell streams: the direction uniforms of a cell come from their own stream (PHILOX: seed xor 0xA0761D6478BD642F, uniform k for the
+ * k-th species in radius order; REPLAY: the slice after the vegetation's). */
+int tmo_step_fpe_3sp(const tmo_params *pveg, const tmo_cons3_params *pc, const double *M, const double *v, const tmo_fke_terms *ft,
+                     const double *const *gD, const double *const *gV, const int32_t *central, int n_central, double fr1, double fr2,
+                     tmo_rng *rng, double *f, double *gamma, double *veff, int trig_libm, const double *means);
 
 #ifdef __cplusplus
 }

@@ -151,8 +151,9 @@ void tmo_gamma_3sp(int L, const double *veg, const double *graz, const double *p
     }
 }
 
-/* f_2Dor_3Sp R/:2607-2650 */
-static void f_2dor_3sp(const tmo_cons3_params *p, double *f, const double *Y)
+/* f_2Dor_3Sp R/:2607-2650.  fpe != 0: f_DorFKE_3Sp F/:2611-2650, which carries the consumers' mortalities -M[1] G, -M[2] Pr in the
+ * reaction terms (F/:2636, 2639; in Rietkerk_FD they sit in the consumers' Dornic beta) */
+static void f_2dor_3sp(const tmo_cons3_params *p, double *f, const double *Y, int fpe, double M1, double M2)
 {
     const int g = p->L, n = g * g;
     const double cgmax = p->c * p->gmax, K2W0 = p->K2 * p->W0, A01H01 = p->A01 * p->H01, A12H12 = p->A12 * p->H12;   /* R/:2614 */
@@ -165,6 +166,10 @@ static void f_2dor_3sp(const tmo_cons3_params *p, double *f, const double *Y)
         f[i] = cgmax * W[i] * P[i] / (W[i] + p->K1) - (p->A01 * P[i] / (1 + A01H01 * P[i])) * G[i];                     /* R/:2633 */
         f[n + i] = (EA1 * P[i] / (1 + A01H01 * P[i])) * G[i] - p->A12 * G[i] / (1 + A12H12 * G[i]) * R[i];              /* R/:2635-2636 */
         f[2 * n + i] = (EA2 * G[i] / (1 + A12H12 * G[i])) * R[i];                                                      /* R/:2638 */
+        if (fpe) {
+            f[n + i] = (EA1 * P[i] / (1 + A01H01 * P[i])) * G[i] - M1 * G[i] - p->A12 * G[i] / (1 + A12H12 * G[i]) * R[i];   /* F/:2636-2637 */
+            f[2 * n + i] = (EA2 * G[i] / (1 + A12H12 * G[i])) * R[i] - M2 * R[i];                                        /* F/:2639 */
+        }
         f[3 * n + i] = p->alpha * (P[i] + K2W0) / (P[i] + p->K2) * O[i] - p->gmax * W[i] * P[i] / (W[i] + p->K1) - p->rW * W[i]
                      + (p->Dw) * (W[up] + W[dn] + W[lf] + W[rt] - 4 * W[i]);                                           /* R/:2640-2641 */
         f[4 * n + i] = p->a - p->alpha * (P[i] + K2W0) / (P[i] + p->K2) * O[i]
@@ -173,20 +178,25 @@ static void f_2dor_3sp(const tmo_cons3_params *p, double *f, const double *Y)
 }
 
 /* RK4_Integrate_Stochastic_MultiSp R/:2652-2720: one step in place on f[5][L*L] */
-int tmo_rk4_3sp(const tmo_cons3_params *p, double *f)
+static int rk4_3sp(const tmo_cons3_params *p, double *f, int fpe, double M1, double M2);
+int tmo_rk4_3sp(const tmo_cons3_params *p, double *f) { return rk4_3sp(p, f, 0, 0.0, 0.0); }
+/* RK4_Integrate_Stochastic_MultiSp of Rietkerk_FPE, F/:2652-2720, over f_DorFKE_3Sp */
+int tmo_rk4_fpe_3sp(const tmo_cons3_params *p, double M1, double M2, double *f) { return rk4_3sp(p, f, 1, M1, M2); }
+
+static int rk4_3sp(const tmo_cons3_params *p, double *f, int fpe, double M1, double M2)
 {
     if (!p || p->L < 1) return -1;
     const size_t n5 = (size_t)5 * p->L * p->L;
     const double dt2 = p->dt / 2.0, dt6 = p->dt / 6.0;
     double *K1 = malloc(sizeof(double) * n5 * 5), *K2 = K1 + n5, *K3 = K2 + n5, *K4 = K3 + n5, *Y = K4 + n5;
     if (!K1) return -1;
-    f_2dor_3sp(p, K1, f);
+    f_2dor_3sp(p, K1, f, fpe, M1, M2);
     for (size_t i = 0; i < n5; i++) Y[i] = f[i] + (dt2) * K1[i];
-    f_2dor_3sp(p, K2, Y);
+    f_2dor_3sp(p, K2, Y, fpe, M1, M2);
     for (size_t i = 0; i < n5; i++) Y[i] = f[i] + (dt2) * K2[i];
-    f_2dor_3sp(p, K3, Y);
+    f_2dor_3sp(p, K3, Y, fpe, M1, M2);
     for (size_t i = 0; i < n5; i++) Y[i] = f[i] + (p->dt) * K3[i];
-    f_2dor_3sp(p, K4, Y);
+    f_2dor_3sp(p, K4, Y, fpe, M1, M2);
     for (size_t i = 0; i < n5; i++) f[i] += (dt6) * (K1[i] + 2.0 * K2[i] + 2.0 * K3[i] + K4[i]);   /* R/:2691 */
     free(K1);
     return 0;

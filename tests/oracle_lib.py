@@ -114,6 +114,9 @@ def oracle():
         L.tmo_rk4_3sp.argtypes = [C.POINTER(OCons3Params), dp]
         L.tmo_step_3sp.argtypes = [C.POINTER(OParams), C.POINTER(OGrazParams), C.POINTER(OGrazParams), C.POINTER(OCons3Params),
                                    C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int, dp]
+        L.tmo_rk4_fpe_3sp.argtypes = [C.POINTER(OCons3Params), C.c_double, C.c_double, dp]
+        L.tmo_step_fpe_3sp.argtypes = [C.POINTER(OParams), C.POINTER(OCons3Params), dp, dp, C.POINTER(OFkeTerms), C.POINTER(dp), C.POINTER(dp),
+                                       C.POINTER(C.c_int32), C.c_int, C.c_double, C.c_double, C.POINTER(ORng), dp, dp, dp, C.c_int, dp]
         L.tmo_step_fpe_2sp.argtypes = [C.POINTER(OParams), C.POINTER(OConsParams), C.c_double, C.POINTER(OFkeTerms), dp, dp,
                                        C.POINTER(C.c_int32), C.c_int, C.c_double, C.POINTER(ORng), dp, dp, dp, dp]
         L.tmo_rk4_fpe_2sp.argtypes = [C.POINTER(OConsParams), C.c_double, dp]
@@ -316,6 +319,35 @@ def step_3sp(pv, pg1, pg2, pc, central, fr1, fr2, rng, f, gamma, trig_libm=False
                                fr1, fr2, C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0, None if m is None else ptr(m))
     assert rc == 0
     return veff
+
+
+def fpe_runner3_params(L, par, derived):
+    """Oracle parameter blocks of the Rietkerk_FPE SPB = 3 runner from the vector of tests/golden/make_fpe_runner3_golden.py (the SPB = 3
+    runner vector plus dtAdv1, dtAdv2) and the [2][8] constants set_global_FKE_params derived for grazer and predator.
+    Returns (pv, pc, M[2], v[2], terms (OFkeTerms * 2), gD[2], gV[2], disc radius, fr1, fr2)."""
+    pv, pg1, pg2, pc, R, fr1, fr2 = runner3_params(L, par[:31])
+    pv.clamp_eps, pv.clamp_lo = float(derived[0][7]), 0.0                     # F/:4458
+    terms = (OFkeTerms * 2)()
+    gD, gV = [], []
+    for s in range(2):
+        d = derived[s]
+        bD, b1, b2 = int(d[4]), int(d[5]), int(d[6])
+        terms[s] = OFkeTerms(L, bD, b1, b2, b1, b2, float(d[3]), float(d[7]))   # CPU path: (.first, .second) on both axes, F/:3640
+        sig = float(par[15 + s])                                                  # sigma[s], F/:3769-3771
+        gD.append(fke_gaussian(sig, bD)); gV.append(fke_gaussian(sig, b1))
+    M = np.array([par[25], par[26]], dtype=np.float64)
+    v = np.array([par[17], par[18]], dtype=np.float64)
+    return pv, pc, M, v, terms, gD, gV, R, fr1, fr2
+
+
+def step_fpe_3sp(pv, pc, M, v, terms, gD, gV, central, fr1, fr2, rng, f, gamma, veff, trig_libm=False, means=None):
+    """One Rietkerk_FPE SPB = 3 runner step (tmo_step_fpe_3sp) in place on f [5][L*L], gamma [2][L*L] and veff [2][L*L][2]."""
+    cen = np.ascontiguousarray(central, dtype=np.int32)
+    m = None if means is None else np.array(means, dtype=np.float64)
+    pD, pV = (dp * 2)(ptr(gD[0]), ptr(gD[1])), (dp * 2)(ptr(gV[0]), ptr(gV[1]))
+    rc = oracle().tmo_step_fpe_3sp(C.byref(pv), C.byref(pc), ptr(M), ptr(v), terms, pD, pV, cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen),
+                                   fr1, fr2, C.byref(rng), ptr(f), ptr(gamma), ptr(veff), 1 if trig_libm else 0, None if m is None else ptr(m))
+    assert rc == 0
 
 
 def fpe_runner_params(L, par, derived):

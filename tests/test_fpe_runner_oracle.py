@@ -66,3 +66,39 @@ def test_fpe_flavours_differ_from_fd_only_where_the_reference_does():
     assert np.array_equal(a, b)                                  # M1 = 0: the FD reaction terms
     assert O.oracle().tmo_rk4_fpe_2sp(O.C.byref(pc), 0.5, O.ptr(b)) == 0
     assert np.all(b[1] < a[1])
+
+
+RUN3 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "runner_fpe_3sp.npz"))
+G3 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "runner_3sp.npz"))
+
+
+@pytest.mark.parametrize("name", ["mixed", "no_predators"])
+def test_fpe_3sp_runner_frames_match_reference(name):
+    """SPB = 3: calc_gamma_vel_3Sp_NonRefugia (a direction uniform per site and species in radius order, the vegetation's included; the
+    perception fields accumulated onto their old values) -> vegetation Dornic -> five-field RK4 with both mortalities -> FKE movement
+    of grazer and predator -> clamp: the oracle consumes the same uniforms in the same order and reproduces the runner's frames."""
+    L = int(RUN3[name + "_L"])
+    seed, n_u = [int(x) for x in RUN3[name + "_seed"]]
+    pv, pc, M, v, terms, gD, gV, R, fr1, fr2 = O.fpe_runner3_params(L, RUN3[name + "_par"], RUN3[name + "_derived"])
+    central = G3["central_R%d" % R]
+    u = np.random.RandomState(seed).random_sample(n_u)
+    rng = O.make_rng(O.SRC_SEQ, u=u, pos=1)
+    f = RUN3[name + "_init"].astype(np.float64).copy()
+    gamma, veff = np.zeros((2, L * L)), np.zeros((2, L * L, 2))
+    frames, times = RUN3[name + "_frames"], RUN3[name + "_times"]
+    dt = pv.dt
+    t, fi = 0.0, 0
+    t_max = times[-1]
+    while t < t_max + dt:
+        if fi < len(times) and abs(t - times[fi]) < 1e-9:
+            ref = frames[fi]
+            for s_ in (0, 1, 2):
+                assert np.array_equal(f[s_] > 0, ref[s_] > 0), "occupancy of field %d at t=%g" % (s_, t)
+            err = np.abs(f - ref) / np.maximum(np.abs(ref), 1e-300)
+            err[(ref == 0) & (f == 0)] = 0
+            assert err.max() <= 1e-12, "frame %d (t=%g): %.3e" % (fi, t, err.max())
+            fi += 1
+        O.step_fpe_3sp(pv, pc, M, v, terms, gD, gV, central, fr1, fr2, rng, f, gamma, veff, trig_libm=True)
+        t += dt
+    assert fi == len(times) and rng.overflow == 0
+    assert rng.pos == int(RUN3[name + "_consumed"]) - 1
