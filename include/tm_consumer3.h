@@ -42,6 +42,18 @@ const char *tm_cons3_last_error(const tm_cons3_ctx *);   /* ctx == NULL: error o
 struct tm_params;
 int tm_cons3_setup(tm_cons3_ctx *, const struct tm_params *veg, const tm_graz_params *graz, const tm_graz_params *pred,
                    const tm_cons3_params *pc, const int32_t *central, int n_central, double fr_graz, double fr_pred);
+/* Rietkerk_FPE flavour of the step: the time-loop body of rietkerk_DorFPE_2D_MultiSp compiled with -DSPB=3,
+ * Rietkerk_FPE/rietkerk_bjork_FKE.cpp:4094-4462 -- calc_gamma_vel_3Sp_NonRefugia (:3371-3483: per site one uniform per species for a new
+ * advection direction, in the order of decreasing perception radius, the vegetation's draw included; the perception fields ACCUMULATED
+ * onto their old values; a vanished consumer gets gamma = 1) -> vegetation Dornic -> five-field RK4 over f_DorFKE_3Sp (:2611-2650: both
+ * mortalities in the reaction terms; no consumer has a Dornic update) -> advdiff_FKE_MultiSp on grazer and predator (:4308, the kernels of
+ * tm_fke.h on the resident fields) -> clamp with the veg->clamp_eps / clamp_lo given to setup (1e-10 and 0 in the reference, :4458).
+ * t[2]: movement windows and stencil sizes of grazer and predator (struct tm_fke_terms, CPU-path convention); gauss_D[2], gauss_V[2]:
+ * their stencils (host).  The directions' Philox streams use the seed xor 0xA0761D6478BD642F; in tm_cons3_replay the second array
+ * carries them (cell i, k-th species in radius order: u[i*stride + k]) and the third is ignored.  Eighteen launches per step.
+ * t == NULL switches back to the Rietkerk_FD flavour. */
+struct tm_fke_terms;
+int tm_cons3_set_fpe(tm_cons3_ctx *, const struct tm_fke_terms *t, const double *const *gauss_D, const double *const *gauss_V, double M1, double M2);
 /* fields [5][L*L]; gamma [2][L*L] (grazer, predator) or NULL (zeros; the three-species perception function assigns, so the entry
  * values only matter for a species it skips) */
 int tm_cons3_upload(tm_cons3_ctx *, const double *fields, const double *gamma);

@@ -326,6 +326,42 @@ int emu_cons_step3(int L, const double *par3, const double *cpar, const int *cen
     dyn_out[3] = dyn.occ_veg; dyn_out[4] = (double)dyn.eff[0]; dyn_out[5] = (double)dyn.eff[1];
     return 0;
 }
+// The Rietkerk_FPE flavour of the SPB = 3 step (cons_step3_enqueue with k.fpe).  fke[2][5] = {bound_D, v_row_lo, v_row_hi, v_col_lo,
+// v_col_hi} of grazer and predator; pref[2], eps; gD/gV: their stencils; Mm[2]: mortalities.  u_veg / u_dir: replay arrays or nullptr.
+int emu_cons_step3_fpe(int L, const double *par3, const double *cpar, const int *central, int n_central, unsigned long long seed,
+                       unsigned trial, unsigned step0, int nsteps, const double *u_veg, const double *u_dir, unsigned stride,
+                       const int *fke, const double *pref, double eps, const double *gD1, const double *gV1, const double *gD2,
+                       const double *gV2, const double *Mm, double *fields, double *gamma, double *veff, double *dyn_out,
+                       unsigned long long *overflow)
+{
+    const size_t n = (size_t)L * L;
+    Cons3Consts cc = cons3_consts(cpar[0], cpar[1], cpar[2], cpar[3], cpar[4], cpar[5], cpar[6], cpar[7], cpar[8], cpar[9], cpar[10],
+                                  cpar[11], cpar[12], cpar[13], cpar[14], cpar[15], cpar[16]);
+    cc.fpe = 1; cc.M1 = Mm[0]; cc.M2 = Mm[1];
+    const double gDc[2] = {par3[7], par3[8]}, gv[2] = {par3[9], par3[10]}, gM[2] = {par3[11], par3[12]}, gs[2] = {par3[13], par3[14]};
+    Step3Consts k = step3_consts(L, n_central, par3[16], par3[17], par3[0], par3[1], par3[2], par3[3], par3[4], par3[5], par3[6],
+                                 gDc, gv, gM, gs, par3[15], cc);
+    k.fpe = 1;
+    for (int s = 0; s < 2; s++) {
+        FkeTerms &t = k.fke[s];
+        t.L = L; t.bD = fke[5 * s]; t.rlo = fke[5 * s + 1]; t.rhi = fke[5 * s + 2]; t.clo = fke[5 * s + 3]; t.chi = fke[5 * s + 4];
+        t.pref = pref[s]; t.eps = eps;
+    }
+    std::vector<double> star(3 * n), ya(5 * n), yb(5 * n), acc(5 * n), part(4 * kConsReduceBlocks);
+    Step3Dyn dyn{};
+    Step3Buffers b{};
+    b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.replay[0] = u_veg; b.replay[1] = u_dir; b.replay[2] = u_dir; b.stride = stride;
+    b.fke_gD[0] = gD1; b.fke_gV[0] = gV1; b.fke_gD[1] = gD2; b.fke_gV[1] = gV2;
+    *overflow = 0;
+    auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
+    for (int s = 0; s < nsteps; s++) cons_step3_enqueue(launch, k, b, seed, trial, step0 + (unsigned)s);
+    const double cells = (double)L * (double)L;
+    for (int s = 0; s < 3; s++) dyn_out[s] = dyn.sum[s] / cells;
+    dyn_out[3] = dyn.occ_veg; dyn_out[4] = (double)dyn.eff[0]; dyn_out[5] = (double)dyn.eff[1];
+    return 0;
+}
 // nsteps RK4 steps of the noise-off DP path through the product's stage kernel (csrc/tm_dpdet.cuh), in place on rho[L*L]
 int emu_dp_noise_off(int L, double a, double b, double D, double dt, double dx, double *rho, int nsteps)
 {

@@ -164,7 +164,7 @@ class Cons3Params(C.Structure):
                                                          "dt a c gmax alpha rW W0 K1 K2 Dw Do A01 H01 E1 A12 H12 E2".split()]
 
 
-CONS3_ABI_SYMBOLS = ["tm_cons3_create", "tm_cons3_destroy", "tm_cons3_last_error", "tm_cons3_setup", "tm_cons3_upload", "tm_cons3_run",
+CONS3_ABI_SYMBOLS = ["tm_cons3_create", "tm_cons3_destroy", "tm_cons3_last_error", "tm_cons3_setup", "tm_cons3_set_fpe", "tm_cons3_upload", "tm_cons3_run",
                      "tm_cons3_replay", "tm_cons3_download", "tm_cons3_last_ms"]
 _bound3 = False
 
@@ -180,6 +180,7 @@ def _lib3():
             "tm_cons3_last_error": (C.c_char_p, [vp]),
             "tm_cons3_setup": (i, [vp, C.POINTER(Params), C.POINTER(GrazParams), C.POINTER(GrazParams), C.POINTER(Cons3Params),
                                    C.POINTER(C.c_int32), i, C.c_double, C.c_double]),
+            "tm_cons3_set_fpe": (i, [vp, vp, C.POINTER(dp), C.POINTER(dp), C.c_double, C.c_double]),
             "tm_cons3_upload": (i, [vp, dp, dp]),
             "tm_cons3_run": (i, [vp, C.c_uint64, C.c_uint32, C.c_uint32, i]),
             "tm_cons3_replay": (i, [vp, dp, dp, dp, C.c_uint32]),
@@ -224,6 +225,17 @@ class ConsumerOps3:
         cen = np.ascontiguousarray(central, dtype=np.int32)
         self._ck(self._l.tm_cons3_setup(self._ctx, C.byref(veg), C.byref(graz), C.byref(pred), C.byref(cons),
                                         cen.ctypes.data_as(C.POINTER(C.c_int32)), len(cen), fr_graz, fr_pred))
+
+    def set_fpe(self, terms, gauss_D, gauss_V, M1, M2):
+        """Rietkerk_FPE flavour (tm_cons3_set_fpe); terms: (fke.FkeTerms * 2) for grazer and predator, or None for Rietkerk_FD."""
+        dp = C.POINTER(C.c_double)
+        if terms is None:
+            self._ck(self._l.tm_cons3_set_fpe(self._ctx, None, None, None, 0.0, 0.0))
+            return
+        gD = [np.ascontiguousarray(x, dtype=np.float64) for x in gauss_D]
+        gV = [np.ascontiguousarray(x, dtype=np.float64) for x in gauss_V]
+        pD, pV = (dp * 2)(_dptr(gD[0]), _dptr(gD[1])), (dp * 2)(_dptr(gV[0]), _dptr(gV[1]))
+        self._ck(self._l.tm_cons3_set_fpe(self._ctx, C.cast(terms, C.c_void_p), pD, pV, float(M1), float(M2)))
 
     def upload(self, fields, gamma=None):
         f = np.ascontiguousarray(fields, dtype=np.float64)

@@ -1,6 +1,7 @@
 // tm_consumer3.cu -- C ABI (include/tm_consumer3.h) over the SPB = 3 launch chain (tm_consumer3.cuh).  sm_100a only; no CPU path.
 #include "../../include/tm_consumer3.h"
 #include "../../include/tm_lattice.h" // TM_E_* codes, struct tm_params
+#include "../../include/tm_fke.h"     // tm_fke_terms
 #include "tm_consumer3.cuh"
 
 #include <cuda_runtime.h>
@@ -21,6 +22,7 @@ struct tm_cons3_ctx {
     int *d_central = nullptr;
     unsigned long long *d_ovf = nullptr;
     double *d_replay = nullptr; size_t replay_cap = 0;
+    double *d_fke_gD[2] = {nullptr, nullptr}, *d_fke_gV[2] = {nullptr, nullptr};   // FPE flavour: the consumers' movement stencils
     bool ready = false;
     Step3Consts k{};
     int n_launches = 0;
@@ -50,6 +52,7 @@ Step3Buffers buffers(tm_cons3_ctx *c)
     Step3Buffers b{};
     b.state = c->d_state; b.star = c->d_star; b.ya = c->d_ya; b.yb = c->d_yb; b.acc = c->d_acc; b.gamma = c->d_gamma; b.veff = c->d_veff;
     b.part = c->d_part; b.dyn = c->d_dyn; b.central = c->d_central; b.overflow = c->d_ovf;
+    for (int s = 0; s < 2; s++) { b.fke_gD[s] = c->d_fke_gD[s]; b.fke_gV[s] = c->d_fke_gV[s]; }
     return b;
 }
 } // namespace
@@ -64,6 +67,7 @@ int tm_cons3_destroy(tm_cons3_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     cudaFree(c->d_state); cudaFree(c->d_star); cudaFree(c->d_ya); cudaFree(c->d_yb); cudaFree(c->d_acc); cudaFree(c->d_gamma);
+    for (int s = 0; s < 2; s++) { cudaFree(c->d_fke_gD[s]); cudaFree(c->d_fke_gV[s]); }
     cudaFree(c->d_veff); cudaFree(c->d_part); cudaFree(c->d_dyn); cudaFree(c->d_central); cudaFree(c->d_ovf); cudaFree(c->d_replay);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -126,6 +130,39 @@ int tm_cons3_setup(tm_cons3_ctx *c, const tm_params *veg, const tm_graz_params *
     return TM_OK;
 }
 
+int tm_cons3_set_fpe(tm_cons3_ctx *c, const tm_fke_terms *t, const double *const *gauss_D, const double *const *gauss_V, double M1, double M2)
+{
+    if (!c) return TM_E_ARG;
+    if (!c->ready) { c->err = "tm_cons3_set_fpe: call tm_cons3_setup first"; return TM_E_ARG; }
+    if (!t) {                                      // back to the Rietkerk_FD flavour
+        c->k.fpe = 0; c->k.c.fpe = 0; c->k.c.M1 = 0.0; c->k.c.M2 = 0.0;
+        return TM_OK;
+    }
+    if (!gauss_D || !gauss_V) { c->err = "tm_cons3_set_fpe: stencils are required"; return TM_E_ARG; }
+    for (int s = 0; s < 2; s++) {
+        const int vmax = fke_max3(fke_max3(t[s].v_row_lo, t[s].v_row_hi, t[s].v_col_lo), t[s].v_col_hi, 0);
+        if (!gauss_D[s] || !gauss_V[s] || t[s].bound_D < 0 || t[s].v_row_lo < 0 || t[s].v_row_hi < 0 || t[s].v_col_lo < 0 || t[s].v_col_hi < 0 ||
+            t[s].bound_D > kFkeMaxBound || vmax > kFkeMaxBound || t[s].n_gauss_D < t[s].bound_D + 1 || t[s].n_gauss_V < vmax + 1) {
+            c->err = "tm_cons3_set_fpe: window bounds must lie in [0, 512] and the stencils must cover them";
+            return TM_E_ARG;
+        }
+    }
+    C3_CK(cudaSetDevice(c->device));
+    C3_CK(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < 2; s++) {
+        cudaFree(c->d_fke_gD[s]); cudaFree(c->d_fke_gV[s]); c->d_fke_gD[s] = c->d_fke_gV[s] = nullptr;
+        C3_CK(cudaMalloc(&c->d_fke_gD[s], t[s].n_gauss_D * sizeof(double)));
+        C3_CK(cudaMalloc(&c->d_fke_gV[s], t[s].n_gauss_V * sizeof(double)));
+        C3_CK(cudaMemcpy(c->d_fke_gD[s], gauss_D[s], t[s].n_gauss_D * sizeof(double), cudaMemcpyHostToDevice));
+        C3_CK(cudaMemcpy(c->d_fke_gV[s], gauss_V[s], t[s].n_gauss_V * sizeof(double), cudaMemcpyHostToDevice));
+        FkeTerms &f = c->k.fke[s];
+        f.L = c->L; f.bD = t[s].bound_D; f.rlo = t[s].v_row_lo; f.rhi = t[s].v_row_hi; f.clo = t[s].v_col_lo; f.chi = t[s].v_col_hi;
+        f.pref = t[s].mu_vel_prefactor; f.eps = t[s].epsilon;
+    }
+    c->k.fpe = 1; c->k.c.fpe = 1; c->k.c.M1 = M1; c->k.c.M2 = M2;
+    return TM_OK;
+}
+
 int tm_cons3_upload(tm_cons3_ctx *c, const double *fields, const double *gamma)
 {
     if (!c) return TM_E_ARG;
@@ -150,7 +187,7 @@ int tm_cons3_run(tm_cons3_ctx *c, uint64_t seed, uint32_t trial, uint32_t step0,
     for (int s = 0; s < nsteps; s++) cons_step3_enqueue(CudaLaunch3{c->stream}, c->k, b, seed, trial, step0 + (uint32_t)s);
     C3_CK(cudaGetLastError());
     C3_CK(cudaEventRecord(c->ev1, c->stream));
-    c->n_launches = kStep3Launches * nsteps;
+    c->n_launches = step3_launches(c->k.fpe) * nsteps;
     return TM_OK;
 }
 
@@ -174,7 +211,7 @@ int tm_cons3_replay(tm_cons3_ctx *c, const double *u_veg, const double *u_graz, 
     cons_step3_enqueue(CudaLaunch3{c->stream}, c->k, b, 0, 0, 0);
     C3_CK(cudaGetLastError());
     C3_CK(cudaEventRecord(c->ev1, c->stream));
-    c->n_launches = kStep3Launches;
+    c->n_launches = step3_launches(c->k.fpe);
     C3_CK(cudaStreamSynchronize(c->stream));   // the uniform arrays are the caller's again
     return TM_OK;
 }

@@ -20,8 +20,10 @@ struct Step3Dyn {
     double rho_inverse[3];       // 1 / max(<rho_s>, 1e-12)                                   R/:3171
     int eff[2];                  // disc offsets summed by grazer / predator                  R/:3199, 3204
     int zero[2];                 // gamma_s = 0 everywhere: <rho_s> or <rho_{s-1}> below 1e-12  R/:3206-3209
-    int skip[2];                 // <rho_s> == 0: the species' Dornic loop is skipped          R/:3910
+    int skip[2];                 // <rho_s> == 0: the species' Dornic loop is skipped          R/:3910 (FPE flavour: always)
     int pred_gone, pad_;         // <Pr> below 1e-12: the grazer's sum is not discounted      R/:3221
+    int one[2];                  // FPE flavour: <rho_s> below 1e-12: gamma_s = 1              F/:3430
+    int maxdisp[2][2];           // FPE flavour: largest |displacement| of each consumer's movement step, zeroed every step
 };
 
 struct Reduce3Args {
@@ -62,6 +64,7 @@ struct Finalize3Args {
     double fr1, fr2;             // pR[s] / (dx r_max_effective), R/:3409
     const double *part;
     Step3Dyn *dyn;
+    int fpe;                     // Rietkerk_FPE flavour: calc_gamma_vel_3Sp_NonRefugia F/:3371-3483
 };
 
 TMC_G void cons3_finalize_kernel(const Finalize3Args A)
@@ -93,6 +96,13 @@ TMC_G void cons3_finalize_kernel(const Finalize3Args A)
         d.eff[s - 1] = eff;
         d.zero[s - 1] = (fr[s - 1] != 0.0 && (avg[s] < eps || avg[s - 1] < eps)) ? 1 : 0;   // R/:3206-3209
         d.skip[s - 1] = (avg[s] == 0.0) ? 1 : 0;                      // R/:3910
+        d.one[s - 1] = 0;
+        if (A.fpe) {                                                  // F/:3430-3433: a vanished consumer gets gamma = 1
+            d.one[s - 1] = (fr[s - 1] != 0.0 && avg[s] < eps) ? 1 : 0;
+            d.zero[s - 1] = (fr[s - 1] != 0.0 && !d.one[s - 1] && avg[s - 1] < eps) ? 1 : 0;
+            d.skip[s - 1] = 1;                                        // no consumer has a Dornic update in Rietkerk_FPE: rho* = rho
+        }
+        d.maxdisp[s - 1][0] = 0; d.maxdisp[s - 1][1] = 0;
     }
     d.pred_gone = avg[2] < eps ? 1 : 0;                               // R/:3221
     d.pad_ = 0;
@@ -106,6 +116,7 @@ struct Gamma3Args {
     const int *offsets;          // [n_central][2]
     double *gamma1, *gamma2;     // [L*L] each, OUT (assigned: R/:3239, 3248)
     const Step3Dyn *dyn;
+    int accumulate;              // FPE flavour: the disc sums are added onto the values the arrays hold (F/:3440-3456), and <rho_s> ~ 0 gives 1
 };
 
 // calc_gamma_3Sp_NonRefugia R/:3153-3268: gamma_1 = clamp01((sum_disc1 veg (1 - pred / <pred>)) / <veg> / eff1) (undiscounted when the
@@ -124,9 +135,10 @@ TMC_G void cons3_gamma_kernel(const Gamma3Args A)
     if (c_j >= g) return;
     const int i = c_i * g + c_j;
     if (A.fr1 != 0.0) {
-        if (d.zero[0]) A.gamma1[i] = 0.0;
+        if (d.one[0]) A.gamma1[i] = 1.0;
+        else if (d.zero[0]) A.gamma1[i] = 0.0;
         else {
-            double sum = 0.0;
+            double sum = A.accumulate ? A.gamma1[i] : 0.0;
             for (int k = 0; k < d.eff[0]; k++) {
                 int nx = c_i + off[2 * k], ny = c_j + off[2 * k + 1];
                 if (nx < 0 || nx >= g) { nx %= g; if (nx < 0) nx += g; }
@@ -141,9 +153,10 @@ TMC_G void cons3_gamma_kernel(const Gamma3Args A)
         }
     }
     if (A.fr2 != 0.0) {
-        if (d.zero[1]) A.gamma2[i] = 0.0;
+        if (d.one[1]) A.gamma2[i] = 1.0;
+        else if (d.zero[1]) A.gamma2[i] = 0.0;
         else {
-            double sum = 0.0;
+            double sum = A.accumulate ? A.gamma2[i] : 0.0;
             for (int k = 0; k < d.eff[1]; k++) {
                 int nx = c_i + off[2 * k], ny = c_j + off[2 * k + 1];
                 if (nx < 0 || nx >= g) { nx %= g; if (nx < 0) nx += g; }
@@ -161,6 +174,8 @@ struct Cons3Consts {
     double dt, dt2, dt6;
     double a, cgmax, gmax, alpha, rW, K1, K2, K2W0, Dw, Do;
     double A01, A01H01, EA1, A12, A12H12, EA2;
+    double M1, M2;               // FPE flavour: the consumers' mortalities, in the reaction terms (f_DorFKE_3Sp F/:2636, 2639)
+    int fpe, pad_;
 };
 
 inline Cons3Consts cons3_consts(double dt, double a, double c, double gmax, double alpha, double rW, double W0, double K1, double K2,
@@ -182,6 +197,10 @@ TMC_D void cons3_rhs(const Cons3Consts &c, double P, double G, double R, double 
     f[0] = c.cgmax * W * P / (W + c.K1) - (c.A01 * P / (1 + c.A01H01 * P)) * G;
     f[1] = (c.EA1 * P / (1 + c.A01H01 * P)) * G - c.A12 * G / (1 + c.A12H12 * G) * R;
     f[2] = (c.EA2 * G / (1 + c.A12H12 * G)) * R;
+    if (c.fpe) {                                                      // f_DorFKE_3Sp F/:2636-2639
+        f[1] = (c.EA1 * P / (1 + c.A01H01 * P)) * G - c.M1 * G - c.A12 * G / (1 + c.A12H12 * G) * R;
+        f[2] = (c.EA2 * G / (1 + c.A12H12 * G)) * R - c.M2 * R;
+    }
     f[3] = c.alpha * (P + c.K2W0) / (P + c.K2) * O - c.gmax * W * P / (W + c.K1) - c.rW * W + (c.Dw) * (Wu + Wd + Wl + Wr - 4 * W);
     f[4] = c.a - c.alpha * (P + c.K2W0) / (P + c.K2) * O + (c.Do) * (Ou + Od + Ol + Or_ - 4 * O);
 }
@@ -196,6 +215,7 @@ struct Rk3StageArgs {
     double *acc;                 // K1 (+ 2 K2 (+ 2 K3)) [5][L*L]
     double *out;                 // stage 4: the committed state (may alias base)
     double eps, lo;              // clamp R/:4176
+    int clamp;                   // stage 4: apply it (the FPE flavour clamps after the movement step instead)
 };
 
 // RK4_Integrate_Stochastic_MultiSp R/:2652-2720, one launch per stage (the SPB = 2 stage kernel with one more species)
@@ -221,7 +241,7 @@ TMC_G void cons3_rk4_stage_kernel(const Rk3StageArgs A)
         else if (A.stage < 4) { A.acc[k] = A.acc[k] + 2.0 * f[s]; A.Ynext[k] = b + (h) * f[s]; }
         else {
             double v = b + (A.c.dt6) * (A.acc[k] + f[s]);               // R/:2691
-            if (v < A.eps && v >= A.lo) v = 0.0;                        // R/:4176
+            if (A.clamp && v < A.eps && v >= A.lo) v = 0.0;             // R/:4176
             A.out[k] = v;
         }
     }
@@ -236,8 +256,67 @@ struct Step3Consts {
     double D[2], v[2], M[2], sigma[2];   // grazer, predator (GrazerArgs)
     double D0floor;              // diff_coefficient[0], R/:4014
     Cons3Consts c;
-    double eps, lo;              // clamp R/:4176
+    double eps, lo;              // clamp R/:4176 (FPE flavour: 1e-10 and 0, F/:4458)
+    int fpe;                     // 1: the time-loop body of rietkerk_DorFPE_2D_MultiSp (Rietkerk_FPE, -DSPB=3), see cons_step3_enqueue
+    FkeTerms fke[2];             // FPE flavour: movement windows of grazer and predator (set_global_FKE_params F/:195)
 };
+
+// FPE flavour: the advection directions of a site, calc_gamma_vel_3Sp_NonRefugia F/:3421-3424: one uniform per species in the order of
+// decreasing perception radius -- the vegetation's draw included -- from the cell's direction stream (Philox key: seed xor kDirSeedSalt)
+struct Dir3Args {
+    int L;
+    double fr1, fr2, v1, v2;
+    double *veff;                // [2][L*L][2]
+    unsigned long long seed; unsigned int trial, step;
+    const double *replay_u; unsigned int stride;
+    unsigned long long *overflow;
+};
+constexpr unsigned long long kDirSeedSalt = 0xA0761D6478BD642Full;
+
+template <bool REPLAY>
+TMC_G void cons3_direction_kernel(const Dir3Args A)
+{
+    const long long n = (long long)A.L * A.L;
+    const long long i = (long long)blockIdx.x * kConsThreads + threadIdx.x;
+    if (i >= n) return;
+    typename std::conditional<REPLAY, ReplaySrc, PhiloxSrc>::type src;
+    if constexpr (REPLAY) src.begin(A.replay_u + (size_t)i * A.stride, A.stride);
+    else src.begin((uint32_t)i, A.trial, A.step, A.seed);
+    const double fr[3] = {0.0, A.fr1, A.fr2}, vel[3] = {0.0, A.v1, A.v2};
+    int order[3] = {0, 1, 2};
+    for (int a = 0; a < 3; a++)
+        for (int b = a + 1; b < 3; b++)
+            if (fr[order[b]] > fr[order[a]]) { const int t = order[a]; order[a] = order[b]; order[b] = t; }
+    for (int o = 0; o < 3; o++) {
+        const int s = order[o];
+        const double ran = src.next();
+        if (s >= 1) {
+            double sn, cs;
+            sincos_turn128(128.0 * ran, sincos_table(), sn, cs);
+            A.veff[2 * ((s - 1) * n + i)] = vel[s] * cs; A.veff[2 * ((s - 1) * n + i) + 1] = vel[s] * sn;
+        }
+    }
+    if (src.overflow_count()) atomicAdd(A.overflow, (unsigned long long)src.overflow_count());
+}
+
+// FPE flavour, last launch of a step: the moved consumers replace fields 1 and 2, then `v < eps && v >= lo -> 0` on all five (F/:4458)
+struct Fpe3CommitArgs {
+    long long n;
+    double *state;               // [5][n]
+    const double *moved;         // [2][n]
+    double eps, lo;
+};
+
+TMC_G void cons3_fpe_commit_kernel(const Fpe3CommitArgs A)
+{
+    const long long i = (long long)blockIdx.x * kConsThreads + threadIdx.x;
+    if (i >= A.n) return;
+    for (int s = 0; s < 5; s++) {
+        double v = (s == 1 || s == 2) ? A.moved[(s - 1) * A.n + i] : A.state[s * A.n + i];
+        if (v < A.eps && v >= A.lo) v = 0.0;
+        A.state[s * A.n + i] = v;
+    }
+}
 
 struct Step3Buffers {
     double *state;               // [5][n] P, G, Pr, W, O
@@ -248,8 +327,9 @@ struct Step3Buffers {
     Step3Dyn *dyn;
     const int *central;
     unsigned long long *overflow;
-    const double *replay[3];     // all null: Philox; else [n][stride] for vegetation, grazer, predator
+    const double *replay[3];     // all null: Philox; else [n][stride] for vegetation, grazer, predator (FPE flavour: [1] = directions)
     unsigned int stride;
+    const double *fke_gD[2], *fke_gV[2];   // FPE flavour: the consumers' Gaussian stencils (device)
 };
 
 constexpr unsigned long long kPredatorSeedSalt = 0xD1B54A32D192ED03ull;   // the predator's Philox streams (the grazer's: kGrazerSeedSalt)
@@ -294,12 +374,20 @@ inline void cons_step3_enqueue(Launch &&launch, const Step3Consts &k, Step3Buffe
     else        launch(grazer_dornic_kernel<false, true>, V, grid, kConsThreads, 0);
     Reduce3Args R{n, b.state, b.state + n, b.state + 2 * n, b.part};
     launch(cons3_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 4 * kConsReduceThreads);
-    Finalize3Args F{L, kConsReduceBlocks, k.n_central, k.fr1, k.fr2, b.part, b.dyn};
+    Finalize3Args F{L, kConsReduceBlocks, k.n_central, k.fr1, k.fr2, b.part, b.dyn, k.fpe};
     launch(cons3_finalize_kernel, F, 1, 32, sizeof(double) * 128);
+    if (k.fpe) {                                                        // the new advection vectors of this step, F/:3421-3424
+        Dir3Args Dd{};
+        Dd.L = L; Dd.fr1 = k.fr1; Dd.fr2 = k.fr2; Dd.v1 = k.v[0]; Dd.v2 = k.v[1]; Dd.veff = b.veff;
+        Dd.seed = seed ^ kDirSeedSalt; Dd.trial = trial; Dd.step = step; Dd.replay_u = b.replay[1]; Dd.stride = b.stride; Dd.overflow = b.overflow;
+        const unsigned gcell = (unsigned)((n + kConsThreads - 1) / kConsThreads);
+        if (replay) launch(cons3_direction_kernel<true>, Dd, gcell, kConsThreads, 0);
+        else        launch(cons3_direction_kernel<false>, Dd, gcell, kConsThreads, 0);
+    }
     Gamma3Args G{};
     G.L = L; G.n_central = k.n_central; G.fr1 = k.fr1; G.fr2 = k.fr2;
     G.veg = b.state; G.graz = b.state + n; G.pred = b.state + 2 * n; G.offsets = b.central;
-    G.gamma1 = b.gamma; G.gamma2 = b.gamma + n; G.dyn = b.dyn;
+    G.gamma1 = b.gamma; G.gamma2 = b.gamma + n; G.dyn = b.dyn; G.accumulate = k.fpe;
     launch(cons3_gamma_kernel, G, grid, kConsThreads, sizeof(int) * 2 * k.n_central);
     const unsigned long long salt[2] = {kGrazerSeedSalt, kPredatorSeedSalt};
     for (int s = 0; s < 2; s++) {                                       // the consumers' Dornic loop, R/:3908-4114, s + 1 = 1, 2
@@ -309,16 +397,32 @@ inline void cons_step3_enqueue(Launch &&launch, const Step3Consts &k, Step3Buffe
         Z.prev = b.state + (s + 1) * n; Z.out = b.star + (s + 1) * n; Z.gamma = b.gamma + s * n; Z.veff = b.veff + 2 * s * n;
         Z.replay_u = b.replay[s + 1]; Z.dyn = nullptr; Z.skip_flag = &b.dyn->skip[s];
         Z.seed = seed ^ salt[s];
+        if (k.fpe) Z.replay_u = b.replay[0];                            // never read: the FPE flavour forces the skip path (rho* = rho)
         if (replay) launch(grazer_dornic_kernel<true, false>, Z, grid, kConsThreads, 0);
         else        launch(grazer_dornic_kernel<false, false>, Z, grid, kConsThreads, 0);
     }
     Rk3StageArgs A{};
     A.L = L; A.c = k.c; A.base = b.state; A.base_sp = b.star; A.acc = b.acc; A.out = b.state; A.eps = k.eps; A.lo = k.lo;
+    A.clamp = k.fpe ? 0 : 1;                                            // Rietkerk_FPE clamps after the movement step (F/:4458)
     A.stage = 1; A.Y = b.state; A.Ynext = b.ya; launch(cons3_rk4_stage_kernel, A, grid, kConsThreads, 0);
     A.stage = 2; A.Y = b.ya; A.Ynext = b.yb; launch(cons3_rk4_stage_kernel, A, grid, kConsThreads, 0);
     A.stage = 3; A.Y = b.yb; A.Ynext = b.ya; launch(cons3_rk4_stage_kernel, A, grid, kConsThreads, 0);
     A.stage = 4; A.Y = b.ya; A.Ynext = nullptr; launch(cons3_rk4_stage_kernel, A, grid, kConsThreads, 0);
+    if (!k.fpe) return;
+    // advdiff_FKE_MultiSp (F/:4308) on the two consumer fields the RK4 left, one after the other (shared scratch: yb = the three source
+    // masses, U1, U2; acc = the two moved fields, then the displacements), then the commit + clamp
+    for (int s = 0; s < 2; s++) {
+        FkeArgs M{};
+        M.t = k.fke[s];
+        M.rho = b.state + (s + 1) * n; M.gamma = b.gamma + s * n; M.veff = b.veff + 2 * s * n; M.out = b.acc + s * n;
+        M.sA = b.yb; M.sB = b.yb + n; M.sD = b.yb + 2 * n; M.U1 = b.yb + 3 * n; M.U2 = b.yb + 4 * n;
+        M.disp = reinterpret_cast<int *>(b.acc + 2 * n); M.maxdisp = b.dyn->maxdisp[s];
+        M.gD = b.fke_gD[s]; M.gV = b.fke_gV[s];
+        fke_move_enqueue(launch, M);
+    }
+    Fpe3CommitArgs C{n, b.state, b.acc, k.eps, k.lo};
+    launch(cons3_fpe_commit_kernel, C, (unsigned)((n + kConsThreads - 1) / kConsThreads), kConsThreads, 0);
 }
-constexpr int kStep3Launches = 10;
+inline int step3_launches(int fpe) { return fpe ? 18 : 10; }
 
 } // namespace tml

@@ -2,6 +2,8 @@
 #include "tm_host_3sp.h"
 #include "tm_host.h"
 #include "tm_host_2sp.h"   // computeNeighboringSitesCentral (R/:1661, the same for every SPB)
+#include "tm_host_fke.h"   // fke_globals, precompute_gaussian
+#include "../../include/tm_fke.h"
 #include "../../include/tm_consumer3.h"
 #include "../../include/tm_lattice.h"
 
@@ -61,11 +63,13 @@ double mean_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i
 double occupied_sites_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i = 0; i < n; ++i) if (x[i] > 0) s += 1; return s; }   // R/:1245
 } // namespace
 
-void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
-                                double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
-                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
-                                double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
-                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+namespace {
+// fpe == false: rietkerk_Dornic_2D_MultiSp (Rietkerk_FD, R/:3397); true: rietkerk_DorFPE_2D_MultiSp (Rietkerk_FPE, F/:3697)
+void run_3sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, double c, double gmax,
+             double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
+             double sigma[], double a_c, double (&A)[SpB][SpB],
+             double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
+             double clow[], double dt, double dx, double dP, int r, int g)
 {
     if (!init_frame) throw std::runtime_error("tm_b200::spb3::init_frame is not set");
     (void)dtV;   // see the header
@@ -84,6 +88,7 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     veg.model = TM_MODEL_RIETKERK; veg.L = g; veg.dt = dt; veg.dx = dx; veg.a = a;
     veg.rc = c; veg.gmax = gmax; veg.alpha = alpha; veg.rW = rW; veg.W0 = W0; veg.d = M[0]; veg.K1 = K[1]; veg.K2 = K[2];
     veg.D0 = D[0]; veg.D1 = D[3]; veg.D2 = D[4]; veg.sigma0 = sigma[0]; veg.clamp_eps = 1.0e-12; veg.clamp_lo = -1.0e-80;   // R/:4176
+    if (fpe) { veg.clamp_eps = fke_globals().epsilon; veg.clamp_lo = 0.0; }                                                 // F/:4458
     tm_graz_params pg[2];
     for (int s = 1; s <= 2; s++) {
         tm_graz_params &q = pg[s - 1];
@@ -98,6 +103,26 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     Ctx ctx;
     if (tm_cons3_create(g, current_device(), &ctx.c) != 0) throw std::runtime_error(std::string("tm_cons3_create: ") + tm_cons3_last_error(nullptr));
     ctx.ck(tm_cons3_setup(ctx.c, &veg, &pg[0], &pg[1], &pc, central.data(), (int)nb.size(), fr_graz, fr_pred), "tm_cons3_setup");
+    if (fpe) {
+        // movement windows and stencils of grazer and predator as the runner builds them (F/:3760-3772) from set_global_FKE_params' globals
+        const FKEGlobals &G = fke_globals();
+        if (G.SpB != SpB || G.L != g) throw std::runtime_error("rietkerk_DorFPE_2D_MultiSp: call set_global_FKE_params(D, v, dtAdv, Dt, dx, g) first");
+        vector<double> gD[2], gV[2];
+        tm_fke_terms t[2];
+        const double *pD[2], *pV[2];
+        for (int s = 1; s <= 2; s++) {
+            gD[s - 1] = precompute_gaussian(sigma[s], G.sig_D_ScaledBounds[s]);
+            gV[s - 1] = precompute_gaussian(sigma[s], G.sig_vD_ScaledBounds[s].first);
+            tm_fke_terms &q = t[s - 1];
+            q = tm_fke_terms{};
+            q.bound_D = G.sig_D_ScaledBounds[s];
+            q.v_row_lo = q.v_col_lo = G.sig_vD_ScaledBounds[s].first; q.v_row_hi = q.v_col_hi = G.sig_vD_ScaledBounds[s].second;   // CPU path, F/:3640-3641
+            q.n_gauss_D = (int)gD[s - 1].size(); q.n_gauss_V = (int)gV[s - 1].size();
+            q.mu_vel_prefactor = G.mu_vel_prefactor[s]; q.epsilon = G.epsilon;
+            pD[s - 1] = gD[s - 1].data(); pV[s - 1] = gV[s - 1].data();
+        }
+        ctx.ck(tm_cons3_set_fpe(ctx.c, t, pD, pV, M[1], M[2]), "tm_cons3_set_fpe");
+    }
 
     D2Vec_Double rho_rep_avg_var(tot_iter, vector<double>(W_, 0.0));
     for (int i = 0; i < tot_iter; i++) rho_rep_avg_var[i][0] = t_meas[i];            // R/:3484-3487
@@ -149,16 +174,37 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     }
 }
 
+} // namespace
+
+void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
+                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
+                                double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
+                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+{
+    run_3sp(false, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g);
+}
+
+void rietkerk_DorFPE_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
+                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
+                                double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
+                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+{
+    run_3sp(true, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g);
+}
+
 const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"
                                  " # Active Sites P(x; t), <<G(x; t)>_x>_r, Var[<G(x; t)>_x]_r, # Surviving Runs G(x; t), # Active Sites G(x; t),"
                                  "<<Pr(x; t)>_x>_r, Var[<Pr(x; t)>_x]_r, # Surviving Runs Pr(x; t), # Active Sites Pr(x; t), \n";   // constants_3Sp.h:10-12
 
-void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
-                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
-                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
-                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
-                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
-                                                       double Gstar, double Vstar)
+namespace {
+void sweep_3sp(bool fpe, int div, double t_max, double a_start, double a_end, double a_c, double c,
+               double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+               double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+               double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+               int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+               double Gstar, double Vstar)
 {
     vector<double> a_space = linspace(a_start, a_end, div);
     vector<double> t_measure = logarithm10_time_bins(t_max, 1 * dt);
@@ -168,19 +214,20 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
     vector<D2Vec_Double> per_a(a_space.size());
     for_each_on_devices((int)a_space.size(), [&](int i) {   // the reference's `omp for` over a-values (R/:4509): one GPU per a-value at a time
         vector<double> tm_i = t_measure;
-        rietkerk_Dornic_2D_MultiSp(per_a[i], tm_i, t_max, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_start, a_end, a_c, A, H, E, M,
-                                   pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
+        run_3sp(fpe, per_a[i], tm_i, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g);
     });
     D2Vec_Double vec;
     for (const D2Vec_Double &rows : per_a) vec.insert(vec.end(), rows.begin(), rows.end());
     std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;
     L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r;
     Dm1 << std::setprecision(3) << D[1]; dix << std::setprecision(2) << dx; geq << std::setprecision(5) << Gstar; veq << std::setprecision(5) << Vstar;
-    const std::string dir = options().data_root + "/Data/Rietkerk/Stochastic/3Sp";
+    // Rietkerk_FD: "../Data/Rietkerk/Stochastic/3Sp/1stCC_Rietkerk_<prefix>_P_c_G_"; Rietkerk_FPE's set_Prefix (F/:143-165):
+    // "../Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_"
+    const std::string dir = options().data_root + (fpe ? "/Data/Rietkerk/Stochastic" : "/Data/Rietkerk/Stochastic/3Sp");
     std::string path;
     for (size_t k = 1; k <= dir.size(); k++)                                         // mkdir -p
         if (k == dir.size() || dir[k] == '/') { path = dir.substr(0, k); mkdir(path.c_str(), 0777); }
-    std::string savefile = dir + "/1stCC_Rietkerk_" + prefix + "_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
+    std::string savefile = dir + (fpe ? "/1stOrderCC_Rietkerk_" : "/1stCC_Rietkerk_") + prefix + "_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
                          + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str();                                    // R/:4582
     if (Gstar != -1) savefile += "_Geq_" + geq.str() + "_R_" + rini.str() + ".csv";
     else if (Vstar != -1) savefile += "_Veq_" + veq.str() + "_R_" + rini.str() + ".csv";
@@ -191,6 +238,27 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
         for (size_t j = 0; j + 1 < vec[i].size(); j++) out << std::setprecision(16) << vec[i][j] << ",";
         out << std::setprecision(16) << vec[i][vec[i].size() - 1] << std::endl;
     }
+}
+} // namespace
+
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                       double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                       int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar, double Vstar)
+{
+    sweep_3sp(false, div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, v, K, sigma, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
+}
+
+void first_order_critical_exp_delta_stochastic_MultiSp_FPE(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                           double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                           double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                           double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                           int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                           double Gstar, double Vstar)
+{
+    sweep_3sp(true, div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, v, K, sigma, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
 }
 
 }} // namespace tm_b200::spb3

@@ -36,6 +36,22 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, 
                                 double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
                                 int g, double Gstar = -1.0, double Vstar = -1.0);
 
+// The Rietkerk_FPE twin, Rietkerk_FPE/rietkerk_bjork_FKE.cpp:3697 compiled with -DSPB=3 (device step: tm_cons3_set_fpe): call
+// tm_b200::set_global_FKE_params (tm_host_fke.h) first, as the reference's drivers do (order_3stoc_unity_rietkerk.cpp).
+void rietkerk_DorFPE_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c,
+                                double gmax, double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB],
+                                double (&K)[3], double sigma[], double a_st, double a_end, double a_c,
+                                double (&A)[SpB][SpB], double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB],
+                                double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
+                                int g, double Gstar = -1.0, double Vstar = -1.0);
+// its a-sweep (F/:4665): CSV "<data_root>/Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_<L>_T_..._R_<r>.csv"
+void first_order_critical_exp_delta_stochastic_MultiSp_FPE(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                           double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                           double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                           double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                           int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                           double Gstar = -1.0, double Vstar = -1.0);
+
 // CSV "<data_root>/Data/Rietkerk/Stochastic/3Sp/1stCC_Rietkerk_<prefix>_P_c_G_<L>_T_<T>_dt_..._R_<r>.csv" with the reference's 3Sp header
 // (rietkerk_bjork_constants_3Sp.h:10-12) and 16-digit rows; a-values dealt over the visible GPUs (tm_host.h).
 extern const std::string prelimheader;

@@ -360,8 +360,21 @@ int tmh_fpe2_run(int L, const double *par, int r, const double *init, int n_init
 // tests/golden/make_runner3_golden.py {a, c, gmax, alpha, rW, W0, d, K1, K2, D0..D4, sigma0..2, v1, v2, aij, hij, ej, ajm, hjm, em, m1, m2,
 // pR1, pR2, dt, dx}; init: n_init frames [5][L*L], replicate j starts from frame j % n_init; rows_out[k][18]; frames_out (may be NULL):
 // [r][n_tmeas][5][L*L].
+int tmh_riet3_run_any(int fpe, int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
+                      double *rows_out, int cap, double *frames_out, int sweep, int div, double a_start, double a_end);
 int tmh_riet3_run(int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
                   double *rows_out, int cap, double *frames_out, int sweep, int div, double a_start, double a_end)
+{
+    return tmh_riet3_run_any(0, L, par, r, init, n_init, t_meas, n_tmeas, rows_out, cap, frames_out, sweep, div, a_start, a_end);
+}
+// Rietkerk_FPE, SPB = 3: par[31], par[32] = dtAdv[1], dtAdv[2]; set_global_FKE_params is called as the driver does (CI = 4, Dt = dt)
+int tmh_fpe3_run(int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
+                 double *rows_out, int cap, double *frames_out, int sweep, int div, double a_start, double a_end)
+{
+    return tmh_riet3_run_any(1, L, par, r, init, n_init, t_meas, n_tmeas, rows_out, cap, frames_out, sweep, div, a_start, a_end);
+}
+int tmh_riet3_run_any(int fpe, int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
+                      double *rows_out, int cap, double *frames_out, int sweep, int div, double a_start, double a_end)
 {
     namespace s3 = tm_b200::spb3;
     double D[s3::Sp] = {par[9], par[10], par[11], par[12], par[13]};
@@ -380,14 +393,22 @@ int tmh_riet3_run(int L, const double *par, int r, const double *init, int n_ini
     else s3::on_measure = nullptr;
     s3::D2Vec_Double Rho;
     try {
+        if (fpe) {
+            double dtAdv[s3::SpB] = {0.0, par[31], par[32]};
+            set_global_FKE_params(D, v, dtAdv, par[29], par[30], L, 4);
+        }
         if (sweep) {
-            s3::first_order_critical_exp_delta_stochastic_MultiSp(div, t_meas[n_tmeas - 1], a_start, a_end, 1.0 / 24.0, par[1], par[2], par[3], par[4],
-                                                                  par[5], D, v, K, sigma, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
+            if (fpe) s3::first_order_critical_exp_delta_stochastic_MultiSp_FPE(div, t_meas[n_tmeas - 1], a_start, a_end, 1.0 / 24.0, par[1], par[2], par[3], par[4],
+                                                                               par[5], D, v, K, sigma, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
+            else s3::first_order_critical_exp_delta_stochastic_MultiSp(div, t_meas[n_tmeas - 1], a_start, a_end, 1.0 / 24.0, par[1], par[2], par[3], par[4],
+                                                                       par[5], D, v, K, sigma, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
             return 0;
         }
         std::vector<double> tm(t_meas, t_meas + n_tmeas);
-        s3::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
-                                       1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
+        if (fpe) s3::rietkerk_DorFPE_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+                                                1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
+        else s3::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+                                            1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L);
     } catch (const std::exception &e) { fprintf(stderr, "tmh_riet3_run: %s\n", e.what()); s3::on_measure = nullptr; return -2; }
     s3::on_measure = nullptr;
     if ((int)Rho.size() > cap) return -1;
