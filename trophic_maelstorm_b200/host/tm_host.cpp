@@ -910,14 +910,10 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     Rho.insert(Rho.end(), per_a[0].begin(), per_a[0].end());
 }
 
-void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
-                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
-                                                       double (&)[SpB], double (&K)[3], double sigma[], double (&)[SpB][SpB],
-                                                       double (&)[SpB][SpB], double (&)[SpB], double (&M)[SpB], double[],
-                                                       int (&)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
-                                                       double Gstar, double Vstar) // R/:4379-4617
+// The a-sweeps' two schedules, R/:4395-4459 (the same lines in every SPB build and in F/): t_measure = {0} U log10 bins (with the
+// 80000..150000 linear window for long runs), returned; frame_tmeas = the same bins with [50, 400] and [400, 1200] re-gridded, set.
+vector<double> sweep_time_schedule(double t_max, double dt)
 {
-    vector<double> a_space = linspace(a_start, a_end, div);
     vector<double> t_measure = logarithm10_time_bins(t_max, 1 * dt);
     t_measure.insert(t_measure.begin(), 0.0);                                    // R/:4401
     std::sort(t_measure.begin(), t_measure.end());
@@ -935,6 +931,18 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
     }
     frame_tmeas.erase(std::unique(frame_tmeas.begin(), frame_tmeas.end()), frame_tmeas.end());
     t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
+    return t_measure;
+}
+
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&)[SpB], double (&K)[3], double sigma[], double (&)[SpB][SpB],
+                                                       double (&)[SpB][SpB], double (&)[SpB], double (&M)[SpB], double[],
+                                                       int (&)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar, double Vstar) // R/:4379-4617
+{
+    vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = sweep_time_schedule(t_max, dt);
 
     vector<D2Vec_Double> per_a;
     riet_batch(per_a, a_space, t_measure, c, gmax, alpha, rW, W0, D, K, sigma, a_start, a_end, a_c, M, clo, dt, dx, dP, r, g, Gstar, Vstar);

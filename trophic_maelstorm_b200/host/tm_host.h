@@ -125,6 +125,8 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
                                                        double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
                                                        int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
                                                        double Gstar = -1.0, double Vstar = -1.0);
+// the sweeps' schedules (R/:4395-4459): returns t_measure and sets frame_tmeas
+std::vector<double> sweep_time_schedule(double t_max, double dt);
 // burn-in frames (the reference's -DINIT=2 path): read_frame_csv parses one frame in save_frame()'s layout
 // (init_csvconstframe R/:909, header matching of init_exprtk_readCSVcolumns_frame R/:609); use_burnin_frames() makes
 // every replicate start from "<parendir><filenamePattern><r>.csv" (init_burnin_wrapper R/:836).

@@ -2,6 +2,7 @@
 #include "tm_host_2sp.h"
 #include "tm_host.h"
 #include "tm_host_fke.h"
+#include "tm_host_side.h"
 #include "../../include/tm_fke.h"
 #include "../../include/tm_consumer.h"
 #include "../../include/tm_lattice.h"
@@ -22,6 +23,12 @@ using std::vector;
 
 std::function<void(double *, int, int, double, double, double, const double[])> init_frame;
 std::function<void(int, int, double, const double *)> on_measure;
+std::string frame_folder, prelim_folder;
+side::Stepper *test_stepper = nullptr;
+const std::string frame_header = "a_c,  x,  P(x; t), G(x; t), W(x; t), O(x; t) \n";            // rietkerk_bjork_constants_2Sp.h:6
+const std::string gammaheader = "a_c,  x,  GAM[P(x; t)], GAM[G(x; t)] \n";                      // :8
+const std::string movmheader = " a , r, L, t , <GAM[P(x; t)]>_x, Var[<GAM[P(x; t)]>_x], <vx[P(x; t)]>_x,  <vy[P(x; t)]>_x,"
+                               " <GAM[G(x; t)]>_x, Var[<GAM[G(x; t)]>_x], <vx[G(x; t)]>_x,  <vy[G(x; t)]>_x, \n";   // :14-15
 
 static bool comparePairs(const std::pair<int, int> &a, const std::pair<int, int> &b)   // R/:108
 {
@@ -75,8 +82,29 @@ struct Ctx {
         if (rc != 0) throw std::runtime_error(std::string(what) + ": " + tm_cons_last_error(c));
     }
 };
-double mean_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i = 0; i < n; ++i) s += x[i]; return s / (double)n; }   // R/:1211
-double occupied_sites_of_vector(const double *x, size_t n) { double s = 0.0; for (size_t i = 0; i < n; ++i) if (x[i] > 0) s += 1; return s; }   // R/:1245
+// the product's Stepper: the resident SPB = 2 step of tm_consumer.h
+struct DeviceStepper : side::Stepper {
+    Ctx ctx;
+    unsigned long long key = 0;
+    size_t n = 0;
+    bool stepped = false;
+    void upload(const double *frame) override
+    {
+        ctx.ck(tm_cons_step2_upload(ctx.c, frame, nullptr), "tm_cons_step2_upload");   // gamma starts as zeros (R/:3523)
+        stepped = false;
+    }
+    void run(uint32_t replicate, uint32_t step0, int nsteps) override
+    {
+        ctx.ck(tm_cons_step2_run(ctx.c, key, replicate, step0, nsteps), "tm_cons_step2_run");
+        stepped = true;
+    }
+    void download(double *frame, double *gamma, double *veff) override
+    {
+        // the advection vectors are per-replicate state that starts as zeros (R/:3526); the context keeps the last replicate's until a step ran
+        ctx.ck(tm_cons_step2_download(ctx.c, frame, gamma, stepped ? veff : nullptr, nullptr, nullptr), "tm_cons_step2_download");
+        if (veff && !stepped) std::fill(veff, veff + 2 * n, 0.0);
+    }
+};
 } // namespace
 
 namespace {
@@ -85,9 +113,9 @@ namespace {
 // Dornic update and clamps at epsilon = 1e-10 (F/:4458).
 void run_2sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, double c, double gmax,
              double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
-             double sigma[], double a_c, double (&A)[SpB][SpB],
+             double sigma[], double a_st, double a_end, double a_c, double (&A)[SpB][SpB],
              double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
-             double clow[], double dt, double dx, double dP, int r, int g)
+             double clow[], double dt, double dx, double dP, int r, int g, double Gstar, double Vstar)
 {
     if (!init_frame) throw std::runtime_error("tm_b200::spb2::init_frame is not set");
     // dtV[s] (the drivers' round(dtv/dt), R/ order_2stoc_test_rietkerk.cpp): in the two-species runners as shipped it only feeds
@@ -95,10 +123,8 @@ void run_2sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, doub
     // build's direction sampling (R/:3972-3990).  Without that macro the direction is drawn at every step (R/:3992-3995), so any
     // dtV gives the same two-species run: accepted and unused here, as there.
     (void)dtV;
-    const int tot_iter = (int)t_meas.size();
+    if (t_meas.empty() || r < 1) throw std::invalid_argument("rietkerk_Dornic_2D_MultiSp: empty t_meas or r < 1");
     const double t_end = t_meas.back();                                               // R/:3439
-    const size_t n = (size_t)g * g;
-    const int Sp2 = 2 * Sp, W_ = 4 * SpB + 3;
 
     const double r_max_effective = (*std::max_element(pR, pR + SpB)) / dx;            // R/:3405
     const double fr_graz = pR[1] / (dx * r_max_effective);                            // R/:3409
@@ -117,7 +143,11 @@ void run_2sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, doub
     pc.L = g; pc.dt = dt; pc.a = a; pc.c = c; pc.gmax = gmax; pc.alpha = alpha; pc.rW = rW; pc.W0 = W0; pc.K1 = K[1]; pc.K2 = K[2];
     pc.Dw = D[2] / (dx * dx); pc.Do = D[3] / (dx * dx); pc.A01 = A[0][1]; pc.H01 = H[0][1]; pc.E1 = E[1];               // R/:3463-3480
 
-    Ctx ctx;
+    DeviceStepper dev;
+    side::Stepper *st = test_stepper;     // null in the product: the device context below
+    if (!st) {
+    Ctx &ctx = dev.ctx;
+    dev.key = stream_seed(options().seed, a); dev.n = (size_t)g * g;
     if (tm_cons_create(g, current_device(), &ctx.c) != 0) throw std::runtime_error(std::string("tm_cons_create: ") + tm_cons_last_error(nullptr));
     ctx.ck(tm_cons_step2_setup(ctx.c, &veg, &pg, &pc, central.data(), (int)nb.size(), fr_graz), "tm_cons_step2_setup");
     if (fpe) {
@@ -133,74 +163,39 @@ void run_2sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, doub
         t.mu_vel_prefactor = G.mu_vel_prefactor[1]; t.epsilon = G.epsilon;
         ctx.ck(tm_cons_step2_set_fpe(ctx.c, &t, gD.data(), gV.data(), M[1]), "tm_cons_step2_set_fpe");
     }
-
-    D2Vec_Double rho_rep_avg_var(tot_iter, vector<double>(W_, 0.0));
-    for (int i = 0; i < tot_iter; i++) rho_rep_avg_var[i][0] = t_meas[i];            // R/:3484-3487
-    vector<double> frame(Sp * n);
-
-    for (int j = 0; j < r; j++) {
-        init_frame(frame.data(), g, j, a, a_c, dP, clow);
-        ctx.ck(tm_cons_step2_upload(ctx.c, frame.data(), nullptr), "tm_cons_step2_upload");   // gamma starts as zeros (R/:3523)
-        D2Vec_Double Rho_M(tot_iter, vector<double>(Sp2, 0.0));
-        double t = 0; int index = 0; int pending = 0; uint32_t step = 0;
-        while (t < t_end + dt) {                                                      // R/:3648
-            const bool meas = index < tot_iter && (t == 0 || (t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0));   // R/:3659
-            if (meas) {
-                if (pending) { ctx.ck(tm_cons_step2_run(ctx.c, stream_seed(options().seed, a), (uint32_t)j, step, pending), "tm_cons_step2_run"); step += pending; pending = 0; }
-                ctx.ck(tm_cons_step2_download(ctx.c, frame.data(), nullptr, nullptr, nullptr, nullptr), "tm_cons_step2_download");
-                for (int s = 0; s < Sp; s++) {
-                    const double *f = &frame[s * n];
-                    for (size_t i = 0; i < n; i++)
-                        if (f[i] != f[i]) { std::cerr << "RHO NAAN PARATHA in field " << s << " at t=" << t << "\n"; exit(3); }   // R/:4156
-                    Rho_M[index][2 * s] = occupied_sites_of_vector(f, n); Rho_M[index][2 * s + 1] = mean_of_vector(f, n);   // R/:3662-3668
-                }
-                if (on_measure) on_measure(j, index, t, frame.data());
-                const bool checkpoint = index == int(tot_iter * 0.6) || index == int(tot_iter * 0.85) || index == int(tot_iter * 0.9)
-                                     || index == int(tot_iter * 0.95) || index == int(tot_iter - 1);
-                const bool dead = Rho_M[index][0] == 0.0;
-                index += 1;
-                if (checkpoint && dead) break;   // save_prelimfileswrapper's break_flag: all vegetation dead, R/:3087, 3714
-            }
-            pending += 1;
-            t += dt;
-        }
-        if (j == 0) {                                                                 // R/:4294-4316
-            for (int i = 0; i < tot_iter; i++) {
-                for (int s = 0; s < SpB; s++) {
-                    rho_rep_avg_var[i][4 * s + 3] = Rho_M[i][2 * s + 1]; rho_rep_avg_var[i][4 * s + 4] = 0.0;
-                    rho_rep_avg_var[i][4 * s + 6] = Rho_M[i][2 * s];
-                    if (Rho_M[i][2 * s] > 0) rho_rep_avg_var[i][4 * s + 5] = 1; else if (Rho_M[i][2 * s] == 0) rho_rep_avg_var[i][4 * s + 5] = 0;
-                }
-                rho_rep_avg_var[i][1] = Rho_M[i][2 * (Sp - 2) + 1]; rho_rep_avg_var[i][2] = Rho_M[i][2 * (Sp - 1) + 1];
-            }
-        } else var_mean_incremental_surv_runs(rho_rep_avg_var, Rho_M, tot_iter, j);   // R/:4321
+    st = &dev;
     }
-    for (int i = 0; i < tot_iter; i++) {                                              // R/:4361-4372
-        Rho.push_back({a, static_cast<double>(r), static_cast<double>(g), rho_rep_avg_var[i][0], rho_rep_avg_var[i][1], rho_rep_avg_var[i][2]});
-        for (int s = 0; s < Sp - 2; s++)
-            Rho[Rho.size() - 1].insert(Rho[Rho.size() - 1].end(), {rho_rep_avg_var[i][4 * s + 3], rho_rep_avg_var[i][4 * s + 4],
-                                                                   rho_rep_avg_var[i][4 * s + 5], rho_rep_avg_var[i][4 * s + 6]});
-    }
+
+    side::Config cfg;
+    cfg.Sp = Sp; cfg.SpB = SpB; cfg.g = g; cfg.a = a; cfg.a_st = a_st; cfg.a_end = a_end; cfg.dt = dt; cfg.dx = dx; cfg.dP = dP;
+    cfg.D1 = D[1]; cfg.D2 = D[2]; cfg.Gstar = Gstar; cfg.Vstar = Vstar; cfg.t_max = t_end;
+    cfg.frame_folder = frame_folder.empty() ? options().data_root + "/Data/Rietkerk/Frames/Stochastic/2Sp/" + prefix + "_" : frame_folder;
+    cfg.prelim_folder = prelim_folder.empty() ? options().data_root + "/Data/Rietkerk/Prelims/Stochastic/2Sp/" + prefix + "_" : prelim_folder;
+    cfg.frame_header = frame_header; cfg.gammaheader = gammaheader; cfg.prelimheader = prelimheader; cfg.movmheader = movmheader;
+    side::Run run;
+    run.r = r; run.a_c = a_c; run.clow = clow; run.init_frame = init_frame; run.on_measure = on_measure;
+    run.var_mean = [](D2Vec_Double &T, const D2Vec_Double &X, int size, int j) { var_mean_incremental_surv_runs(T, X, size, j); };
+    side::run_replicates(*st, cfg, run, t_meas, Rho);
 }
 
 } // namespace
 
 void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
                                 double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
-                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
+                                double sigma[], double a_st, double a_end, double a_c, double (&A)[SpB][SpB],
                                 double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
-                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+                                double clow[], double dt, double dx, double dP, int r, int g, double Gstar, double Vstar)
 {
-    run_2sp(false, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g);
+    run_2sp(false, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_st, a_end, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g, Gstar, Vstar);
 }
 
 void rietkerk_DorFPE_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
                                 double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB], double (&K)[3],
-                                double sigma[], double /*a_st*/, double /*a_end*/, double a_c, double (&A)[SpB][SpB],
+                                double sigma[], double a_st, double a_end, double a_c, double (&A)[SpB][SpB],
                                 double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[], int (&dtV)[SpB],
-                                double clow[], double dt, double dx, double dP, int r, int g, double, double)
+                                double clow[], double dt, double dx, double dP, int r, int g, double Gstar, double Vstar)
 {
-    run_2sp(true, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g);
+    run_2sp(true, Rho, t_meas, a, c, gmax, alpha, rW, W0, D, v, K, sigma, a_st, a_end, a_c, A, H, E, M, pR, dtV, clow, dt, dx, dP, r, g, Gstar, Vstar);
 }
 
 const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"
@@ -215,15 +210,12 @@ void sweep_2sp(bool fpe, int div, double t_max, double a_start, double a_end, do
                double Gstar, double Vstar)
 {
     vector<double> a_space = linspace(a_start, a_end, div);
-    vector<double> t_measure = logarithm10_time_bins(t_max, 1 * dt);
-    t_measure.insert(t_measure.begin(), 0.0);                                        // R/:4401
-    std::sort(t_measure.begin(), t_measure.end());
-    t_measure.erase(std::unique(t_measure.begin(), t_measure.end()), t_measure.end());
+    vector<double> t_measure = sweep_time_schedule(t_max, dt);                       // R/:4395-4459; sets frame_tmeas
     D2Vec_Double vec;
     vector<D2Vec_Double> per_a(a_space.size());
     for_each_on_devices((int)a_space.size(), [&](int i) {   // the reference's `omp for` over a-values (R/:4509, F/:4795): one GPU per a-value at a time
         vector<double> tm_i = t_measure;
-        run_2sp(fpe, per_a[i], tm_i, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_c, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g);
+        run_2sp(fpe, per_a[i], tm_i, a_space[i], c, gmax, alpha, rW, W0, D, v, K, sigma, a_start, a_end, a_c, A, H, E, M, pR, dtV, clo, dt, dx, dP, r, g, Gstar, Vstar);
     });
     for (const D2Vec_Double &rows : per_a) vec.insert(vec.end(), rows.begin(), rows.end());
     std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;

@@ -10,8 +10,9 @@
 // schedule from the accumulated t += dt (R/:3648, 3659), Rho_M = {#occupied, <rho>} per field from left-to-right sums of
 // the downloaded frame (mean_of_vector R/:1211), the stop of a replicate whose vegetation is gone at a checkpoint bin
 // (R/:3710-3716), the replicate-order running mean/variance with the integer 1/(r-1) (R/:1325), and the row layout
-// {a, r, L, t, <W>, <O>, then per living species <rho>, var, #surviving, #active} (R/:4361-4372).  Not carried over: the
-// runner's CSV side outputs (frames, prelim tables, movement averages Rho_Mov) -- the SPB = 1 layer has those writers.
+// {a, r, L, t, <W>, <O>, then per living species <rho>, var, #surviving, #active} (R/:4361-4372), and the
+// runner's CSV side outputs (tm_host_side.h): FRAME_* / GAMMA_* snapshots on tm_b200::frame_tmeas, the movement averages Rho_Mov
+// and the PRELIM_TSERIES_* / PRELIM_MOVSERIES_* checkpoints and PRELIM_AGGRAND_* running tables while tm_b200::write_prelims is on.
 // dtV[s] is accepted and has no effect, as in the reference's two-species build (only its -DLOCUST_WIND variant and the three-species
 // perception functions read the counter it feeds).
 // The Rietkerk_FPE runner of the same model (rietkerk_DorFPE_2D_MultiSp) is here too: same bookkeeping, different device step.
@@ -21,7 +22,13 @@
 #include <utility>
 #include <vector>
 
-namespace tm_b200 { namespace spb2 {
+namespace tm_b200 { namespace side { struct Stepper; }
+namespace spb2 {
+
+// TEST SEAM.  Null in the product (the runners then step on the device, and fail without one).  When set, the runners hand their
+// bookkeeping this Stepper instead of creating a device context: the CPU tests pin the measurement schedule, the running statistics
+// and the CSV writers on the reference's own output tree this way.
+extern side::Stepper *test_stepper;
 
 using D2Vec_Double = std::vector<std::vector<double>>;
 constexpr int Sp = 4, SpB = 2;
@@ -32,6 +39,10 @@ extern std::function<void(double *frame, int g, int replicate, double a, double 
 // Optional observer called at every measurement bin with the downloaded frame (4*g*g) -- what the reference's frame
 // writers see; used by the tests.
 extern std::function<void(int replicate, int index, double t, const double *frame)> on_measure;
+// Output locations of the side outputs; empty (default) = "<data_root>/Data/Rietkerk/{Frames,Prelims}/Stochastic/2Sp/<prefix>_"
+// with tm_b200::prefix (the reference's frame_folder / prelim_folder, header :106-107).
+extern std::string frame_folder, prelim_folder;
+extern const std::string frame_header, gammaheader, movmheader;   // rietkerk_bjork_constants_2Sp.h:6-15
 
 std::vector<std::pair<int, int>> computeNeighboringSitesCentral(int R);
 void var_mean_incremental_surv_runs(D2Vec_Double &t_avg_var_rep_N, const D2Vec_Double &X_curr, int size, int j);

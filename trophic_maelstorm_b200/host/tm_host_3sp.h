@@ -10,14 +10,18 @@
 // of a replicate whose vegetation is gone at a checkpoint bin (R/:3710-3716), the replicate-order running mean/variance with the
 // integer 1/(r-1) (R/:1325) and the row layout {a, r, L, t, <W>, <O>, then per living species <rho>, var, #surviving, #active}
 // (R/:4361-4372: 18 columns).  dtV is accepted and unused (the counter it feeds is read only inside commented-out code of
-// calc_gamma_3Sp_NonRefugia, R/:3211-3214, and by the -DLOCUST_WIND build).  Not carried over: the runner's CSV side outputs.
+// calc_gamma_3Sp_NonRefugia, R/:3211-3214, and by the -DLOCUST_WIND build).  The runner's CSV side outputs (FRAME_* / GAMMA_* snapshots,
+// PRELIM_TSERIES_* / PRELIM_MOVSERIES_* checkpoints, PRELIM_AGGRAND_* running tables) are written as in the SPB = 2 layer (tm_host_side.h).
 #pragma once
 #include <functional>
 #include <string>
 #include <utility>
 #include <vector>
 
-namespace tm_b200 { namespace spb3 {
+namespace tm_b200 { namespace side { struct Stepper; }
+namespace spb3 {
+
+extern side::Stepper *test_stepper;   // TEST SEAM, null in the product: see tm_host_2sp.h
 
 using D2Vec_Double = std::vector<std::vector<double>>;
 constexpr int Sp = 5, SpB = 3;
@@ -26,6 +30,9 @@ constexpr int Sp = 5, SpB = 3;
 extern std::function<void(double *frame, int g, int replicate, double a, double a_c, double dP, const double clow[])> init_frame;
 // Optional observer called at every measurement bin with the downloaded frame (5*g*g).
 extern std::function<void(int replicate, int index, double t, const double *frame)> on_measure;
+// Output locations of the side outputs; empty (default) = "<data_root>/Data/Rietkerk/{Frames,Prelims}/Stochastic/3Sp/<prefix>_"
+extern std::string frame_folder, prelim_folder;
+extern const std::string frame_header, gammaheader, movmheader;   // rietkerk_bjork_constants_3Sp.h:6-17
 
 void var_mean_incremental_surv_runs(D2Vec_Double &t_avg_var_rep_N, const D2Vec_Double &X_curr, int size, int j);   // R/:1293
 

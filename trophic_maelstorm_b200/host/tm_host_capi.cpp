@@ -3,6 +3,7 @@
 #include "tm_host.h"
 #include "tm_host_fke.h"
 #include "tm_host_2sp.h"
+#include "tm_host_side.h"
 #include "tm_host_3sp.h"
 #include <cmath>
 #include <cstdio>
@@ -414,6 +415,85 @@ int tmh_riet3_run_any(int fpe, int L, const double *par, int r, const double *in
     if ((int)Rho.size() > cap) return -1;
     for (size_t k = 0; k < Rho.size(); k++)
         for (size_t j = 0; j < 18; j++) rows_out[18 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
+    return (int)Rho.size();
+}
+// TEST SEAM (tm_host_2sp.h test_stepper): the SPB = 2 / SPB = 3 runners' bookkeeping and CSV writers over a Stepper made of three caller-
+// supplied functions -- no device is touched.  tests/test_side_outputs.py passes the CPU oracle under sequential replay here and
+// compares the output tree with the one the unmodified reference wrote.  spb = 2 | 3; par / init / rows_out as tmh_riet2_run / tmh_riet3_run;
+// frame_t: tm_b200::frame_tmeas for this call; folders "<root>/Frames/Stochastic/<n>Sp/<prefix>_" as set_Prefix lays them out.
+typedef void (*tmh_upload_fn)(const double *frame);
+typedef void (*tmh_run_fn)(uint32_t replicate, uint32_t step0, int nsteps);
+typedef void (*tmh_download_fn)(double *frame, double *gamma, double *veff);
+int tmh_side_run(int spb, int L, const double *par, int r, const double *init, int n_init, const double *t_meas, int n_tmeas,
+                 const double *frame_t, int n_frame_t, const char *root, const char *user_prefix, double Gstar, double Vstar,
+                 tmh_upload_fn up, tmh_run_fn run, tmh_download_fn down, double *rows_out, int cap, int prelims)
+{
+    struct Fn : tm_b200::side::Stepper {
+        tmh_upload_fn u; tmh_run_fn r; tmh_download_fn d;
+        void upload(const double *f) override { u(f); }
+        void run(uint32_t j, uint32_t s0, int n) override { r(j, s0, n); }
+        void download(double *f, double *g, double *v) override { d(f, g, v); }
+    } fn;
+    fn.u = up; fn.r = run; fn.d = down;
+    const std::vector<double> saved_ft = frame_tmeas;
+    const std::string saved_prefix = prefix;
+    const bool saved_wp = write_prelims;
+    frame_tmeas.assign(frame_t, frame_t + n_frame_t);
+    prefix = user_prefix; write_prelims = prelims != 0;
+    const std::string sp = std::to_string(spb) + "Sp/";
+    std::vector<double> tm(t_meas, t_meas + n_tmeas);
+    std::vector<std::vector<double>> Rho;
+    int rc = 0, width = 0;
+    try {
+        if (spb == 2) {
+            namespace s2 = tm_b200::spb2;
+            double D[s2::Sp] = {par[9], par[10], par[11], par[12]};
+            double K[3] = {0.0, par[7], par[8]};
+            double sigma[s2::Sp] = {par[13], par[14], 0, 0};
+            double v[s2::SpB] = {0, par[15]};
+            double A[s2::SpB][s2::SpB] = {{0, par[16]}, {par[16], 0}}, H[s2::SpB][s2::SpB] = {{0, par[17]}, {par[17], 0}};
+            double E[s2::SpB] = {1.0, par[18]}, M[s2::SpB] = {par[6], par[19]}, pR[s2::Sp] = {0.0, par[20]};
+            int dtV[s2::SpB] = {0, 1};
+            double clow[2 * s2::Sp] = {0, 1, 1, 1, 5, 1, 1, 1};
+            const size_t n4 = (size_t)4 * L * L;
+            s2::init_frame = [=](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + (size_t)(j % n_init) * n4, n4 * sizeof(double)); };
+            s2::on_measure = nullptr;
+            s2::frame_folder = std::string(root) + "Frames/Stochastic/" + sp + user_prefix + "_";
+            s2::prelim_folder = std::string(root) + "Prelims/Stochastic/" + sp + user_prefix + "_";
+            s2::test_stepper = &fn;
+            s2::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+                                           1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[21], par[22], 10000.0, r, L, Gstar, Vstar);
+            width = 14;
+        } else if (spb == 3) {
+            namespace s3 = tm_b200::spb3;
+            double D[s3::Sp] = {par[9], par[10], par[11], par[12], par[13]};
+            double K[3] = {0.0, par[7], par[8]};
+            double sigma[s3::Sp] = {par[14], par[15], par[16], 0, 0};
+            double v[s3::SpB] = {0, par[17], par[18]};
+            double A[s3::SpB][s3::SpB] = {{0, par[19], 0}, {par[19], 0, par[22]}, {0, par[22], 0}};
+            double H[s3::SpB][s3::SpB] = {{0, par[20], 0}, {par[20], 0, par[23]}, {0, par[23], 0}};
+            double E[s3::SpB] = {1.0, par[21], par[24]}, M[s3::SpB] = {par[6], par[25], par[26]}, pR[s3::Sp] = {0.0, par[27], par[28], 0.0, 0.0};
+            int dtV[s3::SpB] = {0, 1, 1};
+            double clow[2 * s3::Sp] = {0, 1, 1, 1, 1, 5, 1, 1, 1, 1};
+            const size_t n5 = (size_t)5 * L * L;
+            s3::init_frame = [=](double *f, int, int j, double, double, double, const double[]) { memcpy(f, init + (size_t)(j % n_init) * n5, n5 * sizeof(double)); };
+            s3::on_measure = nullptr;
+            s3::frame_folder = std::string(root) + "Frames/Stochastic/" + sp + user_prefix + "_";
+            s3::prelim_folder = std::string(root) + "Prelims/Stochastic/" + sp + user_prefix + "_";
+            s3::test_stepper = &fn;
+            s3::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+                                           1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L, Gstar, Vstar);
+            width = 18;
+        } else rc = -3;
+    } catch (const std::exception &e) { fprintf(stderr, "tmh_side_run: %s\n", e.what()); rc = -2; }
+    tm_b200::spb2::test_stepper = nullptr; tm_b200::spb3::test_stepper = nullptr;
+    tm_b200::spb2::frame_folder.clear(); tm_b200::spb2::prelim_folder.clear();
+    tm_b200::spb3::frame_folder.clear(); tm_b200::spb3::prelim_folder.clear();
+    frame_tmeas = saved_ft; prefix = saved_prefix; write_prelims = saved_wp;
+    if (rc) return rc;
+    if ((int)Rho.size() > cap) return -1;
+    for (size_t k = 0; k < Rho.size(); k++)
+        for (int j = 0; j < width; j++) rows_out[(size_t)width * k + j] = j < (int)Rho[k].size() ? Rho[k][j] : 0.0;
     return (int)Rho.size();
 }
 }
