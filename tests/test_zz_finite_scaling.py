@@ -1,0 +1,81 @@
+"""DP finite-size scaling drivers of the host layer: critical_exp_finite_scaling_collapse (P/:1424) and
+critical_exp_finite_scaling_stationary (P/:1538) -- percolationDornic_2D at a_c from a full frame over a range of grid sizes, one CSV
+with the first seven columns of the runner's rows.  Checked: file-name grammar, header, row counts from the reference's time-bin
+rules, the L column, t = 0 rows of a full frame, and that every block equals what the runner itself returns for that grid size
+(same Philox key (seed, a) per trial => the same trajectories)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import trophic_maelstorm_b200 as tm
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+dp = C.POINTER(C.c_double)
+HEADER = " a , L, t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt "
+
+
+@pytest.fixture(scope="module")
+def host():
+    tm.lib()
+    h = C.CDLL(os.path.join(ROOT, "trophic_maelstorm_b200", "libtm_host.so"))
+    h.tmh_set_options.argtypes = [C.c_int, C.c_ulonglong, C.c_int, C.c_char_p]
+    h.tmh_dp_run.argtypes = [C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, dp, dp, C.c_int, dp, C.c_int]
+    h.tmh_dp_finite_scaling.argtypes = [C.c_int] * 4 + [C.c_double] * 7 + [C.c_int]
+    return h
+
+
+def runner_rows(host, L, a, b, D, sigma, dt, dx, t_meas, r):
+    rows = np.zeros((4096, 9))
+    tmv = np.ascontiguousarray(t_meas, dtype=np.float64)
+    r0 = np.ones(L * L)
+    n = host.tmh_dp_run(0, L, a, b, 0.0, D, sigma, dt, dx, r, O.ptr(r0), O.ptr(tmv), len(tmv), O.ptr(rows), 4096)
+    assert n > 0, n
+    return rows[:n, :8]
+
+
+def test_finite_scaling_collapse_csv(host, tmp_path):
+    a_c, b, D, sigma, dt, dx, r, t_max = 1.0548, 1.0, 0.25, 2 ** 0.5, 0.1, 1.0, 2, 3.0
+    host.tmh_set_options(0, 11, 0, str(tmp_path).encode())
+    assert host.tmh_dp_finite_scaling(0, 3, 16, 32, t_max, a_c, b, D, sigma, dt, dx, r) == 0
+    path = tmp_path / "Data" / "SPDP" / "DEBUG_P_c_Finite_Scaling_Collapse_T_3_dt_0.1_a_1.0548_L1_16_L2_32_Sig_1.41_R_2.csv"
+    assert path.exists(), list((tmp_path / "Data" / "SPDP").iterdir())
+    lines = path.read_text().splitlines()
+    assert lines[0] == HEADER
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in lines[1:]])
+    bins = np.zeros(64)
+    nb = O.oracle().tmo_logarithm10_time_bins(C.c_double(t_max), C.c_double(dt), O.ptr(bins), 64)
+    per_g = 11 + nb                                        # every step while t <= 1, then the log10 bins (P/:949-964)
+    assert rows.shape == (3 * per_g, 7)
+    assert np.all(rows[:per_g, 1] == 16) and np.all(rows[per_g:2 * per_g, 1] == 24) and np.all(rows[2 * per_g:, 1] == 32)
+    assert np.all(rows[:, 0] == a_c) and np.all(rows[rows[:, 2] == 0][:, 3] == 1.0)       # init_fullframe
+    for k, L in enumerate((16, 24, 32)):
+        want = runner_rows(host, L, a_c, b, D, sigma, dt, dx, bins[:nb], r)
+        got = rows[k * per_g:(k + 1) * per_g]
+        np.testing.assert_allclose(got, want[:, :7], rtol=1e-15, atol=0)                  # setprecision(16) columns; t and a exact
+
+
+def test_finite_scaling_stationary_csv(host, tmp_path, monkeypatch):
+    a_c, b, D, sigma, dt, dx, r = 1.0548, 1.0, 0.25, 2 ** 0.5, 0.1, 1.0, 2
+    monkeypatch.setenv("TM_FSS_WINDOW_SCALE", "0.002")     # the reference's windows are 900 .. 15000 time units long
+    host.tmh_set_options(0, 12, 0, str(tmp_path).encode())
+    assert host.tmh_dp_finite_scaling(1, 2, 32, 64, 50.0, a_c, b, D, sigma, dt, dx, r) == 0
+    path = tmp_path / "Data" / "SPDP" / "DEBUG_P_c_Finite_Scaling_Stationary_T_50_dt_0.1_a_1.0548_L1_32_L2_64_Sig_1.41_R_2.csv"
+    assert path.exists(), list((tmp_path / "Data" / "SPDP").iterdir())
+    lines = path.read_text().splitlines()
+    assert lines[0] == HEADER
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in lines[1:]])
+    import math
+    g0 = int(math.pow(math.exp(1), math.log(32.0)))        # lnspace (P/:281-301) rebuilds its first point as e^(ln 32): 31 with glibc's pow
+    assert rows.shape[1] == 7 and set(rows[:, 1]) == {float(g0), 64.0}
+    for L, (t0, t1) in ((g0, (300, 900)), (64, (1000, 2500))):
+        blk = rows[rows[:, 1] == L]
+        tm_ = np.linspace(t0 * 0.002, t1 * 0.002, 30)
+        want = runner_rows(host, L, a_c, b, D, sigma, dt, dx, tm_, r)
+        assert len(blk) == len(want)
+        np.testing.assert_allclose(blk, want[:, :7], rtol=1e-15, atol=0)
+    # grid sizes the reference has no window for are refused, not guessed
+    assert host.tmh_dp_finite_scaling(1, 2, 16, 64, 50.0, a_c, b, D, sigma, dt, dx, r) == -2

@@ -331,6 +331,88 @@ void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, doubl
                  " a , c , L,  t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n", vec, true);
 }
 
+// ---- finite-size scaling drivers (P/:1424-1665): percolationDornic_2D at a_c over a range of grid sizes ------------
+
+// lnspace, P/:281-301
+vector<double> lnspace(double start_in, double end_in, int log_points)
+{
+    vector<double> v;
+    const double logMin = std::log(start_in), logMax = std::log(end_in);
+    const double delta = (logMax - logMin) / (log_points - 1);
+    if (log_points == 0) return v;
+    if (log_points == 1) { v.push_back(start_in); return v; }
+    for (int i = 0; i < log_points - 1; ++i) v.push_back(std::pow(std::exp(1), logMin + delta * i));
+    v.push_back(end_in);
+    return v;
+}
+
+namespace {
+// both drivers write the first seven columns {a, L, t, mean, var, #surviving, #active} of the runner's rows, P/:1522-1526, 1653-1657
+void write_finite_scaling_csv(const std::string &name, const vector<vector<double>> &vec)
+{
+    mkdirs(options().data_root + "/Data/SPDP");
+    std::ofstream out(options().data_root + "/Data/SPDP/" + name);
+    out << " a , L, t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n";
+    for (const vector<double> &v : vec)
+        out << std::setprecision(8) << v[0] << "," << v[1] << "," << std::setprecision(16) << v[2] << "," << std::setprecision(16) << v[3]
+            << "," << v[4] << "," << std::setprecision(16) << v[5] << "," << v[6] << std::endl;
+}
+std::string finite_scaling_name(const char *kind, double t_max, double dt, double a_c, int g_st, int g_end, double sigma, int r)
+{
+    std::stringstream AC, tm, d3, g1, g2, rini, Sm;
+    tm << t_max; d3 << std::setprecision(3) << dt; g1 << std::setprecision(4) << g_st; g2 << std::setprecision(4) << g_end;
+    rini << r; Sm << std::setprecision(3) << sigma; AC << a_c;
+    return std::string("DEBUG_P_c_Finite_Scaling_") + kind + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + AC.str() + "_L1_" + g1.str()
+         + "_L2_" + g2.str() + "_Sig_" + Sm.str() + "_R_" + rini.str() + ".csv";
+}
+} // namespace
+
+void critical_exp_finite_scaling_collapse(int div, int g_st, int g_end, double t_max, double a_c, double b, double D, double sigma,
+                                          double dt, double dx, int r) // P/:1424-1536
+{
+    const vector<double> gv = linspace(g_st, g_end, div);
+    vector<int> g_space(gv.size());
+    for (size_t i = 0; i < gv.size(); i++) g_space[i] = static_cast<int>(gv[i]);
+    vector<double> t_measure = logarithm10_time_bins(t_max, dt);
+    vector<vector<vector<double>>> per_g(g_space.size());
+    for_each_on_devices((int)g_space.size(), [&](int i) {   // the reference's `omp for` over grid sizes: one GPU per grid size at a time
+        const int g = g_space[i];
+        vector<double> Rho_0((size_t)g * g, 1.0);           // init_fullframe, P/:39
+        vector<double> tm_i = t_measure;
+        percolationDornic_2D(per_g[i], tm_i, Rho_0.data(), t_max, a_c, b, D, sigma, dt, dx, r, g);
+    });
+    vector<vector<double>> vec;                              // in grid order (the reference: in the order its threads finish)
+    for (const auto &rows : per_g) vec.insert(vec.end(), rows.begin(), rows.end());
+    write_finite_scaling_csv(finite_scaling_name("Collapse", t_max, dt, a_c, g_st, g_end, sigma, r), vec);
+}
+
+void critical_exp_finite_scaling_stationary(int div, int g_st, int g_end, double /*t_lim*/, double t_max, double a_c, double b, double D,
+                                            double sigma, double dt, double dx, int r) // P/:1538-1665
+{
+    const vector<double> gv = lnspace(g_st, g_end, div);
+    vector<int> g_space(gv.size());
+    for (size_t i = 0; i < gv.size(); i++) g_space[i] = static_cast<int>(gv[i]);
+    for (int g : g_space)   // P/:1589-1598 assigns the window for g > 30 only and reads it uninitialised below that
+        if (g <= 30) throw std::invalid_argument("critical_exp_finite_scaling_stationary: the reference defines no time window for L <= 30");
+    vector<vector<vector<double>>> per_g(g_space.size());
+    for_each_on_devices((int)g_space.size(), [&](int i) {
+        const int g = g_space[i];
+        double t_start, t_end;                               // P/:1589-1598
+        if (g <= 50) { t_start = 300; t_end = 900; }
+        else if (g <= 100) { t_start = 1000; t_end = 2500; }
+        else if (g <= 150) { t_start = 1250; t_end = 8000; }
+        else if (g <= 200) { t_start = 1400; t_end = 10000; }
+        else { t_start = 2000; t_end = 15000; }
+        if (const char *e = getenv("TM_FSS_WINDOW_SCALE")) { const double f = atof(e); if (f > 0) { t_start *= f; t_end *= f; } }   // tests: shorter windows
+        vector<double> t_measure = linspace(t_start, t_end, 30);
+        vector<double> Rho_0((size_t)g * g, 1.0);
+        percolationDornic_2D(per_g[i], t_measure, Rho_0.data(), t_end + 10, a_c, b, D, sigma, dt, dx, r, g);
+    });
+    vector<vector<double>> vec;
+    for (const auto &rows : per_g) vec.insert(vec.end(), rows.begin(), rows.end());
+    write_finite_scaling_csv(finite_scaling_name("Stationary", t_max, dt, a_c, g_st, g_end, sigma, r), vec);
+}
+
 // ---- DP spreading experiments (P/:1145-1305, :1667-1772) -----------------------------------------
 
 void init_solitarytear(double array[], int length) // P/:90-97

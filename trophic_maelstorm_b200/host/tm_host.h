@@ -7,6 +7,7 @@
 //   expanded_percolationDornic_2D   Percolation_FD/stochasticSPDP.cpp:1809
 //   critical_exp_delta              Percolation_FD/stochasticSPDP.cpp:1309
 //   first_order_critical_exp_delta  Percolation_FD/stochasticSPDP.cpp:2422
+//   critical_exp_finite_scaling_collapse / _stationary   Percolation_FD/stochasticSPDP.cpp:1424, 1538
 //   rietkerk_Dornic_2D_MultiSp      Rietkerk_FD/rietkerk_bjork_basic.cpp:3397   (SPB = 1)
 //   first_order_critical_exp_delta_stochastic_MultiSp   Rietkerk_FD/rietkerk_bjork_basic.cpp:4379
 //   spreading_exp_Dornic_2D         Percolation_FD/stochasticSPDP.cpp:1145   (seed-at-centre runs: N(t), R^2(t), P_surv(t))
@@ -70,6 +71,15 @@ void expanded_percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::v
                                    double dx, int r, int g);
 void critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b, double D,
                         double sigma, double dt, double dx, int r, int g);
+// finite-size scaling at a_c (P/:1424, :1538): percolationDornic_2D from a full frame for `div` grid sizes -- linspace(g_st, g_end)
+// with the log10 time bins, resp. lnspace(g_st, g_end) with 30 linear bins in the reference's per-size stationary window (L > 30) --
+// grid sizes dealt over the visible GPUs; CSV "<data_root>/Data/SPDP/DEBUG_P_c_Finite_Scaling_{Collapse,Stationary}_T_..._R_<r>.csv"
+// with the first seven columns of the runner's rows, in grid order.
+std::vector<double> lnspace(double start_in, double end_in, int log_points);   // P/:281
+void critical_exp_finite_scaling_collapse(int div, int g_st, int g_end, double t_max, double a_c, double b, double D, double sigma,
+                                          double dt, double dx, int r);
+void critical_exp_finite_scaling_stationary(int div, int g_st, int g_end, double t_lim, double t_max, double a_c, double b, double D,
+                                            double sigma, double dt, double dx, int r);
 void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b,
                                     double c, double D, double sigma, double dt, double dx, int r, int g);
 

@@ -417,6 +417,17 @@ int tmh_riet3_run_any(int fpe, int L, const double *par, int r, const double *in
         for (size_t j = 0; j < 18; j++) rows_out[18 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
     return (int)Rho.size();
 }
+// finite-size scaling drivers (P/:1424, :1538); kind 0 = collapse, 1 = stationary; CSV under data_root
+int tmh_dp_finite_scaling(int kind, int div, int g_st, int g_end, double t_max, double a_c, double b, double D, double sigma, double dt,
+                          double dx, int r)
+{
+    try {
+        if (kind == 0) critical_exp_finite_scaling_collapse(div, g_st, g_end, t_max, a_c, b, D, sigma, dt, dx, r);
+        else critical_exp_finite_scaling_stationary(div, g_st, g_end, 0.0, t_max, a_c, b, D, sigma, dt, dx, r);
+    } catch (const std::exception &e) { fprintf(stderr, "tmh_dp_finite_scaling: %s\n", e.what()); return -2; }
+    return 0;
+}
+
 // TEST SEAM (tm_host_2sp.h test_stepper): the SPB = 2 / SPB = 3 runners' bookkeeping and CSV writers over a Stepper made of three caller-
 // supplied functions -- no device is touched.  tests/test_side_outputs.py passes the CPU oracle under sequential replay here and
 // compares the output tree with the one the unmodified reference wrote.  spb = 2 | 3; par / init / rows_out as tmh_riet2_run / tmh_riet3_run;
