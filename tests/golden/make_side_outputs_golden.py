@@ -24,6 +24,43 @@ sys.path.insert(0, HERE)
 from make_runner2_golden import driver_par, frame, ptr, uniforms   # noqa: E402
 
 
+def main_fpe():
+    """the Rietkerk_FPE flavour: side_outputs_fpe_2sp.json.gz from oracle/_ref/libtm_ref_fke_files.so (rietkerk_DorFPE_2D_MultiSp F/:3697)"""
+    tmp = tempfile.mkdtemp(prefix="tmsidefpe_")
+    os.chdir(tmp)
+    root = os.path.join(tmp, "Rietkerk") + "/"
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libtm_ref_fke_files.so"))
+    ref.reffkef_run.restype = C.c_uint64
+    L, r, seed, n_u = 12, 2, 93, 400000
+    dtv1 = round(0.11817455 * 100.0) / 100.0                     # order_2stoc_unity_rietkerk.cpp:58, :62
+    par = np.concatenate([driver_par(dt=dtv1), [dtv1]])
+    dt = par[21]
+    init = np.stack([frame(L, seed + j) for j in range(r)])
+    u = uniforms(seed, n_u)
+    t_meas = np.array([0.0] + [dt * k for k in (1, 2, 3, 5, 7, 9, 12)])      # 8 bins: FPE checkpoints at indices 6, 7 (no 60 % mark)
+    frame_t = np.array([dt * k for k in range(1, 14)] + [1e300])             # 14 entries: frames from frame_index 4 on (last ten), and t = 0
+    a_tag = "%g-%g_dP_%g_Geq_%.5g" % (par[0], par[0], 10000.0, 4.8)
+    os.makedirs(os.path.join(root, "Frames/Stochastic/2Sp", "SIDEFPE_" + a_tag))
+    os.makedirs(os.path.join(root, "Prelims/Stochastic/2Sp", "SIDEFPE_" + a_tag, "TimeSeries"))
+    os.makedirs(os.path.join(root, "Stochastic"))
+    ov = C.c_uint64()
+    cons = ref.reffkef_run(ptr(par), C.c_int(L), C.c_int(r), ptr(init), C.c_int(r), ptr(t_meas), C.c_int(len(t_meas)), ptr(frame_t),
+                           C.c_int(len(frame_t)), ptr(u), C.c_uint64(n_u), root.encode(), b"SIDEFPE", C.c_double(4.8), C.byref(ov))
+    assert ov.value == 0
+    files = {}
+    for dirpath, _, names in os.walk(root):
+        for nm in names:
+            p = os.path.join(dirpath, nm)
+            files[os.path.relpath(p, root)] = open(p).read()
+    print("FPE consumed", cons, "files", len(files))
+    for k in sorted(files):
+        print("  ", k, len(files[k]))
+    out = {"files": files, "par": par.tolist(), "L": L, "r": r, "t_meas": t_meas.tolist(), "frame_t": frame_t[:-1].tolist(), "seed": seed,
+           "n_u": n_u, "init": init.reshape(r, -1).tolist(), "consumed": int(cons), "Gstar": 4.8, "prefix": "SIDEFPE"}
+    with gzip.open(os.path.join(HERE, "side_outputs_fpe_2sp.json.gz"), "wt") as f:
+        json.dump(out, f)
+
+
 def main():
     tmp = tempfile.mkdtemp(prefix="tmside_")
     os.chdir(tmp)
@@ -62,4 +99,6 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--fpe-only" not in sys.argv:
+        main()
+    main_fpe()

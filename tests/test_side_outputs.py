@@ -64,13 +64,15 @@ class OracleStepper2:
         self.steps_done = 0
         self.calls = []
 
+    def _one_step(self, lib):
+        return lib.tmo_step_2sp_means(C.byref(self.pv), C.byref(self.pg), C.byref(self.pc),
+                                      self.central.ctypes.data_as(C.POINTER(C.c_int32)), len(self.central), C.c_double(self.fr),
+                                      C.byref(self.rng), O.ptr(self.f), O.ptr(self.gamma), O.ptr(self.veff), 1, None)
+
     def _step(self, n):
         lib = O.oracle()
         for _ in range(n):
-            rc = lib.tmo_step_2sp_means(C.byref(self.pv), C.byref(self.pg), C.byref(self.pc),
-                                        self.central.ctypes.data_as(C.POINTER(C.c_int32)), len(self.central), C.c_double(self.fr),
-                                        C.byref(self.rng), O.ptr(self.f), O.ptr(self.gamma), O.ptr(self.veff), 1, None)
-            assert rc == 0
+            assert self._one_step(lib) == 0
         self.steps_done += n
 
     def finish_replicate(self):
@@ -102,6 +104,22 @@ class OracleStepper2:
             np.ctypeslib.as_array(gamma, shape=(n,))[:] = self.gamma
         if veff:
             np.ctypeslib.as_array(veff, shape=(2 * n,))[:] = self.veff.reshape(-1)
+
+
+class OracleStepperFpe2(OracleStepper2):
+    """the same for the Rietkerk_FPE runner of the SPB = 2 model (tmo_step_fpe_2sp, pinned in test_fpe_runner_oracle.py); the movement
+    constants are the ones set_global_FKE_params derives (tmo_fke_params, pinned on the reference in test_fke_oracle.py)"""
+
+    def __init__(self, L, par, u, n_loop):
+        OracleStepper2.__init__(self, L, par[:23], u, n_loop)
+        d = O.fke_params(par[10], par[15], par[23], par[22])
+        derived = [d.beta_vel, d.sigma_D, d.sigma_vD, d.mu_vel_prefactor, d.bound_D, d.bound_vD_first, d.bound_vD_second, 1.0e-10]
+        self.pv, self.pc, self.M1, self.terms, self.gD, self.gV, R, self.fr = O.fpe_runner_params(L, par, derived)
+
+    def _one_step(self, lib):
+        return lib.tmo_step_fpe_2sp(C.byref(self.pv), C.byref(self.pc), C.c_double(self.M1), C.byref(self.terms), O.ptr(self.gD),
+                                    O.ptr(self.gV), self.central.ctypes.data_as(C.POINTER(C.c_int32)), len(self.central),
+                                    C.c_double(self.fr), C.byref(self.rng), O.ptr(self.f), O.ptr(self.gamma), O.ptr(self.veff), None)
 
 
 UP = C.CFUNCTYPE(None, dp)
@@ -161,6 +179,39 @@ def test_spb2_output_tree_equals_the_reference(host, tmp_path):
     assert tab.shape == (len(t_meas), 3 + 11)
     np.testing.assert_allclose(rows[:, 3:], tab[:, 3:], rtol=2e-5, atol=1e-300)
     assert np.array_equal(rows[:, 0], np.full(len(t_meas), par[0])) and np.array_equal(rows[:, 1], np.full(len(t_meas), r))
+
+
+def test_fpe_spb2_output_tree_equals_the_reference(host, tmp_path):
+    """rietkerk_DorFPE_2D_MultiSp (F/:3697): the Rietkerk_FPE flavour of the bookkeeping -- checkpoints at the 85 / 90 / 95 / 100 % bins
+    only (F/:3032), frames by its own rule (F/:2886: here t = 0 and the last ten of the schedule) -- against the tree the unmodified
+    reference wrote (oracle/ref_harness_fke_files.cpp)."""
+    with gzip.open(os.path.join(HERE, "golden", "side_outputs_fpe_2sp.json.gz"), "rt") as f:
+        g = json.load(f)
+    L, r = g["L"], g["r"]
+    par = np.array(g["par"])
+    t_meas = np.array(g["t_meas"])
+    frame_t = np.array(g["frame_t"] + [1e300])
+    init = np.array(g["init"]).reshape(r, 4, L * L)
+    u = np.random.RandomState(g["seed"]).random_sample(g["n_u"])
+    st = OracleStepperFpe2(L, par, u, _loop_iterations(t_meas[-1], par[21]))
+    root = str(tmp_path) + "/"
+    rows = _side_run(host, 12, L, par, r, init, t_meas, frame_t, root, g["prefix"], g["Gstar"], st, 14)
+    st.finish_replicate()
+    assert st.rng.overflow == 0 and st.rng.pos == g["consumed"]
+    want = {_normalise(k): v for k, v in g["files"].items()}
+    got = _tree(root)
+    assert sorted(got) == sorted(want)
+    for k in sorted(want):
+        if "MOVSERIES" in k:
+            # Rietkerk_FPE's save_prelimframe walks 3 + 4 SpB columns of every table (F/:2758-2763): two doubles past the end of a
+            # movement row, heap garbage in the reference's file; the host layer writes the same number of columns with zeros there
+            w = ["" if i == 0 else ",".join(ln.split(",")[:12] + ["0", "0", ""]) for i, ln in enumerate(want[k].splitlines())]
+            gl = got[k].splitlines()
+            assert gl[0] == want[k].splitlines()[0] and gl[1:] == w[1:], k
+        else:
+            assert got[k] == want[k], k
+    assert not any("_T_0.6_" in k and "PRELIM" in k for k in got)        # index 4 = int(0.6 * 8): a checkpoint of Rietkerk_FD only
+    assert np.isfinite(rows).all()
 
 
 def test_side_outputs_off(host, tmp_path):

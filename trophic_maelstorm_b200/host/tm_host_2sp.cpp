@@ -167,7 +167,7 @@ void run_2sp(bool fpe, D2Vec_Double &Rho, vector<double> &t_meas, double a, doub
     }
 
     side::Config cfg;
-    cfg.Sp = Sp; cfg.SpB = SpB; cfg.g = g; cfg.a = a; cfg.a_st = a_st; cfg.a_end = a_end; cfg.dt = dt; cfg.dx = dx; cfg.dP = dP;
+    cfg.Sp = Sp; cfg.SpB = SpB; cfg.g = g; cfg.fpe = fpe; cfg.a = a; cfg.a_st = a_st; cfg.a_end = a_end; cfg.dt = dt; cfg.dx = dx; cfg.dP = dP;
     cfg.D1 = D[1]; cfg.D2 = D[2]; cfg.Gstar = Gstar; cfg.Vstar = Vstar; cfg.t_max = t_end;
     cfg.frame_folder = frame_folder.empty() ? options().data_root + "/Data/Rietkerk/Frames/Stochastic/2Sp/" + prefix + "_" : frame_folder;
     cfg.prelim_folder = prelim_folder.empty() ? options().data_root + "/Data/Rietkerk/Prelims/Stochastic/2Sp/" + prefix + "_" : prelim_folder;

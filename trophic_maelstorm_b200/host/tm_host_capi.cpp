@@ -430,7 +430,8 @@ int tmh_dp_finite_scaling(int kind, int div, int g_st, int g_end, double t_max, 
 
 // TEST SEAM (tm_host_2sp.h test_stepper): the SPB = 2 / SPB = 3 runners' bookkeeping and CSV writers over a Stepper made of three caller-
 // supplied functions -- no device is touched.  tests/test_side_outputs.py passes the CPU oracle under sequential replay here and
-// compares the output tree with the one the unmodified reference wrote.  spb = 2 | 3; par / init / rows_out as tmh_riet2_run / tmh_riet3_run;
+// compares the output tree with the one the unmodified reference wrote.  spb = 2 | 3 (Rietkerk_FD runner), 12 | 13 (the Rietkerk_FPE
+// runner rietkerk_DorFPE_2D_MultiSp of the same SPB); par / init / rows_out as tmh_riet2_run / tmh_riet3_run;
 // frame_t: tm_b200::frame_tmeas for this call; folders "<root>/Frames/Stochastic/<n>Sp/<prefix>_" as set_Prefix lays them out.
 typedef void (*tmh_upload_fn)(const double *frame);
 typedef void (*tmh_run_fn)(uint32_t replicate, uint32_t step0, int nsteps);
@@ -451,6 +452,8 @@ int tmh_side_run(int spb, int L, const double *par, int r, const double *init, i
     const bool saved_wp = write_prelims;
     frame_tmeas.assign(frame_t, frame_t + n_frame_t);
     prefix = user_prefix; write_prelims = prelims != 0;
+    const bool fpe = spb >= 12;
+    if (fpe) spb -= 10;
     const std::string sp = std::to_string(spb) + "Sp/";
     std::vector<double> tm(t_meas, t_meas + n_tmeas);
     std::vector<std::vector<double>> Rho;
@@ -472,7 +475,7 @@ int tmh_side_run(int spb, int L, const double *par, int r, const double *init, i
             s2::frame_folder = std::string(root) + "Frames/Stochastic/" + sp + user_prefix + "_";
             s2::prelim_folder = std::string(root) + "Prelims/Stochastic/" + sp + user_prefix + "_";
             s2::test_stepper = &fn;
-            s2::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+            (fpe ? s2::rietkerk_DorFPE_2D_MultiSp : s2::rietkerk_Dornic_2D_MultiSp)(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
                                            1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[21], par[22], 10000.0, r, L, Gstar, Vstar);
             width = 14;
         } else if (spb == 3) {
@@ -492,7 +495,7 @@ int tmh_side_run(int spb, int L, const double *par, int r, const double *init, i
             s3::frame_folder = std::string(root) + "Frames/Stochastic/" + sp + user_prefix + "_";
             s3::prelim_folder = std::string(root) + "Prelims/Stochastic/" + sp + user_prefix + "_";
             s3::test_stepper = &fn;
-            s3::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
+            (fpe ? s3::rietkerk_DorFPE_2D_MultiSp : s3::rietkerk_Dornic_2D_MultiSp)(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
                                            1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[29], par[30], 10000.0, r, L, Gstar, Vstar);
             width = 18;
         } else rc = -3;

@@ -36,6 +36,7 @@ struct Stepper {
 
 struct Config {
     int Sp = 4, SpB = 2, g = 0;
+    bool fpe = false;                             // Rietkerk_FPE's runner: checkpoints at 85 / 90 / 95 / 100 % only (F/:3032), its own frame rule (F/:2886, 2993)
     double a = 0, a_st = 0, a_end = 0, dt = 0, dx = 0, dP = 0, D1 = 0, D2 = 0, Gstar = -1, Vstar = -1, t_max = 0;
     std::string frame_folder, prelim_folder;      // "<...>/Frames/Stochastic/<n>Sp/<prefix>_", "<...>/Prelims/Stochastic/<n>Sp/<prefix>_"
     std::string frame_header, gammaheader, prelimheader, movmheader;
@@ -65,9 +66,14 @@ public:
         write_series(index, j, t, Rho_M, t_meas);
         if (Rho_M[index][0] != 0.0) return 0;
         const int marks[5] = {int(tot_iter_ * 0.6), int(tot_iter_ * 0.85), int(tot_iter_ * 0.9), int(tot_iter_ * 0.95), int(tot_iter_ - 1)};
-        for (int k = 0; k < 5; k++)
+        for (int k = c_.fpe ? 1 : 0; k < 5; k++)                                                 // F/:3091: no 60 % mark
             if (index <= marks[k]) write_series(marks[k], j, t_meas[marks[k]], Rho_M, t_meas);   // R/:3094-3131
         return 1;
+    }
+    bool is_checkpoint(int index) const
+    {
+        return (!c_.fpe && index == int(tot_iter_ * 0.6)) || index == int(tot_iter_ * 0.85) || index == int(tot_iter_ * 0.9)
+            || index == int(tot_iter_ * 0.95) || index == int(tot_iter_ - 1);                    // R/:3703, F/:3032
     }
 
     void frames(double t, int j, const double *frame, const double *gamma)
@@ -114,7 +120,10 @@ private:
     void write_series(int idx, int j, double t, const std::vector<std::vector<double>> &X, const std::vector<double> &t_meas)
     {
         const int Sp = c_.Sp, SpB = c_.SpB;
-        std::vector<std::vector<double>> tab(idx + 1, std::vector<double>(4 * SpB + 3, 0.0)), mov(idx + 1, std::vector<double>(4 * SpB + 1, 0.0));
+        std::vector<std::vector<double>> tab(idx + 1, std::vector<double>(4 * SpB + 3, 0.0));
+        // Rietkerk_FPE's save_prelimframe (F/:2758-2763) always walks 3 + 4 SpB columns, two past the end of a movement row (heap
+        // garbage in the reference's files): the same number of columns here, zeros in the last two
+        std::vector<std::vector<double>> mov(idx + 1, std::vector<double>(4 * SpB + 1 + (c_.fpe ? 2 : 0), 0.0));
         for (int s = 0; s < SpB; s++)
             for (int i = 0; i <= idx; i++) {
                 if (X[i][2 * s] == 0.0) break;
@@ -194,16 +203,16 @@ inline void run_replicates(Stepper &st, const Config &c, const Run &R, const std
                 }
                 if (prelims) w.measure(index, gamma.data(), veff.data());            // R/:3670-3700
                 if (R.on_measure) R.on_measure(j, index, t, frame.data());
-                const bool checkpoint = index == int(tot_iter * 0.6) || index == int(tot_iter * 0.85) || index == int(tot_iter * 0.9)
-                                     || index == int(tot_iter * 0.95) || index == int(tot_iter - 1);
-                if (checkpoint) {                                                     // R/:3703-3716
+                if (w.is_checkpoint(index)) {                                         // R/:3703-3716, F/:4068-4072
                     if (prelims) w.checkpoint(index, j, t, Rho_M, t_meas);
                     if (Rho_M[index][0] == 0.0) break;                                // all vegetation dead: on to the next replicate
                 }
                 index += 1;
             }
             if (snap) {
-                if (frame_index + 10 >= ftm.size() || (t >= 50000 && t <= 150000) || (t >= 20 && t <= 15000) || t == 0) {   // R/:3739
+                bool save = frame_index + 10 >= ftm.size() || (t >= 50000 && t <= 150000) || (t >= (c.fpe ? 50 : 20) && t <= 15000) || t == 0;   // R/:3739, F/:2886
+                if (c.fpe && t > 1500 && t < 6000 && frame_index % 2 != 0) save = false;     // F/:2993-3004: every second frame in that window
+                if (save) {
                     sync(true);
                     w.frames(t, j, frame.data(), gamma.data());
                 }
