@@ -66,3 +66,39 @@ def test_spb2_sweep_tree_with_side_outputs(tmp_path):
     assert one[0].startswith(" a , r, L, t , <GAM[P(x; t)]>_x") and len(one[1].split(",")) == 13   # 12 values + the trailing comma
     table = [k for k in names if k.startswith("Data/Rietkerk/Stochastic/2Sp/1stCC_Rietkerk_")]
     assert len(table) == 1
+
+
+def test_spb2_argv_driver_binary(tmp_path):
+    """drivers/order_2stoc_test_rietkerk: the eleven-argument form of Rietkerk_FD/order_2stoc_test_rietkerk.cpp:159-172 end to end --
+    run folders tagged _Veq_<V*> (:303-309), the MFT initial frame of :245-283 through init_exprtk_randbiMFTframe's rule (R/:474-496),
+    the final table in the reference's place with 14 columns."""
+    import subprocess
+    exe = os.path.join(ROOT, "drivers", "order_2stoc_test_rietkerk")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    env = dict(os.environ, TM_DATA_ROOT=str(tmp_path), TM_SEED="7")
+    out = subprocess.run([exe, "0.1", "1.5", "16", "2", "0.05", "0.06", "2", "10000", "1", "1", "TEST"], text=True, capture_output=True,
+                         env=env, timeout=1500)
+    assert out.returncode == 0, out.stderr
+    t = {k: v.decode() for k, v in _tree(tmp_path).items()}
+    aij = 3.6 * 10.0 ** -6.08 * 20.0 ** -0.37
+    m = 0.061609 * 20.0 ** -0.25 / 8760.0
+    vstar = m / ((0.45 - m) * aij)
+    tag = "TEST_0.05-0.06_dP_10000_Veq_%.5g" % vstar
+    table = "Data/Rietkerk/Stochastic/2Sp/1stCC_Rietkerk_TEST_P_c_G_16_T_1.5_dt_0.1_D1_0.0103_a1_0.05_a2_0.06_dx_0.1_Veq_%.5g_R_2.csv" % vstar
+    assert table in t, sorted(t)[:6]
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in t[table].splitlines()[2:]])
+    assert rows.shape[1] == 14 and set(np.round(rows[:, 0], 6)) == {0.05, 0.06} and np.all(rows[:, 2] == 16) and np.isfinite(rows).all()
+    f0 = "Data/Rietkerk/Frames/Stochastic/2Sp/%s/FRAME_P_c_DP_G_16_T_0_dt_0.1_a_0.05_D1_0.0103_jID_0_dx_0.1_R_0.csv" % tag
+    assert f0 in t, [k for k in sorted(t) if "FRAME" in k][:4]
+    fr = np.array([[float(x) for x in ln.split(",")] for ln in t[f0].splitlines()[1:]])
+    six = lambda x: float("%f" % x)                              # the reference's std::to_string round trip of its MFT constants
+    G = six(7332.541) * (1 - np.exp(six(-15.5375) * (0.05 - six(1 / 24.0))))
+    O = six((vstar + 5000) / ((vstar + 5000 * 0.2) * (0.2 / 24.0))) * 0.05
+    veg = fr[:, 2]
+    assert set(np.unique(veg)) <= {float("%.6g" % six(vstar)), 10000.0} and (veg == 10000.0).sum() <= 0.1 * len(veg)
+    np.testing.assert_allclose(fr[:, 3], G, rtol=1e-5)           # frames carry six significant digits
+    np.testing.assert_allclose(fr[:, 4], six(120.0) * 0.05, rtol=1e-5)
+    np.testing.assert_allclose(fr[:, 5], O, rtol=1e-5)
+    assert any(k.startswith("Data/Rietkerk/Prelims/Stochastic/2Sp/%s/TimeSeries/PRELIM_MOVSERIES_" % tag) for k in t)
+    out = subprocess.run([exe, "0.1", "3"], text=True, capture_output=True)
+    assert out.returncode == 1 and "Please enter the correct number of arguments" in out.stdout

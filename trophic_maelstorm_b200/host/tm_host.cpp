@@ -559,6 +559,24 @@ void default_init_frame(double *f, int g, int replicate, double a, double a_c, d
 }
 } // namespace
 
+// init_exprtk_randbiMFTframe, R/:396-505, for any number of fields: `expr` holds the values of the driver's 2 * n_fields MFT expressions
+// (MFT_Vec_CoexExpr: the state below a_c, then the coexistence state) at this a.  The speckle mask comes from options().seed and the
+// replicate (splitmix64) where the reference seeds mt19937_64 from random_device (R/:420-423).
+void init_randbiMFTframe(double *f, int n_fields, int g, int replicate, double a, double a_c, double dP, double perc, const double clow[],
+                         const double expr[])
+{
+    const size_t n = (size_t)g * g;
+    unsigned long long s = options().seed ^ (0xA5A5A5A5ull * (unsigned long long)(replicate + 1));
+    const int off = a < a_c ? 0 : n_fields;                                      // R/:450, :474
+    const double base = a < a_c ? clow[0] * expr[0] : expr[n_fields];            // R/:463, :487
+    const double high = std::max(dP, clow[off] * expr[off]);                     // R/:452, :476
+    for (size_t i = 0; i < n; i++) f[i] = ((splitmix(s) >> 11) * 0x1.0p-53 <= perc) ? high : base;
+    for (int sp = 1; sp < n_fields; sp++) {
+        const double v = expr[off + sp] == 0 ? clow[off + sp] : clow[off + sp] * expr[off + sp];   // R/:467-470, :491-494
+        for (size_t i = 0; i < n; i++) f[(size_t)sp * n + i] = v;
+    }
+}
+
 std::function<void(double *, int, int, double, double, double, const double[])> init_frame = default_init_frame;
 
 void save_frame(D2Vec_Double &Rho_t, const std::string &parendir, const std::string &filenamePattern, double a, double,

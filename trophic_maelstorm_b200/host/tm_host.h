@@ -135,6 +135,11 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
                                                        double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
                                                        int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
                                                        double Gstar = -1.0, double Vstar = -1.0);
+// init_exprtk_randbiMFTframe (R/:396-505) for any number of fields, given the values expr[2 * n_fields] of the driver's MFT expressions
+// at this a (below-a_c state first, coexistence state second); perc = 0.015 in the runners (R/:3403).  What the SPB >= 2 drivers assign
+// to spb2::init_frame / spb3::init_frame.
+void init_randbiMFTframe(double *frame, int n_fields, int g, int replicate, double a, double a_c, double dP, double perc,
+                         const double clow[], const double expr[]);
 // the sweeps' schedules (R/:4395-4459): returns t_measure and sets frame_tmeas
 std::vector<double> sweep_time_schedule(double t_max, double dt);
 // burn-in frames (the reference's -DINIT=2 path): read_frame_csv parses one frame in save_frame()'s layout
