@@ -66,7 +66,7 @@ int main(int argc, char *argv[])
     if (2 * v[1] * dt / dx > 1) cout << "Warning: CFL condition violated. The velocity of the grazer is too high for the given dx and dt." << endl;
     else cout << "CFL condition satisfied." << endl;
     if (pre == "N/A" || pre == "n/a" || pre == "NA" || pre == "na" || pre == "N" || pre == "n" || pre == "") pre = prefix;
-    set_Prefix(pre);   // tm_b200::prefix; the SPB = 2 layer derives ".../Frames/Stochastic/2Sp/<prefix>_" etc. from it
+    s2::set_Prefix(pre);   // prefix and the three output locations, R/:113-135 with SpB = 2
 
     aij = aij_scale * aij; A[0][1] = aij; A[1][0] = aij;                                                                           // :208
     const double Vstar = m / ((ej - m * hij) * aij);
@@ -87,13 +87,12 @@ int main(int argc, char *argv[])
     };
 
     stringstream ast, est, veq, dPo; ast << a_start; est << a_end; dPo << dP; veq << setprecision(5) << Vstar;
-    const string froot = options().data_root + "/Data/Rietkerk/Frames/Stochastic/2Sp/" + prefix + "_";
-    const string proot = options().data_root + "/Data/Rietkerk/Prelims/Stochastic/2Sp/" + prefix + "_";
     const string tag = ast.str() + "-" + est.str() + "_dP_" + dPo.str() + "_Veq_" + veq.str();
-    recursive_dir_create(froot + tag);
-    recursive_dir_create(proot + tag + "/TimeSeries");
+    recursive_dir_create(s2::frame_folder + tag);
+    recursive_dir_create(s2::prelim_folder + tag + "/TimeSeries");
     recursive_dir_create(options().data_root + "/Data/Rietkerk/Stochastic/2Sp");
-    cout << "Save directory for frames: " << froot << "\nSave directory for preliminary data: " << proot << "\nGPUs: " << device_list().size() << endl;
+    cout << "Save directory for frames: " << s2::frame_folder << "\nSave directory for preliminary data: " << s2::prelim_folder
+         << "\nSave directory for final data: " << s2::stat_prefix << "\nGPUs: " << device_list().size() << endl;
     try {
         s2::first_order_critical_exp_delta_stochastic_MultiSp(div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, v, K, sigma, A, H, E,
                                                               M, pR, dtV, scaling_factor, dt, dx, dP, r, g, -1, Vstar);

@@ -84,7 +84,7 @@ def test_spb2_argv_driver_binary(tmp_path):
     m = 0.061609 * 20.0 ** -0.25 / 8760.0
     vstar = m / ((0.45 - m) * aij)
     tag = "TEST_0.05-0.06_dP_10000_Veq_%.5g" % vstar
-    table = "Data/Rietkerk/Stochastic/2Sp/1stCC_Rietkerk_TEST_P_c_G_16_T_1.5_dt_0.1_D1_0.0103_a1_0.05_a2_0.06_dx_0.1_Veq_%.5g_R_2.csv" % vstar
+    table = "Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_TEST_P_c_G_16_T_1.5_dt_0.1_D1_0.0103_a1_0.05_a2_0.06_dx_0.1_Veq_%.5g_R_2.csv" % vstar   # set_Prefix, R/:133
     assert table in t, sorted(t)[:6]
     rows = np.array([[float(x) for x in ln.split(",")] for ln in t[table].splitlines()[2:]])
     assert rows.shape[1] == 14 and set(np.round(rows[:, 0], 6)) == {0.05, 0.06} and np.all(rows[:, 2] == 16) and np.isfinite(rows).all()
@@ -102,3 +102,36 @@ def test_spb2_argv_driver_binary(tmp_path):
     assert any(k.startswith("Data/Rietkerk/Prelims/Stochastic/2Sp/%s/TimeSeries/PRELIM_MOVSERIES_" % tag) for k in t)
     out = subprocess.run([exe, "0.1", "3"], text=True, capture_output=True)
     assert out.returncode == 1 and "Please enter the correct number of arguments" in out.stdout
+
+
+def test_fpe_spb2_unity_driver_binary(tmp_path):
+    """drivers/order_2stoc_unity_rietkerk: Rietkerk_FPE/order_2stoc_unity_rietkerk.cpp end to end -- dt fixed at the rounded advection
+    time scale 0.12 whatever the first argument says (:58-62, 166), folders under 2Sp_mG_20 (set_Prefix(prefix, mGrazer) :197), the final
+    table at Stochastic/1stOrderCC_Rietkerk_<prefix>_..., the deterministic Gaussian initial frame of F/:3954-3962."""
+    import subprocess
+    exe = os.path.join(ROOT, "drivers", "order_2stoc_unity_rietkerk")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    env = dict(os.environ, TM_DATA_ROOT=str(tmp_path), TM_SEED="7")
+    L = 16
+    out = subprocess.run([exe, "0.5", "1.5", str(L), "2", "0.05", "0.06", "2", "10000", "0.5", "1", "TEST"], text=True, capture_output=True,
+                         env=env, timeout=1500)
+    assert out.returncode == 0, out.stderr
+    t = {k: v.decode() for k, v in _tree(tmp_path).items()}
+    aij = 3.6 * 10.0 ** -6.08 * 20.0 ** -0.37
+    m = 0.061609 * 20.0 ** -0.25 / 8760.0
+    vstar = m / ((0.45 - m) * aij)
+    tag = "TEST_0.05-0.06_dP_10000_Veq_%.5g" % vstar
+    table = "Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_TEST_P_c_G_16_T_1.5_dt_0.12_D1_0.0103_a1_0.05_a2_0.06_dx_0.1_Veq_%.5g_R_2.csv" % vstar
+    assert table in t, sorted(t)[:6]
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in t[table].splitlines()[2:]])
+    assert rows.shape[1] == 14 and set(np.round(rows[:, 0], 6)) == {0.05, 0.06} and np.isfinite(rows).all()
+    assert np.allclose(np.unique(np.round(rows[:, 3] / 0.12)) * 0.12, np.unique(rows[:, 3]))       # every bin is a multiple of dt = 0.12
+    f0 = "Data/Rietkerk/Frames/Stochastic/2Sp_mG_20/%s/FRAME_P_c_DP_G_16_T_0_dt_0.12_a_0.05_D1_0.0103_jID_0_dx_0.1_R_0.csv" % tag
+    assert f0 in t, [k for k in sorted(t) if "FRAME" in k][:4]
+    fr = np.array([[float(x) for x in ln.split(",")] for ln in t[f0].splitlines()[1:]])
+    i, j = np.divmod(np.arange(L * L), L)
+    P = 5.0 * np.exp(-((i - L // 8) ** 2 + (j - L // 8) ** 2) / (2 * (L / 8.0) ** 2))             # amp = clow[Sp..]: {5, init_frac, 1, 1}
+    G = 0.5 * np.exp(-((i - 7 * L // 8) ** 2 + (j - L // 8) ** 2) / (2 * (L / 16.0) ** 2))
+    np.testing.assert_allclose(fr[:, 2], P, rtol=1e-5)
+    np.testing.assert_allclose(fr[:, 3], G, rtol=1e-5, atol=1e-300)
+    assert np.all(fr[:, 4] == 1.0) and np.all(fr[:, 5] == 1.0)

@@ -577,6 +577,23 @@ void init_randbiMFTframe(double *f, int n_fields, int g, int replicate, double a
     }
 }
 
+// init_gaussframe + init_gaussiantear, F/:1089-1199: what Rietkerk_FPE's runner starts from as shipped (F/:3954-3962, amp = clow[Sp..2Sp),
+// sd = {g/8, g/16, g/16, ...}).  The first n_gauss fields are Gaussian bumps amp[s] exp(-((i - cx)^2 + (j - cy)^2) / (2 sd^2)) around the
+// corners (g/8, g/8), (7g/8, g/8), (7g/8, 7g/8), (g/8, 7g/8) in turn (not wrapped periodically), the others the constants amp[s].
+void init_gaussframe(double *f, int n_fields, int n_gauss, int g, const double amp[])
+{
+    const size_t n = (size_t)g * g;
+    for (int s = 0; s < n_gauss; s++) {
+        const double cx = (s % 4) % 3 == 0 ? int(g / 8) : int(7 * g / 8), cy = (s % 4) < 2 ? int(g / 8) : int(7 * g / 8);   // F/:1120-1121
+        const double sd = s == 0 ? g / 8.0 : g / 16.0;                                                                     // F/:3959
+        for (int i = 0; i < g; i++)
+            for (int j = 0; j < g; j++)
+                f[s * n + (size_t)i * g + j] = amp[s] * std::exp(-((i - cx) * (i - cx) + (j - cy) * (j - cy)) / (2 * sd * sd));   // F/:1196
+    }
+    for (int s = n_gauss; s < n_fields; s++)
+        for (size_t i = 0; i < n; i++) f[s * n + i] = amp[s];
+}
+
 std::function<void(double *, int, int, double, double, double, const double[])> init_frame = default_init_frame;
 
 void save_frame(D2Vec_Double &Rho_t, const std::string &parendir, const std::string &filenamePattern, double a, double,
@@ -620,21 +637,24 @@ std::string prelim_folder;                            // default "<data_root>/Da
 std::string stat_prefix;                              // default "<data_root>/Data/Rietkerk/Stochastic/1Sp/1stCC_Rietkerk_<prefix>_P_c_G_"
 bool write_prelims = true;
 
-void set_Prefix(const std::string &user_prefix, double mG, double mP) // R/:113-135
+void set_Prefix_for(int n_biota, const std::string &user_prefix, double mG, double mP, std::string &frames, std::string &prelims,
+                    std::string &stats) // R/:113-135 (F/:143-165) for a binary compiled with -DSPB=n_biota
 {
     prefix = user_prefix;
     mG = (mG == int(mG)) ? int(mG) : std::round(mG * 100) / 100;
     mP = (mP == int(mP)) ? int(mP) : std::round(mP * 100) / 100;
     std::ostringstream g_, p_;
     g_ << std::defaultfloat << mG; p_ << std::defaultfloat << mP;
-    std::string sp = std::to_string(SpB) + "Sp";
+    std::string sp = std::to_string(n_biota) + "Sp";
     if (mG > 0.0 && mP > 0.0) sp += "_mG_" + g_.str() + "_mP_" + p_.str();
     else if (mG > 0.0 && mP == 0.0) sp += "_mG_" + g_.str();
     const std::string root = options().data_root + "/Data/Rietkerk/";
-    frame_folder = root + "Frames/Stochastic/" + sp + "/" + prefix + "_";
-    prelim_folder = root + "Prelims/Stochastic/" + sp + "/" + prefix + "_";
-    stat_prefix = root + "Stochastic/1stOrderCC_Rietkerk_" + prefix + "_P_c_G_";
+    frames = root + "Frames/Stochastic/" + sp + "/" + prefix + "_";
+    prelims = root + "Prelims/Stochastic/" + sp + "/" + prefix + "_";
+    stats = root + "Stochastic/1stOrderCC_Rietkerk_" + prefix + "_P_c_G_";
 }
+
+void set_Prefix(const std::string &user_prefix, double mG, double mP) { set_Prefix_for(SpB, user_prefix, mG, mP, frame_folder, prelim_folder, stat_prefix); }
 
 void recursive_dir_create(const std::string &path) { mkdirs(path); }
 const std::string prelimheader = " a , r, L, t , <<W(x; t)>_x>_r, <<O(x; t)>_x>_r,  <<P(x; t)>_x>_r, Var[<P(x; t)>_x]_r, # Surviving Runs P(x; t),"

@@ -140,6 +140,9 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
 // to spb2::init_frame / spb3::init_frame.
 void init_randbiMFTframe(double *frame, int n_fields, int g, int replicate, double a, double a_c, double dP, double perc,
                          const double clow[], const double expr[]);
+// init_gaussframe (F/:1089-1199): the deterministic initial frame Rietkerk_FPE's runner uses as shipped (F/:3954-3962): Gaussian bumps
+// of amplitude amp[s] for the first n_gauss (= SpB) fields, constants amp[s] for the rest; the runner passes amp = clow[Sp..2Sp)
+void init_gaussframe(double *frame, int n_fields, int n_gauss, int g, const double amp[]);
 // the sweeps' schedules (R/:4395-4459): returns t_measure and sets frame_tmeas
 std::vector<double> sweep_time_schedule(double t_max, double dt);
 // burn-in frames (the reference's -DINIT=2 path): read_frame_csv parses one frame in save_frame()'s layout
@@ -150,6 +153,9 @@ void use_burnin_frames(const std::string &parendir, const std::string &filenameP
 void use_default_init_frame();   // back to the MFT speckle rule
 // set_Prefix (R/:113-135): prefix and the three output locations derived from it, "<data_root>/Data/Rietkerk/..." for the reference's "../Data/Rietkerk/..."
 void set_Prefix(const std::string &user_prefix, double mG = 0.0, double mP = 0.0);
+// the same rule for a binary compiled with -DSPB=n_biota, writing the three locations into the caller's variables (spb2 / spb3 set_Prefix)
+void set_Prefix_for(int n_biota, const std::string &user_prefix, double mG, double mP, std::string &frames, std::string &prelims,
+                    std::string &stats);
 void recursive_dir_create(const std::string &path);    // R/: mkdir -p
 extern std::string prefix, prelim_folder, stat_prefix; // R/ header :97-108; empty folders = "<data_root>/Data/Rietkerk/..."
 extern bool write_prelims;                             // PRELIM_AGGRAND_*.csv per replicate (R/:4327-4349) and the TimeSeries/PRELIM_TSERIES_* checkpoints (R/:3029)

@@ -42,6 +42,10 @@ extern std::function<void(int replicate, int index, double t, const double *fram
 // Output locations of the side outputs; empty (default) = "<data_root>/Data/Rietkerk/{Frames,Prelims}/Stochastic/2Sp/<prefix>_"
 // with tm_b200::prefix (the reference's frame_folder / prelim_folder, header :106-107).
 extern std::string frame_folder, prelim_folder;
+// set_Prefix (R/:113-135, F/:143-165) of the -DSPB=2 binaries: tm_b200::prefix and the three output locations
+// "<data_root>/Data/Rietkerk/{Frames,Prelims}/Stochastic/2Sp[_mG_<mG>[_mP_<mP>]]/<prefix>_", ".../Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_"
+extern std::string stat_prefix;   // empty (default): the header's location of the final table, ".../Stochastic/2Sp/1stCC_Rietkerk_<prefix>_P_c_G_"
+void set_Prefix(const std::string &user_prefix, double mG = 0.0, double mP = 0.0);
 extern const std::string frame_header, gammaheader, movmheader;   // rietkerk_bjork_constants_2Sp.h:6-15
 
 std::vector<std::pair<int, int>> computeNeighboringSitesCentral(int R);

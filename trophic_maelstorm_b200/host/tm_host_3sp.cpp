@@ -24,7 +24,8 @@ using std::vector;
 
 std::function<void(double *, int, int, double, double, double, const double[])> init_frame;
 std::function<void(int, int, double, const double *)> on_measure;
-std::string frame_folder, prelim_folder;
+std::string frame_folder, prelim_folder, stat_prefix;
+void set_Prefix(const std::string &user_prefix, double mG, double mP) { set_Prefix_for(SpB, user_prefix, mG, mP, frame_folder, prelim_folder, stat_prefix); }
 side::Stepper *test_stepper = nullptr;
 const std::string frame_header = "a_c,  x,  P(x; t), G(x; t), Pr(x; t), W(x; t), O(x; t) \n";            // rietkerk_bjork_constants_3Sp.h:6
 const std::string gammaheader = "a_c,  x,  GAM[P(x; t)], GAM[G(x; t)], GAM[Pr(x; t)] \n";                 // :8
@@ -216,14 +217,12 @@ void sweep_3sp(bool fpe, int div, double t_max, double a_start, double a_end, do
     // Rietkerk_FD: "../Data/Rietkerk/Stochastic/3Sp/1stCC_Rietkerk_<prefix>_P_c_G_"; Rietkerk_FPE's set_Prefix (F/:143-165):
     // "../Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_"
     const std::string dir = options().data_root + (fpe ? "/Data/Rietkerk/Stochastic" : "/Data/Rietkerk/Stochastic/3Sp");
-    std::string path;
-    for (size_t k = 1; k <= dir.size(); k++)                                         // mkdir -p
-        if (k == dir.size() || dir[k] == '/') { path = dir.substr(0, k); mkdir(path.c_str(), 0777); }
-    std::string savefile = dir + (fpe ? "/1stOrderCC_Rietkerk_" : "/1stCC_Rietkerk_") + prefix + "_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
+    std::string savefile = (stat_prefix.empty() ? dir + (fpe ? "/1stOrderCC_Rietkerk_" : "/1stCC_Rietkerk_") + prefix + "_P_c_G_" : stat_prefix) + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_D1_" + Dm1.str()
                          + "_a1_" + p1.str() + "_a2_" + p2.str() + "_dx_" + dix.str();                                    // R/:4582
     if (Gstar != -1) savefile += "_Geq_" + geq.str() + "_R_" + rini.str() + ".csv";
     else if (Vstar != -1) savefile += "_Veq_" + veq.str() + "_R_" + rini.str() + ".csv";
     else savefile += "_R_" + rini.str() + ".csv";
+    recursive_dir_create(savefile.substr(0, savefile.find_last_of('/')));
     std::ofstream out(savefile);
     out << prelimheader << "\n";                                                     // R/:4601
     for (size_t i = 0; i < vec.size(); i++) {

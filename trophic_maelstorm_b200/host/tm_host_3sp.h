@@ -32,6 +32,10 @@ extern std::function<void(double *frame, int g, int replicate, double a, double 
 extern std::function<void(int replicate, int index, double t, const double *frame)> on_measure;
 // Output locations of the side outputs; empty (default) = "<data_root>/Data/Rietkerk/{Frames,Prelims}/Stochastic/3Sp/<prefix>_"
 extern std::string frame_folder, prelim_folder;
+// set_Prefix (R/:113-135, F/:143-165) of the -DSPB=3 binaries: tm_b200::prefix and the three output locations
+// "<data_root>/Data/Rietkerk/{Frames,Prelims}/Stochastic/3Sp[_mG_<mG>[_mP_<mP>]]/<prefix>_", ".../Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_"
+extern std::string stat_prefix;   // empty (default): the header's location of the final table, ".../Stochastic/3Sp/1stCC_Rietkerk_<prefix>_P_c_G_"
+void set_Prefix(const std::string &user_prefix, double mG = 0.0, double mP = 0.0);
 extern const std::string frame_header, gammaheader, movmheader;   // rietkerk_bjork_constants_3Sp.h:6-17
 
 void var_mean_incremental_surv_runs(D2Vec_Double &t_avg_var_rep_N, const D2Vec_Double &X_curr, int size, int j);   // R/:1293
