@@ -135,3 +135,43 @@ def test_fpe_spb2_unity_driver_binary(tmp_path):
     np.testing.assert_allclose(fr[:, 2], P, rtol=1e-5)
     np.testing.assert_allclose(fr[:, 3], G, rtol=1e-5, atol=1e-300)
     assert np.all(fr[:, 4] == 1.0) and np.all(fr[:, 5] == 1.0)
+
+
+def test_spb3_argv_driver_binary(tmp_path):
+    """drivers/order_3stoc_test_rietkerk: the twelve-argument form of Rietkerk_FD/order_3stoc_test_rietkerk.cpp:182-196 end to end -- dx = 1 km,
+    folders under 3Sp_mG_20_mP_100 tagged _Geq_<G*>, the MFT initial frame from the driver's tables, an 18-column final table; an
+    unsupported attack-rate scaling and a CFL violation are refused with the reference's exit codes."""
+    import subprocess
+    exe = os.path.join(ROOT, "drivers", "order_3stoc_test_rietkerk")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    env = dict(os.environ, TM_DATA_ROOT=str(tmp_path), TM_SEED="7")
+    args = ["0.1", "1.5", "16", "2", "0.05", "0.06", "2", "10000", "1", "1", "1", "TEST"]
+    out = subprocess.run([exe] + args, text=True, capture_output=True, env=env, timeout=1500)
+    assert out.returncode == 0, out.stderr
+    t = {k: v.decode() for k, v in _tree(tmp_path).items()}
+    ajm = 3.6 * 10.0 ** -6.08 * 100.0 ** -0.37
+    mm = 0.061609 * 100.0 ** -0.25 / 8760.0
+    gstar = mm / ((0.85 - mm) * ajm)
+    tag = "TEST_0.05-0.06_dP_10000_Geq_%.5g" % gstar
+    table = "Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_TEST_P_c_G_16_T_1.5_dt_0.1_D1_0.0298_a1_0.05_a2_0.06_dx_1_Geq_%.5g_R_2.csv" % gstar
+    assert table in t, sorted(t)[:6]
+    lines = t[table].splitlines()
+    assert "<<Pr(x; t)>_x>_r" in lines[0]
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in lines[2:]])
+    assert rows.shape[1] == 18 and set(np.round(rows[:, 0], 6)) == {0.05, 0.06} and np.isfinite(rows).all()
+    f0 = "Data/Rietkerk/Frames/Stochastic/3Sp_mG_20_mP_100/%s/FRAME_P_c_DP_G_16_T_0_dt_0.1_a_0.05_D1_0.0298_jID_0_dx_1_R_0.csv" % tag
+    assert f0 in t, [k for k in sorted(t) if "FRAME" in k][:4]
+    fr = np.array([[float(x) for x in ln.split(",")] for ln in t[f0].splitlines()[1:]])
+    six = lambda x: float("%f" % x)
+    V = six(960000.0) * 0.05 + six(-40000.0)
+    assert set(np.unique(fr[:, 2])) <= {V, 5 * V}                                       # speckles: max(dP, 5 V*) = 40000
+    np.testing.assert_allclose(fr[:, 3], six(gstar), rtol=1e-5)
+    np.testing.assert_allclose(fr[:, 4], six(4.49723728e+05) * (1 - np.exp(six(-1.73381257) * (0.05 - six(1 / 24.0)))), rtol=1e-5)
+    np.testing.assert_allclose(fr[:, 5], six(-3.90344309) * 0.05 + six(5.18), rtol=1e-5)
+    np.testing.assert_allclose(fr[:, 6], six(120.0) * 0.05, rtol=1e-5)
+    g0 = f0.replace("FRAME_P_c_DP_G_16", "GAMMA_G_16")
+    assert g0 in t and t[g0].splitlines()[0] == "a_c,  x,  GAM[P(x; t)], GAM[G(x; t)], GAM[Pr(x; t)] "
+    bad = subprocess.run([exe] + args[:9] + ["7", "1", "TEST"], text=True, capture_output=True, env=env)
+    assert bad.returncode == 1 and "Scaling factor for aij not supported" in bad.stderr
+    cfl = subprocess.run([exe, "2.0"] + args[1:], text=True, capture_output=True, env=env)
+    assert cfl.returncode == 2 and "CFL condition violated" in cfl.stdout
