@@ -175,3 +175,36 @@ def test_spb3_argv_driver_binary(tmp_path):
     assert bad.returncode == 1 and "Scaling factor for aij not supported" in bad.stderr
     cfl = subprocess.run([exe, "2.0"] + args[1:], text=True, capture_output=True, env=env)
     assert cfl.returncode == 2 and "CFL condition violated" in cfl.stdout
+
+
+def test_fpe_spb3_unity_driver_binary(tmp_path):
+    """drivers/order_3stoc_unity_rietkerk: Rietkerk_FPE/order_3stoc_unity_rietkerk.cpp end to end -- dt = min(0.12, 0.77), dx = 0.1, the
+    Gaussian initial frame with amp = {500, 10 G*, 40, 4, 10}, 18-column table under Stochastic/1stOrderCC_Rietkerk_<prefix>_..."""
+    import subprocess
+    exe = os.path.join(ROOT, "drivers", "order_3stoc_unity_rietkerk")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    env = dict(os.environ, TM_DATA_ROOT=str(tmp_path), TM_SEED="7")
+    L = 16
+    out = subprocess.run([exe, "0.5", "1.5", str(L), "2", "0.05", "0.06", "2", "10000", "1", "1", "1", "TEST"], text=True, capture_output=True,
+                         env=env, timeout=1500)
+    assert out.returncode == 0, out.stderr
+    t = {k: v.decode() for k, v in _tree(tmp_path).items()}
+    ajm = 3.6 * 10.0 ** -6.08 * 100.0 ** -0.37
+    mm = 0.061609 * 100.0 ** -0.25 / 8760.0
+    gstar = mm / ((0.85 - mm) * ajm)
+    tag = "TEST_0.05-0.06_dP_10000_Geq_%.5g" % gstar
+    table = "Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_TEST_P_c_G_16_T_1.5_dt_0.12_D1_0.0298_a1_0.05_a2_0.06_dx_0.1_Geq_%.5g_R_2.csv" % gstar
+    assert table in t, sorted(t)[:6]
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in t[table].splitlines()[2:]])
+    assert rows.shape[1] == 18 and set(np.round(rows[:, 0], 6)) == {0.05, 0.06} and np.isfinite(rows).all()
+    f0 = "Data/Rietkerk/Frames/Stochastic/3Sp_mG_20_mP_100/%s/FRAME_P_c_DP_G_16_T_0_dt_0.12_a_0.05_D1_0.0298_jID_0_dx_0.1_R_0.csv" % tag
+    assert f0 in t, [k for k in sorted(t) if "FRAME" in k][:4]
+    fr = np.array([[float(x) for x in ln.split(",")] for ln in t[f0].splitlines()[1:]])
+    i, j = np.divmod(np.arange(L * L), L)
+    bump = lambda amp, cx, cy, sd: amp * np.exp(-((i - cx) ** 2 + (j - cy) ** 2) / (2 * sd * sd))
+    np.testing.assert_allclose(fr[:, 2], bump(500.0, L // 8, L // 8, L / 8.0), rtol=1e-5)
+    np.testing.assert_allclose(fr[:, 3], bump(10 * gstar, 7 * L // 8, L // 8, L / 16.0), rtol=1e-5, atol=1e-300)
+    np.testing.assert_allclose(fr[:, 4], bump(40.0, 7 * L // 8, 7 * L // 8, L / 16.0), rtol=1e-5, atol=1e-300)
+    assert np.all(fr[:, 5] == 4.0) and np.all(fr[:, 6] == 10.0)
+    bad = subprocess.run([exe, "0.5", "1.5", str(L), "2", "0.05", "0.06", "2", "10000", "1", "10", "50", "TEST"], text=True, capture_output=True, env=env)
+    assert bad.returncode == 1 and "not supported" in bad.stderr
