@@ -88,6 +88,11 @@ int tm_cons_step2_upload(tm_cons_ctx *, const double *fields, const double *gamm
 /* RK4 part of the step: 0 (default) = one launch for the four stages and the clamp (tile-fused, six launches per step);
  * 1 = one launch per stage (nine per step).  Bit-identical results; the second form is kept as the cross-check. */
 int tm_cons_step2_set_rk4_stages(tm_cons_ctx *, int on);
+/* Means of the step: 0 (default) = the device reduction tree (reproducible, a few ulp from the reference's left-to-right sums, so
+ * that the step equals the oracle bit for bit GIVEN those means); 1 = strict: mean_of_vector's own left-to-right sums (R/:1211-1219) by one
+ * thread per field -- the step then equals the reference-pinned oracle bit for bit free-running, at the cost of a dependent chain of L*L
+ * additions per step (parity runs; ~70 ms at L = 4096). */
+int tm_cons_step2_set_strict_means(tm_cons_ctx *, int on);
 /* Rietkerk_FPE flavour of the resident step: the body of the time loop of rietkerk_DorFPE_2D_MultiSp compiled with -DSPB=2,
  * Rietkerk_FPE/rietkerk_bjork_FKE.cpp:4094-4462 -- perception field with calc_gamma_vel_2Sp_NonRefugia's rules (:2534-2607: a
  * vanished consumer gets gamma = 1) -> vegetation Dornic (:4154-4211) -> four-field RK4 over f_DorFKE_2Sp (:2449-2531: the grazer's

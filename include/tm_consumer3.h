@@ -56,6 +56,8 @@ struct tm_fke_terms;
 int tm_cons3_set_fpe(tm_cons3_ctx *, const struct tm_fke_terms *t, const double *const *gauss_D, const double *const *gauss_V, double M1, double M2);
 /* fields [5][L*L]; gamma [2][L*L] (grazer, predator) or NULL (zeros; the three-species perception function assigns, so the entry
  * values only matter for a species it skips) */
+/* 1: the three spatial means by left-to-right sums as mean_of_vector computes them (R/:1211-1219; see tm_cons_step2_set_strict_means) */
+int tm_cons3_set_strict_means(tm_cons3_ctx *, int on);
 int tm_cons3_upload(tm_cons3_ctx *, const double *fields, const double *gamma);
 /* nsteps steps with Philox streams keyed (seed, trial, step0 + s, cell); the grazer's and the predator's streams use the seed xor
  * 0x9E3779B97F4A7C15 and 0xD1B54A32D192ED03.  Asynchronous. */

@@ -242,6 +242,10 @@ int emu_grazer_dornic(int L, const double *par, unsigned long long seed, unsigne
 
 // nsteps SPB = 2 runner steps through the product's launch chain (cons_step2_enqueue), launch shapes as tm_consumer.cu.
 // par2 = {dt, dx, d, D0, sigma0, clamp_eps, clamp_lo, gD, gv, gM, gsigma, gD0floor, fr}; cpar as emu_cons_rk4's par.
+// strict means of the SPB = 2 / 3 chains (Step2Buffers / Step3Buffers::strict_means) for the emu_cons_step* calls that follow
+static int g_strict_means = 0;
+void emu_set_strict_means(int on) { g_strict_means = on ? 1 : 0; }
+
 // u_veg/u_graz == nullptr: Philox (seed, trial, step0 + s); else one replay step.  dyn_out[4] = {<P>, <G>, #{P>0}, eff} of the
 // state the last step started from.
 int emu_cons_step2(int L, const double *par2, const double *cpar, const int *central, int n_central, unsigned long long seed,
@@ -257,7 +261,7 @@ int emu_cons_step2(int L, const double *par2, const double *cpar, const int *cen
     Step2Dyn dyn{};
     Step2Buffers b{};
     b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
-    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow; b.strict_means = g_strict_means;
     b.replay_veg = u_veg; b.replay_graz = u_graz; b.stride = stride; b.rk4_stages = rk4_stages;
     *overflow = 0;
     auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
@@ -287,7 +291,7 @@ int emu_cons_step2_fpe(int L, const double *par2, const double *cpar, const int 
     Step2Dyn dyn{};
     Step2Buffers b{};
     b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
-    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow; b.strict_means = g_strict_means;
     b.replay_veg = u_veg; b.replay_graz = u_veg; b.stride = stride; b.rk4_stages = rk4_stages;   // the grazer draws nothing in this flavour
     b.fke_gD = gD; b.fke_gV = gV;
     *overflow = 0;
@@ -316,7 +320,7 @@ int emu_cons_step3(int L, const double *par3, const double *cpar, const int *cen
     Step3Dyn dyn{};
     Step3Buffers b{};
     b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
-    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow; b.strict_means = g_strict_means;
     b.replay[0] = u_veg; b.replay[1] = u_graz; b.replay[2] = u_pred; b.stride = stride;
     *overflow = 0;
     auto launch = [](auto kernel, const auto &args, unsigned grid, unsigned block, size_t smem) { emu_launch(kernel, args, grid, block, smem); };
@@ -351,7 +355,7 @@ int emu_cons_step3_fpe(int L, const double *par3, const double *cpar, const int 
     Step3Dyn dyn{};
     Step3Buffers b{};
     b.state = fields; b.star = star.data(); b.ya = ya.data(); b.yb = yb.data(); b.acc = acc.data(); b.gamma = gamma; b.veff = veff;
-    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow;
+    b.part = part.data(); b.dyn = &dyn; b.central = central; b.overflow = overflow; b.strict_means = g_strict_means;
     b.replay[0] = u_veg; b.replay[1] = u_dir; b.replay[2] = u_dir; b.stride = stride;
     b.fke_gD[0] = gD1; b.fke_gV[0] = gV1; b.fke_gD[1] = gD2; b.fke_gV[1] = gV2;
     *overflow = 0;

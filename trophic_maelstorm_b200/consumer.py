@@ -18,7 +18,7 @@ class GrazParams(C.Structure):
 
 CONS_ABI_SYMBOLS = ["tm_cons_create", "tm_cons_destroy", "tm_cons_last_error", "tm_cons_rk4_host", "tm_cons_gamma_host",
                     "tm_cons_grazer_dornic_host", "tm_cons_last_ms", "tm_cons_step2_setup", "tm_cons_step2_upload", "tm_cons_step2_run",
-                    "tm_cons_step2_replay", "tm_cons_step2_download", "tm_cons_step2_set_rk4_stages", "tm_cons_step2_set_fpe"]
+                    "tm_cons_step2_replay", "tm_cons_step2_download", "tm_cons_step2_set_rk4_stages", "tm_cons_step2_set_fpe", "tm_cons_step2_set_strict_means"]
 
 _bound = False
 
@@ -42,6 +42,7 @@ def _lib():
             "tm_cons_step2_run": (i, [vp, C.c_uint64, C.c_uint32, C.c_uint32, i]),
             "tm_cons_step2_replay": (i, [vp, dp, dp, C.c_uint32]),
             "tm_cons_step2_set_rk4_stages": (i, [vp, i]),
+            "tm_cons_step2_set_strict_means": (i, [vp, i]),
             "tm_cons_step2_set_fpe": (i, [vp, vp, dp, dp, C.c_double]),
             "tm_cons_step2_download": (i, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint64)]),
         }
@@ -126,6 +127,9 @@ class ConsumerOps:
     def step2_set_rk4_stages(self, on):
         self._ck(self._l.tm_cons_step2_set_rk4_stages(self._ctx, 1 if on else 0))
 
+    def step2_set_strict_means(self, on):
+        self._ck(self._l.tm_cons_step2_set_strict_means(self._ctx, 1 if on else 0))
+
     def step2_set_fpe(self, terms, gauss_D, gauss_V, M1):
         """Rietkerk_FPE flavour of the step (tm_cons_step2_set_fpe); terms: fke.FkeTerms, or None for the Rietkerk_FD flavour."""
         if terms is None:
@@ -165,7 +169,7 @@ class Cons3Params(C.Structure):
 
 
 CONS3_ABI_SYMBOLS = ["tm_cons3_create", "tm_cons3_destroy", "tm_cons3_last_error", "tm_cons3_setup", "tm_cons3_set_fpe", "tm_cons3_upload", "tm_cons3_run",
-                     "tm_cons3_replay", "tm_cons3_download", "tm_cons3_last_ms"]
+                     "tm_cons3_replay", "tm_cons3_download", "tm_cons3_last_ms", "tm_cons3_set_strict_means"]
 _bound3 = False
 
 
@@ -182,6 +186,7 @@ def _lib3():
                                    C.POINTER(C.c_int32), i, C.c_double, C.c_double]),
             "tm_cons3_set_fpe": (i, [vp, vp, C.POINTER(dp), C.POINTER(dp), C.c_double, C.c_double]),
             "tm_cons3_upload": (i, [vp, dp, dp]),
+            "tm_cons3_set_strict_means": (i, [vp, i]),
             "tm_cons3_run": (i, [vp, C.c_uint64, C.c_uint32, C.c_uint32, i]),
             "tm_cons3_replay": (i, [vp, dp, dp, dp, C.c_uint32]),
             "tm_cons3_download": (i, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint64)]),
@@ -236,6 +241,9 @@ class ConsumerOps3:
         gV = [np.ascontiguousarray(x, dtype=np.float64) for x in gauss_V]
         pD, pV = (dp * 2)(_dptr(gD[0]), _dptr(gD[1])), (dp * 2)(_dptr(gV[0]), _dptr(gV[1]))
         self._ck(self._l.tm_cons3_set_fpe(self._ctx, C.cast(terms, C.c_void_p), pD, pV, float(M1), float(M2)))
+
+    def set_strict_means(self, on):
+        self._ck(self._l.tm_cons3_set_strict_means(self._ctx, 1 if on else 0))
 
     def upload(self, fields, gamma=None):
         f = np.ascontiguousarray(fields, dtype=np.float64)

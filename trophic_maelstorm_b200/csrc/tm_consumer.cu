@@ -24,6 +24,7 @@ struct tm_cons_ctx {
     // the resident SPB = 2 stepper (tm_cons_step2_*)
     bool step2_ready = false;
     int rk4_stages = 0;            // tm_cons_step2_set_rk4_stages
+    int strict_means = 0;          // tm_cons_step2_set_strict_means
     Step2Consts k2{};
     double *d_star = nullptr, *d_veff = nullptr, *d_part = nullptr;
     Step2Dyn *d_dyn = nullptr;
@@ -53,7 +54,7 @@ static Step2Buffers step2_buffers(tm_cons_ctx *c)
     Step2Buffers b{};
     b.state = c->d_state; b.star = c->d_star; b.ya = c->d_ya; b.yb = c->d_yb; b.acc = c->d_acc; b.gamma = c->d_gamma; b.veff = c->d_veff;
     b.part = c->d_part; b.dyn = c->d_dyn; b.central = c->d_central; b.overflow = c->d_ovf;
-    b.rk4_stages = c->rk4_stages;
+    b.rk4_stages = c->rk4_stages; b.strict_means = c->strict_means;
     b.fke_gD = c->d_fke_gD; b.fke_gV = c->d_fke_gV;
     return b;
 }
@@ -282,6 +283,13 @@ int tm_cons_step2_set_rk4_stages(tm_cons_ctx *c, int on)
 {
     if (!c) return TM_E_ARG;
     c->rk4_stages = on ? 1 : 0;
+    return TM_OK;
+}
+
+int tm_cons_step2_set_strict_means(tm_cons_ctx *c, int on)
+{
+    if (!c) return TM_E_ARG;
+    c->strict_means = on ? 1 : 0;
     return TM_OK;
 }
 

@@ -92,6 +92,36 @@ TMC_G void cons_reduce_kernel(const ReduceArgs A)
     if (tid == 0) { A.part[3 * blockIdx.x] = sh[0]; A.part[3 * blockIdx.x + 1] = sh[T]; A.part[3 * blockIdx.x + 2] = sh[2 * T]; }
 }
 
+// Strict means (tm_cons_step2_set_strict_means / tm_cons3_set_strict_means): mean_of_vector's own left-to-right sum (R/:1211-1219) --
+// ONE thread per field walks it in index order, a third/fourth lane counts the vegetation cover -- written as block 0's partial with
+// every other block's partial zeroed, so that the finalize kernel's additions (x + 0.0) hand the sequential sums on unchanged and the
+// whole step equals the reference-pinned oracle bit for bit WITHOUT being given its means.  A dependent DADD chain of L*L terms: for
+// parity runs, not for production (70 ms at L = 4096 against 3 ms for the step).
+struct SeqSumArgs {
+    long long n;
+    const double *f[3];          // the biotic fields DRho[0 .. nf-1]
+    int nf;                      // 2 (SPB = 2) or 3 (SPB = 3)
+    double *part;                // [nblocks][nf + 1]
+    int nblocks;
+};
+
+TMC_G void cons_seqsum_kernel(const SeqSumArgs A)
+{
+    const int lane = threadIdx.x, w = A.nf + 1;
+    for (long long k = w + lane; k < (long long)A.nblocks * w; k += blockDim.x) A.part[k] = 0.0;
+    if (lane < A.nf) {
+        const double *x = A.f[lane];
+        double s = 0.0;
+        for (long long i = 0; i < A.n; ++i) s += x[i];
+        A.part[lane] = s;
+    } else if (lane == A.nf) {
+        const double *x = A.f[0];
+        double oc = 0.0;
+        for (long long i = 0; i < A.n; ++i) if (x[i] > 0) oc += 1;
+        A.part[lane] = oc;
+    }
+}
+
 struct FinalizeArgs {
     int L, nblocks, n_central;   // n_central: length of the full disc list of computeNeighboringSitesCentral(int(r_max))
     double fr;                   // pR[1] / (dx r_max_effective), R/:3409
@@ -428,6 +458,7 @@ struct Step2Buffers {
     int rk4_stages;              // 1: the four-launch RK4 (kept as the cross-check); 0: cons_rk4_fused_kernel, which writes the
                                  // new state into `ya` -- cons_step2_enqueue then swaps `state` and `ya`
     const double *fke_gD, *fke_gV;   // FPE flavour: the grazer's two Gaussian stencils (device)
+    int strict_means;            // 1: <P>, <G> by cons_seqsum_kernel (the reference's left-to-right sums) instead of the reduction tree
 };
 
 // FPE flavour, last launch of a step: the moved grazer field replaces field 1, then `v < eps && v >= lo -> 0` on all four (F/:4458)
@@ -503,8 +534,13 @@ inline void cons_step2_enqueue(Launch &&launch, const Step2Consts &k, Step2Buffe
     V.veg = k.veg; V.dyn = nullptr;
     if (replay) launch(grazer_dornic_kernel<true, true>, V, grid, kConsThreads, 0);
     else        launch(grazer_dornic_kernel<false, true>, V, grid, kConsThreads, 0);
-    ReduceArgs R{n, b.state, b.state + n, b.part};
-    launch(cons_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 3 * kConsReduceThreads);
+    if (b.strict_means) {
+        SeqSumArgs S{n, {b.state, b.state + n, nullptr}, 2, b.part, kConsReduceBlocks};
+        launch(cons_seqsum_kernel, S, 1, 32, 0);
+    } else {
+        ReduceArgs R{n, b.state, b.state + n, b.part};
+        launch(cons_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 3 * kConsReduceThreads);
+    }
     FinalizeArgs F{L, kConsReduceBlocks, k.n_central, k.fr, b.part, b.dyn, k.fpe};
     launch(cons_finalize_kernel, F, 1, 32, sizeof(double) * 96);
     GammaArgs G{};

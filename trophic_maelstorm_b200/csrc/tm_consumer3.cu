@@ -24,6 +24,7 @@ struct tm_cons3_ctx {
     double *d_replay = nullptr; size_t replay_cap = 0;
     double *d_fke_gD[2] = {nullptr, nullptr}, *d_fke_gV[2] = {nullptr, nullptr};   // FPE flavour: the consumers' movement stencils
     bool ready = false;
+    int strict_means = 0;          // tm_cons3_set_strict_means
     Step3Consts k{};
     int n_launches = 0;
     std::string err;
@@ -53,6 +54,7 @@ Step3Buffers buffers(tm_cons3_ctx *c)
     b.state = c->d_state; b.star = c->d_star; b.ya = c->d_ya; b.yb = c->d_yb; b.acc = c->d_acc; b.gamma = c->d_gamma; b.veff = c->d_veff;
     b.part = c->d_part; b.dyn = c->d_dyn; b.central = c->d_central; b.overflow = c->d_ovf;
     for (int s = 0; s < 2; s++) { b.fke_gD[s] = c->d_fke_gD[s]; b.fke_gV[s] = c->d_fke_gV[s]; }
+    b.strict_means = c->strict_means;
     return b;
 }
 } // namespace
@@ -160,6 +162,13 @@ int tm_cons3_set_fpe(tm_cons3_ctx *c, const tm_fke_terms *t, const double *const
         f.pref = t[s].mu_vel_prefactor; f.eps = t[s].epsilon;
     }
     c->k.fpe = 1; c->k.c.fpe = 1; c->k.c.M1 = M1; c->k.c.M2 = M2;
+    return TM_OK;
+}
+
+int tm_cons3_set_strict_means(tm_cons3_ctx *c, int on)
+{
+    if (!c) return TM_E_ARG;
+    c->strict_means = on ? 1 : 0;
     return TM_OK;
 }
 

@@ -330,6 +330,7 @@ struct Step3Buffers {
     const double *replay[3];     // all null: Philox; else [n][stride] for vegetation, grazer, predator (FPE flavour: [1] = directions)
     unsigned int stride;
     const double *fke_gD[2], *fke_gV[2];   // FPE flavour: the consumers' Gaussian stencils (device)
+    int strict_means;            // 1: the three means by cons_seqsum_kernel (left-to-right sums, tm_consumer.cuh) instead of the tree
 };
 
 constexpr unsigned long long kPredatorSeedSalt = 0xD1B54A32D192ED03ull;   // the predator's Philox streams (the grazer's: kGrazerSeedSalt)
@@ -372,8 +373,13 @@ inline void cons_step3_enqueue(Launch &&launch, const Step3Consts &k, Step3Buffe
     V.veg = k.veg; V.dyn = nullptr; V.skip_flag = nullptr;
     if (replay) launch(grazer_dornic_kernel<true, true>, V, grid, kConsThreads, 0);
     else        launch(grazer_dornic_kernel<false, true>, V, grid, kConsThreads, 0);
-    Reduce3Args R{n, b.state, b.state + n, b.state + 2 * n, b.part};
-    launch(cons3_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 4 * kConsReduceThreads);
+    if (b.strict_means) {
+        SeqSumArgs S{n, {b.state, b.state + n, b.state + 2 * n}, 3, b.part, kConsReduceBlocks};
+        launch(cons_seqsum_kernel, S, 1, 32, 0);
+    } else {
+        Reduce3Args R{n, b.state, b.state + n, b.state + 2 * n, b.part};
+        launch(cons3_reduce_kernel, R, kConsReduceBlocks, kConsReduceThreads, sizeof(double) * 4 * kConsReduceThreads);
+    }
     Finalize3Args F{L, kConsReduceBlocks, k.n_central, k.fr1, k.fr2, b.part, b.dyn, k.fpe};
     launch(cons3_finalize_kernel, F, 1, 32, sizeof(double) * 128);
     if (k.fpe) {                                                        // the new advection vectors of this step, F/:3421-3424
