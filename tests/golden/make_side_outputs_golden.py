@@ -61,6 +61,41 @@ def main_fpe():
         json.dump(out, f)
 
 
+def main_3sp():
+    """SPB = 3: side_outputs_3sp.json.gz from oracle/_ref/libtm_ref_riet3_files.so"""
+    import make_runner3_golden as G3
+    tmp = tempfile.mkdtemp(prefix="tmside3_")
+    os.chdir(tmp)
+    root = os.path.join(tmp, "Rietkerk") + "/"
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libtm_ref_riet3_files.so"))
+    ref.ref3f_run.restype = C.c_uint64
+    L, r, seed, n_u = 10, 2, 95, 600000
+    par = G3.driver_par()
+    dt = par[29]
+    init = np.stack([G3.frame(L, seed + j) for j in range(r)])
+    u = uniforms(seed, n_u)
+    t_meas = np.array([0.0] + [dt * k for k in (1, 2, 3, 5, 7, 9, 12)])
+    frame_t = np.array([dt * k for k in (2, 5, 9, 12)] + [1e300])
+    a_tag = "%g-%g_dP_%g_Geq_%.5g" % (par[0], par[0], 10000.0, 4.8)
+    os.makedirs(os.path.join(root, "Frames/Stochastic/3Sp", "SIDE3_" + a_tag))
+    os.makedirs(os.path.join(root, "Prelims/Stochastic/3Sp", "SIDE3_" + a_tag, "TimeSeries"))
+    os.makedirs(os.path.join(root, "Stochastic"))
+    ov = C.c_uint64()
+    cons = ref.ref3f_run(ptr(par), C.c_int(L), C.c_int(r), ptr(init), C.c_int(r), ptr(t_meas), C.c_int(len(t_meas)), ptr(frame_t),
+                         C.c_int(len(frame_t)), ptr(u), C.c_uint64(n_u), root.encode(), b"SIDE3", C.c_double(4.8), C.byref(ov))
+    assert ov.value == 0
+    files = {}
+    for dirpath, _, names in os.walk(root):
+        for nm in names:
+            p = os.path.join(dirpath, nm)
+            files[os.path.relpath(p, root)] = open(p).read()
+    print("3Sp consumed", cons, "files", len(files))
+    out = {"files": files, "par": par.tolist(), "L": L, "r": r, "t_meas": t_meas.tolist(), "frame_t": frame_t[:-1].tolist(), "seed": seed,
+           "n_u": n_u, "init": init.reshape(r, -1).tolist(), "consumed": int(cons), "Gstar": 4.8, "prefix": "SIDE3"}
+    with gzip.open(os.path.join(HERE, "side_outputs_3sp.json.gz"), "wt") as f:
+        json.dump(out, f)
+
+
 def main():
     tmp = tempfile.mkdtemp(prefix="tmside_")
     os.chdir(tmp)
@@ -99,6 +134,10 @@ def main():
 
 
 if __name__ == "__main__":
+    if "--3sp-only" in sys.argv:
+        main_3sp()
+        sys.exit(0)
     if "--fpe-only" not in sys.argv:
         main()
+        main_3sp()
     main_fpe()

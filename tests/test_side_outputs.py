@@ -122,6 +122,47 @@ class OracleStepperFpe2(OracleStepper2):
                                     C.c_double(self.fr), C.byref(self.rng), O.ptr(self.f), O.ptr(self.gamma), O.ptr(self.veff), None)
 
 
+class OracleStepper3(OracleStepper2):
+    """SPB = 3: tmo_step_3sp (pinned in test_consumer3_oracle.py) behind the same three calls; gamma [2][n], veff [2][n][2]"""
+
+    def __init__(self, L, par, u, n_loop):
+        self.L, self.n_loop = L, n_loop
+        self.pv, self.pg1, self.pg2, self.pc, R, self.fr1, self.fr2 = O.runner3_params(L, par)
+        G3 = np.load(os.path.join(HERE, "golden", "runner_3sp.npz"))
+        self.central = np.ascontiguousarray(G3["central_R%d" % R], dtype=np.int32)
+        self.u = u
+        self.rng = O.make_rng(O.SRC_SEQ, u=u, pos=0)
+        self.f = np.zeros((5, L * L))
+        self.gamma = np.zeros((2, L * L))
+        self.veff = np.zeros((2, L * L, 2))
+        self.replicate, self.steps_done, self.calls = -1, 0, []
+
+    def _one_step(self, lib):
+        return lib.tmo_step_3sp(C.byref(self.pv), C.byref(self.pg1), C.byref(self.pg2), C.byref(self.pc),
+                                self.central.ctypes.data_as(C.POINTER(C.c_int32)), len(self.central), C.c_double(self.fr1),
+                                C.c_double(self.fr2), C.byref(self.rng), O.ptr(self.f), O.ptr(self.gamma), O.ptr(self.veff), 1, None)
+
+    def upload(self, frame):
+        self.finish_replicate()
+        self.replicate += 1
+        if self.replicate == 0:
+            self.rng.pos += 1
+        n = 5 * self.L * self.L
+        self.f[:] = np.ctypeslib.as_array(frame, shape=(n,)).reshape(5, -1)
+        self.gamma[:] = 0.0
+        self.veff[:] = 0.0
+        self.steps_done = 0
+        self.rng.norm_saved_available = 0
+
+    def download(self, frame, gamma, veff):
+        n = self.L * self.L
+        np.ctypeslib.as_array(frame, shape=(5 * n,))[:] = self.f.reshape(-1)
+        if gamma:
+            np.ctypeslib.as_array(gamma, shape=(2 * n,))[:] = self.gamma.reshape(-1)
+        if veff:
+            np.ctypeslib.as_array(veff, shape=(4 * n,))[:] = self.veff.reshape(-1)
+
+
 UP = C.CFUNCTYPE(None, dp)
 RUN = C.CFUNCTYPE(None, C.c_uint32, C.c_uint32, C.c_int)
 DOWN = C.CFUNCTYPE(None, dp, dp, dp)
@@ -212,6 +253,30 @@ def test_fpe_spb2_output_tree_equals_the_reference(host, tmp_path):
             assert got[k] == want[k], k
     assert not any("_T_0.6_" in k and "PRELIM" in k for k in got)        # index 4 = int(0.6 * 8): a checkpoint of Rietkerk_FD only
     assert np.isfinite(rows).all()
+
+
+def test_spb3_output_tree_equals_the_reference(host, tmp_path):
+    """the same for the vegetation + grazer + predator runner (R/:3397 with -DSPB=3): five-field frames, both perception fields, the
+    3Sp headers (rietkerk_bjork_constants_3Sp.h:6-17), 18-column tables, twelve movement columns"""
+    with gzip.open(os.path.join(HERE, "golden", "side_outputs_3sp.json.gz"), "rt") as f:
+        g = json.load(f)
+    L, r = g["L"], g["r"]
+    par = np.array(g["par"])
+    t_meas = np.array(g["t_meas"])
+    frame_t = np.array(g["frame_t"] + [1e300])
+    init = np.array(g["init"]).reshape(r, 5, L * L)
+    u = np.random.RandomState(g["seed"]).random_sample(g["n_u"])
+    st = OracleStepper3(L, par, u, _loop_iterations(t_meas[-1], par[29]))
+    root = str(tmp_path) + "/"
+    rows = _side_run(host, 3, L, par, r, init, t_meas, frame_t, root, g["prefix"], g["Gstar"], st, 18)
+    st.finish_replicate()
+    assert st.rng.overflow == 0 and st.rng.pos == g["consumed"]
+    want = {_normalise(k): v for k, v in g["files"].items()}
+    got = _tree(root)
+    assert sorted(got) == sorted(want)
+    for k in sorted(want):
+        assert got[k] == want[k], k
+    assert any("GAM[Pr(x; t)]" in v for k, v in got.items() if "GAMMA_" in k) and np.isfinite(rows).all()
 
 
 def test_side_outputs_off(host, tmp_path):
