@@ -79,3 +79,28 @@ def test_finite_scaling_stationary_csv(host, tmp_path, monkeypatch):
         np.testing.assert_allclose(blk, want[:, :7], rtol=1e-15, atol=0)
     # grid sizes the reference has no window for are refused, not guessed
     assert host.tmh_dp_finite_scaling(1, 2, 16, 64, 50.0, a_c, b, D, sigma, dt, dx, r) == -2
+
+
+@pytest.mark.parametrize("exe,stdin,pattern,ncol", [
+    ("delta_frame_test", "0.1\n3\n24\n2\n1.0524\n1.0554\n2\n", "DEBUG_P_c_Delta_DP_G_24_T_3_dt_0.1_a1_1.052_a2_1.055_Sig_1.41_R_2.csv", 8),
+    ("spreading_exp_test", "0.1\n3\n25\n3\n2\n1.0548\n", "SPREADING_P_c_ThDel_DP_G_25_T_3_*", None),
+    ("finite_scaling_delta", "0.1\n50\n33\n64\n2\n2\n1.0548\n", "DEBUG_P_c_Finite_Scaling_Stationary_T_50_dt_0.1_a_1.0548_L1_33_L2_64_Sig_1.41_R_2.csv", 7),
+])
+def test_dp_driver_binaries(tmp_path, monkeypatch, exe, stdin, pattern, ncol):
+    """drivers/{delta_frame_test, spreading_exp_test, finite_scaling_delta}: the stdin protocols and constants of the reference's DP driver
+    mains (Percolation_FD/<same name>.cpp) over the host layer; each writes its one CSV in the reference's place."""
+    import glob
+    import subprocess
+    path = os.path.join(ROOT, "drivers", exe)
+    assert os.path.exists(path), "run __graft_entry__.build()"
+    env = dict(os.environ, TM_DATA_ROOT=str(tmp_path), TM_SEED="7", TM_FSS_WINDOW_SCALE="0.002")
+    out = subprocess.run([path], input=stdin, text=True, capture_output=True, env=env, timeout=1500)
+    assert out.returncode == 0, out.stderr
+    files = glob.glob(str(tmp_path / "Data" / "SPDP" / pattern))
+    assert len(files) == 1, os.listdir(tmp_path / "Data" / "SPDP")
+    rows = np.loadtxt(files[0], delimiter=",", skiprows=1)
+    assert rows.ndim == 2 and len(rows) > 4 and np.isfinite(rows).all()
+    if ncol:
+        assert rows.shape[1] == ncol
+    bad = subprocess.run([path], input="0.1\nnot-a-number\n", text=True, capture_output=True, env=env)
+    assert bad.returncode == 2
