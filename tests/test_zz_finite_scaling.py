@@ -104,3 +104,38 @@ def test_dp_driver_binaries(tmp_path, monkeypatch, exe, stdin, pattern, ncol):
         assert rows.shape[1] == ncol
     bad = subprocess.run([path], input="0.1\nnot-a-number\n", text=True, capture_output=True, env=env)
     assert bad.returncode == 2
+
+
+def test_bifurc_prob_driver_and_terminal_runner(host, tmp_path):
+    """drivers/bifurc_prob -> first_order_terminal_diff (P/:2548) -> terminal_percolationDornic_2D (P/:2158): one row per initial density
+    and replicate, {a, c, L, j, t, <rho(0)>, <rho(t)>, #active}; an empty start stays empty; every row equals an independent run of the
+    same trial through the C ABI (cubic DP step, the runner's stream key, the reference's window rule for the measurement step)."""
+    import subprocess
+    exe = os.path.join(ROOT, "drivers", "bifurc_prob")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    L, a, t_event, dt, r, seed = 24, -0.9, 1.0, 0.1, 2, 7
+    env = dict(os.environ, TM_DATA_ROOT=str(tmp_path), TM_SEED=str(seed))
+    out = subprocess.run([exe], input="%g\n%g\n%d\n%g\n0\n1.5\n4\n%d\n" % (dt, t_event, L, a, r), text=True, capture_output=True, env=env, timeout=1500)
+    assert out.returncode == 0, out.stderr
+    path = tmp_path / "Data" / "SPDP" / "1stOrder_Rep_DP_G_24_T_1_dt_0.1_a_-0.9_c_1_p1_0_p2_1.5_dx_2.5_Sig_1_R_2.csv"
+    assert path.exists(), os.listdir(tmp_path / "Data" / "SPDP")
+    lines = path.read_text().splitlines()
+    assert lines[0] == "  a , c , L, r, t ,  <<Rho(x; 0)>_x>, <<Rho(x; t)>_x>, # Active Sites "
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in lines[1:]])
+    assert rows.shape == (4 * r, 8) and np.all(rows[:, 0] == a) and np.all(rows[:, 1] == 1) and np.all(rows[:, 2] == L) and np.all(rows[:, 4] == t_event)
+    assert list(rows[:, 3]) == [0, 1] * 4 and np.allclose(rows[:, 5], np.repeat([0, 0.5, 1.0, 1.5], r))
+    assert np.all(rows[:r, 6:] == 0) and np.all(rows[r:, 6] > 0)
+    steps, t = 0, 0.0
+    while not (t != 0.0 and t_event - dt / 2.0 <= t < t_event + dt / 2.0):
+        t += dt
+        steps += 1
+    host.tmh_stream_seed.restype = C.c_ulonglong
+    host.tmh_stream_seed.argtypes = [C.c_ulonglong, C.c_double]
+    for k, p0 in enumerate([0.5, 1.0, 1.5], start=1):
+        lat = tm.Lattice(tm.dp_params(L, a=a, b=-2.0, D=6.25, sigma=1.0, dt=dt, dx=2.5, c=1.0), r)
+        lat.seed(host.tmh_stream_seed(host.tmh_stream_seed(seed, a), p0))
+        lat.upload(np.full((r, 1, L, L), p0))
+        lat.step(steps)
+        stats = lat.measure()
+        for j in range(r):
+            assert rows[k * r + j, 6] == stats[j].mean[0] and rows[k * r + j, 7] == stats[j].active[0]

@@ -331,6 +331,65 @@ void first_order_critical_exp_delta(double Rho_0[], int div, double t_max, doubl
                  " a , c , L,  t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n", vec, true);
 }
 
+// ---- terminal state after a fixed time from a range of initial densities (P/:2158-2420, :2548-2676; driver bifurc_prob.cpp) -------
+
+// terminal_percolationDornic_2D, P/:2158: the cubic DP step from the frame Rh0, r replicates; <rho> and the active sites at t = 0 and
+// in the window of t_meas[0] (P/:2216-2224), one row per replicate {a, c, L, j, t_meas.back(), <rho(0)>, <rho(t)>, #active(t)}
+// (P/:2413-2417).  The reference keeps stepping for another 100 time units without looking at the lattice again (t_max = t_meas.back()
+// + 100, P/:2178): not done here.  Streams: keyed by (TM_SEED, a, Rh0[0]) so that the sweep's initial densities are independent.
+void terminal_percolationDornic_2D(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[], double /*t_max*/, double a,
+                                   double b, double c, double D, double sigma, double dt, double dx, int r, int g)
+{
+    if (t_meas.empty() || r < 1) throw std::invalid_argument("terminal_percolationDornic_2D: empty t_meas or r < 1");
+    tm_params p{};
+    p.model = TM_MODEL_DP_CUBIC;
+    p.L = g; p.dt = dt; p.dx = dx; p.a = a; p.b = b; p.c = c; p.D = D; p.sigma = sigma;
+    Ctx ctx(p, r);
+    const size_t n = (size_t)g * g;
+    vector<double> host(n * r);
+    for (int j = 0; j < r; j++) memcpy(&host[n * j], Rh0, n * sizeof(double));
+    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
+    ctx.ck(tm_seed(ctx.c, stream_seed(stream_seed(options().seed, a), Rh0[0]), 0), "tm_seed");
+    vector<tm_stats> st0(r), st1(r);
+    ctx.ck(tm_measure(ctx.c, st0.data()), "tm_measure");                          // t == 0
+    int steps = 0;                                                                // iterations before the window of t_meas[0] opens
+    for (double t = 0; t < t_meas.back() + 100 + dt; t += dt, steps++)
+        if (t != 0.0 && t >= t_meas[0] - dt / 2.0 && t < t_meas[0] + dt / 2.0) break;
+    ctx.ck(tm_step(ctx.c, steps), "tm_step");
+    ctx.ck(tm_measure(ctx.c, st1.data()), "tm_measure");
+    for (int j = 0; j < r; j++) {
+        if (st0[j].nonfinite || st1[j].nonfinite) { std::cerr << "RK4 BLEW IT: non-finite density in replicate " << j << std::endl; exit(3); }   // P/:2370-2398
+        const bool dead0 = st0[j].active[0] == 0;                                 // extinct at t = 0: the replicate stops there (P/:2222)
+        Rho.push_back({a, c, static_cast<double>(g), static_cast<double>(j), t_meas.back(), st0[j].mean[0],
+                       dead0 ? 0.0 : st1[j].mean[0], dead0 ? 0.0 : (double)st1[j].active[0]});
+    }
+}
+
+// first_order_terminal_diff, P/:2548: the runner above from constant frames p in linspace(p_start, p_end, div), dealt over the GPUs;
+// CSV "<data_root>/Data/SPDP/1stOrder_Rep_DP_G_<L>_T_<t>_dt_..._R_<r>.csv"
+void first_order_terminal_diff(int div, double t_event, double p_start, double p_end, double a, double b, double c, double D, double sigma,
+                               double dt, double dx, int r, int g)
+{
+    const vector<double> p_space = linspace(p_start, p_end, div);
+    vector<vector<vector<double>>> per_p(p_space.size());
+    for_each_on_devices((int)p_space.size(), [&](int i) {
+        vector<double> Rho_0((size_t)g * g, p_space[i]);                          // init_constframe, P/:46
+        vector<double> t_measure{t_event};
+        terminal_percolationDornic_2D(per_p[i], t_measure, Rho_0.data(), t_event, a, b, c, D, sigma, dt, dx, r, g);
+    });
+    std::stringstream L, coco, tm, d3, p1, p2, rini, Sm, dix, aoili;
+    L << g; tm << t_event; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << p_start; p2 << std::setprecision(4) << p_end;
+    rini << r; Sm << std::setprecision(3) << sigma; coco << std::setprecision(4) << c; dix << std::setprecision(2) << dx; aoili << std::setprecision(4) << a;
+    mkdirs(options().data_root + "/Data/SPDP");
+    std::ofstream out(options().data_root + "/Data/SPDP/1stOrder_Rep_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + aoili.str()
+                      + "_c_" + coco.str() + "_p1_" + p1.str() + "_p2_" + p2.str() + "_dx_" + dix.str() + "_Sig_" + Sm.str() + "_R_" + rini.str() + ".csv");
+    out << "  a , c , L, r, t ,  <<Rho(x; 0)>_x>, <<Rho(x; t)>_x>, # Active Sites \n";
+    for (const auto &rows : per_p)
+        for (const vector<double> &v : rows)
+            out << std::setprecision(8) << v[0] << "," << v[1] << "," << v[2] << "," << v[3] << "," << v[4] << "," << std::setprecision(16) << v[5]
+                << "," << std::setprecision(16) << v[6] << "," << std::setprecision(16) << v[7] << std::endl;   // P/:2664-2667
+}
+
 // ---- finite-size scaling drivers (P/:1424-1665): percolationDornic_2D at a_c over a range of grid sizes ------------
 
 // lnspace, P/:281-301

@@ -8,6 +8,7 @@
 //   critical_exp_delta              Percolation_FD/stochasticSPDP.cpp:1309
 //   first_order_critical_exp_delta  Percolation_FD/stochasticSPDP.cpp:2422
 //   critical_exp_finite_scaling_collapse / _stationary   Percolation_FD/stochasticSPDP.cpp:1424, 1538
+//   terminal_percolationDornic_2D, first_order_terminal_diff   Percolation_FD/stochasticSPDP.cpp:2158, 2548
 //   rietkerk_Dornic_2D_MultiSp      Rietkerk_FD/rietkerk_bjork_basic.cpp:3397   (SPB = 1)
 //   first_order_critical_exp_delta_stochastic_MultiSp   Rietkerk_FD/rietkerk_bjork_basic.cpp:4379
 //   spreading_exp_Dornic_2D         Percolation_FD/stochasticSPDP.cpp:1145   (seed-at-centre runs: N(t), R^2(t), P_surv(t))
@@ -71,6 +72,13 @@ void expanded_percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::v
                                    double dx, int r, int g);
 void critical_exp_delta(double Rho_0[], int div, double t_max, double a_start, double a_end, double b, double D,
                         double sigma, double dt, double dx, int r, int g);
+// terminal state after a fixed time (P/:2158, :2548; driver bifurc_prob.cpp): the cubic DP step from a given frame, r replicates, rows
+// {a, c, L, j, t, <rho(0)>, <rho(t)>, #active(t)}; the sweep over constant initial densities p writes
+// "<data_root>/Data/SPDP/1stOrder_Rep_DP_G_<L>_T_<t>_dt_..._p1_<p1>_p2_<p2>_..._R_<r>.csv"
+void terminal_percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_meas, double Rh0[], double t_max,
+                                   double a, double b, double c, double D, double sigma, double dt, double dx, int r, int g);
+void first_order_terminal_diff(int div, double t_event, double p_start, double p_end, double a, double b, double c, double D, double sigma,
+                               double dt, double dx, int r, int g);
 // finite-size scaling at a_c (P/:1424, :1538): percolationDornic_2D from a full frame for `div` grid sizes -- linspace(g_st, g_end)
 // with the log10 time bins, resp. lnspace(g_st, g_end) with 30 linear bins in the reference's per-size stationary window (L > 30) --
 // grid sizes dealt over the visible GPUs; CSV "<data_root>/Data/SPDP/DEBUG_P_c_Finite_Scaling_{Collapse,Stationary}_T_..._R_<r>.csv"
