@@ -139,3 +139,51 @@ def test_bifurc_prob_driver_and_terminal_runner(host, tmp_path):
         stats = lat.measure()
         for j in range(r):
             assert abs(rows[k * r + j, 6] - stats[j].mean[0]) <= 1e-15 * stats[j].mean[0] and rows[k * r + j, 7] == stats[j].active[0]   # setprecision(16)
+
+
+def test_frame_capture_runner_and_frameDP_driver(host, tmp_path):
+    """frames_expanded_percolationDornic_2D (P/:2678): every replicate's lattice at the step whose accumulated t falls in the window of
+    t_event, appended to one CSV; equal (to the file's six digits) to an independent run of the same trials through the C ABI; no file when
+    the window coincides with a measurement bin (the reference's dangling `else if`, P/:2763-2791).  drivers/frameDP end to end."""
+    import subprocess
+    L, a, dt, r, seed, t_event = 16, -0.71, 0.1, 2, 9, 1.6
+    host.tmh_dp_frames.argtypes = [C.c_int] + [C.c_double] * 7 + [C.c_int, dp, dp, C.c_int, C.c_double]
+    host.tmh_stream_seed.restype = C.c_ulonglong
+    host.tmh_stream_seed.argtypes = [C.c_ulonglong, C.c_double]
+    host.tmh_set_options(0, seed, 0, str(tmp_path).encode())
+    rh0 = np.abs(np.random.default_rng(3).normal(1.0, 0.25, L * L))
+    bins = np.zeros(64)
+    nb = O.oracle().tmo_logarithm10_time_bins(C.c_double(20.0), C.c_double(dt), O.ptr(bins), 64)
+    assert not np.any(np.abs(bins[:nb] - t_event) < dt / 2)            # 1.6 is not one of the log10 bins at dt = 0.1
+    assert host.tmh_dp_frames(L, a, -2.0, 1.0, 6.25, 1.0, dt, 2.5, r, O.ptr(rh0), O.ptr(bins), nb, t_event) == 0
+    path = tmp_path / "Data" / "SPDP" / "Frames" / "1RBOKCHOYFRAME_P_c_G_16_T_1.6_dt_0.1_a1_-0.71_Sig_1_dx_2.5_R_2.csv"
+    assert path.exists(), os.listdir(tmp_path / "Data" / "SPDP" / "Frames")
+    lines = path.read_text().splitlines()
+    assert len(lines) == r * (1 + L * L) and lines[0] == " a, c, t , x,  Rho(x; t)" and lines[1 + L * L] == lines[0]
+    steps, t = 0, 0.0
+    while not (t_event - dt / 2.0 <= t < t_event + dt / 2.0):
+        t += dt
+        steps += 1
+    lat = tm.Lattice(tm.dp_params(L, a=a, b=-2.0, D=6.25, sigma=1.0, dt=dt, dx=2.5, c=1.0), r)
+    lat.seed(host.tmh_stream_seed(seed, a))
+    lat.upload(np.tile(rh0, (r, 1)).reshape(r, 1, L, L))
+    lat.step(steps)
+    want = lat.download().reshape(r, L * L)
+    for j in range(r):
+        blk = np.array([[float(x) for x in ln.split(",")] for ln in lines[j * (1 + L * L) + 1:(j + 1) * (1 + L * L)]])
+        assert np.all(blk[:, 0] == a) and np.all(blk[:, 1] == 1) and np.allclose(blk[:, 2], t_event) and np.array_equal(blk[:, 3], np.arange(L * L))
+        np.testing.assert_allclose(blk[:, 4], want[j], rtol=5e-6, atol=1e-300)
+    # hidden by a measurement bin: 1.5 is one of them
+    assert np.any(np.abs(bins[:nb] - 1.5) < dt / 2)
+    assert host.tmh_dp_frames(L, a, -2.0, 1.0, 6.25, 1.0, dt, 2.5, r, O.ptr(rh0), O.ptr(bins), nb, 1.5) == 0
+    assert not (tmp_path / "Data" / "SPDP" / "Frames" / "1RBOKCHOYFRAME_P_c_G_16_T_1.5_dt_0.1_a1_-0.71_Sig_1_dx_2.5_R_2.csv").exists()
+    # the driver: two a-values from one random frame
+    exe = os.path.join(ROOT, "drivers", "frameDP")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    root = tmp_path / "drv"
+    env = dict(os.environ, TM_DATA_ROOT=str(root), TM_SEED="7")
+    out = subprocess.run([exe], input="0.1\n20\n1.6\n16\n-0.72\n-0.70\n2\n2\n", text=True, capture_output=True, env=env, timeout=1500)
+    assert out.returncode == 0, out.stderr
+    names = sorted(os.listdir(root / "Data" / "SPDP" / "Frames"))
+    assert set(names) == {"1RBOKCHOYFRAME_P_c_G_16_T_1.6_dt_0.1_a1_-0.7_Sig_1_dx_2.5_R_2.csv", "1RBOKCHOYFRAME_P_c_G_16_T_1.6_dt_0.1_a1_-0.72_Sig_1_dx_2.5_R_2.csv"}
+    assert len((root / "Data" / "SPDP" / "Frames" / names[0]).read_text().splitlines()) == r * (1 + L * L)

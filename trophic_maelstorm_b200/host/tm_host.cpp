@@ -390,6 +390,72 @@ void first_order_terminal_diff(int div, double t_event, double p_start, double p
                 << "," << std::setprecision(16) << v[6] << "," << std::setprecision(16) << v[7] << std::endl;   // P/:2664-2667
 }
 
+// ---- frame capture at a given time (P/:2678-2995, :2997-3129; driver frameDP.cpp) --------------------------------------------------
+
+// frames_expanded_percolationDornic_2D, P/:2678: the cubic DP step from Rh0, r replicates; the lattice of every replicate is appended to
+// "<data_root>/Data/SPDP/Frames/1RBOKCHOYFRAME_P_c_G_<L>_T_<t_event>_dt_<dt>_a1_<a>_Sig_<sigma>_dx_<dx>_R_<r>.csv" (header + L*L rows
+// "a,c,t,x,rho" at default precision, replicate 0 truncating the file) at the step whose accumulated t falls in the window of t_event --
+// and, since the dump hangs on an `else if` behind the measurement test (P/:2763, 2791), only if that step is past t = 1 and not in a
+// t_meas window.  Nothing is returned in Rho (the reference's accumulation is commented out, P/:2957-2993); it keeps stepping to
+// t_event + 50 without looking at the lattice again: not done here.
+void frames_expanded_percolationDornic_2D(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[], double /*t_max*/, double t_event,
+                                          double a, double b, double c, double D, double sigma, double dt, double dx, int g, int r)
+{
+    (void)Rho;
+    if (r < 1) throw std::invalid_argument("frames_expanded_percolationDornic_2D: r < 1");
+    int steps = -1, k = 0;
+    double t_dump = 0;
+    size_t index = 0;
+    for (double t = 0; t < t_event + 50 + dt; t += dt, k++) {                     // P/:2755-2796
+        const bool win = index < t_meas.size() && t >= t_meas[index] - dt / 2.0 && t < t_meas[index] + dt / 2.0;
+        if (t <= 1.0 || win) { if (t > 1.0) index += 1; continue; }
+        if (t >= t_event - dt / 2.0 && t < t_event + dt / 2.0) { steps = k; t_dump = t; break; }
+    }
+    if (steps < 0) return;                                                        // the window is hidden by a measurement step: no file
+    tm_params p{};
+    p.model = TM_MODEL_DP_CUBIC;
+    p.L = g; p.dt = dt; p.dx = dx; p.a = a; p.b = b; p.c = c; p.D = D; p.sigma = sigma;
+    Ctx ctx(p, r);
+    const size_t n = (size_t)g * g;
+    vector<double> host(n * r);
+    for (int j = 0; j < r; j++) memcpy(&host[n * j], Rh0, n * sizeof(double));
+    ctx.ck(tm_upload(ctx.c, host.data()), "tm_upload");
+    ctx.ck(tm_seed(ctx.c, stream_seed(options().seed, a), 0), "tm_seed");
+    ctx.ck(tm_step(ctx.c, steps), "tm_step");
+    ctx.ck(tm_download(ctx.c, host.data()), "tm_download");
+    std::stringstream L, tm, d3, p1, dX, Sm, repli;
+    L << g; tm << t_event; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a; repli << r;
+    dX << std::setprecision(3) << dx; Sm << std::setprecision(3) << sigma;
+    mkdirs(options().data_root + "/Data/SPDP/Frames");
+    std::ofstream out(options().data_root + "/Data/SPDP/Frames/1RBOKCHOYFRAME_P_c_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a1_" + p1.str()
+                      + "_Sig_" + Sm.str() + "_dx_" + dX.str() + "_R_" + repli.str() + ".csv");
+    for (int j = 0; j < r; j++) {                                                 // P/:2806-2813, once per replicate
+        out << " a, c, t , x,  Rho(x; t)\n";
+        for (size_t i = 0; i < n; i++) out << a << "," << c << "," << t_dump << "," << i << "," << host[n * j + i] << std::endl;
+    }
+}
+
+// capture_frame_decay, P/:2997: the runner above for a in linspace(a_start, a_end, div) from ONE random frame N(1, 0.25) clipped at 0
+// (init_randframe P/:53: mt19937_64(random_device) there, splitmix64 from TM_SEED with Box-Muller here), the a-values dealt over the GPUs
+void capture_frame_decay(double Rho_0[], int div, double t_max, double t_event, double a_start, double a_end, double b, double c, double D,
+                         double sigma, double dt, double dx, int r, int g)
+{
+    unsigned long long s = options().seed ^ 0x5DEECE66Dull;
+    auto u01 = [&]() { unsigned long long z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                       z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31; return ((z >> 11) + 0.5) * 0x1.0p-53; };
+    for (int i = 0; i < g * g; i++) {
+        const double v = 1.00 + 0.25 * std::sqrt(-2.0 * std::log(u01())) * std::cos(6.283185307179586 * u01());
+        Rho_0[i] = v < 0 ? 0.0 : v;
+    }
+    const vector<double> a_space = linspace(a_start, a_end, div);
+    vector<double> t_measure = logarithm10_time_bins(t_max, dt);
+    for_each_on_devices((int)a_space.size(), [&](int i) {
+        vector<vector<double>> none;
+        vector<double> tm_i = t_measure;
+        frames_expanded_percolationDornic_2D(none, tm_i, Rho_0, t_max, t_event, a_space[i], b, c, D, sigma, dt, dx, g, r);
+    });
+}
+
 // ---- finite-size scaling drivers (P/:1424-1665): percolationDornic_2D at a_c over a range of grid sizes ------------
 
 // lnspace, P/:281-301

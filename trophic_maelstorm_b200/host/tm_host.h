@@ -9,6 +9,7 @@
 //   first_order_critical_exp_delta  Percolation_FD/stochasticSPDP.cpp:2422
 //   critical_exp_finite_scaling_collapse / _stationary   Percolation_FD/stochasticSPDP.cpp:1424, 1538
 //   terminal_percolationDornic_2D, first_order_terminal_diff   Percolation_FD/stochasticSPDP.cpp:2158, 2548
+//   frames_expanded_percolationDornic_2D, capture_frame_decay  Percolation_FD/stochasticSPDP.cpp:2678, 2997
 //   rietkerk_Dornic_2D_MultiSp      Rietkerk_FD/rietkerk_bjork_basic.cpp:3397   (SPB = 1)
 //   first_order_critical_exp_delta_stochastic_MultiSp   Rietkerk_FD/rietkerk_bjork_basic.cpp:4379
 //   spreading_exp_Dornic_2D         Percolation_FD/stochasticSPDP.cpp:1145   (seed-at-centre runs: N(t), R^2(t), P_surv(t))
@@ -79,6 +80,12 @@ void terminal_percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::v
                                    double a, double b, double c, double D, double sigma, double dt, double dx, int r, int g);
 void first_order_terminal_diff(int div, double t_event, double p_start, double p_end, double a, double b, double c, double D, double sigma,
                                double dt, double dx, int r, int g);
+// frame capture at t_event (P/:2678, :2997; driver frameDP.cpp): the lattices of r replicates of the cubic DP model appended to
+// "<data_root>/Data/SPDP/Frames/1RBOKCHOYFRAME_P_c_G_<L>_T_<t_event>_dt_..._R_<r>.csv"; capture_frame_decay sweeps a from one random frame
+void frames_expanded_percolationDornic_2D(std::vector<std::vector<double>> &Rho, std::vector<double> &t_meas, double Rh0[], double t_max,
+                                          double t_event, double a, double b, double c, double D, double sigma, double dt, double dx, int g, int r);
+void capture_frame_decay(double Rho_0[], int div, double t_max, double t_event, double a_start, double a_end, double b, double c, double D,
+                         double sigma, double dt, double dx, int r, int g);
 // finite-size scaling at a_c (P/:1424, :1538): percolationDornic_2D from a full frame for `div` grid sizes -- linspace(g_st, g_end)
 // with the log10 time bins, resp. lnspace(g_st, g_end) with 30 linear bins in the reference's per-size stationary window (L > 30) --
 // grid sizes dealt over the visible GPUs; CSV "<data_root>/Data/SPDP/DEBUG_P_c_Finite_Scaling_{Collapse,Stationary}_T_..._R_<r>.csv"

@@ -417,6 +417,17 @@ int tmh_riet3_run_any(int fpe, int L, const double *par, int r, const double *in
         for (size_t j = 0; j < 18; j++) rows_out[18 * k + j] = j < Rho[k].size() ? Rho[k][j] : 0.0;
     return (int)Rho.size();
 }
+// frames_expanded_percolationDornic_2D (P/:2678) from the frame rh0[L*L]; the file lands under data_root
+int tmh_dp_frames(int L, double a, double b, double c, double D, double sigma, double dt, double dx, int r, const double *rh0,
+                  const double *t_meas, int n_tmeas, double t_event)
+{
+    std::vector<std::vector<double>> Rho;
+    std::vector<double> tm(t_meas, t_meas + n_tmeas), r0(rh0, rh0 + (size_t)L * L);
+    try { frames_expanded_percolationDornic_2D(Rho, tm, r0.data(), tm.empty() ? t_event : tm.back(), t_event, a, b, c, D, sigma, dt, dx, L, r); }
+    catch (const std::exception &e) { fprintf(stderr, "tmh_dp_frames: %s\n", e.what()); return -2; }
+    return 0;
+}
+
 // finite-size scaling drivers (P/:1424, :1538); kind 0 = collapse, 1 = stationary; CSV under data_root
 int tmh_dp_finite_scaling(int kind, int div, int g_st, int g_end, double t_max, double a_c, double b, double D, double sigma, double dt,
                           double dx, int r)
