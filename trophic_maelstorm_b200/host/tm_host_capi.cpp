@@ -212,6 +212,14 @@ void tmh_use_burnin(const char *parendir, const char *pattern)
     if (parendir && pattern) use_burnin_frames(parendir, pattern); else use_default_init_frame();
 }
 
+// the runner shims below return rows and frames to the caller: the runners' CSV side outputs are switched off for the call
+// (no frame schedule, no prelim tables) unless the call is a sweep, which writes its whole tree under data_root
+struct QuietSideOutputs {
+    std::vector<double> ft; bool wp; bool on;
+    explicit QuietSideOutputs(bool on_) : ft(frame_tmeas), wp(write_prelims), on(on_) { if (on) { frame_tmeas.clear(); write_prelims = false; } }
+    ~QuietSideOutputs() { if (on) { frame_tmeas = ft; write_prelims = wp; } }
+};
+
 // SPB = 2 runner (tm_host_2sp.h).  par = {a, c, gmax, alpha, rW, W0, d, K1, K2, D0, D1, D2, D3, sigma0, sigma1, v1, aij, hij, ej,
 // m1, pR1, dt, dx} (the vector of tests/golden/make_runner2_golden.py); init: [n_init][4][L*L], replicate j starts from frame
 // j % n_init; rows_out[k][14]; frames_out (may be NULL): [r][n_tmeas][4][L*L], the frame seen at every measurement bin.
@@ -234,6 +242,7 @@ int tmh_riet2_run(int L, const double *par, int r, const double *init, int n_ini
     else s2::on_measure = nullptr;
     s2::D2Vec_Double Rho;
     std::vector<double> tm(t_meas, t_meas + n_tmeas);
+    QuietSideOutputs quiet(true);
     try {
         s2::rietkerk_Dornic_2D_MultiSp(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], D, v, K, sigma, par[0], par[0],
                                        1.0 / 24.0, A, H, E, M, pR, dtV, clow, par[21], par[22], 10000.0, r, L);
@@ -339,6 +348,7 @@ int tmh_fpe2_run(int L, const double *par, int r, const double *init, int n_init
         s2::on_measure = [=](int j, int index, double, const double *f) { memcpy(frames_out + ((size_t)j * n_tmeas + index) * n4, f, n4 * sizeof(double)); };
     else s2::on_measure = nullptr;
     s2::D2Vec_Double Rho;
+    QuietSideOutputs quiet(!sweep);
     try {
         set_global_FKE_params(D, v, dtAdv, par[21], par[22], L, 4);
         if (sweep) {
@@ -393,6 +403,7 @@ int tmh_riet3_run_any(int fpe, int L, const double *par, int r, const double *in
         s3::on_measure = [=](int j, int index, double, const double *f) { memcpy(frames_out + ((size_t)j * n_tmeas + index) * n5, f, n5 * sizeof(double)); };
     else s3::on_measure = nullptr;
     s3::D2Vec_Double Rho;
+    QuietSideOutputs quiet(!sweep);
     try {
         if (fpe) {
             double dtAdv[s3::SpB] = {0.0, par[31], par[32]};
