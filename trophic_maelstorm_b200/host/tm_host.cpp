@@ -1216,30 +1216,36 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
 // header name with blanks removed, as R/:665-672 does; a file without a header is taken as a_c, x, P, W, O).
 // frame: 3*g*g doubles (P, W, O).  Returns the number of lattice rows read (g*g on success), -1 if the file cannot be opened,
 // -2 if a named column is missing.
-int read_frame_csv(const std::string &filename, int g, double *frame)
+// n_fields = 3 (P, W, O), 4 (P, G, W, O) or 5 (P, G, Pr, W, O): the biotic columns are the first n_fields - 2 of "P(x;t)", "G(x;t)",
+// "Pr(x;t)" and land in that order, water last (R/:700-705); a file without a header is taken as a_c, x, then the fields in memory order
+int read_frame_csv_fields(const std::string &filename, int g, int n_fields, double *frame)
 {
+    if (n_fields < 3 || n_fields > 5) return -3;
     std::ifstream in(filename);
     if (!in.is_open()) { std::cerr << "Error opening file: " << filename << std::endl; return -1; }
     const size_t n = (size_t)g * g;
-    int col[3] = {2, 3, 4};
-    static const char *names[3] = {"P(x;t)", "W(x;t)", "O(x;t)"};
+    static const char *biota[3] = {"P(x;t)", "G(x;t)", "Pr(x;t)"};
+    const char *names[5]; int col[5];
+    for (int k = 0; k < n_fields - 2; k++) names[k] = biota[k];
+    names[n_fields - 2] = "W(x;t)"; names[n_fields - 1] = "O(x;t)";
+    for (int k = 0; k < n_fields; k++) col[k] = 2 + k;
     std::string line;
     size_t row = 0;
     while (std::getline(in, line)) {
         if (line.find("a_c") != std::string::npos) {            // header line (R/:941)
-            std::stringstream hs(line); std::string name; int idx = 0; int found[3] = {-1, -1, -1};
+            std::stringstream hs(line); std::string name; int idx = 0; int found[5] = {-1, -1, -1, -1, -1};
             while (std::getline(hs, name, ',')) {
                 name.erase(std::remove_if(name.begin(), name.end(), [](unsigned char ch) { return std::isspace(ch); }), name.end());
-                for (int k = 0; k < 3; k++) if (name == names[k]) found[k] = idx;
+                for (int k = 0; k < n_fields; k++) if (name == names[k]) found[k] = idx;
                 idx++;
             }
-            for (int k = 0; k < 3; k++) { if (found[k] < 0) { std::cerr << "Column missing in CSV file: " << names[k] << " in file " << filename << std::endl; return -2; } col[k] = found[k]; }
+            for (int k = 0; k < n_fields; k++) { if (found[k] < 0) { std::cerr << "Column missing in CSV file: " << names[k] << " in file " << filename << std::endl; return -2; } col[k] = found[k]; }
             continue;
         }
         if (row >= n) break;
         std::stringstream ss(line); std::string cell; int idx = 0;
         while (std::getline(ss, cell, ',')) {
-            for (int k = 0; k < 3; k++)
+            for (int k = 0; k < n_fields; k++)
                 if (idx == col[k]) {
                     double v = 0;
                     try { v = std::stod(cell); } catch (const std::exception &) {
@@ -1254,13 +1260,14 @@ int read_frame_csv(const std::string &filename, int g, double *frame)
     return (int)row;
 }
 
-void use_default_init_frame() { init_frame = default_init_frame; }
+int read_frame_csv(const std::string &filename, int g, double *frame) { return read_frame_csv_fields(filename, g, 3, frame); }
 
-// init_burnin_wrapper R/:836-906: frames "<parendir><pattern><r'>.csv" with r' = (replicate + offset) mod (max replicate + 1);
-// the reference draws the offset from mt19937_64(random_device) (R/:623-631), here it comes from options().seed.
-void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern)
+// init_burnin_wrapper R/:836-906 for any number of fields: frames "<parendir><pattern><r'>.csv" with r' = (replicate + offset) mod (max
+// replicate + 1); the reference draws the offset from mt19937_64(random_device) (R/:623-631), here it comes from options().seed.
+std::function<void(double *, int, int, double, double, double, const double[])> burnin_frame_rule(const std::string &parendir,
+                                                                                                   const std::string &filenamePattern, int n_fields)
 {
-    init_frame = [parendir, filenamePattern](double *f, int g, int replicate, double, double, double, const double[]) {
+    return [parendir, filenamePattern, n_fields](double *f, int g, int replicate, double, double, double, const double[]) {
         int maxrep = -1;
         struct stat sb;
         while (stat((parendir + filenamePattern + std::to_string(maxrep + 1) + ".csv").c_str(), &sb) == 0) maxrep++;
@@ -1271,9 +1278,13 @@ void use_burnin_frames(const std::string &parendir, const std::string &filenameP
         unsigned long long s = options().seed ^ 0xB0B1B2B3ull;
         const int offset = (int)(splitmix(s) % (unsigned long long)(maxrep + 1));
         const int rr = (replicate + offset) % (maxrep + 1);
-        const int got = read_frame_csv(parendir + filenamePattern + std::to_string(rr) + ".csv", g, f);
+        const int got = read_frame_csv_fields(parendir + filenamePattern + std::to_string(rr) + ".csv", g, n_fields, f);
         if (got != g * g) { std::cerr << "RUN-TIME ERROR: burn-in frame has " << got << " rows, expected " << g * g << ". EXITING." << std::endl; exit(5); }
     };
 }
+
+void use_default_init_frame() { init_frame = default_init_frame; }
+
+void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern) { init_frame = burnin_frame_rule(parendir, filenamePattern, Sp); }
 
 } // namespace tm_b200

@@ -164,6 +164,11 @@ std::vector<double> sweep_time_schedule(double t_max, double dt);
 // (init_csvconstframe R/:909, header matching of init_exprtk_readCSVcolumns_frame R/:609); use_burnin_frames() makes
 // every replicate start from "<parendir><filenamePattern><r>.csv" (init_burnin_wrapper R/:836).
 int read_frame_csv(const std::string &filename, int g, double *frame);
+// ... for n_fields = 3 | 4 | 5 fields (P[, G[, Pr]], W, O), the columns located by header name (R/:665-705); and the burn-in rule for
+// any of them as an init_frame function (what use_burnin_frames and its spb2 / spb3 twins assign)
+int read_frame_csv_fields(const std::string &filename, int g, int n_fields, double *frame);
+std::function<void(double *, int, int, double, double, double, const double[])> burnin_frame_rule(const std::string &parendir,
+                                                                                                   const std::string &filenamePattern, int n_fields);
 void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern);
 void use_default_init_frame();   // back to the MFT speckle rule
 // set_Prefix (R/:113-135): prefix and the three output locations derived from it, "<data_root>/Data/Rietkerk/..." for the reference's "../Data/Rietkerk/..."

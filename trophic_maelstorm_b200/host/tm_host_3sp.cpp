@@ -25,6 +25,7 @@ using std::vector;
 std::function<void(double *, int, int, double, double, double, const double[])> init_frame;
 std::function<void(int, int, double, const double *)> on_measure;
 std::string frame_folder, prelim_folder, stat_prefix;
+void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern) { init_frame = burnin_frame_rule(parendir, filenamePattern, Sp); }
 void set_Prefix(const std::string &user_prefix, double mG, double mP) { set_Prefix_for(SpB, user_prefix, mG, mP, frame_folder, prelim_folder, stat_prefix); }
 side::Stepper *test_stepper = nullptr;
 const std::string frame_header = "a_c,  x,  P(x; t), G(x; t), Pr(x; t), W(x; t), O(x; t) \n";            // rietkerk_bjork_constants_3Sp.h:6

@@ -36,6 +36,9 @@ extern std::string frame_folder, prelim_folder;
 // "<data_root>/Data/Rietkerk/{Frames,Prelims}/Stochastic/3Sp[_mG_<mG>[_mP_<mP>]]/<prefix>_", ".../Stochastic/1stOrderCC_Rietkerk_<prefix>_P_c_G_"
 extern std::string stat_prefix;   // empty (default): the header's location of the final table, ".../Stochastic/3Sp/1stCC_Rietkerk_<prefix>_P_c_G_"
 void set_Prefix(const std::string &user_prefix, double mG = 0.0, double mP = 0.0);
+// burn-in frames (the reference's -DINIT=2 path, init_burnin_wrapper R/:836): every replicate starts from "<parendir><pattern><r'>.csv", a
+// frame in save_frame()'s layout with this model's columns (located by header name, water last)
+void use_burnin_frames(const std::string &parendir, const std::string &filenamePattern);
 extern const std::string frame_header, gammaheader, movmheader;   // rietkerk_bjork_constants_3Sp.h:6-17
 
 void var_mean_incremental_surv_runs(D2Vec_Double &t_avg_var_rep_N, const D2Vec_Double &X_curr, int size, int j);   // R/:1293

@@ -206,6 +206,15 @@ void tmh_save_frame(const char *parendir, const char *pattern, const double *fra
     save_frame(fr, parendir, pattern, a, a, a, 0.0, 0.1, 0.1, 0.0, r, g);
 }
 int tmh_read_frame_csv(const char *filename, int g, double *frame) { return read_frame_csv(filename, g, frame); }
+int tmh_read_frame_csv_fields(const char *filename, int g, int n_fields, double *frame) { return read_frame_csv_fields(filename, g, n_fields, frame); }
+// the burn-in rule of the SPB = 2 / 3 layers applied once: frame of `replicate` from "<parendir><pattern><r'>.csv"
+int tmh_burnin_frame(int spb, const char *parendir, const char *pattern, int g, int replicate, double *frame)
+{
+    if (spb == 2) { tm_b200::spb2::use_burnin_frames(parendir, pattern); tm_b200::spb2::init_frame(frame, g, replicate, 0, 0, 0, nullptr); tm_b200::spb2::init_frame = nullptr; }
+    else if (spb == 3) { tm_b200::spb3::use_burnin_frames(parendir, pattern); tm_b200::spb3::init_frame(frame, g, replicate, 0, 0, 0, nullptr); tm_b200::spb3::init_frame = nullptr; }
+    else return -3;
+    return 0;
+}
 // every later Rietkerk run starts from <parendir><pattern><r>.csv (parendir == NULL: back to the MFT speckle default)
 void tmh_use_burnin(const char *parendir, const char *pattern)
 {
