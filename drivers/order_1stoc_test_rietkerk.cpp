@@ -5,6 +5,9 @@
 //   order_1stoc_test_rietkerk dt t_max g r a_start a_end div dP PREFIX
 // Outputs go under <TM_DATA_ROOT>/Data/Rietkerk/... (default "..", as the reference writes "../Data/Rietkerk/...").
 // Sweeps are spread over every visible GPU (TM_DEVICES / TM_DEVICE_LIST / TM_DEVICE narrow that); results do not depend on it.
+// Compiled with -DTM_FPE_PROGRAM (drivers/order_1stoc_test_rietkerk_fpe) it is Rietkerk_FPE/order_1stoc_test_rietkerk.cpp -- the same
+// source text there, linked against rietkerk_bjork_FKE.cpp: the FPE runner (clamp at 1e-10, its checkpoint and frame rules) starting from
+// the deterministic Gaussian frame that runner uses as shipped (F/:3954-3962).
 #include "tm_host.h"
 #include <cmath>
 #include <cstdlib>
@@ -60,8 +63,14 @@ int main(int argc, char *argv[])
     recursive_dir_create(prelim_folder + tag + "/TimeSeries");
     recursive_dir_create(options().data_root + "/Data/Rietkerk/Stochastic/" + to_string(SpB) + "Sp");
     try {
+#ifdef TM_FPE_PROGRAM
+        init_frame = [](double *frame, int g_, int, double, double, double, const double clow[]) { init_gaussframe(frame, Sp, SpB, g_, clow + Sp); };
+        first_order_critical_exp_delta_stochastic_MultiSp_FPE(div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, v, K, sigma, A, H, E,
+                                                              M, pR, dtV, scaling_factor, dt, dx, dP, r, g, Wstar);
+#else
         first_order_critical_exp_delta_stochastic_MultiSp(div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, v, K, sigma, A, H, E,
                                                           M, pR, dtV, scaling_factor, dt, dx, dP, r, g, Wstar);
+#endif
     } catch (const exception &e) {
         cerr << "order_1stoc_test_rietkerk: " << e.what() << endl;
         return 1;

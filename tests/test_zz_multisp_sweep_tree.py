@@ -208,3 +208,33 @@ def test_fpe_spb3_unity_driver_binary(tmp_path):
     assert np.all(fr[:, 5] == 4.0) and np.all(fr[:, 6] == 10.0)
     bad = subprocess.run([exe, "0.5", "1.5", str(L), "2", "0.05", "0.06", "2", "10000", "1", "10", "50", "TEST"], text=True, capture_output=True, env=env)
     assert bad.returncode == 1 and "not supported" in bad.stderr
+
+
+def test_fpe_spb1_driver_binary(tmp_path):
+    """drivers/order_1stoc_test_rietkerk_fpe = Rietkerk_FPE/order_1stoc_test_rietkerk.cpp (BASELINE config 3's program at SPB = 1): the
+    vegetation-only model under rietkerk_DorFPE_2D_MultiSp's rules -- Gaussian initial frame, checkpoints at the 85 / 90 / 95 / 100 % bins
+    only -- beside the Rietkerk_FD program of the same arguments, which also writes the 60 % checkpoint."""
+    import subprocess
+    trees = {}
+    for name in ("order_1stoc_test_rietkerk", "order_1stoc_test_rietkerk_fpe"):
+        exe = os.path.join(ROOT, "drivers", name)
+        assert os.path.exists(exe), "run __graft_entry__.build()"
+        root = tmp_path / name
+        env = dict(os.environ, TM_DATA_ROOT=str(root), TM_SEED="7")
+        out = subprocess.run([exe, "0.1", "3", "16", "2", "0.05", "0.06", "2", "10000", "TEST"], text=True, capture_output=True, env=env, timeout=1500)
+        assert out.returncode == 0, out.stderr
+        trees[name] = {k: v.decode() for k, v in _tree(root).items()}
+    fd, fpe = trees["order_1stoc_test_rietkerk"], trees["order_1stoc_test_rietkerk_fpe"]
+    table = "Data/Rietkerk/Stochastic/1stOrderCC_Rietkerk_TEST_P_c_G_16_T_3_dt_0.1_D1_1.04e-05_a1_0.05_a2_0.06_dx_0.1_Geq_5_R_2.csv"
+    assert table in fd and table in fpe
+    cp = lambda t: sorted({re.search(r"_T_([0-9.]+)_dt", k).group(1) for k in t if "PRELIM_TSERIES" in k}, key=float)
+    assert len(cp(fd)) == len(cp(fpe)) + 1 and set(cp(fpe)) < set(cp(fd))        # the 60 % mark is Rietkerk_FD's alone (F/:3032)
+    f0 = [k for k in fpe if "/FRAME_P_c_DP_G_16_T_0_" in k and "_a_0.05_" in k and k.endswith("R_0.csv")]
+    assert len(f0) == 1
+    fr = np.array([[float(x) for x in ln.split(",")] for ln in fpe[f0[0]].splitlines()[1:]])
+    L = 16
+    i, j = np.divmod(np.arange(L * L), L)
+    np.testing.assert_allclose(fr[:, 2], 5.0 * np.exp(-((i - L // 8) ** 2 + (j - L // 8) ** 2) / (2 * (L / 8.0) ** 2)), rtol=1e-5)
+    assert np.all(fr[:, 3] == 1.0) and np.all(fr[:, 4] == 1.0)
+    rows = np.array([[float(x) for x in ln.split(",")] for ln in fpe[table].splitlines()[2:]])
+    assert rows.shape[1] == 10 and np.isfinite(rows).all()

@@ -790,7 +790,8 @@ namespace {
 // and replicates serially, R/:4519, :3501); rows come back per a-value in the reference's layout.
 void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values, vector<double> &t_meas, double c, double gmax,
                 double alpha, double rW, double W0, double (&D)[Sp], double (&K)[3], double sigma[], double a_st, double a_end,
-                double a_c, double (&M)[SpB], double clow[], double dt, double dx, double dP, int r, int g, double Gstar, double Vstar)
+                double a_c, double (&M)[SpB], double clow[], double dt, double dx, double dP, int r, int g, double Gstar, double Vstar,
+                bool fpe = false)   // fpe: Rietkerk_FPE's runner of the same model (rietkerk_DorFPE_2D_MultiSp, F/:3697, -DSPB=1)
 {
     if (t_meas.empty() || r < 1 || a_values.empty()) throw std::invalid_argument("rietkerk_Dornic_2D_MultiSp: empty t_meas, no a-value or r < 1");
     const int na = (int)a_values.size(), nt = na * r;
@@ -799,6 +800,7 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
     p.rc = c; p.gmax = gmax; p.alpha = alpha; p.rW = rW; p.W0 = W0; p.d = M[0]; p.K1 = K[1]; p.K2 = K[2];
     p.D0 = D[0]; p.D1 = D[1]; p.D2 = D[2]; p.sigma0 = sigma[0];
     p.clamp_eps = 1.0e-12; p.clamp_lo = -1.0e-80; // R/:3402, :4176
+    if (fpe) { p.clamp_eps = 1.0e-10; p.clamp_lo = 0.0; }   // F/:4460 (epsilon of the header :119)
     const size_t n = (size_t)g * g;
 
     const int tot_iter = (int)t_meas.size();               // R/:3438
@@ -862,14 +864,15 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
             for (int j = c0; j < c1; j++) {
                 if (broke[j]) continue;   // this replicate left the time loop at an earlier checkpoint: its later rows stay 0 (R/:3714)
                 if (st[j - c0].nonfinite) { std::cerr << "RHO NAAN PARATHA in trial " << j << " at t=" << t << "\n"; exit(3); } // R/:4206-4276
+                if (fpe && st[j - c0].negative) { std::cerr << "RHO FALLS BELOW O in trial " << j << " at t=" << t << "\n"; exit(3); }   // F/:4359-4369 (checked here at the measurement steps)
                 for (int s = 0; s < Sp; s++) {
                     RhoM[j][2 * Sp * index + 2 * s] = (double)st[j - c0].active[s];
                     RhoM[j][2 * Sp * index + 2 * s + 1] = st[j - c0].mean[s];
                 }
             }
             // per-replicate time-series checkpoints, R/:3710-3716 -> save_prelimfileswrapper R/:3029-3140
-            if ((index == int(tot_iter * 0.6) || index == int(tot_iter * 0.85) || index == int(tot_iter * 0.9)
-                                  || index == int(tot_iter * 0.95) || index == int(tot_iter - 1))) {
+            if (((!fpe && index == int(tot_iter * 0.6)) || index == int(tot_iter * 0.85) || index == int(tot_iter * 0.9)
+                                  || index == int(tot_iter * 0.95) || index == int(tot_iter - 1))) {   // F/:3032: no 60 % mark
                 for (int tr = c0; tr < c1; tr++) {
                     if (broke[tr]) continue;
                     const double a = a_values[tr / r]; const int j = tr % r;
@@ -877,7 +880,7 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
                     if (write_prelims) write_tseries(RhoM[tr], t_meas, index, t, a, a_st, a_end, dt, dx, dP, D[2], j, g, pdir + subdir + "/TimeSeries");
                     if (dead) {   // the future checkpoints are written now, with zeros after this time, and the replicate stops
                         const int range[5] = {int(tot_iter * 0.6), int(tot_iter * 0.85), int(tot_iter * 0.9), int(tot_iter * 0.95), int(tot_iter - 1)};
-                        for (int k = 0; k < 5; k++) {
+                        for (int k = fpe ? 1 : 0; k < 5; k++) {
                             if (index > range[k] || !write_prelims) continue;
                             write_tseries(RhoM[tr], t_meas, range[k], t_meas[range[k]], a, a_st, a_end, dt, dx, dP, D[2], j, g,
                                           pdir + subdir + "/TimeSeries");
@@ -890,7 +893,9 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
         }
         if (snap) {
             const size_t ftot = frame_tmeas.size();
-            if ((frame_index + 10 >= ftot) || (t >= 50000 && t <= 150000) || (t >= 20 && t <= 15000) || t == 0) { // R/:3739
+            bool save = (frame_index + 10 >= ftot) || (t >= 50000 && t <= 150000) || (t >= (fpe ? 50 : 20) && t <= 15000) || t == 0; // R/:3739, F/:2886
+            if (fpe && t > 1500 && t < 6000 && frame_index % 2 != 0) save = false;   // F/:2993-3004
+            if (save) {
                 ctx.ck(tm_download(ctx.c, host.data()), "tm_download");
                 for (int tr = c0; tr < c1; tr++) {
                     if (broke[tr]) continue;   // the reference left this replicate's time loop (R/:3714): no further frames of it
@@ -1155,6 +1160,19 @@ void rietkerk_Dornic_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, doubl
     Rho.insert(Rho.end(), per_a[0].begin(), per_a[0].end());
 }
 
+// Rietkerk_FPE's runner of the same vegetation-only model (F/:3697 compiled with -DSPB=1; there is nothing to move): the step is the same
+// kernel pair with the clamp `v < 1e-10 && v >= 0` (F/:4460); bookkeeping in the FPE flavour (checkpoints at 85 / 90 / 95 / 100 %, its frame rule)
+void rietkerk_DorFPE_2D_MultiSp(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax,
+                                double alpha, double rW, double W0, double (&D)[Sp], double (&)[SpB], double (&K)[3],
+                                double sigma[], double a_st, double a_end, double a_c, double (&)[SpB][SpB], double (&)[SpB][SpB],
+                                double (&)[SpB], double (&M)[SpB], double[], int (&)[SpB], double clow[], double dt, double dx,
+                                double dP, int r, int g, double Gstar, double Vstar)
+{
+    vector<D2Vec_Double> per_a;
+    riet_batch(per_a, vector<double>{a}, t_meas, c, gmax, alpha, rW, W0, D, K, sigma, a_st, a_end, a_c, M, clow, dt, dx, dP, r, g, Gstar, Vstar, true);
+    Rho.insert(Rho.end(), per_a[0].begin(), per_a[0].end());
+}
+
 // The a-sweeps' two schedules, R/:4395-4459 (the same lines in every SPB build and in F/): t_measure = {0} U log10 bins (with the
 // 80000..150000 linear window for long runs), returned; frame_tmeas = the same bins with [50, 400] and [400, 1200] re-gridded, set.
 vector<double> sweep_time_schedule(double t_max, double dt)
@@ -1179,18 +1197,16 @@ vector<double> sweep_time_schedule(double t_max, double dt)
     return t_measure;
 }
 
-void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
-                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
-                                                       double (&)[SpB], double (&K)[3], double sigma[], double (&)[SpB][SpB],
-                                                       double (&)[SpB][SpB], double (&)[SpB], double (&M)[SpB], double[],
-                                                       int (&)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
-                                                       double Gstar, double Vstar) // R/:4379-4617
+namespace {
+void sweep_1sp(bool fpe, int div, double t_max, double a_start, double a_end, double a_c, double c, double gmax, double alpha, double rW, double W0,
+               double (&D)[Sp], double (&K)[3], double sigma[], double (&M)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+               double Gstar, double Vstar) // R/:4379-4617, F/:4665-4880
 {
     vector<double> a_space = linspace(a_start, a_end, div);
     vector<double> t_measure = sweep_time_schedule(t_max, dt);
 
     vector<D2Vec_Double> per_a;
-    riet_batch(per_a, a_space, t_measure, c, gmax, alpha, rW, W0, D, K, sigma, a_start, a_end, a_c, M, clo, dt, dx, dP, r, g, Gstar, Vstar);
+    riet_batch(per_a, a_space, t_measure, c, gmax, alpha, rW, W0, D, K, sigma, a_start, a_end, a_c, M, clo, dt, dx, dP, r, g, Gstar, Vstar, fpe);
 
     std::stringstream L, tm, d3, p1, p2, rini, Dm1, dix, geq, veq;
     L << g; tm << t_max; d3 << std::setprecision(3) << dt; p1 << a_start; p2 << a_end; rini << r;
@@ -1208,6 +1224,27 @@ void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, do
             for (size_t j = 0; j + 1 < v.size(); j++) out << std::setprecision(16) << v[j] << ",";
             out << std::setprecision(16) << v[v.size() - 1] << std::endl;
         }
+}
+} // namespace
+
+void first_order_critical_exp_delta_stochastic_MultiSp(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                       double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                       double (&)[SpB], double (&K)[3], double sigma[], double (&)[SpB][SpB],
+                                                       double (&)[SpB][SpB], double (&)[SpB], double (&M)[SpB], double[],
+                                                       int (&)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                       double Gstar, double Vstar)
+{
+    sweep_1sp(false, div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, K, sigma, M, clo, dt, dx, dP, r, g, Gstar, Vstar);
+}
+
+void first_order_critical_exp_delta_stochastic_MultiSp_FPE(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                           double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                           double (&)[SpB], double (&K)[3], double sigma[], double (&)[SpB][SpB],
+                                                           double (&)[SpB][SpB], double (&)[SpB], double (&M)[SpB], double[],
+                                                           int (&)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                           double Gstar, double Vstar)
+{
+    sweep_1sp(true, div, t_max, a_start, a_end, a_c, c, gmax, alpha, rW, W0, D, K, sigma, M, clo, dt, dx, dP, r, g, Gstar, Vstar);
 }
 
 

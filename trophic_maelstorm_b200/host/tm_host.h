@@ -160,6 +160,21 @@ void init_randbiMFTframe(double *frame, int n_fields, int g, int replicate, doub
 void init_gaussframe(double *frame, int n_fields, int n_gauss, int g, const double amp[]);
 // the sweeps' schedules (R/:4395-4459): returns t_measure and sets frame_tmeas
 std::vector<double> sweep_time_schedule(double t_max, double dt);
+// Rietkerk_FPE's runner and sweep of the same vegetation-only model (Rietkerk_FPE/rietkerk_bjork_FKE.cpp:3697, :4665 compiled with
+// -DSPB=1): same signatures; clamp `v < 1e-10 && v >= 0` (F/:4460), checkpoints at the 85 / 90 / 95 / 100 % bins only (F/:3032), the FPE
+// frame-saving rule (F/:2886, 2993), exit on a negative density (F/:4359).  BASELINE config 3's program at SPB = 1.
+void rietkerk_DorFPE_2D_MultiSp(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c,
+                                double gmax, double alpha, double rW, double W0, double (&D)[Sp], double (&v)[SpB],
+                                double (&K)[3], double sigma[], double a_st, double a_end, double a_c,
+                                double (&A)[SpB][SpB], double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB],
+                                double pR[], int (&dtV)[SpB], double clow[], double dt, double dx, double dP, int r,
+                                int g, double Gstar = -1.0, double Vstar = -1.0);
+void first_order_critical_exp_delta_stochastic_MultiSp_FPE(int div, double t_max, double a_start, double a_end, double a_c, double c,
+                                                           double gmax, double alpha, double rW, double W0, double (&D)[Sp],
+                                                           double (&v)[SpB], double (&K)[3], double sigma[], double (&A)[SpB][SpB],
+                                                           double (&H)[SpB][SpB], double (&E)[SpB], double (&M)[SpB], double pR[],
+                                                           int (&dtV)[SpB], double clo[], double dt, double dx, double dP, int r, int g,
+                                                           double Gstar = -1.0, double Vstar = -1.0);
 // burn-in frames (the reference's -DINIT=2 path): read_frame_csv parses one frame in save_frame()'s layout
 // (init_csvconstframe R/:909, header matching of init_exprtk_readCSVcolumns_frame R/:609); use_burnin_frames() makes
 // every replicate start from "<parendir><filenamePattern><r>.csv" (init_burnin_wrapper R/:836).
