@@ -58,16 +58,17 @@ def kernel_lines(sites, ms_dornic, ms_rk4, n, peak):
     return out
 
 
-def ncu_traffic_per_launch(L, trials):
-    """dram bytes per launch from the committed ncu --set full capture, if it matches this workload."""
+def ncu_traffic_per_launch(L, trials, with_source=False):
+    """dram bytes per launch from the committed ncu --set full capture, if it matches this workload (with_source: and which build
+    the capture was taken of -- the number is not measured by this run)."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
             d = json.load(fh)
         if d.get("L") == L and d.get("trials") == trials:
-            return float(d["dram_bytes_per_launch"])
+            return (float(d["dram_bytes_per_launch"]), d.get("source")) if with_source else float(d["dram_bytes_per_launch"])
     except Exception:
         pass
-    return None
+    return (None, None) if with_source else None
 
 
 class ClockSampler:
@@ -387,6 +388,8 @@ def run_ours(a):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic_per_launch(L, trials), "peak_source": peak_src,
+                     "traffic_source": "not measured by this run: " + str(ncu_traffic_per_launch(L, trials, True)[1])
+                                       + " (the kernels' memory access pattern has not changed since)",
                      "algorithmic_bytes_per_step": trials * L * L * BYTES_PER_SITE_UPDATE,
                      "kernel": "one step = tml::riet_dornic_kernel<STRICT=0> + tml::riet_step_kernel<DET=0,STRICT=0,SRC=pre,DORNIC_ONLY=0>",
                      "kernels": kernel_lines(trials * L * L, ms_dornic, ms_rk4, n_timed, peak)},
