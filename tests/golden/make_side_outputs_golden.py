@@ -96,6 +96,45 @@ def main_3sp():
         json.dump(out, f)
 
 
+def main_fpe3():
+    """Rietkerk_FPE, SPB = 3: side_outputs_fpe_3sp.json.gz from oracle/_ref/libtm_ref_fke3_files.so"""
+    import make_runner3_golden as G3
+    tmp = tempfile.mkdtemp(prefix="tmsidefpe3_")
+    os.chdir(tmp)
+    root = os.path.join(tmp, "Rietkerk") + "/"
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libtm_ref_fke3_files.so"))
+    ref.reffke3f_run.restype = C.c_uint64
+    L, r, seed, n_u = 12, 2, 97, 600000
+    dtv1, dtv2 = round(0.11817455 * 100.0) / 100.0, round(0.765270868 * 100.0) / 100.0
+    par = np.concatenate([G3.driver_par(dt=dtv1), [dtv1, dtv2]])
+    dt = par[29]
+    init = np.stack([G3.frame(L, seed + j) for j in range(r)])
+    u = uniforms(seed, n_u)
+    t_meas = np.array([0.0] + [dt * k for k in (1, 2, 3, 5, 7, 9, 12)])
+    frame_t = np.array([dt * k for k in range(1, 14)] + [1e300])
+    a_tag = "%g-%g_dP_%g_Geq_%.5g" % (par[0], par[0], 10000.0, 4.8)
+    os.makedirs(os.path.join(root, "Frames/Stochastic/3Sp", "SIDEFPE3_" + a_tag))
+    os.makedirs(os.path.join(root, "Prelims/Stochastic/3Sp", "SIDEFPE3_" + a_tag, "TimeSeries"))
+    os.makedirs(os.path.join(root, "Stochastic"))
+    derived = np.zeros((2, 8))
+    ref.reffke3f_set_params(ptr(par), C.c_int(L), ptr(derived))
+    ov = C.c_uint64()
+    cons = ref.reffke3f_run(ptr(par), C.c_int(L), C.c_int(r), ptr(init), C.c_int(r), ptr(t_meas), C.c_int(len(t_meas)), ptr(frame_t),
+                            C.c_int(len(frame_t)), ptr(u), C.c_uint64(n_u), root.encode(), b"SIDEFPE3", C.c_double(4.8), C.byref(ov))
+    assert ov.value == 0
+    files = {}
+    for dirpath, _, names in os.walk(root):
+        for nm in names:
+            p = os.path.join(dirpath, nm)
+            files[os.path.relpath(p, root)] = open(p).read()
+    print("FPE 3Sp consumed", cons, "files", len(files))
+    out = {"files": files, "par": par.tolist(), "L": L, "r": r, "t_meas": t_meas.tolist(), "frame_t": frame_t[:-1].tolist(), "seed": seed,
+           "n_u": n_u, "init": init.reshape(r, -1).tolist(), "consumed": int(cons), "Gstar": 4.8, "prefix": "SIDEFPE3",
+           "derived": derived.tolist()}
+    with gzip.open(os.path.join(HERE, "side_outputs_fpe_3sp.json.gz"), "wt") as f:
+        json.dump(out, f)
+
+
 def main():
     tmp = tempfile.mkdtemp(prefix="tmside_")
     os.chdir(tmp)
@@ -134,10 +173,14 @@ def main():
 
 
 if __name__ == "__main__":
+    if "--fpe3-only" in sys.argv:
+        main_fpe3()
+        sys.exit(0)
     if "--3sp-only" in sys.argv:
         main_3sp()
         sys.exit(0)
     if "--fpe-only" not in sys.argv:
         main()
         main_3sp()
+        main_fpe3()
     main_fpe()

@@ -163,6 +163,21 @@ class OracleStepper3(OracleStepper2):
             np.ctypeslib.as_array(veff, shape=(4 * n,))[:] = self.veff.reshape(-1)
 
 
+class OracleStepperFpe3(OracleStepper3):
+    """Rietkerk_FPE, SPB = 3: tmo_step_fpe_3sp (pinned in test_fpe_runner_oracle.py); the advection vectors are state there"""
+
+    def __init__(self, L, par, u, n_loop, derived):
+        OracleStepper3.__init__(self, L, par[:31], u, n_loop)
+        self.pv, self.pc, self.M, self.v, self.terms, self.gD, self.gV, R, self.fr1, self.fr2 = O.fpe_runner3_params(L, par, derived)
+        self.pD = (dp * 2)(O.ptr(self.gD[0]), O.ptr(self.gD[1]))
+        self.pV = (dp * 2)(O.ptr(self.gV[0]), O.ptr(self.gV[1]))
+
+    def _one_step(self, lib):
+        return lib.tmo_step_fpe_3sp(C.byref(self.pv), C.byref(self.pc), O.ptr(self.M), O.ptr(self.v), self.terms, self.pD, self.pV,
+                                    self.central.ctypes.data_as(C.POINTER(C.c_int32)), len(self.central), C.c_double(self.fr1),
+                                    C.c_double(self.fr2), C.byref(self.rng), O.ptr(self.f), O.ptr(self.gamma), O.ptr(self.veff), 1, None)
+
+
 UP = C.CFUNCTYPE(None, dp)
 RUN = C.CFUNCTYPE(None, C.c_uint32, C.c_uint32, C.c_int)
 DOWN = C.CFUNCTYPE(None, dp, dp, dp)
@@ -277,6 +292,37 @@ def test_spb3_output_tree_equals_the_reference(host, tmp_path):
     for k in sorted(want):
         assert got[k] == want[k], k
     assert any("GAM[Pr(x; t)]" in v for k, v in got.items() if "GAMMA_" in k) and np.isfinite(rows).all()
+
+
+def test_fpe_spb3_output_tree_equals_the_reference(host, tmp_path):
+    """rietkerk_DorFPE_2D_MultiSp with -DSPB=3 (F/:3697): the FPE flavour of the bookkeeping with five fields, two perception fields and
+    the per-site advection directions in the movement tables (fifteen columns walked by F/'s writer: two past the row)"""
+    with gzip.open(os.path.join(HERE, "golden", "side_outputs_fpe_3sp.json.gz"), "rt") as f:
+        g = json.load(f)
+    L, r = g["L"], g["r"]
+    par = np.array(g["par"])
+    t_meas = np.array(g["t_meas"])
+    frame_t = np.array(g["frame_t"] + [1e300])
+    init = np.array(g["init"]).reshape(r, 5, L * L)
+    u = np.random.RandomState(g["seed"]).random_sample(g["n_u"])
+    st = OracleStepperFpe3(L, par, u, _loop_iterations(t_meas[-1], par[29]), np.array(g["derived"]))
+    root = str(tmp_path) + "/"
+    rows = _side_run(host, 13, L, par, r, init, t_meas, frame_t, root, g["prefix"], g["Gstar"], st, 18)
+    st.finish_replicate()
+    assert st.rng.overflow == 0 and st.rng.pos == g["consumed"]
+    want = {_normalise(k): v for k, v in g["files"].items()}
+    got = _tree(root)
+    assert sorted(got) == sorted(want)
+    for k in sorted(want):
+        if "MOVSERIES" in k:    # F/:2758-2763 walks 3 + 4 SpB = 15 columns of a 13-column movement row: zeros here for the two beyond
+            w = [",".join(ln.split(",")[:16] + ["0", "0", ""]) for ln in want[k].splitlines()]
+            gl = got[k].splitlines()
+            assert gl[0] == want[k].splitlines()[0] and gl[1:] == w[1:], k
+        else:
+            assert got[k] == want[k], k
+    assert np.isfinite(rows).all()
+    mov = [v for k, v in got.items() if "MOVSERIES" in k][0].splitlines()
+    assert any(float(x) != 0 for x in mov[2].split(",")[10:12])           # <v_x>, <v_y> of the grazer: the drawn directions are reported
 
 
 def test_side_outputs_off(host, tmp_path):
