@@ -5,6 +5,7 @@
 #include "tm_consumer3.cuh"
 
 #include <cuda_runtime.h>
+#include <cmath>
 #include <new>
 #include <string>
 
@@ -146,6 +147,13 @@ int tm_cons3_set_fpe(tm_cons3_ctx *c, const tm_fke_terms *t, const double *const
         if (!gauss_D[s] || !gauss_V[s] || t[s].bound_D < 0 || t[s].v_row_lo < 0 || t[s].v_row_hi < 0 || t[s].v_col_lo < 0 || t[s].v_col_hi < 0 ||
             t[s].bound_D > kFkeMaxBound || vmax > kFkeMaxBound || t[s].n_gauss_D < t[s].bound_D + 1 || t[s].n_gauss_V < vmax + 1) {
             c->err = "tm_cons3_set_fpe: window bounds must lie in [0, 512] and the stencils must cover them";
+            return TM_E_ARG;
+        }
+        // every cell of consumer s is displaced by |v_s| mu_vel_prefactor_s cells (F/:3635-3637); the gather-form column pass visits
+        // (2 R + 1)^2 candidate sources per target for a largest displacement R (tm_fke.cuh), fine for the reference's fractions of a
+        // cell, quadratic beyond: refuse a configuration that would turn the pass into minutes per step instead of running it
+        if (!(fabs(c->k.v[s] * t[s].mu_vel_prefactor) <= 64.0)) {
+            c->err = "tm_cons3_set_fpe: |v| * mu_vel_prefactor exceeds 64 cells per step (the gather-form movement pass is sized for small displacements)";
             return TM_E_ARG;
         }
     }
