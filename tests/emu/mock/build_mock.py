@@ -6,7 +6,7 @@ threads).  The product sources are not touched: the rewrite happens on copies un
 Use (see README.md here): dry-run `-m gpu` tests of code that has not yet been on a GPU, at small sizes:
 
     python tests/emu/mock/build_mock.py
-    TM_LATTICE_LIB=$PWD/tests/emu/mock/libtm_lattice.so LD_PRELOAD=$PWD/tests/emu/mock/libtm_lattice.so \
+    TM_TEST_MOCK_LIB=$PWD/tests/emu/mock/libtm_lattice.so LD_PRELOAD=$PWD/tests/emu/mock/libtm_lattice.so \
         python -m pytest tests/test_zz_consumer_step3.py -m gpu
 
 Not a fallback: the library is never built by __graft_entry__.build(), lives under tests/, and nothing in trophic_maelstorm_b200/

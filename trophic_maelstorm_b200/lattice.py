@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path():
-    """The in-tree library; TM_LATTICE_LIB overrides it (kernel-variant experiments only)."""
-    return os.environ.get("TM_LATTICE_LIB") or os.path.join(_HERE, "libtm_lattice.so")
+    """The in-tree library (nothing else is ever loaded: no environment override, no fallback)."""
+    return os.path.join(_HERE, "libtm_lattice.so")
 
 
 class TmError(RuntimeError):
