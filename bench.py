@@ -18,6 +18,9 @@ roofline: algorithmic bytes (48 B per site-update: 3 fields x (8 read + 8 writte
          Dornic sweep, then the RK4 marching kernel); `roofline.kernels` times each of them with CUDA events
          recorded between the launches in a second, separate pass (tm_set_kernel_timing), with its own
          algorithmic bytes (16 B and 48 B per site: the pair moves 64 B where a fused kernel would move 48).
+other_configs / slab_L16384: the other BASELINE configurations beside the headline, measured by the same run after the headline
+         (configs 2, 3, 4 as one GPU's share each, weak; config 5 as ONE L=16384 lattice over the N ranks, strong), each under a
+         watchdog so that the headline line is printed whatever happens to them.
 """
 import argparse
 import json
@@ -35,6 +38,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 BYTES_PER_SITE_UPDATE = 48.0  # Rietkerk SPB=1, 3 fields x (8 B read + 8 B written)
 METRIC = "lattice site-updates/sec (FP64, device-timed), Rietkerk Dornic+RK4 step"
 UNIT = "site-updates/s"
+PEER_FAILED = 1.0e300  # what a rank that failed inside an extra section contributes to its peers' MAX all-reduce
+
+
+class PeerFailed(RuntimeError):
+    pass
 
 
 def measured_peaks():
@@ -415,28 +423,50 @@ def run_ours(a):
         out["cpu_baseline"] = cpu_reference(a.ref_L or L, a.ref_steps, host_cores())
         out["cpu_baseline_small_lattice"] = cpu_reference(512, 12, host_cores())
     lat.close()
-    if not a.no_slab:
-        # BASELINE config 5 beside the headline, so that every N of a scaling run carries it: ONE L=16384 lattice over the N GPUs
-        # of this run (strong scaling; N=1 is the undivided lattice, the base of the speed-up)
-        torch.cuda.empty_cache()
-        # the headline above is already measured: if this extra section does not finish in time (a stuck transport), the line is
-        # printed without it and every rank leaves
+    torch.cuda.empty_cache()
+
+    # The headline above is already measured.  The extra sections below run under a watchdog each: a section that does not finish
+    # in time is reported as skipped, the line is printed and every rank leaves.
+    def guarded(key, budget_s, fn, keep=None):
         def give_up():
             if rank == 0:
-                out["slab_L16384"] = {"error": "the row-slab section did not finish within %d s; skipped" % a.slab_budget_s}
+                out[key] = {"error": "this section did not finish within %d s; skipped" % budget_s}
                 print(json.dumps(out), flush=True)
             os._exit(0)
-        dog = threading.Timer(a.slab_budget_s, give_up)
+        dog = threading.Timer(budget_s, give_up)
         dog.daemon = True
         dog.start()
+        ok = True
         try:
-            sl = slab_measure(a, 16384, 10, 3, rank, world, local, dist)
+            r = fn()
             if rank == 0:
-                out["slab_L16384"] = {k: sl[k] for k in ("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config", "check", "comm", "e2e", "finite")}
+                out[key] = r if keep is None else {k: r[k] for k in keep}
         except Exception as e:   # the headline must still be printed
+            ok = False
             if rank == 0:
-                out["slab_L16384"] = {"error": "%s: %s" % (type(e).__name__, e)}
+                out[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+            if dist is not None and not isinstance(e, PeerFailed):
+                try:             # the peers are inside a one-element MAX all-reduce of this section: make theirs fail too
+                    t = torch.tensor([PEER_FAILED], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                except Exception:
+                    pass
         dog.cancel()
+        return ok
+
+    all_ok = True
+    if not a.no_other_configs:
+        # BASELINE configs 2, 3 (one GPU's share) and 4 (one GPU's share) beside the headline
+        all_ok = guarded("other_configs", a.other_budget_s, lambda: other_configs_measure(rank, world, local, dist))
+        torch.cuda.empty_cache()
+    if not a.no_slab and dist is not None and not all_ok:
+        if rank == 0:
+            out["slab_L16384"] = {"error": "skipped: the other_configs section failed on a rank (the ranks' collectives may be out of step)"}
+    elif not a.no_slab:
+        # BASELINE config 5 beside the headline, so that every N of a scaling run carries it: ONE L=16384 lattice over the N GPUs
+        # of this run (strong scaling; N=1 is the undivided lattice, the base of the speed-up)
+        guarded("slab_L16384", a.slab_budget_s, lambda: slab_measure(a, 16384, 10, 3, rank, world, local, dist),
+                keep=("value", "unit", "n_gpus", "steps", "ms_per_step", "scaling", "config", "check", "comm", "e2e", "finite"))
     if rank == 0:
         print(json.dumps(out), flush=True)
     if dist is not None:
@@ -447,6 +477,107 @@ def run_ours(a):
         dist.barrier()
         dist.destroy_process_group()
         bye.cancel()
+
+
+def other_configs_measure(rank, world, local, dist, shapes=((256, 16), (1024, 32), (2048, 8)), K=20, W=5):
+    """BASELINE configs 2, 3 and 4 beside the headline, so that the driver's own runs carry them (each N of a scaling run included):
+    every rank steps its share, no data-path collective, CUDA events on the kernel stream, max over ranks, whole-job value.
+      rietkerk_L256x16      config 2: Rietkerk SPB=1, L=256, 16 trials per GPU (state fits the L2: timed warm AND with an L2 flush
+                            between single steps)
+      rietkerk_fpe_L1024x32 config 3's share of one GPU: Rietkerk_FPE clamp rule (1e-10 / 0, F/:4460), L=1024, 32 trials per GPU
+                            (256 trials at N=8)
+      dp_L2048x8            config 4's share of one GPU: DP Dornic step, L=2048, 8 a-values in [1.0524, 1.0554] per GPU
+    Not the headline; same kernels, same ABI."""
+    import numpy as np
+    import torch
+    import oracle_lib as O          # the synthetic frame rule only
+    import trophic_maelstorm_b200 as tm
+
+    peak, _ = measured_peaks()
+
+    def maxr(x):       # the only collective of this section (so that a failing rank can be told apart, see run_ours.guarded)
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        v = float(t.item())
+        if v >= PEER_FAILED:
+            raise PeerFailed("another rank failed in this section")
+        return v
+
+    def barrier(lat):
+        lat.sync()
+        maxr(0.0)
+
+    def timed(lat, sites_per_rank, bytes_per_site, flush):
+        lat.step(W)
+        barrier(lat)
+        lat.step(K)
+        lat.sync()
+        ms, n_launch = lat.last_step_ms()
+        ms = maxr(ms)
+        r = {"value": world * sites_per_rank * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+             "ms_per_step": ms / K, "scaling": "weak", "dtype": "f64", "data": "synthetic", "gpu_launches": n_launch,
+             "roofline_frac": sites_per_rank * bytes_per_site / (ms * 1e-3 / K) / 1e9 / peak}
+        if flush:
+            # the state fits the 126 MB L2: single steps with a 256 MB write in between (timing rule: flush or exceed the L2)
+            junk = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device="cuda")
+            msf = 0.0
+            for _ in range(K):
+                junk.fill_(1)
+                torch.cuda.synchronize()
+                lat.step(1)
+                lat.sync()
+                msf += lat.last_step_ms()[0]
+            del junk
+            msf = maxr(msf)
+            r["l2_flushed"] = {"value": world * sites_per_rank * K / (msf * 1e-3), "ms_per_step": msf / K,
+                               "roofline_frac": sites_per_rank * bytes_per_site / (msf * 1e-3 / K) / 1e9 / peak}
+        st = lat.measure()
+        r["finite"] = all(s.nonfinite == 0 for s in st)
+        return r
+
+    out = {}
+
+    def riet(key, L, trials, fpe, what):
+        lat = tm.Lattice(tm.rietkerk_params(L, fpe_clamp=fpe), trials, device=local)
+        try:
+            lat.seed(20261019, trial0=rank * trials)
+            base = [O.synthetic_rietkerk_frame(L, seed=777 + k, fringe=False) for k in range(min(trials, 4))]
+            frames = np.empty((trials, 3, L, L))
+            for t in range(trials):
+                frames[t] = base[t % len(base)]     # four distinct speckle frames; every trial has its own Philox stream
+            lat.upload(frames)
+            state_mib = trials * 3 * L * L * 8 / 2 ** 20
+            fits = trials * 3 * L * L * 8 * 2 <= 126e6
+            r = timed(lat, float(trials) * L * L, BYTES_PER_SITE_UPDATE, fits)
+            r["config"] = {"workload": what % (L, trials),
+                           "l2": ("state %.0f MiB per GPU (x2 ping-pong) fits the 126 MB L2: `value` is warm, `l2_flushed` has a 256 MB "
+                                  "write between single steps" if fits else
+                                  "state %.0f MiB per GPU (x2 ping-pong) exceeds the 126 MB L2; no flush needed") % state_mib}
+            out[key] = r
+        finally:
+            lat.close()
+
+    riet("rietkerk_L%dx%d" % shapes[0], shapes[0][0], shapes[0][1], False, "BASELINE config 2: Rietkerk SPB=1 Dornic+RK4 step, L=%d, %d trials per GPU")
+    riet("rietkerk_fpe_L%dx%d" % shapes[1], shapes[1][0], shapes[1][1], True,
+         "BASELINE config 3 (one GPU's share; 256 trials at N=8): Rietkerk_FPE SPB=1 step (clamp 1e-10 / 0), L=%d, %d trials per GPU")
+    L, n_a = shapes[2]
+    lat = tm.Lattice(tm.dp_params(L, a=1.0524, b=1.0, D=0.25, sigma=2 ** 0.5, dt=0.1, dx=1.0), n_a, device=local)
+    try:
+        for i, av in enumerate(np.linspace(1.0524, 1.0554, n_a)):
+            lat.set_trial_a(i, float(av))
+        lat.seed(7, trial0=rank * n_a)
+        lat.upload(np.ones((n_a, 1, L, L)))
+        r = timed(lat, float(n_a) * L * L, 16.0, False)
+        r["metric"] = "lattice site-updates/sec (FP64, device-timed), DP Dornic step"
+        r["config"] = {"workload": "BASELINE config 4 (one GPU's share): DP Dornic step (percolationDornic_2D), L=%d, %d a-values in "
+                                   "[1.0524, 1.0554] per GPU, rho0=1; 16 B per site-update, sampler-bound by construction" % (L, n_a),
+                       "l2": "state %.0f MiB per GPU (x2 ping-pong) exceeds the 126 MB L2; no flush needed" % (n_a * L * L * 8 / 2 ** 20)}
+        out["dp_L%dx%d" % (L, n_a)] = r
+    finally:
+        lat.close()
+    return out
 
 
 def slab_measure(a, L, K, W, rank, world, local, dist):
@@ -737,6 +868,8 @@ def main():
     ap.add_argument("--sustain-s", type=float, default=2.0, help="seconds of back-to-back steps for the sustained figure")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-slab", action="store_true", help="skip the L=16384 row-slab line (BASELINE config 5) the default run carries under 'slab_L16384'")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE config 2-4 lines the default run carries under 'other_configs'")
+    ap.add_argument("--other-budget-s", type=int, default=90, help="wall-clock budget of the other-configs section of the default run")
     ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke", "spb2", "slab"],
                     help="dp, fke, spb2: extra, non-headline lines; slab: BASELINE config 5, one L=16384 lattice over the ranks (strong scaling)")
     ap.add_argument("--slab-transport", default="nccl", choices=["peer", "nccl"],
