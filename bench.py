@@ -459,6 +459,17 @@ def run_ours(a):
         # BASELINE configs 2, 3 (one GPU's share) and 4 (one GPU's share) beside the headline
         all_ok = guarded("other_configs", a.other_budget_s, lambda: other_configs_measure(rank, world, local, dist))
         torch.cuda.empty_cache()
+    if not a.no_other_configs and world == 1:
+        # SURVEY 8 f2 beside the headline: the FKE movement step at L=4096 with the reference's own CUDA kernel timed on the same
+        # buffers (run_fke_extra), in a process of its own: a kernel that is not the product's runs there, not here
+        def fke_sub():
+            cmd = [sys.executable, os.path.abspath(__file__), "--workload", "fke", "--L", "4096", "--steps", "10", "--warmup", "3"]
+            pr = subprocess.run(cmd, capture_output=True, text=True, timeout=max(10, a.other_budget_s - 10))
+            lines = [l for l in pr.stdout.splitlines() if l.startswith("{")]
+            if pr.returncode != 0 or not lines:
+                raise RuntimeError("bench.py --workload fke: rc %d: %s" % (pr.returncode, (pr.stderr or "").strip()[-300:]))
+            return json.loads(lines[-1])
+        guarded("fke_movement_L4096", a.other_budget_s, fke_sub)
     if not a.no_slab and dist is not None and not all_ok:
         if rank == 0:
             out["slab_L16384"] = {"error": "skipped: the other_configs section failed on a rank (the ranks' collectives may be out of step)"}
@@ -795,6 +806,50 @@ def run_fke_extra(a):
         tc = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": Lc * Lc / tc, "unit": "sites/s", "cores": 1, "kind": kind,
                                 "sample": "advdiff_FKE_MultiSp on the L=%d corner of the same inputs, one call (the reference's loop is serial)" % Lc}
+    # the reference's OWN CUDA kernel on the same device buffers (updateMovement, kernel_advdiff_FKE2D.cu:92-180, compiled unmodified
+    # for sm_100a into oracle/_ref/libtm_ref_fke_gpu.so): a reported baseline beside the product's three kernels
+    refgpu = os.path.join(ROOT, "oracle", "_ref", "libtm_ref_fke_gpu.so")
+    if os.path.exists(refgpu):
+        try:
+            rg = C.CDLL(refgpu)
+            rg.ref_fke_gpu_setup.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double]
+            rg.ref_fke_gpu_move.argtypes = [C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+            m.move_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), out.data_ptr())
+            m.sync()
+            ours = out.clone()
+            sD, sV = torch.from_numpy(gD).to(dev), torch.from_numpy(gV).to(dev)
+            tsar = torch.empty(L * L, dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()
+            # the reference's set-up prints its constants with printf: keep this program's stdout to the one JSON line
+            libc = C.CDLL(None)
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                rc = rg.ref_fke_gpu_setup(bD, bV, bV, pref)
+                libc.fflush(None)
+            finally:
+                os.dup2(saved, 1)
+                os.close(saved)
+            ms_r, ms_k = C.c_float(0), C.c_float(0)
+            if rc == 0:
+                rc = rg.ref_fke_gpu_move(L, d[0].data_ptr(), tsar.data_ptr(), d[1].data_ptr(), d[2].data_ptr(), sD.data_ptr(), sV.data_ptr(),
+                                         W, C.byref(ms_r), C.byref(ms_k))
+            if rc == 0:
+                rc = rg.ref_fke_gpu_move(L, d[0].data_ptr(), tsar.data_ptr(), d[1].data_ptr(), d[2].data_ptr(), sD.data_ptr(), sV.data_ptr(),
+                                         K, C.byref(ms_r), C.byref(ms_k))
+            if rc != 0:
+                raise RuntimeError("cudaError_t %d from the reference kernel's harness" % rc)
+            diff = float((tsar - ours).abs().max().item()) / max(float(ours.abs().max().item()), 1e-300)
+            line["reference_gpu_baseline"] = {
+                "kernel": "updateMovement (Rietkerk_FPE/kernel_advdiff_FKE2D.cu:92-180), unmodified, sm_100a, FP64 atomics",
+                "ms_per_step": ms_r.value, "ms_kernel_only": ms_k.value, "value": L * L / (ms_r.value * 1e-3), "unit": "sites/s",
+                "steps": K, "reference_ms_over_product_ms": ms_r.value / ms,
+                "max_abs_diff_over_max": diff,
+                "note": "same device buffers; per step the reference zeroes Rho_tsar and launches once (F/:4282-4299 without its host "
+                        "copies); the product's step is its three launches"}
+        except Exception as e:
+            line["reference_gpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line), flush=True)
     m.close()
 
