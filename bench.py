@@ -460,16 +460,21 @@ def run_ours(a):
         all_ok = guarded("other_configs", a.other_budget_s, lambda: other_configs_measure(rank, world, local, dist))
         torch.cuda.empty_cache()
     if not a.no_other_configs and world == 1:
-        # SURVEY 8 f2 beside the headline: the FKE movement step at L=4096 with the reference's own CUDA kernel timed on the same
-        # buffers (run_fke_extra), in a process of its own: a kernel that is not the product's runs there, not here
-        def fke_sub():
-            cmd = [sys.executable, os.path.abspath(__file__), "--workload", "fke", "--L", "4096", "--steps", "10", "--warmup", "3"]
-            pr = subprocess.run(cmd, capture_output=True, text=True, timeout=max(10, a.other_budget_s - 10))
-            lines = [l for l in pr.stdout.splitlines() if l.startswith("{")]
-            if pr.returncode != 0 or not lines:
-                raise RuntimeError("bench.py --workload fke: rc %d: %s" % (pr.returncode, (pr.stderr or "").strip()[-300:]))
-            return json.loads(lines[-1])
-        guarded("fke_movement_L4096", a.other_budget_s, fke_sub)
+        # The two "next" rows of SURVEY 8 that have a bench workload of their own, beside the headline, each in a process of its own:
+        #   fke_movement_L4096  f2: the FKE movement step, with the reference's own CUDA kernel timed on the same buffers (a kernel
+        #                       that is not the product's runs in that process, not in this one)
+        #   spb2_step_L4096     f3: the vegetation + grazer (SPB = 2) time step resident on the device
+        def sub(workload):
+            def run():
+                cmd = [sys.executable, os.path.abspath(__file__), "--workload", workload, "--L", "4096", "--steps", "10", "--warmup", "3"]
+                pr = subprocess.run(cmd, capture_output=True, text=True, timeout=max(10, a.other_budget_s - 10))
+                lines = [l for l in pr.stdout.splitlines() if l.startswith("{")]
+                if pr.returncode != 0 or not lines:
+                    raise RuntimeError("bench.py --workload %s: rc %d: %s" % (workload, pr.returncode, (pr.stderr or "").strip()[-300:]))
+                return json.loads(lines[-1])
+            return run
+        guarded("fke_movement_L4096", a.other_budget_s, sub("fke"))
+        guarded("spb2_step_L4096", a.other_budget_s, sub("spb2"))
     if not a.no_slab and dist is not None and not all_ok:
         if rank == 0:
             out["slab_L16384"] = {"error": "skipped: the other_configs section failed on a rank (the ranks' collectives may be out of step)"}
