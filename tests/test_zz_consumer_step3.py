@@ -86,10 +86,10 @@ def follow(one_step, pv, pg1, pg2, pc, central, fr1, fr2, f, nsteps, seed):
     return fp, gp
 
 
-def test_emulated_step3_follows_the_oracle(emu):
-    L = 16
+@pytest.mark.parametrize("L,nsteps", [(16, 2), (150, 1)])   # 150: two column tiles per lattice row, the second one 22 columns wide
+def test_emulated_step3_follows_the_oracle(emu, L, nsteps):
     par, pv, pg1, pg2, pc, central, fr1, fr2, f = setup(L, 7)
-    follow(lambda f_, g_, s: emu_step(emu, L, par, central, fr1, fr2, f_, g_, s, 99), pv, pg1, pg2, pc, central, fr1, fr2, f, 2, 99)
+    follow(lambda f_, g_, s: emu_step(emu, L, par, central, fr1, fr2, f_, g_, s, 99), pv, pg1, pg2, pc, central, fr1, fr2, f, nsteps, 99)
 
 
 @pytest.mark.parametrize("gs,ps", [(1.0, 0.0), (0.0, 1.0)])

@@ -79,12 +79,11 @@ def follow(one_step, pv, pc, M1, terms, gD, gV, central, fr, f, nsteps, seed):
     return fp, gp
 
 
-@pytest.mark.parametrize("rk4_stages", [0, 1])
-def test_emulated_fpe_step_follows_the_oracle(emu, rk4_stages):
-    L = 16
+@pytest.mark.parametrize("L,nsteps,rk4_stages", [(16, 2, 0), (16, 2, 1), (150, 1, 0), (150, 1, 1)])   # 150: two column tiles per row, 6 x 6 fused-RK4 tiles
+def test_emulated_fpe_step_follows_the_oracle(emu, L, nsteps, rk4_stages):
     par, derived, pv, pc, M1, terms, gD, gV, central, fr, f = setup(L, 7)
     follow(lambda f_, g_, s: emu_step(emu, L, par, derived, central, fr, gD, gV, f_, g_, s, 99, rk4_stages),
-           pv, pc, M1, terms, gD, gV, central, fr, f, 2, 99)
+           pv, pc, M1, terms, gD, gV, central, fr, f, nsteps, 99)
 
 
 def test_emulated_fpe_step_without_grazers_and_without_vegetation(emu):

@@ -86,13 +86,13 @@ def follow(one_step, pv, pc, M, v, terms, gD, gV, central, fr1, fr2, f, nsteps, 
     return fp, gp
 
 
-@pytest.mark.parametrize("pred_scale", [1.0, 0.0])
-def test_emulated_fpe_step3_follows_the_oracle(emu, pred_scale):
-    """all three species; and with the predators gone (gamma_2 = 1 everywhere, F/:3430; the grazer's disc sum undiscounted)"""
-    L = 16
+@pytest.mark.parametrize("L,nsteps,pred_scale", [(16, 2, 1.0), (16, 2, 0.0), (150, 1, 1.0)])
+def test_emulated_fpe_step3_follows_the_oracle(emu, L, nsteps, pred_scale):
+    """all three species; with the predators gone (gamma_2 = 1 everywhere, F/:3430; the grazer's disc sum undiscounted); and L = 150: two
+    column tiles per lattice row"""
     par, derived, pv, pc, M, v, terms, gD, gV, central, fr1, fr2, f = setup(L, 7, pred_scale)
     fp, gp = follow(lambda f_, g_, s: emu_step(emu, L, par, derived, central, fr1, fr2, gD, gV, f_, g_, s, 99),
-                    pv, pc, M, v, terms, gD, gV, central, fr1, fr2, f, 2, 99)
+                    pv, pc, M, v, terms, gD, gV, central, fr1, fr2, f, nsteps, 99)
     if pred_scale == 0.0:
         assert np.all(gp[1] == 1.0) and np.all(fp[2] == 0.0)
 
