@@ -142,7 +142,7 @@ def product_setup(L, par, central, fr1, fr2):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("L,gs,ps", [(18, 1.0, 1.0), (96, 1.0, 1.0), (32, 1.0, 0.0), (32, 0.0, 1.0)])
+@pytest.mark.parametrize("L,gs,ps", [(18, 1.0, 1.0), (96, 1.0, 1.0), (32, 1.0, 0.0), (32, 0.0, 1.0), (150, 1.0, 1.0)])
 def test_gpu_step3_follows_the_oracle(L, gs, ps):
     par, pv, pg1, pg2, pc, central, fr1, fr2, f = setup(L, 7, graz_scale=gs, pred_scale=ps)
     ops = product_setup(L, par, central, fr1, fr2)

@@ -114,7 +114,7 @@ def product_setup(L, par, derived, central, fr, gD, gV):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("L,rk4_stages", [(20, 0), (20, 1), (96, 0)])
+@pytest.mark.parametrize("L,rk4_stages", [(20, 0), (20, 1), (96, 0), (150, 0)])
 def test_gpu_fpe_step_follows_the_oracle(L, rk4_stages):
     par, derived, pv, pc, M1, terms, gD, gV, central, fr, f = setup(L, 7)
     ops = product_setup(L, par, derived, central, fr, gD, gV)

@@ -118,7 +118,7 @@ def product_setup(L, par, derived, central, fr1, fr2, gD, gV):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("L,pred_scale", [(16, 1.0), (96, 1.0), (32, 0.0)])
+@pytest.mark.parametrize("L,pred_scale", [(16, 1.0), (96, 1.0), (32, 0.0), (150, 1.0)])
 def test_gpu_fpe_step3_follows_the_oracle(L, pred_scale):
     par, derived, pv, pc, M, v, terms, gD, gV, central, fr1, fr2, f = setup(L, 7, pred_scale)
     ops = product_setup(L, par, derived, central, fr1, fr2, gD, gV)
