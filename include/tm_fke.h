@@ -68,7 +68,10 @@ int tm_fke_sync(tm_fke_ctx *);
 void *tm_fke_cuda_stream(tm_fke_ctx *);
 /* Device time (ms, CUDA events on the ctx stream) of the kernels of the last move call, and how many launches that was. */
 int tm_fke_last_ms(tm_fke_ctx *, float *ms, int *n_launches);
-/* max |displacement| (rows, columns) found by the last move of species s: the gather radius it used. */
+/* max |displacement| (rows, columns) found by the last move of species s: the gather radius it used.  A displacement beyond 64 cells
+ * on either axis (|v_eff * mu_vel_prefactor| > 64: three orders of magnitude above what the reference's constants give) is refused by
+ * the column pass: the moved field of that species comes back as NaN and this call reports the offending radius.  The reference's
+ * scatter (kernel_advdiff_FKE2D.cu:119-121) has no such limit; the gather form would visit (2 R + 1)^2 sources per target. */
 int tm_fke_last_displacement(tm_fke_ctx *, int s, int32_t out[2]);
 
 #ifdef __cplusplus

@@ -77,6 +77,22 @@ def test_emulated_kernels_match_oracle(emu, L, bD, rows, cols, pref, vmax):
     assert rel_err(got, want) <= TOL
 
 
+def test_emulated_kernels_refuse_displacements_beyond_the_bound(emu):
+    """kFkeMaxDisp (tm_fke.cuh): one site displaced by 70 cells makes the column pass refuse -- the moved field is NaN everywhere (loud),
+    nothing is gathered (the pass would visit (2 R + 1)^2 candidate sources per target); 64 cells are still served and equal the oracle."""
+    L, bD, rows, cols, pref = 200, 1, (1, 1), (1, 1), 1.0
+    rho, gamma, veff = random_inputs(L, 11, 0.4)
+    rho[5 * L + 7] = 3.0
+    gD = O.fke_gaussian(1.0, bD); gV = O.fke_gaussian(1.0, 1)
+    veff[5 * L + 7] = (70.0, 0.0)
+    got, md = emu_move(emu, L, bD, rows, cols, pref, 1e-10, rho, gamma, veff, gD, gV)
+    assert md[0] == 70 and np.isnan(got).all()
+    veff[5 * L + 7] = (64.0, -64.0)
+    got, md = emu_move(emu, L, bD, rows, cols, pref, 1e-10, rho, gamma, veff, gD, gV)
+    assert md == (64, 64)
+    assert rel_err(got, O.fke_move(L, bD, rows, cols, pref, 1e-10, rho, gamma, veff, gD, gV)) <= TOL
+
+
 def test_abi_exports_fke_symbols():
     lib = tm.lib()
     for name in tm.FKE_ABI_SYMBOLS:

@@ -22,6 +22,7 @@
 // to a few ulp.  HBM-bound: 32 B read + 8 B written per site algorithmically; the three passes move ~130 B.
 #pragma once
 #include <stdint.h>
+#include <math.h>
 
 #if defined(__CUDACC__)
 #define TMF_D __device__ __forceinline__
@@ -57,6 +58,11 @@ struct FkeArgs {
 
 constexpr int kFkeThreads = 128;        // columns per CTA in the two convolution passes
 constexpr int kFkeMaxBound = 512;       // largest stencil half-width supported (shared-memory tile)
+constexpr int kFkeMaxDisp = 64;         // largest |displacement| (cells per step, either axis) the gather-form column pass accepts: it
+                                        // visits (2 R_x + 1)(2 R_y + 1) candidate sources per target, fine for the reference's fractions
+                                        // of a cell, minutes per step for an outlier of hundreds of cells.  Beyond it the pass REFUSES:
+                                        // the moved field comes back as NaN (the runners' non-finite guards then stop the run, as the
+                                        // reference's own numerical-failure exit does) instead of occupying the GPU.
 
 TMF_D int fke_pack(int ex, int ey) { return (ex & 0xFFFF) | (int)((unsigned)ey << 16); }
 TMF_D int fke_mod(int a, int g) { int r = a % g; return r < 0 ? r + g : r; }
@@ -123,6 +129,11 @@ TMF_G void fke_cols_kernel(const FkeArgs A)
     for (int k = tid; k <= t.bD; k += kFkeThreads) gD[k] = A.gD[k];
     for (int k = tid; k < nV; k += kFkeThreads) gV[k] = A.gV[k];
     const int Rx = A.maxdisp[0], Ry = A.maxdisp[1];
+    if (Rx > kFkeMaxDisp || Ry > kFkeMaxDisp) {            // uniform over the launch (see kFkeMaxDisp): poison, do not gather
+        const int yq = y0 + tid;
+        if (yq < g) { A.U1[x * g + yq] = nan(""); A.U2[x * g + yq] = nan(""); }
+        return;
+    }
     // Index arithmetic: 32-bit throughout (L <= 32767, so L*L < 2^30) and periodic indices walked with a conditional
     // wrap -- an integer division and a 64-bit address per candidate source made this pass instruction-bound
     // (1100 warp instructions per 32 sites, 0.85 ms at L = 4096).  Candidates are read unconditionally and selected,
