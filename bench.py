@@ -45,6 +45,41 @@ class PeerFailed(RuntimeError):
     pass
 
 
+def run_guarded(out, rank, dist, key, budget_s, fn, keep=None):
+    """One extra section of the default run (the headline in `out` is already measured).  `fn` runs under a watchdog and a `try`:
+    its result (rank 0: the whole dict, or the keys in `keep`) goes to out[key]; an exception is reported there as {"error": ...}; a
+    section that does not finish within `budget_s` seconds is reported as skipped, the ONE JSON line is printed by rank 0 and every
+    rank leaves (exit code 0).  Returns False when the section failed on this rank.  With several ranks a failing rank contributes
+    PEER_FAILED to the one-element MAX all-reduce its peers are in (the only collective an extra section may use), so that they fail
+    at the same point instead of waiting for it."""
+    def give_up():
+        if rank == 0:
+            out[key] = {"error": "this section did not finish within %d s; skipped" % budget_s}
+            print(json.dumps(out), flush=True)
+        os._exit(0)
+    dog = threading.Timer(budget_s, give_up)
+    dog.daemon = True
+    dog.start()
+    ok = True
+    try:
+        r = fn()
+        if rank == 0:
+            out[key] = r if keep is None else {k: r[k] for k in keep}
+    except Exception as e:   # the headline must still be printed
+        ok = False
+        if rank == 0:
+            out[key] = {"error": "%s: %s" % (type(e).__name__, e)}
+        if dist is not None and not isinstance(e, PeerFailed):
+            try:
+                import torch
+                t = torch.tensor([PEER_FAILED], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            except Exception:
+                pass
+    dog.cancel()
+    return ok
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -425,34 +460,8 @@ def run_ours(a):
     lat.close()
     torch.cuda.empty_cache()
 
-    # The headline above is already measured.  The extra sections below run under a watchdog each: a section that does not finish
-    # in time is reported as skipped, the line is printed and every rank leaves.
     def guarded(key, budget_s, fn, keep=None):
-        def give_up():
-            if rank == 0:
-                out[key] = {"error": "this section did not finish within %d s; skipped" % budget_s}
-                print(json.dumps(out), flush=True)
-            os._exit(0)
-        dog = threading.Timer(budget_s, give_up)
-        dog.daemon = True
-        dog.start()
-        ok = True
-        try:
-            r = fn()
-            if rank == 0:
-                out[key] = r if keep is None else {k: r[k] for k in keep}
-        except Exception as e:   # the headline must still be printed
-            ok = False
-            if rank == 0:
-                out[key] = {"error": "%s: %s" % (type(e).__name__, e)}
-            if dist is not None and not isinstance(e, PeerFailed):
-                try:             # the peers are inside a one-element MAX all-reduce of this section: make theirs fail too
-                    t = torch.tensor([PEER_FAILED], dtype=torch.float64, device="cuda")
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                except Exception:
-                    pass
-        dog.cancel()
-        return ok
+        return run_guarded(out, rank, dist, key, budget_s, fn, keep)
 
     all_ok = True
     if not a.no_other_configs:
