@@ -504,7 +504,7 @@ def run_ours(a):
         bye.cancel()
 
 
-def other_configs_measure(rank, world, local, dist, shapes=((256, 16), (1024, 32), (2048, 8)), K=20, W=5):
+def other_configs_measure(rank, world, local, dist, shapes=((256, 16), (1024, 32), (2048, 8), (4096, 1)), K=20, W=5):
     """BASELINE configs 2, 3 and 4 beside the headline, so that the driver's own runs carry them (each N of a scaling run included):
     every rank steps its share, no data-path collective, CUDA events on the kernel stream, max over ranks, whole-job value.
       rietkerk_L256x16      config 2: Rietkerk SPB=1, L=256, 16 trials per GPU (state fits the L2: timed warm AND with an L2 flush
@@ -512,6 +512,9 @@ def other_configs_measure(rank, world, local, dist, shapes=((256, 16), (1024, 32
       rietkerk_fpe_L1024x32 config 3's share of one GPU: Rietkerk_FPE clamp rule (1e-10 / 0, F/:4460), L=1024, 32 trials per GPU
                             (256 trials at N=8)
       dp_L2048x8            config 4's share of one GPU: DP Dornic step, L=2048, 8 a-values in [1.0524, 1.0554] per GPU
+      rietkerk_L4096x1_fringe  the headline workload on a frame with an extinction fringe (an eighth of the columns empty, a
+                            sixteenth at densities 1e-5..1e-1: the exact Poisson / Gamma samplers' regime, riet_cell_exact in the
+                            Dornic sweep's second walk), which the headline's all-vegetated frame never enters
     Not the headline; same kernels, same ABI."""
     import numpy as np
     import torch
@@ -564,11 +567,11 @@ def other_configs_measure(rank, world, local, dist, shapes=((256, 16), (1024, 32
 
     out = {}
 
-    def riet(key, L, trials, fpe, what):
+    def riet(key, L, trials, fpe, what, fringe=False):
         lat = tm.Lattice(tm.rietkerk_params(L, fpe_clamp=fpe), trials, device=local)
         try:
             lat.seed(20261019, trial0=rank * trials)
-            base = [O.synthetic_rietkerk_frame(L, seed=777 + k, fringe=False) for k in range(min(trials, 4))]
+            base = [O.synthetic_rietkerk_frame(L, seed=777 + k, fringe=fringe) for k in range(min(trials, 4))]
             frames = np.empty((trials, 3, L, L))
             for t in range(trials):
                 frames[t] = base[t % len(base)]     # four distinct speckle frames; every trial has its own Philox stream
@@ -587,6 +590,9 @@ def other_configs_measure(rank, world, local, dist, shapes=((256, 16), (1024, 32
     riet("rietkerk_L%dx%d" % shapes[0], shapes[0][0], shapes[0][1], False, "BASELINE config 2: Rietkerk SPB=1 Dornic+RK4 step, L=%d, %d trials per GPU")
     riet("rietkerk_fpe_L%dx%d" % shapes[1], shapes[1][0], shapes[1][1], True,
          "BASELINE config 3 (one GPU's share; 256 trials at N=8): Rietkerk_FPE SPB=1 step (clamp 1e-10 / 0), L=%d, %d trials per GPU")
+    riet("rietkerk_L%dx%d_fringe" % shapes[3], shapes[3][0], shapes[3][1], False,
+         "the headline workload (Rietkerk SPB=1 Dornic+RK4 step, L=%d, %d trial per GPU) on a frame with an extinction fringe: 12.5 %% of the "
+         "columns empty, 6.25 %% at densities 1e-5..1e-1 (exact Poisson / Gamma samplers)", fringe=True)
     L, n_a = shapes[2]
     lat = tm.Lattice(tm.dp_params(L, a=1.0524, b=1.0, D=0.25, sigma=2 ** 0.5, dt=0.1, dx=1.0), n_a, device=local)
     try:

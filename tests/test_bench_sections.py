@@ -40,5 +40,5 @@ def test_watchdog_prints_the_line_and_exits_zero():
 def test_default_run_names_every_baseline_config():
     """the section keys the default run carries exist in the source the driver executes"""
     src = open(os.path.join(ROOT, "bench.py")).read()
-    for key in ('"other_configs"', '"fke_movement_L4096"', '"spb2_step_L4096"', '"slab_L16384"', "rietkerk_L%dx%d", "rietkerk_fpe_L%dx%d", "dp_L%dx%d"):
+    for key in ('"other_configs"', '"fke_movement_L4096"', '"spb2_step_L4096"', '"slab_L16384"', "rietkerk_L%dx%d", "rietkerk_fpe_L%dx%d", "dp_L%dx%d", "rietkerk_L%dx%d_fringe"):
         assert key in src, key
