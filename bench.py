@@ -944,7 +944,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-slab", action="store_true", help="skip the L=16384 row-slab line (BASELINE config 5) the default run carries under 'slab_L16384'")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the BASELINE config 2-4 lines the default run carries under 'other_configs'")
-    ap.add_argument("--other-budget-s", type=int, default=90, help="wall-clock budget of the other-configs section of the default run")
+    ap.add_argument("--other-budget-s", type=int, default=180, help="wall-clock budget of the other-configs section of the default run")
     ap.add_argument("--workload", default="rietkerk", choices=["rietkerk", "dp", "fke", "spb2", "slab"],
                     help="dp, fke, spb2: extra, non-headline lines; slab: BASELINE config 5, one L=16384 lattice over the ranks (strong scaling)")
     ap.add_argument("--slab-transport", default="nccl", choices=["peer", "nccl"],
