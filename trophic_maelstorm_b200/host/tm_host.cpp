@@ -16,6 +16,7 @@
 #include <stdexcept>
 #include <thread>
 #include <sys/stat.h>
+#include <dirent.h>
 
 namespace tm_b200 {
 
@@ -1011,8 +1012,50 @@ static void default_init_frame_noise_off(double *f, int g, int replicate, double
 }
 std::function<void(double *, int, int, double, const double[], const double[])> init_frame_noise_off = default_init_frame_noise_off;
 
+bool write_noise_off_frames = true;
+
+// The snapshot the noise-off runner saves at a measurement row (R/:1959-1972, through save_frame R/:2836): the name grammar of R/:1962-1971
+// with its stream precisions, the reference's header for this runner, rows `a,i,P,W,O` at the default 6-digit precision.  As in the
+// reference the folder is NOT created here (the driver main makes "<a_st>-<a_end>_dP_<dP>" with the default precision of dP, the runner
+// names it with setprecision(3): for dP = 10000 the two differ and the reference writes no frames, only its error line) and an existing
+// file is never overwritten: the replicate suffix becomes (largest suffix present) + 1 (findMaxRepNo R/:1544).
+static void save_noise_off_frame(const double *frame, double a, double a_st, double a_end, double t, double dt, double dx, double dP,
+                                 double D0, double D1, double alpha, double gmax, int j, int g)
+{
+    std::stringstream L, tm, d3, p1, rini, gm, a1, a2, Dm0, Dm1, alph, dix, dimitri;
+    L << g; tm << t; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a; dix << std::setprecision(2) << dx;
+    rini << j; Dm0 << std::setprecision(3) << D0; Dm1 << std::setprecision(3) << D1; gm << std::setprecision(3) << gmax;
+    alph << std::setprecision(3) << alpha; dimitri << std::setprecision(3) << dP; a1 << a_st; a2 << a_end;
+    const std::string parendir = options().data_root + "/Data/Rietkerk/Frames/Non-Stochastic/" + a1.str() + "-" + a2.str() + "_dP_" + dimitri.str();
+    const std::string pattern = "FRAME_RAND_Basic_P_c_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str() + "_D0_" + Dm0.str()
+                              + "_D1_" + Dm1.str() + "_dx_" + dix.str() + "_alph_" + alph.str() + "_gmax_" + gm.str() + "_R_";
+    std::string filename = parendir + "/" + pattern + rini.str() + ".csv";
+    struct stat sb;
+    if (stat(filename.c_str(), &sb) == 0) {
+        int max_rep = 0;
+        if (DIR *dir = opendir(parendir.c_str())) {
+            while (struct dirent *e = readdir(dir)) {
+                const std::string name = e->d_name;
+                if (name.size() <= pattern.size() + 4 || name.compare(0, pattern.size(), pattern) != 0 || name.compare(name.size() - 4, 4, ".csv") != 0) continue;
+                const std::string num = name.substr(pattern.size(), name.size() - 4 - pattern.size());
+                if (num.find_first_not_of("0123456789") != std::string::npos) continue;
+                const int rep = atoi(num.c_str());
+                if (rep > max_rep) max_rep = rep;
+            }
+            closedir(dir);
+        }
+        filename = parendir + "/" + pattern + std::to_string(max_rep + 1) + ".csv";
+    }
+    const size_t n = (size_t)g * g;
+    std::ostringstream oss;
+    oss << "a_c,  x,  P(x; tmax), W(x; tmax), O(x; tmax) \n";
+    for (size_t i = 0; i < n; i++) oss << a << "," << i << "," << frame[i] << "," << frame[n + i] << "," << frame[2 * n + i] << "\n";
+    if (FILE *fp = fopen(filename.c_str(), "w")) { fprintf(fp, "%s", oss.str().c_str()); fclose(fp); }
+    else std::cerr << "Error: Could not open file " << filename << std::endl;
+}
+
 void RK4_Wrapper_2D(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/, double a, double c, double gmax, double alpha,
-                    double d, double rW, double W0, double (&D)[Sp], double (&K)[3], double /*a_st*/, double /*a_end*/, double dt,
+                    double d, double rW, double W0, double (&D)[Sp], double (&K)[3], double a_st, double a_end, double dt,
                     double dx, double dP, int r, int g)
 {
     if (t_meas.empty() || r < 1) throw std::invalid_argument("RK4_Wrapper_2D: empty t_meas or r < 1");
@@ -1058,6 +1101,11 @@ void RK4_Wrapper_2D(D2Vec_Double &Rho, vector<double> &t_meas, double /*t_max*/,
                 }
             }
             iter_index += 1;
+            // snapshots of every replicate at t = 0, for 500 <= t <= 2500 and in the last 15 rows (R/:1959)
+            if (write_noise_off_frames && ((t >= 500 && t <= 2500) || t == 0 || (iter_index >= tot_iter - 15 && iter_index <= tot_iter))) {
+                ctx.ck(tm_download(ctx.c, host.data()), "tm_download");
+                for (int j = 0; j < r; j++) save_noise_off_frame(&host[3 * n * j], a, a_st, a_end, t, dt, dx, dP, D[0], D[1], alpha, gmax, j, g);
+            }
             if (t > 1.0) index += 1;                                                                // R/:1987
         }
         pending += 1;

@@ -123,6 +123,10 @@ extern std::function<void(double *frame, int g, int replicate, double a, double 
 // init_randconstframe (R/:272: every cell is c_high with probability 0.015, else c_low, all three fields together) around
 // the analytic steady state (R/:1855-1866), the mask drawn from options().seed instead of mt19937_64(random_device).
 extern std::function<void(double *frame, int g, int replicate, double perc, const double c_high[], const double c_low[])> init_frame_noise_off;
+// The runner's snapshots (R/:1959-1972): every replicate's frame at t = 0, for 500 <= t <= 2500 and in the last 15 measurement rows,
+// "<data_root>/Data/Rietkerk/Frames/Non-Stochastic/<a_st>-<a_end>_dP_<dP>/FRAME_RAND_Basic_P_c_DP_G_<L>_T_<t>_dt_..._R_<j>.csv"; as
+// in the reference the folder is the driver main's to create (no folder: an error line per frame, nothing written).
+extern bool write_noise_off_frames;
 void RK4_Wrapper_2D(D2Vec_Double &Rho, std::vector<double> &t_meas, double t_max, double a, double c, double gmax, double alpha,
                     double d, double rW, double W0, double (&D)[Sp], double (&K)[3], double a_st, double a_end, double dt, double dx,
                     double dP, int r, int g);

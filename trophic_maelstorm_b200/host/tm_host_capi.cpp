@@ -295,8 +295,11 @@ int tmh_riet_det_run(const double *par, int L, int r, const double *init, const 
     D2Vec_Double Rho;
     std::vector<double> tm(t_meas, t_meas + n_tmeas);
     int rc = 0;
+    const bool saved_frames = write_noise_off_frames;
+    write_noise_off_frames = false;        // rows back to the caller: the runner's snapshots are switched off for the call
     try { RK4_Wrapper_2D(Rho, tm, tm.back(), par[0], par[1], par[2], par[3], par[4], par[5], par[6], D, K, par[0], par[0], par[12], par[13], par[14], r, L); }
     catch (const std::exception &e) { fprintf(stderr, "tmh_riet_det_run: %s\n", e.what()); rc = -2; }
+    write_noise_off_frames = saved_frames;
     init_frame_noise_off = saved;
     if (rc) return rc;
     if ((int)Rho.size() > cap) return -1;
