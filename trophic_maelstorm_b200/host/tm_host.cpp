@@ -215,6 +215,7 @@ void dp_runner(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[]
     for (double t = 0; t <= 1; t += dt) { if (ind < tot_iter) acc[ind][0] = t; ind += 1; } // P/:961
     for (size_t i = 0; i < t_meas.size() && ind + (int)i < tot_iter; i++) acc[ind + i][0] = t_meas[i];
     vector<double> surv_rep(t_meas.size() + 1, 0.0);
+    vector<double> surv_rep3(t_meas.size() + 1, 0.0);   // ... as it stands after the third replicate (the PRELIMINARY table below)
 
     // per-replicate series Rho_M[s] = {N_active, <rho>}; a replicate stops logging once extinct (P/:1021)
     vector<vector<double>> RhoM(r, vector<double>(2 * (size_t)tot_iter, 0.0));
@@ -234,7 +235,7 @@ void dp_runner(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[]
                     std::cerr << "RK4 BLEW IT: non-finite density in replicate " << j << " at t=" << plan.t[k] << std::endl;
                     exit(3);
                 }
-                if (plan.window[k] >= 0 && st[j].mean[0] > 0) surv_rep[plan.window[k]] += 1; // P/:1008-1013
+                if (plan.window[k] >= 0 && st[j].mean[0] > 0) { surv_rep[plan.window[k]] += 1; if (j <= 2) surv_rep3[plan.window[k]] += 1; } // P/:1008-1013
                 if (s_of[j] < tot_iter) { RhoM[j][2 * s_of[j]] = (double)st[j].active[0]; RhoM[j][2 * s_of[j] + 1] = st[j].mean[0]; }
                 s_of[j] += 1;
                 if (st[j].active[0] == 0) alive[j] = 0; else any = true;
@@ -253,6 +254,22 @@ void dp_runner(vector<vector<double>> &Rho, vector<double> &t_meas, double Rh0[]
             }
         } else {
             var_mean_incremental_surv_runs(acc, X, tot_iter);
+        }
+        if (j == 2 && write_prelims) {
+            // P/:1100-1128, :2101-2128: the running table after three replicates, default stream precision, t_max = the last bin
+            std::stringstream L, tm, d3, p1, rini, Sm;
+            L << g; tm << t_meas.back(); d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a; rini << j; Sm << std::setprecision(3) << sigma;
+            mkdirs(options().data_root + "/Data/SPDP");
+            std::ofstream out(options().data_root + "/Data/SPDP/PRELIMINARY_P_c_Delta_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a1_" + p1.str()
+                              + "_Sig_" + Sm.str() + "_R_" + rini.str() + ".csv");
+            out << (cubic ? " a , c, L, t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n"
+                          : " a , L, t ,  <<Rho(x; t)>_x>_r, Var[<Rho(t)>_x]_r, # Surviving Runs, # Active Sites, # Surviving Runs Alt \n");
+            for (int i = 0; i < tot_iter; i++) {
+                out << a << ",";
+                if (cubic) out << c << ",";
+                out << g << "," << acc[i][0] << "," << acc[i][1] << "," << acc[i][2] << "," << acc[i][3] << "," << acc[i][4] << ",";
+                if (i < ind) out << j << std::endl; else out << surv_rep3[i - ind] << std::endl;
+            }
         }
     }
     for (int i = 0; i < tot_iter; i++) { // P/:1130-1142, :2139-2149
