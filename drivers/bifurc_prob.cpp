@@ -8,6 +8,7 @@
 int main()
 {
     using namespace std;
+    tm_b200::independent_run_defaults();   // no TM_SEED: a fresh seed and file-name tokens per run, as the reference's random_device gives
     double p_start, p_end, a, b = -2, c = 1, t_event, dt; int div, r, g;
     cout << "Enter desired time-step (dt): "; cin >> dt;
     cout << "Enter time of frame capture (in hr): "; cin >> t_event;

@@ -10,6 +10,7 @@
 int main()
 {
     using namespace std;
+    tm_b200::independent_run_defaults();   // no TM_SEED: a fresh seed and file-name tokens per run, as the reference's random_device gives
     double a_start, a_end, b = -2, c = 1, t_max, D, sigma, dt, dx;
     int div, r, g;
     cout << "Enter desired time-step (dt): "; cin >> dt;

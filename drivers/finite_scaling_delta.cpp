@@ -8,6 +8,7 @@
 int main()
 {
     using namespace std;
+    tm_b200::independent_run_defaults();   // no TM_SEED: a fresh seed and file-name tokens per run, as the reference's random_device gives
     double a_c, b = 1, t_max, t_lim = 0, dt; int div, r, g_st, g_end;
     cout << "Enter desired time-step (dt): "; cin >> dt;
     cout << "Enter maximum duration of simulation (end of time-window) (in hr): "; cin >> t_max;

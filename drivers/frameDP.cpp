@@ -9,6 +9,7 @@
 int main()
 {
     using namespace std;
+    tm_b200::independent_run_defaults();   // no TM_SEED: a fresh seed and file-name tokens per run, as the reference's random_device gives
     double a_start, a_end, b = -2, c = 1, t_max, t_event, dt; int div, r = 5, g;
     cout << "Enter desired time-step (dt): "; cin >> dt;
     cout << "Enter maximum duration of simulation (in hr): "; cin >> t_max;

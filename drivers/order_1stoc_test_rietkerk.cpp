@@ -19,6 +19,7 @@ int main(int argc, char *argv[])
 {
     using namespace std;
     using namespace tm_b200;
+    tm_b200::independent_run_defaults();   // no TM_SEED: a fresh seed and file-name tokens per run, as the reference's random_device gives
     // units: kg, km, hr (Bonachela et al. 2015), :28
     const double c = 10000, gmax = 0.05 * pow(10, -3.0) / 24.0, d = 0.25 / 24.0, alpha = 0.2 / 24.0, W0 = 0.2, rW = 0.2 / 24.0;
     const double dx = 0.1, a_c = 1 / 24.0;

@@ -16,6 +16,7 @@ int main(int argc, char *argv[])
 {
     using namespace std;
     using namespace tm_b200;
+    tm_b200::independent_run_defaults();   // no TM_SEED: a fresh seed and file-name tokens per run, as the reference's random_device gives
     // g, m, day (Bonachela et al. 2015), :12-24
     const double a_note = 0.575;
     const double c = 10, d = 0.25, gmax = 0.05, alpha = 0.2, W0 = 0.2, rW = 0.2;

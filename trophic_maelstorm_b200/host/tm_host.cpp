@@ -12,6 +12,7 @@
 #include <iomanip>
 #include <iostream>
 #include <mutex>
+#include <random>
 #include <sstream>
 #include <stdexcept>
 #include <thread>
@@ -36,6 +37,7 @@ Options &options()
         if (const char *e = getenv("TM_SEED")) x.seed = strtoull(e, nullptr, 0);
         if (const char *e = getenv("TM_STRICT")) x.strict = atoi(e) != 0;
         if (const char *e = getenv("TM_DATA_ROOT")) x.data_root = e;
+        if (const char *e = getenv("TM_FILE_IDS")) x.file_ids = atoi(e) != 0;
         return x;
     }();
     return o;
@@ -671,6 +673,41 @@ void critical_exp_theta_delta(double Rho_0[], int div, double t_max, double a_c,
 std::vector<double> frame_tmeas;
 std::string frame_folder;
 
+// splitmix64 step for the file-name tokens below
+static unsigned long long token_mix(unsigned long long &s)
+{
+    unsigned long long z = (s += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+void independent_run_defaults()
+{
+    Options &o = options();
+    if (getenv("TM_SEED")) return;                                            // a reproducible run: the caller's seed, constant tokens
+    std::random_device rd;
+    o.seed = ((unsigned long long)rd() << 32) ^ (unsigned long long)rd();
+    if (!getenv("TM_FILE_IDS")) o.file_ids = true;
+    std::cout << "TM_SEED=" << o.seed << "   (streams and file-name tokens of this run; set TM_SEED to repeat it)" << std::endl;
+}
+
+std::string jid_token(double a)
+{
+    if (!options().file_ids) return "0";
+    unsigned long long s = stream_seed(options().seed ^ 0x7D1Dull, a);
+    const double u = (double)(token_mix(s) >> 11) * (1.0 / 9007199254740992.0);
+    std::stringstream t; t << (int)std::round(u * 10000);                     // R/:3634
+    return t.str();
+}
+
+std::string id_token(double a, int replicate)
+{
+    if (!options().file_ids) return "0";
+    unsigned long long s = stream_seed(options().seed ^ (0x1D0ull + 0x9E3779B97F4A7C15ull * (unsigned long long)(replicate + 1)), a);
+    const double u = (double)(token_mix(s) >> 11) * (1.0 / 9007199254740992.0);
+    std::stringstream t; t << (u * 1000.0) / 1000.0;                          // R/:4343, default stream precision
+    return t.str();
+}
+
 namespace {
 // splitmix64: the speckle mask of the default initial frame (the reference uses mt19937_64(random_device), R/:420)
 inline unsigned long long splitmix(unsigned long long &s)
@@ -853,7 +890,7 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
         L << g_; tm << t_now; d3 << std::setprecision(3) << dt_; p1 << std::setprecision(5) << a;
         (void)D2;
         const std::string pattern = "/PRELIM_TSERIES_P_c_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
-                                  + "_jID_0_R_";   // R/ header :112, R/:3076 (jID = the thread's random ID there)
+                                  + "_jID_" + jid_token(a) + "_R_";   // R/ header :112, R/:3076 (jID = the thread's random ID there)
         save_prelimframe(tab, dir, pattern, a, a_st_, a_end_, t_now, dt_, dx_, dP_, j, g_, prelimheader, false, false);
     };
 
@@ -924,7 +961,7 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
                     L << g; tm << t; d3 << std::setprecision(3) << dt; p1 << std::setprecision(4) << a; dix << std::setprecision(2) << dx;
                     Dm1 << std::setprecision(3) << D[1];
                     const std::string pattern = "/FRAME_P_c_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
-                                              + "_D1_" + Dm1.str() + "_jID_0_dx_" + dix.str() + "_R_"; // R/:2914
+                                              + "_D1_" + Dm1.str() + "_jID_" + jid_token(a) + "_dx_" + dix.str() + "_R_"; // R/:2914
                     save_frame(fr, fdir + subdir, pattern, a, a_st, a_end, t, dt, dx, dP, j, g);
                 }
             }
@@ -992,7 +1029,7 @@ void riet_batch(vector<D2Vec_Double> &Rho_per_a, const vector<double> &a_values,
             if (write_prelims) { // the running table after every replicate, R/:4327-4349 (jID is a random number there)
                 std::stringstream L, tm, d3, p1, Dm;
                 L << g; tm << t_end; d3 << std::setprecision(3) << dt; p1 << std::setprecision(5) << a; Dm << std::setprecision(4) << D[2];
-                const std::string pattern = "/PRELIM_AGGRAND_P_c_ID_0_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
+                const std::string pattern = "/PRELIM_AGGRAND_P_c_ID_" + id_token(a, j) + "_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str()
                                           + "_D2_" + Dm.str() + "_R_";
                 save_prelimframe(acc, pdir + subdir, pattern, a, a_st, a_end, t, dt, dx, dP, j, g, prelimheader, true);
             }

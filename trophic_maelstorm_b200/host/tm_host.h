@@ -39,8 +39,18 @@ struct Options {
     bool strict = false;                      // reference operation order in the RK4 stages
     bool quiet = true;                        // the reference's progress chatter on stdout
     std::string data_root = "..";             // outputs go to <data_root>/Data/... like the reference's "../Data/..."
+    bool file_ids = false;                    // the two random tokens of the Rietkerk file names ("jID_<n>": thrID R/:3634, an integer in
+                                              // 0..10000 per a-value; "_ID_<x>_": R/:4343, a real in [0,1) per replicate) drawn from
+                                              // (seed, a, replicate) instead of the constant 0 (env TM_FILE_IDS=1)
 };
-Options &options(); // process-wide; env TM_DEVICE, TM_SEED, TM_STRICT, TM_DATA_ROOT override the defaults
+Options &options(); // process-wide; env TM_DEVICE, TM_SEED, TM_STRICT, TM_DATA_ROOT, TM_FILE_IDS override the defaults
+// What a driver main calls first.  The reference seeds every replicate from std::random_device: two runs of a program are independent and
+// -- through the random tokens in their file names -- leave their frames and tables side by side in the same folders.  Without TM_SEED in
+// the environment this does the same: options().seed from std::random_device (printed, so that the run can be repeated with TM_SEED=...)
+// and file_ids on.  With TM_SEED set the run is reproducible: that seed, and the constant tokens unless TM_FILE_IDS=1.
+void independent_run_defaults();
+std::string jid_token(double a);              // "0", or the a-value's thrID when options().file_ids
+std::string id_token(double a, int replicate); // "0", or the replicate's ID
 
 // The Philox key a runner hands to the device for control parameter `a`: options().seed mixed with the bit pattern of a.
 // The reference seeds every replicate of every a-value from std::random_device (P/:973, R/:3511), so the a-values of a

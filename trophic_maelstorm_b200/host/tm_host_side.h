@@ -7,7 +7,8 @@
 //   frames()         save_framefileswrapper (R/:2886-2925): FRAME_* of all fields and GAMMA_* of the perception fields
 //   end_replicate()  the running table so far as PRELIM_AGGRAND_* (R/:4327-4349)
 // File names, headers and number formats are the reference's (save_frame R/:2836, save_prelimframe R/:2720: default 6-digit precision);
-// its two random file-name tokens (thrID -> "jID", R/:3634; the per-replicate ID, R/:4343) are the constant 0, as in the SPB = 1 layer.
+// its two random file-name tokens (thrID -> "jID", R/:3634; the per-replicate ID, R/:4343) come from jid_token() / id_token() (tm_host.h): the
+// constant 0 in a reproducible run (TM_SEED set), drawn from the run's seed otherwise -- as in the SPB = 1 layer.
 // Also here: Stepper, the seam between a runner's bookkeeping and the device, and run_replicates(), the replicate / time loop both
 // multi-species runners share (R/:3501-4372).  The product's Stepper is the device context of tm_consumer.h / tm_consumer3.h; the CPU
 // tests hand run_replicates() a Stepper of their own (test_stepper in tm_host_2sp.h / tm_host_3sp.h) to pin the bookkeeping and the
@@ -83,7 +84,7 @@ public:
         L << c_.g; tm << t; d3 << std::setprecision(3) << c_.dt; p1 << std::setprecision(4) << c_.a; dix << std::setprecision(2) << c_.dx;
         Dm1 << std::setprecision(3) << c_.D1;
         const std::string dir = c_.frame_folder + run_tag();
-        const std::string tail = L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str() + "_D1_" + Dm1.str() + "_jID_0_dx_" + dix.str() + "_R_";
+        const std::string tail = L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str() + "_D1_" + Dm1.str() + "_jID_" + jid_token(c_.a) + "_dx_" + dix.str() + "_R_";
         std::vector<std::vector<double>> fr(c_.Sp, std::vector<double>(n)), gm(c_.SpB, std::vector<double>(n, 0.0));
         for (int s = 0; s < c_.Sp; s++) std::copy(frame + s * n, frame + (s + 1) * n, fr[s].begin());
         for (int s = 1; s < c_.SpB; s++) std::copy(gamma + (s - 1) * n, gamma + s * n, gm[s].begin());
@@ -97,7 +98,7 @@ public:
         L << c_.g; tm << c_.t_max; d3 << std::setprecision(3) << c_.dt; p1 << std::setprecision(5) << c_.a; Dm << std::setprecision(4) << c_.D2;
         std::string dir = c_.prelim_folder + run_tag();
         if (c_.Gstar == -1 && c_.Vstar != -1) dir += "/TimeSeries";              // R/:4337: the reference's own slip, kept
-        const std::string pattern = "/PRELIM_AGGRAND_P_c_ID_0_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str() + "_D2_" + Dm.str() + "_R_";
+        const std::string pattern = "/PRELIM_AGGRAND_P_c_ID_" + id_token(c_.a, j) + "_DP_G_" + L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str() + "_D2_" + Dm.str() + "_R_";
         save_prelimframe(rho_rep_avg_var, dir, pattern, c_.a, c_.a_st, c_.a_end, c_.t_max, c_.dt, c_.dx, c_.dP, j, c_.g, c_.prelimheader, true);
     }
 
@@ -137,7 +138,7 @@ private:
         std::stringstream L, tm, d3, p1;
         L << c_.g; tm << t; d3 << std::setprecision(3) << c_.dt; p1 << std::setprecision(5) << c_.a;
         const std::string dir = c_.prelim_folder + run_tag() + "/TimeSeries";
-        const std::string tail = L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str() + "_jID_0_R_";
+        const std::string tail = L.str() + "_T_" + tm.str() + "_dt_" + d3.str() + "_a_" + p1.str() + "_jID_" + jid_token(c_.a) + "_R_";
         save_prelimframe(tab, dir, "/PRELIM_TSERIES_P_c_DP_G_" + tail, c_.a, c_.a_st, c_.a_end, t, c_.dt, c_.dx, c_.dP, j, c_.g, c_.prelimheader, false, false);
         save_prelimframe(mov, dir, "/PRELIM_MOVSERIES_P_c_DP_G_" + tail, c_.a, c_.a_st, c_.a_end, t, c_.dt, c_.dx, c_.dP, j, c_.g, c_.movmheader, false, false);
     }
